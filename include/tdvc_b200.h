@@ -1,0 +1,170 @@
+/* tdvc_b200 — C-ABI of the B200-native (sm_100a) kernels behind TDVC's P-frame coding forward pass.
+ *
+ * Drop-in boundary:
+ *   b2  tdvc_dcn_v2_forward      replaces the reference's only native op,
+ *                                `_ext.dcn_v2_forward` (reference main/utils/dcnv2/src/vision.cpp:5,
+ *                                src/dcn_v2.h:9-46, src/cuda/dcn_v2_cuda.cu:20-95).
+ *   b3  every other entry point  is one fused stage of `VideoCompressor.forward`
+ *                                (reference main/model/pnet.py:26-83); each comment cites the
+ *                                reference lines it replaces.
+ * Conventions: plain pointers and sizes, no torch types. All pointers are DEVICE pointers unless a name
+ * ends in `_host`. No allocation, no host synchronisation, no global mutable state inside: the caller
+ * owns every buffer (workspace sizes are spelled out per call) and passes the CUDA stream (a
+ * `cudaStream_t` cast to void*), so calls are re-entrant and thread-safe (nn.DataParallel replicas).
+ * Return value: 0 on success, a negative TDVC_E* code otherwise; tdvc_last_error() gives the text.
+ * Activations are fp32, channels-last (NHWC): element (n,y,x,c) at ((n*H + y)*W + x)*ld + c, where `ld`
+ * (floats per pixel) may exceed the channel count (views into wider tensors).
+ */
+#ifndef TDVC_B200_H
+#define TDVC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDVC_OK 0
+#define TDVC_EINVAL (-1)   /* bad argument (shape / alignment / unsupported configuration) */
+#define TDVC_ECUDA (-2)    /* CUDA launch error */
+
+#define TDVC_ACT_NONE 0
+#define TDVC_ACT_RELU 1
+#define TDVC_ACT_LRELU 2   /* slope in `slope` */
+#define TDVC_ACT_CLAMP01 3
+#define TDVC_POST_NONE 0
+#define TDVC_POST_GDN 1    /* v = mul * rsqrt(v)   (compressai GDN,  SURVEY App. A) */
+#define TDVC_POST_IGDN 2   /* v = mul * sqrt(v)    (compressai IGDN) */
+
+int tdvc_version(void);
+const char* tdvc_last_error(void);
+
+/* ---- generic 2-D convolution, implicit GEMM over NHWC (every nn.Conv2d / Conv3d(1,3,3) /
+ * 1x1 / MaskedConv2d / GDN channel mix of the hot path; reference pnet.py passim, utils.py:43-56,
+ * flownet.py:187-227; compressai layers per SURVEY App. A).
+ * Input = channel concatenation of up to 4 sources (replaces torch.cat/stack, pnet.py:148,156,181,257,259,288).
+ * v = bias + sum w*x ; post (GDN/IGDN with `mul`) ; act ; + res1 ; + res2 ; store (optionally pixel-shuffled x2).
+ * weight layout: [kh*kw][cin_pad][cout_pad] fp32, zero padded; for shuffle==2 the output-channel order is
+ * permuted on the host to co' = (dy*2+dx)*(cout/4) + c (nn.PixelShuffle folded into the store).
+ * Constraints: src_c[i] % 4 == 0, src_ld[i] % 4 == 0, 16-byte aligned sources, cin_pad % 8 == 0,
+ * cout_pad % 16 == 0.  `impl`: 0 = auto, 1 = SIMT fp32 FFMA kernel, 2 = tcgen05 tensor-core kernel
+ * (3xBF16 split, fp32 accumulate in TMEM; needs weight_bf16).                                       */
+typedef struct {
+  const float* src[4];
+  int32_t src_c[4];
+  int32_t src_ld[4];
+  int32_t n_src;
+  int32_t N, H, W;          /* input size */
+  int32_t Ho, Wo;           /* output size (before pixel shuffle) */
+  const float* weight;
+  const float* bias;        /* [cout_pad] or NULL */
+  int32_t cin, cin_pad, cout, cout_pad;
+  int32_t kh, kw, stride, pad;
+  int32_t in_square;        /* 1: x -> x*x on load (GDN) */
+  int32_t act;
+  float slope;
+  int32_t post;
+  const float* mul; int32_t mul_ld;
+  const float* res1; int32_t res1_ld;
+  const float* res2; int32_t res2_ld;
+  float* out; int32_t out_ld;
+  int32_t shuffle;          /* 0 or 2 */
+  int32_t impl;
+  const void* weight_bf16;  /* tcgen05 path: [kh*kw][2 (hi,lo)][cout_pad][cin_pad] bf16, or NULL */
+  float* chan_sum;          /* optional [N][gridDim-dependent] — reserved for fused SE partial sums */
+} TdvcConvParams;
+int tdvc_conv2d(const TdvcConvParams* p, void* stream);
+
+/* ---- DCNv2 forward, the reference's `_ext.dcn_v2_forward` (dcn_v2.h:9-46): contiguous NCHW fp32,
+ * offset (N, 2*dg*kh*kw, H, W) ordered [g][tap][dy,dx], mask (N, dg*kh*kw, H, W), weight (O, C, kh, kw),
+ * bias (O).  Only the configuration TDVC uses is implemented: 3x3, stride 1, pad 1, dilation 1; anything
+ * else returns TDVC_EINVAL (the reference raises through AT_ASSERTM, dcn_v2_cuda.cu:38-62).
+ * workspace: at least tdvc_dcn_v2_workspace_bytes(N,C,O,H,W,dg) bytes.  No im2col `columns` tensor is
+ * materialised (reference dcn_v2_cuda.cu:68, 4.5 GB at 1920x1024).                                     */
+size_t tdvc_dcn_v2_workspace_bytes(int N, int C, int O, int H, int W, int dg);
+int tdvc_dcn_v2_forward(const float* input, const float* weight, const float* bias, const float* offset,
+                        const float* mask, float* output, int N, int C, int O, int H, int W,
+                        int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused channels-last form used inside the P-frame graph (reference dcn_v2_amp.py:219-234 + :67-69 +
+ * pnet.py:180): offsets / mask read straight from the 27*dg-channel conv_offset_mask output, sigmoid,
+ * bilinear gather, 9*C -> O contraction, bias, optional fp16 rounding (`round_fp16`, the reference's
+ * `.half()`), optional LeakyReLU evaluated on the fp16 value.  weight_packed: [C*9][O_pad] fp32 with
+ * row j = c*9 + tap (O_pad = O rounded up to 64).                                                      */
+typedef struct {
+  const float* input; int32_t in_ld;      /* (N,H,W,C) */
+  const float* offset; int32_t off_ld;    /* channel g*18 + 2*tap (+1)  */
+  const float* mask; int32_t mask_ld;     /* channel g*9 + tap */
+  int32_t mask_is_logit;                  /* 1: apply sigmoid */
+  const float* weight_packed; const float* bias;
+  float* out; int32_t out_ld;
+  int32_t N, H, W, C, O, O_pad, dg;
+  int32_t round_fp16;
+  int32_t act; float slope;
+  int32_t impl;                           /* 0 = auto, 1 = SIMT fp32 contraction, 2 = tcgen05 (3xBF16 split) */
+  const void* weight_bf16;                /* tcgen05 path: packed hi/lo bf16 weights (see conv_tc.cu), or NULL */
+} TdvcDcnParams;
+int tdvc_dcn_nhwc(const TdvcDcnParams* p, void* stream);
+
+/* ---- layout ---- */
+int tdvc_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int dst_ld, void* stream); /* pads c>=C with 0 */
+int tdvc_nhwc_to_nchw(const float* src, int src_ld, float* dst, int N, int C, int H, int W, void* stream);
+
+/* ---- SPyNet pieces (reference flownet.py:82-140) ----
+ * avgpool2x2: F.avg_pool2d(2,2) (:102-114).
+ * spynet_prep: flow_up = 2 * bilinear_x2(flow_prev, align_corners=True) (:124-128) [zeros if flow_prev NULL];
+ *   warped = grid_sample(supp, border, align_corners=True) with the reference's normalise round trip (:8-48);
+ *   out8 = [ref(3), warped(3), flow_up(2)] (:131-138).  Images are NHWC with ld 4 (3 channels + 0 pad). */
+int tdvc_avgpool2x2(const float* src, float* dst, int N, int H, int W, int C, void* stream);
+int tdvc_spynet_prep(const float* ref4, const float* supp4, const float* flow_prev, float* out8,
+                     int N, int h, int w, void* stream);
+/* nn.Upsample(x2, bilinear, align_corners=False) on NHWC (reference pnet.py:117,159) */
+int tdvc_upsample2x(const float* src, float* dst, int N, int H, int W, int C, void* stream);
+/* offset + flow.repeat(1, C/2, 1, 1)  (reference pnet.py:163) */
+int tdvc_add_flow_tiled(const float* offset, const float* flow2, float* out, int N, int H, int W, int C, void* stream);
+
+/* ---- element-wise ---- */
+int tdvc_axpby(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, void* stream);
+/* out[t] = lrelu(x[t] + tmp) for t < T (Bottleneck3D temporal broadcast add, reference pnet.py:313-314) */
+int tdvc_bcast_add_lrelu(const float* x, const float* tmp, float* out, int T, int64_t n_per_t, float slope, void* stream);
+int tdvc_round_half_even(const float* x, float* out, int64_t n, void* stream);
+
+/* ---- squeeze-excitation (reference inflate.py:159-208): two launches.
+ * se_partial_sums: partial[b][n][c] = sum over a slab of pixels (deterministic two-stage mean).
+ * se_apply: s = sigmoid(W2 relu(W1 mean + b1) + b2) recomputed per block; out = act(x*s) (+ res).
+ * w1: [Cr][C], w2: [C][Cr] (the 1x1 conv weights as stored). nblk <= 1024.                          */
+int tdvc_se_partial_sums(const float* x, int ld, int N, int64_t HW, int C, float* partial, int nblk, void* stream);
+int tdvc_se_apply(const float* x, int ld, const float* partial, int nblk, const float* w1, const float* b1,
+                  const float* w2, const float* b2, int N, int64_t HW, int C, int Cr, int act, float slope,
+                  const float* res, int res_ld, float* out, int out_ld, void* stream);
+
+/* ---- entropy models -> bits (compressai EntropyBottleneck / GaussianConditional forward in eval mode,
+ * SURVEY App. A; reductions of reference pnet.py:38-43,62-67).  `acc` is a device double: += sum ln(p).
+ * eb_bits: z NHWC (ld=C); per-channel MLP params already softplus'ed / tanh'ed on the host side:
+ *   mats: [C][33] = M0(3x1) M1(3x3) M2(3x3) M3(3x3) M4(1x3); biases: [C][13]; factors: [C][12]; medians [C].
+ *   writes z_hat = round(z - med) + med.
+ * gc_bits: y NHWC (ld=C), params NHWC with scales at channel c and means at channel C + c (ld = params_ld).   */
+int tdvc_eb_bits(const float* z, float* z_hat, const float* mats, const float* biases, const float* factors,
+                 const float* medians, int64_t npix, int C, double* acc, void* stream);
+int tdvc_gc_bits(const float* y, const float* params, int params_ld, int64_t npix, int C, double* acc, void* stream);
+
+/* ---- reference-based in-loop filter pieces (reference pnet.py:213-257) ----
+ * avgpool_scale: nn.AvgPool2d(scale) -> (N, H/scale, W/scale, C)                         (:219-226)
+ * ff_descriptors: unfold(3, pad 3, stride 3) + F.normalize -> desc (N, P, C*9), feature c*9 + ky*3 + kx;
+ *   PH = (ph + 3)/3 + 1 ... as F.unfold computes; transpose irrelevant                   (:230-236)
+ * ff_match: ind[n][q] = first argmax_r <q, r>                                             (:235-238)
+ * ff_gather: block placement of f_ref by ind (unfold/gather/fold, :247-254), cor = cosine similarity over
+ *   channels (:255), writes a = f_in*cor, b = gathered*cor (the two halves of cat(...)*cor, :257);
+ *   optional debug outputs gathered / cor may be NULL.                                                  */
+int tdvc_avgpool_scale(const float* x, int ld, float* out, int N, int H, int W, int C, int scale, void* stream);
+int tdvc_ff_descriptors(const float* pooled, float* desc, int N, int ph, int pw, int C, void* stream);
+int tdvc_ff_match(const float* desc_q, const float* desc_r, int32_t* ind, float* sim_or_null, int N, int P, int D, void* stream);
+int tdvc_ff_gather(const float* f_in, const float* f_ref, const int32_t* ind, float* out_a, float* out_b,
+                   float* gathered_or_null, float* cor_or_null, int N, int H, int W, int C, int scale, void* stream);
+
+/* ---- on-device metrics for the GOP driver (reference tools/predict.py:86-90): acc[0] += sum (a-b)^2 */
+int tdvc_sq_err_sum(const float* a, const float* b, int64_t n, double* acc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

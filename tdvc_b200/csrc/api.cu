@@ -1,0 +1,36 @@
+// C-ABI plumbing: error text, version, conv dispatch.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace tdvc {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int conv2d_validate(const TdvcConvParams* p);
+int conv2d_simt(const TdvcConvParams& p, cudaStream_t st);
+int conv2d_tc_supported(const TdvcConvParams& p);
+int conv2d_tc(const TdvcConvParams& p, cudaStream_t st);
+}  // namespace tdvc
+
+extern "C" int tdvc_version(void) { return 100; }
+extern "C" const char* tdvc_last_error(void) { return tdvc::g_err; }
+
+extern "C" int tdvc_conv2d(const TdvcConvParams* p, void* stream) {
+  int rc = tdvc::conv2d_validate(p);
+  if (rc != TDVC_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p->impl == 2) {
+    if (!tdvc::conv2d_tc_supported(*p)) {
+      tdvc::set_error("conv2d: impl=2 (tcgen05) does not support this shape");
+      return TDVC_EINVAL;
+    }
+    return tdvc::conv2d_tc(*p, st);
+  }
+  if (p->impl == 0 && tdvc::conv2d_tc_supported(*p)) return tdvc::conv2d_tc(*p, st);
+  return tdvc::conv2d_simt(*p, st);
+}

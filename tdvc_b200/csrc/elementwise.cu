@@ -1,0 +1,272 @@
+// Memory-bound glue kernels: layout changes, fused element-wise steps, squeeze-excitation, metrics.
+// All are grid-stride, float4-vectorised where alignment allows, sized as multiples of the SM count.
+#include "common.cuh"
+
+namespace tdvc {
+
+// ------------------------------------------------------------------ layout
+// src [N][C][HW]  ->  dst [N][HW][ld]   (32x32 smem tile transpose, +1 padding against bank conflicts)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t HW, int ld) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float* s = src + (int64_t)n * C * HW;
+  float* d = dst + (int64_t)n * HW * ld;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? s[(int64_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t p = p0 + i;
+    const int c = c0 + threadIdx.x;
+    if (p < HW && c < ld) d[p * ld + c] = tile[threadIdx.x][i];  // c in [C, ld) gets the zero fill
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, int C, int64_t HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float* s = src + (int64_t)n * HW * ld;
+  float* d = dst + (int64_t)n * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t p = p0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? s[p * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t p = p0 + threadIdx.x;
+    if (c < C && p < HW) d[(int64_t)c * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------ element-wise
+__global__ void axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                             int64_t n, float alpha, float beta, int vec) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = t; i < n4; i += stride) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i);
+      const float4 y = __ldg(reinterpret_cast<const float4*>(b) + i);
+      float4 r;
+      r.x = alpha * x.x + beta * y.x; r.y = alpha * x.y + beta * y.y;
+      r.z = alpha * x.z + beta * y.z; r.w = alpha * x.w + beta * y.w;
+      reinterpret_cast<float4*>(out)[i] = r;
+    }
+    for (int64_t i = (n4 << 2) + t; i < n; i += stride) out[i] = alpha * a[i] + beta * b[i];
+  } else {
+    for (int64_t i = t; i < n; i += stride) out[i] = alpha * a[i] + beta * b[i];
+  }
+}
+
+__global__ void bcast_add_lrelu_kernel(const float* __restrict__ x, const float* __restrict__ tmp, float* __restrict__ out,
+                                       int T, int64_t n4, float slope) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(tmp) + i);
+    for (int t = 0; t < T; ++t) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x) + (int64_t)t * n4 + i);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+      v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+      reinterpret_cast<float4*>(out)[(int64_t)t * n4 + i] = v;
+    }
+  }
+}
+
+__global__ void round_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = rintf(x[i]);
+}
+
+__global__ void sq_err_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, double* acc) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float d = a[i] - b[i];
+    s += (double)d * d;
+  }
+  s = warp_sum_d(s);
+  __shared__ double sh[32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    s = warp_sum_d(s);
+    if (threadIdx.x == 0) atomicAdd(acc, s);
+  }
+}
+
+// ------------------------------------------------------------------ squeeze-excitation
+// partial[b][n][c] = sum over pixel slab b of x[n][p][c].  256 threads: C/4 float4 lanes x (1024/C) pixel lanes.
+__global__ void se_partial_kernel(const float* __restrict__ x, int ld, int64_t HW, int C, float* __restrict__ partial) {
+  extern __shared__ float4 sh4[];
+  const int lanes_c = C >> 2;
+  const int lanes_p = blockDim.x / lanes_c;
+  const int c4 = threadIdx.x % lanes_c;
+  const int pl = threadIdx.x / lanes_c;
+  const int n = blockIdx.y, b = blockIdx.x, nblk = gridDim.x;
+  const int64_t chunk = (HW + nblk - 1) / nblk;
+  const int64_t p0 = (int64_t)b * chunk;
+  const int64_t p1 = p0 + chunk < HW ? p0 + chunk : HW;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pl < lanes_p) {
+    const float* base = x + (int64_t)n * HW * ld + c4 * 4;
+    for (int64_t p = p0 + pl; p < p1; p += lanes_p) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + p * ld));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  sh4[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < lanes_c) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < lanes_p; ++q) {  // fixed order: deterministic
+      const float4 v = sh4[q * lanes_c + threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    reinterpret_cast<float4*>(partial + ((int64_t)b * gridDim.y + n) * C)[threadIdx.x] = t;
+  }
+}
+
+__global__ void se_apply_kernel(const float* __restrict__ x, int ld, const float* __restrict__ partial, int nblk,
+                                const float* __restrict__ w1, const float* __restrict__ b1,
+                                const float* __restrict__ w2, const float* __restrict__ b2,
+                                int N, int64_t HW, int C, int Cr, int act, float slope,
+                                const float* __restrict__ res, int res_ld, float* __restrict__ out, int out_ld) {
+  extern __shared__ float sh[];
+  float* mean = sh;            // [C]
+  float* hid = sh + C;         // [Cr]
+  float* sc = sh + C + Cr;     // [C]
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < nblk; ++b) s += partial[((int64_t)b * N + n) * C + c];
+    mean[c] = s / (float)HW;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < Cr; r += blockDim.x) {
+    float s = b1[r];
+    for (int c = 0; c < C; ++c) s = fmaf(w1[r * C + c], mean[c], s);
+    hid[r] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = b2[c];
+    for (int r = 0; r < Cr; ++r) s = fmaf(w2[c * Cr + r], hid[r], s);
+    sc[c] = 1.f / (1.f + expf(-s));
+  }
+  __syncthreads();
+  const int lanes_c = C >> 2;
+  const int64_t total = HW * lanes_c;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float* xb = x + (int64_t)n * HW * ld;
+  float* ob = out + (int64_t)n * HW * out_ld;
+  const float* rb = res ? res + (int64_t)n * HW * res_ld : nullptr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t p = i / lanes_c;
+    const int c = (int)(i - p * lanes_c) * 4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(xb + p * ld + c));
+    v.x = apply_act(v.x * sc[c], act, slope); v.y = apply_act(v.y * sc[c + 1], act, slope);
+    v.z = apply_act(v.z * sc[c + 2], act, slope); v.w = apply_act(v.w * sc[c + 3], act, slope);
+    if (rb) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(rb + p * res_ld + c));
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    *reinterpret_cast<float4*>(ob + p * out_ld + c) = v;
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace tdvc
+
+using namespace tdvc;
+
+extern "C" int tdvc_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int dst_ld, void* stream) {
+  TDVC_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && dst_ld >= C, "nchw_to_nhwc: bad args");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid(cdiv(HW, 32), cdiv(dst_ld, 32), N), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW, dst_ld);
+  TDVC_CHECK_LAUNCH("nchw_to_nhwc");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_nhwc_to_nchw(const float* src, int src_ld, float* dst, int N, int C, int H, int W, void* stream) {
+  TDVC_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && src_ld >= C, "nhwc_to_nchw: bad args");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, src_ld, dst, C, HW);
+  TDVC_CHECK_LAUNCH("nhwc_to_nchw");
+  return TDVC_OK;
+}
+
+static int ew_grid(int64_t work_items) {
+  int64_t b = (work_items + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" int tdvc_axpby(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, void* stream) {
+  TDVC_REQUIRE(a && b && out && n >= 0, "axpby: bad args");
+  if (n == 0) return TDVC_OK;
+  const int vec = aligned16(a) && aligned16(b) && aligned16(out);
+  axpby_kernel<<<ew_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, alpha, beta, vec);
+  TDVC_CHECK_LAUNCH("axpby");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_bcast_add_lrelu(const float* x, const float* tmp, float* out, int T, int64_t n_per_t, float slope, void* stream) {
+  TDVC_REQUIRE(x && tmp && out && T > 0 && n_per_t > 0 && n_per_t % 4 == 0, "bcast_add_lrelu: bad args");
+  TDVC_REQUIRE(aligned16(x) && aligned16(tmp) && aligned16(out), "bcast_add_lrelu: alignment");
+  bcast_add_lrelu_kernel<<<ew_grid(n_per_t / 4), 256, 0, (cudaStream_t)stream>>>(x, tmp, out, T, n_per_t / 4, slope);
+  TDVC_CHECK_LAUNCH("bcast_add_lrelu");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_round_half_even(const float* x, float* out, int64_t n, void* stream) {
+  TDVC_REQUIRE(x && out && n >= 0, "round: bad args");
+  if (n == 0) return TDVC_OK;
+  round_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, out, n);
+  TDVC_CHECK_LAUNCH("round");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_sq_err_sum(const float* a, const float* b, int64_t n, double* acc, void* stream) {
+  TDVC_REQUIRE(a && b && acc && n > 0, "sq_err_sum: bad args");
+  sq_err_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(a, b, n, acc);
+  TDVC_CHECK_LAUNCH("sq_err_sum");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_se_partial_sums(const float* x, int ld, int N, int64_t HW, int C, float* partial, int nblk, void* stream) {
+  TDVC_REQUIRE(x && partial && N > 0 && HW > 0 && nblk > 0 && nblk <= 1024, "se_partial_sums: bad args");
+  TDVC_REQUIRE(C % 4 == 0 && C <= 1024 && ld % 4 == 0 && aligned16(x) && aligned16(partial), "se_partial_sums: C/ld/alignment");
+  dim3 grid(nblk, N);
+  se_partial_kernel<<<grid, 256, 256 * sizeof(float4), (cudaStream_t)stream>>>(x, ld, HW, C, partial);
+  TDVC_CHECK_LAUNCH("se_partial_sums");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_se_apply(const float* x, int ld, const float* partial, int nblk, const float* w1, const float* b1,
+                             const float* w2, const float* b2, int N, int64_t HW, int C, int Cr, int act, float slope,
+                             const float* res, int res_ld, float* out, int out_ld, void* stream) {
+  TDVC_REQUIRE(x && partial && w1 && b1 && w2 && b2 && out && N > 0 && HW > 0 && Cr > 0, "se_apply: bad args");
+  TDVC_REQUIRE(C % 4 == 0 && ld % 4 == 0 && out_ld % 4 == 0 && aligned16(x) && aligned16(out), "se_apply: C/ld/alignment");
+  TDVC_REQUIRE(res == nullptr || (res_ld % 4 == 0 && aligned16(res)), "se_apply: res alignment");
+  int gx = ew_grid(HW * (C / 4));
+  if (gx > kNumSMs * 4) gx = kNumSMs * 4;
+  dim3 grid(gx, N);
+  se_apply_kernel<<<grid, 256, (2 * C + Cr) * sizeof(float), (cudaStream_t)stream>>>(
+      x, ld, partial, nblk, w1, b1, w2, b2, N, HW, C, Cr, act, slope, res, res_ld, out, out_ld);
+  TDVC_CHECK_LAUNCH("se_apply");
+  return TDVC_OK;
+}

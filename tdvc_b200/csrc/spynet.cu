@@ -1,0 +1,171 @@
+// SPyNet / OffsetGen memory-bound pieces (reference main/model/flownet.py:8-48,82-140; pnet.py:117,159,163).
+// One thread per output pixel (images are NHWC with ld 4, so a pixel is one float4 load), grid-stride.
+#include "common.cuh"
+
+namespace tdvc {
+
+// F.avg_pool2d(kernel 2, stride 2): raster-order sum then divide (flownet.py:102-114)
+__global__ void avgpool2x2_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int H, int W, int C4) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int64_t total = (int64_t)N * Ho * Wo * C4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C4);
+    int64_t r = i / C4;
+    const int x = (int)(r % Wo); r /= Wo;
+    const int y = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    const float4* s = reinterpret_cast<const float4*>(src) + (((int64_t)n * H + 2 * y) * W + 2 * x) * C4 + c;
+    const float4 a = __ldg(s), b = __ldg(s + C4), d = __ldg(s + (int64_t)W * C4), e = __ldg(s + (int64_t)W * C4 + C4);
+    float4 o;
+    o.x = (((a.x + b.x) + d.x) + e.x) / 4.f; o.y = (((a.y + b.y) + d.y) + e.y) / 4.f;
+    o.z = (((a.z + b.z) + d.z) + e.z) / 4.f; o.w = (((a.w + b.w) + d.w) + e.w) / 4.f;
+    reinterpret_cast<float4*>(dst)[i] = o;
+  }
+}
+
+// One SPyNet level's input assembly.  flow_prev: (N, h/2, w/2, 2) or NULL (level 0 => zero flow).
+__global__ void spynet_prep_kernel(const float* __restrict__ ref4, const float* __restrict__ supp4,
+                                   const float* __restrict__ flow_prev, float* __restrict__ out8, int N, int h, int w) {
+  const int64_t total = (int64_t)N * h * w;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int hp = h >> 1, wp = w >> 1;
+  // align_corners=True source scale, as ATen computes it: (in-1)/(out-1) in fp32
+  const float rh = h > 1 ? (float)(hp - 1) / (float)(h - 1) : 0.f;
+  const float rw = w > 1 ? (float)(wp - 1) / (float)(w - 1) : 0.f;
+  const float wm1 = (float)(w - 1 > 1 ? w - 1 : 1), hm1 = (float)(h - 1 > 1 ? h - 1 : 1);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int x = (int)(i % w);
+    const int64_t r = i / w;
+    const int y = (int)(r % h);
+    const int n = (int)(r / h);
+    float fx = 0.f, fy = 0.f;
+    if (flow_prev != nullptr) {
+      const float h1r = rh * (float)y, w1r = rw * (float)x;
+      const int h1 = (int)h1r, w1 = (int)w1r;
+      const int h1p = h1 < hp - 1 ? 1 : 0, w1p = w1 < wp - 1 ? 1 : 0;
+      const float h1l = h1r - (float)h1, w1l = w1r - (float)w1;
+      const float h0l = 1.f - h1l, w0l = 1.f - w1l;
+      const float2* fp = reinterpret_cast<const float2*>(flow_prev) + ((int64_t)n * hp + h1) * wp + w1;
+      const float2 v00 = __ldg(fp), v01 = __ldg(fp + w1p), v10 = __ldg(fp + (int64_t)h1p * wp), v11 = __ldg(fp + (int64_t)h1p * wp + w1p);
+      fx = (h0l * (w0l * v00.x + w1l * v01.x) + h1l * (w0l * v10.x + w1l * v11.x)) * 2.0f;
+      fy = (h0l * (w0l * v00.y + w1l * v01.y) + h1l * (w0l * v10.y + w1l * v11.y)) * 2.0f;
+    }
+    // flow_warp: normalise to [-1,1] then grid_sample's un-normalise (align_corners=True), border clamp
+    const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)x, fx)), wm1), 1.0f);
+    const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)y, fy)), hm1), 1.0f);
+    float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(w - 1));
+    float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(h - 1));
+    ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
+    iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
+    const float ixf = floorf(ix), iyf = floorf(iy);
+    const int x0 = (int)ixf, y0 = (int)iyf;
+    const float tx = ix - ixf, ty = iy - iyf;  // (ix - ix_nw), (iy - iy_nw)
+    const float ux = (ixf + 1.f) - ix, uy = (iyf + 1.f) - iy;  // (ix_se - ix), (iy_se - iy)
+    const float wnw = ux * uy, wne = tx * uy, wsw = ux * ty, wse = tx * ty;
+    const float4* sp = reinterpret_cast<const float4*>(supp4) + (int64_t)n * h * w;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    {  // x0,y0 are always in range after the clamp
+      const float4 v = __ldg(sp + (int64_t)y0 * w + x0);
+      acc.x += v.x * wnw; acc.y += v.y * wnw; acc.z += v.z * wnw;
+    }
+    if (x0 + 1 < w) {
+      const float4 v = __ldg(sp + (int64_t)y0 * w + x0 + 1);
+      acc.x += v.x * wne; acc.y += v.y * wne; acc.z += v.z * wne;
+    }
+    if (y0 + 1 < h) {
+      const float4 v = __ldg(sp + (int64_t)(y0 + 1) * w + x0);
+      acc.x += v.x * wsw; acc.y += v.y * wsw; acc.z += v.z * wsw;
+    }
+    if (x0 + 1 < w && y0 + 1 < h) {
+      const float4 v = __ldg(sp + (int64_t)(y0 + 1) * w + x0 + 1);
+      acc.x += v.x * wse; acc.y += v.y * wse; acc.z += v.z * wse;
+    }
+    const float4 rf = __ldg(reinterpret_cast<const float4*>(ref4) + i);
+    float4* o = reinterpret_cast<float4*>(out8) + i * 2;
+    o[0] = make_float4(rf.x, rf.y, rf.z, acc.x);
+    o[1] = make_float4(acc.y, acc.z, fx, fy);
+  }
+}
+
+// nn.Upsample(scale_factor=2, bilinear, align_corners=False): src = 0.5*(dst+0.5)-0.5 clamped at 0
+__global__ void upsample2x_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int H, int W, int C4) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int64_t total = (int64_t)N * Ho * Wo * C4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C4);
+    int64_t r = i / C4;
+    const int x = (int)(r % Wo); r /= Wo;
+    const int y = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float sy = 0.5f * ((float)y + 0.5f) - 0.5f, sx = 0.5f * ((float)x + 0.5f) - 0.5f;
+    sy = sy < 0.f ? 0.f : sy; sx = sx < 0.f ? 0.f : sx;
+    const int y1 = (int)sy, x1 = (int)sx;
+    const int yp = y1 < H - 1 ? 1 : 0, xp = x1 < W - 1 ? 1 : 0;
+    const float ly = sy - (float)y1, lx = sx - (float)x1;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float4* s = reinterpret_cast<const float4*>(src) + (((int64_t)n * H + y1) * W + x1) * C4 + c;
+    const float4 a = __ldg(s), b = __ldg(s + (int64_t)xp * C4), d = __ldg(s + (int64_t)yp * W * C4),
+                 e = __ldg(s + ((int64_t)yp * W + xp) * C4);
+    float4 o;
+    o.x = hy * (hx * a.x + lx * b.x) + ly * (hx * d.x + lx * e.x);
+    o.y = hy * (hx * a.y + lx * b.y) + ly * (hx * d.y + lx * e.y);
+    o.z = hy * (hx * a.z + lx * b.z) + ly * (hx * d.z + lx * e.z);
+    o.w = hy * (hx * a.w + lx * b.w) + ly * (hx * d.w + lx * e.w);
+    reinterpret_cast<float4*>(dst)[i] = o;
+  }
+}
+
+__global__ void add_flow_tiled_kernel(const float* __restrict__ offset, const float* __restrict__ flow2,
+                                      float* __restrict__ out, int64_t npix, int C4) {
+  const int64_t total = npix * C4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t p = i / C4;
+    const float2 f = __ldg(reinterpret_cast<const float2*>(flow2) + p);
+    float4 v = __ldg(reinterpret_cast<const float4*>(offset) + i);
+    v.x += f.x; v.y += f.y; v.z += f.x; v.w += f.y;
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+static int grid_for(int64_t items) {
+  int64_t b = (items + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace tdvc
+
+using namespace tdvc;
+
+extern "C" int tdvc_avgpool2x2(const float* src, float* dst, int N, int H, int W, int C, void* stream) {
+  TDVC_REQUIRE(src && dst && N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "avgpool2x2: bad args");
+  avgpool2x2_kernel<<<grid_for((int64_t)N * (H / 2) * (W / 2) * (C / 4)), 256, 0, (cudaStream_t)stream>>>(src, dst, N, H, W, C / 4);
+  TDVC_CHECK_LAUNCH("avgpool2x2");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_spynet_prep(const float* ref4, const float* supp4, const float* flow_prev, float* out8,
+                                int N, int h, int w, void* stream) {
+  TDVC_REQUIRE(ref4 && supp4 && out8 && N > 0 && h >= 2 && w >= 2, "spynet_prep: bad args");
+  TDVC_REQUIRE(flow_prev == nullptr || (h % 2 == 0 && w % 2 == 0), "spynet_prep: odd level size");
+  spynet_prep_kernel<<<grid_for((int64_t)N * h * w), 256, 0, (cudaStream_t)stream>>>(ref4, supp4, flow_prev, out8, N, h, w);
+  TDVC_CHECK_LAUNCH("spynet_prep");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_upsample2x(const float* src, float* dst, int N, int H, int W, int C, void* stream) {
+  TDVC_REQUIRE(src && dst && N > 0 && H > 0 && W > 0 && C % 4 == 0, "upsample2x: bad args");
+  upsample2x_kernel<<<grid_for((int64_t)N * 4 * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(src, dst, N, H, W, C / 4);
+  TDVC_CHECK_LAUNCH("upsample2x");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_add_flow_tiled(const float* offset, const float* flow2, float* out, int N, int H, int W, int C, void* stream) {
+  TDVC_REQUIRE(offset && flow2 && out && N > 0 && H > 0 && W > 0 && C % 4 == 0, "add_flow_tiled: bad args");
+  add_flow_tiled_kernel<<<grid_for((int64_t)N * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(offset, flow2, out, (int64_t)N * H * W, C / 4);
+  TDVC_CHECK_LAUNCH("add_flow_tiled");
+  return TDVC_OK;
+}
