@@ -1,0 +1,117 @@
+"""GOP evaluation driver — mirrors the reference's `validation` loop (reference tools/predict.py:43-100):
+reference-frame buffer with warm-up duplication (:55-60), pad-to-64 / crop (reference
+main/utils/utils.py:59-87), per-frame PSNR = 10 log10(1/MSE) (:87-88) and bpp = bpp_res + bpp_mv (:90).
+
+Differences that do not change results: the per-frame `.cpu()` metric read-backs (one device sync per frame
+per metric in the reference) become on-device accumulations (`tdvc_sq_err_sum`) read once per GOP, and GOPs
+are sharded round-robin over ranks with one all-reduce of seven fp64 sums at the end.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from tdvc_b200 import lib as L
+
+
+def pad(x, p=64):
+    """reference main/utils/utils.py:59-73 (zero padding, centred)."""
+    h, w = x.size(2), x.size(3)
+    H, W = (h + p - 1) // p * p, (w + p - 1) // p * p
+    left, top = (W - w) // 2, (H - h) // 2
+    if H == h and W == w:
+        return x
+    return F.pad(x, (left, W - w - left, top, H - h - top), mode="constant", value=0)
+
+
+def crop(x, size):
+    """reference main/utils/utils.py:76-87."""
+    H, W = x.size(2), x.size(3)
+    h, w = size
+    left, top = (W - w) // 2, (H - h) // 2
+    if H == h and W == w:
+        return x
+    return x[:, :, top:top + h, left:left + w]
+
+
+def reference_window(ref_list):
+    """The 4 reference frames of the next P-frame: [I, x^(t-3), x^(t-2), x^(t-1)] with the reference's
+    warm-up duplication (reference tools/predict.py:55-60).  Returns (N,4,3,H,W)."""
+    n = len(ref_list)
+    if n == 1:
+        sel = [ref_list[0], ref_list[-1], ref_list[-1], ref_list[-1]]
+    elif n == 2:
+        sel = [ref_list[0], ref_list[-2], ref_list[-1], ref_list[-1]]
+    else:
+        sel = [ref_list[0], ref_list[-3], ref_list[-2], ref_list[-1]]
+    return torch.stack(sel, dim=1)
+
+
+def sq_err_sum(a, b, acc, slot):
+    """acc[slot] += sum (a-b)^2 on the device (CUDA kernel; fp64 accumulator)."""
+    a, b = a.contiguous(), b.contiguous()
+    lib = L.load()
+    L.check(lib.tdvc_sq_err_sum(a.data_ptr(), b.data_ptr(), a.numel(), acc.data_ptr() + 8 * slot,
+                                torch.cuda.current_stream(a.device).cuda_stream), "sq_err_sum")
+
+
+def code_gop(net, i_frame, p_frames, enable_amp=False, keep_recon=False):
+    """Code one GOP.  i_frame (1,3,h,w): the (decoded) I-frame; p_frames (T,3,h,w): the frames to code.
+    Returns dict with device tensors `bpp_mv`, `bpp_res` (T,), `sse` (T,) fp64 (sum of squared error over the
+    cropped frame) and `numel`; plus `recon` (list of cropped reconstructions) when keep_recon."""
+    dev = p_frames.device
+    T, _, h, w = p_frames.shape
+    refs = [pad(i_frame, 64)]
+    sse = torch.zeros(T, device=dev, dtype=torch.float64)
+    bmv, bres, recons = [], [], []
+    for i in range(T):
+        x = pad(p_frames[i:i + 1], 64)
+        recon, bpp_res, bpp_mv = net(x, reference_window(refs), enable_amp)
+        refs.append(recon)           # padded, clamped reconstruction feeds the next frame (predict.py:68)
+        if len(refs) > 4:
+            refs = [refs[0]] + refs[-3:]
+        rc = crop(recon, (h, w))
+        sq_err_sum(rc, p_frames[i:i + 1], sse, i)
+        bmv.append(bpp_mv.reshape(-1)[0])
+        bres.append(bpp_res.reshape(-1)[0])
+        if keep_recon:
+            recons.append(rc.clone())
+    out = {"bpp_mv": torch.stack(bmv), "bpp_res": torch.stack(bres), "sse": sse, "numel": 3 * h * w}
+    if keep_recon:
+        out["recon"] = recons
+    return out
+
+
+def gop_stats(res):
+    """Per-GOP sums in the reference's reporting units -> fp64 tensor
+    [sum bpp, sum bpp_mv, sum bpp_res, sum psnr, sum msssim (0: not computed), sum mse, n_frames]."""
+    mse = res["sse"] / res["numel"]
+    psnr = 10.0 * torch.log10(1.0 / mse)
+    bmv, bres = res["bpp_mv"].double(), res["bpp_res"].double()
+    z = torch.zeros((), device=mse.device, dtype=torch.float64)
+    return torch.stack([(bmv + bres).sum(), bmv.sum(), bres.sum(), psnr.sum(), z, mse.sum(),
+                        torch.tensor(float(mse.numel()), device=mse.device, dtype=torch.float64)])
+
+
+def shard_gops(n_gops, rank, world):
+    """GOPs are independent (each restarts from its own I-frame): rank r takes {g : g mod world == r}."""
+    return [g for g in range(n_gops) if g % world == rank]
+
+
+def reduce_stats(stats, group=None):
+    """One all-reduce(sum) of the 7 fp64 sums over ranks (no-op without an initialised process group)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def summarise(stats):
+    s = [float(v) for v in stats.tolist()]
+    n = max(s[6], 1.0)
+    return {"bpp": s[0] / n, "bpp_mv": s[1] / n, "bpp_res": s[2] / n, "psnr": s[3] / n, "mse": s[5] / n,
+            "frames": int(s[6])}
+
+
+def psnr_from_mse(mse):
+    return 10.0 * math.log10(1.0 / mse)

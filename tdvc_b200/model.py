@@ -294,6 +294,14 @@ class Act:
         t = (torch.zeros if zero else torch.empty)((N, H, W, ld), device=device, dtype=torch.float32)
         return Act(t, t.data_ptr(), N, H, W, C, ld)
 
+    @staticmethod
+    def from_nchw(x, ld=None):
+        """NHWC copy (torch permute; tests / plumbing only) of an NCHW tensor, channel-padded with zeros to ld."""
+        N, C, H, W = x.shape
+        a = Act.alloc(N, H, W, C, x.device, ld=ld, zero=True)
+        a.t[..., :C] = x.permute(0, 2, 3, 1)
+        return a
+
     def batch(self, i, n=1):
         return Act(self.t, self.ptr + 4 * i * self.H * self.W * self.ld, n, self.H, self.W, self.C, self.ld)
 
@@ -315,7 +323,7 @@ def _r(x, m):
 
 # =============================================================================== packed weights
 class ConvW:
-    __slots__ = ("w", "b", "cin", "cin_pad", "cout", "cout_pad", "k", "pad", "shuffle", "w_bf16")
+    __slots__ = ("w", "b", "cin", "cin_real", "cin_pad", "cout", "cout_pad", "k", "pad", "shuffle", "w_bf16")
 
 
 def pack_conv(weight, bias, src_layout=None, shuffle=0, pad=None):
@@ -349,6 +357,7 @@ def pack_conv(weight, bias, src_layout=None, shuffle=0, pad=None):
         cw.b = torch.zeros(cout_pad, device=dev, dtype=torch.float32)
         cw.b[:O] = bias.detach().float()
     cw.cin, cw.cin_pad, cw.cout, cw.cout_pad, cw.k = cin, cin_pad, O, cout_pad, k
+    cw.cin_real = I
     cw.pad = k // 2 if pad is None else pad
     cw.shuffle = shuffle
     cw.w_bf16 = None
@@ -502,13 +511,27 @@ class _Plan:
     """Static buffer plan + launch sequence of one P-frame for a fixed (N, H, W) on one device."""
 
     def __init__(self, N, H, W, device):
-        assert H % 64 == 0 and W % 64 == 0, "frames must be padded to a multiple of 64 (reference utils.py:59-87)"
         self.N, self.H, self.W, self.dev = N, H, W, device
         self.lib = L.load()
         self.bufs = {}
         self.acc = torch.zeros(4, device=device, dtype=torch.float64)  # [mv_y, mv_z, res_y, res_z] sum ln p
         self.impl = L.IMPL_AUTO
         self.launches = 0
+        self.prof = None  # list of (label, macs, bytes, start_event, end_event) when instrumented (bench.py)
+
+    def _prof_begin(self):
+        if self.prof is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream(self.dev))
+        return e
+
+    def _prof_end(self, e0, label, macs=0, nbytes=0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(torch.cuda.current_stream(self.dev))
+        self.prof.append((label, macs, nbytes, e0, e1))
 
     # ---------------------------------------------------------------- buffers
     def buf(self, name, N, H, W, C, ld=None, zero=False):
@@ -568,7 +591,13 @@ class _Plan:
         p.shuffle = cw.shuffle
         p.impl = self.impl if impl is None else impl
         p.weight_bf16 = cw.w_bf16.data_ptr() if cw.w_bf16 is not None else None
+        e0 = self._prof_begin()
         L.check(self.lib.tdvc_conv2d(p, self._st()), "conv2d")
+        if e0 is not None:
+            npx = s0.N * p.Ho * p.Wo
+            self._prof_end(e0, f"conv{cw.k}x{cw.k}s{stride}_{cw.cin}to{cw.cout}@{p.Ho}x{p.Wo}",
+                           macs=npx * cw.cout * cw.cin_real * cw.k * cw.k,
+                           nbytes=4 * (s0.N * s0.H * s0.W * cw.cin_real + npx * cw.cout))
         self.launches += 1
         return out
 
@@ -585,8 +614,10 @@ class _Plan:
         self.launches += 2
         return out
 
-    def call(self, fn, *a):
+    def call(self, fn, *a, nbytes=0):
+        e0 = self._prof_begin()
         L.check(getattr(self.lib, fn)(*a, self._st()), fn)
+        self._prof_end(e0, fn[5:], 0, nbytes)
         self.launches += 1
 
     # ---------------------------------------------------------------- blocks
@@ -658,7 +689,8 @@ class _Plan:
         e = self.conv([params, ctx], W[f"{cn}.ep0"], b("ep0", y.H, y.W, c0, ld=_r(c0, 8), zero=True), **lr)
         e = self.conv([e], W[f"{cn}.ep2"], b("ep2", y.H, y.W, c2, ld=_r(c2, 8), zero=True), **lr)
         gp = self.conv([e], W[f"{cn}.ep4"], b("gp", y.H, y.W, 256))
-        self.call("tdvc_gc_bits", y.ptr, gp.ptr, gp.ld, y.N * y.H * y.W, 128, self.acc.data_ptr() + 8 * acc_off)
+        self.call("tdvc_gc_bits", y.ptr, gp.ptr, gp.ld, y.N * y.H * y.W, 128, self.acc.data_ptr() + 8 * acc_off,
+                  nbytes=12 * y.N * y.H * y.W * 128)
         # ---- g_s
         g = self.se(yh, W[f"{cn}.gs0"], b("gs0.o", y.H, y.W))
         g = rb("gs", 1, g)
@@ -716,7 +748,10 @@ class _Plan:
         dp.impl = self.impl
         wb = W.get("mc.dcn.w_bf16")
         dp.weight_bf16 = wb.data_ptr() if wb is not None else None
+        e0 = self._prof_begin()
         L.check(lib.tdvc_dcn_nhwc(dp, self._st()), "dcn_nhwc")
+        # algorithmic bytes: ref 256 + offsets 576 + masks 288 + out 256 B/px
+        self._prof_end(e0, "dcn_nhwc", macs=N * H * Wd * 576 * 64, nbytes=N * H * Wd * 1376)
         self.launches += 1
         o2 = self.conv([dcn_out, ref_f], W["mc.conv"], self.buf("mc.o2", N, H, Wd, 64), **lr1)
         t4 = self.buf("mf.t4", 4 * N, H, Wd, 64)  # per n: [x^(t-3), x^(t-2), x^(t-1) features, prediction1]
@@ -791,7 +826,7 @@ class _Plan:
             h, w = im.H, im.W
             x8 = self.buf(f"spy.in{lvl}", N, h, w, 8)
             self.call("tdvc_spynet_prep", im.batch(0, N).ptr, im.batch(N, N).ptr, flow.ptr if flow is not None else None,
-                      x8.ptr, N, h, w)
+                      x8.ptr, N, h, w, nbytes=N * h * w * 66)  # ref 16 + supp 16 + coarse flow 2 + out 32 B/px
             t = self.conv([x8], W[f"spy.{lvl}.0"], self.buf(f"spy.a{lvl}", N, h, w, 32), act=L.ACT_RELU)
             t = self.conv([t], W[f"spy.{lvl}.1"], self.buf(f"spy.b{lvl}", N, h, w, 64), act=L.ACT_RELU)
             t = self.conv([t], W[f"spy.{lvl}.2"], self.buf(f"spy.c{lvl}", N, h, w, 32), act=L.ACT_RELU)
@@ -860,7 +895,8 @@ class _Plan:
         gth = b("gathered") if taps is not None else None
         cor = self.raw("lf.cor", (N, 1, H, Wd)) if taps is not None else None
         self.call("tdvc_ff_gather", f_in.ptr, f_ref.ptr, ind.data_ptr(), ga.ptr, gb.ptr,
-                  gth.ptr if gth is not None else None, cor.data_ptr() if cor is not None else None, N, H, Wd, 64, scale)
+                  gth.ptr if gth is not None else None, cor.data_ptr() if cor is not None else None, N, H, Wd, 64, scale,
+                  nbytes=N * H * Wd * 1024)  # read f_in + gathered f_ref, write both gated halves
         o = self.conv([ga, gb], W["lf.featfusion"], b("o"), **lr1)
         o = self.conv([o, f_ref], W["lf.featfusion2"], b("o2"))
         o = self.se(o, W["lf.attn"], b("o3"), act=L.ACT_LRELU, slope=0.1)

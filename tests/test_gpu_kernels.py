@@ -1,0 +1,349 @@
+"""GPU tests (-m gpu): each CUDA kernel, called through the C-ABI, against the oracle / plain torch fp32 on the
+CPU for the same seeded inputs.  Tolerances: fp32 kernels 2e-5 relative to the output scale (different
+summation order only); the tcgen05 3xBF16-split convolution 2e-4 relative (|a_lo*b_lo| and bf16 residual
+rounding, ~2^-16 per product); integer / index outputs bit-exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def plan(dev):
+    from tdvc_b200.model import _Plan
+    return _Plan(1, 64, 64, dev)
+
+
+def _conv_case(plan, dev, cin_list, cout, k, stride, H, W, N=1, act=0, slope=0.0, shuffle=0, res=False, impl=1, seed=0,
+               pad=None):
+    from tdvc_b200.model import Act, pack_conv
+    torch.manual_seed(seed)
+    cin = sum(cin_list)
+    conv = torch.nn.Conv2d(cin, cout, k, stride, k // 2 if pad is None else pad)
+    xs = [torch.randn(N, c, H, W) for c in cin_list]
+    want = conv(torch.cat(xs, 1))
+    if act == 1:
+        want = F.relu(want)
+    elif act == 2:
+        want = F.leaky_relu(want, slope)
+    if shuffle == 2:
+        want = F.pixel_shuffle(want, 2)
+    r = torch.randn_like(want) if res else None
+    if res:
+        want = want + r
+    layout = [(c, (c + 3) // 4 * 4) for c in cin_list]
+    cw = pack_conv(conv.weight.to(dev), conv.bias.to(dev), src_layout=layout, shuffle=shuffle, pad=pad)
+    from tdvc_b200 import tc
+    tc.attach_bf16({"w": cw})
+    srcs = [Act.from_nchw(x.to(dev), ld=(x.shape[1] + 3) // 4 * 4) for x in xs]
+    out = Act.alloc(N, want.shape[2], want.shape[3], want.shape[1], dev, ld=(want.shape[1] + 3) // 4 * 4 if want.shape[1] % 4 else None)
+    r1 = Act.from_nchw(r.to(dev)) if res else None
+    plan.conv(srcs, cw, out, stride=stride, act=act, slope=slope, res1=r1, impl=impl)
+    torch.cuda.synchronize()
+    return out.nchw().cpu(), want.detach()
+
+
+CONV_CASES = [
+    # cin_list, cout, k, stride, H, W, kwargs
+    ([64], 64, 3, 1, 24, 40, dict(act=1)),
+    ([64], 64, 3, 1, 17, 23, dict(act=2, slope=0.1, res=True)),       # ragged tile edges
+    ([64, 64], 64, 3, 1, 16, 16, dict()),                              # dual-source (torch.cat replacement)
+    ([3], 64, 3, 1, 20, 20, dict(N=2)),                                # image input, channel pad 3->4
+    ([64], 128, 3, 2, 32, 32, dict(act=2, slope=0.01)),               # stride 2
+    ([64], 128, 1, 2, 32, 32, dict(pad=0)),                            # 1x1 stride-2 skip
+    ([128], 512, 3, 1, 8, 12, dict(shuffle=2, act=2, slope=0.01)),    # subpel conv (PixelShuffle folded in)
+    ([128], 256, 5, 1, 8, 8, dict()),                                  # 5x5 (context model shape)
+    ([8], 32, 7, 1, 16, 16, dict(act=1)),                              # SPyNet 7x7
+    ([16], 2, 7, 1, 16, 16, dict(res=True)),                           # SPyNet last layer, cout 2
+    ([64], 216, 3, 1, 16, 16, dict()),                                 # DCN offset/mask head
+    ([64], 3, 3, 1, 16, 16, dict()),                                   # featdown
+    ([64, 64, 64], 64, 1, 1, 8, 8, dict(pad=0)),                       # temporal (3,1,1) as 1x1 over 3 sources
+    ([192], 768, 3, 1, 4, 4, dict(shuffle=2)),                         # h_s subpel
+]
+
+
+@pytest.mark.parametrize("idx", range(len(CONV_CASES)))
+def test_conv2d_simt_vs_torch(plan, dev, idx):
+    cin_list, cout, k, stride, H, W, kw = CONV_CASES[idx]
+    got, want = _conv_case(plan, dev, cin_list, cout, k, stride, H, W, impl=1, seed=idx, **kw)
+    assert got.shape == want.shape
+    assert (got - want).abs().max() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+def test_conv2d_rejects_bad_arguments(plan, dev):
+    from tdvc_b200 import lib as L
+    p = L.ConvParams()
+    p.n_src = 0
+    assert L.load().tdvc_conv2d(p, None) == -1
+    assert b"n_src" in L.load().tdvc_last_error()
+
+
+def test_gdn_as_fused_conv(plan, dev):
+    """compressai GDN / IGDN = 1x1 conv of x^2 with fused rsqrt/sqrt * x epilogue."""
+    from oracle.compressai_port import GDN
+    from tdvc_b200.model import Act, _reparam, pack_conv
+    torch.manual_seed(3)
+    for inverse in (False, True):
+        g = GDN(128, inverse=inverse)
+        g.beta.data.add_(torch.rand(128) * 0.5)
+        g.gamma.data.add_(torch.rand(128, 128) * 0.02)
+        x = torch.randn(1, 128, 9, 11) * 2
+        idt = torch.randn(1, 128, 9, 11)
+        want = g(x) + idt
+        gd = g.to(dev)
+        cw = pack_conv(_reparam(gd.gamma, gd.gamma_reparam).reshape(128, 128, 1, 1), _reparam(gd.beta, gd.beta_reparam))
+        xa = Act.from_nchw(x.to(dev))
+        out = Act.alloc(1, 9, 11, 128, dev)
+        from tdvc_b200 import lib as L
+        plan.conv([xa], cw, out, in_square=True, post=L.POST_IGDN if inverse else L.POST_GDN, mul=xa,
+                  res1=Act.from_nchw(idt.to(dev)), impl=1)
+        assert (out.nchw().cpu() - want).abs().max() < 2e-5 * want.abs().max()
+
+
+# ------------------------------------------------------------------------------------------------ DCN
+def test_dcn_zero_offset_known_answer(dev):
+    """reference main/utils/dcnv2/testcuda.py:36-71 (check_zero_offset): 2*dcn(x) == x."""
+    from tdvc_b200.ops import dcn_v2_forward
+    torch.manual_seed(0)
+    for (N, C, H, W, dg) in ((2, 64, 13, 19, 8), (2, 8, 7, 9, 2)):  # fast path (8 ch/group) and generic path
+        x = torch.randn(N, C, H, W, device=dev)
+        wgt = torch.zeros(C, C, 3, 3, device=dev)
+        for c in range(C):
+            wgt[c, c, 1, 1] = 1.0
+        off = torch.zeros(N, dg * 18, H, W, device=dev)
+        msk = torch.sigmoid(torch.zeros(N, dg * 9, H, W, device=dev))
+        out = dcn_v2_forward(x, wgt, torch.zeros(C, device=dev), off, msk, 3, 3, 1, 1, 1, 1, 1, 1, dg)
+        assert (2 * out - x).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 64, 21, 30, 8), (2, 16, 24, 9, 7, 2), (1, 6, 4, 5, 6, 3)])
+def test_dcn_forward_vs_oracle(dev, shape):
+    """Random offsets (sigma 3 px, many samples leave the image), random masks: against the oracle restatement of
+    dcn_v2_im2col_cuda.cu:125-195 + dcn_v2_cuda.cu:73-92."""
+    from oracle import dcn_naive
+    from tdvc_b200.ops import dcn_v2_forward
+    N, C, O, H, W, dg = shape
+    torch.manual_seed(5)
+    x = torch.randn(N, C, H, W)
+    wgt = torch.randn(O, C, 3, 3) * 0.1
+    b = torch.randn(O)
+    off = torch.randn(N, dg * 18, H, W) * 3.0
+    msk = torch.rand(N, dg * 9, H, W)
+    want = dcn_naive.dcn_v2_forward(x, wgt, b, off, msk, dg)
+    got = dcn_v2_forward(x.to(dev), wgt.to(dev), b.to(dev), off.to(dev), msk.to(dev), 3, 3, 1, 1, 1, 1, 1, 1, dg).cpu()
+    assert (got - want).abs().max() < 2e-5 * max(1.0, want.abs().max().item())
+
+
+def test_dcn_generic_geometry_vs_torchvision(dev):
+    """Outside the TDVC configuration (stride 2, 5x3 kernel, dilation) the `_ext` drop-in still answers."""
+    import torchvision.ops
+    from tdvc_b200.ops import dcn_v2_forward
+    torch.manual_seed(7)
+    N, C, O, H, W, dg = 1, 4, 6, 11, 12, 2
+    kh, kw, sh, sw, ph, pw, dh, dw = 5, 3, 2, 1, 2, 1, 1, 2
+    Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    x, wgt, b = torch.randn(N, C, H, W), torch.randn(O, C, kh, kw) * 0.2, torch.randn(O)
+    off, msk = torch.randn(N, dg * 2 * kh * kw, Ho, Wo) * 2, torch.rand(N, dg * kh * kw, Ho, Wo)
+    want = torchvision.ops.deform_conv2d(x, off, wgt, b, stride=(sh, sw), padding=(ph, pw), dilation=(dh, dw), mask=msk)
+    got = dcn_v2_forward(x.to(dev), wgt.to(dev), b.to(dev), off.to(dev), msk.to(dev), kh, kw, sh, sw, ph, pw, dh, dw, dg).cpu()
+    assert (got - want).abs().max() < 2e-5 * max(1.0, want.abs().max().item())
+
+
+def test_dcn_errors_like_reference(dev):
+    from tdvc_b200.ops import dcn_v2_forward
+    x = torch.randn(1, 8, 4, 4, device=dev)
+    w = torch.randn(8, 8, 3, 3, device=dev)
+    with pytest.raises(RuntimeError):
+        dcn_v2_forward(x.cpu(), w, torch.zeros(8, device=dev), torch.zeros(1, 18, 4, 4, device=dev),
+                       torch.zeros(1, 9, 4, 4, device=dev), 3, 3, 1, 1, 1, 1, 1, 1, 1)
+    with pytest.raises(RuntimeError):  # kernel size does not match the weight (reference AT_ASSERTM)
+        dcn_v2_forward(x, w, torch.zeros(8, device=dev), torch.zeros(1, 18, 4, 4, device=dev),
+                       torch.zeros(1, 9, 4, 4, device=dev), 5, 5, 1, 1, 1, 1, 1, 1, 1)
+
+
+# ------------------------------------------------------------------------------------------------ SPyNet pieces
+def test_spynet_prep_vs_oracle(plan, dev):
+    """x2 flow upsample (align_corners=True, *2) + border warp with the reference's coordinate round trip
+    (reference flownet.py:8-48,124-138)."""
+    from oracle.model import flow_warp_border
+    from tdvc_b200.model import Act
+    torch.manual_seed(2)
+    for (h, w) in ((8, 10), (32, 60), (64, 64)):
+        ref, supp = torch.rand(1, 3, h, w), torch.rand(1, 3, h, w)
+        flow = torch.randn(1, 2, h // 2, w // 2) * 3
+        up = F.interpolate(flow, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
+        warped = flow_warp_border(supp, up.permute(0, 2, 3, 1))
+        want = torch.cat([ref, warped, up], 1)
+        r4, s4 = Act.from_nchw(ref.to(dev), ld=4), Act.from_nchw(supp.to(dev), ld=4)
+        fl = Act.from_nchw(flow.to(dev))
+        out = Act.alloc(1, h, w, 8, dev)
+        plan.call("tdvc_spynet_prep", r4.ptr, s4.ptr, fl.ptr, out.ptr, 1, h, w)
+        got = out.nchw().cpu()
+        assert (got - want).abs().max() < 3e-6 * max(1.0, want.abs().max().item())
+        plan.call("tdvc_spynet_prep", r4.ptr, s4.ptr, None, out.ptr, 1, h, w)  # level 0: zero flow => identity warp
+        got0 = out.nchw().cpu()
+        assert torch.equal(got0[:, 3:6], supp) and got0[:, 6:].abs().max() == 0
+
+
+def test_pool_upsample_flowadd(plan, dev):
+    from tdvc_b200.model import Act
+    torch.manual_seed(4)
+    x = torch.rand(2, 3, 12, 20)
+    a = Act.from_nchw(x.to(dev), ld=4)
+    o = Act.alloc(2, 6, 10, 3, dev, ld=4)
+    plan.call("tdvc_avgpool2x2", a.ptr, o.ptr, 2, 12, 20, 4)
+    assert (o.nchw().cpu() - F.avg_pool2d(x, 2, 2)).abs().max() < 1e-7
+    y = torch.randn(1, 64, 6, 9)
+    u = Act.alloc(1, 12, 18, 64, dev)
+    plan.call("tdvc_upsample2x", Act.from_nchw(y.to(dev)).ptr, u.ptr, 1, 6, 9, 64)
+    want = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=False)
+    assert (u.nchw().cpu() - want).abs().max() < 1e-6
+    off, fl = torch.randn(1, 64, 5, 7), torch.randn(1, 2, 5, 7)
+    o2 = Act.alloc(1, 5, 7, 64, dev)
+    plan.call("tdvc_add_flow_tiled", Act.from_nchw(off.to(dev)).ptr, Act.from_nchw(fl.to(dev)).ptr, o2.ptr, 1, 5, 7, 64)
+    assert torch.equal(o2.nchw().cpu(), off + fl.repeat(1, 32, 1, 1))
+
+
+def test_layout_roundtrip(plan, dev):
+    x = torch.randn(2, 3, 37, 41, device=dev)
+    nhwc = torch.empty(2, 37, 41, 4, device=dev)
+    back = torch.empty_like(x)
+    plan.call("tdvc_nchw_to_nhwc", x.data_ptr(), nhwc.data_ptr(), 2, 3, 37, 41, 4)
+    plan.call("tdvc_nhwc_to_nchw", nhwc.data_ptr(), 4, back.data_ptr(), 2, 3, 37, 41)
+    assert torch.equal(back, x) and nhwc[..., 3].abs().max() == 0 and torch.equal(nhwc[..., :3], x.permute(0, 2, 3, 1))
+
+
+# ------------------------------------------------------------------------------------------------ SE, element-wise
+def test_se_layer_vs_oracle(plan, dev):
+    from oracle.model import SELayer
+    from tdvc_b200 import lib as L
+    from tdvc_b200.model import Act
+    torch.manual_seed(6)
+    for C, H, W in ((64, 24, 40), (128, 5, 7)):
+        se = SELayer(C)
+        x, r = torch.randn(2, C, H, W), torch.randn(2, C, H, W)
+        want = F.leaky_relu(se(x), 0.1) + r
+        w = (se.conv1.conv.weight.reshape(C // 16, C).to(dev).contiguous(), se.conv1.conv.bias.to(dev),
+             se.conv2.conv.weight.reshape(C, C // 16).to(dev).contiguous(), se.conv2.conv.bias.to(dev))
+        out = Act.alloc(2, H, W, C, dev)
+        plan.se(Act.from_nchw(x.to(dev)), w, out, act=L.ACT_LRELU, slope=0.1, res=Act.from_nchw(r.to(dev)))
+        assert (out.nchw().cpu() - want.detach()).abs().max() < 1e-5
+
+
+def test_elementwise(plan, dev):
+    torch.manual_seed(8)
+    a, b = torch.randn(1003, device=dev), torch.randn(1003, device=dev)
+    o = torch.empty_like(a)
+    plan.call("tdvc_axpby", a.data_ptr(), b.data_ptr(), o.data_ptr(), 1003, 1.0, -1.0)
+    assert torch.equal(o, a - b)
+    y = torch.tensor([0.5, 1.5, 2.5, -0.5, -1.5, 2.4999, -3.5001, 7.0], device=dev)
+    o = torch.empty_like(y)
+    plan.call("tdvc_round_half_even", y.data_ptr(), o.data_ptr(), 8)
+    assert torch.equal(o, torch.round(y)) and o.tolist() == [0.0, 2.0, 2.0, -0.0, -2.0, 2.0, -4.0, 7.0]
+    x, t = torch.randn(4, 640, device=dev), torch.randn(640, device=dev)
+    o = torch.empty_like(x)
+    plan.call("tdvc_bcast_add_lrelu", x.data_ptr(), t.data_ptr(), o.data_ptr(), 4, 640, 0.1)
+    assert torch.equal(o, F.leaky_relu(x + t, 0.1))
+    acc = torch.zeros(1, device=dev, dtype=torch.float64)
+    plan.call("tdvc_sq_err_sum", a.data_ptr(), b.data_ptr(), 1003, acc.data_ptr())
+    assert abs(acc.item() - ((a - b).double() ** 2).sum().item()) < 1e-9 * acc.item()
+
+
+# ------------------------------------------------------------------------------------------------ entropy models
+def test_entropy_bottleneck_bits_vs_oracle(plan, dev):
+    from oracle.compressai_port import EntropyBottleneck
+    torch.manual_seed(9)
+    eb = EntropyBottleneck(128).eval()
+    eb.quantiles.data[:, :, 1].add_(torch.randn(128, 1) * 0.3)
+    for i in range(4):
+        getattr(eb, f"_factor{i}").data.copy_(torch.randn(128, 3, 1) * 0.3)
+    z = torch.randn(1, 128, 6, 10) * 4
+    with torch.no_grad():
+        zh, lik = eb(z)
+    C = 128
+    mats = torch.cat([F.softplus(getattr(eb, f"_matrix{i}").detach()).reshape(C, -1) for i in range(5)], 1).to(dev).contiguous()
+    biases = torch.cat([getattr(eb, f"_bias{i}").detach().reshape(C, -1) for i in range(5)], 1).to(dev).contiguous()
+    factors = torch.cat([torch.tanh(getattr(eb, f"_factor{i}").detach()).reshape(C, -1) for i in range(4)], 1).to(dev).contiguous()
+    med = eb.quantiles.detach()[:, 0, 1].to(dev).contiguous()
+    from tdvc_b200.model import Act
+    za = Act.from_nchw(z.to(dev))
+    zo = Act.alloc(1, 6, 10, 128, dev)
+    acc = torch.zeros(1, device=dev, dtype=torch.float64)
+    plan.call("tdvc_eb_bits", za.ptr, zo.ptr, mats.data_ptr(), biases.data_ptr(), factors.data_ptr(), med.data_ptr(),
+              60, 128, acc.data_ptr())
+    assert torch.equal(zo.nchw().cpu(), zh)  # quantised symbols bit-exact
+    want = torch.log(lik).double().sum().item()
+    assert abs(acc.item() - want) < 1e-4 * abs(want)
+
+
+def test_gaussian_conditional_bits_vs_oracle(plan, dev):
+    from oracle.compressai_port import GaussianConditional
+    from tdvc_b200.model import Act
+    torch.manual_seed(10)
+    gc = GaussianConditional(None).eval()
+    y = torch.randn(1, 128, 7, 9) * 5
+    scales = torch.exp(torch.randn(1, 128, 7, 9) * 1.5) * 0.3  # crosses the 0.11 floor
+    means = torch.randn(1, 128, 7, 9)
+    with torch.no_grad():
+        _, lik = gc(y, scales, means=means)
+    gp = Act.from_nchw(torch.cat([scales, means], 1).to(dev))
+    acc = torch.zeros(1, device=dev, dtype=torch.float64)
+    plan.call("tdvc_gc_bits", Act.from_nchw(y.to(dev)).ptr, gp.ptr, gp.ld, 63, 128, acc.data_ptr())
+    want = torch.log(lik).double().sum().item()
+    assert (scales < 0.11).any() and (lik <= 1e-9).any()  # exercises both bounds
+    assert abs(acc.item() - want) < 1e-4 * abs(want)
+
+
+# ------------------------------------------------------------------------------------------------ in-loop filter pieces
+@pytest.mark.parametrize("hw", [(64, 64), (128, 192), (64, 320)])
+def test_featurefix_match_and_gather_vs_oracle(plan, dev, hw):
+    """avg-pool -> unfold/normalise -> similarity/argmax -> block placement -> cosine gate
+    (reference pnet.py:219-257) against the oracle's unfold/bmm/gather/fold restatement."""
+    from tdvc_b200.model import Act
+    H, W = hw
+    torch.manual_seed(11)
+    f_in, f_ref = torch.randn(1, 64, H, W), torch.randn(1, 64, H, W)
+    scale = int(H / 8)
+    p_in, p_ref = F.avg_pool2d(f_in, scale, scale), F.avg_pool2d(f_ref, scale, scale)
+    q = F.unfold(p_in, 3, padding=3, stride=3).transpose(2, 1)
+    k = F.unfold(p_ref, 3, padding=3, stride=3).transpose(2, 1).reshape(1, -1, 576)
+    sim = torch.bmm(F.normalize(q, dim=2), F.normalize(k.transpose(2, 1), dim=1))
+    ind = sim.max(dim=2)[1]
+    bs = 3 * scale
+    blocks = F.unfold(f_ref, bs, padding=bs, stride=bs).transpose(2, 1).reshape(1, -1, 64 * bs * bs)
+    idx = ind.view(1, 1, -1).expand(-1, 64 * bs * bs, -1).permute(0, 2, 1)
+    picked = torch.gather(blocks, 1, idx).view(1, -1, 64, bs, bs).permute(0, 2, 3, 4, 1).reshape(1, -1, q.size(1))
+    gathered = F.fold(picked, (H, W), bs, padding=bs, stride=bs)
+    cor = torch.cosine_similarity(f_in, gathered).unsqueeze(1)
+
+    fa, fr = Act.from_nchw(f_in.to(dev)), Act.from_nchw(f_ref.to(dev))
+    ph, pw = H // scale, W // scale
+    P = q.size(1)
+    pin, pref = torch.empty(1, ph, pw, 64, device=dev), torch.empty(1, ph, pw, 64, device=dev)
+    plan.call("tdvc_avgpool_scale", fa.ptr, 64, pin.data_ptr(), 1, H, W, 64, scale)
+    plan.call("tdvc_avgpool_scale", fr.ptr, 64, pref.data_ptr(), 1, H, W, 64, scale)
+    assert (pin.permute(0, 3, 1, 2).cpu() - p_in).abs().max() < 1e-6
+    din, dref = torch.empty(1, P, 576, device=dev), torch.empty(1, P, 576, device=dev)
+    plan.call("tdvc_ff_descriptors", pin.data_ptr(), din.data_ptr(), 1, ph, pw, 64)
+    plan.call("tdvc_ff_descriptors", pref.data_ptr(), dref.data_ptr(), 1, ph, pw, 64)
+    gi = torch.empty(1, P, dtype=torch.int32, device=dev)
+    gs = torch.empty(1, P, P, device=dev)
+    plan.call("tdvc_ff_match", din.data_ptr(), dref.data_ptr(), gi.data_ptr(), gs.data_ptr(), 1, P, 576)
+    assert (gs.cpu() - sim).abs().max() < 1e-5
+    assert torch.equal(gi.cpu().long(), ind)  # indices bit-exact (incl. first-index tie-break on all-zero patches)
+    oa, ob = Act.alloc(1, H, W, 64, dev), Act.alloc(1, H, W, 64, dev)
+    og, oc = Act.alloc(1, H, W, 64, dev), torch.empty(1, 1, H, W, device=dev)
+    plan.call("tdvc_ff_gather", fa.ptr, fr.ptr, gi.data_ptr(), oa.ptr, ob.ptr, og.ptr, oc.data_ptr(), 1, H, W, 64, scale)
+    assert torch.equal(og.nchw().cpu(), gathered)  # pure data movement: bit-exact
+    assert (oc.cpu() - cor).abs().max() < 1e-5
+    assert (oa.nchw().cpu() - f_in * cor).abs().max() < 1e-4 and (ob.nchw().cpu() - gathered * cor).abs().max() < 1e-4

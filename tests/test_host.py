@@ -1,0 +1,206 @@
+"""CPU tests (-m "not gpu") of the host logic: C-ABI library loads and exports every symbol the header declares
+(no compute calls), state_dict compatibility with the reference key set, weight packing, GOP driver semantics
+(reference tools/predict.py:51-68), GOP sharding + the 7-sum all-reduce over a world_size-2 gloo group."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "tdvc_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(tdvc_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tdvc_b200 import build, lib as L
+    build.build()
+    lib = L.load()
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/tdvc_b200.h but not exported"
+        assert s in L.SIGNATURES, f"{s} has no ctypes signature"
+    assert lib.tdvc_version() >= 100
+    assert lib.tdvc_dcn_v2_workspace_bytes(1, 64, 64, 64, 64, 8) > 64 * 64 * (64 + 216 + 64) * 4
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors of the two parameter structs must have the C sizes (checked against a tiny C program)."""
+    import ctypes
+    import subprocess
+    import tempfile
+    from tdvc_b200 import lib as L
+    src = '#include <stdio.h>\n#include "tdvc_b200.h"\nint main(){printf("%zu %zu\\n", sizeof(TdvcConvParams), sizeof(TdvcDcnParams));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
+        a, b = subprocess.check_output([os.path.join(d, "s")]).split()
+    assert int(a) == ctypes.sizeof(L.ConvParams) and int(b) == ctypes.sizeof(L.DcnParams)
+
+
+def test_state_dict_matches_reference_key_set(oracle_model):
+    from tdvc_b200.model import VideoCompressor
+    net = VideoCompressor()
+    osd = oracle_model.state_dict()
+    assert list(net.state_dict().keys()) == list(osd.keys())
+    net.load_state_dict(osd, strict=True)
+    oracle_model.load_state_dict(net.state_dict(), strict=True)
+    for k, v in net.state_dict().items():
+        assert v.shape == osd[k].shape and torch.equal(v, osd[k]), k
+
+
+def test_forward_refuses_cpu_and_training():
+    from tdvc_b200.model import VideoCompressor
+    net = VideoCompressor().eval()
+    x, r = torch.zeros(1, 3, 64, 64), torch.zeros(1, 4, 3, 64, 64)
+    with pytest.raises(RuntimeError):
+        net(x, r, False)  # no CPU fallback
+    with pytest.raises(NotImplementedError):
+        net(x, r, False, True)
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(x, r, False)
+
+
+def _emulate_packed_conv(xs, cw, stride=1):
+    """The implicit GEMM the kernel performs, in torch: NHWC sources (stored channel counts), packed weights."""
+    x = torch.cat(xs, dim=-1)  # (N,H,W,cin)
+    N, Hh, Ww, cin = x.shape
+    assert cin == cw.cin
+    xp = F.pad(x, (0, cw.cin_pad - cin, cw.pad, cw.pad, cw.pad, cw.pad))
+    Ho = (Hh + 2 * cw.pad - cw.k) // stride + 1
+    Wo = (Ww + 2 * cw.pad - cw.k) // stride + 1
+    out = torch.zeros(N, Ho, Wo, cw.cout_pad)
+    for ky in range(cw.k):
+        for kx in range(cw.k):
+            patch = xp[:, ky:ky + stride * (Ho - 1) + 1:stride, kx:kx + stride * (Wo - 1) + 1:stride]
+            out += patch @ cw.w[ky * cw.k + kx]
+    if cw.b is not None:
+        out += cw.b
+    out = out[..., :cw.cout]
+    if cw.shuffle == 2:
+        cr = cw.cout // 4
+        o = out.view(N, Ho, Wo, 2, 2, cr).permute(0, 1, 3, 2, 4, 5).reshape(N, 2 * Ho, 2 * Wo, cr)
+        return o
+    return out
+
+
+@pytest.mark.parametrize("case", ["plain", "two_src", "image", "odd_cin", "shuffle", "stride2_1x1"])
+def test_pack_conv_layouts(case):
+    from tdvc_b200.model import pack_conv
+    torch.manual_seed(0)
+    if case == "plain":
+        conv = torch.nn.Conv2d(8, 20, 3, 1, 1)
+        x = torch.randn(1, 8, 6, 7)
+        cw = pack_conv(conv.weight, conv.bias)
+        got = _emulate_packed_conv([x.permute(0, 2, 3, 1)], cw)
+        want = conv(x)
+    elif case == "two_src":
+        conv = torch.nn.Conv2d(16, 8, 3, 1, 1)
+        a, b = torch.randn(1, 8, 5, 5), torch.randn(1, 8, 5, 5)
+        cw = pack_conv(conv.weight, conv.bias, src_layout=[(8, 8), (8, 8)])
+        got = _emulate_packed_conv([a.permute(0, 2, 3, 1), b.permute(0, 2, 3, 1)], cw)
+        want = conv(torch.cat([a, b], 1))
+    elif case == "image":
+        conv = torch.nn.Conv2d(3, 16, 3, 1, 1)
+        x = torch.randn(2, 3, 5, 6)
+        cw = pack_conv(conv.weight, conv.bias, src_layout=[(3, 4)])
+        got = _emulate_packed_conv([F.pad(x.permute(0, 2, 3, 1), (0, 1))], cw)
+        want = conv(x)
+    elif case == "odd_cin":
+        conv = torch.nn.Conv2d(426, 341, 1)
+        x = torch.randn(1, 426, 3, 3)
+        cw = pack_conv(conv.weight, conv.bias, src_layout=[(426, 428)])
+        assert cw.cin == 428 and cw.cin_pad == 432 and cw.cout_pad == 352 and cw.pad == 0
+        got = _emulate_packed_conv([F.pad(x.permute(0, 2, 3, 1), (0, 2))], cw)
+        want = conv(x)
+    elif case == "shuffle":
+        conv = torch.nn.Conv2d(8, 32, 3, 1, 1)
+        x = torch.randn(1, 8, 4, 5)
+        cw = pack_conv(conv.weight, conv.bias, shuffle=2)
+        got = _emulate_packed_conv([x.permute(0, 2, 3, 1)], cw)
+        want = F.pixel_shuffle(conv(x), 2)
+    else:
+        conv = torch.nn.Conv2d(8, 16, 1, 2)
+        x = torch.randn(1, 8, 6, 8)
+        cw = pack_conv(conv.weight, conv.bias, pad=0)
+        got = _emulate_packed_conv([x.permute(0, 2, 3, 1)], cw, stride=2)
+        want = conv(x)
+    assert (got.permute(0, 3, 1, 2) - want).abs().max() < 1e-5
+
+
+def test_reference_window_matches_predict_py():
+    """reference tools/predict.py:55-62 builds torch.stack([...]).transpose(1,0).view(-1,4,3,H,W)."""
+    from tdvc_b200 import gop as G
+    fr = [torch.full((1, 3, 2, 2), float(i)) for i in range(6)]
+    for n in range(1, 6):
+        lst = fr[:n]
+        if n == 1:
+            ref = torch.stack([lst[0], lst[-1], lst[-1], lst[-1]])
+        elif n == 2:
+            ref = torch.stack([lst[0], lst[-2], lst[-1], lst[-1]])
+        else:
+            ref = torch.stack([lst[0], lst[-3], lst[-2], lst[-1]])
+        want = ref.transpose(1, 0).reshape(-1, 4, 3, 2, 2)
+        assert torch.equal(G.reference_window(lst), want)
+
+
+def test_pad_crop_like_reference():
+    from tdvc_b200 import gop as G
+    x = torch.arange(2 * 3 * 70 * 130, dtype=torch.float32).view(2, 3, 70, 130)
+    p = G.pad(x, 64)
+    assert p.shape == (2, 3, 128, 192)
+    assert torch.equal(G.crop(p, (70, 130)), x)
+    assert p[:, :, :29].abs().sum() == 0 and p[:, :, :, :31].abs().sum() == 0  # (128-70)//2 = 29, (192-130)//2 = 31
+    y = torch.zeros(1, 3, 64, 128)
+    assert G.pad(y, 64) is y and G.crop(y, (64, 128)) is y
+
+
+def test_shard_gops_partition():
+    from tdvc_b200 import gop as G
+    for world in (1, 2, 4, 8):
+        parts = [G.shard_gops(96, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(96))
+        assert len({len(p) for p in parts}) == 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from tdvc_b200 import gop as G
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = G.shard_gops(6, rank, world)
+    s = torch.zeros(7, dtype=torch.float64)
+    for g in mine:  # fake per-GOP statistics: bpp = g, 11 frames each
+        s += torch.tensor([11.0 * g, 4.0 * g, 7.0 * g, 11 * 30.0, 0.0, 11 * 1e-3, 11.0], dtype=torch.float64)
+    G.reduce_stats(s)
+    q.put((rank, s.tolist()))
+    dist.destroy_process_group()
+
+
+def test_stats_allreduce_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    want = [11.0 * 15, 4.0 * 15, 7.0 * 15, 6 * 11 * 30.0, 0.0, 6 * 11 * 1e-3, 66.0]
+    for _, s in res:
+        assert all(abs(a - b) < 1e-9 for a, b in zip(s, want))
+    from tdvc_b200 import gop as G
+    summ = G.summarise(torch.tensor(res[0][1], dtype=torch.float64))
+    assert summ["frames"] == 66 and abs(summ["psnr"] - 30.0) < 1e-9 and abs(summ["bpp"] - 2.5) < 1e-9
