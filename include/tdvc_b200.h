@@ -17,6 +17,7 @@
  */
 #ifndef TDVC_B200_H
 #define TDVC_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -72,6 +73,11 @@ typedef struct {
   float* chan_sum;          /* optional [N][gridDim-dependent] — reserved for fused SE partial sums */
 } TdvcConvParams;
 int tdvc_conv2d(const TdvcConvParams* p, void* stream);
+/* tcgen05 path: size of / builder for the bf16 (hi, lo) weight blocks of a convolution, from its fp32 packed
+ * `weight` ([kh*kw][cin_pad][cout_pad]).  Only geometry fields (kh, kw, stride, pad, cin, cin_pad, cout, cout_pad,
+ * post, in_square) and `weight` are read.  bytes == 0: the shape has no tensor-core path (SIMT kernel is used). */
+size_t tdvc_conv2d_bf16_bytes(const TdvcConvParams* p);
+int tdvc_conv2d_pack_bf16(const TdvcConvParams* p, void* out, void* stream);
 
 /* ---- DCNv2 forward, the reference's `_ext.dcn_v2_forward` (dcn_v2.h:9-46): contiguous NCHW fp32,
  * offset (N, 2*dg*kh*kw, H, W) ordered [g][tap][dy,dx], mask (N, dg*kh*kw, H, W), weight (O, C, kh, kw),

@@ -1,8 +1,521 @@
-// placeholder until the tcgen05 kernels land
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM) for the
+// dense KxK stride-1 convolutions of the P-frame graph (reference main/model/pnet.py passim,
+// main/utils/utils.py:43-56, main/model/flownet.py:187-227, compressai blocks of SURVEY.md App. A).
+//
+// Numerics: activations and weights stay fp32 in HBM.  Each operand is split on the fly into two bf16 terms
+// (x = x_hi + x_lo, |x_lo| <= 2^-9 |x|) and the product is evaluated as x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with
+// fp32 accumulation in TMEM ("3xBF16"): relative error per product ~2^-16, i.e. the fp32-class accuracy the
+// parity bar needs (>= 99.9 % identical quantised symbols), at 3 MMA passes.
+//
+// Work decomposition (persistent, one CTA per SM, 320 threads):
+//   work item  = 16x16 output pixels ("super tile" = two 8-wide x 16-tall MMA tiles, M = 128 each) x NT output
+//                channels;  K loop = cin chunks of CK channels ("units") x KS*KS taps x CK/16 MMA k-steps.
+//   warps 4-7  producers: read the (16+KS-1)^2 fp32 halo of one unit from global (float4, coalesced 256 B per
+//              pixel), split into bf16 hi / lo and store it to shared memory in the tcgen05 K-major
+//              "interleaved" (no-swizzle) canonical layout: [channel/8][halo pixel][8 channels] — 8 x-adjacent
+//              pixels form one 8x16 B core matrix, so every tap of the convolution is the SAME buffer read
+//              through a descriptor whose start address is shifted by (ky*HALO_W + kx)*16 B.  No im2col copy.
+//   warp 9     streams pre-packed bf16 weight blocks [2*NT rows = w_hi | w_lo][CK] (one per unit x tap)
+//              with cp.async.bulk (1-D TMA) into a 3-4 stage ring, completion on mbarriers.
+//   warp 8     one elected thread issues, per k-step and MMA tile:
+//                 D[:, 0:2NT] (+)= A_hi (128x16) * [W_hi | W_lo]^T      (N = 2*NT)
+//                 D[:, 0:NT ]  += A_lo (128x16) *  W_hi^T               (N = NT)
+//              and tcgen05.commit's the ring slots back to the producers.
+//   warps 0-3  epilogue: tcgen05.ld the accumulator (lane = pixel), add the hi*hi+lo*hi and hi*lo halves, bias,
+//              activation, up to two residual adds, optional PixelShuffle(2) store; overlaps the next item's MMAs
+//              (two accumulator stages in TMEM: 8*NT columns).
 #include "common.cuh"
+#include <cuda_bf16.h>
+
 namespace tdvc {
-int conv2d_tc_supported(const TdvcConvParams&) { return 0; }
-int conv2d_tc(const TdvcConvParams&, cudaStream_t) { set_error("tcgen05 conv not built"); return TDVC_EINVAL; }
+
+namespace tc {
+
+constexpr int kEpiWarps = 4, kProdWarps = 4;
+constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 320
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kTile = 16;  // super-tile edge (pixels)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle ("interleaved") shared-memory matrix descriptor: 8x16B core matrices, LBO = byte distance
+// between the two K-adjacent core matrices of one MMA (K=16), SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N
+__host__ __device__ constexpr uint32_t instr_desc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <int KS, int CK, int NT>
+struct Cfg {
+  static constexpr int PAD = KS / 2;
+  static constexpr int HALO = kTile + KS - 1;
+  static constexpr int NPIX = HALO * HALO;
+  static constexpr int NPIXP = NPIX | 1;             // odd pitch: conflict-free 8-byte stores
+  static constexpr int NCH8 = CK / 8;
+  static constexpr int A_HALF = NCH8 * NPIXP * 16;   // bytes of the hi (or lo) plane of one unit
+  static constexpr int A_STAGE = 2 * A_HALF;
+  static constexpr int LBO_A = NPIXP * 16, SBO_A = HALO * 16;
+  static constexpr int B_BLOCK = 2 * NT * CK * 2;    // [2*NT rows][CK] bf16
+  static constexpr int LBO_B = 128, SBO_B = NCH8 * 128;
+  static constexpr int KSTEPS = CK / 16;
+  static constexpr int TAPS = KS * KS;
+  static constexpr int NA = 2;
+  static constexpr int NB = (KS == 3) ? 3 : 4;
+  static constexpr int TMEM_COLS = 8 * NT;           // 2 stages x 2 tiles x 2*NT
+  static constexpr int SMEM = NA * A_STAGE + NB * B_BLOCK + 256;
+  static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static_assert(A_STAGE % 128 == 0 || true, "");
+};
+
+struct Item {
+  int n, y0, x0, jt;
+};
+
+__device__ __forceinline__ Item decode_item(int item, int n_jt, int tiles_x, int tiles_y) {
+  Item it;
+  it.jt = item % n_jt;
+  int st = item / n_jt;
+  it.x0 = (st % tiles_x) * kTile;
+  st /= tiles_x;
+  it.y0 = (st % tiles_y) * kTile;
+  it.n = st / tiles_y;
+  return it;
+}
+
+template <int KS, int CK, int NT>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvParams p, int tiles_x, int tiles_y, int n_jt,
+                                                              int n_units, int n_items) {
+  using C = Cfg<KS, CK, NT>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* a_buf = smem;                                  // NA stages of [hi plane | lo plane]
+  uint8_t* b_buf = smem + C::NA * C::A_STAGE;             // NB weight blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_buf + C::NB * C::B_BLOCK);
+  // barrier indices
+  constexpr int A_FULL = 0, A_EMPTY = A_FULL + C::NA, B_FULL = A_EMPTY + C::NA, B_EMPTY = B_FULL + C::NB,
+                ACC_FULL = B_EMPTY + C::NB, ACC_EMPTY = ACC_FULL + 2, NBARS = ACC_EMPTY + 2;
+  static_assert(NBARS * 8 + 8 <= 256, "barrier area");
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::NA; ++i) { mbar_init(bar(A_FULL + i), kProdThreads); mbar_init(bar(A_EMPTY + i), 1); }
+    for (int i = 0; i < C::NB; ++i) { mbar_init(bar(B_FULL + i), 1); mbar_init(bar(B_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(ACC_FULL + i), 1); mbar_init(bar(ACC_EMPTY + i), kEpiWarps * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp < kEpiWarps) {
+    // ===================================================================== epilogue
+    const int m = warp * 32 + lane;          // accumulator row = TMEM lane
+    const int py = m >> 3, px = m & 7;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    int acc_it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
+      const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
+      const int sa = acc_it & 1;
+      mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
+      tc_fence_after();
+      const int y = it.y0 + py;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int x = it.x0 + 8 * t + px;
+        const bool valid = (y < p.Ho) && (x < p.Wo);
+        const uint32_t tcol = lane_addr + (uint32_t)((sa * 2 + t) * 2 * NT);
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t ra[16], rb[16];
+          tmem_ld16(tcol + c0, ra);
+          tmem_ld16(tcol + NT + c0, rb);
+          tmem_ld_wait();
+          const int co0 = it.jt * NT + c0;
+          if (!valid || co0 >= p.cout) continue;
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
+          // output location (PixelShuffle(2) folded into the store: co' = q*(cout/4) + c)
+          int64_t opix;
+          int oc;
+          if (p.shuffle == 2) {
+            const int cr = p.cout >> 2;
+            const int q = co0 / cr;
+            oc = co0 - q * cr;
+            opix = ((int64_t)it.n * (2 * p.Ho) + (2 * y + (q >> 1))) * (2 * p.Wo) + (2 * x + (q & 1));
+          } else {
+            oc = co0;
+            opix = ((int64_t)it.n * p.Ho + y) * p.Wo + x;
+          }
+          const bool vec = (co0 + 16 <= p.cout) && ((p.out_ld & 3) == 0) && (!p.res1 || (p.res1_ld & 3) == 0) &&
+                           (!p.res2 || (p.res2_ld & 3) == 0);
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (p.bias) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
+                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+              }
+              o.x = apply_act(o.x, p.act, p.slope); o.y = apply_act(o.y, p.act, p.slope);
+              o.z = apply_act(o.z, p.act, p.slope); o.w = apply_act(o.w, p.act, p.slope);
+              if (p.res1) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res1 + opix * p.res1_ld + oc + j));
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+              if (p.res2) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res2 + opix * p.res2_ld + oc + j));
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+              *reinterpret_cast<float4*>(p.out + opix * p.out_ld + oc + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (co0 + j >= p.cout) continue;
+              float o = v[j] + (p.bias ? __ldg(p.bias + co0 + j) : 0.f);
+              o = apply_act(o, p.act, p.slope);
+              int64_t op2 = opix;
+              int oc2 = oc + j;
+              if (p.shuffle == 2) {  // a 16-group may straddle a shuffle quadrant only when cout/4 % 16 != 0
+                const int cr = p.cout >> 2;
+                const int q = (co0 + j) / cr;
+                oc2 = co0 + j - q * cr;
+                op2 = ((int64_t)it.n * (2 * p.Ho) + (2 * y + (q >> 1))) * (2 * p.Wo) + (2 * x + (q & 1));
+              }
+              if (p.res1) o += __ldg(p.res1 + op2 * p.res1_ld + oc2);
+              if (p.res2) o += __ldg(p.res2 + op2 * p.res2_ld + oc2);
+              p.out[op2 * p.out_ld + oc2] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar(ACC_EMPTY + sa));
+    }
+  } else if (warp < kEpiWarps + kProdWarps) {
+    // ===================================================================== producers: fp32 halo -> bf16 hi/lo planes
+    const int ptid = threadIdx.x - kEpiWarps * 32;
+    constexpr int F4 = CK / 4;                 // float4 per pixel per unit
+    constexpr int PPP = kProdThreads / F4;     // pixels per pass
+    const int fi = ptid % F4, pslot = ptid / F4;
+    const int j8 = fi >> 1, half = fi & 1;
+    int a_it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
+      const int iy0 = it.y0 - C::PAD, ix0 = it.x0 - C::PAD;
+      for (int u = 0; u < n_units; ++u, ++a_it) {
+        // resolve this thread's 4 channels (concatenated index) to a source tensor
+        const float* sp = nullptr;
+        int sld = 0;
+        {
+          int cc = u * CK + fi * 4;
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            if (s < p.n_src && sp == nullptr) {
+              if (cc < p.src_c[s]) { sp = p.src[s] + cc; sld = p.src_ld[s]; }
+              else cc -= p.src_c[s];
+            }
+          }
+        }
+        const int st = a_it % C::NA;
+        mbar_wait(bar(A_EMPTY + st), ((a_it / C::NA) & 1) ^ 1);
+        uint8_t* hi = a_buf + st * C::A_STAGE + (j8 * C::NPIXP) * 16 + half * 8;
+        uint8_t* lo = hi + C::A_HALF;
+        const float* img = sp ? sp + (int64_t)it.n * p.H * p.W * sld : nullptr;
+        constexpr int UNR = 8;
+        for (int pb = pslot; pb < C::NPIX; pb += PPP * UNR) {
+          float4 v[UNR];
+#pragma unroll
+          for (int q = 0; q < UNR; ++q) {
+            const int pp = pb + q * PPP;
+            v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pp < C::NPIX && img != nullptr) {
+              const int hy = pp / C::HALO, hx = pp - hy * C::HALO;
+              const int iy = iy0 + hy, ix = ix0 + hx;
+              if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                v[q] = __ldg(reinterpret_cast<const float4*>(img + ((int64_t)iy * p.W + ix) * sld));
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < UNR; ++q) {
+            const int pp = pb + q * PPP;
+            if (pp < C::NPIX) {
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[q].x, v[q].y);
+              const __nv_bfloat162 h23 = __floats2bfloat162_rn(v[q].z, v[q].w);
+              const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+              const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[q].x - f01.x, v[q].y - f01.y);
+              const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[q].z - f23.x, v[q].w - f23.y);
+              uint2 hv, lv;
+              hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+              lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+              *reinterpret_cast<uint2*>(hi + pp * 16) = hv;
+              *reinterpret_cast<uint2*>(lo + pp * 16) = lv;
+            }
+          }
+        }
+        fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(bar(A_FULL + st));
+      }
+    }
+  } else if (warp == 8) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC_2N = instr_desc(2 * NT), IDESC_N = instr_desc(NT);
+      const uint32_t a0 = smem_u32(a_buf), b0 = smem_u32(b_buf);
+      int a_it = 0, b_it = 0, acc_it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
+        const int sa = acc_it & 1;
+        mbar_wait(bar(ACC_EMPTY + sa), ((acc_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int u = 0; u < n_units; ++u, ++a_it) {
+          const int sA = a_it % C::NA;
+          mbar_wait(bar(A_FULL + sA), (a_it / C::NA) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = a0 + sA * C::A_STAGE, a_lo = a_hi + C::A_HALF;
+#pragma unroll 1
+          for (int tap = 0; tap < C::TAPS; ++tap, ++b_it) {
+            const int sB = b_it % C::NB;
+            mbar_wait(bar(B_FULL + sB), (b_it / C::NB) & 1);
+            tc_fence_after();
+            const int ky = tap / KS, kx = tap - ky * KS;
+            const uint32_t bblk = b0 + sB * C::B_BLOCK;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const uint32_t d = tmem_base + (uint32_t)((sa * 2 + t) * 2 * NT);
+              const uint32_t aoff = (uint32_t)((ky * C::HALO + kx + 8 * t) * 16);
+#pragma unroll
+              for (int s = 0; s < C::KSTEPS; ++s) {
+                const uint64_t bd = smem_desc(bblk + s * 2 * C::LBO_B, C::LBO_B, C::SBO_B);
+                const uint64_t adh = smem_desc(a_hi + aoff + s * 2 * C::LBO_A, C::LBO_A, C::SBO_A);
+                const uint64_t adl = smem_desc(a_lo + aoff + s * 2 * C::LBO_A, C::LBO_A, C::SBO_A);
+                tc_mma(d, adh, bd, IDESC_2N, (u | tap | s) != 0);
+                tc_mma(d, adl, bd, IDESC_N, 1u);
+              }
+            }
+            tc_commit(bar(B_EMPTY + sB));
+          }
+          tc_commit(bar(A_EMPTY + sA));
+        }
+        tc_commit(bar(ACC_FULL + sa));
+      }
+    }
+  } else {
+    // ===================================================================== weight loader (1-D bulk TMA)
+    if (lane == 0) {
+      const uint8_t* wb = static_cast<const uint8_t*>(p.weight_bf16);
+      const uint32_t b0 = smem_u32(b_buf);
+      int b_it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int jt = item % n_jt;
+        for (int u = 0; u < n_units; ++u) {
+          const uint8_t* src = wb + ((int64_t)(jt * n_units + u) * C::TAPS) * C::B_BLOCK;
+          for (int tap = 0; tap < C::TAPS; ++tap, ++b_it) {
+            const int sB = b_it % C::NB;
+            mbar_wait(bar(B_EMPTY + sB), ((b_it / C::NB) & 1) ^ 1);
+            mbar_expect_tx(bar(B_FULL + sB), C::B_BLOCK);
+            bulk_g2s(b0 + sB * C::B_BLOCK, src + (int64_t)tap * C::B_BLOCK, C::B_BLOCK, bar(B_FULL + sB));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// fp32 packed weights [T][cin_pad][cout_pad] -> per (cout tile, unit, tap) bf16 block [2*NT rows][CK] in the
+// canonical K-major interleaved layout [(n/8)][(k/8)][n%8][k%8]; rows 0..NT-1 = hi, NT..2NT-1 = lo.
+__global__ void pack_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int T, int cin, int cin_pad,
+                                 int cout, int cout_pad, int CK, int NT, int n_units, int n_jt) {
+  const int64_t per_block = (int64_t)2 * NT * CK;
+  const int64_t total = (int64_t)n_jt * n_units * T * per_block;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int k8 = (int)(r % 8); r /= 8;
+    const int n8 = (int)(r % 8); r /= 8;
+    const int kc = (int)(r % (CK / 8)); r /= (CK / 8);
+    const int ng = (int)(r % (2 * NT / 8)); r /= (2 * NT / 8);
+    const int tap = (int)(r % T); r /= T;
+    const int u = (int)(r % n_units);
+    const int jt = (int)(r / n_units);
+    const int n2 = ng * 8 + n8, k = kc * 8 + k8;
+    const int ci = u * CK + k, co = jt * NT + (n2 % NT);
+    float v = 0.f;
+    if (ci < cin_pad && co < cout_pad && ci < cin && co < cout) v = w[((int64_t)tap * cin_pad + ci) * cout_pad + co];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[i] = (n2 < NT) ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+struct Choice {
+  int ks, ck, nt;
+};
+
+static bool choose(const TdvcConvParams& p, Choice* c) {
+  if (p.kh != p.kw || p.stride != 1 || p.pad != p.kh / 2) return false;
+  if (p.post != TDVC_POST_NONE || p.in_square) return false;
+  if (p.kh == 3) {
+    if (p.cin < 64) return false;
+    *c = {3, 64, 64};
+    return true;
+  }
+  if (p.kh == 7) {
+    const int ck = p.cin >= 32 ? 32 : 16;
+    const int nt = p.cout >= 64 ? 64 : (p.cout >= 32 ? 32 : 16);
+    *c = {7, ck, nt};
+    return true;
+  }
+  return false;
+}
+
+template <int KS, int CK, int NT>
+static int launch(const TdvcConvParams& p, cudaStream_t st) {
+  using C = Cfg<KS, CK, NT>;
+  static bool attr_set = false;  // idempotent; a benign race sets it twice
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, CK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) {
+      set_error("conv_tc: cudaFuncSetAttribute(%d bytes) failed: %s", C::SMEM, cudaGetErrorString(e));
+      return TDVC_ECUDA;
+    }
+    attr_set = true;
+  }
+  const int tiles_x = cdiv(p.Wo, kTile), tiles_y = cdiv(p.Ho, kTile);
+  const int n_jt = cdiv(p.cout, NT), n_units = cdiv(p.cin, CK);
+  const int64_t items = (int64_t)p.N * tiles_x * tiles_y * n_jt;
+  TDVC_REQUIRE(items < (1ll << 31), "conv_tc: too many work items");
+  const int grid = (int)(items < kNumSMs ? items : kNumSMs);
+  conv_tc_kernel<KS, CK, NT><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items);
+  TDVC_CHECK_LAUNCH("conv_tc");
+  return TDVC_OK;
+}
+
+}  // namespace tc
+
+int conv2d_tc_supported(const TdvcConvParams& p) {
+  tc::Choice c;
+  if (p.weight_bf16 == nullptr) return 0;
+  if (!tc::choose(p, &c)) return 0;
+  for (int s = 0; s < p.n_src; ++s)
+    if (p.src_c[s] % 4 != 0 || p.src_ld[s] % 4 != 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(p.weight_bf16) & 15) != 0) return 0;
+  return 1;
+}
+
+int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
+  tc::Choice c;
+  if (!tc::choose(p, &c)) {
+    set_error("conv_tc: unsupported shape");
+    return TDVC_EINVAL;
+  }
+  if (c.ks == 3) return tc::launch<3, 64, 64>(p, st);
+  if (c.ck == 32 && c.nt == 64) return tc::launch<7, 32, 64>(p, st);
+  if (c.ck == 32 && c.nt == 32) return tc::launch<7, 32, 32>(p, st);
+  if (c.ck == 32 && c.nt == 16) return tc::launch<7, 32, 16>(p, st);
+  if (c.ck == 16 && c.nt == 32) return tc::launch<7, 16, 32>(p, st);
+  if (c.ck == 16 && c.nt == 16) return tc::launch<7, 16, 16>(p, st);
+  if (c.ck == 16 && c.nt == 64) return tc::launch<7, 16, 64>(p, st);
+  set_error("conv_tc: no instantiation for ks=%d ck=%d nt=%d", c.ks, c.ck, c.nt);
+  return TDVC_EINVAL;
+}
+
 int dcn_tc_supported(const TdvcDcnParams&) { return 0; }
-int dcn_tc(const TdvcDcnParams&, cudaStream_t) { set_error("tcgen05 dcn not built"); return TDVC_EINVAL; }
+int dcn_tc(const TdvcDcnParams&, cudaStream_t) {
+  set_error("tcgen05 dcn not built");
+  return TDVC_EINVAL;
+}
+
+}  // namespace tdvc
+
+using namespace tdvc;
+
+extern "C" size_t tdvc_conv2d_bf16_bytes(const TdvcConvParams* p) {
+  tc::Choice c;
+  if (p == nullptr || !tc::choose(*p, &c)) return 0;
+  const int n_jt = cdiv(p->cout, c.nt), n_units = cdiv(p->cin, c.ck);
+  return (size_t)n_jt * n_units * c.ks * c.ks * 2 * c.nt * c.ck * sizeof(__nv_bfloat16);
+}
+
+extern "C" int tdvc_conv2d_pack_bf16(const TdvcConvParams* p, void* out, void* stream) {
+  tc::Choice c;
+  TDVC_REQUIRE(p && out && p->weight, "conv2d_pack_bf16: null pointer");
+  TDVC_REQUIRE(tc::choose(*p, &c), "conv2d_pack_bf16: shape has no tcgen05 path");
+  const int n_jt = cdiv(p->cout, c.nt), n_units = cdiv(p->cin, c.ck);
+  const int64_t total = (int64_t)n_jt * n_units * c.ks * c.ks * 2 * c.nt * c.ck;
+  int grid = cdiv(total, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  tc::pack_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->weight, static_cast<__nv_bfloat16*>(out), c.ks * c.ks, p->cin,
+                                                             p->cin_pad, p->cout, p->cout_pad, c.ck, c.nt, n_units, n_jt);
+  TDVC_CHECK_LAUNCH("conv2d_pack_bf16");
+  return TDVC_OK;
 }

@@ -45,6 +45,8 @@ SIGNATURES = {
     "tdvc_version": [],
     "tdvc_last_error": [],
     "tdvc_conv2d": [C.POINTER(ConvParams), vp],
+    "tdvc_conv2d_bf16_bytes": [C.POINTER(ConvParams)],
+    "tdvc_conv2d_pack_bf16": [C.POINTER(ConvParams), vp, vp],
     "tdvc_dcn_v2_workspace_bytes": [i32] * 6,
     "tdvc_dcn_v2_forward": [vp] * 6 + [i32] * 14 + [vp, sz, vp],
     "tdvc_dcn_nhwc": [C.POINTER(DcnParams), vp],
@@ -86,6 +88,7 @@ def load():
         fn.restype = C.c_int
     lib.tdvc_last_error.restype = C.c_char_p
     lib.tdvc_dcn_v2_workspace_bytes.restype = C.c_size_t
+    lib.tdvc_conv2d_bf16_bytes.restype = C.c_size_t
     _lib = lib
     return lib
 
