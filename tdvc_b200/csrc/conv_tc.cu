@@ -7,21 +7,21 @@
 // fp32 accumulation in TMEM ("3xBF16"): relative error per product ~2^-16, i.e. the fp32-class accuracy the
 // parity bar needs (>= 99.9 % identical quantised symbols), at 3 MMA passes.
 //
-// Work decomposition (persistent, one CTA per SM, 320 threads):
+// Work decomposition (persistent, one CTA per SM, 576 threads = 18 warps):
 //   work item  = 16x16 output pixels ("super tile" = two 8-wide x 16-tall MMA tiles, M = 128 each) x NT output
 //                channels;  K loop = cin chunks of CK channels ("units") x KS*KS taps x CK/16 MMA k-steps.
-//   warps 4-7  producers: read the (16+KS-1)^2 fp32 halo of one unit from global (float4, coalesced 256 B per
+//   warps 8-15 producers (one halo row per warp at a time): read the (16+KS-1)^2 fp32 halo of one unit from global (float4, coalesced 256 B per
 //              pixel), split into bf16 hi / lo and store it to shared memory in the tcgen05 K-major
 //              "interleaved" (no-swizzle) canonical layout: [channel/8][halo pixel][8 channels] — 8 x-adjacent
 //              pixels form one 8x16 B core matrix, so every tap of the convolution is the SAME buffer read
 //              through a descriptor whose start address is shifted by (ky*HALO_W + kx)*16 B.  No im2col copy.
-//   warp 9     streams pre-packed bf16 weight blocks [2*NT rows = w_hi | w_lo][CK] (one per unit x tap)
+//   warp 17    streams pre-packed bf16 weight blocks [2*NT rows = w_hi | w_lo][CK] (one per unit x tap)
 //              with cp.async.bulk (1-D TMA) into a 3-4 stage ring, completion on mbarriers.
-//   warp 8     one elected thread issues, per k-step and MMA tile:
+//   warp 16    one elected thread issues, per k-step and MMA tile:
 //                 D[:, 0:2NT] (+)= A_hi (128x16) * [W_hi | W_lo]^T      (N = 2*NT)
 //                 D[:, 0:NT ]  += A_lo (128x16) *  W_hi^T               (N = NT)
 //              and tcgen05.commit's the ring slots back to the producers.
-//   warps 0-3  epilogue: tcgen05.ld the accumulator (lane = pixel), add the hi*hi+lo*hi and hi*lo halves, bias,
+//   warps 0-7  epilogue (TMEM lane quadrant x MMA tile): tcgen05.ld the accumulator (lane = pixel), add the hi*hi+lo*hi and hi*lo halves, bias,
 //              activation, up to two residual adds, optional PixelShuffle(2) store; overlaps the next item's MMAs
 //              (two accumulator stages in TMEM: 8*NT columns).
 #include "common.cuh"
@@ -31,8 +31,9 @@ namespace tdvc {
 
 namespace tc {
 
-constexpr int kEpiWarps = 4, kProdWarps = 4;
-constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 320
+constexpr int kEpiWarps = 8, kProdWarps = 8;                 // 2 of each per SM sub-partition
+constexpr int kMmaWarp = kEpiWarps + kProdWarps, kLoadWarp = kMmaWarp + 1;
+constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 576
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kTile = 16;  // super-tile edge (pixels)
 
@@ -83,6 +84,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+        "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+        "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     for (int i = 0; i < 2; ++i) { mbar_init(bar(ACC_FULL + i), 1); mbar_init(bar(ACC_EMPTY + i), kEpiWarps * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
@@ -171,38 +182,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp < kEpiWarps) {
-    // ===================================================================== epilogue
-    const int m = warp * 32 + lane;          // accumulator row = TMEM lane
+    // ===================================================================== epilogue (8 warps: quadrant x tile)
+    const int quad = warp & 3, t = warp >> 2;  // TMEM lane quadrant (= warp id % 4), MMA tile of the super tile
+    const int m = quad * 32 + lane;            // accumulator row = TMEM lane
     const int py = m >> 3, px = m & 7;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    constexpr int CH = NT >= 32 ? 32 : 16;     // channels per TMEM read
+    const int cr = p.cout >> 2;
+    const bool vec_ok = ((p.out_ld & 3) == 0) && (!p.res1 || (p.res1_ld & 3) == 0) && (!p.res2 || (p.res2_ld & 3) == 0) &&
+                        (p.shuffle != 2 || (cr % CH) == 0);
     int acc_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
       const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
       const int sa = acc_it & 1;
       mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
       tc_fence_after();
-      const int y = it.y0 + py;
+      const int y = it.y0 + py, x = it.x0 + 8 * t + px;
+      const bool valid = (y < p.Ho) && (x < p.Wo);
+      const uint32_t tcol = lane_addr + (uint32_t)((sa * 2 + t) * 2 * NT);
 #pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        const int x = it.x0 + 8 * t + px;
-        const bool valid = (y < p.Ho) && (x < p.Wo);
-        const uint32_t tcol = lane_addr + (uint32_t)((sa * 2 + t) * 2 * NT);
-#pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          uint32_t ra[16], rb[16];
+      for (int c0 = 0; c0 < NT; c0 += CH) {
+        uint32_t ra[CH], rb[CH];
+        if constexpr (CH == 32) {
+          tmem_ld32(tcol + c0, ra);
+          tmem_ld32(tcol + NT + c0, rb);
+        } else {
           tmem_ld16(tcol + c0, ra);
           tmem_ld16(tcol + NT + c0, rb);
-          tmem_ld_wait();
-          const int co0 = it.jt * NT + c0;
-          if (!valid || co0 >= p.cout) continue;
-          float v[16];
+        }
+        tmem_ld_wait();
+        const int co0 = it.jt * NT + c0;
+        if (!valid || co0 >= p.cout) continue;
+        float v[CH];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
-          // output location (PixelShuffle(2) folded into the store: co' = q*(cout/4) + c)
+        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
+        if (vec_ok && co0 + CH <= p.cout) {
           int64_t opix;
           int oc;
-          if (p.shuffle == 2) {
-            const int cr = p.cout >> 2;
+          if (p.shuffle == 2) {  // PixelShuffle(2) folded into the store: co' = q*(cout/4) + c
             const int q = co0 / cr;
             oc = co0 - q * cr;
             opix = ((int64_t)it.n * (2 * p.Ho) + (2 * y + (q >> 1))) * (2 * p.Wo) + (2 * x + (q & 1));
@@ -210,46 +227,64 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             oc = co0;
             opix = ((int64_t)it.n * p.Ho + y) * p.Wo + x;
           }
-          const bool vec = (co0 + 16 <= p.cout) && ((p.out_ld & 3) == 0) && (!p.res1 || (p.res1_ld & 3) == 0) &&
-                           (!p.res2 || (p.res2_ld & 3) == 0);
-          if (vec) {
+          float4* op = reinterpret_cast<float4*>(p.out + opix * p.out_ld + oc);
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + co0);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (p.bias) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
-                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-              }
-              o.x = apply_act(o.x, p.act, p.slope); o.y = apply_act(o.y, p.act, p.slope);
-              o.z = apply_act(o.z, p.act, p.slope); o.w = apply_act(o.w, p.act, p.slope);
-              if (p.res1) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res1 + opix * p.res1_ld + oc + j));
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-              }
-              if (p.res2) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res2 + opix * p.res2_ld + oc + j));
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-              }
-              *reinterpret_cast<float4*>(p.out + opix * p.out_ld + oc + j) = o;
+            for (int j = 0; j < CH / 4; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
             }
-          } else {
+          }
+          if (p.act == TDVC_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (co0 + j >= p.cout) continue;
-              float o = v[j] + (p.bias ? __ldg(p.bias + co0 + j) : 0.f);
-              o = apply_act(o, p.act, p.slope);
-              int64_t op2 = opix;
-              int oc2 = oc + j;
-              if (p.shuffle == 2) {  // a 16-group may straddle a shuffle quadrant only when cout/4 % 16 != 0
-                const int cr = p.cout >> 2;
-                const int q = (co0 + j) / cr;
-                oc2 = co0 + j - q * cr;
-                op2 = ((int64_t)it.n * (2 * p.Ho) + (2 * y + (q >> 1))) * (2 * p.Wo) + (2 * x + (q & 1));
-              }
-              if (p.res1) o += __ldg(p.res1 + op2 * p.res1_ld + oc2);
-              if (p.res2) o += __ldg(p.res2 + op2 * p.res2_ld + oc2);
-              p.out[op2 * p.out_ld + oc2] = o;
+            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == TDVC_ACT_LRELU) {
+            const float sl = p.slope;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
+          } else if (p.act == TDVC_ACT_CLAMP01) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 1.f);
+          }
+          if (p.res1) {
+            const float4* rp = reinterpret_cast<const float4*>(p.res1 + opix * p.res1_ld + oc);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) {
+              const float4 r = __ldg(rp + j);
+              v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
             }
+          }
+          if (p.res2) {
+            const float4* rp = reinterpret_cast<const float4*>(p.res2 + opix * p.res2_ld + oc);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) {
+              const float4 r = __ldg(rp + j);
+              v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const int co = co0 + j;
+            if (co >= p.cout) continue;
+            float o = v[j] + (p.bias ? __ldg(p.bias + co) : 0.f);
+            o = apply_act(o, p.act, p.slope);
+            int64_t op2;
+            int oc2;
+            if (p.shuffle == 2) {
+              const int q = co / cr;
+              oc2 = co - q * cr;
+              op2 = ((int64_t)it.n * (2 * p.Ho) + (2 * y + (q >> 1))) * (2 * p.Wo) + (2 * x + (q & 1));
+            } else {
+              oc2 = co;
+              op2 = ((int64_t)it.n * p.Ho + y) * p.Wo + x;
+            }
+            if (p.res1) o += __ldg(p.res1 + op2 * p.res1_ld + oc2);
+            if (p.res2) o += __ldg(p.res2 + op2 * p.res2_ld + oc2);
+            p.out[op2 * p.out_ld + oc2] = o;
           }
         }
       }
@@ -258,17 +293,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     }
   } else if (warp < kEpiWarps + kProdWarps) {
     // ===================================================================== producers: fp32 halo -> bf16 hi/lo planes
-    const int ptid = threadIdx.x - kEpiWarps * 32;
-    constexpr int F4 = CK / 4;                 // float4 per pixel per unit
-    constexpr int PPP = kProdThreads / F4;     // pixels per pass
-    const int fi = ptid % F4, pslot = ptid / F4;
+    // One warp per halo row: LPP lanes cover the CK channels of a pixel (coalesced 16*LPP bytes), 32/LPP pixels per
+    // load instruction, all loads of the row issued before the first conversion (memory-level parallelism).
+    const int pw = warp - kEpiWarps;
+    constexpr int LPP = CK / 4;                       // lanes (float4) per pixel
+    constexpr int PPI = 32 / LPP;                     // pixels per warp-wide load
+    constexpr int ITERS = (C::HALO + PPI - 1) / PPI;
+    const int fi = lane % LPP, psub = lane / LPP;
     const int j8 = fi >> 1, half = fi & 1;
     int a_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
       const int iy0 = it.y0 - C::PAD, ix0 = it.x0 - C::PAD;
       for (int u = 0; u < n_units; ++u, ++a_it) {
-        // resolve this thread's 4 channels (concatenated index) to a source tensor
+        // resolve this lane's 4 channels (index in the concatenated input) to a source tensor
         const float* sp = nullptr;
         int sld = 0;
         {
@@ -284,36 +322,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         const int st = a_it % C::NA;
         mbar_wait(bar(A_EMPTY + st), ((a_it / C::NA) & 1) ^ 1);
         uint8_t* hi = a_buf + st * C::A_STAGE + (j8 * C::NPIXP) * 16 + half * 8;
-        uint8_t* lo = hi + C::A_HALF;
         const float* img = sp ? sp + (int64_t)it.n * p.H * p.W * sld : nullptr;
-        constexpr int UNR = 8;
-        for (int pb = pslot; pb < C::NPIX; pb += PPP * UNR) {
-          float4 v[UNR];
+#pragma unroll 1
+        for (int hy = pw; hy < C::HALO; hy += kProdWarps) {
+          const int iy = iy0 + hy;
+          const bool rowok = (img != nullptr) && iy >= 0 && iy < p.H;
+          const float* rowp = rowok ? img + ((int64_t)iy * p.W + ix0) * sld : nullptr;
+          float4 v[ITERS];
 #pragma unroll
-          for (int q = 0; q < UNR; ++q) {
-            const int pp = pb + q * PPP;
-            v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pp < C::NPIX && img != nullptr) {
-              const int hy = pp / C::HALO, hx = pp - hy * C::HALO;
-              const int iy = iy0 + hy, ix = ix0 + hx;
-              if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-                v[q] = __ldg(reinterpret_cast<const float4*>(img + ((int64_t)iy * p.W + ix) * sld));
-            }
+          for (int k = 0; k < ITERS; ++k) {
+            const int hx = psub + k * PPI;
+            const int ix = ix0 + hx;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowok && hx < C::HALO && ix >= 0 && ix < p.W) v[k] = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)hx * sld));
           }
+          uint8_t* rhi = hi + (hy * C::HALO + psub) * 16;
 #pragma unroll
-          for (int q = 0; q < UNR; ++q) {
-            const int pp = pb + q * PPP;
-            if (pp < C::NPIX) {
-              const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[q].x, v[q].y);
-              const __nv_bfloat162 h23 = __floats2bfloat162_rn(v[q].z, v[q].w);
+          for (int k = 0; k < ITERS; ++k) {
+            const int hx = psub + k * PPI;
+            if (hx < C::HALO) {
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[k].x, v[k].y);
+              const __nv_bfloat162 h23 = __floats2bfloat162_rn(v[k].z, v[k].w);
               const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-              const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[q].x - f01.x, v[q].y - f01.y);
-              const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[q].z - f23.x, v[q].w - f23.y);
+              const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[k].x - f01.x, v[k].y - f01.y);
+              const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[k].z - f23.x, v[k].w - f23.y);
               uint2 hv, lv;
               hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
               lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-              *reinterpret_cast<uint2*>(hi + pp * 16) = hv;
-              *reinterpret_cast<uint2*>(lo + pp * 16) = lv;
+              *reinterpret_cast<uint2*>(rhi + k * PPI * 16) = hv;
+              *reinterpret_cast<uint2*>(rhi + C::A_HALF + k * PPI * 16) = lv;
             }
           }
         }
@@ -321,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         mbar_arrive(bar(A_FULL + st));
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t IDESC_2N = instr_desc(2 * NT), IDESC_N = instr_desc(NT);
@@ -386,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
                  : "memory");

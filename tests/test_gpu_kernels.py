@@ -192,7 +192,8 @@ def test_spynet_prep_vs_oracle(plan, dev):
         assert (got - want).abs().max() < 3e-6 * max(1.0, want.abs().max().item())
         plan.call("tdvc_spynet_prep", r4.ptr, s4.ptr, None, out.ptr, 1, h, w)  # level 0: zero flow => identity warp
         got0 = out.nchw().cpu()
-        assert torch.equal(got0[:, 3:6], supp) and got0[:, 6:].abs().max() == 0
+        want0 = flow_warp_border(supp, torch.zeros(1, h, w, 2))  # the coordinate round trip is not exact
+        assert (got0[:, 3:6] - want0).abs().max() < 3e-6 and got0[:, 6:].abs().max() == 0
 
 
 def test_pool_upsample_flowadd(plan, dev):
