@@ -284,7 +284,7 @@ def main():
                     "share_of_frame": dms / total_ms, "peak_source": which}
         kernels = {k: {"launches": v[0], "ms": round(v[1], 4),
                        "tflops": round(2.0 * v[2] / (v[1] / 1e3) / 1e12, 2) if v[2] and v[1] > 0 else None,
-                       "gbs": round(v[3] / (v[1] / 1e3) / 1e9, 1) if v[3] and v[1] > 0 else None} for k, v in top[:12]}
+                       "gbs": round(v[3] / (v[1] / 1e3) / 1e9, 1) if v[3] and v[1] > 0 else None} for k, v in top}
         frame_tflops = 2.0 * MACS_PER_PX * hh * ww / (ms / K / 1e3) / 1e12
         cpu = None
         if not args.no_cpu_baseline:

@@ -1,0 +1,44 @@
+"""Developer tool (GPU box): code ONE 1920x1024 P-frame eagerly (no CUDA graph) inside a cudaProfilerStart/Stop
+range after warm-up frames, so that `ncu --profile-from-start off` sees exactly one frame's launches.
+
+    python tools/profile_frame.py [H W [conv_impl]]
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+        --log-file gpurun_out/launches.csv python tools/profile_frame.py
+"""
+import sys
+import warnings
+
+import torch
+
+warnings.filterwarnings("ignore")
+sys.path.insert(0, ".")
+
+
+def main(h=1024, w=1920, impl=0):
+    from tdvc_b200 import gop as G
+    from tdvc_b200 import synth
+    from tdvc_b200.model import VideoCompressor
+    dev = torch.device("cuda:0")
+    torch.manual_seed(synth.SEED)
+    net = VideoCompressor().eval()
+    sd = net.state_dict()
+    synth.condition_state_dict(sd)
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    net.conv_impl = impl
+    g = synth.make_gop(h, w, gop=4, seed=100).to(dev)
+    refs = [g[0:1]]
+    with torch.no_grad():
+        for t in (1, 2):
+            recon, _, _ = net(g[t:t + 1], G.reference_window(refs), False)
+            refs.append(recon)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        recon, bres, bmv = net(g[3:4], G.reference_window(refs), False)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+    print(f"profiled 1 P-frame {h}x{w}: launches {net.last_launches}, bpp_res {bres.item():.4f} bpp_mv {bmv.item():.4f}")
+
+
+if __name__ == "__main__":
+    main(*[int(a) for a in sys.argv[1:]])
