@@ -47,7 +47,7 @@ const char* tdvc_last_error(void);
  * permuted on the host to co' = (dy*2+dx)*(cout/4) + c (nn.PixelShuffle folded into the store).
  * Constraints: src_c[i] % 4 == 0, src_ld[i] % 4 == 0, 16-byte aligned sources, cin_pad % 8 == 0,
  * cout_pad % 16 == 0.  `impl`: 0 = auto, 1 = SIMT fp32 FFMA kernel, 2 = tcgen05 tensor-core kernel
- * (3xBF16 split, fp32 accumulate in TMEM; needs weight_bf16).                                       */
+ * (3xFP16 split: x = hi + lo in fp16, x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, fp32 accumulate in TMEM; needs weight_f16).                                       */
 typedef struct {
   const float* src[4];
   int32_t src_c[4];
@@ -69,15 +69,15 @@ typedef struct {
   float* out; int32_t out_ld;
   int32_t shuffle;          /* 0 or 2 */
   int32_t impl;
-  const void* weight_bf16;  /* tcgen05 path: [kh*kw][2 (hi,lo)][cout_pad][cin_pad] bf16, or NULL */
+  const void* weight_f16;  /* tcgen05 path: fp16 (hi | lo*2^12) weight blocks built by tdvc_conv2d_pack_f16, or NULL */
   float* chan_sum;          /* optional [N][gridDim-dependent] — reserved for fused SE partial sums */
 } TdvcConvParams;
 int tdvc_conv2d(const TdvcConvParams* p, void* stream);
-/* tcgen05 path: size of / builder for the bf16 (hi, lo) weight blocks of a convolution, from its fp32 packed
+/* tcgen05 path: size of / builder for the fp16 (hi, lo) weight blocks of a convolution, from its fp32 packed
  * `weight` ([kh*kw][cin_pad][cout_pad]).  Only geometry fields (kh, kw, stride, pad, cin, cin_pad, cout, cout_pad,
  * post, in_square) and `weight` are read.  bytes == 0: the shape has no tensor-core path (SIMT kernel is used). */
-size_t tdvc_conv2d_bf16_bytes(const TdvcConvParams* p);
-int tdvc_conv2d_pack_bf16(const TdvcConvParams* p, void* out, void* stream);
+size_t tdvc_conv2d_f16_bytes(const TdvcConvParams* p);
+int tdvc_conv2d_pack_f16(const TdvcConvParams* p, void* out, void* stream);
 
 /* ---- DCNv2 forward, the reference's `_ext.dcn_v2_forward` (dcn_v2.h:9-46): contiguous NCHW fp32,
  * offset (N, 2*dg*kh*kw, H, W) ordered [g][tap][dy,dx], mask (N, dg*kh*kw, H, W), weight (O, C, kh, kw),
@@ -106,8 +106,8 @@ typedef struct {
   int32_t N, H, W, C, O, O_pad, dg;
   int32_t round_fp16;
   int32_t act; float slope;
-  int32_t impl;                           /* 0 = auto, 1 = SIMT fp32 contraction, 2 = tcgen05 (3xBF16 split) */
-  const void* weight_bf16;                /* tcgen05 path: packed hi/lo bf16 weights (see conv_tc.cu), or NULL */
+  int32_t impl;                           /* 0 = auto, 1 = SIMT fp32 contraction, 2 = tcgen05 (3xFP16 split) */
+  const void* weight_f16;                /* tcgen05 path: packed hi/lo fp16 weights (see dcn_tc.cu), or NULL */
 } TdvcDcnParams;
 int tdvc_dcn_nhwc(const TdvcDcnParams* p, void* stream);
 

@@ -2,20 +2,23 @@
 // dense KxK stride-1 convolutions of the P-frame graph (reference main/model/pnet.py passim,
 // main/utils/utils.py:43-56, main/model/flownet.py:187-227, compressai blocks of SURVEY.md App. A).
 //
-// Numerics: activations and weights stay fp32 in HBM.  Each operand is split on the fly into two bf16 terms
-// (x = x_hi + x_lo, |x_lo| <= 2^-9 |x|) and the product is evaluated as x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with
-// fp32 accumulation in TMEM ("3xBF16"): relative error per product ~2^-16, i.e. the fp32-class accuracy the
-// parity bar needs (>= 99.9 % identical quantised symbols), at 3 MMA passes.
+// Numerics: activations and weights stay fp32 in HBM.  Each operand is split on the fly into two fp16 terms
+// (x = x_hi + x_lo, x_hi = fp16(x), x_lo = fp16(x - x_hi): 22 significand bits) and the product is evaluated as
+// x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with fp32 accumulation in TMEM ("3xFP16"): relative error per product ~2^-22,
+// i.e. the fp32-class accuracy the parity bar needs (>= 99.9 % identical quantised symbols), at 3 MMA passes.
+// w_lo is stored scaled by 2^12 (kept out of the fp16 subnormal range; its accumulator columns are rescaled by
+// 2^-12 in the epilogue - both exact).  fp16 range: |x| is saturated to 65504 on conversion (cvt.satfinite);
+// activations of an image codec with [0,1] inputs sit orders of magnitude below that.
 //
 // Work decomposition (persistent, one CTA per SM, 576 threads = 18 warps):
 //   work item  = 16x16 output pixels ("super tile" = two 8-wide x 16-tall MMA tiles, M = 128 each) x NT output
 //                channels;  K loop = cin chunks of CK channels ("units") x KS*KS taps x CK/16 MMA k-steps.
 //   warps 8-15 producers (one halo row per warp at a time): read the (16+KS-1)^2 fp32 halo of one unit from global (float4, coalesced 256 B per
-//              pixel), split into bf16 hi / lo and store it to shared memory in the tcgen05 K-major
+//              pixel), split into fp16 hi / lo and store it to shared memory in the tcgen05 K-major
 //              "interleaved" (no-swizzle) canonical layout: [channel/8][halo pixel][8 channels] — 8 x-adjacent
 //              pixels form one 8x16 B core matrix, so every tap of the convolution is the SAME buffer read
 //              through a descriptor whose start address is shifted by (ky*HALO_W + kx)*16 B.  No im2col copy.
-//   warp 17    streams pre-packed bf16 weight blocks [2*NT rows = w_hi | w_lo][CK] (one per unit x tap)
+//   warp 17    streams pre-packed fp16 weight blocks [2*NT rows = w_hi | w_lo][CK] (one per unit x tap)
 //              with cp.async.bulk (1-D TMA) into a 3-4 stage ring, completion on mbarriers.
 //   warp 16    one elected thread issues, per k-step and MMA tile:
 //                 D[:, 0:2NT] (+)= A_hi (128x16) * [W_hi | W_lo]^T      (N = 2*NT)
@@ -24,8 +27,7 @@
 //   warps 0-7  epilogue (TMEM lane quadrant x MMA tile): tcgen05.ld the accumulator (lane = pixel), add the hi*hi+lo*hi and hi*lo halves, bias,
 //              activation, up to two residual adds, optional PixelShuffle(2) store; overlaps the next item's MMAs
 //              (two accumulator stages in TMEM: 8*NT columns).
-#include "common.cuh"
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 
 namespace tdvc {
 
@@ -37,98 +39,43 @@ constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 576
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kTile = 16;  // super-tile edge (pixels)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P1;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
-      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
-        "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
-        "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no-swizzle ("interleaved") shared-memory matrix descriptor: 8x16B core matrices, LBO = byte distance
-// between the two K-adjacent core matrices of one MMA (K=16), SBO = byte distance between 8-row groups.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N
-__host__ __device__ constexpr uint32_t instr_desc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
-template <int KS, int CK, int NT>
+template <int KS, int CK, int NT, int S>
 struct Cfg {
+  static_assert(S == 1 || (S == 2 && (KS == 1 || KS == 3)), "stride");
   static constexpr int PAD = KS / 2;
-  static constexpr int HALO = kTile + KS - 1;
-  static constexpr int NPIX = HALO * HALO;
+  // input halo of one 16x16 output super tile: IH x IW input pixels, input pixel = origin + h*STEP
+  static constexpr int STEP = (KS == 1) ? S : 1;            // 1x1: only every S-th input pixel is touched
+  static constexpr int IH = (KS == 1) ? kTile : (kTile - 1) * S + KS;
+  static constexpr int IW = IH;
+  // stride-2 3x3: the halo is stored de-interleaved into 4 parity planes (row parity, column parity) so that every
+  // tap again reads 8 x-adjacent plane pixels per core matrix: tap (ky,kx) -> plane (ky&1, kx&1), shift (ky>>1, kx>>1)
+  static constexpr bool PLANES = (S == 2 && KS == 3);
+  static constexpr int PW = PLANES ? kTile + 1 : IW;        // plane (or halo) row pitch in pixels
+  static constexpr int PH = PLANES ? kTile + 1 : IH;
+  static constexpr int NPIX = PLANES ? 4 * PH * PW : IH * IW;
   static constexpr int NPIXP = NPIX | 1;             // odd pitch: conflict-free 8-byte stores
   static constexpr int NCH8 = CK / 8;
   static constexpr int A_HALF = NCH8 * NPIXP * 16;   // bytes of the hi (or lo) plane of one unit
   static constexpr int A_STAGE = 2 * A_HALF;
-  static constexpr int LBO_A = NPIXP * 16, SBO_A = HALO * 16;
-  static constexpr int B_BLOCK = 2 * NT * CK * 2;    // [2*NT rows][CK] bf16
+  static constexpr int LBO_A = NPIXP * 16, SBO_A = PW * 16;
+  static constexpr int B_BLOCK = 2 * NT * CK * 2;    // [2*NT rows][CK] fp16
   static constexpr int LBO_B = 128, SBO_B = NCH8 * 128;
   static constexpr int KSTEPS = CK / 16;
   static constexpr int TAPS = KS * KS;
   static constexpr int NA = 2;
-  static constexpr int NB = (KS == 3) ? 3 : 4;
+  static constexpr int NB = (KS == 3 && CK == 64) ? 3 : 4;
   static constexpr int TMEM_COLS = 8 * NT;           // 2 stages x 2 tiles x 2*NT
   static constexpr int SMEM = NA * A_STAGE + NB * B_BLOCK + 256;
   static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
-  static_assert(A_STAGE % 128 == 0 || true, "");
+  // smem pixel slot of halo pixel (hy, hx)
+  __host__ __device__ static constexpr int slot(int hy, int hx) {
+    return PLANES ? (((hy & 1) * 2 + (hx & 1)) * PH + (hy >> 1)) * PW + (hx >> 1) : hy * IW + hx;
+  }
+  // smem pixel slot read by output pixel (0,0) of MMA tile 0 for tap (ky, kx)
+  __host__ __device__ static constexpr int tap_slot(int ky, int kx) {
+    return PLANES ? (((ky & 1) * 2 + (kx & 1)) * PH + (ky >> 1)) * PW + (kx >> 1) : ky * IW + kx;
+  }
 };
 
 struct Item {
@@ -146,10 +93,10 @@ __device__ __forceinline__ Item decode_item(int item, int n_jt, int tiles_x, int
   return it;
 }
 
-template <int KS, int CK, int NT>
+template <int KS, int CK, int NT, int S>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvParams p, int tiles_x, int tiles_y, int n_jt,
                                                               int n_units, int n_items) {
-  using C = Cfg<KS, CK, NT>;
+  using C = Cfg<KS, CK, NT, S>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* a_buf = smem;                                  // NA stages of [hi plane | lo plane]
   uint8_t* b_buf = smem + C::NA * C::A_STAGE;             // NB weight blocks
@@ -190,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     constexpr int CH = NT >= 32 ? 32 : 16;     // channels per TMEM read
     const int cr = p.cout >> 2;
     const bool vec_ok = ((p.out_ld & 3) == 0) && (!p.res1 || (p.res1_ld & 3) == 0) && (!p.res2 || (p.res2_ld & 3) == 0) &&
-                        (p.shuffle != 2 || (cr % CH) == 0);
+                        (p.post == TDVC_POST_NONE || (p.mul_ld & 3) == 0) && (p.shuffle != 2 || (cr % CH) == 0);
     int acc_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
       const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
@@ -215,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         if (!valid || co0 >= p.cout) continue;
         float v[CH];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
+        for (int j = 0; j < CH; ++j) v[j] = fmaf(__uint_as_float(rb[j]), kLoUnscale, __uint_as_float(ra[j]));
         if (vec_ok && co0 + CH <= p.cout) {
           int64_t opix;
           int oc;
@@ -234,6 +181,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             for (int j = 0; j < CH / 4; ++j) {
               const float4 b4 = __ldg(bp + j);
               v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+          }
+          if (p.post != TDVC_POST_NONE) {  // GDN / IGDN: v = mul * rsqrt(v) | mul * sqrt(v)
+            const float4* mp = reinterpret_cast<const float4*>(p.mul + opix * p.mul_ld + oc);
+            const bool inv = p.post == TDVC_POST_IGDN;
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) {
+              const float4 m4 = __ldg(mp + j);
+              v[4 * j] = m4.x * (inv ? sqrtf(v[4 * j]) : rsqrtf(v[4 * j]));
+              v[4 * j + 1] = m4.y * (inv ? sqrtf(v[4 * j + 1]) : rsqrtf(v[4 * j + 1]));
+              v[4 * j + 2] = m4.z * (inv ? sqrtf(v[4 * j + 2]) : rsqrtf(v[4 * j + 2]));
+              v[4 * j + 3] = m4.w * (inv ? sqrtf(v[4 * j + 3]) : rsqrtf(v[4 * j + 3]));
             }
           }
           if (p.act == TDVC_ACT_RELU) {
@@ -271,7 +230,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             const int co = co0 + j;
             if (co >= p.cout) continue;
             float o = v[j] + (p.bias ? __ldg(p.bias + co) : 0.f);
-            o = apply_act(o, p.act, p.slope);
             int64_t op2;
             int oc2;
             if (p.shuffle == 2) {
@@ -282,6 +240,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
               oc2 = co;
               op2 = ((int64_t)it.n * p.Ho + y) * p.Wo + x;
             }
+            if (p.post != TDVC_POST_NONE) {
+              const float mv = __ldg(p.mul + op2 * p.mul_ld + oc2);
+              o = mv * (p.post == TDVC_POST_IGDN ? sqrtf(o) : rsqrtf(o));
+            }
+            o = apply_act(o, p.act, p.slope);
             if (p.res1) o += __ldg(p.res1 + op2 * p.res1_ld + oc2);
             if (p.res2) o += __ldg(p.res2 + op2 * p.res2_ld + oc2);
             p.out[op2 * p.out_ld + oc2] = o;
@@ -292,19 +255,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       mbar_arrive(bar(ACC_EMPTY + sa));
     }
   } else if (warp < kEpiWarps + kProdWarps) {
-    // ===================================================================== producers: fp32 halo -> bf16 hi/lo planes
+    // ===================================================================== producers: fp32 halo -> fp16 hi/lo planes
     // One warp per halo row: LPP lanes cover the CK channels of a pixel (coalesced 16*LPP bytes), 32/LPP pixels per
     // load instruction, all loads of the row issued before the first conversion (memory-level parallelism).
     const int pw = warp - kEpiWarps;
     constexpr int LPP = CK / 4;                       // lanes (float4) per pixel
     constexpr int PPI = 32 / LPP;                     // pixels per warp-wide load
-    constexpr int ITERS = (C::HALO + PPI - 1) / PPI;
+    constexpr int ITERS = (C::IW + PPI - 1) / PPI;
     const int fi = lane % LPP, psub = lane / LPP;
     const int j8 = fi >> 1, half = fi & 1;
     int a_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
-      const int iy0 = it.y0 - C::PAD, ix0 = it.x0 - C::PAD;
+      const int iy0 = it.y0 * S - C::PAD, ix0 = it.x0 * S - C::PAD;
       for (int u = 0; u < n_units; ++u, ++a_it) {
         // resolve this lane's 4 channels (index in the concatenated input) to a source tensor
         const float* sp = nullptr;
@@ -324,33 +287,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         uint8_t* hi = a_buf + st * C::A_STAGE + (j8 * C::NPIXP) * 16 + half * 8;
         const float* img = sp ? sp + (int64_t)it.n * p.H * p.W * sld : nullptr;
 #pragma unroll 1
-        for (int hy = pw; hy < C::HALO; hy += kProdWarps) {
-          const int iy = iy0 + hy;
+        for (int hy = pw; hy < C::IH; hy += kProdWarps) {
+          const int iy = iy0 + hy * C::STEP;
           const bool rowok = (img != nullptr) && iy >= 0 && iy < p.H;
           const float* rowp = rowok ? img + ((int64_t)iy * p.W + ix0) * sld : nullptr;
           float4 v[ITERS];
 #pragma unroll
           for (int k = 0; k < ITERS; ++k) {
             const int hx = psub + k * PPI;
-            const int ix = ix0 + hx;
+            const int ix = ix0 + hx * C::STEP;
             v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rowok && hx < C::HALO && ix >= 0 && ix < p.W) v[k] = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)hx * sld));
+            if (rowok && hx < C::IW && ix >= 0 && ix < p.W)
+              v[k] = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)(hx * C::STEP) * sld));
           }
-          uint8_t* rhi = hi + (hy * C::HALO + psub) * 16;
+          if (p.in_square) {
+#pragma unroll
+            for (int k = 0; k < ITERS; ++k) { v[k].x *= v[k].x; v[k].y *= v[k].y; v[k].z *= v[k].z; v[k].w *= v[k].w; }
+          }
 #pragma unroll
           for (int k = 0; k < ITERS; ++k) {
             const int hx = psub + k * PPI;
-            if (hx < C::HALO) {
-              const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[k].x, v[k].y);
-              const __nv_bfloat162 h23 = __floats2bfloat162_rn(v[k].z, v[k].w);
-              const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-              const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[k].x - f01.x, v[k].y - f01.y);
-              const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[k].z - f23.x, v[k].w - f23.y);
+            if (hx < C::IW) {
               uint2 hv, lv;
-              hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-              lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-              *reinterpret_cast<uint2*>(rhi + k * PPI * 16) = hv;
-              *reinterpret_cast<uint2*>(rhi + C::A_HALF + k * PPI * 16) = lv;
+              split4(v[k], hv, lv);
+              uint8_t* dst = hi + C::slot(hy, hx) * 16;
+              *reinterpret_cast<uint2*>(dst) = hv;
+              *reinterpret_cast<uint2*>(dst + C::A_HALF) = lv;
             }
           }
         }
@@ -383,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
               const uint32_t d = tmem_base + (uint32_t)((sa * 2 + t) * 2 * NT);
-              const uint32_t aoff = (uint32_t)((ky * C::HALO + kx + 8 * t) * 16);
+              const uint32_t aoff = (uint32_t)((C::tap_slot(ky, kx) + 8 * t) * 16);
 #pragma unroll
               for (int s = 0; s < C::KSTEPS; ++s) {
                 const uint64_t bd = smem_desc(bblk + s * 2 * C::LBO_B, C::LBO_B, C::SBO_B);
@@ -403,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   } else {
     // ===================================================================== weight loader (1-D bulk TMA)
     if (lane == 0) {
-      const uint8_t* wb = static_cast<const uint8_t*>(p.weight_bf16);
+      const uint8_t* wb = static_cast<const uint8_t*>(p.weight_f16);
       const uint32_t b0 = smem_u32(b_buf);
       int b_it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -430,9 +392,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   }
 }
 
-// fp32 packed weights [T][cin_pad][cout_pad] -> per (cout tile, unit, tap) bf16 block [2*NT rows][CK] in the
-// canonical K-major interleaved layout [(n/8)][(k/8)][n%8][k%8]; rows 0..NT-1 = hi, NT..2NT-1 = lo.
-__global__ void pack_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int T, int cin, int cin_pad,
+// fp32 packed weights [T][cin_pad][cout_pad] -> per (cout tile, unit, tap) fp16 block [2*NT rows][CK] in the
+// canonical K-major interleaved layout [(n/8)][(k/8)][n%8][k%8]; rows 0..NT-1 = hi, NT..2NT-1 = lo * 2^12.
+__global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict__ out, int T, int cin, int cin_pad,
                                  int cout, int cout_pad, int CK, int NT, int n_units, int n_jt) {
   const int64_t per_block = (int64_t)2 * NT * CK;
   const int64_t total = (int64_t)n_jt * n_units * T * per_block;
@@ -449,8 +411,9 @@ __global__ void pack_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __r
     const int ci = u * CK + k, co = jt * NT + (n2 % NT);
     float v = 0.f;
     if (ci < cin_pad && co < cout_pad && ci < cin && co < cout) v = w[((int64_t)tap * cin_pad + ci) * cout_pad + co];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    out[i] = (n2 < NT) ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    const __half hi = __float2half_rn(v);
+    out[i] = (n2 < NT) ? hi : __float2half_rn((v - __half2float(hi)) * kLoScale);
   }
 }
 
@@ -459,11 +422,28 @@ struct Choice {
 };
 
 static bool choose(const TdvcConvParams& p, Choice* c) {
-  if (p.kh != p.kw || p.stride != 1 || p.pad != p.kh / 2) return false;
-  if (p.post != TDVC_POST_NONE || p.in_square) return false;
+  if (p.kh != p.kw || p.pad != p.kh / 2) return false;
+  if (p.stride == 2) {
+    if (p.cin < 64 || p.cout < 64) return false;
+    if (p.kh == 3) { *c = {3, 16, 64}; return true; }
+    if (p.kh == 1) { *c = {1, 64, 64}; return true; }
+    return false;
+  }
+  if (p.stride != 1) return false;
   if (p.kh == 3) {
+    if (p.cin <= 16) { *c = {3, 16, 64}; return p.cout > 16; }   // image inputs (3 channels padded to 4)
     if (p.cin < 64) return false;
-    *c = {3, 64, 64};
+    *c = {3, 64, p.cout <= 16 ? 16 : 64};
+    return true;
+  }
+  if (p.kh == 1) {
+    if (p.cin < 64 || p.cout < 64) return false;
+    *c = {1, 64, 64};
+    return true;
+  }
+  if (p.kh == 5) {
+    if (p.cin < 32 || p.cout < 64) return false;
+    *c = {5, 32, 64};
     return true;
   }
   if (p.kh == 7) {
@@ -475,12 +455,12 @@ static bool choose(const TdvcConvParams& p, Choice* c) {
   return false;
 }
 
-template <int KS, int CK, int NT>
+template <int KS, int CK, int NT, int S = 1>
 static int launch(const TdvcConvParams& p, cudaStream_t st) {
-  using C = Cfg<KS, CK, NT>;
+  using C = Cfg<KS, CK, NT, S>;
   static bool attr_set = false;  // idempotent; a benign race sets it twice
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, CK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, CK, NT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute(%d bytes) failed: %s", C::SMEM, cudaGetErrorString(e));
       return TDVC_ECUDA;
@@ -492,7 +472,7 @@ static int launch(const TdvcConvParams& p, cudaStream_t st) {
   const int64_t items = (int64_t)p.N * tiles_x * tiles_y * n_jt;
   TDVC_REQUIRE(items < (1ll << 31), "conv_tc: too many work items");
   const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  conv_tc_kernel<KS, CK, NT><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items);
+  conv_tc_kernel<KS, CK, NT, S><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items);
   TDVC_CHECK_LAUNCH("conv_tc");
   return TDVC_OK;
 }
@@ -501,11 +481,11 @@ static int launch(const TdvcConvParams& p, cudaStream_t st) {
 
 int conv2d_tc_supported(const TdvcConvParams& p) {
   tc::Choice c;
-  if (p.weight_bf16 == nullptr) return 0;
+  if (p.weight_f16 == nullptr) return 0;
   if (!tc::choose(p, &c)) return 0;
   for (int s = 0; s < p.n_src; ++s)
     if (p.src_c[s] % 4 != 0 || p.src_ld[s] % 4 != 0) return 0;
-  if ((reinterpret_cast<uintptr_t>(p.weight_bf16) & 15) != 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(p.weight_f16) & 15) != 0) return 0;
   return 1;
 }
 
@@ -515,7 +495,13 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
     set_error("conv_tc: unsupported shape");
     return TDVC_EINVAL;
   }
-  if (c.ks == 3) return tc::launch<3, 64, 64>(p, st);
+  if (p.stride == 2 && c.ks == 3) return tc::launch<3, 16, 64, 2>(p, st);
+  if (p.stride == 2 && c.ks == 1) return tc::launch<1, 64, 64, 2>(p, st);
+  if (c.ks == 3 && c.ck == 64 && c.nt == 64) return tc::launch<3, 64, 64>(p, st);
+  if (c.ks == 3 && c.ck == 64 && c.nt == 16) return tc::launch<3, 64, 16>(p, st);
+  if (c.ks == 3 && c.ck == 16 && c.nt == 64) return tc::launch<3, 16, 64>(p, st);
+  if (c.ks == 1) return tc::launch<1, 64, 64>(p, st);
+  if (c.ks == 5) return tc::launch<5, 32, 64>(p, st);
   if (c.ck == 32 && c.nt == 64) return tc::launch<7, 32, 64>(p, st);
   if (c.ck == 32 && c.nt == 32) return tc::launch<7, 32, 32>(p, st);
   if (c.ck == 32 && c.nt == 16) return tc::launch<7, 32, 16>(p, st);
@@ -536,23 +522,23 @@ int dcn_tc(const TdvcDcnParams&, cudaStream_t) {
 
 using namespace tdvc;
 
-extern "C" size_t tdvc_conv2d_bf16_bytes(const TdvcConvParams* p) {
+extern "C" size_t tdvc_conv2d_f16_bytes(const TdvcConvParams* p) {
   tc::Choice c;
   if (p == nullptr || !tc::choose(*p, &c)) return 0;
   const int n_jt = cdiv(p->cout, c.nt), n_units = cdiv(p->cin, c.ck);
-  return (size_t)n_jt * n_units * c.ks * c.ks * 2 * c.nt * c.ck * sizeof(__nv_bfloat16);
+  return (size_t)n_jt * n_units * c.ks * c.ks * 2 * c.nt * c.ck * sizeof(__half);
 }
 
-extern "C" int tdvc_conv2d_pack_bf16(const TdvcConvParams* p, void* out, void* stream) {
+extern "C" int tdvc_conv2d_pack_f16(const TdvcConvParams* p, void* out, void* stream) {
   tc::Choice c;
-  TDVC_REQUIRE(p && out && p->weight, "conv2d_pack_bf16: null pointer");
-  TDVC_REQUIRE(tc::choose(*p, &c), "conv2d_pack_bf16: shape has no tcgen05 path");
+  TDVC_REQUIRE(p && out && p->weight, "conv2d_pack_f16: null pointer");
+  TDVC_REQUIRE(tc::choose(*p, &c), "conv2d_pack_f16: shape has no tcgen05 path");
   const int n_jt = cdiv(p->cout, c.nt), n_units = cdiv(p->cin, c.ck);
   const int64_t total = (int64_t)n_jt * n_units * c.ks * c.ks * 2 * c.nt * c.ck;
   int grid = cdiv(total, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  tc::pack_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->weight, static_cast<__nv_bfloat16*>(out), c.ks * c.ks, p->cin,
+  tc::pack_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->weight, static_cast<__half*>(out), c.ks * c.ks, p->cin,
                                                              p->cin_pad, p->cout, p->cout_pad, c.ck, c.nt, n_units, n_jt);
-  TDVC_CHECK_LAUNCH("conv2d_pack_bf16");
+  TDVC_CHECK_LAUNCH("conv2d_pack_f16");
   return TDVC_OK;
 }

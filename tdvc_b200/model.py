@@ -323,10 +323,10 @@ def _r(x, m):
 
 # =============================================================================== packed weights
 class ConvW:
-    __slots__ = ("w", "b", "cin", "cin_real", "cin_pad", "cout", "cout_pad", "k", "pad", "shuffle", "w_bf16")
+    __slots__ = ("w", "b", "cin", "cin_real", "cin_pad", "cout", "cout_pad", "k", "pad", "shuffle", "w_f16", "stride")
 
 
-def pack_conv(weight, bias, src_layout=None, shuffle=0, pad=None):
+def pack_conv(weight, bias, src_layout=None, shuffle=0, pad=None, stride=1):
     """(O, I, k, k) conv weight -> implicit-GEMM layout [k*k][cin_pad][cout_pad] fp32 (zero padded).
     src_layout: [(real_channels, stored_channels), ...] per concatenated source (stored >= real, % 4 == 0).
     shuffle=2 folds nn.PixelShuffle(2) into the output-channel order: co' = (dy*2+dx)*(O/4) + c."""
@@ -360,7 +360,8 @@ def pack_conv(weight, bias, src_layout=None, shuffle=0, pad=None):
     cw.cin_real = I
     cw.pad = k // 2 if pad is None else pad
     cw.shuffle = shuffle
-    cw.w_bf16 = None
+    cw.stride = stride   # the tcgen05 weight blocking depends on it (csrc/conv_tc.cu `choose`)
+    cw.w_f16 = None
     return cw
 
 
@@ -399,7 +400,7 @@ class _Packed:
         res("extra_fea.res", m.extra_fea.residual_layer)
         me = m.motion_est
         for nme in ("conv_l2_1", "conv_l2_2", "conv_l3_1", "conv_l3_2", "upsample_conv", "feat_fusion_"):
-            cv("me." + nme, getattr(me, nme))
+            cv("me." + nme, getattr(me, nme), stride=getattr(me, nme).stride[0])
         for lv in ("l3", "l2", "l1"):
             cv(f"me.c11.{lv}", me.offset_conv11[lv], src_layout=[(64, 64), (64, 64)])
             cv(f"me.c11_1.{lv}", me.offset_conv11_1[lv])
@@ -458,18 +459,18 @@ class _Packed:
 
         ga, gs = cd.g_a, cd.g_s
         for i in (0, 2, 5):
-            cv(f"{cn}.ga{i}.conv1", ga[i].conv1)
+            cv(f"{cn}.ga{i}.conv1", ga[i].conv1, stride=2)
             cv(f"{cn}.ga{i}.conv2", ga[i].conv2)
-            cv(f"{cn}.ga{i}.skip", ga[i].skip, pad=0)
+            cv(f"{cn}.ga{i}.skip", ga[i].skip, pad=0, stride=2)
             gdn(f"{cn}.ga{i}.gdn", ga[i].gdn)
         for i in (1, 4, 6):
             cv(f"{cn}.ga{i}.conv1", ga[i].conv1)
             cv(f"{cn}.ga{i}.conv2", ga[i].conv2)
         se(f"{cn}.ga3", ga[3])
-        cv(f"{cn}.ga7", ga[7])
+        cv(f"{cn}.ga7", ga[7], stride=2)
         se(f"{cn}.ga8", ga[8])
         for i in (0, 2, 4, 6, 8):
-            cv(f"{cn}.ha{i}", cd.h_a[i])
+            cv(f"{cn}.ha{i}", cd.h_a[i], stride=cd.h_a[i].stride[0])
         cv(f"{cn}.hs0", cd.h_s[0])
         cv(f"{cn}.hs2", cd.h_s[2][0], shuffle=2)
         cv(f"{cn}.hs4", cd.h_s[4])
@@ -567,6 +568,7 @@ class _Plan:
             p.src_ld[i] = s.ld
             cin += sc
         assert cin == cw.cin, (cin, cw.cin)
+        assert stride == cw.stride, (stride, cw.stride)
         p.n_src = len(srcs)
         p.N, p.H, p.W = s0.N, s0.H, s0.W
         p.Ho = (s0.H + 2 * cw.pad - cw.k) // stride + 1
@@ -590,7 +592,7 @@ class _Plan:
         p.out, p.out_ld = out.ptr, out.ld
         p.shuffle = cw.shuffle
         p.impl = self.impl if impl is None else impl
-        p.weight_bf16 = cw.w_bf16.data_ptr() if cw.w_bf16 is not None else None
+        p.weight_f16 = cw.w_f16.data_ptr() if cw.w_f16 is not None else None
         e0 = self._prof_begin()
         L.check(self.lib.tdvc_conv2d(p, self._st()), "conv2d")
         if e0 is not None:
@@ -746,8 +748,8 @@ class _Plan:
         dp.N, dp.H, dp.W, dp.C, dp.O, dp.O_pad, dp.dg = N, H, Wd, 64, 64, 64, 8
         dp.round_fp16, dp.act, dp.slope = 1, L.ACT_LRELU, 0.1
         dp.impl = self.impl
-        wb = W.get("mc.dcn.w_bf16")
-        dp.weight_bf16 = wb.data_ptr() if wb is not None else None
+        wb = W.get("mc.dcn.w_f16")
+        dp.weight_f16 = wb.data_ptr() if wb is not None else None
         e0 = self._prof_begin()
         L.check(lib.tdvc_dcn_nhwc(dp, self._st()), "dcn_nhwc")
         # algorithmic bytes: ref 256 + offsets 576 + masks 288 + out 256 B/px
@@ -940,7 +942,7 @@ class VideoCompressor(nn.Module):
             with torch.no_grad():
                 pk = _Packed(self)
                 from tdvc_b200 import tc
-                tc.attach_bf16(pk.c)
+                tc.attach_f16(pk.c)
             self._packed[dev] = pk
             self._graphs = {k: v for k, v in self._graphs.items() if k[0] != dev}
         return pk.c

@@ -1,6 +1,6 @@
 """GPU tests (-m gpu): each CUDA kernel, called through the C-ABI, against the oracle / plain torch fp32 on the
 CPU for the same seeded inputs.  Tolerances: fp32 kernels 2e-5 relative to the output scale (different
-summation order only); the tcgen05 3xBF16-split convolution 2e-4 relative (|a_lo*b_lo| and bf16 residual
+summation order only); the tcgen05 3xFP16-split convolution 2e-4 relative (|a_lo*b_lo| and bf16 residual
 rounding, ~2^-16 per product); integer / index outputs bit-exact."""
 import math
 
@@ -41,9 +41,9 @@ def _conv_case(plan, dev, cin_list, cout, k, stride, H, W, N=1, act=0, slope=0.0
     if res:
         want = want + r
     layout = [(c, (c + 3) // 4 * 4) for c in cin_list]
-    cw = pack_conv(conv.weight.to(dev), conv.bias.to(dev), src_layout=layout, shuffle=shuffle, pad=pad)
+    cw = pack_conv(conv.weight.to(dev), conv.bias.to(dev), src_layout=layout, shuffle=shuffle, pad=pad, stride=stride)
     from tdvc_b200 import tc
-    tc.attach_bf16({"w": cw})
+    tc.attach_f16({"w": cw})
     srcs = [Act.from_nchw(x.to(dev), ld=(x.shape[1] + 3) // 4 * 4) for x in xs]
     out = Act.alloc(N, want.shape[2], want.shape[3], want.shape[1], dev, ld=(want.shape[1] + 3) // 4 * 4 if want.shape[1] % 4 else None)
     r1 = Act.from_nchw(r.to(dev)) if res else None
@@ -79,6 +79,39 @@ def test_conv2d_simt_vs_torch(plan, dev, idx):
     assert (got - want).abs().max() <= 2e-5 * max(1.0, want.abs().max().item())
 
 
+TC_CASES = [
+    # shapes with a tcgen05 path (csrc/conv_tc.cu `choose`): cin_list, cout, k, stride, H, W, kwargs
+    ([64], 64, 3, 1, 40, 56, dict(act=1)),
+    ([64], 64, 3, 1, 17, 23, dict(act=2, slope=0.1, res=True)),       # ragged tile edges
+    ([64, 64], 64, 3, 1, 33, 16, dict()),                              # two K units from two sources
+    ([128], 128, 3, 1, 24, 24, dict(act=2, slope=0.01)),              # two cout tiles
+    ([128], 512, 3, 1, 8, 12, dict(shuffle=2, act=2, slope=0.01)),    # PixelShuffle store
+    ([64], 216, 3, 1, 16, 16, dict()),                                 # cout not a multiple of the tile
+    ([3], 64, 3, 1, 20, 36, dict(N=2, act=2, slope=0.1)),             # image input (CK=16)
+    ([64], 3, 3, 1, 16, 40, dict()),                                   # featdown (NT=16)
+    ([128], 128, 1, 1, 19, 21, dict(pad=0)),                           # 1x1
+    ([64, 64, 64, 64], 64, 1, 1, 16, 16, dict(pad=0, act=2, slope=0.1)),  # 1x1 fusion over 4 sources
+    ([256, 256], 426, 1, 1, 8, 8, dict(pad=0)),                        # entropy_parameters[0]
+    ([428], 341, 1, 1, 8, 8, dict(pad=0)),                             # entropy_parameters[2] (cin % 64 != 0)
+    ([128], 256, 5, 1, 16, 16, dict()),                                # context model 5x5
+    ([8], 32, 7, 1, 16, 24, dict(act=1)),                              # SPyNet 7x7
+    ([16], 2, 7, 1, 16, 16, dict(res=True)),
+    ([32], 64, 7, 1, 32, 16, dict(act=1)),
+    ([64], 128, 3, 2, 32, 48, dict(act=2, slope=0.01)),               # stride 2
+    ([128], 128, 3, 2, 18, 30, dict(N=2)),
+    ([64], 128, 1, 2, 32, 32, dict(pad=0)),                            # 1x1 stride-2 skip
+]
+
+
+@pytest.mark.parametrize("idx", range(len(TC_CASES)))
+def test_conv2d_tcgen05_vs_torch(plan, dev, idx):
+    """impl=2 forces the tensor-core kernel (3xFP16 split, fp32 accumulate): 2e-4 of the output scale."""
+    cin_list, cout, k, stride, H, W, kw = TC_CASES[idx]
+    got, want = _conv_case(plan, dev, cin_list, cout, k, stride, H, W, impl=2, seed=100 + idx, **kw)
+    assert got.shape == want.shape
+    assert (got - want).abs().max() <= 2e-4 * max(1.0, want.abs().max().item())
+
+
 def test_conv2d_rejects_bad_arguments(plan, dev):
     from tdvc_b200 import lib as L
     p = L.ConvParams()
@@ -104,9 +137,12 @@ def test_gdn_as_fused_conv(plan, dev):
         xa = Act.from_nchw(x.to(dev))
         out = Act.alloc(1, 9, 11, 128, dev)
         from tdvc_b200 import lib as L
-        plan.conv([xa], cw, out, in_square=True, post=L.POST_IGDN if inverse else L.POST_GDN, mul=xa,
-                  res1=Act.from_nchw(idt.to(dev)), impl=1)
-        assert (out.nchw().cpu() - want).abs().max() < 2e-5 * want.abs().max()
+        from tdvc_b200 import tc
+        tc.attach_f16({"w": cw})
+        for impl, tol in ((1, 2e-5), (2, 1e-4)):
+            plan.conv([xa], cw, out, in_square=True, post=L.POST_IGDN if inverse else L.POST_GDN, mul=xa,
+                      res1=Act.from_nchw(idt.to(dev)), impl=impl)
+            assert (out.nchw().cpu() - want).abs().max() < tol * want.abs().max(), impl
 
 
 # ------------------------------------------------------------------------------------------------ DCN

@@ -13,8 +13,8 @@ def case(plan, dev, cin_list, cout, k, H, W, N=1, act=0, slope=0.0, shuffle=0, r
     conv = torch.nn.Conv2d(cin, cout, k, 1, k // 2).to(dev)
     xs = [torch.randn(N, c, H, W, device=dev) for c in cin_list]
     cw = pack_conv(conv.weight, conv.bias, src_layout=[(c, (c + 3) // 4 * 4) for c in cin_list], shuffle=shuffle)
-    tc.attach_bf16({"w": cw})
-    assert cw.w_bf16 is not None, "no tc path"
+    tc.attach_f16({"w": cw})
+    assert cw.w_f16 is not None, "no tc path"
     srcs = [Act.from_nchw(x, ld=(x.shape[1] + 3) // 4 * 4) for x in xs]
     sh = 2 if shuffle == 2 else 1
     oc = cout // 4 if shuffle == 2 else cout
