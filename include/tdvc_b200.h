@@ -71,6 +71,8 @@ typedef struct {
   int32_t impl;
   const void* weight_f16;  /* tcgen05 path: fp16 (hi | lo*2^12) weight blocks built by tdvc_conv2d_pack_f16, or NULL */
   float* chan_sum;          /* optional [N][gridDim-dependent] — reserved for fused SE partial sums */
+  int32_t out_planar;       /* 1: store NCHW planes, out[((n*cout + c)*Ho + y)*Wo + x] (no shuffle / residual / post);
+                               the DCN offset/mask head writes the reference's planar offset & mask tensors this way */
 } TdvcConvParams;
 int tdvc_conv2d(const TdvcConvParams* p, void* stream);
 /* tcgen05 path: size of / builder for the fp16 (hi, lo) weight blocks of a convolution, from its fp32 packed
@@ -107,9 +109,19 @@ typedef struct {
   int32_t round_fp16;
   int32_t act; float slope;
   int32_t impl;                           /* 0 = auto, 1 = SIMT fp32 contraction, 2 = tcgen05 (3xFP16 split) */
-  const void* weight_f16;                /* tcgen05 path: packed hi/lo fp16 weights (see dcn_tc.cu), or NULL */
+  const void* weight_f16;                 /* tcgen05 path: tdvc_dcn_pack_f16 output, or NULL */
+  /* tcgen05 path (csrc/dcn_tc.cu) reads gather-friendly layouts instead of `input` / channels-last offsets:   */
+  const float* input_gp;                  /* "group planar" input [(n*dg + g)][H][W][8] (tdvc_nhwc_to_group_planar) */
+  int32_t params_planar;                  /* 1: offset / mask are NCHW planes as in the reference (dcn_v2.h:9-46):
+                                             offset plane g*18 + 2*tap (+1), mask plane g*9 + tap, H*W floats each;
+                                             off_ld / mask_ld then count the PLANES per image of the tensor they live in */
 } TdvcDcnParams;
 int tdvc_dcn_nhwc(const TdvcDcnParams* p, void* stream);
+/* tcgen05 DCN: fp16 (hi | lo*2^12) weight blocks from weight_packed ([C*9][O_pad] fp32); O <= 64, 8 channels per group */
+size_t tdvc_dcn_f16_bytes(int dg);
+int tdvc_dcn_pack_f16(const float* weight_packed, int O, int O_pad, int dg, void* out, void* stream);
+/* NHWC (src_ld floats per pixel, C % 8 == 0) -> [(n*C/8 + g)][H][W][8]: one 32-byte sector per (pixel, group) */
+int tdvc_nhwc_to_group_planar(const float* src, int src_ld, float* dst, int N, int H, int W, int C, void* stream);
 
 /* ---- layout ---- */
 int tdvc_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int dst_ld, void* stream); /* pads c>=C with 0 */

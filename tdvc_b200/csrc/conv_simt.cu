@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_simt_kernel(const TdvcConvP
       if (co >= p.cout) continue;
       const OutLoc l = out_loc(p, n, oy, ox, co);
       float v = acc[i][j] + (p.bias ? __ldg(p.bias + co) : 0.f);
-      p.out[l.pix * p.out_ld + l.c] = epilogue1(p, v, l);
+      if (p.out_planar) p.out[(((int64_t)n * p.cout + co) * p.Ho + oy) * p.Wo + ox] = apply_act(v, p.act, p.slope);
+      else p.out[l.pix * p.out_ld + l.c] = epilogue1(p, v, l);
     }
   }
 }
@@ -217,6 +218,7 @@ static int launch_simt(const TdvcConvParams& p, cudaStream_t st) {
   const int tiles_x = cdiv(p.Wo, TX), tiles_y = cdiv(p.Ho, TY);
   dim3 grid(tiles_x * tiles_y, p.cout_pad / TN, p.N);
   int vec_ok = (p.out_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+  if (p.out_planar) vec_ok = 0;
   if (p.shuffle == 2) vec_ok = vec_ok && ((p.cout >> 2) % 4 == 0);
   else vec_ok = vec_ok && (p.cout % 4 == 0);
   if (p.post != TDVC_POST_NONE) vec_ok = vec_ok && (p.mul_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.mul) & 15) == 0);
@@ -257,6 +259,8 @@ int conv2d_validate(const TdvcConvParams* p) {
                "conv2d: Ho/Wo (%d,%d) inconsistent", p->Ho, p->Wo);
   TDVC_REQUIRE(p->shuffle == 0 || (p->shuffle == 2 && p->cout % 4 == 0), "conv2d: shuffle %d", p->shuffle);
   TDVC_REQUIRE(p->post == TDVC_POST_NONE || p->mul != nullptr, "conv2d: post needs mul");
+  TDVC_REQUIRE(p->out_planar == 0 || (p->shuffle == 0 && p->post == TDVC_POST_NONE && !p->res1 && !p->res2),
+               "conv2d: out_planar excludes shuffle / post / residual");
   TDVC_REQUIRE(p->N <= 65535 && p->cout_pad / 16 <= 65535, "conv2d: grid too large");
   return TDVC_OK;
 }

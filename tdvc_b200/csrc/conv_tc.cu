@@ -163,7 +163,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         float v[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] = fmaf(__uint_as_float(rb[j]), kLoUnscale, __uint_as_float(ra[j]));
-        if (vec_ok && co0 + CH <= p.cout) {
+        if (p.out_planar) {  // NCHW planes: 8 x-adjacent pixels of a row = one 32-byte sector per channel
+          const int64_t plane = (int64_t)p.Ho * p.Wo;
+          float* op = p.out + ((int64_t)it.n * p.cout + co0) * plane + (int64_t)y * p.Wo + x;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            if (co0 + j < p.cout) op[j * plane] = apply_act(v[j] + (p.bias ? __ldg(p.bias + co0 + j) : 0.f), p.act, p.slope);
+          }
+        } else if (vec_ok && co0 + CH <= p.cout) {
           int64_t opix;
           int oc;
           if (p.shuffle == 2) {  // PixelShuffle(2) folded into the store: co' = q*(cout/4) + c
@@ -509,12 +516,6 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
   if (c.ck == 16 && c.nt == 16) return tc::launch<7, 16, 16>(p, st);
   if (c.ck == 16 && c.nt == 64) return tc::launch<7, 16, 64>(p, st);
   set_error("conv_tc: no instantiation for ks=%d ck=%d nt=%d", c.ks, c.ck, c.nt);
-  return TDVC_EINVAL;
-}
-
-int dcn_tc_supported(const TdvcDcnParams&) { return 0; }
-int dcn_tc(const TdvcDcnParams&, cudaStream_t) {
-  set_error("tcgen05 dcn not built");
   return TDVC_EINVAL;
 }
 

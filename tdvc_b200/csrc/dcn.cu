@@ -250,17 +250,24 @@ int dcn_tc(const TdvcDcnParams& p, cudaStream_t st);
 using namespace tdvc;
 
 extern "C" int tdvc_dcn_nhwc(const TdvcDcnParams* p, void* stream) {
-  TDVC_REQUIRE(p && p->input && p->offset && p->mask && p->weight_packed && p->out, "dcn_nhwc: null pointer");
+  TDVC_REQUIRE(p && (p->input || p->input_gp) && p->offset && p->mask && p->weight_packed && p->out, "dcn_nhwc: null pointer");
   TDVC_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0 && p->dg > 0, "dcn_nhwc: empty input");
   TDVC_REQUIRE(p->C == 8 * p->dg, "dcn_nhwc: needs 8 channels per deformable group (C=%d dg=%d)", p->C, p->dg);
   TDVC_REQUIRE(p->O > 0 && p->O_pad % 64 == 0 && p->O_pad >= p->O, "dcn_nhwc: O=%d O_pad=%d", p->O, p->O_pad);
+  TDVC_REQUIRE(p->params_planar == 0 || p->params_planar == 1, "dcn_nhwc: params_planar %d", p->params_planar);
+  if (p->params_planar) {  // gather-friendly layouts: tensor-core kernel only
+    TDVC_REQUIRE(p->impl != 1, "dcn_nhwc: planar offsets / group-planar input need the tcgen05 kernel (impl 0 or 2)");
+    TDVC_REQUIRE(dcn_tc_supported(*p), "dcn_nhwc: tcgen05 kernel needs input_gp (32-byte aligned), weight_f16, O <= 64");
+    TDVC_REQUIRE(p->off_ld >= 18 * p->dg && p->mask_ld >= 9 * p->dg, "dcn_nhwc: plane counts off_ld=%d mask_ld=%d", p->off_ld, p->mask_ld);
+    return dcn_tc(*p, reinterpret_cast<cudaStream_t>(stream));
+  }
+  TDVC_REQUIRE(p->input != nullptr, "dcn_nhwc: channels-last offsets need the channels-last input");
   TDVC_REQUIRE(p->in_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(p->input) & 15) == 0, "dcn_nhwc: input alignment");
   TDVC_REQUIRE((reinterpret_cast<uintptr_t>(p->weight_packed) & 15) == 0, "dcn_nhwc: weight alignment");
   TDVC_REQUIRE((reinterpret_cast<uintptr_t>(p->out) & 15) == 0 || p->out_ld % 4 != 0, "dcn_nhwc: out alignment");
   TDVC_REQUIRE((int64_t)cdiv(p->W, DCN_TP) * cdiv(p->H, DCN_TP) * p->N < (1ll << 31), "dcn_nhwc: grid too large");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (p->impl != 1 && dcn_tc_supported(*p)) return dcn_tc(*p, st);
-  TDVC_REQUIRE(p->impl != 2, "dcn_nhwc: impl=2 (tcgen05) does not support this shape");
+  TDVC_REQUIRE(p->impl != 2, "dcn_nhwc: impl=2 (tcgen05) needs params_planar = 1 and input_gp");
   return dcn_nhwc_launch(*p, st);
 }
 

@@ -26,7 +26,8 @@ class ConvParams(C.Structure):
                 ("in_square", C.c_int32), ("act", C.c_int32), ("slope", C.c_float), ("post", C.c_int32),
                 ("mul", c_fp), ("mul_ld", C.c_int32), ("res1", c_fp), ("res1_ld", C.c_int32),
                 ("res2", c_fp), ("res2_ld", C.c_int32), ("out", c_fp), ("out_ld", C.c_int32),
-                ("shuffle", C.c_int32), ("impl", C.c_int32), ("weight_f16", c_fp), ("chan_sum", c_fp)]
+                ("shuffle", C.c_int32), ("impl", C.c_int32), ("weight_f16", c_fp), ("chan_sum", c_fp),
+                ("out_planar", C.c_int32)]
 
 
 class DcnParams(C.Structure):
@@ -35,7 +36,8 @@ class DcnParams(C.Structure):
                 ("weight_packed", c_fp), ("bias", c_fp), ("out", c_fp), ("out_ld", C.c_int32),
                 ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("O", C.c_int32),
                 ("O_pad", C.c_int32), ("dg", C.c_int32), ("round_fp16", C.c_int32), ("act", C.c_int32),
-                ("slope", C.c_float), ("impl", C.c_int32), ("weight_f16", c_fp)]
+                ("slope", C.c_float), ("impl", C.c_int32), ("weight_f16", c_fp), ("input_gp", c_fp),
+                ("params_planar", C.c_int32)]
 
 
 i32, i64, f32, vp, sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
@@ -50,6 +52,9 @@ SIGNATURES = {
     "tdvc_dcn_v2_workspace_bytes": [i32] * 6,
     "tdvc_dcn_v2_forward": [vp] * 6 + [i32] * 14 + [vp, sz, vp],
     "tdvc_dcn_nhwc": [C.POINTER(DcnParams), vp],
+    "tdvc_dcn_f16_bytes": [i32],
+    "tdvc_dcn_pack_f16": [vp, i32, i32, i32, vp, vp],
+    "tdvc_nhwc_to_group_planar": [vp, i32, vp, i32, i32, i32, i32, vp],
     "tdvc_nchw_to_nhwc": [vp, vp, i32, i32, i32, i32, i32, vp],
     "tdvc_nhwc_to_nchw": [vp, i32, vp, i32, i32, i32, i32, vp],
     "tdvc_avgpool2x2": [vp, vp, i32, i32, i32, i32, vp],
@@ -89,6 +94,7 @@ def load():
     lib.tdvc_last_error.restype = C.c_char_p
     lib.tdvc_dcn_v2_workspace_bytes.restype = C.c_size_t
     lib.tdvc_conv2d_f16_bytes.restype = C.c_size_t
+    lib.tdvc_dcn_f16_bytes.restype = C.c_size_t
     _lib = lib
     return lib
 
