@@ -556,7 +556,8 @@ class _Plan:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def conv(self, srcs, cw, out, stride=1, act=L.ACT_NONE, slope=0.0, res1=None, res2=None, post=L.POST_NONE,
-             mul=None, in_square=False, impl=None):
+             mul=None, in_square=False, impl=None, planar=False):
+        """planar=True: `out` is a plain (N, cout, Ho, Wo) tensor written as NCHW planes (no shuffle / residual)."""
         p = L.ConvParams()
         s0 = srcs[0]
         cin = 0
@@ -574,8 +575,11 @@ class _Plan:
         p.Ho = (s0.H + 2 * cw.pad - cw.k) // stride + 1
         p.Wo = (s0.W + 2 * cw.pad - cw.k) // stride + 1
         sh = 2 if cw.shuffle == 2 else 1
-        assert (out.N, out.H, out.W) == (s0.N, p.Ho * sh, p.Wo * sh), ((out.N, out.H, out.W), (p.Ho, p.Wo, sh))
-        assert out.C == (cw.cout // 4 if cw.shuffle == 2 else cw.cout)
+        if planar:
+            assert tuple(out.shape) == (s0.N, cw.cout, p.Ho, p.Wo) and out.is_contiguous() and sh == 1
+        else:
+            assert (out.N, out.H, out.W) == (s0.N, p.Ho * sh, p.Wo * sh), ((out.N, out.H, out.W), (p.Ho, p.Wo, sh))
+            assert out.C == (cw.cout // 4 if cw.shuffle == 2 else cw.cout)
         p.weight = cw.w.data_ptr()
         p.bias = cw.b.data_ptr() if cw.b is not None else None
         p.cin, p.cin_pad, p.cout, p.cout_pad = cw.cin, cw.cin_pad, cw.cout, cw.cout_pad
@@ -589,7 +593,10 @@ class _Plan:
             p.res1, p.res1_ld = res1.ptr, res1.ld
         if res2 is not None:
             p.res2, p.res2_ld = res2.ptr, res2.ld
-        p.out, p.out_ld = out.ptr, out.ld
+        if planar:
+            p.out, p.out_ld, p.out_planar = out.data_ptr(), 0, 1
+        else:
+            p.out, p.out_ld = out.ptr, out.ld
         p.shuffle = cw.shuffle
         p.impl = self.impl if impl is None else impl
         p.weight_f16 = cw.w_f16.data_ptr() if cw.w_f16 is not None else None
@@ -737,23 +744,38 @@ class _Plan:
         # ---- motion coder (pnet.py:34-43)
         mv_xhat = self.coder(W, "mv", estmv, 0, taps)
         # ---- motion compensation (pnet.py:52, 179-184; dcn_v2_amp.py:219-234)
-        om = self.conv([mv_xhat], W["mc.offmask"], self.buf("mc.om", N, H, Wd, 216, ld=216))
         dcn_out = self.buf("mc.dcn", N, H, Wd, 64)
         dp = L.DcnParams()
-        dp.input, dp.in_ld = ref_f.ptr, ref_f.ld
-        dp.offset, dp.off_ld = om.ptr, om.ld
-        dp.mask, dp.mask_ld, dp.mask_is_logit = om.chan(144, 72).ptr, om.ld, 1
+        wb = W.get("mc.dcn.w_f16")
+        tc_dcn = self.impl != L.IMPL_SIMT and wb is not None
+        if tc_dcn:
+            # tcgen05 DCN (csrc/dcn_tc.cu): offsets / mask as NCHW planes straight from the offset conv's epilogue,
+            # reference features regrouped to one 32-byte sector per (pixel, deformable group)
+            om = self.raw("mc.om_planar", (N, 216, H, Wd))
+            self.conv([mv_xhat], W["mc.offmask"], om, planar=True)
+            ref_gp = self.raw("mc.ref_gp", (N * 8, H, Wd, 8))
+            self.call("tdvc_nhwc_to_group_planar", ref_f.ptr, ref_f.ld, ref_gp.data_ptr(), N, H, Wd, 64,
+                      nbytes=N * H * Wd * 512)
+            dp.input_gp, dp.params_planar = ref_gp.data_ptr(), 1
+            dp.offset, dp.off_ld = om.data_ptr(), 216
+            dp.mask, dp.mask_ld, dp.mask_is_logit = om.data_ptr() + 4 * 144 * H * Wd, 216, 1
+            dp.weight_f16 = wb.data_ptr()
+            om_nchw = om
+        else:
+            om = self.conv([mv_xhat], W["mc.offmask"], self.buf("mc.om", N, H, Wd, 216, ld=216))
+            dp.input, dp.in_ld = ref_f.ptr, ref_f.ld
+            dp.offset, dp.off_ld = om.ptr, om.ld
+            dp.mask, dp.mask_ld, dp.mask_is_logit = om.chan(144, 72).ptr, om.ld, 1
+            om_nchw = None
         dp.weight_packed, dp.bias = W["mc.dcn.w"].data_ptr(), W["mc.dcn.b"].data_ptr()
         dp.out, dp.out_ld = dcn_out.ptr, dcn_out.ld
         dp.N, dp.H, dp.W, dp.C, dp.O, dp.O_pad, dp.dg = N, H, Wd, 64, 64, 64, 8
         dp.round_fp16, dp.act, dp.slope = 1, L.ACT_LRELU, 0.1
         dp.impl = self.impl
-        wb = W.get("mc.dcn.w_f16")
-        dp.weight_f16 = wb.data_ptr() if wb is not None else None
         e0 = self._prof_begin()
         L.check(lib.tdvc_dcn_nhwc(dp, self._st()), "dcn_nhwc")
         # algorithmic bytes: ref 256 + offsets 576 + masks 288 + out 256 B/px
-        self._prof_end(e0, "dcn_nhwc", macs=N * H * Wd * 576 * 64, nbytes=N * H * Wd * 1376)
+        self._prof_end(e0, "dcn_tc" if tc_dcn else "dcn_nhwc", macs=N * H * Wd * 576 * 64, nbytes=N * H * Wd * 1376)
         self.launches += 1
         o2 = self.conv([dcn_out, ref_f], W["mc.conv"], self.buf("mc.o2", N, H, Wd, 64), **lr1)
         t4 = self.buf("mf.t4", 4 * N, H, Wd, 64)  # per n: [x^(t-3), x^(t-2), x^(t-1) features, prediction1]
@@ -773,7 +795,7 @@ class _Plan:
         bpp = self.acc.view(2, 2).sum(1) / (-_LN2 * N * H * Wd)
         if taps is not None:
             taps.update({"input_feat": in_f.nchw(), "ref_feat": ref_f.nchw(), "estmv": estmv.nchw(),
-                         "mv.x_hat": mv_xhat.nchw(), "mcnet.om": om.nchw(), "mcnet.dcn_act": dcn_out.nchw(),
+                         "mv.x_hat": mv_xhat.nchw(), "mcnet.om": om_nchw.clone() if om_nchw is not None else om.nchw(), "mcnet.dcn_act": dcn_out.nchw(),
                          "prediction1": pred1.nchw(), "prediction": pred.nchw(), "input_residual": resid.nchw(),
                          "recon_feat": rec_f.nchw()})
         return recon, bpp
@@ -943,6 +965,7 @@ class VideoCompressor(nn.Module):
                 pk = _Packed(self)
                 from tdvc_b200 import tc
                 tc.attach_f16(pk.c)
+                tc.attach_dcn_f16(pk.c, "mc.dcn.w", 64, 8)
             self._packed[dev] = pk
             self._graphs = {k: v for k, v in self._graphs.items() if k[0] != dev}
         return pk.c

@@ -25,3 +25,17 @@ def attach_f16(packed):
                     "conv2d_pack_f16")
         cw.w_f16 = buf
     return packed
+
+
+def attach_dcn_f16(packed, key, O, dg):
+    """fp16 (hi | lo) weight blocks of the tcgen05 DCN (csrc/dcn_tc.cu) from packed[key] ([C*9][O_pad] fp32)."""
+    lib = L.load()
+    w = packed[key]
+    if not w.is_cuda:
+        return packed
+    with torch.cuda.device(w.device):
+        buf = torch.empty(lib.tdvc_dcn_f16_bytes(dg), device=w.device, dtype=torch.uint8)
+        L.check(lib.tdvc_dcn_pack_f16(w.data_ptr(), O, w.shape[1], dg, buf.data_ptr(),
+                                      torch.cuda.current_stream(w.device).cuda_stream), "dcn_pack_f16")
+    packed[key + "_f16"] = buf
+    return packed

@@ -179,6 +179,59 @@ def test_dcn_forward_vs_oracle(dev, shape):
     assert (got - want).abs().max() < 2e-5 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("shape", [(1, 21, 30, 64), (2, 16, 48, 64), (1, 40, 33, 37)])
+def test_dcn_tcgen05_vs_oracle(dev, shape):
+    """csrc/dcn_tc.cu (gather producers + tcgen05 contraction, group-planar input, planar offsets / mask logits)
+    against the oracle restatement, including the reference's fp16 rounding of the result
+    (dcn_v2_amp.py:67-69) and the LeakyReLU evaluated on the Half tensor (pnet.py:180).  Tolerance: the 3xFP16
+    split keeps ~2^-22 per product; after the fp16 rounding at most one fp16 ulp may differ
+    where the fp32 value sits on a rounding boundary."""
+    from oracle import dcn_naive
+    from tdvc_b200 import lib as L, tc
+    from tdvc_b200.model import Act
+    N, H, W, O = shape
+    C, dg = 64, 8
+    torch.manual_seed(11)
+    x = torch.randn(N, C, H, W)
+    wgt = torch.randn(O, C, 3, 3) * 0.1
+    b = torch.randn(O)
+    off = torch.randn(N, dg * 18, H, W) * 3.0
+    logit = torch.randn(N, dg * 9, H, W)
+    exact = dcn_naive.dcn_v2_forward(x, wgt, b, off, torch.sigmoid(logit), dg)
+    want = F.leaky_relu(exact.half(), 0.1).float()
+    lib = L.load()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    opad = 64
+    pk = torch.zeros(C * 9, opad, device=dev)
+    pk[:, :O] = wgt.reshape(O, C * 9).t().to(dev)
+    packed = tc.attach_dcn_f16({"w": pk.contiguous()}, "w", O, dg)
+    xa = Act.from_nchw(x.to(dev))
+    gp = torch.empty(N * dg, H, W, 8, device=dev)
+    L.check(lib.tdvc_nhwc_to_group_planar(xa.ptr, xa.ld, gp.data_ptr(), N, H, W, C, st), "gp")
+    assert torch.equal(gp.view(N, dg, H, W, 8), x.to(dev).view(N, dg, 8, H, W).permute(0, 1, 3, 4, 2))
+    om = torch.cat([off, logit], 1).contiguous().to(dev)       # (N, 216, H, W) as the offset conv writes it
+    out = Act.alloc(N, H, W, O, dev, ld=(O + 7) // 8 * 8)
+    for round_fp16 in (0, 1):
+        dp = L.DcnParams()
+        dp.input_gp, dp.params_planar = gp.data_ptr(), 1
+        dp.offset, dp.off_ld = om.data_ptr(), 27 * dg
+        dp.mask, dp.mask_ld, dp.mask_is_logit = om.data_ptr() + 4 * 18 * dg * H * W, 27 * dg, 1
+        bd = b.to(dev)
+        dp.weight_packed, dp.bias, dp.weight_f16 = packed["w"].data_ptr(), bd.data_ptr(), packed["w_f16"].data_ptr()
+        dp.out, dp.out_ld = out.ptr, out.ld
+        dp.N, dp.H, dp.W, dp.C, dp.O, dp.O_pad, dp.dg = N, H, W, C, O, opad, dg
+        dp.round_fp16, dp.act, dp.slope, dp.impl = round_fp16, (L.ACT_LRELU if round_fp16 else L.ACT_NONE), 0.1, 2
+        L.check(lib.tdvc_dcn_nhwc(dp, st), "dcn_tc")
+        torch.cuda.synchronize()
+        got = out.nchw().cpu()
+        if round_fp16:
+            diff = (got - want).abs()
+            assert (diff <= 2.0 ** -9 * want.abs() + 1e-7).all()   # one fp16 ulp in, re-rounded after the 0.1 slope
+            assert (diff > 0).float().mean() < 2e-3          # only fp16 rounding-boundary cases may differ
+        else:
+            assert (got - exact).abs().max() < 2e-5 * max(1.0, exact.abs().max().item())
+
+
 def test_dcn_generic_geometry_vs_torchvision(dev):
     """Outside the TDVC configuration (stride 2, 5x3 kernel, dilation) the `_ext` drop-in still answers."""
     import torchvision.ops
