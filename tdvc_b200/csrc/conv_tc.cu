@@ -1,32 +1,39 @@
 // Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM) for the
-// dense KxK stride-1 convolutions of the P-frame graph (reference main/model/pnet.py passim,
-// main/utils/utils.py:43-56, main/model/flownet.py:187-227, compressai blocks of SURVEY.md App. A).
+// dense KxK convolutions of the P-frame graph (reference main/model/pnet.py passim, main/utils/utils.py:43-56,
+// main/model/flownet.py:187-227, compressai blocks of SURVEY.md App. A).
 //
-// Numerics: activations and weights stay fp32 in HBM.  Each operand is split on the fly into two fp16 terms
+// Numerics: activations and weights stay fp32 in HBM.  Each operand is split into two fp16 terms
 // (x = x_hi + x_lo, x_hi = fp16(x), x_lo = fp16(x - x_hi): 22 significand bits) and the product is evaluated as
-// x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with fp32 accumulation in TMEM ("3xFP16"): relative error per product ~2^-22,
-// i.e. the fp32-class accuracy the parity bar needs (>= 99.9 % identical quantised symbols), at 3 MMA passes.
-// w_lo is stored scaled by 2^12 (kept out of the fp16 subnormal range; its accumulator columns are rescaled by
-// 2^-12 in the epilogue - both exact).  fp16 range: |x| is saturated to 65504 on conversion (cvt.satfinite);
-// activations of an image codec with [0,1] inputs sit orders of magnitude below that.
+// (w_hi + w_lo) * (x_hi + x_lo) with fp32 accumulation in TMEM: relative error per product ~2^-22, i.e. the
+// fp32-class accuracy the parity bar needs (>= 99.9 % identical quantised symbols).  w_lo is stored scaled by 2^12
+// (kept out of the fp16 subnormal range; its accumulator rows are rescaled by 2^-12 in the epilogue - both exact).
+// fp16 range: |x| is saturated to 65504 on conversion (cvt.satfinite); activations of an image codec with [0,1]
+// inputs sit orders of magnitude below that.
+//
+// Operand roles (tools/mma_probe.cu, profiles/r01_mma_probe.txt): with the pixels on the M side every tcgen05.mma
+// of N <= 128 costs >= 88 cycles (the 128-row operand fetch is not hidden), 352 cycles per 256 px * 16 k.  Here the
+// WEIGHTS are the M-side operand - 128 rows = 64 output channels x (hi, lo) - and 256 PIXELS are the N side: two
+// MMAs (x_hi, x_lo) per k-step run at the math floor (259 cycles measured, floor 256).
 //
 // Work decomposition (persistent, one CTA per SM, 576 threads = 18 warps):
-//   work item  = 16x16 output pixels ("super tile" = two 8-wide x 16-tall MMA tiles, M = 128 each) x NT output
-//                channels;  K loop = cin chunks of CK channels ("units") x KS*KS taps x CK/16 MMA k-steps.
-//   warps 8-15 producers (one halo row per warp at a time): read the (16+KS-1)^2 fp32 halo of one unit from global (float4, coalesced 256 B per
-//              pixel), split into fp16 hi / lo and store it to shared memory in the tcgen05 K-major
-//              "interleaved" (no-swizzle) canonical layout: [channel/8][halo pixel][8 channels] — 8 x-adjacent
-//              pixels form one 8x16 B core matrix, so every tap of the convolution is the SAME buffer read
-//              through a descriptor whose start address is shifted by (ky*HALO_W + kx)*16 B.  No im2col copy.
-//   warp 17    streams pre-packed fp16 weight blocks [2*NT rows = w_hi | w_lo][CK] (one per unit x tap)
-//              with cp.async.bulk (1-D TMA) into a 3-4 stage ring, completion on mbarriers.
-//   warp 16    one elected thread issues, per k-step and MMA tile:
-//                 D[:, 0:2NT] (+)= A_hi (128x16) * [W_hi | W_lo]^T      (N = 2*NT)
-//                 D[:, 0:NT ]  += A_lo (128x16) *  W_hi^T               (N = NT)
-//              and tcgen05.commit's the ring slots back to the producers.
-//   warps 0-7  epilogue (TMEM lane quadrant x MMA tile): tcgen05.ld the accumulator (lane = pixel), add the hi*hi+lo*hi and hi*lo halves, bias,
-//              activation, up to two residual adds, optional PixelShuffle(2) store; overlaps the next item's MMAs
-//              (two accumulator stages in TMEM: 8*NT columns).
+//   work item  = 8 x 32 output pixels (N = 256; pixel p = ty*8 + tx) x 64 output channels;
+//                K loop = cin chunks of CK channels ("units") x KS*KS taps x CK/16 MMA k-steps.
+//   warps 8-15 producers: read the fp32 halo of one unit from global (float4 per lane, 16*CK/4 B contiguous per
+//              pixel, all loads of a batch in flight), split into fp16 hi / lo and store it to shared memory in the
+//              tcgen05 K-major no-swizzle canonical layout [channel/8][halo pixel][8 channels]: 8 x-adjacent pixels
+//              form one 8x16 B core matrix and the 32 tile rows are 32 row groups (SBO = halo pitch), so every tap of
+//              the convolution is the SAME buffer read through a descriptor whose start address is shifted by
+//              (ky*pitch + kx)*16 B.  No im2col copy.  Stride 2: the halo is de-interleaved into 4 parity planes.
+//   warp 17    streams pre-packed fp16 weight blocks [128 rows][CK] (one per unit x tap) with cp.async.bulk
+//              (1-D TMA) into a ring, completion on mbarriers.
+//   warp 16    one elected thread issues per k-step  D[128][256] += W * X_hi^T ; D += W * X_lo^T
+//              and tcgen05.commit's the ring slots back to the producers / loader.
+//   warps 0-7  epilogue.  TMEM lane = weight row: lane quadrants 0 / 2 hold the hi rows of output channels 0-31 /
+//              32-63, quadrants 1 / 3 the matching lo rows.  A lo warp reads its rows (tcgen05.ld, 32 pixels per
+//              chunk), rescales and hands them to its hi partner through a double-buffered shared-memory slab
+//              (named barrier per pair); the hi warp adds, applies bias / GDN / activation / residuals and stores:
+//              lane = channel, so each store instruction writes 128 contiguous bytes of one NHWC pixel.
+//              Overlaps the next item's MMAs (two accumulator stages = all 512 TMEM columns).
 #include "tc_common.cuh"
 
 namespace tdvc {
@@ -37,46 +44,53 @@ constexpr int kEpiWarps = 8, kProdWarps = 8;                 // 2 of each per SM
 constexpr int kMmaWarp = kEpiWarps + kProdWarps, kLoadWarp = kMmaWarp + 1;
 constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 576
 constexpr int kProdThreads = kProdWarps * 32;
-constexpr int kTile = 16;  // super-tile edge (pixels)
+constexpr int TW = 8, TH = 32, NPX = TW * TH;  // output tile = N of one MMA
+constexpr int NT = 64;                         // output channels per item (M = 2*NT rows: hi, lo)
+constexpr int kStageBytes = 2 * 2 * 16 * 128 * 4;  // epilogue transposition: 2 pixel halves x 2 buffers x [16 px][128 rows] fp32
 
-template <int KS, int CK, int NT, int S>
+template <int KS, int CK, int S>
 struct Cfg {
   static_assert(S == 1 || (S == 2 && (KS == 1 || KS == 3)), "stride");
+  static_assert(CK == 16 || CK == 32, "cin chunk");
   static constexpr int PAD = KS / 2;
-  // input halo of one 16x16 output super tile: IH x IW input pixels, input pixel = origin + h*STEP
+  // input halo of one 8x32 output tile: IH x IW input pixels, input pixel = origin + h*STEP
   static constexpr int STEP = (KS == 1) ? S : 1;            // 1x1: only every S-th input pixel is touched
-  static constexpr int IH = (KS == 1) ? kTile : (kTile - 1) * S + KS;
-  static constexpr int IW = IH;
+  static constexpr int IH = (KS == 1) ? TH : (TH - 1) * S + KS;
+  static constexpr int IW = (KS == 1) ? TW : (TW - 1) * S + KS;
   // stride-2 3x3: the halo is stored de-interleaved into 4 parity planes (row parity, column parity) so that every
   // tap again reads 8 x-adjacent plane pixels per core matrix: tap (ky,kx) -> plane (ky&1, kx&1), shift (ky>>1, kx>>1)
   static constexpr bool PLANES = (S == 2 && KS == 3);
-  static constexpr int PW = PLANES ? kTile + 1 : IW;        // plane (or halo) row pitch in pixels
-  static constexpr int PH = PLANES ? kTile + 1 : IH;
+  static constexpr int PW = PLANES ? TW + 1 : IW;           // plane (or halo) row pitch in pixels
+  static constexpr int PH = PLANES ? TH + 1 : IH;
+  static constexpr int NHALO = IH * IW;                     // pixels the producers visit
   static constexpr int NPIX = PLANES ? 4 * PH * PW : IH * IW;
-  static constexpr int NPIXP = NPIX | 1;             // odd pitch: conflict-free 8-byte stores
+  // channel-group pitch in pixels, chosen so that a warp's 8-byte stores spread evenly over the banks:
+  // CK = 32 (4 channel groups x 4 pixels per store): pitch = 4 (mod 8);  CK = 16 (2 x 8): any odd pitch
+  static constexpr int NPIXP = (CK == 32) ? ((NPIX + 3) / 8 * 8 + 4) : (NPIX | 1);
   static constexpr int NCH8 = CK / 8;
-  static constexpr int A_HALF = NCH8 * NPIXP * 16;   // bytes of the hi (or lo) plane of one unit
-  static constexpr int A_STAGE = 2 * A_HALF;
-  static constexpr int LBO_A = NPIXP * 16, SBO_A = PW * 16;
-  static constexpr int B_BLOCK = 2 * NT * CK * 2;    // [2*NT rows][CK] fp16
-  static constexpr int LBO_B = 128, SBO_B = NCH8 * 128;
+  static constexpr int X_HALF = NCH8 * NPIXP * 16;   // bytes of the hi (or lo) plane of one unit
+  static constexpr int X_STAGE = 2 * X_HALF;
+  static constexpr int LBO_X = NPIXP * 16, SBO_X = PW * 16;
+  static constexpr int W_BLOCK = 2 * NT * CK * 2;    // [128 rows][CK] fp16
+  static constexpr int LBO_W = 128, SBO_W = NCH8 * 128;
   static constexpr int KSTEPS = CK / 16;
   static constexpr int TAPS = KS * KS;
-  static constexpr int NA = 2;
-  static constexpr int NB = (KS == 3 && CK == 64) ? 3 : 4;
-  static constexpr int TMEM_COLS = 8 * NT;           // 2 stages x 2 tiles x 2*NT
-  static constexpr int SMEM = NA * A_STAGE + NB * B_BLOCK + 256;
-  static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
+  static constexpr int NW = (CK == 32) ? 4 : 6;
+  static constexpr int NX = (3 * X_STAGE + NW * W_BLOCK + kStageBytes + 256 <= 227 * 1024) ? 3 : 2;
+  static constexpr int SMEM = NX * X_STAGE + NW * W_BLOCK + kStageBytes + 256;
+  static_assert(NPIXP >= NPIX, "pitch");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   // smem pixel slot of halo pixel (hy, hx)
   __host__ __device__ static constexpr int slot(int hy, int hx) {
     return PLANES ? (((hy & 1) * 2 + (hx & 1)) * PH + (hy >> 1)) * PW + (hx >> 1) : hy * IW + hx;
   }
-  // smem pixel slot read by output pixel (0,0) of MMA tile 0 for tap (ky, kx)
+  // smem pixel slot read by output pixel (0,0) for tap (ky, kx)
   __host__ __device__ static constexpr int tap_slot(int ky, int kx) {
     return PLANES ? (((ky & 1) * 2 + (kx & 1)) * PH + (ky >> 1)) * PW + (kx >> 1) : ky * IW + kx;
   }
 };
+
+constexpr int TMEM_COLS = 2 * NPX;  // two accumulator stages
 
 struct Item {
   int n, y0, x0, jt;
@@ -86,24 +100,79 @@ __device__ __forceinline__ Item decode_item(int item, int n_jt, int tiles_x, int
   Item it;
   it.jt = item % n_jt;
   int st = item / n_jt;
-  it.x0 = (st % tiles_x) * kTile;
+  it.x0 = (st % tiles_x) * TW;
   st /= tiles_x;
-  it.y0 = (st % tiles_y) * kTile;
+  it.y0 = (st % tiles_y) * TH;
   it.n = st / tiles_y;
   return it;
 }
 
-template <int KS, int CK, int NT, int S>
+// Rare epilogue paths, kept out of line so that the hot loop stays small.
+// NCHW planes (`out_planar`): thread = (channel, tile row); 8 x-adjacent pixels are contiguous in the plane.
+__device__ __noinline__ void epilogue_planar(const TdvcConvParams& p, const Item& it, const float* sb, int t, int ty0, bool vec) {
+  const int ch = t & 63, h2 = t >> 6;
+  const int ty = ty0 + h2;
+  const int cp = it.jt * NT + ch;
+  if (cp >= p.cout || it.y0 + ty >= p.Ho) return;
+  const float* rb = sb + h2 * (8 * 128) + (ch >> 5) * 64 + (ch & 31);
+  float v[8];
+#pragma unroll
+  for (int x = 0; x < 8; ++x) v[x] = apply_act(rb[x * 128] + rb[x * 128 + 32], p.act, p.slope);
+  float* op = p.out + (((int64_t)it.n * p.cout + cp) * p.Ho + (it.y0 + ty)) * p.Wo + it.x0;
+  if (vec && it.x0 + 8 <= p.Wo) {
+    reinterpret_cast<float4*>(op)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(op)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int x = 0; x < 8; ++x)
+      if (it.x0 + x < p.Wo) op[x] = v[x];
+  }
+}
+
+// Ragged channel counts (cout % 4 != 0) or unaligned / odd-pitch views: one element at a time.
+__device__ __noinline__ void epilogue_ragged(const TdvcConvParams& p, const Item& it, const float* sb, int tx, int rd_off, int co,
+                                              int ty0) {
+  const int sh = p.shuffle == 2 ? 2 : 1;
+  const int cr = p.cout >> 2;
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const int y = it.y0 + ty0 + h2, x = it.x0 + tx;
+    if (y >= p.Ho) continue;
+    const float* rb = sb + (h2 * 8 + tx) * 128 + rd_off;
+    for (int e = 0; e < 4; ++e) {
+      const int ce = co + e;
+      if (ce >= p.cout) break;
+      int oce = ce;
+      int64_t pe = ((int64_t)it.n * p.Ho + y) * p.Wo + x;
+      if (sh == 2) {
+        const int q = ce / cr;
+        oce = ce - q * cr;
+        pe = ((int64_t)it.n * (2 * p.Ho) + (2 * y + (q >> 1))) * (2 * p.Wo) + (2 * x + (q & 1));
+      }
+      float o = rb[e] + rb[e + 32];
+      if (p.post != TDVC_POST_NONE) {
+        const float mv = __ldg(p.mul + pe * p.mul_ld + oce);
+        o = mv * (p.post == TDVC_POST_IGDN ? sqrtf(o) : rsqrtf(o));
+      }
+      o = apply_act(o, p.act, p.slope);
+      if (p.res1) o += __ldg(p.res1 + pe * p.res1_ld + oce);
+      if (p.res2) o += __ldg(p.res2 + pe * p.res2_ld + oce);
+      p.out[pe * p.out_ld + oce] = o;
+    }
+  }
+}
+
+template <int KS, int CK, int S>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvParams p, int tiles_x, int tiles_y, int n_jt,
                                                               int n_units, int n_items) {
-  using C = Cfg<KS, CK, NT, S>;
+  using C = Cfg<KS, CK, S>;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* a_buf = smem;                                  // NA stages of [hi plane | lo plane]
-  uint8_t* b_buf = smem + C::NA * C::A_STAGE;             // NB weight blocks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_buf + C::NB * C::B_BLOCK);
+  uint8_t* x_buf = smem;                                  // NX stages of [hi plane | lo plane]
+  uint8_t* w_buf = smem + C::NX * C::X_STAGE;             // NW weight blocks
+  float* stage_buf = reinterpret_cast<float*>(w_buf + C::NW * C::W_BLOCK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_buf) + kStageBytes);
   // barrier indices
-  constexpr int A_FULL = 0, A_EMPTY = A_FULL + C::NA, B_FULL = A_EMPTY + C::NA, B_EMPTY = B_FULL + C::NB,
-                ACC_FULL = B_EMPTY + C::NB, ACC_EMPTY = ACC_FULL + 2, NBARS = ACC_EMPTY + 2;
+  constexpr int X_FULL = 0, X_EMPTY = X_FULL + C::NX, W_FULL = X_EMPTY + C::NX, W_EMPTY = W_FULL + C::NW,
+                ACC_FULL = W_EMPTY + C::NW, ACC_EMPTY = ACC_FULL + 2, NBARS = ACC_EMPTY + 2;
   static_assert(NBARS * 8 + 8 <= 256, "barrier area");
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
   const uint32_t bar0 = smem_u32(bars);
@@ -112,14 +181,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::NA; ++i) { mbar_init(bar(A_FULL + i), kProdThreads); mbar_init(bar(A_EMPTY + i), 1); }
-    for (int i = 0; i < C::NB; ++i) { mbar_init(bar(B_FULL + i), 1); mbar_init(bar(B_EMPTY + i), 1); }
+    for (int i = 0; i < C::NX; ++i) { mbar_init(bar(X_FULL + i), kProdThreads); mbar_init(bar(X_EMPTY + i), 1); }
+    for (int i = 0; i < C::NW; ++i) { mbar_init(bar(W_FULL + i), 1); mbar_init(bar(W_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(ACC_FULL + i), 1); mbar_init(bar(ACC_EMPTY + i), kEpiWarps * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)C::TMEM_COLS)
+                 "r"((uint32_t)TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -129,262 +198,279 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp < kEpiWarps) {
-    // ===================================================================== epilogue (8 warps: quadrant x tile)
-    const int quad = warp & 3, t = warp >> 2;  // TMEM lane quadrant (= warp id % 4), MMA tile of the super tile
-    const int m = quad * 32 + lane;            // accumulator row = TMEM lane
-    const int py = m >> 3, px = m & 7;
+    // ===================================================================== epilogue (8 warps: lane quadrant x pixel half)
+    // The 4 warps of a pixel half (128 threads, named barrier 1 + half) move 16 pixels (two tile rows) at a time:
+    //   write: warp = TMEM lane quadrant, lane = weight row -> slab[px][row] (conflict-free 128 B per pixel and warp);
+    //          the lo rows are rescaled and carry the bias;
+    //   read : thread = (tile column tx, 4 consecutive output channels) -> hi + lo as two float4, GDN / activation /
+    //          residuals, one 16-byte store per tile row: 16 lanes cover the 256 contiguous bytes of an NHWC pixel.
+    const int quad = warp & 3, half = warp >> 2;
+    const bool is_lo = (quad & 1) != 0;
+    float* slab = stage_buf + half * (2 * 16 * 128);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    constexpr int CH = NT >= 32 ? 32 : 16;     // channels per TMEM read
-    const int cr = p.cout >> 2;
-    const bool vec_ok = ((p.out_ld & 3) == 0) && (!p.res1 || (p.res1_ld & 3) == 0) && (!p.res2 || (p.res2_ld & 3) == 0) &&
-                        (p.post == TDVC_POST_NONE || (p.mul_ld & 3) == 0) && (p.shuffle != 2 || (cr % CH) == 0);
+    const int t = quad * 32 + lane;             // thread index within the half (= its TMEM lane = slab row)
+    const int c4 = t & 15, tx = t >> 4;         // read phase: channels 4*c4..+3 of the item's 64, tile column tx
+    const int rd_off = (c4 >> 3) * 64 + (c4 & 7) * 4;   // hi float4 of those channels inside a slab pixel; lo at +32
+    const int Ho = p.Ho, Wo = p.Wo, cout = p.cout, act = p.act, post = p.post;
+    const int sh = p.shuffle == 2 ? 2 : 1;
+    const int cr = cout >> 2;
+    const int oW = Wo * sh, oH = Ho * sh;
+    const bool planar = p.out_planar != 0;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool vec_ok = !planar && (p.out_ld & 3) == 0 && al16(p.out) && (sh == 1 || (cr & 3) == 0) &&
+                        (post == TDVC_POST_NONE || ((p.mul_ld & 3) == 0 && al16(p.mul))) &&
+                        (!p.res1 || ((p.res1_ld & 3) == 0 && al16(p.res1))) && (!p.res2 || ((p.res2_ld & 3) == 0 && al16(p.res2)));
+    const bool planar_vec = planar && (Wo & 3) == 0 && al16(p.out);
+    // branch-free activation: a(v) = min(max(v,0) + a_neg * min(v,0), a_hi)
+    const float a_neg = act == TDVC_ACT_NONE ? 1.f : (act == TDVC_ACT_LRELU ? p.slope : 0.f);
+    const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
+    // element strides of one tile row in out / mul / res1 / res2 (all address the same logical pixel)
+    const int o_rs = sh * oW * p.out_ld, m_rs = sh * oW * p.mul_ld, r1_rs = sh * oW * p.res1_ld, r2_rs = sh * oW * p.res2_ld;
     int acc_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
       const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
       const int sa = acc_it & 1;
       mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
       tc_fence_after();
-      const int y = it.y0 + py, x = it.x0 + 8 * t + px;
-      const bool valid = (y < p.Ho) && (x < p.Wo);
-      const uint32_t tcol = lane_addr + (uint32_t)((sa * 2 + t) * 2 * NT);
+      // write phase: bias of this lane's weight row (lo rows only)
+      float wbias = 0.f;
+      if (is_lo && p.bias) {
+        const int cw = it.jt * NT + (quad >> 1) * 32 + lane;
+        if (cw < cout) wbias = __ldg(p.bias + cw);
+      }
+      // read phase: where this thread's 4 channels land (PixelShuffle(2) folded into the store: co' = q*(cout/4) + c)
+      const int co = it.jt * NT + 4 * c4;
+      int oc = co, qy = 0, qx = 0;
+      if (sh == 2) {
+        const int q = co < cout ? co / cr : 0;
+        oc = co - q * cr;
+        qy = q >> 1;
+        qx = q & 1;
+      }
+      const bool th_ok = it.x0 + tx < Wo && co < cout;
+      const bool th_vec = vec_ok && co + 4 <= cout;
+      const int ny = Ho - it.y0;  // valid tile rows
+      const int64_t pix0 = ((int64_t)it.n * oH + (it.y0 * sh + qy)) * oW + ((it.x0 + tx) * sh + qx);
+      float* const o0 = p.out + pix0 * p.out_ld + oc;
+      const float* const m0 = post != TDVC_POST_NONE ? p.mul + pix0 * p.mul_ld + oc : nullptr;
+      const float* const r10 = p.res1 ? p.res1 + pix0 * p.res1_ld + oc : nullptr;
+      const float* const r20 = p.res2 ? p.res2 + pix0 * p.res2_ld + oc : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += CH) {
-        uint32_t ra[CH], rb[CH];
-        if constexpr (CH == 32) {
-          tmem_ld32(tcol + c0, ra);
-          tmem_ld32(tcol + NT + c0, rb);
-        } else {
-          tmem_ld16(tcol + c0, ra);
-          tmem_ld16(tcol + NT + c0, rb);
-        }
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[16];
+        tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128 + c * 16), r);
         tmem_ld_wait();
-        const int co0 = it.jt * NT + c0;
-        if (!valid || co0 >= p.cout) continue;
-        float v[CH];
+        if (c == 7) {  // all TMEM reads of this warp are done: the accumulator stage may be overwritten
+          tc_fence_before();
+          mbar_arrive(bar(ACC_EMPTY + sa));
+        }
+        float* sb = slab + (c & 1) * (16 * 128);
+        if (is_lo) {
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = fmaf(__uint_as_float(rb[j]), kLoUnscale, __uint_as_float(ra[j]));
-        if (p.out_planar) {  // NCHW planes: 8 x-adjacent pixels of a row = one 32-byte sector per channel
-          const int64_t plane = (int64_t)p.Ho * p.Wo;
-          float* op = p.out + ((int64_t)it.n * p.cout + co0) * plane + (int64_t)y * p.Wo + x;
-#pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            if (co0 + j < p.cout) op[j * plane] = apply_act(v[j] + (p.bias ? __ldg(p.bias + co0 + j) : 0.f), p.act, p.slope);
-          }
-        } else if (vec_ok && co0 + CH <= p.cout) {
-          int64_t opix;
-          int oc;
-          if (p.shuffle == 2) {  // PixelShuffle(2) folded into the store: co' = q*(cout/4) + c
-            const int q = co0 / cr;
-            oc = co0 - q * cr;
-            opix = ((int64_t)it.n * (2 * p.Ho) + (2 * y + (q >> 1))) * (2 * p.Wo) + (2 * x + (q & 1));
-          } else {
-            oc = co0;
-            opix = ((int64_t)it.n * p.Ho + y) * p.Wo + x;
-          }
-          float4* op = reinterpret_cast<float4*>(p.out + opix * p.out_ld + oc);
-          if (p.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + co0);
-#pragma unroll
-            for (int j = 0; j < CH / 4; ++j) {
-              const float4 b4 = __ldg(bp + j);
-              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-            }
-          }
-          if (p.post != TDVC_POST_NONE) {  // GDN / IGDN: v = mul * rsqrt(v) | mul * sqrt(v)
-            const float4* mp = reinterpret_cast<const float4*>(p.mul + opix * p.mul_ld + oc);
-            const bool inv = p.post == TDVC_POST_IGDN;
-#pragma unroll
-            for (int j = 0; j < CH / 4; ++j) {
-              const float4 m4 = __ldg(mp + j);
-              v[4 * j] = m4.x * (inv ? sqrtf(v[4 * j]) : rsqrtf(v[4 * j]));
-              v[4 * j + 1] = m4.y * (inv ? sqrtf(v[4 * j + 1]) : rsqrtf(v[4 * j + 1]));
-              v[4 * j + 2] = m4.z * (inv ? sqrtf(v[4 * j + 2]) : rsqrtf(v[4 * j + 2]));
-              v[4 * j + 3] = m4.w * (inv ? sqrtf(v[4 * j + 3]) : rsqrtf(v[4 * j + 3]));
-            }
-          }
-          if (p.act == TDVC_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.act == TDVC_ACT_LRELU) {
-            const float sl = p.slope;
-#pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
-          } else if (p.act == TDVC_ACT_CLAMP01) {
-#pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 1.f);
-          }
-          if (p.res1) {
-            const float4* rp = reinterpret_cast<const float4*>(p.res1 + opix * p.res1_ld + oc);
-#pragma unroll
-            for (int j = 0; j < CH / 4; ++j) {
-              const float4 r = __ldg(rp + j);
-              v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-            }
-          }
-          if (p.res2) {
-            const float4* rp = reinterpret_cast<const float4*>(p.res2 + opix * p.res2_ld + oc);
-#pragma unroll
-            for (int j = 0; j < CH / 4; ++j) {
-              const float4 r = __ldg(rp + j);
-              v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 16; ++j) sb[j * 128 + t] = fmaf(__uint_as_float(r[j]), kLoUnscale, wbias);
         } else {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            const int co = co0 + j;
-            if (co >= p.cout) continue;
-            float o = v[j] + (p.bias ? __ldg(p.bias + co) : 0.f);
-            int64_t op2;
-            int oc2;
-            if (p.shuffle == 2) {
-              const int q = co / cr;
-              oc2 = co - q * cr;
-              op2 = ((int64_t)it.n * (2 * p.Ho) + (2 * y + (q >> 1))) * (2 * p.Wo) + (2 * x + (q & 1));
-            } else {
-              oc2 = co;
-              op2 = ((int64_t)it.n * p.Ho + y) * p.Wo + x;
+          for (int j = 0; j < 16; ++j) sb[j * 128 + t] = __uint_as_float(r[j]);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        const int ty0 = half * 16 + c * 2;
+        if (th_vec) {
+          if (!th_ok) continue;
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int ty = ty0 + h2;
+            if (ty >= ny) continue;
+            const float* rb = sb + (h2 * 8 + tx) * 128 + rd_off;
+            const float4 hv = *reinterpret_cast<const float4*>(rb);
+            const float4 lv = *reinterpret_cast<const float4*>(rb + 32);
+            float v[4] = {hv.x + lv.x, hv.y + lv.y, hv.z + lv.z, hv.w + lv.w};
+            if (m0) {  // GDN / IGDN: v = mul * rsqrt(v) | mul * sqrt(v)
+              const float4 m = __ldg(reinterpret_cast<const float4*>(m0 + ty * m_rs));
+              if (post == TDVC_POST_IGDN) { v[0] = m.x * sqrtf(v[0]); v[1] = m.y * sqrtf(v[1]); v[2] = m.z * sqrtf(v[2]); v[3] = m.w * sqrtf(v[3]); }
+              else { v[0] = m.x * rsqrtf(v[0]); v[1] = m.y * rsqrtf(v[1]); v[2] = m.z * rsqrtf(v[2]); v[3] = m.w * rsqrtf(v[3]); }
             }
-            if (p.post != TDVC_POST_NONE) {
-              const float mv = __ldg(p.mul + op2 * p.mul_ld + oc2);
-              o = mv * (p.post == TDVC_POST_IGDN ? sqrtf(o) : rsqrtf(o));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = fminf(fmaf(a_neg, fminf(v[e], 0.f), fmaxf(v[e], 0.f)), a_hi);
+            if (r10) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(r10 + ty * r1_rs));
+              v[0] += m.x; v[1] += m.y; v[2] += m.z; v[3] += m.w;
             }
-            o = apply_act(o, p.act, p.slope);
-            if (p.res1) o += __ldg(p.res1 + op2 * p.res1_ld + oc2);
-            if (p.res2) o += __ldg(p.res2 + op2 * p.res2_ld + oc2);
-            p.out[op2 * p.out_ld + oc2] = o;
+            if (r20) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(r20 + ty * r2_rs));
+              v[0] += m.x; v[1] += m.y; v[2] += m.z; v[3] += m.w;
+            }
+            *reinterpret_cast<float4*>(o0 + ty * o_rs) = make_float4(v[0], v[1], v[2], v[3]);
           }
+        } else if (planar) {
+          epilogue_planar(p, it, sb, t, ty0, planar_vec);
+        } else if (th_ok) {
+          epilogue_ragged(p, it, sb, tx, rd_off, co, ty0);
         }
       }
-      tc_fence_before();
-      mbar_arrive(bar(ACC_EMPTY + sa));
     }
   } else if (warp < kEpiWarps + kProdWarps) {
     // ===================================================================== producers: fp32 halo -> fp16 hi/lo planes
-    // One warp per halo row: LPP lanes cover the CK channels of a pixel (coalesced 16*LPP bytes), 32/LPP pixels per
-    // load instruction, all loads of the row issued before the first conversion (memory-level parallelism).
+    // LPP lanes cover the CK channels of a pixel (one float4 each), 32/LPP pixels per warp-wide load; the halo is
+    // walked as a flat pixel list s = (k*8 + warp)*PPI + lane/LPP.  Each thread keeps, for its PER_WARP loads, the
+    // source-pixel offset in a register table (the same for every item and unit), so an interior tile costs one
+    // address instruction per load; all loads of a batch are in flight before the first conversion.
     const int pw = warp - kEpiWarps;
     constexpr int LPP = CK / 4;                       // lanes (float4) per pixel
     constexpr int PPI = 32 / LPP;                     // pixels per warp-wide load
-    constexpr int ITERS = (C::IW + PPI - 1) / PPI;
+    constexpr int NLD = (C::NHALO + PPI - 1) / PPI;   // warp-wide loads per unit
+    constexpr int PER_WARP = (NLD + kProdWarps - 1) / kProdWarps;
+    constexpr int NBATCH = (PER_WARP + 11) / 12;
+    constexpr int BATCH = (PER_WARP + NBATCH - 1) / NBATCH;
     const int fi = lane % LPP, psub = lane / LPP;
-    const int j8 = fi >> 1, half = fi & 1;
-    int a_it = 0;
+    const int j8 = fi >> 1, hf = fi & 1;
+    int tab[PER_WARP];   // non-PLANES: source pixel offset hy*STEP*W + hx*STEP;  PLANES: hy << 8 | hx
+    uint32_t vmask = 0;
+#pragma unroll
+    for (int k = 0; k < PER_WARP; ++k) {
+      const int sidx = (k * kProdWarps + pw) * PPI + psub;
+      const int hy = sidx / C::IW, hx = sidx - hy * C::IW;
+      tab[k] = C::PLANES ? ((hy << 8) | hx) : (hy * C::STEP * p.W + hx * C::STEP);
+      if (sidx < C::NHALO) vmask |= 1u << k;
+    }
+    const uint32_t lane_smem = (uint32_t)((j8 * C::NPIXP) * 16 + hf * 8 + (pw * PPI + psub) * 16);
+    int sX = 0, phX = 1;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
       const int iy0 = it.y0 * S - C::PAD, ix0 = it.x0 * S - C::PAD;
-      for (int u = 0; u < n_units; ++u, ++a_it) {
+      const bool interior = iy0 >= 0 && ix0 >= 0 && iy0 + (C::IH - 1) * C::STEP < p.H && ix0 + (C::IW - 1) * C::STEP < p.W;
+      for (int u = 0; u < n_units; ++u) {
         // resolve this lane's 4 channels (index in the concatenated input) to a source tensor
         const float* sp = nullptr;
         int sld = 0;
         {
           int cc = u * CK + fi * 4;
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            if (s < p.n_src && sp == nullptr) {
-              if (cc < p.src_c[s]) { sp = p.src[s] + cc; sld = p.src_ld[s]; }
-              else cc -= p.src_c[s];
+          for (int q = 0; q < 4; ++q) {
+            if (q < p.n_src && sp == nullptr) {
+              if (cc < p.src_c[q]) { sp = p.src[q] + cc; sld = p.src_ld[q]; }
+              else cc -= p.src_c[q];
             }
           }
         }
-        const int st = a_it % C::NA;
-        mbar_wait(bar(A_EMPTY + st), ((a_it / C::NA) & 1) ^ 1);
-        uint8_t* hi = a_buf + st * C::A_STAGE + (j8 * C::NPIXP) * 16 + half * 8;
-        const float* img = sp ? sp + (int64_t)it.n * p.H * p.W * sld : nullptr;
-#pragma unroll 1
-        for (int hy = pw; hy < C::IH; hy += kProdWarps) {
-          const int iy = iy0 + hy * C::STEP;
-          const bool rowok = (img != nullptr) && iy >= 0 && iy < p.H;
-          const float* rowp = rowok ? img + ((int64_t)iy * p.W + ix0) * sld : nullptr;
-          float4 v[ITERS];
+        mbar_wait(bar(X_EMPTY + sX), phX);
+        uint8_t* hi = x_buf + sX * C::X_STAGE + lane_smem;
+        // pointer to this lane's channels of the halo origin pixel (may lie outside the image: only offsets are added)
+        const float* org = sp ? sp + (((int64_t)it.n * p.H + iy0) * p.W + ix0) * sld : nullptr;
 #pragma unroll
-          for (int k = 0; k < ITERS; ++k) {
-            const int hx = psub + k * PPI;
-            const int ix = ix0 + hx * C::STEP;
-            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rowok && hx < C::IW && ix >= 0 && ix < p.W)
-              v[k] = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)(hx * C::STEP) * sld));
+        for (int b = 0; b < NBATCH; ++b) {
+          float4 v[BATCH];
+          if (interior && org != nullptr) {
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) {
+              const int kk = b * BATCH + k;
+              v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (kk < PER_WARP && ((vmask >> kk) & 1)) {
+                int po = tab[kk < PER_WARP ? kk : 0];
+                if (C::PLANES) po = ((po >> 8) * p.W + (po & 255));
+                v[k] = __ldg(reinterpret_cast<const float4*>(org + (int64_t)po * sld));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) {
+              const int kk = b * BATCH + k;
+              const int sidx = (kk * kProdWarps + pw) * PPI + psub;
+              const int hy = sidx / C::IW, hx = sidx - hy * C::IW;
+              const int iy = iy0 + hy * C::STEP, ix = ix0 + hx * C::STEP;
+              v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (kk < PER_WARP && sidx < C::NHALO && org != nullptr && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                v[k] = __ldg(reinterpret_cast<const float4*>(org + ((int64_t)(hy * C::STEP) * p.W + hx * C::STEP) * sld));
+            }
           }
           if (p.in_square) {
 #pragma unroll
-            for (int k = 0; k < ITERS; ++k) { v[k].x *= v[k].x; v[k].y *= v[k].y; v[k].z *= v[k].z; v[k].w *= v[k].w; }
+            for (int k = 0; k < BATCH; ++k) { v[k].x *= v[k].x; v[k].y *= v[k].y; v[k].z *= v[k].z; v[k].w *= v[k].w; }
           }
 #pragma unroll
-          for (int k = 0; k < ITERS; ++k) {
-            const int hx = psub + k * PPI;
-            if (hx < C::IW) {
+          for (int k = 0; k < BATCH; ++k) {
+            const int kk = b * BATCH + k;
+            if (kk < PER_WARP && ((vmask >> kk) & 1)) {
               uint2 hv, lv;
               split4(v[k], hv, lv);
-              uint8_t* dst = hi + C::slot(hy, hx) * 16;
+              uint8_t* dst;
+              if (C::PLANES) {
+                const int po = tab[kk < PER_WARP ? kk : 0];
+                dst = hi - (pw * PPI + psub) * 16 + C::slot(po >> 8, po & 255) * 16;
+              } else {
+                dst = hi + kk * (kProdWarps * PPI * 16);   // flat slot = sidx
+              }
               *reinterpret_cast<uint2*>(dst) = hv;
-              *reinterpret_cast<uint2*>(dst + C::A_HALF) = lv;
+              *reinterpret_cast<uint2*>(dst + C::X_HALF) = lv;
             }
           }
         }
         fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(bar(A_FULL + st));
+        mbar_arrive(bar(X_FULL + sX));
+        if (++sX == C::NX) { sX = 0; phX ^= 1; }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t IDESC_2N = instr_desc(2 * NT), IDESC_N = instr_desc(NT);
-      const uint32_t a0 = smem_u32(a_buf), b0 = smem_u32(b_buf);
-      int a_it = 0, b_it = 0, acc_it = 0;
+    // ===================================================================== MMA issuer (one elected thread)
+    // Descriptors are built once; every MMA only adds a compile-time offset (16-byte units) to their low word.
+    if (elect_one()) {
+      constexpr uint32_t IDESC = instr_desc(NPX);
+      constexpr uint32_t KX = 2 * C::LBO_X / 16, KW = 2 * C::LBO_W / 16;   // k-step advance of the two operands
+      const uint64_t xdesc0 = smem_desc(smem_u32(x_buf), C::LBO_X, C::SBO_X);
+      const uint64_t wdesc0 = smem_desc(smem_u32(w_buf), C::LBO_W, C::SBO_W);
+      int sX = 0, phX = 0, sW = 0, phW = 0, acc_it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
         const int sa = acc_it & 1;
         mbar_wait(bar(ACC_EMPTY + sa), ((acc_it >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int u = 0; u < n_units; ++u, ++a_it) {
-          const int sA = a_it % C::NA;
-          mbar_wait(bar(A_FULL + sA), (a_it / C::NA) & 1);
+        const uint32_t d = tmem_base + (uint32_t)(sa * NPX);
+        for (int u = 0; u < n_units; ++u) {
+          mbar_wait(bar(X_FULL + sX), phX);
           tc_fence_after();
-          const uint32_t a_hi = a0 + sA * C::A_STAGE, a_lo = a_hi + C::A_HALF;
+          const uint64_t x_hi = desc_add(xdesc0, (uint32_t)(sX * (C::X_STAGE / 16)));
 #pragma unroll 1
-          for (int tap = 0; tap < C::TAPS; ++tap, ++b_it) {
-            const int sB = b_it % C::NB;
-            mbar_wait(bar(B_FULL + sB), (b_it / C::NB) & 1);
-            tc_fence_after();
-            const int ky = tap / KS, kx = tap - ky * KS;
-            const uint32_t bblk = b0 + sB * C::B_BLOCK;
+          for (int ky = 0; ky < KS; ++ky) {
+            // first tap of the kernel row: tap_slot(ky, 0); the other taps of the row are compile-time offsets from it
+            const uint32_t row0 = C::PLANES ? (uint32_t)(((ky & 1) * 2 * C::PH + (ky >> 1)) * C::PW) : (uint32_t)(ky * C::IW);
+            const uint64_t x_row = desc_add(x_hi, row0);
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const uint32_t d = tmem_base + (uint32_t)((sa * 2 + t) * 2 * NT);
-              const uint32_t aoff = (uint32_t)((C::tap_slot(ky, kx) + 8 * t) * 16);
+            for (int kx = 0; kx < KS; ++kx) {
+              mbar_wait(bar(W_FULL + sW), phW);
+              tc_fence_after();
+              const uint64_t wd = desc_add(wdesc0, (uint32_t)(sW * (C::W_BLOCK / 16)));
+              const uint32_t xo = (uint32_t)(C::tap_slot(0, kx) - C::tap_slot(0, 0));
 #pragma unroll
               for (int s = 0; s < C::KSTEPS; ++s) {
-                const uint64_t bd = smem_desc(bblk + s * 2 * C::LBO_B, C::LBO_B, C::SBO_B);
-                const uint64_t adh = smem_desc(a_hi + aoff + s * 2 * C::LBO_A, C::LBO_A, C::SBO_A);
-                const uint64_t adl = smem_desc(a_lo + aoff + s * 2 * C::LBO_A, C::LBO_A, C::SBO_A);
-                tc_mma(d, adh, bd, IDESC_2N, (u | tap | s) != 0);
-                tc_mma(d, adl, bd, IDESC_N, 1u);
+                const uint64_t wk = desc_add(wd, s * KW);
+                const uint64_t xh = desc_add(x_row, xo + s * KX);
+                const uint64_t xl = desc_add(x_row, xo + s * KX + C::X_HALF / 16);
+                if (kx == 0 && s == 0) tc_mma(d, wk, xh, IDESC, (uint32_t)((u | ky) != 0));
+                else tc_mma(d, wk, xh, IDESC, 1u);
+                tc_mma(d, wk, xl, IDESC, 1u);
               }
+              tc_commit(bar(W_EMPTY + sW));
+              if (++sW == C::NW) { sW = 0; phW ^= 1; }
             }
-            tc_commit(bar(B_EMPTY + sB));
           }
-          tc_commit(bar(A_EMPTY + sA));
+          tc_commit(bar(X_EMPTY + sX));
+          if (++sX == C::NX) { sX = 0; phX ^= 1; }
         }
         tc_commit(bar(ACC_FULL + sa));
       }
     }
   } else {
     // ===================================================================== weight loader (1-D bulk TMA)
-    if (lane == 0) {
+    if (elect_one()) {
       const uint8_t* wb = static_cast<const uint8_t*>(p.weight_f16);
-      const uint32_t b0 = smem_u32(b_buf);
-      int b_it = 0;
+      const uint32_t w0 = smem_u32(w_buf);
+      int sW = 0, phW = 1;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int jt = item % n_jt;
-        for (int u = 0; u < n_units; ++u) {
-          const uint8_t* src = wb + ((int64_t)(jt * n_units + u) * C::TAPS) * C::B_BLOCK;
-          for (int tap = 0; tap < C::TAPS; ++tap, ++b_it) {
-            const int sB = b_it % C::NB;
-            mbar_wait(bar(B_EMPTY + sB), ((b_it / C::NB) & 1) ^ 1);
-            mbar_expect_tx(bar(B_FULL + sB), C::B_BLOCK);
-            bulk_g2s(b0 + sB * C::B_BLOCK, src + (int64_t)tap * C::B_BLOCK, C::B_BLOCK, bar(B_FULL + sB));
-          }
+        const uint8_t* src = wb + ((int64_t)jt * n_units * C::TAPS) * C::W_BLOCK;
+        for (int ut = 0; ut < n_units * C::TAPS; ++ut, src += C::W_BLOCK) {
+          mbar_wait(bar(W_EMPTY + sW), phW);
+          mbar_expect_tx(bar(W_FULL + sW), C::W_BLOCK);
+          bulk_g2s(w0 + sW * C::W_BLOCK, src, C::W_BLOCK, bar(W_FULL + sW));
+          if (++sW == C::NW) { sW = 0; phW ^= 1; }
         }
       }
     }
@@ -394,15 +480,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
   }
 }
 
-// fp32 packed weights [T][cin_pad][cout_pad] -> per (cout tile, unit, tap) fp16 block [2*NT rows][CK] in the
-// canonical K-major interleaved layout [(n/8)][(k/8)][n%8][k%8]; rows 0..NT-1 = hi, NT..2NT-1 = lo * 2^12.
+// fp32 packed weights [T][cin_pad][cout_pad] -> per (cout tile of 64, unit, tap) fp16 block [128 rows][CK] in the
+// canonical K-major no-swizzle layout [(row/8)][(k/8)][row%8][k%8].  Row order = TMEM lane order of the accumulator:
+// rows 0-31 hi of channels 0-31, rows 32-63 lo * 2^12 of channels 0-31, rows 64-95 hi of 32-63, rows 96-127 lo of 32-63.
 __global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict__ out, int T, int cin, int cin_pad,
-                                 int cout, int cout_pad, int CK, int NT, int n_units, int n_jt) {
+                                 int cout, int cout_pad, int CK, int n_units, int n_jt) {
   const int64_t per_block = (int64_t)2 * NT * CK;
   const int64_t total = (int64_t)n_jt * n_units * T * per_block;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -414,72 +501,55 @@ __global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict_
     const int tap = (int)(r % T); r /= T;
     const int u = (int)(r % n_units);
     const int jt = (int)(r / n_units);
-    const int n2 = ng * 8 + n8, k = kc * 8 + k8;
-    const int ci = u * CK + k, co = jt * NT + (n2 % NT);
+    const int row = ng * 8 + n8, k = kc * 8 + k8;
+    const int quad = row >> 5;
+    const int ci = u * CK + k, co = jt * NT + (quad >> 1) * 32 + (row & 31);
     float v = 0.f;
     if (ci < cin_pad && co < cout_pad && ci < cin && co < cout) v = w[((int64_t)tap * cin_pad + ci) * cout_pad + co];
     v = fminf(fmaxf(v, -65504.f), 65504.f);
     const __half hi = __float2half_rn(v);
-    out[i] = (n2 < NT) ? hi : __float2half_rn((v - __half2float(hi)) * kLoScale);
+    out[i] = (quad & 1) ? __float2half_rn((v - __half2float(hi)) * kLoScale) : hi;
   }
 }
 
 struct Choice {
-  int ks, ck, nt;
+  int ks, ck, s;
 };
 
+// Every KxK (K in 1,3,5,7; pad K/2) stride-1 convolution and the stride-2 3x3 / 1x1 ones have a tensor-core path;
+// output channels are processed in tiles of 64 (zero rows above cout), input channels in chunks of ck.
 static bool choose(const TdvcConvParams& p, Choice* c) {
-  if (p.kh != p.kw || p.pad != p.kh / 2) return false;
+  if (p.kh != p.kw || p.pad != p.kh / 2 || p.cin < 4 || p.cout < 1) return false;
   if (p.stride == 2) {
-    if (p.cin < 64 || p.cout < 64) return false;
-    if (p.kh == 3) { *c = {3, 16, 64}; return true; }
-    if (p.kh == 1) { *c = {1, 64, 64}; return true; }
+    if (p.kh == 3) { *c = {3, 16, 2}; return true; }
+    if (p.kh == 1) { *c = {1, 32, 2}; return p.cin >= 32; }
     return false;
   }
   if (p.stride != 1) return false;
-  if (p.kh == 3) {
-    if (p.cin <= 16) { *c = {3, 16, 64}; return p.cout > 16; }   // image inputs (3 channels padded to 4)
-    if (p.cin < 64) return false;
-    *c = {3, 64, p.cout <= 16 ? 16 : 64};
-    return true;
-  }
-  if (p.kh == 1) {
-    if (p.cin < 64 || p.cout < 64) return false;
-    *c = {1, 64, 64};
-    return true;
-  }
-  if (p.kh == 5) {
-    if (p.cin < 32 || p.cout < 64) return false;
-    *c = {5, 32, 64};
-    return true;
-  }
-  if (p.kh == 7) {
-    const int ck = p.cin >= 32 ? 32 : 16;
-    const int nt = p.cout >= 64 ? 64 : (p.cout >= 32 ? 32 : 16);
-    *c = {7, ck, nt};
-    return true;
-  }
+  const int ck = p.cin > 16 ? 32 : 16;
+  if (p.kh == 3 || p.kh == 7) { *c = {p.kh, ck, 1}; return true; }
+  if (p.kh == 1 || p.kh == 5) { *c = {p.kh, 32, 1}; return p.cin >= 32; }
   return false;
 }
 
-template <int KS, int CK, int NT, int S = 1>
+template <int KS, int CK, int S = 1>
 static int launch(const TdvcConvParams& p, cudaStream_t st) {
-  using C = Cfg<KS, CK, NT, S>;
+  using C = Cfg<KS, CK, S>;
   static bool attr_set = false;  // idempotent; a benign race sets it twice
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, CK, NT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, CK, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute(%d bytes) failed: %s", C::SMEM, cudaGetErrorString(e));
       return TDVC_ECUDA;
     }
     attr_set = true;
   }
-  const int tiles_x = cdiv(p.Wo, kTile), tiles_y = cdiv(p.Ho, kTile);
+  const int tiles_x = cdiv(p.Wo, TW), tiles_y = cdiv(p.Ho, TH);
   const int n_jt = cdiv(p.cout, NT), n_units = cdiv(p.cin, CK);
   const int64_t items = (int64_t)p.N * tiles_x * tiles_y * n_jt;
   TDVC_REQUIRE(items < (1ll << 31), "conv_tc: too many work items");
   const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  conv_tc_kernel<KS, CK, NT, S><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items);
+  conv_tc_kernel<KS, CK, S><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items);
   TDVC_CHECK_LAUNCH("conv_tc");
   return TDVC_OK;
 }
@@ -491,7 +561,7 @@ int conv2d_tc_supported(const TdvcConvParams& p) {
   if (p.weight_f16 == nullptr) return 0;
   if (!tc::choose(p, &c)) return 0;
   for (int s = 0; s < p.n_src; ++s)
-    if (p.src_c[s] % 4 != 0 || p.src_ld[s] % 4 != 0) return 0;
+    if (p.src_c[s] % 4 != 0 || p.src_ld[s] % 4 != 0 || (reinterpret_cast<uintptr_t>(p.src[s]) & 15) != 0) return 0;
   if ((reinterpret_cast<uintptr_t>(p.weight_f16) & 15) != 0) return 0;
   return 1;
 }
@@ -502,20 +572,15 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
     set_error("conv_tc: unsupported shape");
     return TDVC_EINVAL;
   }
-  if (p.stride == 2 && c.ks == 3) return tc::launch<3, 16, 64, 2>(p, st);
-  if (p.stride == 2 && c.ks == 1) return tc::launch<1, 64, 64, 2>(p, st);
-  if (c.ks == 3 && c.ck == 64 && c.nt == 64) return tc::launch<3, 64, 64>(p, st);
-  if (c.ks == 3 && c.ck == 64 && c.nt == 16) return tc::launch<3, 64, 16>(p, st);
-  if (c.ks == 3 && c.ck == 16 && c.nt == 64) return tc::launch<3, 16, 64>(p, st);
-  if (c.ks == 1) return tc::launch<1, 64, 64>(p, st);
-  if (c.ks == 5) return tc::launch<5, 32, 64>(p, st);
-  if (c.ck == 32 && c.nt == 64) return tc::launch<7, 32, 64>(p, st);
-  if (c.ck == 32 && c.nt == 32) return tc::launch<7, 32, 32>(p, st);
-  if (c.ck == 32 && c.nt == 16) return tc::launch<7, 32, 16>(p, st);
-  if (c.ck == 16 && c.nt == 32) return tc::launch<7, 16, 32>(p, st);
-  if (c.ck == 16 && c.nt == 16) return tc::launch<7, 16, 16>(p, st);
-  if (c.ck == 16 && c.nt == 64) return tc::launch<7, 16, 64>(p, st);
-  set_error("conv_tc: no instantiation for ks=%d ck=%d nt=%d", c.ks, c.ck, c.nt);
+  if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2>(p, st);
+  if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2>(p, st);
+  if (c.ks == 3 && c.ck == 32) return tc::launch<3, 32>(p, st);
+  if (c.ks == 3 && c.ck == 16) return tc::launch<3, 16>(p, st);
+  if (c.ks == 1) return tc::launch<1, 32>(p, st);
+  if (c.ks == 5) return tc::launch<5, 32>(p, st);
+  if (c.ks == 7 && c.ck == 32) return tc::launch<7, 32>(p, st);
+  if (c.ks == 7 && c.ck == 16) return tc::launch<7, 16>(p, st);
+  set_error("conv_tc: no instantiation for ks=%d ck=%d stride=%d", c.ks, c.ck, c.s);
   return TDVC_EINVAL;
 }
 
@@ -526,20 +591,20 @@ using namespace tdvc;
 extern "C" size_t tdvc_conv2d_f16_bytes(const TdvcConvParams* p) {
   tc::Choice c;
   if (p == nullptr || !tc::choose(*p, &c)) return 0;
-  const int n_jt = cdiv(p->cout, c.nt), n_units = cdiv(p->cin, c.ck);
-  return (size_t)n_jt * n_units * c.ks * c.ks * 2 * c.nt * c.ck * sizeof(__half);
+  const int n_jt = cdiv(p->cout, tc::NT), n_units = cdiv(p->cin, c.ck);
+  return (size_t)n_jt * n_units * c.ks * c.ks * 2 * tc::NT * c.ck * sizeof(__half);
 }
 
 extern "C" int tdvc_conv2d_pack_f16(const TdvcConvParams* p, void* out, void* stream) {
   tc::Choice c;
   TDVC_REQUIRE(p && out && p->weight, "conv2d_pack_f16: null pointer");
   TDVC_REQUIRE(tc::choose(*p, &c), "conv2d_pack_f16: shape has no tcgen05 path");
-  const int n_jt = cdiv(p->cout, c.nt), n_units = cdiv(p->cin, c.ck);
-  const int64_t total = (int64_t)n_jt * n_units * c.ks * c.ks * 2 * c.nt * c.ck;
+  const int n_jt = cdiv(p->cout, tc::NT), n_units = cdiv(p->cin, c.ck);
+  const int64_t total = (int64_t)n_jt * n_units * c.ks * c.ks * 2 * tc::NT * c.ck;
   int grid = cdiv(total, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   tc::pack_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->weight, static_cast<__half*>(out), c.ks * c.ks, p->cin,
-                                                             p->cin_pad, p->cout, p->cout_pad, c.ck, c.nt, n_units, n_jt);
+                                                             p->cin_pad, p->cout, p->cout_pad, c.ck, n_units, n_jt);
   TDVC_CHECK_LAUNCH("conv2d_pack_f16");
   return TDVC_OK;
 }

@@ -49,6 +49,11 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -72,6 +77,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // between the two K-adjacent core matrices of one MMA (K=16), SBO = byte distance between 8-row groups.
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// add a 16-byte-unit offset to the start-address field of a descriptor (low word only; the field cannot overflow for
+// addresses inside the 227 KB of shared memory)
+__device__ __forceinline__ uint64_t desc_add(uint64_t desc, uint32_t off16) {
+  return (desc & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)desc + off16);
+}
+// true in exactly one lane of a converged warp (lets ptxas see the single-thread region: no per-lane issue loops)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=fp16 (format 0 in bits 7-9 / 10-12), both K-major, M=128, N
 __host__ __device__ constexpr uint32_t instr_desc(int n) {
