@@ -161,6 +161,105 @@ __device__ __noinline__ void epilogue_ragged(const TdvcConvParams& p, const Item
   }
 }
 
+// ---- producer helpers -------------------------------------------------------------------------------------------
+template <class C, int CK>
+struct ProdCfg {
+  static constexpr int LPP = CK / 4;                       // lanes (float4) per pixel
+  static constexpr int PPI = 32 / LPP;                     // pixels per warp-wide load
+  static constexpr int NLD = (C::NHALO + PPI - 1) / PPI;   // warp-wide loads per unit
+  static constexpr int PER_WARP = (NLD + kProdWarps - 1) / kProdWarps;
+  static constexpr int NBATCH = PER_WARP <= 12 ? 2 : 4;    // even: the two register buffers alternate
+  static constexpr int BATCH = (PER_WARP + NBATCH - 1) / NBATCH;
+};
+struct ProdThread {
+  int pw, psub;
+  uint32_t vmask, lane_smem;
+};
+struct ProdUnit {
+  const float* org;
+  uint8_t* hi;
+  int sld, iy0, ix0, stage;
+  bool fast;
+};
+
+// issue the loads of batch B of a unit into v (zeros where the halo leaves the image / the channel range)
+template <class C, class P, int B>
+__device__ __forceinline__ void prod_issue(const TdvcConvParams& p, const ProdThread& th, const int (&tab)[P::PER_WARP],
+                                           const ProdUnit& c, float4 (&v)[P::BATCH]) {
+  if (c.fast) {
+#pragma unroll
+    for (int k = 0; k < P::BATCH; ++k) {
+      const int kk = B * P::BATCH + k;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kk < P::PER_WARP) {
+        if ((th.vmask >> kk) & 1) {
+          int po = tab[kk < P::PER_WARP ? kk : 0];
+          if (C::PLANES) po = (po >> 8) * p.W + (po & 255);
+          v[k] = __ldg(reinterpret_cast<const float4*>(c.org + (int64_t)po * c.sld));
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < P::BATCH; ++k) {
+      const int kk = B * P::BATCH + k;
+      const int sidx = (kk * kProdWarps + th.pw) * P::PPI + th.psub;
+      const int hy = sidx / C::IW, hx = sidx - hy * C::IW;
+      const int iy = c.iy0 + hy * C::STEP, ix = c.ix0 + hx * C::STEP;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kk < P::PER_WARP && sidx < C::NHALO && c.org != nullptr && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+        v[k] = __ldg(reinterpret_cast<const float4*>(c.org + ((int64_t)(hy * C::STEP) * p.W + hx * C::STEP) * c.sld));
+    }
+  }
+}
+
+// split batch B into fp16 hi / lo and store it at its halo slots of the unit's stage
+template <class C, class P, int B>
+__device__ __forceinline__ void prod_convert(const TdvcConvParams& p, const ProdThread& th, const int (&tab)[P::PER_WARP],
+                                             const ProdUnit& c, float4 (&v)[P::BATCH]) {
+  if (p.in_square) {
+#pragma unroll
+    for (int k = 0; k < P::BATCH; ++k) { v[k].x *= v[k].x; v[k].y *= v[k].y; v[k].z *= v[k].z; v[k].w *= v[k].w; }
+  }
+#pragma unroll
+  for (int k = 0; k < P::BATCH; ++k) {
+    const int kk = B * P::BATCH + k;
+    if (kk < P::PER_WARP) {
+      if ((th.vmask >> kk) & 1) {
+        uint2 hv, lv;
+        split4(v[k], hv, lv);
+        uint8_t* dst;
+        if (C::PLANES) {
+          const int po = tab[kk < P::PER_WARP ? kk : 0];
+          dst = c.hi - (th.pw * P::PPI + th.psub) * 16 + C::slot(po >> 8, po & 255) * 16;
+        } else {
+          dst = c.hi + kk * (kProdWarps * P::PPI * 16);   // flat slot = pixel index
+        }
+        *reinterpret_cast<uint2*>(dst) = hv;
+        *reinterpret_cast<uint2*>(dst + C::X_HALF) = lv;
+      }
+    }
+  }
+}
+
+// batch index known only after unrolling the caller's loop (it is a compile-time constant there): dispatch 0..3
+template <class C, class P>
+__device__ __forceinline__ void prod_issue_rt(const TdvcConvParams& p, const ProdThread& th, const int (&tab)[P::PER_WARP],
+                                              const ProdUnit& c, float4 (&v)[P::BATCH], int b) {
+  if (b == 0) prod_issue<C, P, 0>(p, th, tab, c, v);
+  else if (b == 1) prod_issue<C, P, 1>(p, th, tab, c, v);
+  else if (b == 2) prod_issue<C, P, 2>(p, th, tab, c, v);
+  else prod_issue<C, P, 3>(p, th, tab, c, v);
+}
+template <class C, class P>
+__device__ __forceinline__ void prod_convert_rt(const TdvcConvParams& p, const ProdThread& th, const int (&tab)[P::PER_WARP],
+                                                const ProdUnit& c, float4 (&v)[P::BATCH], int b) {
+  if (b == 0) prod_convert<C, P, 0>(p, th, tab, c, v);
+  else if (b == 1) prod_convert<C, P, 1>(p, th, tab, c, v);
+  else if (b == 2) prod_convert<C, P, 2>(p, th, tab, c, v);
+  else prod_convert<C, P, 3>(p, th, tab, c, v);
+}
+
 template <int KS, int CK, int S>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvParams p, int tiles_x, int tiles_y, int n_jt,
                                                               int n_units, int n_items) {
@@ -221,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
                         (post == TDVC_POST_NONE || ((p.mul_ld & 3) == 0 && al16(p.mul))) &&
                         (!p.res1 || ((p.res1_ld & 3) == 0 && al16(p.res1))) && (!p.res2 || ((p.res2_ld & 3) == 0 && al16(p.res2)));
     const bool planar_vec = planar && (Wo & 3) == 0 && al16(p.out);
-    // branch-free activation: a(v) = min(max(v,0) + a_neg * min(v,0), a_hi)
+    // branch-free activation: a(v) = min(max(v, a_neg * v), a_hi)   (0 <= a_neg <= 1)
     const float a_neg = act == TDVC_ACT_NONE ? 1.f : (act == TDVC_ACT_LRELU ? p.slope : 0.f);
     const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
     // element strides of one tile row in out / mul / res1 / res2 (all address the same logical pixel)
@@ -255,10 +354,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       const float* const m0 = post != TDVC_POST_NONE ? p.mul + pix0 * p.mul_ld + oc : nullptr;
       const float* const r10 = p.res1 ? p.res1 + pix0 * p.res1_ld + oc : nullptr;
       const float* const r20 = p.res2 ? p.res2 + pix0 * p.res2_ld + oc : nullptr;
+      uint32_t r[16];
+      tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128), r);
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
-        uint32_t r[16];
-        tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128 + c * 16), r);
         tmem_ld_wait();
         if (c == 7) {  // all TMEM reads of this warp are done: the accumulator stage may be overwritten
           tc_fence_before();
@@ -272,34 +371,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 #pragma unroll
           for (int j = 0; j < 16; ++j) sb[j * 128 + t] = __uint_as_float(r[j]);
         }
+        // next chunk's accumulator columns: the TMEM read overlaps the barrier and the read phase below
+        if (c < 7) tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128 + (c + 1) * 16), r);
         asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
         const int ty0 = half * 16 + c * 2;
         if (th_vec) {
-          if (!th_ok) continue;
-#pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const int ty = ty0 + h2;
-            if (ty >= ny) continue;
-            const float* rb = sb + (h2 * 8 + tx) * 128 + rd_off;
-            const float4 hv = *reinterpret_cast<const float4*>(rb);
-            const float4 lv = *reinterpret_cast<const float4*>(rb + 32);
-            float v[4] = {hv.x + lv.x, hv.y + lv.y, hv.z + lv.z, hv.w + lv.w};
-            if (m0) {  // GDN / IGDN: v = mul * rsqrt(v) | mul * sqrt(v)
-              const float4 m = __ldg(reinterpret_cast<const float4*>(m0 + ty * m_rs));
-              if (post == TDVC_POST_IGDN) { v[0] = m.x * sqrtf(v[0]); v[1] = m.y * sqrtf(v[1]); v[2] = m.z * sqrtf(v[2]); v[3] = m.w * sqrtf(v[3]); }
-              else { v[0] = m.x * rsqrtf(v[0]); v[1] = m.y * rsqrtf(v[1]); v[2] = m.z * rsqrtf(v[2]); v[3] = m.w * rsqrtf(v[3]); }
+          if (!th_ok || ty0 >= ny) continue;
+          const bool two = ty0 + 1 < ny;
+          const float* rb = sb + tx * 128 + rd_off;
+          const float4 h0 = *reinterpret_cast<const float4*>(rb), l0 = *reinterpret_cast<const float4*>(rb + 32);
+          const float4 h1 = *reinterpret_cast<const float4*>(rb + 8 * 128), l1 = *reinterpret_cast<const float4*>(rb + 8 * 128 + 32);
+          float4 v0 = make_float4(h0.x + l0.x, h0.y + l0.y, h0.z + l0.z, h0.w + l0.w);
+          float4 v1 = make_float4(h1.x + l1.x, h1.y + l1.y, h1.z + l1.z, h1.w + l1.w);
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m0) {  // GDN / IGDN: v = mul * rsqrt(v) | mul * sqrt(v)
+            const float4 ma = __ldg(reinterpret_cast<const float4*>(m0 + ty0 * m_rs));
+            const float4 mb = two ? __ldg(reinterpret_cast<const float4*>(m0 + (ty0 + 1) * m_rs)) : z4;
+            if (post == TDVC_POST_IGDN) {
+              v0 = make_float4(ma.x * sqrtf(v0.x), ma.y * sqrtf(v0.y), ma.z * sqrtf(v0.z), ma.w * sqrtf(v0.w));
+              v1 = make_float4(mb.x * sqrtf(v1.x), mb.y * sqrtf(v1.y), mb.z * sqrtf(v1.z), mb.w * sqrtf(v1.w));
+            } else {
+              v0 = make_float4(ma.x * rsqrtf(v0.x), ma.y * rsqrtf(v0.y), ma.z * rsqrtf(v0.z), ma.w * rsqrtf(v0.w));
+              v1 = make_float4(mb.x * rsqrtf(v1.x), mb.y * rsqrtf(v1.y), mb.z * rsqrtf(v1.z), mb.w * rsqrtf(v1.w));
             }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = fminf(fmaf(a_neg, fminf(v[e], 0.f), fmaxf(v[e], 0.f)), a_hi);
-            if (r10) {
-              const float4 m = __ldg(reinterpret_cast<const float4*>(r10 + ty * r1_rs));
-              v[0] += m.x; v[1] += m.y; v[2] += m.z; v[3] += m.w;
-            }
-            if (r20) {
-              const float4 m = __ldg(reinterpret_cast<const float4*>(r20 + ty * r2_rs));
-              v[0] += m.x; v[1] += m.y; v[2] += m.z; v[3] += m.w;
-            }
-            *reinterpret_cast<float4*>(o0 + ty * o_rs) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+          float4 ra = z4, rbv = z4, rc = z4, rd = z4;
+          if (r10) {
+            ra = __ldg(reinterpret_cast<const float4*>(r10 + ty0 * r1_rs));
+            if (two) rbv = __ldg(reinterpret_cast<const float4*>(r10 + (ty0 + 1) * r1_rs));
+          }
+          if (r20) {
+            rc = __ldg(reinterpret_cast<const float4*>(r20 + ty0 * r2_rs));
+            if (two) rd = __ldg(reinterpret_cast<const float4*>(r20 + (ty0 + 1) * r2_rs));
+          }
+          // activation a(v) = min(max(v, a_neg * v), a_hi): identity (a_neg 1), ReLU (0), LeakyReLU (slope), clamp01
+          v0.x = fminf(fmaxf(v0.x, a_neg * v0.x), a_hi) + (ra.x + rc.x);
+          v0.y = fminf(fmaxf(v0.y, a_neg * v0.y), a_hi) + (ra.y + rc.y);
+          v0.z = fminf(fmaxf(v0.z, a_neg * v0.z), a_hi) + (ra.z + rc.z);
+          v0.w = fminf(fmaxf(v0.w, a_neg * v0.w), a_hi) + (ra.w + rc.w);
+          *reinterpret_cast<float4*>(o0 + ty0 * o_rs) = v0;
+          if (two) {
+            v1.x = fminf(fmaxf(v1.x, a_neg * v1.x), a_hi) + (rbv.x + rd.x);
+            v1.y = fminf(fmaxf(v1.y, a_neg * v1.y), a_hi) + (rbv.y + rd.y);
+            v1.z = fminf(fmaxf(v1.z, a_neg * v1.z), a_hi) + (rbv.z + rd.z);
+            v1.w = fminf(fmaxf(v1.w, a_neg * v1.w), a_hi) + (rbv.w + rd.w);
+            *reinterpret_cast<float4*>(o0 + (ty0 + 1) * o_rs) = v1;
           }
         } else if (planar) {
           epilogue_planar(p, it, sb, t, ty0, planar_vec);
@@ -313,101 +429,85 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     // LPP lanes cover the CK channels of a pixel (one float4 each), 32/LPP pixels per warp-wide load; the halo is
     // walked as a flat pixel list s = (k*8 + warp)*PPI + lane/LPP.  Each thread keeps, for its PER_WARP loads, the
     // source-pixel offset in a register table (the same for every item and unit), so an interior tile costs one
-    // address instruction per load; all loads of a batch are in flight before the first conversion.
+    // address instruction per load.  The loads of a unit are split into NBATCH batches and software-pipelined across
+    // batches AND units: the loads of batch b+1 (or of the next unit's batch 0) are issued before batch b is converted,
+    // so the memory latency is covered by the fp32 -> fp16 hi/lo conversion of the previous batch.
+    using P = ProdCfg<C, CK>;
     const int pw = warp - kEpiWarps;
-    constexpr int LPP = CK / 4;                       // lanes (float4) per pixel
-    constexpr int PPI = 32 / LPP;                     // pixels per warp-wide load
-    constexpr int NLD = (C::NHALO + PPI - 1) / PPI;   // warp-wide loads per unit
-    constexpr int PER_WARP = (NLD + kProdWarps - 1) / kProdWarps;
-    constexpr int NBATCH = (PER_WARP + 11) / 12;
-    constexpr int BATCH = (PER_WARP + NBATCH - 1) / NBATCH;
-    const int fi = lane % LPP, psub = lane / LPP;
-    const int j8 = fi >> 1, hf = fi & 1;
-    int tab[PER_WARP];   // non-PLANES: source pixel offset hy*STEP*W + hx*STEP;  PLANES: hy << 8 | hx
-    uint32_t vmask = 0;
+    const int fi = lane % P::LPP, psub = lane / P::LPP;
+    ProdThread th;
+    th.pw = pw;
+    th.psub = psub;
+    th.vmask = 0;
+    int tab[P::PER_WARP];   // non-PLANES: source pixel offset hy*STEP*W + hx*STEP;  PLANES: hy << 8 | hx
 #pragma unroll
-    for (int k = 0; k < PER_WARP; ++k) {
-      const int sidx = (k * kProdWarps + pw) * PPI + psub;
+    for (int k = 0; k < P::PER_WARP; ++k) {
+      const int sidx = (k * kProdWarps + pw) * P::PPI + psub;
       const int hy = sidx / C::IW, hx = sidx - hy * C::IW;
       tab[k] = C::PLANES ? ((hy << 8) | hx) : (hy * C::STEP * p.W + hx * C::STEP);
-      if (sidx < C::NHALO) vmask |= 1u << k;
+      if (sidx < C::NHALO) th.vmask |= 1u << k;
     }
-    const uint32_t lane_smem = (uint32_t)((j8 * C::NPIXP) * 16 + hf * 8 + (pw * PPI + psub) * 16);
-    int sX = 0, phX = 1;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    th.lane_smem = (uint32_t)(((fi >> 1) * C::NPIXP) * 16 + (fi & 1) * 8 + (pw * P::PPI + psub) * 16);
+
+    // unit context: where the lane's 4 channels of unit (item, u) come from and which stage they go to
+    int item = blockIdx.x, u = 0, sX = 0, phX = 1;
+    auto setup = [&](ProdUnit& c) {
       const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
-      const int iy0 = it.y0 * S - C::PAD, ix0 = it.x0 * S - C::PAD;
-      const bool interior = iy0 >= 0 && ix0 >= 0 && iy0 + (C::IH - 1) * C::STEP < p.H && ix0 + (C::IW - 1) * C::STEP < p.W;
-      for (int u = 0; u < n_units; ++u) {
-        // resolve this lane's 4 channels (index in the concatenated input) to a source tensor
-        const float* sp = nullptr;
-        int sld = 0;
-        {
-          int cc = u * CK + fi * 4;
+      c.iy0 = it.y0 * S - C::PAD;
+      c.ix0 = it.x0 * S - C::PAD;
+      const float* sp = nullptr;
+      int sld = 0;
+      int cc = u * CK + fi * 4;   // index of this lane's first channel in the concatenated input
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q < p.n_src && sp == nullptr) {
-              if (cc < p.src_c[q]) { sp = p.src[q] + cc; sld = p.src_ld[q]; }
-              else cc -= p.src_c[q];
-            }
-          }
+      for (int q = 0; q < 4; ++q) {
+        if (q < p.n_src && sp == nullptr) {
+          if (cc < p.src_c[q]) { sp = p.src[q] + cc; sld = p.src_ld[q]; }
+          else cc -= p.src_c[q];
         }
-        mbar_wait(bar(X_EMPTY + sX), phX);
-        uint8_t* hi = x_buf + sX * C::X_STAGE + lane_smem;
-        // pointer to this lane's channels of the halo origin pixel (may lie outside the image: only offsets are added)
-        const float* org = sp ? sp + (((int64_t)it.n * p.H + iy0) * p.W + ix0) * sld : nullptr;
-#pragma unroll
-        for (int b = 0; b < NBATCH; ++b) {
-          float4 v[BATCH];
-          if (interior && org != nullptr) {
-#pragma unroll
-            for (int k = 0; k < BATCH; ++k) {
-              const int kk = b * BATCH + k;
-              v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (kk < PER_WARP && ((vmask >> kk) & 1)) {
-                int po = tab[kk < PER_WARP ? kk : 0];
-                if (C::PLANES) po = ((po >> 8) * p.W + (po & 255));
-                v[k] = __ldg(reinterpret_cast<const float4*>(org + (int64_t)po * sld));
-              }
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < BATCH; ++k) {
-              const int kk = b * BATCH + k;
-              const int sidx = (kk * kProdWarps + pw) * PPI + psub;
-              const int hy = sidx / C::IW, hx = sidx - hy * C::IW;
-              const int iy = iy0 + hy * C::STEP, ix = ix0 + hx * C::STEP;
-              v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (kk < PER_WARP && sidx < C::NHALO && org != nullptr && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-                v[k] = __ldg(reinterpret_cast<const float4*>(org + ((int64_t)(hy * C::STEP) * p.W + hx * C::STEP) * sld));
-            }
-          }
-          if (p.in_square) {
-#pragma unroll
-            for (int k = 0; k < BATCH; ++k) { v[k].x *= v[k].x; v[k].y *= v[k].y; v[k].z *= v[k].z; v[k].w *= v[k].w; }
-          }
-#pragma unroll
-          for (int k = 0; k < BATCH; ++k) {
-            const int kk = b * BATCH + k;
-            if (kk < PER_WARP && ((vmask >> kk) & 1)) {
-              uint2 hv, lv;
-              split4(v[k], hv, lv);
-              uint8_t* dst;
-              if (C::PLANES) {
-                const int po = tab[kk < PER_WARP ? kk : 0];
-                dst = hi - (pw * PPI + psub) * 16 + C::slot(po >> 8, po & 255) * 16;
-              } else {
-                dst = hi + kk * (kProdWarps * PPI * 16);   // flat slot = sidx
-              }
-              *reinterpret_cast<uint2*>(dst) = hv;
-              *reinterpret_cast<uint2*>(dst + C::X_HALF) = lv;
-            }
-          }
-        }
-        fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(bar(X_FULL + sX));
-        if (++sX == C::NX) { sX = 0; phX ^= 1; }
       }
+      c.sld = sld;
+      // pointer to this lane's channels of the halo origin pixel (may lie outside the image: only offsets are added)
+      c.org = sp ? sp + (((int64_t)it.n * p.H + c.iy0) * p.W + c.ix0) * sld : nullptr;
+      c.fast = sp != nullptr && c.iy0 >= 0 && c.ix0 >= 0 && c.iy0 + (C::IH - 1) * C::STEP < p.H &&
+               c.ix0 + (C::IW - 1) * C::STEP < p.W;
+      mbar_wait(bar(X_EMPTY + sX), phX);
+      c.stage = sX;
+      c.hi = x_buf + sX * C::X_STAGE + th.lane_smem;
+      if (++sX == C::NX) { sX = 0; phX ^= 1; }
+    };
+    auto advance = [&]() {  // next (item, u) of this CTA; false when there is none
+      if (++u == n_units) { u = 0; item += gridDim.x; }
+      return item < n_items;
+    };
+
+    float4 va[P::BATCH], vb[P::BATCH];
+    ProdUnit cur, nxt;
+    bool have = item < n_items;
+    if (have) {
+      setup(cur);
+      prod_issue<C, P, 0>(p, th, tab, cur, va);
+    }
+    while (have) {
+      bool have_next = false;
+#pragma unroll
+      for (int b = 0; b < P::NBATCH; b += 2) {
+        prod_issue_rt<C, P>(p, th, tab, cur, vb, b + 1);
+        prod_convert_rt<C, P>(p, th, tab, cur, va, b);
+        if (b + 2 < P::NBATCH) {
+          prod_issue_rt<C, P>(p, th, tab, cur, va, b + 2);
+        } else {
+          have_next = advance();
+          if (have_next) {
+            setup(nxt);
+            prod_issue<C, P, 0>(p, th, tab, nxt, va);
+          }
+        }
+        prod_convert_rt<C, P>(p, th, tab, cur, vb, b + 1);
+      }
+      fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(bar(X_FULL + cur.stage));
+      cur = nxt;
+      have = have_next;
     }
   } else if (warp == kMmaWarp) {
     // ===================================================================== MMA issuer (one elected thread)
