@@ -26,6 +26,20 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
+// images (C <= 4, ld == 4): one pixel per thread, coalesced plane reads, one 16-byte store
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t HW, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, px = i - n * HW;
+    const float* s = src + n * C * HW + px;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = __ldg(s);
+    if (C > 1) v.y = __ldg(s + HW);
+    if (C > 2) v.z = __ldg(s + 2 * HW);
+    if (C > 3) v.w = __ldg(s + 3 * HW);
+    reinterpret_cast<float4*>(dst)[i] = v;
+  }
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, int C, int64_t HW) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -194,6 +208,14 @@ using namespace tdvc;
 extern "C" int tdvc_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int dst_ld, void* stream) {
   TDVC_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && dst_ld >= C, "nchw_to_nhwc: bad args");
   const int64_t HW = (int64_t)H * W;
+  if (C <= 4 && dst_ld == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int64_t total = (int64_t)N * HW;
+    int g = cdiv(total, 256);
+    if (g > kNumSMs * 16) g = kNumSMs * 16;
+    nchw_to_nhwc4_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(src, dst, C, HW, total);
+    TDVC_CHECK_LAUNCH("nchw_to_nhwc");
+    return TDVC_OK;
+  }
   dim3 grid(cdiv(HW, 32), cdiv(dst_ld, 32), N), block(32, 8);
   nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW, dst_ld);
   TDVC_CHECK_LAUNCH("nchw_to_nhwc");

@@ -6,9 +6,10 @@
 
 namespace tdvc {
 
-// nn.AvgPool2d(scale): one CTA per pooled cell; C/4 float4 lanes x (256/(C/4)) pixel lanes, fixed-order reduce.
-__global__ void avgpool_scale_kernel(const float* __restrict__ x, int ld, float* __restrict__ out, int H, int W, int C,
-                                     int scale, int ph, int pw) {
+// nn.AvgPool2d(scale): one CTA of 1024 threads per pooled cell; C/4 float4 lanes x (1024/(C/4)) pixel lanes, four
+// independent partial sums per thread (loads in flight), fixed-order tree over the pixel lanes: deterministic.
+__global__ void __launch_bounds__(1024) avgpool_scale_kernel(const float* __restrict__ x, int ld, float* __restrict__ out, int H,
+                                                             int W, int C, int scale, int ph, int pw) {
   extern __shared__ float4 sh4[];
   const int lanes_c = C >> 2;
   const int lanes_p = blockDim.x / lanes_c;
@@ -16,26 +17,44 @@ __global__ void avgpool_scale_kernel(const float* __restrict__ x, int ld, float*
   const int cell = blockIdx.x, n = blockIdx.y;
   const int cy = cell / pw, cx = cell - cy * pw;
   const float* base = x + (((int64_t)n * H + (int64_t)cy * scale) * W + (int64_t)cx * scale) * ld + c4 * 4;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 s[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (pl < lanes_p) {
     const int total = scale * scale;
-    for (int q = pl; q < total; q += lanes_p) {
-      const int qy = q / scale, qx = q - qy * scale;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)qy * W + qx) * ld));
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    for (int q0 = pl; q0 < total; q0 += 4 * lanes_p) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = q0 + j * lanes_p;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < total) {
+          const int qy = q / scale, qx = q - qy * scale;
+          v[j] = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)qy * W + qx) * ld));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[j].x += v[j].x; s[j].y += v[j].y; s[j].z += v[j].z; s[j].w += v[j].w; }
     }
   }
-  sh4[threadIdx.x] = s;
+  float4 t = make_float4((s[0].x + s[1].x) + (s[2].x + s[3].x), (s[0].y + s[1].y) + (s[2].y + s[3].y),
+                         (s[0].z + s[1].z) + (s[2].z + s[3].z), (s[0].w + s[1].w) + (s[2].w + s[3].w));
+  sh4[threadIdx.x] = t;
   __syncthreads();
-  if (threadIdx.x < lanes_c) {
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < lanes_p; ++q) {
-      const float4 v = sh4[q * lanes_c + threadIdx.x];
-      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+  for (int stride = 1; stride < lanes_p; stride <<= 1) {  // pairwise tree over the pixel lanes (lanes_p is a power of two)
+    if (pl < lanes_p && (pl % (2 * stride)) == 0 && pl + stride < lanes_p) {
+      float4 a = sh4[threadIdx.x];
+      const float4 b = sh4[threadIdx.x + stride * lanes_c];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      sh4[threadIdx.x] = a;
     }
+    __syncthreads();
+  }
+  if (threadIdx.x < lanes_c) {
+    float4 r = sh4[threadIdx.x];
     const float d = (float)(scale * scale);
-    t.x /= d; t.y /= d; t.z /= d; t.w /= d;
-    reinterpret_cast<float4*>(out + (((int64_t)n * ph + cy) * pw + cx) * C)[threadIdx.x] = t;
+    r.x /= d; r.y /= d; r.z /= d; r.w /= d;
+    reinterpret_cast<float4*>(out + (((int64_t)n * ph + cy) * pw + cx) * C)[threadIdx.x] = r;
   }
 }
 
@@ -136,10 +155,10 @@ using namespace tdvc;
 
 extern "C" int tdvc_avgpool_scale(const float* x, int ld, float* out, int N, int H, int W, int C, int scale, void* stream) {
   TDVC_REQUIRE(x && out && N > 0 && scale > 0 && H >= scale && W >= scale, "avgpool_scale: bad args");
-  TDVC_REQUIRE(C % 4 == 0 && C <= 1024 && ld % 4 == 0, "avgpool_scale: C/ld");
+  TDVC_REQUIRE(C % 4 == 0 && C <= 1024 && ld % 4 == 0 && ((C >> 2) & ((C >> 2) - 1)) == 0, "avgpool_scale: C/4 must be a power of two <= 256, ld %% 4 == 0");
   const int ph = H / scale, pw = W / scale;
   dim3 grid(ph * pw, N);
-  avgpool_scale_kernel<<<grid, 256, 256 * sizeof(float4), (cudaStream_t)stream>>>(x, ld, out, H, W, C, scale, ph, pw);
+  avgpool_scale_kernel<<<grid, 1024, 1024 * sizeof(float4), (cudaStream_t)stream>>>(x, ld, out, H, W, C, scale, ph, pw);
   TDVC_CHECK_LAUNCH("avgpool_scale");
   return TDVC_OK;
 }
