@@ -107,56 +107,39 @@ __device__ __forceinline__ Item decode_item(int item, int n_jt, int tiles_x, int
   return it;
 }
 
-// Rare epilogue paths, kept out of line so that the hot loop stays small.
-// NCHW planes (`out_planar`): thread = (channel, tile row); 8 x-adjacent pixels are contiguous in the plane.
-__device__ __noinline__ void epilogue_planar(const TdvcConvParams& p, const Item& it, const float* sb, int t, int ty0, bool vec) {
-  const int ch = t & 63, h2 = t >> 6;
-  const int ty = ty0 + h2;
-  const int cp = it.jt * NT + ch;
-  if (cp >= p.cout || it.y0 + ty >= p.Ho) return;
-  const float* rb = sb + h2 * (8 * 128) + (ch >> 5) * 64 + (ch & 31);
-  float v[8];
-#pragma unroll
-  for (int x = 0; x < 8; ++x) v[x] = apply_act(rb[x * 128] + rb[x * 128 + 32], p.act, p.slope);
-  float* op = p.out + (((int64_t)it.n * p.cout + cp) * p.Ho + (it.y0 + ty)) * p.Wo + it.x0;
-  if (vec && it.x0 + 8 <= p.Wo) {
-    reinterpret_cast<float4*>(op)[0] = make_float4(v[0], v[1], v[2], v[3]);
-    reinterpret_cast<float4*>(op)[1] = make_float4(v[4], v[5], v[6], v[7]);
-  } else {
-#pragma unroll
-    for (int x = 0; x < 8; ++x)
-      if (it.x0 + x < p.Wo) op[x] = v[x];
-  }
-}
-
-// Ragged channel counts (cout % 4 != 0) or unaligned / odd-pitch views: one element at a time.
-__device__ __noinline__ void epilogue_ragged(const TdvcConvParams& p, const Item& it, const float* sb, int tx, int rd_off, int co,
-                                              int ty0) {
-  const int sh = p.shuffle == 2 ? 2 : 1;
-  const int cr = p.cout >> 2;
+// Rare epilogue path, kept out of line so that the hot loop stays small: ragged channel counts (cout % 4 != 0) or
+// unaligned / odd-pitch views, one element at a time.
+struct RaggedArgs {   // passed by value (registers): taking the kernel parameter block by reference would move it to local memory
+  float* out; const float* mul; const float* res1; const float* res2;
+  int out_ld, mul_ld, res1_ld, res2_ld, post, act, shuffle, cout, Ho, Wo;
+  float slope;
+};
+__device__ __noinline__ void epilogue_ragged(RaggedArgs a, int n, int y0, int x0, const float* sb, int tx, int rd_off, int co, int ty0) {
+  const int sh = a.shuffle == 2 ? 2 : 1;
+  const int cr = a.cout >> 2;
   for (int h2 = 0; h2 < 2; ++h2) {
-    const int y = it.y0 + ty0 + h2, x = it.x0 + tx;
-    if (y >= p.Ho) continue;
+    const int y = y0 + ty0 + h2, x = x0 + tx;
+    if (y >= a.Ho) continue;
     const float* rb = sb + (h2 * 8 + tx) * 128 + rd_off;
     for (int e = 0; e < 4; ++e) {
       const int ce = co + e;
-      if (ce >= p.cout) break;
+      if (ce >= a.cout) break;
       int oce = ce;
-      int64_t pe = ((int64_t)it.n * p.Ho + y) * p.Wo + x;
+      int64_t pe = ((int64_t)n * a.Ho + y) * a.Wo + x;
       if (sh == 2) {
         const int q = ce / cr;
         oce = ce - q * cr;
-        pe = ((int64_t)it.n * (2 * p.Ho) + (2 * y + (q >> 1))) * (2 * p.Wo) + (2 * x + (q & 1));
+        pe = ((int64_t)n * (2 * a.Ho) + (2 * y + (q >> 1))) * (2 * a.Wo) + (2 * x + (q & 1));
       }
       float o = rb[e] + rb[e + 32];
-      if (p.post != TDVC_POST_NONE) {
-        const float mv = __ldg(p.mul + pe * p.mul_ld + oce);
-        o = mv * (p.post == TDVC_POST_IGDN ? sqrtf(o) : rsqrtf(o));
+      if (a.post != TDVC_POST_NONE) {
+        const float mv = __ldg(a.mul + pe * a.mul_ld + oce);
+        o = mv * (a.post == TDVC_POST_IGDN ? sqrtf(o) : rsqrtf(o));
       }
-      o = apply_act(o, p.act, p.slope);
-      if (p.res1) o += __ldg(p.res1 + pe * p.res1_ld + oce);
-      if (p.res2) o += __ldg(p.res2 + pe * p.res2_ld + oce);
-      p.out[pe * p.out_ld + oce] = o;
+      o = apply_act(o, a.act, a.slope);
+      if (a.res1) o += __ldg(a.res1 + pe * a.res1_ld + oce);
+      if (a.res2) o += __ldg(a.res2 + pe * a.res2_ld + oce);
+      a.out[pe * a.out_ld + oce] = o;
     }
   }
 }
@@ -320,6 +303,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
                         (post == TDVC_POST_NONE || ((p.mul_ld & 3) == 0 && al16(p.mul))) &&
                         (!p.res1 || ((p.res1_ld & 3) == 0 && al16(p.res1))) && (!p.res2 || ((p.res2_ld & 3) == 0 && al16(p.res2)));
     const bool planar_vec = planar && (Wo & 3) == 0 && al16(p.out);
+    // a plain store may also fill the pad lanes of a channel-padded view (weight rows >= cout are zero, no bias there)
+    const int cout_st = (sh == 1 && post == TDVC_POST_NONE && !p.res1 && !p.res2 && p.out_ld >= ((cout + 3) & ~3)) ? ((cout + 3) & ~3) : cout;
     // branch-free activation: a(v) = min(max(v, a_neg * v), a_hi)   (0 <= a_neg <= 1)
     const float a_neg = act == TDVC_ACT_NONE ? 1.f : (act == TDVC_ACT_LRELU ? p.slope : 0.f);
     const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
@@ -347,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         qx = q & 1;
       }
       const bool th_ok = it.x0 + tx < Wo && co < cout;
-      const bool th_vec = vec_ok && co + 4 <= cout;
+      const bool th_vec = vec_ok && co + 4 <= cout_st;
       const int ny = Ho - it.y0;  // valid tile rows
       const int64_t pix0 = ((int64_t)it.n * oH + (it.y0 * sh + qy)) * oW + ((it.x0 + tx) * sh + qx);
       float* const o0 = p.out + pix0 * p.out_ld + oc;
@@ -358,6 +343,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128), r);
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
+        const int ty0 = half * 16 + c * 2;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 ma = z4, mb = z4, ra = z4, rbv = z4, rc = z4, rd = z4;
+        const bool row0 = th_vec && th_ok && ty0 < ny, row1 = row0 && ty0 + 1 < ny;
         tmem_ld_wait();
         if (c == 7) {  // all TMEM reads of this warp are done: the accumulator stage may be overwritten
           tc_fence_before();
@@ -374,19 +363,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         // next chunk's accumulator columns: the TMEM read overlaps the barrier and the read phase below
         if (c < 7) tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128 + (c + 1) * 16), r);
         asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-        const int ty0 = half * 16 + c * 2;
         if (th_vec) {
-          if (!th_ok || ty0 >= ny) continue;
-          const bool two = ty0 + 1 < ny;
+          if (!row0) continue;
+          const bool two = row1;
+          // residual / GDN-multiplier rows (issuing them before the slab exchange measured 2 % slower: more live registers)
+          if (m0) { ma = __ldg(reinterpret_cast<const float4*>(m0 + ty0 * m_rs)); if (two) mb = __ldg(reinterpret_cast<const float4*>(m0 + (ty0 + 1) * m_rs)); }
+          if (r10) { ra = __ldg(reinterpret_cast<const float4*>(r10 + ty0 * r1_rs)); if (two) rbv = __ldg(reinterpret_cast<const float4*>(r10 + (ty0 + 1) * r1_rs)); }
+          if (r20) { rc = __ldg(reinterpret_cast<const float4*>(r20 + ty0 * r2_rs)); if (two) rd = __ldg(reinterpret_cast<const float4*>(r20 + (ty0 + 1) * r2_rs)); }
           const float* rb = sb + tx * 128 + rd_off;
           const float4 h0 = *reinterpret_cast<const float4*>(rb), l0 = *reinterpret_cast<const float4*>(rb + 32);
           const float4 h1 = *reinterpret_cast<const float4*>(rb + 8 * 128), l1 = *reinterpret_cast<const float4*>(rb + 8 * 128 + 32);
           float4 v0 = make_float4(h0.x + l0.x, h0.y + l0.y, h0.z + l0.z, h0.w + l0.w);
           float4 v1 = make_float4(h1.x + l1.x, h1.y + l1.y, h1.z + l1.z, h1.w + l1.w);
-          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (m0) {  // GDN / IGDN: v = mul * rsqrt(v) | mul * sqrt(v)
-            const float4 ma = __ldg(reinterpret_cast<const float4*>(m0 + ty0 * m_rs));
-            const float4 mb = two ? __ldg(reinterpret_cast<const float4*>(m0 + (ty0 + 1) * m_rs)) : z4;
             if (post == TDVC_POST_IGDN) {
               v0 = make_float4(ma.x * sqrtf(v0.x), ma.y * sqrtf(v0.y), ma.z * sqrtf(v0.z), ma.w * sqrtf(v0.w));
               v1 = make_float4(mb.x * sqrtf(v1.x), mb.y * sqrtf(v1.y), mb.z * sqrtf(v1.z), mb.w * sqrtf(v1.w));
@@ -394,15 +383,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
               v0 = make_float4(ma.x * rsqrtf(v0.x), ma.y * rsqrtf(v0.y), ma.z * rsqrtf(v0.z), ma.w * rsqrtf(v0.w));
               v1 = make_float4(mb.x * rsqrtf(v1.x), mb.y * rsqrtf(v1.y), mb.z * rsqrtf(v1.z), mb.w * rsqrtf(v1.w));
             }
-          }
-          float4 ra = z4, rbv = z4, rc = z4, rd = z4;
-          if (r10) {
-            ra = __ldg(reinterpret_cast<const float4*>(r10 + ty0 * r1_rs));
-            if (two) rbv = __ldg(reinterpret_cast<const float4*>(r10 + (ty0 + 1) * r1_rs));
-          }
-          if (r20) {
-            rc = __ldg(reinterpret_cast<const float4*>(r20 + ty0 * r2_rs));
-            if (two) rd = __ldg(reinterpret_cast<const float4*>(r20 + (ty0 + 1) * r2_rs));
           }
           // activation a(v) = min(max(v, a_neg * v), a_hi): identity (a_neg 1), ReLU (0), LeakyReLU (slope), clamp01
           v0.x = fminf(fmaxf(v0.x, a_neg * v0.x), a_hi) + (ra.x + rc.x);
@@ -417,10 +397,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             v1.w = fminf(fmaxf(v1.w, a_neg * v1.w), a_hi) + (rbv.w + rd.w);
             *reinterpret_cast<float4*>(o0 + (ty0 + 1) * o_rs) = v1;
           }
-        } else if (planar) {
-          epilogue_planar(p, it, sb, t, ty0, planar_vec);
+        } else if (planar) {  // NCHW planes: thread = (channel, tile row); 8 x-adjacent pixels are contiguous in the plane
+          const int ch = t & 63, h2 = t >> 6;
+          const int ty = ty0 + h2;
+          const int cp = it.jt * NT + ch;
+          if (cp < cout && ty < ny) {
+            const float* rb = sb + h2 * (8 * 128) + (ch >> 5) * 64 + (ch & 31);
+            float v[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+              const float o = rb[x * 128] + rb[x * 128 + 32];
+              v[x] = fminf(fmaxf(o, a_neg * o), a_hi);
+            }
+            float* op = p.out + (((int64_t)it.n * cout + cp) * Ho + (it.y0 + ty)) * Wo + it.x0;
+            if (planar_vec && it.x0 + 8 <= Wo) {
+              reinterpret_cast<float4*>(op)[0] = make_float4(v[0], v[1], v[2], v[3]);
+              reinterpret_cast<float4*>(op)[1] = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+              for (int x = 0; x < 8; ++x)
+                if (it.x0 + x < Wo) op[x] = v[x];
+            }
+          }
         } else if (th_ok) {
-          epilogue_ragged(p, it, sb, tx, rd_off, co, ty0);
+          epilogue_ragged(RaggedArgs{p.out, p.mul, p.res1, p.res2, p.out_ld, p.mul_ld, p.res1_ld, p.res2_ld, post, act, p.shuffle,
+                                     cout, Ho, Wo, p.slope},
+                          it.n, it.y0, it.x0, sb, tx, rd_off, co, ty0);
         }
       }
     }

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtdvc_b200.so")
+LIB_PATH = os.environ.get("TDVC_B200_LIB") or os.path.join(HERE, "libtdvc_b200.so")   # override: developer A/B builds only
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_CLAMP01 = 0, 1, 2, 3
 POST_NONE, POST_GDN, POST_IGDN = 0, 1, 2

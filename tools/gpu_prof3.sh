@@ -1,0 +1,6 @@
+set -x
+python tools/conv_bench.py 64 216 3 1024 1920 2 3 1 1 1 0 > gpurun_out/plain_planar.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 3 -c 1 -f -o gpurun_out/prof_planar python tools/conv_bench.py 64 216 3 1024 1920 2 3 1 1 1 0 > gpurun_out/ncu_planar.log 2>&1
+python tools/conv_bench.py 64 64 3 1024 1920 2 5 1 1 0 2 1
+python tools/conv_bench.py 64 3 3 1024 1920 2 5 1 1 0 3
+python tools/tc_check.py | tail -2
