@@ -47,7 +47,7 @@ const char* tdvc_last_error(void);
  * permuted on the host to co' = (dy*2+dx)*(cout/4) + c (nn.PixelShuffle folded into the store).
  * Constraints: src_c[i] % 4 == 0, src_ld[i] % 4 == 0, 16-byte aligned sources, cin_pad % 8 == 0,
  * cout_pad % 16 == 0.  `impl`: 0 = auto, 1 = SIMT fp32 FFMA kernel, 2 = tcgen05 tensor-core kernel
- * (3xFP16 split: x = hi + lo in fp16, x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, fp32 accumulate in TMEM; needs weight_f16).                                       */
+ * (fp16 split: x = hi + lo, w = hi + lo, (w_hi + w_lo)*(x_hi + x_lo), fp32 accumulate in TMEM; needs weight_f16).                                             */
 typedef struct {
   const float* src[4];
   int32_t src_c[4];
@@ -108,7 +108,7 @@ typedef struct {
   int32_t N, H, W, C, O, O_pad, dg;
   int32_t round_fp16;
   int32_t act; float slope;
-  int32_t impl;                           /* 0 = auto, 1 = SIMT fp32 contraction, 2 = tcgen05 (3xFP16 split) */
+  int32_t impl;                           /* 0 = auto, 1 = SIMT fp32 contraction, 2 = tcgen05 (fp16 hi/lo split) */
   const void* weight_f16;                 /* tcgen05 path: tdvc_dcn_pack_f16 output, or NULL */
   /* tcgen05 path (csrc/dcn_tc.cu) reads gather-friendly layouts instead of `input` / channels-last offsets:   */
   const float* input_gp;                  /* "group planar" input [(n*dg + g)][H][W][8] (tdvc_nhwc_to_group_planar) */

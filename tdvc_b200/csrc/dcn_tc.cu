@@ -167,9 +167,27 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const TdvcDcnParams
         mbar_wait(bar(A_EMPTY + st), ((a_it / NA) & 1) ^ 1);
         uint8_t* stage = a_buf + st * A_STAGE;
         const float* in_g = p.input_gp + ((int64_t)n * dg + g) * HW * 8;
-        // 8 row pairs x 9 taps = 72 warp tasks per stage, 6 per producer warp
-#pragma unroll 1
-        for (int q = pw; q < 72; q += kProdWarps) {
+        // 8 row pairs x 9 taps = 72 warp tasks per stage, 6 per producer warp.  The three parameters (dy, dx, mask) of all
+        // six tasks are loaded first (18 coalesced loads in flight), so each task then waits for ONE memory latency
+        // (its four corner sectors) instead of two.
+        constexpr int TPW = 72 / kProdWarps;
+        float pdy[TPW], pdx[TPW], pmk[TPW];
+#pragma unroll
+        for (int j = 0; j < TPW; ++j) {
+          const int q = pw + j * kProdWarps;
+          const int rp = q & 7, tap = q >> 3;
+          const int y = y0 + 2 * rp + (lane >> 4), x = x0 + (lane & 15);
+          pdy[j] = pdx[j] = pmk[j] = 0.f;
+          if (y < H && x < W) {
+            const int64_t pix = (int64_t)y * W + x;
+            pdy[j] = __ldg(off_n + (int64_t)(g * 18 + 2 * tap) * HW + pix);
+            pdx[j] = __ldg(off_n + (int64_t)(g * 18 + 2 * tap + 1) * HW + pix);
+            pmk[j] = __ldg(msk_n + (int64_t)(g * 9 + tap) * HW + pix);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < TPW; ++j) {
+          const int q = pw + j * kProdWarps;
           const int rp = q & 7, tap = q >> 3;
           const int ly = 2 * rp + (lane >> 4), lx = lane & 15;
           const int y = y0 + ly, x = x0 + lx;
@@ -178,10 +196,8 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const TdvcDcnParams
 #pragma unroll
           for (int c = 0; c < 8; ++c) val[c] = 0.f;
           if (y < H && x < W) {
-            const int64_t pix = (int64_t)y * W + x;
-            const float dy = __ldg(off_n + (int64_t)(g * 18 + 2 * tap) * HW + pix);
-            const float dx = __ldg(off_n + (int64_t)(g * 18 + 2 * tap + 1) * HW + pix);
-            float mk = __ldg(msk_n + (int64_t)(g * 9 + tap) * HW + pix);
+            const float dy = pdy[j], dx = pdx[j];
+            float mk = pmk[j];
             if (p.mask_is_logit) mk = sigmoid_exact(mk);
             const int ki = tap / 3, kj = tap - ki * 3;
             const float h_im = (float)(y - 1 + ki) + dy;
@@ -220,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const TdvcDcnParams
     }
   } else if (warp == kMmaWarp) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t IDESC_2N = instr_desc(2 * NT), IDESC_N = instr_desc(NT);
       const uint32_t a0 = smem_u32(a_buf), b0 = smem_u32(b_buf);
       int a_it = 0, acc_it = 0;
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const TdvcDcnParams
     }
   } else {
     // ===================================================================== weight loader
-    if (lane == 0) {
+    if (elect_one()) {
       const uint8_t* wb = static_cast<const uint8_t*>(p.weight_f16);
       const uint32_t b0 = smem_u32(b_buf);
       int b_it = 0;

@@ -1,4 +1,4 @@
-"""Host side of the tcgen05 (3xFP16 split) convolution: asks the C-ABI which packed convolutions have a
+"""Host side of the tcgen05 (fp16 hi/lo split) convolution: asks the C-ABI which packed convolutions have a
 tensor-core path and lets it build their fp16 (hi, lo) weight blocks on the device (csrc/conv_tc.cu)."""
 import torch
 

@@ -1,6 +1,6 @@
 """GPU tests (-m gpu): each CUDA kernel, called through the C-ABI, against the oracle / plain torch fp32 on the
 CPU for the same seeded inputs.  Tolerances: fp32 kernels 2e-5 relative to the output scale (different
-summation order only); the tcgen05 3xFP16-split convolution 2e-4 relative (|a_lo*b_lo| and bf16 residual
+summation order only); the tcgen05 fp16 hi/lo-split convolution 2e-4 relative (fp16 residual
 rounding, ~2^-16 per product); integer / index outputs bit-exact."""
 import math
 
@@ -105,7 +105,7 @@ TC_CASES = [
 
 @pytest.mark.parametrize("idx", range(len(TC_CASES)))
 def test_conv2d_tcgen05_vs_torch(plan, dev, idx):
-    """impl=2 forces the tensor-core kernel (3xFP16 split, fp32 accumulate): 2e-4 of the output scale."""
+    """impl=2 forces the tensor-core kernel (fp16 hi/lo split, fp32 accumulate): 2e-4 of the output scale."""
     cin_list, cout, k, stride, H, W, kw = TC_CASES[idx]
     got, want = _conv_case(plan, dev, cin_list, cout, k, stride, H, W, impl=2, seed=100 + idx, **kw)
     assert got.shape == want.shape
@@ -183,7 +183,7 @@ def test_dcn_forward_vs_oracle(dev, shape):
 def test_dcn_tcgen05_vs_oracle(dev, shape):
     """csrc/dcn_tc.cu (gather producers + tcgen05 contraction, group-planar input, planar offsets / mask logits)
     against the oracle restatement, including the reference's fp16 rounding of the result
-    (dcn_v2_amp.py:67-69) and the LeakyReLU evaluated on the Half tensor (pnet.py:180).  Tolerance: the 3xFP16
+    (dcn_v2_amp.py:67-69) and the LeakyReLU evaluated on the Half tensor (pnet.py:180).  Tolerance: the fp16 hi/lo
     split keeps ~2^-22 per product; after the fp16 rounding at most one fp16 ulp may differ
     where the fp32 value sits on a rounding boundary."""
     from oracle import dcn_naive

@@ -4,7 +4,7 @@ golden fixtures produced by the reference's own unmodified code (tests/golden, o
 
 Bars (BASELINE.json north_star): reconstruction <= 1e-3 max-abs, PSNR within 0.01 dB, bpp within 0.1 % relative,
 >= 99.9 % of quantised latent symbols identical.  The exact-fp32 path (conv_impl=1) and the tensor-core path
-(conv_impl=0: 3xFP16-split tcgen05 MMA, fp32 accumulate) are both held to the same bars.
+(conv_impl=0: fp16 hi/lo-split tcgen05 MMA, fp32 accumulate) are both held to the same bars.
 """
 import math
 
