@@ -71,6 +71,8 @@ typedef struct {
   int32_t impl;
   const void* weight_f16;  /* tcgen05 path: fp16 (hi | lo*2^12) weight blocks built by tdvc_conv2d_pack_f16, or NULL */
   float* chan_sum;          /* optional [N][gridDim-dependent] — reserved for fused SE partial sums */
+  int32_t w_shift;          /* tcgen05 split scheme (tdvc_conv2d_f16_is_split): the fp16 weight blocks hold w * 2^w_shift, chosen by
+                               the caller so that max|w| * 2^w_shift lies in [2^13, 2^14]; same value at pack time and at launch */
   int32_t out_planar;       /* 1: store NCHW planes, out[((n*cout + c)*Ho + y)*Wo + x] (no shuffle / residual / post);
                                the DCN offset/mask head writes the reference's planar offset & mask tensors this way */
 } TdvcConvParams;
@@ -80,6 +82,8 @@ int tdvc_conv2d(const TdvcConvParams* p, void* stream);
  * post, in_square) and `weight` are read.  bytes == 0: the shape has no tensor-core path (SIMT kernel is used). */
 size_t tdvc_conv2d_f16_bytes(const TdvcConvParams* p);
 int tdvc_conv2d_pack_f16(const TdvcConvParams* p, void* out, void* stream);
+/* 1 when the shape uses the 3-product split scheme (128-channel tiles; needs p->w_shift), else 0 */
+int tdvc_conv2d_f16_is_split(const TdvcConvParams* p);
 
 /* ---- DCNv2 forward, the reference's `_ext.dcn_v2_forward` (dcn_v2.h:9-46): contiguous NCHW fp32,
  * offset (N, 2*dg*kh*kw, H, W) ordered [g][tap][dy,dx], mask (N, dg*kh*kw, H, W), weight (O, C, kh, kw),

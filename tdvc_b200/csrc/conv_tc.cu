@@ -48,7 +48,11 @@ constexpr int TW = 8, TH = 32, NPX = TW * TH;  // output tile = N of one MMA
 constexpr int NT = 64;                         // output channels per item (M = 2*NT rows: hi, lo)
 constexpr int kStageBytes = 2 * 2 * 16 * 128 * 4;  // epilogue transposition: 2 pixel halves x 2 buffers x [16 px][128 rows] fp32
 
-template <int KS, int CK, int S>
+// SPLIT = 0: item = 64 output channels, weight rows [hi | lo*2^12] of those channels (4 products, 2 MMAs per k-step);
+// SPLIT = 1: item = 128 output channels, separate W_hi / W_lo blocks (pre-scaled by 2^w_shift so that W_lo stays in
+//            the fp16 normal range) accumulating into ONE row per channel: x_hi*w_hi + x_lo*w_hi + x_hi*w_lo,
+//            3 MMAs per k-step for twice the channels (-25 % tensor work) and no hi/lo merge in the epilogue.
+template <int KS, int CK, int S, int SPLIT = 0>
 struct Cfg {
   static_assert(S == 1 || (S == 2 && (KS == 1 || KS == 3)), "stride");
   static_assert(CK == 16 || CK == 32, "cin chunk");
@@ -71,11 +75,13 @@ struct Cfg {
   static constexpr int X_HALF = NCH8 * NPIXP * 16;   // bytes of the hi (or lo) plane of one unit
   static constexpr int X_STAGE = 2 * X_HALF;
   static constexpr int LBO_X = NPIXP * 16, SBO_X = PW * 16;
-  static constexpr int W_BLOCK = 2 * NT * CK * 2;    // [128 rows][CK] fp16
+  static constexpr int NTT = SPLIT ? 128 : 64;       // output channels per item
+  static constexpr int W_HALF = 128 * CK * 2;        // one [128 rows][CK] fp16 block
+  static constexpr int W_BLOCK = SPLIT ? 2 * W_HALF : W_HALF;   // SPLIT: [W_hi block | W_lo block]
   static constexpr int LBO_W = 128, SBO_W = NCH8 * 128;
   static constexpr int KSTEPS = CK / 16;
   static constexpr int TAPS = KS * KS;
-  static constexpr int NW = (CK == 32) ? 4 : 6;
+  static constexpr int NW = (CK == 32) ? 4 : (SPLIT ? 4 : 6);
   static constexpr int NX = (3 * X_STAGE + NW * W_BLOCK + kStageBytes + 256 <= 227 * 1024) ? 3 : 2;
   static constexpr int SMEM = NX * X_STAGE + NW * W_BLOCK + kStageBytes + 256;
   static_assert(NPIXP >= NPIX, "pitch");
@@ -114,7 +120,8 @@ struct RaggedArgs {   // passed by value (registers): taking the kernel paramete
   int out_ld, mul_ld, res1_ld, res2_ld, post, act, shuffle, cout, Ho, Wo;
   float slope;
 };
-__device__ __noinline__ void epilogue_ragged(RaggedArgs a, int n, int y0, int x0, const float* sb, int tx, int rd_off, int co, int ty0) {
+__device__ __noinline__ void epilogue_ragged(RaggedArgs a, int n, int y0, int x0, const float* sb, int tx, int rd_off, int co, int ty0,
+                                              int lo_off) {
   const int sh = a.shuffle == 2 ? 2 : 1;
   const int cr = a.cout >> 2;
   for (int h2 = 0; h2 < 2; ++h2) {
@@ -131,7 +138,7 @@ __device__ __noinline__ void epilogue_ragged(RaggedArgs a, int n, int y0, int x0
         oce = ce - q * cr;
         pe = ((int64_t)n * (2 * a.Ho) + (2 * y + (q >> 1))) * (2 * a.Wo) + (2 * x + (q & 1));
       }
-      float o = rb[e] + rb[e + 32];
+      float o = lo_off ? rb[e] + rb[e + lo_off] : rb[e];
       if (a.post != TDVC_POST_NONE) {
         const float mv = __ldg(a.mul + pe * a.mul_ld + oce);
         o = mv * (a.post == TDVC_POST_IGDN ? sqrtf(o) : rsqrtf(o));
@@ -225,14 +232,16 @@ __device__ __forceinline__ void prod_convert(const TdvcConvParams& p, const Prod
   }
 }
 
-// batch index known only after unrolling the caller's loop (it is a compile-time constant there): dispatch 0..3
+// batch index known only after unrolling the caller's loop (it is a compile-time constant there): dispatch 0..5
 template <class C, class P>
 __device__ __forceinline__ void prod_issue_rt(const TdvcConvParams& p, const ProdThread& th, const int (&tab)[P::PER_WARP],
                                               const ProdUnit& c, float4 (&v)[P::BATCH], int b) {
   if (b == 0) prod_issue<C, P, 0>(p, th, tab, c, v);
   else if (b == 1) prod_issue<C, P, 1>(p, th, tab, c, v);
   else if (b == 2) prod_issue<C, P, 2>(p, th, tab, c, v);
-  else prod_issue<C, P, 3>(p, th, tab, c, v);
+  else if (b == 3) prod_issue<C, P, 3>(p, th, tab, c, v);
+  else if (b == 4) prod_issue<C, P, 4>(p, th, tab, c, v);
+  else prod_issue<C, P, 5>(p, th, tab, c, v);
 }
 template <class C, class P>
 __device__ __forceinline__ void prod_convert_rt(const TdvcConvParams& p, const ProdThread& th, const int (&tab)[P::PER_WARP],
@@ -240,13 +249,15 @@ __device__ __forceinline__ void prod_convert_rt(const TdvcConvParams& p, const P
   if (b == 0) prod_convert<C, P, 0>(p, th, tab, c, v);
   else if (b == 1) prod_convert<C, P, 1>(p, th, tab, c, v);
   else if (b == 2) prod_convert<C, P, 2>(p, th, tab, c, v);
-  else prod_convert<C, P, 3>(p, th, tab, c, v);
+  else if (b == 3) prod_convert<C, P, 3>(p, th, tab, c, v);
+  else if (b == 4) prod_convert<C, P, 4>(p, th, tab, c, v);
+  else prod_convert<C, P, 5>(p, th, tab, c, v);
 }
 
-template <int KS, int CK, int S>
+template <int KS, int CK, int S, int SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvParams p, int tiles_x, int tiles_y, int n_jt,
                                                               int n_units, int n_items) {
-  using C = Cfg<KS, CK, S>;
+  using C = Cfg<KS, CK, S, SPLIT>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* x_buf = smem;                                  // NX stages of [hi plane | lo plane]
   uint8_t* w_buf = smem + C::NX * C::X_STAGE;             // NW weight blocks
@@ -286,6 +297,151 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     //          the lo rows are rescaled and carry the bias;
     //   read : thread = (tile column tx, 4 consecutive output channels) -> hi + lo as two float4, GDN / activation /
     //          residuals, one 16-byte store per tile row: 16 lanes cover the 256 contiguous bytes of an NHWC pixel.
+    if constexpr (SPLIT == 1) {
+    // ---- 128 output channels per item, one accumulator row per channel: write = TMEM lane quadrant q -> channels
+    //      32q..32q+31 (scaled back by 2^-w_shift, bias added); read = thread (4 channels, tile columns txb and txb+4).
+    const int quad = warp & 3, half = warp >> 2;
+    float* slab = stage_buf + half * (2 * 16 * 128);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int t = quad * 32 + lane;
+    const int c4 = t & 31, txb = t >> 5;
+    const int rd_off = c4 * 4;
+    const int Ho = p.Ho, Wo = p.Wo, cout = p.cout, act = p.act, post = p.post;
+    const int sh = p.shuffle == 2 ? 2 : 1;
+    const int cr = cout >> 2;
+    const int oW = Wo * sh, oH = Ho * sh;
+    const bool planar = p.out_planar != 0;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool vec_ok = !planar && (p.out_ld & 3) == 0 && al16(p.out) && (sh == 1 || (cr & 3) == 0) &&
+                        (post == TDVC_POST_NONE || ((p.mul_ld & 3) == 0 && al16(p.mul))) &&
+                        (!p.res1 || ((p.res1_ld & 3) == 0 && al16(p.res1))) && (!p.res2 || ((p.res2_ld & 3) == 0 && al16(p.res2)));
+    const bool planar_vec = planar && (Wo & 3) == 0 && al16(p.out);
+    const float a_neg = act == TDVC_ACT_NONE ? 1.f : (act == TDVC_ACT_LRELU ? p.slope : 0.f);
+    const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
+    const float unscale = __int_as_float((127 - p.w_shift) << 23);   // 2^-w_shift, exact
+    const int o_rs = sh * oW * p.out_ld, m_rs = sh * oW * p.mul_ld, r1_rs = sh * oW * p.res1_ld, r2_rs = sh * oW * p.res2_ld;
+    const int o_p4 = 4 * sh * p.out_ld, m_p4 = 4 * sh * p.mul_ld, r1_p4 = 4 * sh * p.res1_ld, r2_p4 = 4 * sh * p.res2_ld;  // 4 tile columns
+    int acc_it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
+      const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
+      const int sa = acc_it & 1;
+      mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
+      tc_fence_after();
+      float wbias = 0.f;
+      {
+        const int cw = it.jt * C::NTT + t;
+        if (p.bias && cw < cout) wbias = __ldg(p.bias + cw);
+      }
+      const int co = it.jt * C::NTT + 4 * c4;
+      int oc = co, qy = 0, qx = 0;
+      if (sh == 2) {
+        const int q = co < cout ? co / cr : 0;
+        oc = co - q * cr;
+        qy = q >> 1;
+        qx = q & 1;
+      }
+      const bool c_ok = co < cout;
+      const bool th_vec = vec_ok && co + 4 <= cout;
+      const int ny = Ho - it.y0;
+      const int nxv = Wo - it.x0 - txb;   // column txb valid iff nxv > 0, column txb + 4 iff nxv > 4
+      const int64_t pix0 = ((int64_t)it.n * oH + (it.y0 * sh + qy)) * oW + ((it.x0 + txb) * sh + qx);
+      float* const o0 = p.out + pix0 * p.out_ld + oc;
+      const float* const m0 = post != TDVC_POST_NONE ? p.mul + pix0 * p.mul_ld + oc : nullptr;
+      const float* const r10 = p.res1 ? p.res1 + pix0 * p.res1_ld + oc : nullptr;
+      const float* const r20 = p.res2 ? p.res2 + pix0 * p.res2_ld + oc : nullptr;
+      uint32_t r[16];
+      tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128), r);
+      // residual / GDN-multiplier rows are pulled into L2 two chunks ahead (see the 64-channel epilogue below)
+      auto l2_prefetch_rows = [&](int tyb) {
+        if (!(th_vec && c_ok)) return;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int h2 = k >> 1, g = k & 1;
+          if (tyb + h2 < ny && nxv > 4 * g) {
+            if (m0) prefetch_l2(m0 + (tyb + h2) * m_rs + g * m_p4);
+            if (r10) prefetch_l2(r10 + (tyb + h2) * r1_rs + g * r1_p4);
+            if (r20) prefetch_l2(r20 + (tyb + h2) * r2_rs + g * r2_p4);
+          }
+        }
+      };
+      if (m0 || r10 || r20) {
+        l2_prefetch_rows(half * 16);
+        l2_prefetch_rows(half * 16 + 2);
+      }
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        const int ty0 = half * 16 + c * 2;
+        tmem_ld_wait();
+        if (c == 7) {
+          tc_fence_before();
+          mbar_arrive(bar(ACC_EMPTY + sa));
+        }
+        float* sb = slab + (c & 1) * (16 * 128);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sb[j * 128 + t] = fmaf(__uint_as_float(r[j]), unscale, wbias);
+        if (c < 7) tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128 + (c + 1) * 16), r);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        if (th_vec) {
+          if (!c_ok) continue;
+          if (c < 6 && (m0 || r10 || r20)) l2_prefetch_rows(ty0 + 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // (tile row, column group)
+            const int h2 = k >> 1, g = k & 1;
+            const int ty = ty0 + h2;
+            if (ty >= ny || nxv <= 4 * g) continue;
+            const float4 sv = *reinterpret_cast<const float4*>(sb + (h2 * 8 + txb + 4 * g) * 128 + rd_off);
+            float v[4] = {sv.x, sv.y, sv.z, sv.w};
+            if (m0) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(m0 + ty * m_rs + g * m_p4));
+              if (post == TDVC_POST_IGDN) { v[0] = m.x * sqrtf(v[0]); v[1] = m.y * sqrtf(v[1]); v[2] = m.z * sqrtf(v[2]); v[3] = m.w * sqrtf(v[3]); }
+              else { v[0] = m.x * rsqrtf(v[0]); v[1] = m.y * rsqrtf(v[1]); v[2] = m.z * rsqrtf(v[2]); v[3] = m.w * rsqrtf(v[3]); }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = fminf(fmaxf(v[e], a_neg * v[e]), a_hi);
+            if (r10) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(r10 + ty * r1_rs + g * r1_p4));
+              v[0] += m.x; v[1] += m.y; v[2] += m.z; v[3] += m.w;
+            }
+            if (r20) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(r20 + ty * r2_rs + g * r2_p4));
+              v[0] += m.x; v[1] += m.y; v[2] += m.z; v[3] += m.w;
+            }
+            *reinterpret_cast<float4*>(o0 + ty * o_rs + g * o_p4) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        } else if (planar) {  // NCHW planes: thread = channel; 8 x-adjacent pixels of a tile row are contiguous in the plane
+          const int cp = it.jt * C::NTT + t;
+          if (cp < cout) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int ty = ty0 + h2;
+              if (ty >= ny) continue;
+              const float* rb = sb + h2 * (8 * 128) + t;
+              float v[8];
+#pragma unroll
+              for (int x = 0; x < 8; ++x) {
+                const float o = rb[x * 128];
+                v[x] = fminf(fmaxf(o, a_neg * o), a_hi);
+              }
+              float* op = p.out + (((int64_t)it.n * cout + cp) * Ho + (it.y0 + ty)) * Wo + it.x0;
+              if (planar_vec && it.x0 + 8 <= Wo) {
+                reinterpret_cast<float4*>(op)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                reinterpret_cast<float4*>(op)[1] = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+#pragma unroll
+                for (int x = 0; x < 8; ++x)
+                  if (it.x0 + x < Wo) op[x] = v[x];
+              }
+            }
+          }
+        } else if (c_ok) {
+          const RaggedArgs ra{p.out, p.mul, p.res1, p.res2, p.out_ld, p.mul_ld, p.res1_ld, p.res2_ld, post, act, p.shuffle,
+                              cout, Ho, Wo, p.slope};
+          if (nxv > 0) epilogue_ragged(ra, it.n, it.y0, it.x0, sb, txb, rd_off, co, ty0, 0);
+          if (nxv > 4) epilogue_ragged(ra, it.n, it.y0, it.x0, sb, txb + 4, rd_off, co, ty0, 0);
+        }
+      }
+    }
+    } else {
     const int quad = warp & 3, half = warp >> 2;
     const bool is_lo = (quad & 1) != 0;
     float* slab = stage_buf + half * (2 * 16 * 128);
@@ -341,10 +497,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       const float* const r20 = p.res2 ? p.res2 + pix0 * p.res2_ld + oc : nullptr;
       uint32_t r[16];
       tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128), r);
+      // residual (res1) and GDN-multiplier rows: their DRAM latency (~1.5 us under load) is longer than the slab exchange of
+      // a chunk, so they are pulled into L2 two chunks (4 tile rows) ahead with prefetch.global.L2 - no registers held
+      // (holding them in registers one chunk ahead spilled at the 96-register cap and slowed every variant)
+      auto l2_prefetch_rows = [&](int tyb) {
+        if (!(th_vec && th_ok)) return;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (tyb + q < ny) {
+            if (m0) prefetch_l2(m0 + (tyb + q) * m_rs);
+            if (r10) prefetch_l2(r10 + (tyb + q) * r1_rs);
+            if (r20) prefetch_l2(r20 + (tyb + q) * r2_rs);
+          }
+        }
+      };
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 || r10 || r20) {
+        l2_prefetch_rows(half * 16);
+        l2_prefetch_rows(half * 16 + 2);
+      }
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         const int ty0 = half * 16 + c * 2;
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 ma = z4, mb = z4, ra = z4, rbv = z4, rc = z4, rd = z4;
         const bool row0 = th_vec && th_ok && ty0 < ny, row1 = row0 && ty0 + 1 < ny;
         tmem_ld_wait();
@@ -366,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         if (th_vec) {
           if (!row0) continue;
           const bool two = row1;
-          // residual / GDN-multiplier rows (issuing them before the slab exchange measured 2 % slower: more live registers)
+          if (c < 6 && (m0 || r10 || r20)) l2_prefetch_rows(ty0 + 4);
           if (m0) { ma = __ldg(reinterpret_cast<const float4*>(m0 + ty0 * m_rs)); if (two) mb = __ldg(reinterpret_cast<const float4*>(m0 + (ty0 + 1) * m_rs)); }
           if (r10) { ra = __ldg(reinterpret_cast<const float4*>(r10 + ty0 * r1_rs)); if (two) rbv = __ldg(reinterpret_cast<const float4*>(r10 + (ty0 + 1) * r1_rs)); }
           if (r20) { rc = __ldg(reinterpret_cast<const float4*>(r20 + ty0 * r2_rs)); if (two) rd = __ldg(reinterpret_cast<const float4*>(r20 + (ty0 + 1) * r2_rs)); }
@@ -422,9 +596,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         } else if (th_ok) {
           epilogue_ragged(RaggedArgs{p.out, p.mul, p.res1, p.res2, p.out_ld, p.mul_ld, p.res1_ld, p.res2_ld, post, act, p.shuffle,
                                      cout, Ho, Wo, p.slope},
-                          it.n, it.y0, it.x0, sb, tx, rd_off, co, ty0);
+                          it.n, it.y0, it.x0, sb, tx, rd_off, co, ty0, 32);
         }
       }
+    }
     }
   } else if (warp < kEpiWarps + kProdWarps) {
     // ===================================================================== producers: fp32 halo -> fp16 hi/lo planes
@@ -548,6 +723,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
                 if (kx == 0 && s == 0) tc_mma(d, wk, xh, IDESC, (uint32_t)((u | ky) != 0));
                 else tc_mma(d, wk, xh, IDESC, 1u);
                 tc_mma(d, wk, xl, IDESC, 1u);
+                if constexpr (SPLIT == 1) tc_mma(d, desc_add(wk, C::W_HALF / 16), xh, IDESC, 1u);   // W_lo * x_hi
               }
               tc_commit(bar(W_EMPTY + sW));
               if (++sW == C::NW) { sW = 0; phW ^= 1; }
@@ -590,68 +766,77 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 // fp32 packed weights [T][cin_pad][cout_pad] -> per (cout tile of 64, unit, tap) fp16 block [128 rows][CK] in the
 // canonical K-major no-swizzle layout [(row/8)][(k/8)][row%8][k%8].  Row order = TMEM lane order of the accumulator:
 // rows 0-31 hi of channels 0-31, rows 32-63 lo * 2^12 of channels 0-31, rows 64-95 hi of 32-63, rows 96-127 lo of 32-63.
+// split = 1: per (cout tile of 128, unit, tap) two such blocks, W_hi then W_lo, row = channel, both scaled by 2^w_shift.
 __global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict__ out, int T, int cin, int cin_pad,
-                                 int cout, int cout_pad, int CK, int n_units, int n_jt) {
-  const int64_t per_block = (int64_t)2 * NT * CK;
+                                 int cout, int cout_pad, int CK, int n_units, int n_jt, int split, float scale) {
+  const int64_t per_block = (int64_t)(split ? 2 : 1) * 128 * CK;
   const int64_t total = (int64_t)n_jt * n_units * T * per_block;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i;
     const int k8 = (int)(r % 8); r /= 8;
     const int n8 = (int)(r % 8); r /= 8;
     const int kc = (int)(r % (CK / 8)); r /= (CK / 8);
-    const int ng = (int)(r % (2 * NT / 8)); r /= (2 * NT / 8);
+    const int ng = (int)(r % 16); r /= 16;
+    int which = 0;
+    if (split) { which = (int)(r % 2); r /= 2; }
     const int tap = (int)(r % T); r /= T;
     const int u = (int)(r % n_units);
     const int jt = (int)(r / n_units);
     const int row = ng * 8 + n8, k = kc * 8 + k8;
     const int quad = row >> 5;
-    const int ci = u * CK + k, co = jt * NT + (quad >> 1) * 32 + (row & 31);
+    const int ci = u * CK + k;
+    const int co = split ? jt * 128 + row : jt * NT + (quad >> 1) * 32 + (row & 31);
+    const bool lo = split ? which == 1 : (quad & 1) != 0;
     float v = 0.f;
-    if (ci < cin_pad && co < cout_pad && ci < cin && co < cout) v = w[((int64_t)tap * cin_pad + ci) * cout_pad + co];
+    if (ci < cin_pad && co < cout_pad && ci < cin && co < cout) v = w[((int64_t)tap * cin_pad + ci) * cout_pad + co] * scale;
     v = fminf(fmaxf(v, -65504.f), 65504.f);
     const __half hi = __float2half_rn(v);
-    out[i] = (quad & 1) ? __float2half_rn((v - __half2float(hi)) * kLoScale) : hi;
+    out[i] = lo ? __float2half_rn((v - __half2float(hi)) * (split ? 1.f : kLoScale)) : hi;
   }
 }
 
 struct Choice {
-  int ks, ck, s;
+  int ks, ck, s, split;
 };
 
 // Every KxK (K in 1,3,5,7; pad K/2) stride-1 convolution and the stride-2 3x3 / 1x1 ones have a tensor-core path;
-// output channels are processed in tiles of 64 (zero rows above cout), input channels in chunks of ck.
+// input channels are processed in chunks of ck; output channels in tiles of 64 (4-product scheme) or, for layers
+// with >= 96 output channels (a multiple of 4), in tiles of 128 with the 3-product split scheme.
 static bool choose(const TdvcConvParams& p, Choice* c) {
   if (p.kh != p.kw || p.pad != p.kh / 2 || p.cin < 4 || p.cout < 1) return false;
+  const int split = (p.cout >= 96 && (p.cout & 3) == 0 && p.kh != 7) ? 1 : 0;
   if (p.stride == 2) {
-    if (p.kh == 3) { *c = {3, 16, 2}; return true; }
-    if (p.kh == 1) { *c = {1, 32, 2}; return p.cin >= 32; }
+    if (p.kh == 3) { *c = {3, 16, 2, split}; return true; }
+    if (p.kh == 1) { *c = {1, 32, 2, split}; return p.cin >= 32; }
     return false;
   }
   if (p.stride != 1) return false;
   const int ck = p.cin > 16 ? 32 : 16;
-  if (p.kh == 3 || p.kh == 7) { *c = {p.kh, ck, 1}; return true; }
-  if (p.kh == 1 || p.kh == 5) { *c = {p.kh, 32, 1}; return p.cin >= 32; }
+  if (p.kh == 3) { *c = {3, ck, 1, ck == 32 ? split : 0}; return true; }
+  if (p.kh == 7) { *c = {7, ck, 1, 0}; return true; }
+  if (p.kh == 1 || p.kh == 5) { *c = {p.kh, 32, 1, split}; return p.cin >= 32; }
   return false;
 }
 
-template <int KS, int CK, int S = 1>
+template <int KS, int CK, int S, int SPLIT>
 static int launch(const TdvcConvParams& p, cudaStream_t st) {
-  using C = Cfg<KS, CK, S>;
+  using C = Cfg<KS, CK, S, SPLIT>;
   static bool attr_set = false;  // idempotent; a benign race sets it twice
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, CK, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, CK, S, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute(%d bytes) failed: %s", C::SMEM, cudaGetErrorString(e));
       return TDVC_ECUDA;
     }
     attr_set = true;
   }
+  if (SPLIT) TDVC_REQUIRE(p.w_shift >= -100 && p.w_shift <= 100, "conv_tc: w_shift %d out of range", p.w_shift);
   const int tiles_x = cdiv(p.Wo, TW), tiles_y = cdiv(p.Ho, TH);
-  const int n_jt = cdiv(p.cout, NT), n_units = cdiv(p.cin, CK);
+  const int n_jt = cdiv(p.cout, C::NTT), n_units = cdiv(p.cin, CK);
   const int64_t items = (int64_t)p.N * tiles_x * tiles_y * n_jt;
   TDVC_REQUIRE(items < (1ll << 31), "conv_tc: too many work items");
   const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  conv_tc_kernel<KS, CK, S><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items);
+  conv_tc_kernel<KS, CK, S, SPLIT><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items);
   TDVC_CHECK_LAUNCH("conv_tc");
   return TDVC_OK;
 }
@@ -674,15 +859,23 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
     set_error("conv_tc: unsupported shape");
     return TDVC_EINVAL;
   }
-  if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2>(p, st);
-  if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2>(p, st);
-  if (c.ks == 3 && c.ck == 32) return tc::launch<3, 32>(p, st);
-  if (c.ks == 3 && c.ck == 16) return tc::launch<3, 16>(p, st);
-  if (c.ks == 1) return tc::launch<1, 32>(p, st);
-  if (c.ks == 5) return tc::launch<5, 32>(p, st);
-  if (c.ks == 7 && c.ck == 32) return tc::launch<7, 32>(p, st);
-  if (c.ks == 7 && c.ck == 16) return tc::launch<7, 16>(p, st);
-  set_error("conv_tc: no instantiation for ks=%d ck=%d stride=%d", c.ks, c.ck, c.s);
+  if (c.split) {
+    if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2, 1>(p, st);
+    if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2, 1>(p, st);
+    if (c.ks == 3) return tc::launch<3, 32, 1, 1>(p, st);
+    if (c.ks == 1) return tc::launch<1, 32, 1, 1>(p, st);
+    if (c.ks == 5) return tc::launch<5, 32, 1, 1>(p, st);
+  } else {
+    if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2, 0>(p, st);
+    if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2, 0>(p, st);
+    if (c.ks == 3 && c.ck == 32) return tc::launch<3, 32, 1, 0>(p, st);
+    if (c.ks == 3 && c.ck == 16) return tc::launch<3, 16, 1, 0>(p, st);
+    if (c.ks == 1) return tc::launch<1, 32, 1, 0>(p, st);
+    if (c.ks == 5) return tc::launch<5, 32, 1, 0>(p, st);
+    if (c.ks == 7 && c.ck == 32) return tc::launch<7, 32, 1, 0>(p, st);
+    if (c.ks == 7 && c.ck == 16) return tc::launch<7, 16, 1, 0>(p, st);
+  }
+  set_error("conv_tc: no instantiation for ks=%d ck=%d stride=%d split=%d", c.ks, c.ck, c.s, c.split);
   return TDVC_EINVAL;
 }
 
@@ -690,23 +883,37 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
 
 using namespace tdvc;
 
+static size_t f16_elems(const TdvcConvParams* p, const tc::Choice& c) {
+  const int ntt = c.split ? 128 : tc::NT;
+  const int n_jt = cdiv(p->cout, ntt), n_units = cdiv(p->cin, c.ck);
+  return (size_t)n_jt * n_units * c.ks * c.ks * (c.split ? 2 : 1) * 128 * c.ck;
+}
+
 extern "C" size_t tdvc_conv2d_f16_bytes(const TdvcConvParams* p) {
   tc::Choice c;
   if (p == nullptr || !tc::choose(*p, &c)) return 0;
-  const int n_jt = cdiv(p->cout, tc::NT), n_units = cdiv(p->cin, c.ck);
-  return (size_t)n_jt * n_units * c.ks * c.ks * 2 * tc::NT * c.ck * sizeof(__half);
+  return f16_elems(p, c) * sizeof(__half);
+}
+
+extern "C" int tdvc_conv2d_f16_is_split(const TdvcConvParams* p) {
+  tc::Choice c;
+  if (p == nullptr || !tc::choose(*p, &c)) return 0;
+  return c.split;
 }
 
 extern "C" int tdvc_conv2d_pack_f16(const TdvcConvParams* p, void* out, void* stream) {
   tc::Choice c;
   TDVC_REQUIRE(p && out && p->weight, "conv2d_pack_f16: null pointer");
   TDVC_REQUIRE(tc::choose(*p, &c), "conv2d_pack_f16: shape has no tcgen05 path");
-  const int n_jt = cdiv(p->cout, tc::NT), n_units = cdiv(p->cin, c.ck);
-  const int64_t total = (int64_t)n_jt * n_units * c.ks * c.ks * 2 * tc::NT * c.ck;
+  TDVC_REQUIRE(!c.split || (p->w_shift >= -100 && p->w_shift <= 100), "conv2d_pack_f16: w_shift %d out of range", p->w_shift);
+  const int ntt = c.split ? 128 : tc::NT;
+  const int n_jt = cdiv(p->cout, ntt), n_units = cdiv(p->cin, c.ck);
+  const int64_t total = (int64_t)f16_elems(p, c);
   int grid = cdiv(total, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  const float scale = c.split ? ldexpf(1.f, p->w_shift) : 1.f;
   tc::pack_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->weight, static_cast<__half*>(out), c.ks * c.ks, p->cin,
-                                                             p->cin_pad, p->cout, p->cout_pad, c.ck, n_units, n_jt);
+                                                             p->cin_pad, p->cout, p->cout_pad, c.ck, n_units, n_jt, c.split, scale);
   TDVC_CHECK_LAUNCH("conv2d_pack_f16");
   return TDVC_OK;
 }

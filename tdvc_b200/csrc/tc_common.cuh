@@ -113,6 +113,8 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hv, uint2& lv) {
 }
 
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // 256-bit global accesses (sm_100+): one request for the 8 channels of a deformable group / half a pixel row
 __device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

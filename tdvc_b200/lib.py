@@ -27,7 +27,7 @@ class ConvParams(C.Structure):
                 ("mul", c_fp), ("mul_ld", C.c_int32), ("res1", c_fp), ("res1_ld", C.c_int32),
                 ("res2", c_fp), ("res2_ld", C.c_int32), ("out", c_fp), ("out_ld", C.c_int32),
                 ("shuffle", C.c_int32), ("impl", C.c_int32), ("weight_f16", c_fp), ("chan_sum", c_fp),
-                ("out_planar", C.c_int32)]
+                ("w_shift", C.c_int32), ("out_planar", C.c_int32)]
 
 
 class DcnParams(C.Structure):
@@ -48,6 +48,7 @@ SIGNATURES = {
     "tdvc_last_error": [],
     "tdvc_conv2d": [C.POINTER(ConvParams), vp],
     "tdvc_conv2d_f16_bytes": [C.POINTER(ConvParams)],
+    "tdvc_conv2d_f16_is_split": [C.POINTER(ConvParams)],
     "tdvc_conv2d_pack_f16": [C.POINTER(ConvParams), vp, vp],
     "tdvc_dcn_v2_workspace_bytes": [i32] * 6,
     "tdvc_dcn_v2_forward": [vp] * 6 + [i32] * 14 + [vp, sz, vp],

@@ -323,7 +323,7 @@ def _r(x, m):
 
 # =============================================================================== packed weights
 class ConvW:
-    __slots__ = ("w", "b", "cin", "cin_real", "cin_pad", "cout", "cout_pad", "k", "pad", "shuffle", "w_f16", "stride")
+    __slots__ = ("w", "b", "cin", "cin_real", "cin_pad", "cout", "cout_pad", "k", "pad", "shuffle", "w_f16", "stride", "w_shift")
 
 
 def pack_conv(weight, bias, src_layout=None, shuffle=0, pad=None, stride=1):
@@ -362,6 +362,7 @@ def pack_conv(weight, bias, src_layout=None, shuffle=0, pad=None, stride=1):
     cw.shuffle = shuffle
     cw.stride = stride   # the tcgen05 weight blocking depends on it (csrc/conv_tc.cu `choose`)
     cw.w_f16 = None
+    cw.w_shift = 0
     return cw
 
 
@@ -600,6 +601,7 @@ class _Plan:
         p.shuffle = cw.shuffle
         p.impl = self.impl if impl is None else impl
         p.weight_f16 = cw.w_f16.data_ptr() if cw.w_f16 is not None else None
+        p.w_shift = cw.w_shift
         e0 = self._prof_begin()
         L.check(self.lib.tdvc_conv2d(p, self._st()), "conv2d")
         if e0 is not None:

@@ -1,5 +1,7 @@
 """Host side of the tcgen05 (fp16 hi/lo split) convolution: asks the C-ABI which packed convolutions have a
 tensor-core path and lets it build their fp16 (hi, lo) weight blocks on the device (csrc/conv_tc.cu)."""
+import math
+
 import torch
 
 from tdvc_b200 import lib as L
@@ -19,6 +21,13 @@ def attach_f16(packed):
         nb = lib.tdvc_conv2d_f16_bytes(p)
         if nb == 0:
             continue
+        cw.w_shift = 0
+        if lib.tdvc_conv2d_f16_is_split(p):
+            # 3-product split scheme: weights are stored * 2^w_shift with max|w| * 2^w_shift in [2^13, 2^14), so that
+            # w_lo = w - fp16(w) stays in the fp16 normal range for every weight above 2^-16 of the largest one
+            m = float(cw.w.abs().max())
+            cw.w_shift = 13 - math.frexp(m)[1] + 1 if m > 0 else 0
+        p.w_shift = cw.w_shift
         with torch.cuda.device(cw.w.device):
             buf = torch.empty(nb, device=cw.w.device, dtype=torch.uint8)
             L.check(lib.tdvc_conv2d_pack_f16(p, buf.data_ptr(), torch.cuda.current_stream(cw.w.device).cuda_stream),
