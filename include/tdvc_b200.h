@@ -73,6 +73,8 @@ typedef struct {
   float* chan_sum;          /* optional [N][gridDim-dependent] — reserved for fused SE partial sums */
   int32_t w_shift;          /* tcgen05 split scheme (tdvc_conv2d_f16_is_split): the fp16 weight blocks hold w * 2^w_shift, chosen by
                                the caller so that max|w| * 2^w_shift lies in [2^13, 2^14]; same value at pack time and at launch */
+  int32_t order;            /* tcgen05 path: 1 = walk the output tiles in descending order.  Alternating the direction between
+                               consecutive layers lets a layer start on the tiles its producer wrote last (still in the 126 MB L2) */
   int32_t out_planar;       /* 1: store NCHW planes, out[((n*cout + c)*Ho + y)*Wo + x] (no shuffle / residual / post);
                                the DCN offset/mask head writes the reference's planar offset & mask tensors this way */
 } TdvcConvParams;

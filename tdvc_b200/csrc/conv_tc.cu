@@ -102,8 +102,10 @@ struct Item {
   int n, y0, x0, jt;
 };
 
-__device__ __forceinline__ Item decode_item(int item, int n_jt, int tiles_x, int tiles_y) {
+// `flip` >= 0: items are walked in descending order (item -> flip - item), see TdvcConvParams::order
+__device__ __forceinline__ Item decode_item(int item, int n_jt, int tiles_x, int tiles_y, int flip) {
   Item it;
+  if (flip >= 0) item = flip - item;
   it.jt = item % n_jt;
   int st = item / n_jt;
   it.x0 = (st % tiles_x) * TW;
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   auto bar = [&](int i) { return bar0 + 8u * i; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int flip = p.order ? n_items - 1 : -1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::NX; ++i) { mbar_init(bar(X_FULL + i), kProdThreads); mbar_init(bar(X_EMPTY + i), 1); }
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     const int o_p4 = 4 * sh * p.out_ld, m_p4 = 4 * sh * p.mul_ld, r1_p4 = 4 * sh * p.res1_ld, r2_p4 = 4 * sh * p.res2_ld;  // 4 tile columns
     int acc_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
-      const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
+      const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip);
       const int sa = acc_it & 1;
       mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
       tc_fence_after();
@@ -468,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     const int o_rs = sh * oW * p.out_ld, m_rs = sh * oW * p.mul_ld, r1_rs = sh * oW * p.res1_ld, r2_rs = sh * oW * p.res2_ld;
     int acc_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
-      const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
+      const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip);
       const int sa = acc_it & 1;
       mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
       tc_fence_after();
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     // unit context: where the lane's 4 channels of unit (item, u) come from and which stage they go to
     int item = blockIdx.x, u = 0, sX = 0, phX = 1;
     auto setup = [&](ProdUnit& c) {
-      const Item it = decode_item(item, n_jt, tiles_x, tiles_y);
+      const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip);
       c.iy0 = it.y0 * S - C::PAD;
       c.ix0 = it.x0 * S - C::PAD;
       const float* sp = nullptr;
@@ -742,7 +745,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       const uint32_t w0 = smem_u32(w_buf);
       int sW = 0, phW = 1;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int jt = item % n_jt;
+        const int jt = (flip >= 0 ? flip - item : item) % n_jt;
         const uint8_t* src = wb + ((int64_t)jt * n_units * C::TAPS) * C::W_BLOCK;
         for (int ut = 0; ut < n_units * C::TAPS; ++ut, src += C::W_BLOCK) {
           mbar_wait(bar(W_EMPTY + sW), phW);

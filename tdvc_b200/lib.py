@@ -27,7 +27,7 @@ class ConvParams(C.Structure):
                 ("mul", c_fp), ("mul_ld", C.c_int32), ("res1", c_fp), ("res1_ld", C.c_int32),
                 ("res2", c_fp), ("res2_ld", C.c_int32), ("out", c_fp), ("out_ld", C.c_int32),
                 ("shuffle", C.c_int32), ("impl", C.c_int32), ("weight_f16", c_fp), ("chan_sum", c_fp),
-                ("w_shift", C.c_int32), ("out_planar", C.c_int32)]
+                ("w_shift", C.c_int32), ("order", C.c_int32), ("out_planar", C.c_int32)]
 
 
 class DcnParams(C.Structure):

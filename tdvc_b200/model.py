@@ -13,6 +13,7 @@ Scope: inference (`eval()`), `is_compress=False`.  Training-mode quantisation no
 rANS bitstream are "next" rows and raise NotImplementedError.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -520,6 +521,8 @@ class _Plan:
         self.impl = L.IMPL_AUTO
         self.launches = 0
         self.prof = None  # list of (label, macs, bytes, start_event, end_event) when instrumented (bench.py)
+        self._order = 0
+        self.alternate_order = os.environ.get("TDVC_B200_NO_ALTERNATE") is None   # developer A/B switch
 
     def _prof_begin(self):
         if self.prof is None:
@@ -602,6 +605,8 @@ class _Plan:
         p.impl = self.impl if impl is None else impl
         p.weight_f16 = cw.w_f16.data_ptr() if cw.w_f16 is not None else None
         p.w_shift = cw.w_shift
+        self._order ^= 1          # alternate the tile walk direction between consecutive layers (L2 reuse)
+        p.order = self._order if self.alternate_order else 0
         e0 = self._prof_begin()
         L.check(self.lib.tdvc_conv2d(p, self._st()), "conv2d")
         if e0 is not None:
@@ -726,6 +731,7 @@ class _Plan:
         lib = self.lib
         lr1 = dict(act=L.ACT_LRELU, slope=0.1)
         self.acc.zero_()
+        self._order = 0
         # ---- NCHW -> NHWC (ld 4).  imgs: [x, ref(t-1)] per n, refs4: all four references
         imgs = self.buf("imgs", 2 * N, H, Wd, 3, ld=4)        # [0:N] = input, [N:2N] = x^(t-1)
         r123 = self.buf("r123", 3 * N, H, Wd, 3, ld=4)        # per n: x^(t-3), x^(t-2), x^(t-1)
