@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     const bool vec_ok = !planar && (p.out_ld & 3) == 0 && al16(p.out) && (sh == 1 || (cr & 3) == 0) &&
                         (post == TDVC_POST_NONE || ((p.mul_ld & 3) == 0 && al16(p.mul))) &&
                         (!p.res1 || ((p.res1_ld & 3) == 0 && al16(p.res1))) && (!p.res2 || ((p.res2_ld & 3) == 0 && al16(p.res2)));
-    const bool planar_vec = planar && (Wo & 3) == 0 && al16(p.out);
+    const bool planar_vec = planar && (Wo & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0;
     const float a_neg = act == TDVC_ACT_NONE ? 1.f : (act == TDVC_ACT_LRELU ? p.slope : 0.f);
     const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
     const float unscale = __int_as_float((127 - p.w_shift) << 23);   // 2^-w_shift, exact
@@ -427,8 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
               }
               float* op = p.out + (((int64_t)it.n * cout + cp) * Ho + (it.y0 + ty)) * Wo + it.x0;
               if (planar_vec && it.x0 + 8 <= Wo) {
-                reinterpret_cast<float4*>(op)[0] = make_float4(v[0], v[1], v[2], v[3]);
-                reinterpret_cast<float4*>(op)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                stg256(op, v);   // one full 32-byte sector: two 16-byte stores made L2 read the sector back (partial writes)
               } else {
 #pragma unroll
                 for (int x = 0; x < 8; ++x)
@@ -461,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     const bool vec_ok = !planar && (p.out_ld & 3) == 0 && al16(p.out) && (sh == 1 || (cr & 3) == 0) &&
                         (post == TDVC_POST_NONE || ((p.mul_ld & 3) == 0 && al16(p.mul))) &&
                         (!p.res1 || ((p.res1_ld & 3) == 0 && al16(p.res1))) && (!p.res2 || ((p.res2_ld & 3) == 0 && al16(p.res2)));
-    const bool planar_vec = planar && (Wo & 3) == 0 && al16(p.out);
+    const bool planar_vec = planar && (Wo & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0;
     // a plain store may also fill the pad lanes of a channel-padded view (weight rows >= cout are zero, no bias there)
     const int cout_st = (sh == 1 && post == TDVC_POST_NONE && !p.res1 && !p.res2 && p.out_ld >= ((cout + 3) & ~3)) ? ((cout + 3) & ~3) : cout;
     // branch-free activation: a(v) = min(max(v, a_neg * v), a_hi)   (0 <= a_neg <= 1)
@@ -588,8 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             }
             float* op = p.out + (((int64_t)it.n * cout + cp) * Ho + (it.y0 + ty)) * Wo + it.x0;
             if (planar_vec && it.x0 + 8 <= Wo) {
-              reinterpret_cast<float4*>(op)[0] = make_float4(v[0], v[1], v[2], v[3]);
-              reinterpret_cast<float4*>(op)[1] = make_float4(v[4], v[5], v[6], v[7]);
+              stg256(op, v);   // one full 32-byte sector: two 16-byte stores made L2 read the sector back (partial writes)
             } else {
 #pragma unroll
               for (int x = 0; x < 8; ++x)
