@@ -297,6 +297,12 @@ def main():
         kernels = {k: {"launches": v[0], "ms": round(v[1], 4),
                        "tflops": round(2.0 * v[2] / (v[1] / 1e3) / 1e12, 2) if v[2] and v[1] > 0 else None,
                        "gbs": round(v[3] / (v[1] / 1e3) / 1e9, 1) if v[3] and v[1] > 0 else None} for k, v in top}
+        # memory-bound kernels of the frame against the measured HBM peak (warp, DCN gather, GDN, bits)
+        mem_rows = {}
+        for k, v in agg.items():
+            if v[3] and v[1] > 0 and (not k.startswith("conv") or k.startswith("conv1x1")):
+                gbs = v[3] / (v[1] / 1e3) / 1e9
+                mem_rows[k] = {"ms": round(v[1], 4), "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 3)}
         frame_tflops = 2.0 * MACS_PER_PX * hh * ww / (ms / K / 1e3) / 1e12
         cpu = None
         if not args.no_cpu_baseline:
@@ -318,7 +324,7 @@ def main():
                 "gpu_launches": launches, "clocks": clocks,
                 "roofline": roof, "frame_tensor_tflops": frame_tflops,
                 "frame_tensor_frac_of_sustained_bf16": frame_tflops / peaks["bf16_tflops_sustained"],
-                "kernels": kernels, "cpu_baseline": cpu, "stats": G.summarise(stats)}
+                "memory_bound_kernels": mem_rows, "kernels": kernels, "cpu_baseline": cpu, "stats": G.summarise(stats)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -40,6 +40,19 @@ __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ src, float* __res
   }
 }
 
+// images (C <= 4, ld == 4): one pixel per thread, one 16-byte load, coalesced plane stores
+__global__ void nhwc4_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t HW, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, px = i - n * HW;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    float* d = dst + n * C * HW + px;
+    d[0] = v.x;
+    if (C > 1) d[HW] = v.y;
+    if (C > 2) d[2 * HW] = v.z;
+    if (C > 3) d[3 * HW] = v.w;
+  }
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, int C, int64_t HW) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -134,10 +147,23 @@ __global__ void se_partial_kernel(const float* __restrict__ x, int ld, int64_t H
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (pl < lanes_p) {
     const float* base = x + (int64_t)n * HW * ld + c4 * 4;
-    for (int64_t p = p0 + pl; p < p1; p += lanes_p) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(base + p * ld));
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    // four independent loads in flight per thread (one per iteration left the kernel latency-bound at ~3 TB/s);
+    // the four partial sums are combined in a fixed order: deterministic
+    float4 a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t p = p0 + pl; p < p1; p += 4 * lanes_p) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t q = p + (int64_t)j * lanes_p;
+        v[j] = q < p1 ? __ldg(reinterpret_cast<const float4*>(base + q * ld)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j].x += v[j].x; a[j].y += v[j].y; a[j].z += v[j].z; a[j].w += v[j].w; }
     }
+    s = make_float4((a[0].x + a[1].x) + (a[2].x + a[3].x), (a[0].y + a[1].y) + (a[2].y + a[3].y),
+                    (a[0].z + a[1].z) + (a[2].z + a[3].z), (a[0].w + a[1].w) + (a[2].w + a[3].w));
   }
   sh4[threadIdx.x] = s;
   __syncthreads();
@@ -185,17 +211,36 @@ __global__ void se_apply_kernel(const float* __restrict__ x, int ld, const float
   const float* xb = x + (int64_t)n * HW * ld;
   float* ob = out + (int64_t)n * HW * out_ld;
   const float* rb = res ? res + (int64_t)n * HW * res_ld : nullptr;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t p = i / lanes_c;
-    const int c = (int)(i - p * lanes_c) * 4;
-    float4 v = __ldg(reinterpret_cast<const float4*>(xb + p * ld + c));
-    v.x = apply_act(v.x * sc[c], act, slope); v.y = apply_act(v.y * sc[c + 1], act, slope);
-    v.z = apply_act(v.z * sc[c + 2], act, slope); v.w = apply_act(v.w * sc[c + 3], act, slope);
-    if (rb) {
-      const float4 r = __ldg(reinterpret_cast<const float4*>(rb + p * res_ld + c));
-      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  // four float4 per thread and iteration, all loads issued before the first use (memory-level parallelism)
+  const bool pow2 = (lanes_c & (lanes_c - 1)) == 0;
+  const int lshift = __ffs(lanes_c) - 1;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    float4 v[4], r[4];
+    int64_t pp[4];
+    int cc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = i0 + j * stride;
+      pp[j] = pow2 ? (i >> lshift) : i / lanes_c;   // C/4 is a power of two for every SE block of the model
+      cc[j] = (int)(i - pp[j] * lanes_c) * 4;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      r[j] = v[j];
+      if (i < total) {
+        v[j] = __ldg(reinterpret_cast<const float4*>(xb + pp[j] * ld + cc[j]));
+        if (rb) r[j] = __ldg(reinterpret_cast<const float4*>(rb + pp[j] * res_ld + cc[j]));
+      }
     }
-    *reinterpret_cast<float4*>(ob + p * out_ld + c) = v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j * stride >= total) continue;
+      const int c = cc[j];
+      float4 o;
+      o.x = apply_act(v[j].x * sc[c], act, slope) + r[j].x;
+      o.y = apply_act(v[j].y * sc[c + 1], act, slope) + r[j].y;
+      o.z = apply_act(v[j].z * sc[c + 2], act, slope) + r[j].z;
+      o.w = apply_act(v[j].w * sc[c + 3], act, slope) + r[j].w;
+      *reinterpret_cast<float4*>(ob + pp[j] * out_ld + c) = o;
+    }
   }
 }
 
@@ -225,6 +270,14 @@ extern "C" int tdvc_nchw_to_nhwc(const float* src, float* dst, int N, int C, int
 extern "C" int tdvc_nhwc_to_nchw(const float* src, int src_ld, float* dst, int N, int C, int H, int W, void* stream) {
   TDVC_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && src_ld >= C, "nhwc_to_nchw: bad args");
   const int64_t HW = (int64_t)H * W;
+  if (C <= 4 && src_ld == 4 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int64_t total = (int64_t)N * HW;
+    int g = cdiv(total, 256);
+    if (g > kNumSMs * 16) g = kNumSMs * 16;
+    nhwc4_to_nchw_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(src, dst, C, HW, total);
+    TDVC_CHECK_LAUNCH("nhwc_to_nchw");
+    return TDVC_OK;
+  }
   dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
   nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, src_ld, dst, C, HW);
   TDVC_CHECK_LAUNCH("nhwc_to_nchw");
@@ -285,7 +338,7 @@ extern "C" int tdvc_se_apply(const float* x, int ld, const float* partial, int n
   TDVC_REQUIRE(C % 4 == 0 && ld % 4 == 0 && out_ld % 4 == 0 && aligned16(x) && aligned16(out), "se_apply: C/ld/alignment");
   TDVC_REQUIRE(res == nullptr || (res_ld % 4 == 0 && aligned16(res)), "se_apply: res alignment");
   int gx = ew_grid(HW * (C / 4));
-  if (gx > kNumSMs * 4) gx = kNumSMs * 4;
+  if (gx > kNumSMs * 8) gx = kNumSMs * 8;
   dim3 grid(gx, N);
   se_apply_kernel<<<grid, 256, (2 * C + Cr) * sizeof(float), (cudaStream_t)stream>>>(
       x, ld, partial, nblk, w1, b1, w2, b2, N, HW, C, Cr, act, slope, res, res_ld, out, out_ld);

@@ -613,7 +613,8 @@ class _Plan:
             npx = s0.N * p.Ho * p.Wo
             self._prof_end(e0, f"conv{cw.k}x{cw.k}s{stride}_{cw.cin}to{cw.cout}@{p.Ho}x{p.Wo}",
                            macs=npx * cw.cout * cw.cin_real * cw.k * cw.k,
-                           nbytes=4 * (s0.N * s0.H * s0.W * cw.cin_real + npx * cw.cout))
+                           nbytes=4 * (s0.N * s0.H * s0.W * cw.cin_real +
+                                       npx * cw.cout * (1 + (mul is not None) + (res1 is not None) + (res2 is not None))))
         self.launches += 1
         return out
 
@@ -622,11 +623,15 @@ class _Plan:
         HW = x.H * x.W
         nblk = max(1, min(592, HW // 64))
         part = self.raw(("se_part", x.C), (nblk * x.N * x.C,))
+        e0 = self._prof_begin()
         L.check(self.lib.tdvc_se_partial_sums(x.ptr, x.ld, x.N, HW, x.C, part.data_ptr(), nblk, self._st()), "se_partial_sums")
+        self._prof_end(e0, "se_partial_sums", 0, 4 * x.N * HW * x.C)
+        e0 = self._prof_begin()
         L.check(self.lib.tdvc_se_apply(x.ptr, x.ld, part.data_ptr(), nblk, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
                                        b2.data_ptr(), x.N, HW, x.C, w1.shape[0], act, slope,
                                        res.ptr if res is not None else None, res.ld if res is not None else 0,
                                        out.ptr, out.ld, self._st()), "se_apply")
+        self._prof_end(e0, "se_apply", 0, 4 * x.N * HW * x.C * (3 if res is not None else 2))
         self.launches += 2
         return out
 
@@ -699,7 +704,7 @@ class _Plan:
         params = self.conv([s], W[f"{cn}.hs8"], b("params", s.H, s.W, 256))
         # ---- y_hat, context model, entropy parameters, conditional likelihood
         yh = b("y_hat", y.H, y.W)
-        self.call("tdvc_round_half_even", y.ptr, yh.ptr, y.N * y.H * y.W * 128)
+        self.call("tdvc_round_half_even", y.ptr, yh.ptr, y.N * y.H * y.W * 128, nbytes=8 * y.N * y.H * y.W * 128)
         ctx = self.conv([yh], W[f"{cn}.ctx"], b("ctx", y.H, y.W, 256))
         c0, c2 = W[f"{cn}.ep0"].cout, W[f"{cn}.ep2"].cout
         e = self.conv([params, ctx], W[f"{cn}.ep0"], b("ep0", y.H, y.W, c0, ld=_r(c0, 8), zero=True), **lr)
@@ -736,13 +741,13 @@ class _Plan:
         imgs = self.buf("imgs", 2 * N, H, Wd, 3, ld=4)        # [0:N] = input, [N:2N] = x^(t-1)
         r123 = self.buf("r123", 3 * N, H, Wd, 3, ld=4)        # per n: x^(t-3), x^(t-2), x^(t-1)
         ifr = self.buf("iframe", N, H, Wd, 3, ld=4)
-        self.call("tdvc_nchw_to_nhwc", x_nchw.data_ptr(), imgs.ptr, N, 3, H, Wd, 4)
+        self.call("tdvc_nchw_to_nhwc", x_nchw.data_ptr(), imgs.ptr, N, 3, H, Wd, 4, nbytes=28 * N * H * Wd)
         fr = 3 * H * Wd * 4
         for n in range(N):
             base = refs_nchw.data_ptr() + n * 4 * fr
-            self.call("tdvc_nchw_to_nhwc", base, ifr.batch(n).ptr, 1, 3, H, Wd, 4)
-            self.call("tdvc_nchw_to_nhwc", base + fr, r123.batch(3 * n).ptr, 3, 3, H, Wd, 4)
-            self.call("tdvc_nchw_to_nhwc", base + 3 * fr, imgs.batch(N + n).ptr, 1, 3, H, Wd, 4)
+            self.call("tdvc_nchw_to_nhwc", base, ifr.batch(n).ptr, 1, 3, H, Wd, 4, nbytes=28 * H * Wd)
+            self.call("tdvc_nchw_to_nhwc", base + fr, r123.batch(3 * n).ptr, 3, 3, H, Wd, 4, nbytes=84 * H * Wd)
+            self.call("tdvc_nchw_to_nhwc", base + 3 * fr, imgs.batch(N + n).ptr, 1, 3, H, Wd, 4, nbytes=28 * H * Wd)
         # ---- feature extraction on both images (pnet.py:29-30, 86-96)
         f0 = self.conv([imgs], W["extra_fea.conv_first"], self.buf("fe.0", 2 * N, H, Wd, 64), **lr1)
         feats = self.res_stack(W, "extra_fea.res", 2, f0, "fe", out_last=self.buf("feats", 2 * N, H, Wd, 64))
@@ -793,12 +798,12 @@ class _Plan:
         pred = self.mcfilter(W, pred1, r123, t4)
         # ---- residual coder (pnet.py:55-67, 76)
         resid = self.buf("resid", N, H, Wd, 64)
-        self.call("tdvc_axpby", in_f.ptr, pred.ptr, resid.ptr, N * H * Wd * 64, 1.0, -1.0)
+        self.call("tdvc_axpby", in_f.ptr, pred.ptr, resid.ptr, N * H * Wd * 64, 1.0, -1.0, nbytes=768 * N * H * Wd)
         rec_f = self.coder(W, "rs", resid, 2, taps, final_res=pred, out=self.buf("rec_f", N, H, Wd, 64))
         # ---- reference-based in-loop filter (pnet.py:213-263) + clamp (:78)
         recon4 = self.loopfilter(W, rec_f, ifr, taps)
         recon = self.raw("recon", (N, 3, H, Wd))
-        self.call("tdvc_nhwc_to_nchw", recon4.ptr, recon4.ld, recon.data_ptr(), N, 3, H, Wd)
+        self.call("tdvc_nhwc_to_nchw", recon4.ptr, recon4.ld, recon.data_ptr(), N, 3, H, Wd, nbytes=28 * N * H * Wd)
         # ---- bpp (pnet.py:38-43, 62-67): sum ln p / (-ln2 * N*H*W), per coder
         bpp = self.acc.view(2, 2).sum(1) / (-_LN2 * N * H * Wd)
         if taps is not None:
@@ -831,13 +836,13 @@ class _Plan:
                 off = self.conv([up, o1], W[f"me.ff.{lv}"], b(f"off.{lv}", N, h, w), **lr1)
             if i > 1:
                 u = b(f"up2x.{lv}", N, 2 * h, 2 * w)
-                self.call("tdvc_upsample2x", off.ptr, u.ptr, N, h, w, 64)
+                self.call("tdvc_upsample2x", off.ptr, u.ptr, N, h, w, 64, nbytes=1280 * N * h * w)  # read 256 + write 4 * 256 B/px
                 up = self.conv([u], W["me.upsample_conv"], b(f"up.{lv}", N, 2 * h, 2 * w))
             if taps is not None:
                 taps[f"motion_est.offset_{lv}"] = off.nchw()
         flow = self.spynet(W, imgs, taps)
         offf = b("off_flow", N, H, Wd)
-        self.call("tdvc_add_flow_tiled", off.ptr, flow.ptr, offf.ptr, N, H, Wd, 64)
+        self.call("tdvc_add_flow_tiled", off.ptr, flow.ptr, offf.ptr, N, H, Wd, 64, nbytes=520 * N * H * Wd)
         ff = self.conv([offf], W["me.feat_fusion_"], b("ff", N, H, Wd))
         return self.se(ff, W["me.attn"], b("estmv", N, H, Wd))
 
@@ -849,7 +854,7 @@ class _Plan:
         for l in range(5):
             s = pyr[-1]
             d = self.buf(f"spy.pyr{l}", 2 * N, s.H // 2, s.W // 2, 3, ld=4)
-            self.call("tdvc_avgpool2x2", s.ptr, d.ptr, 2 * N, s.H, s.W, 4)
+            self.call("tdvc_avgpool2x2", s.ptr, d.ptr, 2 * N, s.H, s.W, 4, nbytes=20 * 2 * N * s.H * s.W)
             pyr.append(d)
         pyr = pyr[::-1]
         flow = None
@@ -886,7 +891,8 @@ class _Plan:
         o = b("c1", 4 * N)  # reuse
         for n in range(N):
             self.conv([s.batch(4 * n), s.batch(4 * n + 1), s.batch(4 * n + 2)], W["mf.l1.temporal"], tmp.batch(n))
-            self.call("tdvc_bcast_add_lrelu", s.batch(4 * n).ptr, tmp.batch(n).ptr, o.batch(4 * n).ptr, 4, H * Wd * 64, 0.1)
+            self.call("tdvc_bcast_add_lrelu", s.batch(4 * n).ptr, tmp.batch(n).ptr, o.batch(4 * n).ptr, 4, H * Wd * 64, 0.1,
+                      nbytes=9 * 256 * H * Wd)  # read 4 frames + the temporal term, write 4 frames
         bo = self.conv([o], W["mf.l1.conv3"], b("s", 4 * N), res1=a)  # reuse `s`
         fu = b("fu", N)
         for n in range(N):
@@ -909,8 +915,8 @@ class _Plan:
         ph, pw = H // scale, Wd // scale
         p_in = self.raw("lf.p_in", (N, ph, pw, 64))
         p_ref = self.raw("lf.p_ref", (N, ph, pw, 64))
-        self.call("tdvc_avgpool_scale", f_in.ptr, f_in.ld, p_in.data_ptr(), N, H, Wd, 64, scale)
-        self.call("tdvc_avgpool_scale", f_ref.ptr, f_ref.ld, p_ref.data_ptr(), N, H, Wd, 64, scale)
+        self.call("tdvc_avgpool_scale", f_in.ptr, f_in.ld, p_in.data_ptr(), N, H, Wd, 64, scale, nbytes=256 * N * H * Wd)
+        self.call("tdvc_avgpool_scale", f_ref.ptr, f_ref.ld, p_ref.data_ptr(), N, H, Wd, 64, scale, nbytes=256 * N * H * Wd)
         PH, PW = (ph + 3) // 3 + 1, (pw + 3) // 3 + 1
         P = PH * PW
         bs = 3 * scale
