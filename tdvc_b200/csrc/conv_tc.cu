@@ -40,9 +40,9 @@ namespace tdvc {
 
 namespace tc {
 
-constexpr int kEpiWarps = 8, kProdWarps = 8;                 // 2 of each per SM sub-partition
+constexpr int kEpiWarps = 8, kProdWarps = 10;                // 20 warps = 5 per SM sub-partition: still 96 registers per thread
 constexpr int kMmaWarp = kEpiWarps + kProdWarps, kLoadWarp = kMmaWarp + 1;
-constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 576
+constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 640
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int TW = 8, TH = 32, NPX = TW * TH;  // output tile = N of one MMA
 constexpr int NT = 64;                         // output channels per item (M = 2*NT rows: hi, lo)
