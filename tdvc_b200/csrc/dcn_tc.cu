@@ -17,7 +17,7 @@
 //           offset / mask tensors (dcn_v2.h:9-46), and what the offset/mask convolution writes with out_planar = 1.
 //
 // Work decomposition (persistent, one CTA per SM, 576 threads):
-//   item = 16x16 output pixels = two MMA tiles (M = 128: 8 rows x 16 px, row m = (y%8)*16 + x);
+//   item = 16x8 output pixels = one MMA tile (M = 128: 8 rows x 16 px, row m = (y%8)*16 + x); kTiles tiles per item;
 //   K is ordered k' = (g*9 + tap)*8 + c (one 16-byte core-matrix row per (pixel, g, tap)), padded per group from 72
 //   to 80 (5 MMA k-steps); one pipeline stage = one deformable group.
 //   warps 4-15  producers: lane = pixel, task = (32 pixels, tap): 3 coalesced parameter loads, 4 x 256-bit corner
@@ -37,16 +37,20 @@ constexpr int kEpiWarps = 4, kProdWarps = 12;
 constexpr int kMmaWarp = kEpiWarps + kProdWarps, kLoadWarp = kMmaWarp + 1;
 constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 576
 constexpr int kProdThreads = kProdWarps * 32;
-constexpr int kTile = 16;
+constexpr int kTile = 16;                     // item width (pixels)
+constexpr int kTiles = 1;                    // MMA tiles (8 rows x 16 px, M = 128) per item.  One tile keeps the CTA at 140 KB
+                                             // of shared memory, so ~85 KB stay L1: the bilinear gather of a group (a ~26x18-pixel
+                                             // window x 32 B, re-read by 9 taps x 4 corners) then hits L1 instead of L2
+constexpr int kTileH = 8 * kTiles;
 constexpr int NT = 64;                       // output channels (padded)
 constexpr int KCH = 10;                      // 16-byte K chunks per group (9 taps + 1 zero pad)
 constexpr int CHUNK_BYTES = 128 * 16;        // one K chunk of one MMA tile: 128 rows x 16 B
 constexpr int A_PLANE = KCH * CHUNK_BYTES;   // hi (or lo) plane of one tile: 20 KB
-constexpr int A_STAGE = 2 * 2 * A_PLANE;     // [tile][hi|lo]: 80 KB
+constexpr int A_STAGE = kTiles * 2 * A_PLANE; // [tile][hi|lo]
 constexpr int B_BLOCK = 2 * NT * KCH * 8 * 2;  // [128 rows][80] fp16: 20 KB
 constexpr int NA = 2, NB = 3;
 constexpr int SMEM = NA * A_STAGE + NB * B_BLOCK + 256;
-constexpr int TMEM_COLS = 512;               // 2 stages x 2 tiles x 128 columns
+constexpr int TMEM_COLS = 2 * kTiles * 128;   // 2 stages x tiles x 128 columns
 constexpr int KSTEPS = KCH / 2;
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const TdvcDcnParams
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // the pad chunk (k = 72..79 of every group) of every A plane is zero for the whole kernel
-  for (int i = threadIdx.x; i < NA * 4 * (CHUNK_BYTES / 16); i += kThreads) {
+  for (int i = threadIdx.x; i < NA * kTiles * 2 * (CHUNK_BYTES / 16); i += kThreads) {
     const int plane = i / (CHUNK_BYTES / 16), r = i % (CHUNK_BYTES / 16);
     *reinterpret_cast<uint4*>(a_buf + plane * A_PLANE + (KCH - 1) * CHUNK_BYTES + r * 16) = make_uint4(0, 0, 0, 0);
   }
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const TdvcDcnParams
   auto decode = [&](int item, int& n, int& y0, int& x0) {
     x0 = (item % tiles_x) * kTile;
     item /= tiles_x;
-    y0 = (item % tiles_y) * kTile;
+    y0 = (item % tiles_y) * kTileH;
     n = item / tiles_y;
   };
 
@@ -111,10 +115,10 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const TdvcDcnParams
       mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < kTiles; ++t) {
         const int y = y0 + 8 * t + (m >> 4), x = x0 + (m & 15);
         const bool valid = y < H && x < W;
-        const uint32_t tcol = lane_addr + (uint32_t)((sa * 2 + t) * 2 * NT);
+        const uint32_t tcol = lane_addr + (uint32_t)((sa * kTiles + t) * 2 * NT);
 #pragma unroll 1
         for (int c0 = 0; c0 < NT; c0 += 32) {
           uint32_t ra[32], rb[32];
@@ -167,15 +171,17 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const TdvcDcnParams
         mbar_wait(bar(A_EMPTY + st), ((a_it / NA) & 1) ^ 1);
         uint8_t* stage = a_buf + st * A_STAGE;
         const float* in_g = p.input_gp + ((int64_t)n * dg + g) * HW * 8;
-        // 8 row pairs x 9 taps = 72 warp tasks per stage, 6 per producer warp.  The three parameters (dy, dx, mask) of all
-        // six tasks are loaded first (18 coalesced loads in flight), so each task then waits for ONE memory latency
+        // RP row pairs x 9 taps warp tasks per stage, TPW per producer warp.  The three parameters (dy, dx, mask) of all
+        // its tasks are loaded first (coalesced loads in flight), so each task then waits for ONE memory latency
         // (its four corner sectors) instead of two.
-        constexpr int TPW = 72 / kProdWarps;
+        constexpr int RP = 4 * kTiles;                 // row pairs of the item
+        static_assert((RP * 9) % kProdWarps == 0, "tasks per producer warp");
+        constexpr int TPW = RP * 9 / kProdWarps;
         float pdy[TPW], pdx[TPW], pmk[TPW];
 #pragma unroll
         for (int j = 0; j < TPW; ++j) {
           const int q = pw + j * kProdWarps;
-          const int rp = q & 7, tap = q >> 3;
+          const int rp = q % RP, tap = q / RP;
           const int y = y0 + 2 * rp + (lane >> 4), x = x0 + (lane & 15);
           pdy[j] = pdx[j] = pmk[j] = 0.f;
           if (y < H && x < W) {
@@ -188,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const TdvcDcnParams
 #pragma unroll
         for (int j = 0; j < TPW; ++j) {
           const int q = pw + j * kProdWarps;
-          const int rp = q & 7, tap = q >> 3;
+          const int rp = q % RP, tap = q / RP;
           const int ly = 2 * rp + (lane >> 4), lx = lane & 15;
           const int y = y0 + ly, x = x0 + lx;
           const int t = ly >> 3, m = (ly & 7) * 16 + lx;
@@ -251,8 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const TdvcDcnParams
           tc_fence_after();
           const uint32_t bblk = b0 + sB * B_BLOCK;
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const uint32_t d = tmem_base + (uint32_t)((sa * 2 + t) * 2 * NT);
+          for (int t = 0; t < kTiles; ++t) {
+            const uint32_t d = tmem_base + (uint32_t)((sa * kTiles + t) * 2 * NT);
             const uint32_t a_hi = a0 + sA * A_STAGE + (t * 2) * A_PLANE, a_lo = a_hi + A_PLANE;
 #pragma unroll
             for (int s = 0; s < KSTEPS; ++s) {
@@ -342,9 +348,11 @@ int dcn_tc(const TdvcDcnParams& p, cudaStream_t st) {
       set_error("dcn_tc: cudaFuncSetAttribute(%d bytes) failed: %s", dcn::SMEM, cudaGetErrorString(e));
       return TDVC_ECUDA;
     }
+    // ask for the smallest shared-memory carve-out that holds the CTA: the rest of the 228 KB stays L1 for the gather
+    cudaFuncSetAttribute(dcn::dcn_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (dcn::SMEM + 1024) * 100 / (228 * 1024) + 1);
     attr_set = true;
   }
-  const int tiles_x = cdiv(p.W, dcn::kTile), tiles_y = cdiv(p.H, dcn::kTile);
+  const int tiles_x = cdiv(p.W, dcn::kTile), tiles_y = cdiv(p.H, dcn::kTileH);
   const int64_t items = (int64_t)p.N * tiles_x * tiles_y;
   TDVC_REQUIRE(items < (1ll << 31), "dcn_tc: too many work items");
   const int grid = (int)(items < kNumSMs ? items : kNumSMs);

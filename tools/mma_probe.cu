@@ -26,6 +26,7 @@ constexpr int SMEM = 200 * 1024;
 // mode 3: two N=128 MMAs   mode 4: two N=64 MMAs   mode 5: one N=256 MMA   (pixels = M)
 // mode 6: pixels = M, cout tile 128: N=256 (A_hi) + N=128 (A_lo), one tile
 // mode 7: as 1 but two N=128 pixel tiles (8x16 each) per operand instead of one N=256
+// mode 8 / 9: does an M = 64 MMA cost less than an M = 128 one?
 __global__ void __launch_bounds__(128, 1) probe(int mode, int iters, unsigned long long* cycles) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_s;
@@ -54,12 +55,14 @@ __global__ void __launch_bounds__(128, 1) probe(int mode, int iters, unsigned lo
   if (threadIdx.x == 0) {
     const uint32_t s0 = smem_u32(smem);
     // pixel operand: [ch/8][NPIXP][16 B] hi plane then lo plane (64 channels);  weights: blocks of [128 rows][64] fp16
-    const int IW = (mode == 1 || mode == 2) ? 10 : 18;
-    const int NPIXP = ((mode == 1 || mode == 2) ? 10 * 34 : 18 * 18) | 1;
+    const bool wm = mode == 1 || mode == 2 || mode == 8 || mode == 9;
+    const int IW = wm ? 10 : 18;
+    const int NPIXP = (wm ? 10 * 34 : 18 * 18) | 1;
     const uint32_t LBO_X = NPIXP * 16, SBO_X = IW * 16, X_HALF = 8 * NPIXP * 16;
     const uint32_t x_hi = s0, x_lo = s0 + X_HALF, w0 = s0 + 2 * X_HALF;   // 3 weight blocks of 16 KB follow
     const uint32_t LBO_W = 128, SBO_W = 8 * 128, W_BLOCK = 128 * 64 * 2;
     const uint32_t I256 = instr_desc(256), I128 = instr_desc(128), I64 = instr_desc(64);
+    const uint32_t I256_M64 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       for (int tap = 0; tap < 9; ++tap) {
@@ -100,6 +103,12 @@ __global__ void __launch_bounds__(128, 1) probe(int mode, int iters, unsigned lo
               tc_mma(tmem, wd, xh, I128, acc);        tc_mma(tmem, wd, xl, I128, 1);
               tc_mma(tmem + 128, wd, xh2, I128, acc); tc_mma(tmem + 128, wd, xl2, I128, 1);
               break;
+            case 8:   // M = 64 rows of weights, N = 256 pixels, twice
+              tc_mma(tmem, wd, xh, I256_M64, acc); tc_mma(tmem, wd, xl, I256_M64, 1);
+              break;
+            case 9:   // M = 128 (x_hi) + M = 64 (x_lo: only the W_hi rows are needed)
+              tc_mma(tmem, wd, xh, I256, acc); tc_mma(tmem, wd, xl, I256_M64, 1);
+              break;
           }
         }
       }
@@ -122,11 +131,12 @@ int main(int argc, char** argv) {
   const char* names[] = {"pixels=M 2 tiles: N128 + N64        (floor 192)", "weights=M SS: 2 x N256 px           (floor 256)",
                          "weights=M TS: 2 x N256 px           (floor 256)", "pixels=M: 2 x N128                  (floor 128)",
                          "pixels=M: 2 x N64                   (floor  64)", "pixels=M: 1 x N256                  (floor 128)",
-                         "pixels=M cout128: N256 + N128       (floor 192)", "weights=M SS: 4 x N128 px           (floor 256)"};
+                         "pixels=M cout128: N256 + N128       (floor 192)", "weights=M SS: 4 x N128 px           (floor 256)",
+                         "weights=M (M=64) SS: 2 x N256 px    (floor 256?)", "weights=M: M128 N256 + M64 N256     (floor 256?)"};
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   unsigned long long* d;
   cudaMalloc(&d, 148 * sizeof(unsigned long long));
-  for (int mode = 0; mode < 8; ++mode) {
+  for (int mode = 0; mode < 10; ++mode) {
     std::vector<unsigned long long> h(148);
     for (int rep = 0; rep < 2; ++rep) {
       probe<<<148, 128, SMEM>>>(mode, iters, d);
