@@ -188,6 +188,16 @@ int tdvc_ff_gather(const float* f_in, const float* f_ref, const int32_t* ind, fl
 /* ---- on-device metrics for the GOP driver (reference tools/predict.py:86-90): acc[0] += sum (a-b)^2 */
 int tdvc_sq_err_sum(const float* a, const float* b, int64_t n, double* acc, void* stream);
 
+/* ---- MS-SSIM (reference main/model/ms_ssim_torch.py:21-87,138-200; tools/predict.py:93-96) ----
+ * ssim_level: one scale of `_ssim` on contiguous NCHW planes: separable 11-tap Gaussian (`win11_host`: the 11 window
+ *   weights, HOST pointer, copied into the launch), SSIM and contrast-structure maps over the (H-10)x(W-10) valid region;
+ *   acc[2*n] += sum of the SSIM map, acc[2*n+1] += sum of the cs map of image n (fp64, caller zeroes them and divides by
+ *   C*(H-10)*(W-10)).
+ * avgpool2_pad: F.avg_pool2d(x, 2, padding=(H%2, W%2)), the downsampling between scales (:188-190). */
+int tdvc_ssim_level(const float* x, const float* y, int N, int C, int H, int W, const float* win11_host, float C1, float C2,
+                    double* acc, void* stream);
+int tdvc_avgpool2_pad(const float* src, float* dst, int planes, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,36 @@ def main():
             d["stat_" + k] = np.array([v.mean().item(), v.abs().mean().item(), v.abs().max().item()])
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
         print(name, "bpp_res", r_bres.item(), "bpp_mv", r_bmv.item(), "recon mean", r_recon.mean().item())
+    make_msssim_golden()
+
+
+MSSSIM_CASES = [(0, (2, 3, 176, 200), 0.05), (1, (1, 3, 161, 175), 0.02), (2, (1, 3, 256, 320), 0.1)]
+
+
+def msssim_inputs(seed, shape, noise):
+    """Deterministic image pair in [0,1] for the MS-SSIM fixtures (also used by the tests)."""
+    g = torch.Generator().manual_seed(4242 + seed)
+    x = torch.rand(shape, generator=g)
+    x = torch.nn.functional.avg_pool2d(x, 3, 1, 1)  # some spatial structure
+    y = (x + noise * torch.randn(shape, generator=g)).clamp(0, 1)
+    return x, y
+
+
+def make_msssim_golden():
+    """tests/golden/msssim.json: values of the REFERENCE's own ms_ssim (reference main/model/ms_ssim_torch.py:138-200)."""
+    import importlib
+    import json
+    from oracle import ref_import
+    ref_import.load_reference_pnet()
+    R = importlib.import_module("main.model.ms_ssim_torch")
+    out = []
+    for seed, shape, noise in MSSSIM_CASES:
+        x, y = msssim_inputs(seed, shape, noise)
+        per = R.ms_ssim(x, y, data_range=1.0, size_average=False)
+        out.append({"seed": seed, "shape": list(shape), "noise": noise, "per_image": [float(v) for v in per],
+                    "mean": float(R.ms_ssim(x, y, data_range=1.0))})
+        print("msssim", seed, shape, out[-1]["mean"])
+    json.dump(out, open(os.path.join(OUT, "msssim.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -55,7 +55,7 @@ def sq_err_sum(a, b, acc, slot):
                                 torch.cuda.current_stream(a.device).cuda_stream), "sq_err_sum")
 
 
-def code_gop(net, i_frame, p_frames, enable_amp=False, keep_recon=False):
+def code_gop(net, i_frame, p_frames, enable_amp=False, keep_recon=False, with_msssim=False):
     """Code one GOP.  i_frame (1,3,h,w): the (decoded) I-frame; p_frames (T,3,h,w): the frames to code.
     Returns dict with device tensors `bpp_mv`, `bpp_res` (T,), `sse` (T,) fp64 (sum of squared error over the
     cropped frame) and `numel`; plus `recon` (list of cropped reconstructions) when keep_recon."""
@@ -63,7 +63,7 @@ def code_gop(net, i_frame, p_frames, enable_amp=False, keep_recon=False):
     T, _, h, w = p_frames.shape
     refs = [pad(i_frame, 64)]
     sse = torch.zeros(T, device=dev, dtype=torch.float64)
-    bmv, bres, recons = [], [], []
+    bmv, bres, recons, mss = [], [], [], []
     for i in range(T):
         x = pad(p_frames[i:i + 1], 64)
         recon, bpp_res, bpp_mv = net(x, reference_window(refs), enable_amp)
@@ -72,11 +72,16 @@ def code_gop(net, i_frame, p_frames, enable_amp=False, keep_recon=False):
             refs = [refs[0]] + refs[-3:]
         rc = crop(recon, (h, w))
         sq_err_sum(rc, p_frames[i:i + 1], sse, i)
+        if with_msssim:              # tools/predict.py:93-94 (the enable_amp branch of the shipped cfg/predict.yaml)
+            from tdvc_b200.metrics import ms_ssim
+            mss.append(ms_ssim(rc.float(), p_frames[i:i + 1], data_range=1.0))
         bmv.append(bpp_mv.reshape(-1)[0])
         bres.append(bpp_res.reshape(-1)[0])
         if keep_recon:
             recons.append(rc.clone())
     out = {"bpp_mv": torch.stack(bmv), "bpp_res": torch.stack(bres), "sse": sse, "numel": 3 * h * w}
+    if with_msssim:
+        out["msssim"] = torch.stack(mss)
     if keep_recon:
         out["recon"] = recons
     return out
@@ -84,11 +89,11 @@ def code_gop(net, i_frame, p_frames, enable_amp=False, keep_recon=False):
 
 def gop_stats(res):
     """Per-GOP sums in the reference's reporting units -> fp64 tensor
-    [sum bpp, sum bpp_mv, sum bpp_res, sum psnr, sum msssim (0: not computed), sum mse, n_frames]."""
+    [sum bpp, sum bpp_mv, sum bpp_res, sum psnr, sum msssim (0 unless code_gop(with_msssim=True)), sum mse, n_frames]."""
     mse = res["sse"] / res["numel"]
     psnr = 10.0 * torch.log10(1.0 / mse)
     bmv, bres = res["bpp_mv"].double(), res["bpp_res"].double()
-    z = torch.zeros((), device=mse.device, dtype=torch.float64)
+    z = res["msssim"].double().sum() if "msssim" in res else torch.zeros((), device=mse.device, dtype=torch.float64)
     return torch.stack([(bmv + bres).sum(), bmv.sum(), bres.sum(), psnr.sum(), z, mse.sum(),
                         torch.tensor(float(mse.numel()), device=mse.device, dtype=torch.float64)])
 
@@ -109,7 +114,7 @@ def reduce_stats(stats, group=None):
 def summarise(stats):
     s = [float(v) for v in stats.tolist()]
     n = max(s[6], 1.0)
-    return {"bpp": s[0] / n, "bpp_mv": s[1] / n, "bpp_res": s[2] / n, "psnr": s[3] / n, "mse": s[5] / n,
+    return {"bpp": s[0] / n, "bpp_mv": s[1] / n, "bpp_res": s[2] / n, "psnr": s[3] / n, "msssim": s[4] / n, "mse": s[5] / n,
             "frames": int(s[6])}
 
 

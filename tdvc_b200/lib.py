@@ -74,6 +74,8 @@ SIGNATURES = {
     "tdvc_ff_match": [vp, vp, vp, vp, i32, i32, i32, vp],
     "tdvc_ff_gather": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "tdvc_sq_err_sum": [vp, vp, i64, vp, vp],
+    "tdvc_ssim_level": [vp, vp, i32, i32, i32, i32, C.POINTER(C.c_float), f32, f32, vp, vp],
+    "tdvc_avgpool2_pad": [vp, vp, i32, i32, i32, vp],
 }
 
 _lib = None

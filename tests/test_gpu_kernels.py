@@ -439,3 +439,44 @@ def test_featurefix_match_and_gather_vs_oracle(plan, dev, hw):
     assert torch.equal(og.nchw().cpu(), gathered)  # pure data movement: bit-exact
     assert (oc.cpu() - cor).abs().max() < 1e-5
     assert (oa.nchw().cpu() - f_in * cor).abs().max() < 1e-4 and (ob.nchw().cpu() - gathered * cor).abs().max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ MS-SSIM
+def test_msssim_vs_oracle_and_reference_golden(dev):
+    """tdvc_b200.metrics.ms_ssim (fused CUDA scale kernel) against oracle/ms_ssim.py and against the committed values of the
+    reference's own function (tests/golden/msssim.json).  fp32 filter sums in a different order: 2e-5 absolute."""
+    import json
+    import os
+    from conftest import ROOT
+    from oracle import ms_ssim as O
+    from oracle.make_golden import msssim_inputs
+    from tdvc_b200.metrics import ms_ssim
+    for c in json.load(open(os.path.join(ROOT, "tests", "golden", "msssim.json"))):
+        x, y = msssim_inputs(c["seed"], tuple(c["shape"]), c["noise"])
+        got = ms_ssim(x.to(dev), y.to(dev), data_range=1.0, size_average=False).cpu()
+        assert torch.allclose(got, torch.tensor(c["per_image"]), atol=2e-5, rtol=0), (got, c["per_image"])
+        assert torch.allclose(got, O.ms_ssim(x, y, data_range=1.0, size_average=False), atol=2e-5, rtol=0)
+        assert abs(float(ms_ssim(x.to(dev), y.to(dev), data_range=1.0)) - c["mean"]) < 2e-5
+    torch.manual_seed(9)
+    x = torch.rand(1, 3, 163, 177)      # odd sizes: padded pooling between the scales
+    y = (x + 0.1 * torch.randn_like(x)).clamp(0, 1)
+    assert abs(float(ms_ssim(x.to(dev), y.to(dev), data_range=1.0)) - float(O.ms_ssim(x, y, data_range=1.0))) < 2e-5
+
+
+def test_msssim_full_size_properties(dev):
+    """1920x1024 (BASELINE config 2): identity gives 1, symmetry, monotone in the distortion, errors like the reference."""
+    from tdvc_b200.metrics import ms_ssim
+    torch.manual_seed(1)
+    x = torch.rand(1, 3, 1024, 1920, device=dev)
+    x = F.avg_pool2d(x, 5, 1, 2)
+    assert abs(float(ms_ssim(x, x, data_range=1.0)) - 1.0) < 1e-6
+    n = torch.randn_like(x)
+    a = float(ms_ssim(x, (x + 0.02 * n).clamp(0, 1), data_range=1.0))
+    b = float(ms_ssim(x, (x + 0.08 * n).clamp(0, 1), data_range=1.0))
+    assert 0.0 < b < a < 1.0
+    y = (x + 0.05 * n).clamp(0, 1)
+    assert abs(float(ms_ssim(x, y, data_range=1.0)) - float(ms_ssim(y, x, data_range=1.0))) < 1e-6
+    with pytest.raises(ValueError):
+        ms_ssim(x, x[:, :, :512], data_range=1.0)
+    with pytest.raises(RuntimeError):
+        ms_ssim(x.cpu(), x.cpu(), data_range=1.0)

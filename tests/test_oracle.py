@@ -118,3 +118,39 @@ def test_compressai_port_basics():
     assert lk[0, 0, 0, 0] > 0.99999  # sigma floored at 0.11
     m = MaskedConv2d(2, 4, 5, padding=2)
     assert int(m.mask[0, 0].sum()) == 12
+
+
+# ------------------------------------------------------------------------------------------------ MS-SSIM
+def _msssim_cases():
+    import json
+    import os
+    from conftest import ROOT
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "msssim.json")))
+
+
+def test_msssim_oracle_vs_golden():
+    """oracle/ms_ssim.py against values of the reference's own ms_ssim (fixture made by oracle/make_golden.py)."""
+    from oracle import ms_ssim as O
+    from oracle.make_golden import msssim_inputs
+    for c in _msssim_cases():
+        x, y = msssim_inputs(c["seed"], tuple(c["shape"]), c["noise"])
+        per = O.ms_ssim(x, y, data_range=1.0, size_average=False)
+        assert torch.allclose(per, torch.tensor(c["per_image"]), atol=2e-5, rtol=0)
+        assert abs(float(O.ms_ssim(x, y, data_range=1.0)) - c["mean"]) < 2e-5
+
+
+@needs_ref
+def test_msssim_oracle_vs_reference_function():
+    """... and against the reference function imported verbatim, on fresh inputs (odd sizes exercise the padded pooling)."""
+    import importlib
+    from oracle import ms_ssim as O
+    ref_import.load_reference_pnet()
+    R = importlib.import_module("main.model.ms_ssim_torch")
+    torch.manual_seed(3)
+    for shape in ((1, 3, 163, 177), (2, 3, 192, 224)):
+        x = torch.rand(shape)
+        y = (x + 0.08 * torch.randn(shape)).clamp(0, 1)
+        assert torch.allclose(O.ms_ssim(x, y, data_range=1.0, size_average=False),
+                              R.ms_ssim(x, y, data_range=1.0, size_average=False), atol=2e-5, rtol=0)
+    x = torch.rand(1, 3, 176, 176)
+    assert abs(float(R.ms_ssim(x, x, data_range=1.0)) - 1.0) < 1e-6 and abs(float(O.ms_ssim(x, x, data_range=1.0)) - 1.0) < 1e-6
