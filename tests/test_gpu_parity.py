@@ -95,6 +95,35 @@ def test_pframe_forward_vs_reference_golden(net, dev, name, impl):
         assert np.abs(recon.cpu().numpy() - g["recon"]).max() <= 1e-3
 
 
+@pytest.mark.parametrize("impl", [1, 0])
+def test_batch_of_two_vs_oracle(net, oracle_model, dev, impl):
+    """N = 2 (the reference's DataParallel / training batches, bpp aggregated over the batch: reference pnet.py:38-43,82-83):
+    two different frame pairs in one call against the oracle on the same batch."""
+    from tdvc_b200 import synth
+    xa, ra = synth.make_frame_pair(64, 128, seed=11)
+    xb, rb = synth.make_frame_pair(64, 128, seed=12)
+    x, refs = torch.cat([xa, xb], 0), torch.cat([ra, rb], 0)
+    ot, gt = {}, {}
+    net.conv_impl = impl
+    with torch.no_grad():
+        o = oracle_model(x, refs, False, taps=ot)
+        g = net(x.to(dev), refs.to(dev), False, taps=gt)
+    net.conv_impl = 0
+    for c in ("mv", "res"):
+        assert (ot[f"{c}.y_hat"] == gt[f"{c}.y_hat"].cpu()).float().mean().item() >= 0.999
+        assert (ot[f"{c}.z_hat"] == gt[f"{c}.z_hat"].cpu()).float().mean().item() >= 0.999
+    assert torch.equal(ot["loopfilter.ind"], gt["loopfilter.ind"].cpu())
+    assert (o[0] - g[0].cpu()).abs().max().item() <= 1e-3
+    assert abs(o[1].item() - g[1].item()) <= 1e-3 * o[1].item() and abs(o[2].item() - g[2].item()) <= 1e-3 * o[2].item()
+    # and the batch result equals the two single-frame results (recon) / their mean (bpp)
+    with torch.no_grad():
+        ga = net(xa.to(dev), ra.to(dev), False)
+        gb = net(xb.to(dev), rb.to(dev), False)
+    # (not bit-identical: the batched launches tile / reduce in a different order)
+    assert (g[0][0:1] - ga[0]).abs().max().item() <= 1e-4 and (g[0][1:2] - gb[0]).abs().max().item() <= 1e-4
+    assert abs(g[1].item() - 0.5 * (ga[1].item() + gb[1].item())) <= 1e-4 * g[1].item()
+
+
 def test_default_init_degenerate_case(dev):
     """Module default init: all symbols 0, DCN offsets exactly 0 - still must agree."""
     from oracle.stats import build_oracle
