@@ -145,6 +145,30 @@ def test_gdn_as_fused_conv(plan, dev):
             assert (out.nchw().cpu() - want).abs().max() < tol * want.abs().max(), impl
 
 
+@pytest.mark.parametrize("cout,H,W", [(64, 17, 23), (216, 33, 9), (128, 40, 31), (32, 35, 12)])
+def test_conv_tc_writes_only_its_view(plan, dev, cout, H, W):
+    """Guard bands: the tensor-core kernel stores through a channel view (ld > C, offset 4 floats... here 8 to keep the
+    16-byte alignment) of a larger tensor with guard rows before and after; everything outside the view keeps its
+    sentinel (ragged tiles in x, y and in the channel dimension)."""
+    from tdvc_b200.model import Act, pack_conv
+    from tdvc_b200 import tc
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(64, cout, 3, 1, 1)
+    x = torch.randn(1, 64, H, W)
+    want = conv(x)
+    cw = pack_conv(conv.weight.to(dev), conv.bias.to(dev), src_layout=[(64, 64)])
+    tc.attach_f16({"w": cw})
+    ld = cout + 16
+    big = torch.full((H + 4, W, ld), 12345.0, device=dev)          # 2 guard rows above and below
+    view = Act(big, big.data_ptr() + 4 * (2 * W * ld + 8), 1, H, W, cout, ld)
+    plan.conv([Act.from_nchw(x.to(dev))], cw, view, impl=2)
+    torch.cuda.synchronize()
+    got = big[2:H + 2, :, 8:8 + cout].permute(2, 0, 1).unsqueeze(0).cpu()
+    assert (got - want).abs().max() < 1e-4 * want.abs().max()
+    assert (big[:2] == 12345.0).all() and (big[H + 2:] == 12345.0).all()
+    assert (big[2:H + 2, :, :8] == 12345.0).all() and (big[2:H + 2, :, 8 + cout:] == 12345.0).all()
+
+
 # ------------------------------------------------------------------------------------------------ DCN
 def test_dcn_zero_offset_known_answer(dev):
     """reference main/utils/dcnv2/testcuda.py:36-71 (check_zero_offset): 2*dcn(x) == x."""
