@@ -813,6 +813,31 @@ class _Plan:
                          "recon_feat": rec_f.nchw()})
         return recon, bpp
 
+    def fusion_and_filter(self, W, pred1_nchw, refs_nchw, recf_nchw):
+        """BASELINE config 5: the multi-frame feature fusion (reference pnet.py:266-293, 296-317) and the reference-based
+        in-loop filter (:187-263) on their own.  pred1 / recf (N,64,H,W), refs (N,4,3,H,W) contiguous fp32 CUDA."""
+        N, H, Wd = self.N, self.H, self.W
+        self._order = 0
+        r123 = self.buf("r123", 3 * N, H, Wd, 3, ld=4)
+        ifr = self.buf("iframe", N, H, Wd, 3, ld=4)
+        fr = 3 * H * Wd * 4
+        for n in range(N):
+            base = refs_nchw.data_ptr() + n * 4 * fr
+            self.call("tdvc_nchw_to_nhwc", base, ifr.batch(n).ptr, 1, 3, H, Wd, 4)
+            self.call("tdvc_nchw_to_nhwc", base + fr, r123.batch(3 * n).ptr, 3, 3, H, Wd, 4)
+        t4 = self.buf("mf.t4", 4 * N, H, Wd, 64)
+        pred1 = self.buf("pred1", N, H, Wd, 64) if N > 1 else t4.batch(3)
+        self.call("tdvc_nchw_to_nhwc", pred1_nchw.data_ptr(), pred1.ptr, N, 64, H, Wd, 64)
+        rec_f = self.buf("rec_f", N, H, Wd, 64)
+        self.call("tdvc_nchw_to_nhwc", recf_nchw.data_ptr(), rec_f.ptr, N, 64, H, Wd, 64)
+        pred = self.mcfilter(W, pred1, r123, t4)
+        recon4 = self.loopfilter(W, rec_f, ifr, None)
+        pred_out = self.raw("c5.pred", (N, 64, H, Wd))
+        recon = self.raw("recon", (N, 3, H, Wd))
+        self.call("tdvc_nhwc_to_nchw", pred.ptr, pred.ld, pred_out.data_ptr(), N, 64, H, Wd)
+        self.call("tdvc_nhwc_to_nchw", recon4.ptr, recon4.ld, recon.data_ptr(), N, 3, H, Wd)
+        return pred_out, recon
+
     def motion_est(self, W, feats, imgs, taps):
         N, H, Wd = self.N, self.H, self.W
         lr1 = dict(act=L.ACT_LRELU, slope=0.1)
@@ -1023,6 +1048,28 @@ class VideoCompressor(nn.Module):
             bpp = bpp.float()
         # reference returns (recon, bpp_res.view(-1), bpp_mv.view(-1))  (pnet.py:82-83)
         return recon, bpp[1].view(-1), bpp[0].view(-1)
+
+    def fusion_and_filter(self, prediction1, refer_frames, recon_feat):
+        """BASELINE config 5 entry: `mcfilter` (reference pnet.py:53) on `prediction1` and `loopfilter` + clamp (:77-78) on
+        `recon_feat`, with the 4 reference frames.  Returns (prediction (N,64,H,W), recon (N,3,H,W))."""
+        if not prediction1.is_cuda:
+            raise RuntimeError("tdvc_b200.VideoCompressor runs on CUDA (sm_100a) only; there is no CPU fallback")
+        N, C, H, W = prediction1.shape
+        if C != 64 or recon_feat.shape != prediction1.shape or refer_frames.shape != (N, 4, 3, H, W):
+            raise RuntimeError("expected prediction1 / recon_feat (N,64,H,W) and refer_frames (N,4,3,H,W)")
+        if H % 64 or W % 64:
+            raise RuntimeError("H and W must be multiples of 64")
+        dev = prediction1.device
+        with torch.cuda.device(dev), torch.no_grad():
+            Wt = self._weights(dev)
+            plan = self._plan(N, H, W, dev)
+            plan.impl = self.conv_impl
+            plan.launches = 0
+            pred, recon = plan.fusion_and_filter(Wt, prediction1.detach().float().contiguous(),
+                                                 refer_frames.detach().float().contiguous(),
+                                                 recon_feat.detach().float().contiguous())
+            self.last_launches = plan.launches
+            return pred.clone(), recon.clone()
 
     def _graph_forward(self, plan, Wt, x, refs):
         k = (x.device, plan.N, plan.H, plan.W, self.conv_impl)

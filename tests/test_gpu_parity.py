@@ -124,6 +124,26 @@ def test_batch_of_two_vs_oracle(net, oracle_model, dev, impl):
     assert abs(g[1].item() - 0.5 * (ga[1].item() + gb[1].item())) <= 1e-4 * g[1].item()
 
 
+@pytest.mark.parametrize("impl", [1, 0])
+def test_config5_fusion_and_inloop_filter_vs_oracle(net, oracle_model, dev, impl):
+    """BASELINE config 5: multi-frame feature fusion + reference-based in-loop filter with 4 reference frames, fed with the
+    oracle's own intermediate tensors (prediction1, recon_feat) of a synthetic frame pair."""
+    from tdvc_b200 import synth
+    x, refs = synth.make_frame_pair(128, 192, seed=5)
+    taps = {}
+    with torch.no_grad():
+        oracle_model(x, refs, False, taps=taps)
+        pred1, recf = taps["prediction1"], taps["recon_feat"]
+        want_pred = oracle_model.mcfilter(pred1, refs)
+        want_recon = oracle_model.loopfilter(recf, refs).clamp(0.0, 1.0)
+    net.conv_impl = impl
+    got_pred, got_recon = net.fusion_and_filter(pred1.to(dev), refs.to(dev), recf.to(dev))
+    net.conv_impl = 0
+    assert (got_pred.cpu() - want_pred).abs().max().item() <= 1e-4 * max(1.0, want_pred.abs().max().item())
+    assert (got_recon.cpu() - want_recon).abs().max().item() <= 1e-4
+    assert net.last_launches > 40
+
+
 def test_default_init_degenerate_case(dev):
     """Module default init: all symbols 0, DCN offsets exactly 0 - still must agree."""
     from oracle.stats import build_oracle
