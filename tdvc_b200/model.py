@@ -523,6 +523,8 @@ class _Plan:
         self.prof = None  # list of (label, macs, bytes, start_event, end_event) when instrumented (bench.py)
         self._order = 0
         self.alternate_order = os.environ.get("TDVC_B200_NO_ALTERNATE") is None   # developer A/B switch
+        self.overlap_hyper = os.environ.get("TDVC_B200_NO_OVERLAP") is None       # developer A/B switch
+        self._side = None
 
     def _prof_begin(self):
         if self.prof is None:
@@ -685,6 +687,44 @@ class _Plan:
         a = rb("ga", 6, a)
         a = self.conv([a], W[f"{cn}.ga7"], b("ga7.o", H // 16, Wd // 16), stride=2)
         y = self.se(a, W[f"{cn}.ga8"], b("y", a.H, a.W))
+        # ---- y_hat first: both the synthesis transform and the entropy model start from it
+        yh = b("y_hat", y.H, y.W)
+        self.call("tdvc_round_half_even", y.ptr, yh.ptr, y.N * y.H * y.W * 128, nbytes=8 * y.N * y.H * y.W * 128)
+        # The hyperprior / context / entropy-parameter chain only feeds the bit count (x_hat depends on round(y) alone,
+        # SURVEY.md App. A): ~17 small, latency-bound launches at H/16..H/64.  They run on a side stream, concurrently
+        # with the (equally small) first layers of g_s, and are joined before this coder returns.
+        main = torch.cuda.current_stream(self.dev)
+        side = self._side_stream() if self.overlap_hyper else None
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side if side is not None else main):
+            gp, z, zh = self._hyper_path(W, cn, y, yh, acc_off, b, lr)
+        # ---- g_s
+        g = self.se(yh, W[f"{cn}.gs0"], b("gs0.o", y.H, y.W))
+        g = rb("gs", 1, g)
+        g = rb_up(2, g)
+        g = rb("gs", 3, g)
+        g = rb_up(4, g)
+        g = self.se(g, W[f"{cn}.gs5"], b("gs5.o", g.H, g.W))
+        g = rb("gs", 6, g)
+        g = rb_up(7, g)
+        g = rb("gs", 8, g)
+        xh = self.conv([g], W[f"{cn}.gs9"], out if out is not None else b("x_hat", H, Wd, 64), res1=final_res)
+        if side is not None:
+            main.wait_stream(side)
+        if taps is not None:
+            nm = "mv" if cn == "mv" else "res"
+            taps.update({f"{nm}.y": y.nchw(), f"{nm}.z": z.nchw(), f"{nm}.y_hat": yh.nchw(), f"{nm}.z_hat": zh.nchw(),
+                         f"{nm}.scales_hat": gp.chan(0, 128).nchw(), f"{nm}.means_hat": gp.chan(128, 128).nchw()})
+        return xh
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        return self._side
+
+    def _hyper_path(self, W, cn, y, yh, acc_off, b, lr):
+        """h_a, factorised prior on z, h_s, context model, entropy parameters, conditional likelihood -> sum ln p."""
         # ---- h_a
         h = self.conv([y], W[f"{cn}.ha0"], b("ha0", y.H, y.W), **lr)
         h = self.conv([h], W[f"{cn}.ha2"], b("ha2", y.H, y.W), **lr)
@@ -702,9 +742,7 @@ class _Plan:
         s = self.conv([s], W[f"{cn}.hs4"], b("hs4", s.H, s.W, 192), **lr)
         s = self.conv([s], W[f"{cn}.hs6"], b("hs6", 2 * s.H, 2 * s.W, 192), **lr)
         params = self.conv([s], W[f"{cn}.hs8"], b("params", s.H, s.W, 256))
-        # ---- y_hat, context model, entropy parameters, conditional likelihood
-        yh = b("y_hat", y.H, y.W)
-        self.call("tdvc_round_half_even", y.ptr, yh.ptr, y.N * y.H * y.W * 128, nbytes=8 * y.N * y.H * y.W * 128)
+        # ---- context model, entropy parameters, conditional likelihood
         ctx = self.conv([yh], W[f"{cn}.ctx"], b("ctx", y.H, y.W, 256))
         c0, c2 = W[f"{cn}.ep0"].cout, W[f"{cn}.ep2"].cout
         e = self.conv([params, ctx], W[f"{cn}.ep0"], b("ep0", y.H, y.W, c0, ld=_r(c0, 8), zero=True), **lr)
@@ -712,22 +750,7 @@ class _Plan:
         gp = self.conv([e], W[f"{cn}.ep4"], b("gp", y.H, y.W, 256))
         self.call("tdvc_gc_bits", y.ptr, gp.ptr, gp.ld, y.N * y.H * y.W, 128, self.acc.data_ptr() + 8 * acc_off,
                   nbytes=12 * y.N * y.H * y.W * 128)
-        # ---- g_s
-        g = self.se(yh, W[f"{cn}.gs0"], b("gs0.o", y.H, y.W))
-        g = rb("gs", 1, g)
-        g = rb_up(2, g)
-        g = rb("gs", 3, g)
-        g = rb_up(4, g)
-        g = self.se(g, W[f"{cn}.gs5"], b("gs5.o", g.H, g.W))
-        g = rb("gs", 6, g)
-        g = rb_up(7, g)
-        g = rb("gs", 8, g)
-        xh = self.conv([g], W[f"{cn}.gs9"], out if out is not None else b("x_hat", H, Wd, 64), res1=final_res)
-        if taps is not None:
-            nm = "mv" if cn == "mv" else "res"
-            taps.update({f"{nm}.y": y.nchw(), f"{nm}.z": z.nchw(), f"{nm}.y_hat": yh.nchw(), f"{nm}.z_hat": zh.nchw(),
-                         f"{nm}.scales_hat": gp.chan(0, 128).nchw(), f"{nm}.means_hat": gp.chan(128, 128).nchw()})
-        return xh
+        return gp, z, zh
 
     # ---------------------------------------------------------------- one P-frame
     def forward(self, W, x_nchw, refs_nchw, taps=None):
