@@ -101,6 +101,13 @@ def cpu_oracle_rate(steps, warmup):
                 ts.append(time.perf_counter() - t0)
     t = sum(ts) / len(ts)
     scale = (H * W) / (h * w)
+    # BASELINE config 1 (the reference's own CPU-runnable case): one 256x256 frame pair, batch 1
+    x1, r1 = synth.make_frame_pair(256, 256, seed=4)
+    with torch.no_grad():
+        orc(x1, r1, False)
+        t0 = time.perf_counter()
+        orc(x1, r1, False)
+        cpu_oracle_rate.config1_s = time.perf_counter() - t0
     return 1.0 / (t * scale), t, cores, torch.get_num_threads()
 
 
@@ -116,7 +123,8 @@ def run_reference(args):
             "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "UVG-shaped synthetic 1920x1024 sequence, GOP 12, P-frame forward (bounded CPU sample)"},
-            "cpu_baseline": {"value": fps, "unit": "P-frames/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "P-frames/s", "cores": threads, "kind": "port", "sample": sample,
+                             "config1_256x256_s_per_frame": cpu_oracle_rate.config1_s},
             "e2e": {"value": fps, "unit": "P-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -309,7 +317,8 @@ def main():
             fps_cpu, tcpu, cores, threads = cpu_oracle_rate(1, 1)
             cpu = {"value": fps_cpu, "unit": "P-frames/s", "cores": threads, "kind": "port",
                    "sample": f"1 P-frame at {CPU_SAMPLE[0]}x{CPU_SAMPLE[1]} (1/8 of the 1920x1024 pixels) after 1 warm-up, "
-                             f"{tcpu:.2f} s, rate scaled by pixel count; oracle/model.py, torch fp32, {threads} threads"}
+                             f"{tcpu:.2f} s, rate scaled by pixel count; oracle/model.py, torch fp32, {threads} threads",
+                   "config1_256x256_s_per_frame": cpu_oracle_rate.config1_s}
         frame_bytes = 3 * hh * ww * 4
         line = {"metric": "1920x1024 P-frames/sec", "value": value, "unit": "P-frames/s", "n_gpus": world, "steps": K,
                 "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
