@@ -46,7 +46,8 @@ const char* tdvc_last_error(void);
  * weight layout: [kh*kw][cin_pad][cout_pad] fp32, zero padded; for shuffle==2 the output-channel order is
  * permuted on the host to co' = (dy*2+dx)*(cout/4) + c (nn.PixelShuffle folded into the store).
  * Constraints: src_c[i] % 4 == 0, src_ld[i] % 4 == 0, 16-byte aligned sources, cin_pad % 8 == 0,
- * cout_pad % 16 == 0.  `impl`: 0 = auto, 1 = SIMT fp32 FFMA kernel, 2 = tcgen05 tensor-core kernel
+ * cout_pad % 16 == 0.  `impl`: 0 = auto, 1 = SIMT fp32 FFMA kernel, 3 = SIMT fp32 kernel for <= 4 output channels
+ * (single source, 3x3 / 7x7, stride 1; csrc/conv_small.cu; auto picks it for those shapes), 2 = tcgen05 tensor-core kernel
  * (fp16 split: x = hi + lo, w = hi + lo, (w_hi + w_lo)*(x_hi + x_lo), fp32 accumulate in TMEM; needs weight_f16).                                             */
 typedef struct {
   const float* src[4];
@@ -154,10 +155,11 @@ int tdvc_round_half_even(const float* x, float* out, int64_t n, void* stream);
 
 /* ---- squeeze-excitation (reference inflate.py:159-208): two launches.
  * se_partial_sums: partial[b][n][c] = sum over a slab of pixels (deterministic two-stage mean).
- * se_apply: s = sigmoid(W2 relu(W1 mean + b1) + b2) recomputed per block; out = act(x*s) (+ res).
+ * se_apply: s = sigmoid(W2 relu(W1 mean + b1) + b2) computed once per image (a one-block kernel that overwrites
+ * partial[n*C + c] with the gate), then out = act(x*s) (+ res) streamed by a second kernel.
  * w1: [Cr][C], w2: [C][Cr] (the 1x1 conv weights as stored). nblk <= 1024.                          */
 int tdvc_se_partial_sums(const float* x, int ld, int N, int64_t HW, int C, float* partial, int nblk, void* stream);
-int tdvc_se_apply(const float* x, int ld, const float* partial, int nblk, const float* w1, const float* b1,
+int tdvc_se_apply(const float* x, int ld, float* partial, int nblk, const float* w1, const float* b1,
                   const float* w2, const float* b2, int N, int64_t HW, int C, int Cr, int act, float slope,
                   const float* res, int res_ld, float* out, int out_ld, void* stream);
 

@@ -15,6 +15,8 @@ int conv2d_validate(const TdvcConvParams* p);
 int conv2d_simt(const TdvcConvParams& p, cudaStream_t st);
 int conv2d_tc_supported(const TdvcConvParams& p);
 int conv2d_tc(const TdvcConvParams& p, cudaStream_t st);
+int conv2d_small_supported(const TdvcConvParams& p);
+int conv2d_small(const TdvcConvParams& p, cudaStream_t st);
 }  // namespace tdvc
 
 extern "C" int tdvc_version(void) { return 100; }
@@ -31,6 +33,8 @@ extern "C" int tdvc_conv2d(const TdvcConvParams* p, void* stream) {
     }
     return tdvc::conv2d_tc(*p, st);
   }
+  if (p->impl == 3) return tdvc::conv2d_small(*p, st);
+  if (p->impl == 0 && tdvc::conv2d_small_supported(*p)) return tdvc::conv2d_small(*p, st);
   if (p->impl == 0 && tdvc::conv2d_tc_supported(*p)) return tdvc::conv2d_tc(*p, st);
   return tdvc::conv2d_simt(*p, st);
 }

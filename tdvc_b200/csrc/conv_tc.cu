@@ -805,7 +805,8 @@ struct Choice {
 // with >= 96 output channels (a multiple of 4), in tiles of 128 with the 3-product split scheme.
 static bool choose(const TdvcConvParams& p, Choice* c) {
   if (p.kh != p.kw || p.pad != p.kh / 2 || p.cin < 4 || p.cout < 1) return false;
-  // (1x1 layers are epilogue / latency-bound, not MMA-bound: the 64-channel tiles give them twice as many work items)
+  // 1x1 layers stay on 64-channel tiles: 128-channel split tiles were measured slower for them (GDN 128->128 @512x960:
+  // 0.35 -> 0.48 ms) - they are bound by the epilogue's latency chain, and the smaller tiles give twice as many items
   const int split = (p.cout >= 96 && (p.cout & 3) == 0 && p.kh != 7 && p.kh != 1) ? 1 : 0;
   if (p.stride == 2) {
     if (p.kh == 3) { *c = {3, 16, 2, split}; return true; }

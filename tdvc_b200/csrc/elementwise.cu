@@ -177,33 +177,50 @@ __global__ void se_partial_kernel(const float* __restrict__ x, int ld, int64_t H
   }
 }
 
-__global__ void se_apply_kernel(const float* __restrict__ x, int ld, const float* __restrict__ partial, int nblk,
-                                const float* __restrict__ w1, const float* __restrict__ b1,
-                                const float* __restrict__ w2, const float* __restrict__ b2,
-                                int N, int64_t HW, int C, int Cr, int act, float slope,
-                                const float* __restrict__ res, int res_ld, float* __restrict__ out, int out_ld) {
+// Squeeze-excite gate of image n (reference inflate.py:189-207): channel means from the partial sums, C -> C/16 ReLU ->
+// C sigmoid.  One block per image; the C gate values are written back over the image's first row of partial sums
+// (partial[n*C + c], read by se_apply_kernel), so the streaming kernel's blocks do not each repeat the reduction.
+__global__ void se_scale_kernel(float* __restrict__ partial, int nblk, const float* __restrict__ w1,
+                                const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                                int N, int64_t HW, int C, int Cr) {
   extern __shared__ float sh[];
   float* mean = sh;            // [C]
   float* hid = sh + C;         // [Cr]
-  float* sc = sh + C + Cr;     // [C]
-  const int n = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += partial[((int64_t)b * N + n) * C + c];
-    mean[c] = s / (float)HW;
+  float* red = sh + C + Cr;    // [blockDim.x]
+  const int n = blockIdx.x;
+  const int nsl = blockDim.x / C;               // slices of the partial-sum rows summed in parallel (blockDim.x % C == 0)
+  const int c = threadIdx.x % C, sl = threadIdx.x / C;
+  float s = 0.f;
+  if (sl < nsl)
+    for (int b = sl; b < nblk; b += nsl) s += partial[((int64_t)b * N + n) * C + c];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.f;
+    for (int k = 0; k < nsl; ++k) t += red[k * C + threadIdx.x];
+    mean[threadIdx.x] = t / (float)HW;
   }
   __syncthreads();
   for (int r = threadIdx.x; r < Cr; r += blockDim.x) {
-    float s = b1[r];
-    for (int c = 0; c < C; ++c) s = fmaf(w1[r * C + c], mean[c], s);
-    hid[r] = fmaxf(s, 0.f);
+    float t = b1[r];
+    for (int k = 0; k < C; ++k) t = fmaf(w1[r * C + k], mean[k], t);
+    hid[r] = fmaxf(t, 0.f);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = b2[c];
-    for (int r = 0; r < Cr; ++r) s = fmaf(w2[c * Cr + r], hid[r], s);
-    sc[c] = 1.f / (1.f + expf(-s));
+  if (threadIdx.x < C) {
+    float t = b2[threadIdx.x];
+    for (int r = 0; r < Cr; ++r) t = fmaf(w2[threadIdx.x * Cr + r], hid[r], t);
+    partial[(int64_t)n * C + threadIdx.x] = 1.f / (1.f + expf(-t));
   }
+}
+
+__global__ void se_apply_kernel(const float* __restrict__ x, int ld, const float* __restrict__ gate,
+                                int N, int64_t HW, int C, int act, float slope,
+                                const float* __restrict__ res, int res_ld, float* __restrict__ out, int out_ld) {
+  extern __shared__ float sh[];
+  float* sc = sh;              // [C]
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sc[c] = gate[(int64_t)n * C + c];
   __syncthreads();
   const int lanes_c = C >> 2;
   const int64_t total = HW * lanes_c;
@@ -331,7 +348,7 @@ extern "C" int tdvc_se_partial_sums(const float* x, int ld, int N, int64_t HW, i
   return TDVC_OK;
 }
 
-extern "C" int tdvc_se_apply(const float* x, int ld, const float* partial, int nblk, const float* w1, const float* b1,
+extern "C" int tdvc_se_apply(const float* x, int ld, float* partial, int nblk, const float* w1, const float* b1,
                              const float* w2, const float* b2, int N, int64_t HW, int C, int Cr, int act, float slope,
                              const float* res, int res_ld, float* out, int out_ld, void* stream) {
   TDVC_REQUIRE(x && partial && w1 && b1 && w2 && b2 && out && N > 0 && HW > 0 && Cr > 0, "se_apply: bad args");
@@ -340,8 +357,13 @@ extern "C" int tdvc_se_apply(const float* x, int ld, const float* partial, int n
   int gx = ew_grid(HW * (C / 4));
   if (gx > kNumSMs * 8) gx = kNumSMs * 8;
   dim3 grid(gx, N);
-  se_apply_kernel<<<grid, 256, (2 * C + Cr) * sizeof(float), (cudaStream_t)stream>>>(
-      x, ld, partial, nblk, w1, b1, w2, b2, N, HW, C, Cr, act, slope, res, res_ld, out, out_ld);
+  const int sthreads = C <= 256 ? (256 / C) * C : C;   // a multiple of C
+  TDVC_REQUIRE(C <= 1024, "se_apply: C %d > 1024", C);
+  se_scale_kernel<<<N, sthreads, (C + Cr + sthreads) * sizeof(float), (cudaStream_t)stream>>>(
+      partial, nblk, w1, b1, w2, b2, N, HW, C, Cr);
+  TDVC_CHECK_LAUNCH("se_scale");
+  se_apply_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>(
+      x, ld, partial, N, HW, C, act, slope, res, res_ld, out, out_ld);
   TDVC_CHECK_LAUNCH("se_apply");
   return TDVC_OK;
 }

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("TDVC_B200_LIB") or os.path.join(HERE, "libtdvc_b200.s
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_CLAMP01 = 0, 1, 2, 3
 POST_NONE, POST_GDN, POST_IGDN = 0, 1, 2
-IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_SMALL = 0, 1, 2, 3
 
 c_fp = C.c_void_p  # device pointers travel as integers
 

@@ -634,7 +634,7 @@ class _Plan:
                                        res.ptr if res is not None else None, res.ld if res is not None else 0,
                                        out.ptr, out.ld, self._st()), "se_apply")
         self._prof_end(e0, "se_apply", 0, 4 * x.N * HW * x.C * (3 if res is not None else 2))
-        self.launches += 2
+        self.launches += 3   # partial sums, gate (one block per image), apply
         return out
 
     def call(self, fn, *a, nbytes=0):

@@ -112,6 +112,25 @@ def test_conv2d_tcgen05_vs_torch(plan, dev, idx):
     assert (got - want).abs().max() <= 2e-4 * max(1.0, want.abs().max().item())
 
 
+SMALL_CASES = [
+    # <= 4 output channels, exact fp32 SIMT kernel (csrc/conv_small.cu): cin_list, cout, k, stride, H, W, kwargs
+    ([16], 2, 7, 1, 16, 16, dict(res=True)),                           # SPyNet flow head
+    ([16], 2, 7, 1, 45, 70, dict(res=True, N=2)),                      # several tiles, ragged edges, batch
+    ([64], 3, 3, 1, 16, 40, dict()),                                   # featdown
+    ([64], 3, 3, 1, 37, 33, dict(act=2, slope=0.1, res=True)),
+    ([32], 4, 3, 1, 9, 5, dict(act=1)),
+    ([16], 1, 7, 1, 33, 8, dict()),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(SMALL_CASES)))
+def test_conv2d_small_cout_vs_torch(plan, dev, idx):
+    cin_list, cout, k, stride, H, W, kw = SMALL_CASES[idx]
+    got, want = _conv_case(plan, dev, cin_list, cout, k, stride, H, W, impl=3, seed=200 + idx, **kw)
+    assert got.shape == want.shape
+    assert (got - want).abs().max() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
 def test_conv2d_rejects_bad_arguments(plan, dev):
     from tdvc_b200 import lib as L
     p = L.ConvParams()
