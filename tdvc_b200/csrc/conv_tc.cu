@@ -15,26 +15,32 @@
 // WEIGHTS are the M-side operand - 128 rows = 64 output channels x (hi, lo) - and 256 PIXELS are the N side: two
 // MMAs (x_hi, x_lo) per k-step run at the math floor (259 cycles measured, floor 256).
 //
-// Work decomposition (persistent, one CTA per SM, 576 threads = 18 warps):
+// Work decomposition (persistent, one CTA per SM, 640 threads = 20 warps):
 //   work item  = 8 x 32 output pixels (N = 256; pixel p = ty*8 + tx) x 64 output channels;
 //                K loop = cin chunks of CK channels ("units") x KS*KS taps x CK/16 MMA k-steps.
-//   warps 8-15 producers: read the fp32 halo of one unit from global (float4 per lane, 16*CK/4 B contiguous per
+//   warps 8-17 producers: read the fp32 halo of one unit from global (float4 per lane, 16*CK/4 B contiguous per
 //              pixel, all loads of a batch in flight), split into fp16 hi / lo and store it to shared memory in the
 //              tcgen05 K-major no-swizzle canonical layout [channel/8][halo pixel][8 channels]: 8 x-adjacent pixels
 //              form one 8x16 B core matrix and the 32 tile rows are 32 row groups (SBO = halo pitch), so every tap of
 //              the convolution is the SAME buffer read through a descriptor whose start address is shifted by
 //              (ky*pitch + kx)*16 B.  No im2col copy.  Stride 2: the halo is de-interleaved into 4 parity planes.
-//   warp 17    streams pre-packed fp16 weight blocks [128 rows][CK] (one per unit x tap) with cp.async.bulk
+//   warp 19    streams pre-packed fp16 weight blocks [128 rows][CK] (one per unit x tap) with cp.async.bulk
 //              (1-D TMA) into a ring, completion on mbarriers.
-//   warp 16    one elected thread issues per k-step  D[128][256] += W * X_hi^T ; D += W * X_lo^T
+//   warp 18    one elected thread issues per k-step  D[128][256] += W * X_hi^T ; D += W * X_lo^T
 //              and tcgen05.commit's the ring slots back to the producers / loader.
-//   warps 0-7  epilogue.  TMEM lane = weight row: lane quadrants 0 / 2 hold the hi rows of output channels 0-31 /
-//              32-63, quadrants 1 / 3 the matching lo rows.  A lo warp reads its rows (tcgen05.ld, 32 pixels per
-//              chunk), rescales and hands them to its hi partner through a double-buffered shared-memory slab
-//              (named barrier per pair); the hi warp adds, applies bias / GDN / activation / residuals and stores:
-//              lane = channel, so each store instruction writes 128 contiguous bytes of one NHWC pixel.
-//              Overlaps the next item's MMAs (two accumulator stages = all 512 TMEM columns).
+//   warps 0-7  epilogue, straight from TMEM to global memory (no shared-memory transposition, no barrier; the first
+//              version went through a slab and was bound by that latency chain: image-input 3x3 0.28 -> 0.20 ms).
+//              TMEM lane = weight row.  64-channel items: lane quadrant q = channels 16q..16q+15, hi rows in lanes 0-15,
+//              lo rows in lanes 16-31; a warp reads 16 pixels per chunk (tcgen05.ld), merges hi + lo * 2^-12 with one
+//              lane-xor-16 shuffle per pixel, and each half-warp stores one tile row: 16 lanes = 64 contiguous bytes of
+//              an NHWC pixel.  128-channel items (split scheme): lane = channel, 32 lanes = 128 contiguous bytes.
+//              Bias / GDN / activation / residuals are applied in registers; GDN multipliers and the first residual
+//              are loaded one chunk ahead.  Overlaps the next item's MMAs (two accumulator stages = all 512 TMEM columns).
 #include "tc_common.cuh"
+
+#ifndef TDVC_CONV_TC_NX_MAX
+#define TDVC_CONV_TC_NX_MAX 3   // activation stages in shared memory; a 4th fits since the epilogue slab went away but measured slower (64->64 3x3: 0.424 vs 0.409 ms)
+#endif
 
 namespace tdvc {
 
@@ -46,7 +52,6 @@ constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 640
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int TW = 8, TH = 32, NPX = TW * TH;  // output tile = N of one MMA
 constexpr int NT = 64;                         // output channels per item (M = 2*NT rows: hi, lo)
-constexpr int kStageBytes = 2 * 2 * 16 * 128 * 4;  // epilogue transposition: 2 pixel halves x 2 buffers x [16 px][128 rows] fp32
 
 // SPLIT = 0: item = 64 output channels, weight rows [hi | lo*2^12] of those channels (4 products, 2 MMAs per k-step);
 // SPLIT = 1: item = 128 output channels, separate W_hi / W_lo blocks (pre-scaled by 2^w_shift so that W_lo stays in
@@ -82,8 +87,10 @@ struct Cfg {
   static constexpr int KSTEPS = CK / 16;
   static constexpr int TAPS = KS * KS;
   static constexpr int NW = (CK == 32) ? 4 : (SPLIT ? 4 : 6);
-  static constexpr int NX = (3 * X_STAGE + NW * W_BLOCK + kStageBytes + 256 <= 227 * 1024) ? 3 : 2;
-  static constexpr int SMEM = NX * X_STAGE + NW * W_BLOCK + kStageBytes + 256;
+  static constexpr int kNxMax = TDVC_CONV_TC_NX_MAX;
+  static constexpr bool fits(int nx) { return nx * X_STAGE + NW * W_BLOCK + 256 <= 227 * 1024; }
+  static constexpr int NX = (kNxMax >= 4 && fits(4)) ? 4 : (fits(3) ? 3 : 2);
+  static constexpr int SMEM = NX * X_STAGE + NW * W_BLOCK + 256;
   static_assert(NPIXP >= NPIX, "pitch");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   // smem pixel slot of halo pixel (hy, hx)
@@ -113,44 +120,6 @@ __device__ __forceinline__ Item decode_item(int item, int n_jt, int tiles_x, int
   it.y0 = (st % tiles_y) * TH;
   it.n = st / tiles_y;
   return it;
-}
-
-// Rare epilogue path, kept out of line so that the hot loop stays small: ragged channel counts (cout % 4 != 0) or
-// unaligned / odd-pitch views, one element at a time.
-struct RaggedArgs {   // passed by value (registers): taking the kernel parameter block by reference would move it to local memory
-  float* out; const float* mul; const float* res1; const float* res2;
-  int out_ld, mul_ld, res1_ld, res2_ld, post, act, shuffle, cout, Ho, Wo;
-  float slope;
-};
-__device__ __noinline__ void epilogue_ragged(RaggedArgs a, int n, int y0, int x0, const float* sb, int tx, int rd_off, int co, int ty0,
-                                              int lo_off) {
-  const int sh = a.shuffle == 2 ? 2 : 1;
-  const int cr = a.cout >> 2;
-  for (int h2 = 0; h2 < 2; ++h2) {
-    const int y = y0 + ty0 + h2, x = x0 + tx;
-    if (y >= a.Ho) continue;
-    const float* rb = sb + (h2 * 8 + tx) * 128 + rd_off;
-    for (int e = 0; e < 4; ++e) {
-      const int ce = co + e;
-      if (ce >= a.cout) break;
-      int oce = ce;
-      int64_t pe = ((int64_t)n * a.Ho + y) * a.Wo + x;
-      if (sh == 2) {
-        const int q = ce / cr;
-        oce = ce - q * cr;
-        pe = ((int64_t)n * (2 * a.Ho) + (2 * y + (q >> 1))) * (2 * a.Wo) + (2 * x + (q & 1));
-      }
-      float o = lo_off ? rb[e] + rb[e + lo_off] : rb[e];
-      if (a.post != TDVC_POST_NONE) {
-        const float mv = __ldg(a.mul + pe * a.mul_ld + oce);
-        o = mv * (a.post == TDVC_POST_IGDN ? sqrtf(o) : rsqrtf(o));
-      }
-      o = apply_act(o, a.act, a.slope);
-      if (a.res1) o += __ldg(a.res1 + pe * a.res1_ld + oce);
-      if (a.res2) o += __ldg(a.res2 + pe * a.res2_ld + oce);
-      a.out[pe * a.out_ld + oce] = o;
-    }
-  }
 }
 
 // ---- producer helpers -------------------------------------------------------------------------------------------
@@ -263,8 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* x_buf = smem;                                  // NX stages of [hi plane | lo plane]
   uint8_t* w_buf = smem + C::NX * C::X_STAGE;             // NW weight blocks
-  float* stage_buf = reinterpret_cast<float*>(w_buf + C::NW * C::W_BLOCK);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_buf) + kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_buf + C::NW * C::W_BLOCK);
   // barrier indices
   constexpr int X_FULL = 0, X_EMPTY = X_FULL + C::NX, W_FULL = X_EMPTY + C::NX, W_EMPTY = W_FULL + C::NW,
                 ACC_FULL = W_EMPTY + C::NW, ACC_EMPTY = ACC_FULL + 2, NBARS = ACC_EMPTY + 2;
@@ -301,75 +269,76 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     //   read : thread = (tile column tx, 4 consecutive output channels) -> hi + lo as two float4, GDN / activation /
     //          residuals, one 16-byte store per tile row: 16 lanes cover the 256 contiguous bytes of an NHWC pixel.
     if constexpr (SPLIT == 1) {
-    // ---- 128 output channels per item, one accumulator row per channel: write = TMEM lane quadrant q -> channels
-    //      32q..32q+31 (scaled back by 2^-w_shift, bias added); read = thread (4 channels, tile columns txb and txb+4).
+    // ---- 128 output channels per item, one accumulator row per channel (TMEM lane = channel): every lane stores its own
+    //      channel straight from the registers tcgen05.ld filled - per pixel the 32 lanes of a warp write 128 contiguous
+    //      bytes of the NHWC pixel and the 4 quadrant warps cover its 512 bytes.  No shared-memory transposition.
     const int quad = warp & 3, half = warp >> 2;
-    float* slab = stage_buf + half * (2 * 16 * 128);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int t = quad * 32 + lane;
-    const int c4 = t & 31, txb = t >> 5;
-    const int rd_off = c4 * 4;
     const int Ho = p.Ho, Wo = p.Wo, cout = p.cout, act = p.act, post = p.post;
     const int sh = p.shuffle == 2 ? 2 : 1;
     const int cr = cout >> 2;
     const int oW = Wo * sh, oH = Ho * sh;
     const bool planar = p.out_planar != 0;
-    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    const bool vec_ok = !planar && (p.out_ld & 3) == 0 && al16(p.out) && (sh == 1 || (cr & 3) == 0) &&
-                        (post == TDVC_POST_NONE || ((p.mul_ld & 3) == 0 && al16(p.mul))) &&
-                        (!p.res1 || ((p.res1_ld & 3) == 0 && al16(p.res1))) && (!p.res2 || ((p.res2_ld & 3) == 0 && al16(p.res2)));
     const bool planar_vec = planar && (Wo & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0;
     const float a_neg = act == TDVC_ACT_NONE ? 1.f : (act == TDVC_ACT_LRELU ? p.slope : 0.f);
     const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
     const float unscale = __int_as_float((127 - p.w_shift) << 23);   // 2^-w_shift, exact
     const int o_rs = sh * oW * p.out_ld, m_rs = sh * oW * p.mul_ld, r1_rs = sh * oW * p.res1_ld, r2_rs = sh * oW * p.res2_ld;
-    const int o_p4 = 4 * sh * p.out_ld, m_p4 = 4 * sh * p.mul_ld, r1_p4 = 4 * sh * p.res1_ld, r2_p4 = 4 * sh * p.res2_ld;  // 4 tile columns
+    const int o_xs = sh * p.out_ld, m_xs = sh * p.mul_ld, r1_xs = sh * p.res1_ld, r2_xs = sh * p.res2_ld;
     int acc_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
       const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip);
       const int sa = acc_it & 1;
       mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
       tc_fence_after();
-      float wbias = 0.f;
-      {
-        const int cw = it.jt * C::NTT + t;
-        if (p.bias && cw < cout) wbias = __ldg(p.bias + cw);
-      }
-      const int co = it.jt * C::NTT + 4 * c4;
+      const int co = it.jt * C::NTT + t;
+      const bool ch_ok = co < cout;
+      const float wbias = (p.bias && ch_ok) ? __ldg(p.bias + co) : 0.f;
       int oc = co, qy = 0, qx = 0;
       if (sh == 2) {
-        const int q = co < cout ? co / cr : 0;
+        const int q = ch_ok ? co / cr : 0;
         oc = co - q * cr;
         qy = q >> 1;
         qx = q & 1;
       }
-      const bool c_ok = co < cout;
-      const bool th_vec = vec_ok && co + 4 <= cout;
-      const int ny = Ho - it.y0;
-      const int nxv = Wo - it.x0 - txb;   // column txb valid iff nxv > 0, column txb + 4 iff nxv > 4
-      const int64_t pix0 = ((int64_t)it.n * oH + (it.y0 * sh + qy)) * oW + ((it.x0 + txb) * sh + qx);
-      float* const o0 = p.out + pix0 * p.out_ld + oc;
+      const int ny = Ho - it.y0, nx = Wo - it.x0;   // valid tile rows / columns
+      const int64_t pix0 = ((int64_t)it.n * oH + (it.y0 * sh + qy)) * oW + (it.x0 * sh + qx);
+      float* const o0 = planar ? p.out + (((int64_t)it.n * cout + co) * Ho + it.y0) * Wo + it.x0 : p.out + pix0 * p.out_ld + oc;
       const float* const m0 = post != TDVC_POST_NONE ? p.mul + pix0 * p.mul_ld + oc : nullptr;
       const float* const r10 = p.res1 ? p.res1 + pix0 * p.res1_ld + oc : nullptr;
       const float* const r20 = p.res2 ? p.res2 + pix0 * p.res2_ld + oc : nullptr;
+      const bool side = m0 || r10 || r20;
       uint32_t r[16];
       tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128), r);
-      // residual / GDN-multiplier rows are pulled into L2 two chunks ahead (see the 64-channel epilogue below)
+      // residual / GDN-multiplier rows are pulled into L2 two chunks (4 tile rows) ahead: lane l < 16 covers pixel (row l / 8,
+      // column l % 8) of the chunk - the 128 bytes of this quadrant's 32 channels are one line
       auto l2_prefetch_rows = [&](int tyb) {
-        if (!(th_vec && c_ok)) return;
+        const int ty = tyb + (lane >> 3), k = lane & 7;
+        if (lane < 16 && ty < ny && k < nx && ch_ok) {
+          if (m0) prefetch_l2(m0 + ty * m_rs + k * m_xs);
+          if (r10) prefetch_l2(r10 + ty * r1_rs + k * r1_xs);
+          if (r20) prefetch_l2(r20 + ty * r2_rs + k * r2_xs);
+        }
+      };
+      // first residual of the two rows a lane stores next, held in registers one chunk ahead
+      float ra[16];
+      auto res_load = [&](int tyb) {
+        if (r10 && ch_ok && nx >= 8) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int h2 = k >> 1, g = k & 1;
-          if (tyb + h2 < ny && nxv > 4 * g) {
-            if (m0) prefetch_l2(m0 + (tyb + h2) * m_rs + g * m_p4);
-            if (r10) prefetch_l2(r10 + (tyb + h2) * r1_rs + g * r1_p4);
-            if (r20) prefetch_l2(r20 + (tyb + h2) * r2_rs + g * r2_p4);
+          for (int h2 = 0; h2 < 2; ++h2) {
+            if (tyb + h2 < ny) {
+              const float* rp = r10 + (tyb + h2) * r1_rs;
+#pragma unroll
+              for (int k = 0; k < 8; ++k, rp += r1_xs) ra[h2 * 8 + k] = __ldg(rp);
+            }
           }
         }
       };
-      if (m0 || r10 || r20) {
+      if (side) {
         l2_prefetch_rows(half * 16);
         l2_prefetch_rows(half * 16 + 2);
+        res_load(half * 16);
       }
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
@@ -379,109 +348,119 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           tc_fence_before();
           mbar_arrive(bar(ACC_EMPTY + sa));
         }
-        float* sb = slab + (c & 1) * (16 * 128);
+        float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) sb[j * 128 + t] = fmaf(__uint_as_float(r[j]), unscale, wbias);
+        for (int j = 0; j < 16; ++j) o[j] = fmaf(__uint_as_float(r[j]), unscale, wbias);
         if (c < 7) tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128 + (c + 1) * 16), r);
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-        if (th_vec) {
-          if (!c_ok) continue;
-          if (c < 6 && (m0 || r10 || r20)) l2_prefetch_rows(ty0 + 4);
+        if (!(ch_ok && ty0 < ny)) continue;
+        if (side && c < 6) l2_prefetch_rows(ty0 + 4);
+        if (planar) {  // NCHW planes: the 8 x-adjacent pixels of a tile row are contiguous in this channel's plane
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // (tile row, column group)
-            const int h2 = k >> 1, g = k & 1;
-            const int ty = ty0 + h2;
-            if (ty >= ny || nxv <= 4 * g) continue;
-            const float4 sv = *reinterpret_cast<const float4*>(sb + (h2 * 8 + txb + 4 * g) * 128 + rd_off);
-            float v[4] = {sv.x, sv.y, sv.z, sv.w};
-            if (m0) {
-              const float4 m = __ldg(reinterpret_cast<const float4*>(m0 + ty * m_rs + g * m_p4));
-              if (post == TDVC_POST_IGDN) { v[0] = m.x * sqrtf(v[0]); v[1] = m.y * sqrtf(v[1]); v[2] = m.z * sqrtf(v[2]); v[3] = m.w * sqrtf(v[3]); }
-              else { v[0] = m.x * rsqrtf(v[0]); v[1] = m.y * rsqrtf(v[1]); v[2] = m.z * rsqrtf(v[2]); v[3] = m.w * rsqrtf(v[3]); }
-            }
+          for (int h2 = 0; h2 < 2; ++h2) {
+            if (ty0 + h2 >= ny) continue;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = fminf(fmaxf(v[e], a_neg * v[e]), a_hi);
-            if (r10) {
-              const float4 m = __ldg(reinterpret_cast<const float4*>(r10 + ty * r1_rs + g * r1_p4));
-              v[0] += m.x; v[1] += m.y; v[2] += m.z; v[3] += m.w;
+            for (int k = 0; k < 8; ++k) o[h2 * 8 + k] = fminf(fmaxf(o[h2 * 8 + k], a_neg * o[h2 * 8 + k]), a_hi);
+            float* op = o0 + (int64_t)(ty0 + h2) * Wo;
+            if (planar_vec && nx >= 8) {
+              stg256(op, o + h2 * 8);   // one full 32-byte sector
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (k < nx) op[k] = o[h2 * 8 + k];
             }
-            if (r20) {
-              const float4 m = __ldg(reinterpret_cast<const float4*>(r20 + ty * r2_rs + g * r2_p4));
-              v[0] += m.x; v[1] += m.y; v[2] += m.z; v[3] += m.w;
-            }
-            *reinterpret_cast<float4*>(o0 + ty * o_rs + g * o_p4) = make_float4(v[0], v[1], v[2], v[3]);
           }
-        } else if (planar) {  // NCHW planes: thread = channel; 8 x-adjacent pixels of a tile row are contiguous in the plane
-          const int cp = it.jt * C::NTT + t;
-          if (cp < cout) {
+          continue;
+        }
+        if (nx >= 8) {   // interior tile columns
+          if (m0) {
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
-              const int ty = ty0 + h2;
-              if (ty >= ny) continue;
-              const float* rb = sb + h2 * (8 * 128) + t;
-              float v[8];
+              if (ty0 + h2 >= ny) continue;
+              const float* mp = m0 + (ty0 + h2) * m_rs;
+              float mv[8];
 #pragma unroll
-              for (int x = 0; x < 8; ++x) {
-                const float o = rb[x * 128];
-                v[x] = fminf(fmaxf(o, a_neg * o), a_hi);
-              }
-              float* op = p.out + (((int64_t)it.n * cout + cp) * Ho + (it.y0 + ty)) * Wo + it.x0;
-              if (planar_vec && it.x0 + 8 <= Wo) {
-                stg256(op, v);   // one full 32-byte sector: two 16-byte stores made L2 read the sector back (partial writes)
-              } else {
+              for (int k = 0; k < 8; ++k, mp += m_xs) mv[k] = __ldg(mp);
 #pragma unroll
-                for (int x = 0; x < 8; ++x)
-                  if (it.x0 + x < Wo) op[x] = v[x];
-              }
+              for (int k = 0; k < 8; ++k)
+                o[h2 * 8 + k] = mv[k] * (post == TDVC_POST_IGDN ? sqrtf(o[h2 * 8 + k]) : rsqrtf(o[h2 * 8 + k]));
             }
           }
-        } else if (c_ok) {
-          const RaggedArgs ra{p.out, p.mul, p.res1, p.res2, p.out_ld, p.mul_ld, p.res1_ld, p.res2_ld, post, act, p.shuffle,
-                              cout, Ho, Wo, p.slope};
-          if (nxv > 0) epilogue_ragged(ra, it.n, it.y0, it.x0, sb, txb, rd_off, co, ty0, 0);
-          if (nxv > 4) epilogue_ragged(ra, it.n, it.y0, it.x0, sb, txb + 4, rd_off, co, ty0, 0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = fminf(fmaxf(o[j], a_neg * o[j]), a_hi);
+          if (r10) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] += ra[j];   // (rows past ny are never stored)
+            if (c < 7) res_load(ty0 + 2);
+          }
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            if (ty0 + h2 >= ny) continue;
+            if (r20) {
+              const float* rp = r20 + (ty0 + h2) * r2_rs;
+              float rc[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k, rp += r2_xs) rc[k] = __ldg(rp);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[h2 * 8 + k] += rc[k];
+            }
+            float* op = o0 + (ty0 + h2) * o_rs;
+#pragma unroll
+            for (int k = 0; k < 8; ++k, op += o_xs) *op = o[h2 * 8 + k];
+          }
+        } else {         // ragged right edge (Wo % 8 != 0): one pixel at a time
+#pragma unroll 1
+          for (int j = 0; j < 16; ++j) {
+            const int ty = ty0 + (j >> 3), k = j & 7;
+            if (ty >= ny || k >= nx) continue;
+            float v = o[0];
+#pragma unroll
+            for (int q = 1; q < 16; ++q) v = (j == q) ? o[q] : v;
+            if (m0) {
+              const float mvk = __ldg(m0 + ty * m_rs + k * m_xs);
+              v = mvk * (post == TDVC_POST_IGDN ? sqrtf(v) : rsqrtf(v));
+            }
+            v = fminf(fmaxf(v, a_neg * v), a_hi);
+            if (r10) v += __ldg(r10 + ty * r1_rs + k * r1_xs);
+            if (r20) v += __ldg(r20 + ty * r2_rs + k * r2_xs);
+            o0[ty * o_rs + k * o_xs] = v;
+          }
         }
       }
     }
     } else {
+    // ---- 64 output channels per item, rows [hi | lo * 2^12].  Row order (pack_f16_kernel): TMEM lane quadrant q holds channels
+    //      16q..16q+15, hi rows in lanes 0-15 and the matching lo rows in lanes 16-31, so the two terms of a channel sit in
+    //      ONE warp and are merged with a lane-xor-16 shuffle - no shared-memory transposition, no barrier.  After the merge
+    //      lanes 0-15 own the chunk's first tile row (8 pixels) and lanes 16-31 the second: per pixel the 16 lanes write 64
+    //      contiguous bytes (two full sectors) of the NHWC pixel, and the 4 quadrant warps cover its 256 bytes.
     const int quad = warp & 3, half = warp >> 2;
-    const bool is_lo = (quad & 1) != 0;
-    float* slab = stage_buf + half * (2 * 16 * 128);
+    const int part = lane >> 4, cl = lane & 15;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int t = quad * 32 + lane;             // thread index within the half (= its TMEM lane = slab row)
-    const int c4 = t & 15, tx = t >> 4;         // read phase: channels 4*c4..+3 of the item's 64, tile column tx
-    const int rd_off = (c4 >> 3) * 64 + (c4 & 7) * 4;   // hi float4 of those channels inside a slab pixel; lo at +32
     const int Ho = p.Ho, Wo = p.Wo, cout = p.cout, act = p.act, post = p.post;
     const int sh = p.shuffle == 2 ? 2 : 1;
     const int cr = cout >> 2;
     const int oW = Wo * sh, oH = Ho * sh;
     const bool planar = p.out_planar != 0;
-    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    const bool vec_ok = !planar && (p.out_ld & 3) == 0 && al16(p.out) && (sh == 1 || (cr & 3) == 0) &&
-                        (post == TDVC_POST_NONE || ((p.mul_ld & 3) == 0 && al16(p.mul))) &&
-                        (!p.res1 || ((p.res1_ld & 3) == 0 && al16(p.res1))) && (!p.res2 || ((p.res2_ld & 3) == 0 && al16(p.res2)));
     const bool planar_vec = planar && (Wo & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0;
     // a plain store may also fill the pad lanes of a channel-padded view (weight rows >= cout are zero, no bias there)
-    const int cout_st = (sh == 1 && post == TDVC_POST_NONE && !p.res1 && !p.res2 && p.out_ld >= ((cout + 3) & ~3)) ? ((cout + 3) & ~3) : cout;
+    const int cout_st = (!planar && sh == 1 && post == TDVC_POST_NONE && !p.res1 && !p.res2 && p.out_ld >= ((cout + 3) & ~3)) ? ((cout + 3) & ~3) : cout;
     // branch-free activation: a(v) = min(max(v, a_neg * v), a_hi)   (0 <= a_neg <= 1)
     const float a_neg = act == TDVC_ACT_NONE ? 1.f : (act == TDVC_ACT_LRELU ? p.slope : 0.f);
     const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
-    // element strides of one tile row in out / mul / res1 / res2 (all address the same logical pixel)
+    const float rscale = part ? kLoUnscale : 1.f;   // lo rows carry w_lo * 2^12
+    // element strides of one tile row / one tile column in out / mul / res1 / res2 (all address the same logical pixel)
     const int o_rs = sh * oW * p.out_ld, m_rs = sh * oW * p.mul_ld, r1_rs = sh * oW * p.res1_ld, r2_rs = sh * oW * p.res2_ld;
+    const int o_xs = sh * p.out_ld, m_xs = sh * p.mul_ld, r1_xs = sh * p.res1_ld, r2_xs = sh * p.res2_ld;
     int acc_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
       const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip);
       const int sa = acc_it & 1;
       mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
       tc_fence_after();
-      // write phase: bias of this lane's weight row (lo rows only)
-      float wbias = 0.f;
-      if (is_lo && p.bias) {
-        const int cw = it.jt * NT + (quad >> 1) * 32 + lane;
-        if (cw < cout) wbias = __ldg(p.bias + cw);
-      }
-      // read phase: where this thread's 4 channels land (PixelShuffle(2) folded into the store: co' = q*(cout/4) + c)
-      const int co = it.jt * NT + 4 * c4;
+      const int co = it.jt * NT + quad * 16 + cl;   // this lane's output channel (same for its hi and lo lane)
+      float wbias = 0.f;                           // added once, on the lo row
+      if (part && p.bias && co < cout) wbias = __ldg(p.bias + co);
+      // where the channel lands (PixelShuffle(2) folded into the store: co' = q*(cout/4) + c)
       int oc = co, qy = 0, qx = 0;
       if (sh == 2) {
         const int q = co < cout ? co / cr : 0;
@@ -489,115 +468,133 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         qy = q >> 1;
         qx = q & 1;
       }
-      const bool th_ok = it.x0 + tx < Wo && co < cout;
-      const bool th_vec = vec_ok && co + 4 <= cout_st;
-      const int ny = Ho - it.y0;  // valid tile rows
-      const int64_t pix0 = ((int64_t)it.n * oH + (it.y0 * sh + qy)) * oW + ((it.x0 + tx) * sh + qx);
-      float* const o0 = p.out + pix0 * p.out_ld + oc;
+      const bool ch_ok = co < cout_st;
+      const int ny = Ho - it.y0, nx = Wo - it.x0;   // valid tile rows / columns
+      const int64_t pix0 = ((int64_t)it.n * oH + (it.y0 * sh + qy)) * oW + (it.x0 * sh + qx);
+      float* const o0 = planar ? p.out + (((int64_t)it.n * cout + co) * Ho + it.y0) * Wo + it.x0 : p.out + pix0 * p.out_ld + oc;
       const float* const m0 = post != TDVC_POST_NONE ? p.mul + pix0 * p.mul_ld + oc : nullptr;
       const float* const r10 = p.res1 ? p.res1 + pix0 * p.res1_ld + oc : nullptr;
       const float* const r20 = p.res2 ? p.res2 + pix0 * p.res2_ld + oc : nullptr;
+      const bool side = m0 || r10 || r20;
       uint32_t r[16];
       tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128), r);
-      // residual (res1) and GDN-multiplier rows: their DRAM latency (~1.5 us under load) is longer than the slab exchange of
-      // a chunk, so they are pulled into L2 two chunks (4 tile rows) ahead with prefetch.global.L2 - no registers held
-      // (holding them in registers one chunk ahead spilled at the 96-register cap and slowed every variant)
-      auto l2_prefetch_rows = [&](int tyb) {
-        if (!(th_vec && th_ok)) return;
+      // residual and GDN-multiplier rows: their DRAM latency (~1.5 us under load) is longer than a chunk, so they are pulled
+      // into L2 two chunks (4 tile rows) ahead with prefetch.global.L2 - no registers held.  Lane cl < 8 covers tile column
+      // cl of its part's row: the 64 bytes of this quadrant's 16 channels lie in one 128-byte line.
+      auto l2_prefetch_row = [&](int ty) {
+        if (cl < 8 && cl < nx && ty < ny && ch_ok) {
+          if (m0) prefetch_l2(m0 + ty * m_rs + cl * m_xs);
+          if (r10) prefetch_l2(r10 + ty * r1_rs + cl * r1_xs);
+          if (r20) prefetch_l2(r20 + ty * r2_rs + cl * r2_xs);
+        }
+      };
+      // GDN multiplier and first residual of the row a lane stores next, held in registers one chunk ahead
+      float mv[8], ra[8];
+      auto side_load = [&](int ty) {
+        if (ch_ok && ty < ny && nx >= 8) {
+          if (m0) {
+            const float* mp = m0 + ty * m_rs;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (tyb + q < ny) {
-            if (m0) prefetch_l2(m0 + (tyb + q) * m_rs);
-            if (r10) prefetch_l2(r10 + (tyb + q) * r1_rs);
-            if (r20) prefetch_l2(r20 + (tyb + q) * r2_rs);
+            for (int k = 0; k < 8; ++k, mp += m_xs) mv[k] = __ldg(mp);
+          }
+          if (r10) {
+            const float* rp = r10 + ty * r1_rs;
+#pragma unroll
+            for (int k = 0; k < 8; ++k, rp += r1_xs) ra[k] = __ldg(rp);
           }
         }
       };
-      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 || r10 || r20) {
-        l2_prefetch_rows(half * 16);
-        l2_prefetch_rows(half * 16 + 2);
+      if (side) {
+        l2_prefetch_row(half * 16 + part);
+        l2_prefetch_row(half * 16 + 2 + part);
+        side_load(half * 16 + part);
       }
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
-        const int ty0 = half * 16 + c * 2;
-        float4 ma = z4, mb = z4, ra = z4, rbv = z4, rc = z4, rd = z4;
-        const bool row0 = th_vec && th_ok && ty0 < ny, row1 = row0 && ty0 + 1 < ny;
+        const int ty = half * 16 + c * 2 + part;
         tmem_ld_wait();
         if (c == 7) {  // all TMEM reads of this warp are done: the accumulator stage may be overwritten
           tc_fence_before();
           mbar_arrive(bar(ACC_EMPTY + sa));
         }
-        float* sb = slab + (c & 1) * (16 * 128);
-        if (is_lo) {
+        // merge: lane (part 0) keeps columns 0-7 and receives their lo terms; lane (part 1) keeps columns 8-15 and receives
+        // their hi terms.  a + b is commutative, so both orders give the same bits as hi + lo.
+        float o[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sb[j * 128 + t] = fmaf(__uint_as_float(r[j]), kLoUnscale, wbias);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) sb[j * 128 + t] = __uint_as_float(r[j]);
+        for (int k = 0; k < 8; ++k) {
+          const float va = fmaf(__uint_as_float(r[k]), rscale, wbias), vb = fmaf(__uint_as_float(r[8 + k]), rscale, wbias);
+          const float got = __shfl_xor_sync(0xffffffffu, part ? va : vb, 16);
+          o[k] = (part ? vb : va) + got;
         }
-        // next chunk's accumulator columns: the TMEM read overlaps the barrier and the read phase below
+        // next chunk's accumulator columns: the TMEM read overlaps the loads / stores below
         if (c < 7) tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128 + (c + 1) * 16), r);
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-        if (th_vec) {
-          if (!row0) continue;
-          const bool two = row1;
-          if (c < 6 && (m0 || r10 || r20)) l2_prefetch_rows(ty0 + 4);
-          if (m0) { ma = __ldg(reinterpret_cast<const float4*>(m0 + ty0 * m_rs)); if (two) mb = __ldg(reinterpret_cast<const float4*>(m0 + (ty0 + 1) * m_rs)); }
-          if (r10) { ra = __ldg(reinterpret_cast<const float4*>(r10 + ty0 * r1_rs)); if (two) rbv = __ldg(reinterpret_cast<const float4*>(r10 + (ty0 + 1) * r1_rs)); }
-          if (r20) { rc = __ldg(reinterpret_cast<const float4*>(r20 + ty0 * r2_rs)); if (two) rd = __ldg(reinterpret_cast<const float4*>(r20 + (ty0 + 1) * r2_rs)); }
-          const float* rb = sb + tx * 128 + rd_off;
-          const float4 h0 = *reinterpret_cast<const float4*>(rb), l0 = *reinterpret_cast<const float4*>(rb + 32);
-          const float4 h1 = *reinterpret_cast<const float4*>(rb + 8 * 128), l1 = *reinterpret_cast<const float4*>(rb + 8 * 128 + 32);
-          float4 v0 = make_float4(h0.x + l0.x, h0.y + l0.y, h0.z + l0.z, h0.w + l0.w);
-          float4 v1 = make_float4(h1.x + l1.x, h1.y + l1.y, h1.z + l1.z, h1.w + l1.w);
-          if (m0) {  // GDN / IGDN: v = mul * rsqrt(v) | mul * sqrt(v)
-            if (post == TDVC_POST_IGDN) {
-              v0 = make_float4(ma.x * sqrtf(v0.x), ma.y * sqrtf(v0.y), ma.z * sqrtf(v0.z), ma.w * sqrtf(v0.w));
-              v1 = make_float4(mb.x * sqrtf(v1.x), mb.y * sqrtf(v1.y), mb.z * sqrtf(v1.z), mb.w * sqrtf(v1.w));
-            } else {
-              v0 = make_float4(ma.x * rsqrtf(v0.x), ma.y * rsqrtf(v0.y), ma.z * rsqrtf(v0.z), ma.w * rsqrtf(v0.w));
-              v1 = make_float4(mb.x * rsqrtf(v1.x), mb.y * rsqrtf(v1.y), mb.z * rsqrtf(v1.z), mb.w * rsqrtf(v1.w));
-            }
-          }
-          // activation a(v) = min(max(v, a_neg * v), a_hi): identity (a_neg 1), ReLU (0), LeakyReLU (slope), clamp01
-          v0.x = fminf(fmaxf(v0.x, a_neg * v0.x), a_hi) + (ra.x + rc.x);
-          v0.y = fminf(fmaxf(v0.y, a_neg * v0.y), a_hi) + (ra.y + rc.y);
-          v0.z = fminf(fmaxf(v0.z, a_neg * v0.z), a_hi) + (ra.z + rc.z);
-          v0.w = fminf(fmaxf(v0.w, a_neg * v0.w), a_hi) + (ra.w + rc.w);
-          *reinterpret_cast<float4*>(o0 + ty0 * o_rs) = v0;
-          if (two) {
-            v1.x = fminf(fmaxf(v1.x, a_neg * v1.x), a_hi) + (rbv.x + rd.x);
-            v1.y = fminf(fmaxf(v1.y, a_neg * v1.y), a_hi) + (rbv.y + rd.y);
-            v1.z = fminf(fmaxf(v1.z, a_neg * v1.z), a_hi) + (rbv.z + rd.z);
-            v1.w = fminf(fmaxf(v1.w, a_neg * v1.w), a_hi) + (rbv.w + rd.w);
-            *reinterpret_cast<float4*>(o0 + (ty0 + 1) * o_rs) = v1;
-          }
-        } else if (planar) {  // NCHW planes: thread = (channel, tile row); 8 x-adjacent pixels are contiguous in the plane
-          const int ch = t & 63, h2 = t >> 6;
-          const int ty = ty0 + h2;
-          const int cp = it.jt * NT + ch;
-          if (cp < cout && ty < ny) {
-            const float* rb = sb + h2 * (8 * 128) + (ch >> 5) * 64 + (ch & 31);
-            float v[8];
+        if (!(ch_ok && ty < ny)) continue;
+        if (side && c < 6) l2_prefetch_row(ty + 4);
+        if (planar) {  // NCHW planes: the 8 x-adjacent pixels of the tile row are contiguous in this channel's plane
+          if (co < cout) {
 #pragma unroll
-            for (int x = 0; x < 8; ++x) {
-              const float o = rb[x * 128] + rb[x * 128 + 32];
-              v[x] = fminf(fmaxf(o, a_neg * o), a_hi);
-            }
-            float* op = p.out + (((int64_t)it.n * cout + cp) * Ho + (it.y0 + ty)) * Wo + it.x0;
-            if (planar_vec && it.x0 + 8 <= Wo) {
-              stg256(op, v);   // one full 32-byte sector: two 16-byte stores made L2 read the sector back (partial writes)
+            for (int k = 0; k < 8; ++k) o[k] = fminf(fmaxf(o[k], a_neg * o[k]), a_hi);
+            float* op = o0 + (int64_t)ty * Wo;
+            if (planar_vec && nx >= 8) {
+              stg256(op, o);   // one full 32-byte sector
             } else {
 #pragma unroll
-              for (int x = 0; x < 8; ++x)
-                if (it.x0 + x < Wo) op[x] = v[x];
+              for (int k = 0; k < 8; ++k)
+                if (k < nx) op[k] = o[k];
             }
           }
-        } else if (th_ok) {
-          epilogue_ragged(RaggedArgs{p.out, p.mul, p.res1, p.res2, p.out_ld, p.mul_ld, p.res1_ld, p.res2_ld, post, act, p.shuffle,
-                                     cout, Ho, Wo, p.slope},
-                          it.n, it.y0, it.x0, sb, tx, rd_off, co, ty0, 32);
+          continue;
+        }
+        float* op = o0 + ty * o_rs;
+        if (nx >= 8) {   // interior tile columns: no per-pixel predicates, running pointers
+          if (side) {
+            if (m0) {  // GDN / IGDN: v = mul * rsqrt(v) | mul * sqrt(v)
+              if (post == TDVC_POST_IGDN) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = mv[k] * sqrtf(o[k]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = mv[k] * rsqrtf(o[k]);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fminf(fmaxf(o[k], a_neg * o[k]), a_hi);
+            if (r10) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] += ra[k];
+            }
+            if (c < 7) side_load(ty + 2);   // next chunk's multiplier / residual values: in flight across the stores,
+                                            // the TMEM wait and the merge of the next iteration
+            if (r20) {
+              const float* rp = r20 + ty * r2_rs;
+              float rc[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k, rp += r2_xs) rc[k] = __ldg(rp);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] += rc[k];
+            }
+          } else {
+            // activation a(v) = min(max(v, a_neg * v), a_hi): identity (a_neg 1), ReLU (0), LeakyReLU (slope), clamp01
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fminf(fmaxf(o[k], a_neg * o[k]), a_hi);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k, op += o_xs) *op = o[k];
+        } else {         // ragged right edge (Wo % 8 != 0): one pixel at a time
+#pragma unroll 1
+          for (int k = 0; k < nx; ++k) {
+            float v = o[0];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) v = (k == q) ? o[q] : v;
+            if (m0) {
+              const float mvk = __ldg(m0 + ty * m_rs + k * m_xs);
+              v = mvk * (post == TDVC_POST_IGDN ? sqrtf(v) : rsqrtf(v));
+            }
+            v = fminf(fmaxf(v, a_neg * v), a_hi);
+            if (r10) v += __ldg(r10 + ty * r1_rs + k * r1_xs);
+            if (r20) v += __ldg(r20 + ty * r2_rs + k * r2_xs);
+            op[k * o_xs] = v;
+          }
         }
       }
     }
@@ -766,7 +763,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 
 // fp32 packed weights [T][cin_pad][cout_pad] -> per (cout tile of 64, unit, tap) fp16 block [128 rows][CK] in the
 // canonical K-major no-swizzle layout [(row/8)][(k/8)][row%8][k%8].  Row order = TMEM lane order of the accumulator:
-// rows 0-31 hi of channels 0-31, rows 32-63 lo * 2^12 of channels 0-31, rows 64-95 hi of 32-63, rows 96-127 lo of 32-63.
+// lane quadrant q (rows 32q..32q+31) = channels 16q..16q+15: rows 32q+0..15 their hi terms, rows 32q+16..31 their lo * 2^12.
 // split = 1: per (cout tile of 128, unit, tap) two such blocks, W_hi then W_lo, row = channel, both scaled by 2^w_shift.
 __global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict__ out, int T, int cin, int cin_pad,
                                  int cout, int cout_pad, int CK, int n_units, int n_jt, int split, float scale) {
@@ -786,8 +783,8 @@ __global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict_
     const int row = ng * 8 + n8, k = kc * 8 + k8;
     const int quad = row >> 5;
     const int ci = u * CK + k;
-    const int co = split ? jt * 128 + row : jt * NT + (quad >> 1) * 32 + (row & 31);
-    const bool lo = split ? which == 1 : (quad & 1) != 0;
+    const int co = split ? jt * 128 + row : jt * NT + quad * 16 + (row & 15);
+    const bool lo = split ? which == 1 : (row & 16) != 0;
     float v = 0.f;
     if (ci < cin_pad && co < cout_pad && ci < cin && co < cout) v = w[((int64_t)tap * cin_pad + ci) * cout_pad + co] * scale;
     v = fminf(fmaxf(v, -65504.f), 65504.f);
