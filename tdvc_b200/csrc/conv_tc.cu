@@ -321,16 +321,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           if (r20) prefetch_l2(r20 + ty * r2_rs + k * r2_xs);
         }
       };
-      // first residual of the two rows a lane stores next, held in registers one chunk ahead
+      // GDN multiplier (or, without one, the first residual) of the two rows a lane stores next, held in registers one
+      // chunk ahead
+      const float* const pf0 = m0 ? m0 : r10;
+      const int pf_rs = m0 ? m_rs : r1_rs, pf_xs = m0 ? m_xs : r1_xs;
       float ra[16];
       auto res_load = [&](int tyb) {
-        if (r10 && ch_ok && nx >= 8) {
+        if (pf0 && ch_ok && nx >= 8) {
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             if (tyb + h2 < ny) {
-              const float* rp = r10 + (tyb + h2) * r1_rs;
+              const float* rp = pf0 + (tyb + h2) * pf_rs;
 #pragma unroll
-              for (int k = 0; k < 8; ++k, rp += r1_xs) ra[h2 * 8 + k] = __ldg(rp);
+              for (int k = 0; k < 8; ++k, rp += pf_xs) ra[h2 * 8 + k] = __ldg(rp);
             }
           }
         }
@@ -372,26 +375,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           continue;
         }
         if (nx >= 8) {   // interior tile columns
-          if (m0) {
+          if (m0) {   // GDN / IGDN: v = mul * rsqrt(v) | mul * sqrt(v)   (rows past ny are never stored)
+            if (post == TDVC_POST_IGDN) {
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              if (ty0 + h2 >= ny) continue;
-              const float* mp = m0 + (ty0 + h2) * m_rs;
-              float mv[8];
+              for (int j = 0; j < 16; ++j) o[j] = ra[j] * sqrtf(o[j]);
+            } else {
 #pragma unroll
-              for (int k = 0; k < 8; ++k, mp += m_xs) mv[k] = __ldg(mp);
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                o[h2 * 8 + k] = mv[k] * (post == TDVC_POST_IGDN ? sqrtf(o[h2 * 8 + k]) : rsqrtf(o[h2 * 8 + k]));
+              for (int j = 0; j < 16; ++j) o[j] = ra[j] * rsqrtf(o[j]);
             }
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = fminf(fmaxf(o[j], a_neg * o[j]), a_hi);
           if (r10) {
+            if (m0) {   // multiplier and residual together: the residual is loaded in place
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] += ra[j];   // (rows past ny are never stored)
-            if (c < 7) res_load(ty0 + 2);
+              for (int h2 = 0; h2 < 2; ++h2) {
+                if (ty0 + h2 >= ny) continue;
+                const float* rp = r10 + (ty0 + h2) * r1_rs;
+                float rc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k, rp += r1_xs) rc[k] = __ldg(rp);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[h2 * 8 + k] += rc[k];
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] += ra[j];
+            }
           }
+          if (pf0 && c < 7) res_load(ty0 + 2);
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             if (ty0 + h2 >= ny) continue;
@@ -802,9 +814,9 @@ struct Choice {
 // with >= 96 output channels (a multiple of 4), in tiles of 128 with the 3-product split scheme.
 static bool choose(const TdvcConvParams& p, Choice* c) {
   if (p.kh != p.kw || p.pad != p.kh / 2 || p.cin < 4 || p.cout < 1) return false;
-  // 1x1 layers stay on 64-channel tiles: 128-channel split tiles were measured slower for them (GDN 128->128 @512x960:
-  // 0.35 -> 0.48 ms) - they are bound by the epilogue's latency chain, and the smaller tiles give twice as many items
-  const int split = (p.cout >= 96 && (p.cout & 3) == 0 && p.kh != 7 && p.kh != 1) ? 1 : 0;
+  // (1x1 layers included: with the slab epilogue they were faster on 64-channel tiles, with the direct epilogue the
+  // 128-channel tiles win - GDN 128->128 @512x960 0.230 -> 0.179 ms, 1x1 + residual 0.219 -> 0.135 ms)
+  const int split = (p.cout >= 96 && (p.cout & 3) == 0 && p.kh != 7) ? 1 : 0;
   if (p.stride == 2) {
     if (p.kh == 3) { *c = {3, 16, 2, split}; return true; }
     if (p.kh == 1) { *c = {1, 32, 2, split}; return p.cin >= 32; }
