@@ -88,32 +88,36 @@ __global__ void spynet_prep_kernel(const float* __restrict__ ref4, const float* 
   }
 }
 
-// nn.Upsample(scale_factor=2, bilinear, align_corners=False): src = 0.5*(dst+0.5)-0.5 clamped at 0
+// nn.Upsample(scale_factor=2, bilinear, align_corners=False): src = 0.5*(dst+0.5)-0.5 clamped at 0.
+// One block row per output row (blockIdx.y = n*Ho + y): the row's source rows and vertical weights are block constants and
+// the index arithmetic is 32-bit; consecutive threads write consecutive float4 of the output row.
 __global__ void upsample2x_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int H, int W, int C4) {
   const int Ho = 2 * H, Wo = 2 * W;
-  const int64_t total = (int64_t)N * Ho * Wo * C4;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int c = (int)(i % C4);
-    int64_t r = i / C4;
-    const int x = (int)(r % Wo); r /= Wo;
-    const int y = (int)(r % Ho);
-    const int n = (int)(r / Ho);
-    float sy = 0.5f * ((float)y + 0.5f) - 0.5f, sx = 0.5f * ((float)x + 0.5f) - 0.5f;
-    sy = sy < 0.f ? 0.f : sy; sx = sx < 0.f ? 0.f : sx;
-    const int y1 = (int)sy, x1 = (int)sx;
-    const int yp = y1 < H - 1 ? 1 : 0, xp = x1 < W - 1 ? 1 : 0;
-    const float ly = sy - (float)y1, lx = sx - (float)x1;
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const float4* s = reinterpret_cast<const float4*>(src) + (((int64_t)n * H + y1) * W + x1) * C4 + c;
-    const float4 a = __ldg(s), b = __ldg(s + (int64_t)xp * C4), d = __ldg(s + (int64_t)yp * W * C4),
-                 e = __ldg(s + ((int64_t)yp * W + xp) * C4);
+  const int y = blockIdx.y % Ho, n = blockIdx.y / Ho;
+  float sy = 0.5f * ((float)y + 0.5f) - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  const int y1 = (int)sy;
+  const int yp = y1 < H - 1 ? 1 : 0;
+  const float ly = sy - (float)y1, hy = 1.f - ly;
+  const float4* s0 = reinterpret_cast<const float4*>(src) + ((int64_t)n * H + y1) * W * C4;
+  const float4* s1 = s0 + (int64_t)yp * W * C4;
+  float4* drow = reinterpret_cast<float4*>(dst) + ((int64_t)n * Ho + y) * Wo * C4;
+  const int row = Wo * C4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row; i += gridDim.x * blockDim.x) {
+    const int x = i / C4, c = i - x * C4;
+    float sx = 0.5f * ((float)x + 0.5f) - 0.5f;
+    sx = sx < 0.f ? 0.f : sx;
+    const int x1 = (int)sx;
+    const int xp = x1 < W - 1 ? C4 : 0;
+    const float lx = sx - (float)x1, hx = 1.f - lx;
+    const int o0 = x1 * C4 + c;
+    const float4 a = __ldg(s0 + o0), b = __ldg(s0 + o0 + xp), d = __ldg(s1 + o0), e = __ldg(s1 + o0 + xp);
     float4 o;
     o.x = hy * (hx * a.x + lx * b.x) + ly * (hx * d.x + lx * e.x);
     o.y = hy * (hx * a.y + lx * b.y) + ly * (hx * d.y + lx * e.y);
     o.z = hy * (hx * a.z + lx * b.z) + ly * (hx * d.z + lx * e.z);
     o.w = hy * (hx * a.w + lx * b.w) + ly * (hx * d.w + lx * e.w);
-    reinterpret_cast<float4*>(dst)[i] = o;
+    drow[i] = o;
   }
 }
 
@@ -158,7 +162,10 @@ extern "C" int tdvc_spynet_prep(const float* ref4, const float* supp4, const flo
 
 extern "C" int tdvc_upsample2x(const float* src, float* dst, int N, int H, int W, int C, void* stream) {
   TDVC_REQUIRE(src && dst && N > 0 && H > 0 && W > 0 && C % 4 == 0, "upsample2x: bad args");
-  upsample2x_kernel<<<grid_for((int64_t)N * 4 * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(src, dst, N, H, W, C / 4);
+  TDVC_REQUIRE((int64_t)N * 2 * H <= 65535 && (int64_t)2 * W * (C / 4) < (1ll << 30), "upsample2x: image too large");
+  const int row = 2 * W * (C / 4);
+  dim3 grid((row + 255) / 256 > 8 ? 8 : (row + 255) / 256, N * 2 * H);
+  upsample2x_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, N, H, W, C / 4);
   TDVC_CHECK_LAUNCH("upsample2x");
   return TDVC_OK;
 }

@@ -613,10 +613,13 @@ class _Plan:
         L.check(self.lib.tdvc_conv2d(p, self._st()), "conv2d")
         if e0 is not None:
             npx = s0.N * p.Ho * p.Wo
-            self._prof_end(e0, f"conv{cw.k}x{cw.k}s{stride}_{cw.cin}to{cw.cout}@{p.Ho}x{p.Wo}",
+            gdn = post != L.POST_NONE and mul is not None and mul.ptr == s0.ptr   # x is both the conv input and the multiplier
+            name = ("gdn" if post == L.POST_GDN else "igdn") if gdn else f"conv{cw.k}x{cw.k}s{stride}"
+            # algorithmic bytes: inputs + output (+ multiplier / residual rows); a GDN reads x once (1,024 B/px)
+            self._prof_end(e0, f"{name}_{cw.cin}to{cw.cout}@{p.Ho}x{p.Wo}",
                            macs=npx * cw.cout * cw.cin_real * cw.k * cw.k,
                            nbytes=4 * (s0.N * s0.H * s0.W * cw.cin_real +
-                                       npx * cw.cout * (1 + (mul is not None) + (res1 is not None) + (res2 is not None))))
+                                       npx * cw.cout * (1 + (mul is not None and not gdn) + (res1 is not None) + (res2 is not None))))
         self.launches += 1
         return out
 
@@ -627,20 +630,20 @@ class _Plan:
         part = self.raw(("se_part", x.C), (nblk * x.N * x.C,))
         e0 = self._prof_begin()
         L.check(self.lib.tdvc_se_partial_sums(x.ptr, x.ld, x.N, HW, x.C, part.data_ptr(), nblk, self._st()), "se_partial_sums")
-        self._prof_end(e0, "se_partial_sums", 0, 4 * x.N * HW * x.C)
+        self._prof_end(e0, f"se_partial_sums_{x.C}ch@{x.H}x{x.W}", 0, 4 * x.N * HW * x.C)
         e0 = self._prof_begin()
         L.check(self.lib.tdvc_se_apply(x.ptr, x.ld, part.data_ptr(), nblk, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
                                        b2.data_ptr(), x.N, HW, x.C, w1.shape[0], act, slope,
                                        res.ptr if res is not None else None, res.ld if res is not None else 0,
                                        out.ptr, out.ld, self._st()), "se_apply")
-        self._prof_end(e0, "se_apply", 0, 4 * x.N * HW * x.C * (3 if res is not None else 2))
+        self._prof_end(e0, f"se_apply_{x.C}ch@{x.H}x{x.W}", 0, 4 * x.N * HW * x.C * (3 if res is not None else 2))
         self.launches += 3   # partial sums, gate (one block per image), apply
         return out
 
-    def call(self, fn, *a, nbytes=0):
+    def call(self, fn, *a, nbytes=0, tag=""):
         e0 = self._prof_begin()
         L.check(getattr(self.lib, fn)(*a, self._st()), fn)
-        self._prof_end(e0, fn[5:], 0, nbytes)
+        self._prof_end(e0, fn[5:] + tag, 0, nbytes)
         self.launches += 1
 
     # ---------------------------------------------------------------- blocks
@@ -884,7 +887,7 @@ class _Plan:
                 off = self.conv([up, o1], W[f"me.ff.{lv}"], b(f"off.{lv}", N, h, w), **lr1)
             if i > 1:
                 u = b(f"up2x.{lv}", N, 2 * h, 2 * w)
-                self.call("tdvc_upsample2x", off.ptr, u.ptr, N, h, w, 64, nbytes=1280 * N * h * w)  # read 256 + write 4 * 256 B/px
+                self.call("tdvc_upsample2x", off.ptr, u.ptr, N, h, w, 64, nbytes=1280 * N * h * w, tag=f"@{h}x{w}")  # read 256 + write 4 * 256 B/px
                 up = self.conv([u], W["me.upsample_conv"], b(f"up.{lv}", N, 2 * h, 2 * w))
             if taps is not None:
                 taps[f"motion_est.offset_{lv}"] = off.nchw()
@@ -902,7 +905,7 @@ class _Plan:
         for l in range(5):
             s = pyr[-1]
             d = self.buf(f"spy.pyr{l}", 2 * N, s.H // 2, s.W // 2, 3, ld=4)
-            self.call("tdvc_avgpool2x2", s.ptr, d.ptr, 2 * N, s.H, s.W, 4, nbytes=20 * 2 * N * s.H * s.W)
+            self.call("tdvc_avgpool2x2", s.ptr, d.ptr, 2 * N, s.H, s.W, 4, nbytes=20 * 2 * N * s.H * s.W, tag=f"@{s.H}x{s.W}")
             pyr.append(d)
         pyr = pyr[::-1]
         flow = None
@@ -911,7 +914,7 @@ class _Plan:
             h, w = im.H, im.W
             x8 = self.buf(f"spy.in{lvl}", N, h, w, 8)
             self.call("tdvc_spynet_prep", im.batch(0, N).ptr, im.batch(N, N).ptr, flow.ptr if flow is not None else None,
-                      x8.ptr, N, h, w, nbytes=N * h * w * 66)  # ref 16 + supp 16 + coarse flow 2 + out 32 B/px
+                      x8.ptr, N, h, w, nbytes=N * h * w * 66, tag=f"@{h}x{w}")  # ref 16 + supp 16 + coarse flow 2 + out 32 B/px
             t = self.conv([x8], W[f"spy.{lvl}.0"], self.buf(f"spy.a{lvl}", N, h, w, 32), act=L.ACT_RELU)
             t = self.conv([t], W[f"spy.{lvl}.1"], self.buf(f"spy.b{lvl}", N, h, w, 64), act=L.ACT_RELU)
             t = self.conv([t], W[f"spy.{lvl}.2"], self.buf(f"spy.c{lvl}", N, h, w, 32), act=L.ACT_RELU)
