@@ -57,14 +57,23 @@ constexpr int NT = 64;                         // output channels per item (M = 
 // SPLIT = 1: item = 128 output channels, separate W_hi / W_lo blocks (pre-scaled by 2^w_shift so that W_lo stays in
 //            the fp16 normal range) accumulating into ONE row per channel: x_hi*w_hi + x_lo*w_hi + x_hi*w_lo,
 //            3 MMAs per k-step for twice the channels (-25 % tensor work) and no hi/lo merge in the epilogue.
-template <int KS, int CK, int S, int SPLIT = 0>
+// NPH > 1 ("row phases", for layers with <= 64 / NPH output channels, 7x7 only): an item is 8 x 32*NPH output pixels; the
+//            MMA's 256 N columns are the pixels of every NPH-th row (row-group pitch = NPH halo rows) and the 64
+//            (hi, lo) row pairs of the M side are 64 / NPH channels x NPH row phases: the rows of phase f hold the
+//            kernel shifted down by f rows (tap (ky', kx) -> W[ky' - f][kx], zero outside), so one pass over KS + NPH - 1
+//            kernel rows produces NPH output rows per N column.  A 32-channel 7x7 layer then needs 8 x 7 MMA taps per
+//            512 pixels instead of 7 x 7 per 256 with half of the M rows idle.
+template <int KS, int CK, int S, int SPLIT = 0, int NPH = 1>
 struct Cfg {
   static_assert(S == 1 || (S == 2 && (KS == 1 || KS == 3)), "stride");
+  static_assert(NPH == 1 || (KS == 7 && S == 1 && SPLIT == 0 && (NPH == 2 || NPH == 4)), "row phases");
+  static constexpr int THO = TH * NPH;                       // output rows of an item
+  static constexpr int KY = KS + NPH - 1;                    // kernel rows walked by the MMA loop
   static_assert(CK == 16 || CK == 32, "cin chunk");
   static constexpr int PAD = KS / 2;
   // input halo of one 8x32 output tile: IH x IW input pixels, input pixel = origin + h*STEP
   static constexpr int STEP = (KS == 1) ? S : 1;            // 1x1: only every S-th input pixel is touched
-  static constexpr int IH = (KS == 1) ? TH : (TH - 1) * S + KS;
+  static constexpr int IH = (KS == 1) ? TH : (THO - 1) * S + KS;
   static constexpr int IW = (KS == 1) ? TW : (TW - 1) * S + KS;
   // stride-2 3x3: the halo is stored de-interleaved into 4 parity planes (row parity, column parity) so that every
   // tap again reads 8 x-adjacent plane pixels per core matrix: tap (ky,kx) -> plane (ky&1, kx&1), shift (ky>>1, kx>>1)
@@ -79,13 +88,13 @@ struct Cfg {
   static constexpr int NCH8 = CK / 8;
   static constexpr int X_HALF = NCH8 * NPIXP * 16;   // bytes of the hi (or lo) plane of one unit
   static constexpr int X_STAGE = 2 * X_HALF;
-  static constexpr int LBO_X = NPIXP * 16, SBO_X = PW * 16;
-  static constexpr int NTT = SPLIT ? 128 : 64;       // output channels per item
+  static constexpr int LBO_X = NPIXP * 16, SBO_X = NPH * PW * 16;
+  static constexpr int NTT = SPLIT ? 128 : 64 / NPH;  // output channels per item
   static constexpr int W_HALF = 128 * CK * 2;        // one [128 rows][CK] fp16 block
   static constexpr int W_BLOCK = SPLIT ? 2 * W_HALF : W_HALF;   // SPLIT: [W_hi block | W_lo block]
   static constexpr int LBO_W = 128, SBO_W = NCH8 * 128;
   static constexpr int KSTEPS = CK / 16;
-  static constexpr int TAPS = KS * KS;
+  static constexpr int TAPS = KY * KS;               // weight blocks per unit
   static constexpr int NW = (CK == 32) ? 4 : (SPLIT ? 4 : 6);
   static constexpr int kNxMax = TDVC_CONV_TC_NX_MAX;
   static constexpr bool fits(int nx) { return nx * X_STAGE + NW * W_BLOCK + 256 <= 227 * 1024; }
@@ -110,14 +119,14 @@ struct Item {
 };
 
 // `flip` >= 0: items are walked in descending order (item -> flip - item), see TdvcConvParams::order
-__device__ __forceinline__ Item decode_item(int item, int n_jt, int tiles_x, int tiles_y, int flip) {
+__device__ __forceinline__ Item decode_item(int item, int n_jt, int tiles_x, int tiles_y, int flip, int th = TH) {
   Item it;
   if (flip >= 0) item = flip - item;
   it.jt = item % n_jt;
   int st = item / n_jt;
   it.x0 = (st % tiles_x) * TW;
   st /= tiles_x;
-  it.y0 = (st % tiles_y) * TH;
+  it.y0 = (st % tiles_y) * th;
   it.n = st / tiles_y;
   return it;
 }
@@ -225,10 +234,10 @@ __device__ __forceinline__ void prod_convert_rt(const TdvcConvParams& p, const P
   else prod_convert<C, P, 5>(p, th, tab, c, v);
 }
 
-template <int KS, int CK, int S, int SPLIT>
+template <int KS, int CK, int S, int SPLIT, int NPH>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvParams p, int tiles_x, int tiles_y, int n_jt,
                                                               int n_units, int n_items) {
-  using C = Cfg<KS, CK, S, SPLIT>;
+  using C = Cfg<KS, CK, S, SPLIT, NPH>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* x_buf = smem;                                  // NX stages of [hi plane | lo plane]
   uint8_t* w_buf = smem + C::NX * C::X_STAGE;             // NW weight blocks
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     const int o_xs = sh * p.out_ld, m_xs = sh * p.mul_ld, r1_xs = sh * p.res1_ld, r2_xs = sh * p.res2_ld;
     int acc_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
-      const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip);
+      const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip, C::THO);
       const int sa = acc_it & 1;
       mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
       tc_fence_after();
@@ -447,6 +456,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     //      contiguous bytes (two full sectors) of the NHWC pixel, and the 4 quadrant warps cover its 256 bytes.
     const int quad = warp & 3, half = warp >> 2;
     const int part = lane >> 4, cl = lane & 15;
+    // row phases (Cfg::NPH): this lane's (hi, lo) row pair belongs to phase phi and channel cch of the item
+    constexpr int NPHS = NPH;
+    const int phi = (quad * 16 + cl) / C::NTT, cch = (quad * 16 + cl) - phi * C::NTT;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int Ho = p.Ho, Wo = p.Wo, cout = p.cout, act = p.act, post = p.post;
     const int sh = p.shuffle == 2 ? 2 : 1;
@@ -461,15 +473,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
     const float rscale = part ? kLoUnscale : 1.f;   // lo rows carry w_lo * 2^12
     // element strides of one tile row / one tile column in out / mul / res1 / res2 (all address the same logical pixel)
-    const int o_rs = sh * oW * p.out_ld, m_rs = sh * oW * p.mul_ld, r1_rs = sh * oW * p.res1_ld, r2_rs = sh * oW * p.res2_ld;
+    // (a tile row is NPHS image rows apart; the phase offset is folded into the base pointers)
+    const int o_rs = NPHS * sh * oW * p.out_ld, m_rs = NPHS * sh * oW * p.mul_ld, r1_rs = NPHS * sh * oW * p.res1_ld,
+              r2_rs = NPHS * sh * oW * p.res2_ld;
     const int o_xs = sh * p.out_ld, m_xs = sh * p.mul_ld, r1_xs = sh * p.res1_ld, r2_xs = sh * p.res2_ld;
     int acc_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
-      const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip);
+      const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip, C::THO);
       const int sa = acc_it & 1;
       mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
       tc_fence_after();
-      const int co = it.jt * NT + quad * 16 + cl;   // this lane's output channel (same for its hi and lo lane)
+      const int co = it.jt * C::NTT + cch;   // this lane's output channel (same for its hi and lo lane)
       float wbias = 0.f;                           // added once, on the lo row
       if (part && p.bias && co < cout) wbias = __ldg(p.bias + co);
       // where the channel lands (PixelShuffle(2) folded into the store: co' = q*(cout/4) + c)
@@ -481,9 +495,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         qx = q & 1;
       }
       const bool ch_ok = co < cout_st;
-      const int ny = Ho - it.y0, nx = Wo - it.x0;   // valid tile rows / columns
-      const int64_t pix0 = ((int64_t)it.n * oH + (it.y0 * sh + qy)) * oW + (it.x0 * sh + qx);
-      float* const o0 = planar ? p.out + (((int64_t)it.n * cout + co) * Ho + it.y0) * Wo + it.x0 : p.out + pix0 * p.out_ld + oc;
+      const int yb = it.y0 + phi;                   // first output row of this lane's phase
+      const int ny = Ho > yb ? (Ho - yb + NPHS - 1) / NPHS : 0, nx = Wo - it.x0;   // valid tile rows / columns
+      const int64_t pix0 = ((int64_t)it.n * oH + (yb * sh + qy)) * oW + (it.x0 * sh + qx);
+      float* const o0 = planar ? p.out + (((int64_t)it.n * cout + co) * Ho + yb) * Wo + it.x0 : p.out + pix0 * p.out_ld + oc;
       const float* const m0 = post != TDVC_POST_NONE ? p.mul + pix0 * p.mul_ld + oc : nullptr;
       const float* const r10 = p.res1 ? p.res1 + pix0 * p.res1_ld + oc : nullptr;
       const float* const r20 = p.res2 ? p.res2 + pix0 * p.res2_ld + oc : nullptr;
@@ -546,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           if (co < cout) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] = fminf(fmaxf(o[k], a_neg * o[k]), a_hi);
-            float* op = o0 + (int64_t)ty * Wo;
+            float* op = o0 + (int64_t)ty * NPHS * Wo;
             if (planar_vec && nx >= 8) {
               stg256(op, o);   // one full 32-byte sector
             } else {
@@ -639,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     // unit context: where the lane's 4 channels of unit (item, u) come from and which stage they go to
     int item = blockIdx.x, u = 0, sX = 0, phX = 1;
     auto setup = [&](ProdUnit& c) {
-      const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip);
+      const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip, C::THO);
       c.iy0 = it.y0 * S - C::PAD;
       c.ix0 = it.x0 * S - C::PAD;
       const float* sp = nullptr;
@@ -715,7 +730,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           tc_fence_after();
           const uint64_t x_hi = desc_add(xdesc0, (uint32_t)(sX * (C::X_STAGE / 16)));
 #pragma unroll 1
-          for (int ky = 0; ky < KS; ++ky) {
+          for (int ky = 0; ky < C::KY; ++ky) {
             // first tap of the kernel row: tap_slot(ky, 0); the other taps of the row are compile-time offsets from it
             const uint32_t row0 = C::PLANES ? (uint32_t)(((ky & 1) * 2 * C::PH + (ky >> 1)) * C::PW) : (uint32_t)(ky * C::IW);
             const uint64_t x_row = desc_add(x_hi, row0);
@@ -777,8 +792,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 // canonical K-major no-swizzle layout [(row/8)][(k/8)][row%8][k%8].  Row order = TMEM lane order of the accumulator:
 // lane quadrant q (rows 32q..32q+31) = channels 16q..16q+15: rows 32q+0..15 their hi terms, rows 32q+16..31 their lo * 2^12.
 // split = 1: per (cout tile of 128, unit, tap) two such blocks, W_hi then W_lo, row = channel, both scaled by 2^w_shift.
+// nph > 1 (row phases, see Cfg): T = (ks + nph - 1) * ks packed taps; the item's 64 row pairs are 64 / nph channels x nph phases
+// and the rows of phase f take tap (ky' - f, kx) of the ks x ks kernel (zero where that leaves the kernel).
 __global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict__ out, int T, int cin, int cin_pad,
-                                 int cout, int cout_pad, int CK, int n_units, int n_jt, int split, float scale) {
+                                 int cout, int cout_pad, int CK, int n_units, int n_jt, int split, float scale, int ks, int nph) {
   const int64_t per_block = (int64_t)(split ? 2 : 1) * 128 * CK;
   const int64_t total = (int64_t)n_jt * n_units * T * per_block;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -795,10 +812,19 @@ __global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict_
     const int row = ng * 8 + n8, k = kc * 8 + k8;
     const int quad = row >> 5;
     const int ci = u * CK + k;
-    const int co = split ? jt * 128 + row : jt * NT + quad * 16 + (row & 15);
+    const int ntt = NT / nph;                       // channels per item (64-channel scheme)
+    const int vc = quad * 16 + (row & 15);          // (phase, channel) pair of this row
+    const int phase = split ? 0 : vc / ntt;
+    const int co = split ? jt * 128 + row : jt * ntt + (vc - phase * ntt);
     const bool lo = split ? which == 1 : (row & 16) != 0;
+    int src_tap = tap;
+    if (nph > 1) {
+      const int ky = tap / ks - phase, kx = tap % ks;
+      src_tap = (ky >= 0 && ky < ks) ? ky * ks + kx : -1;
+    }
     float v = 0.f;
-    if (ci < cin_pad && co < cout_pad && ci < cin && co < cout) v = w[((int64_t)tap * cin_pad + ci) * cout_pad + co] * scale;
+    if (src_tap >= 0 && ci < cin_pad && co < cout_pad && ci < cin && co < cout)
+      v = w[((int64_t)src_tap * cin_pad + ci) * cout_pad + co] * scale;
     v = fminf(fmaxf(v, -65504.f), 65504.f);
     const __half hi = __float2half_rn(v);
     out[i] = lo ? __float2half_rn((v - __half2float(hi)) * (split ? 1.f : kLoScale)) : hi;
@@ -806,7 +832,7 @@ __global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict_
 }
 
 struct Choice {
-  int ks, ck, s, split;
+  int ks, ck, s, split, nph;
 };
 
 // Every KxK (K in 1,3,5,7; pad K/2) stride-1 convolution and the stride-2 3x3 / 1x1 ones have a tensor-core path;
@@ -818,24 +844,29 @@ static bool choose(const TdvcConvParams& p, Choice* c) {
   // 128-channel tiles win - GDN 128->128 @512x960 0.230 -> 0.179 ms, 1x1 + residual 0.219 -> 0.135 ms)
   const int split = (p.cout >= 96 && (p.cout & 3) == 0 && p.kh != 7) ? 1 : 0;
   if (p.stride == 2) {
-    if (p.kh == 3) { *c = {3, 16, 2, split}; return true; }
-    if (p.kh == 1) { *c = {1, 32, 2, split}; return p.cin >= 32; }
+    if (p.kh == 3) { *c = {3, 16, 2, split, 1}; return true; }
+    if (p.kh == 1) { *c = {1, 32, 2, split, 1}; return p.cin >= 32; }
     return false;
   }
   if (p.stride != 1) return false;
   const int ck = p.cin > 16 ? 32 : 16;
-  if (p.kh == 3) { *c = {3, ck, 1, ck == 32 ? split : 0}; return true; }
-  if (p.kh == 7) { *c = {7, ck, 1, 0}; return true; }
-  if (p.kh == 1 || p.kh == 5) { *c = {p.kh, 32, 1, split}; return p.cin >= 32; }
+  if (p.kh == 3) { *c = {3, ck, 1, ck == 32 ? split : 0, 1}; return true; }
+  if (p.kh == 7) {
+    // <= 32 output channels (SPyNet 8->32, 64->32, 32->16): two row phases fill the 64 row pairs of the M side
+    if (p.cout <= 32) { *c = {7, 16, 1, 0, 2}; return true; }
+    *c = {7, ck, 1, 0, 1};
+    return true;
+  }
+  if (p.kh == 1 || p.kh == 5) { *c = {p.kh, 32, 1, split, 1}; return p.cin >= 32; }
   return false;
 }
 
-template <int KS, int CK, int S, int SPLIT>
+template <int KS, int CK, int S, int SPLIT, int NPH = 1>
 static int launch(const TdvcConvParams& p, cudaStream_t st) {
-  using C = Cfg<KS, CK, S, SPLIT>;
+  using C = Cfg<KS, CK, S, SPLIT, NPH>;
   static bool attr_set = false;  // idempotent; a benign race sets it twice
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, CK, S, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, CK, S, SPLIT, NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute(%d bytes) failed: %s", C::SMEM, cudaGetErrorString(e));
       return TDVC_ECUDA;
@@ -843,12 +874,12 @@ static int launch(const TdvcConvParams& p, cudaStream_t st) {
     attr_set = true;
   }
   if (SPLIT) TDVC_REQUIRE(p.w_shift >= -100 && p.w_shift <= 100, "conv_tc: w_shift %d out of range", p.w_shift);
-  const int tiles_x = cdiv(p.Wo, TW), tiles_y = cdiv(p.Ho, TH);
+  const int tiles_x = cdiv(p.Wo, TW), tiles_y = cdiv(p.Ho, C::THO);
   const int n_jt = cdiv(p.cout, C::NTT), n_units = cdiv(p.cin, CK);
   const int64_t items = (int64_t)p.N * tiles_x * tiles_y * n_jt;
   TDVC_REQUIRE(items < (1ll << 31), "conv_tc: too many work items");
   const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  conv_tc_kernel<KS, CK, S, SPLIT><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items);
+  conv_tc_kernel<KS, CK, S, SPLIT, NPH><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items);
   TDVC_CHECK_LAUNCH("conv_tc");
   return TDVC_OK;
 }
@@ -884,6 +915,7 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
     if (c.ks == 3 && c.ck == 16) return tc::launch<3, 16, 1, 0>(p, st);
     if (c.ks == 1) return tc::launch<1, 32, 1, 0>(p, st);
     if (c.ks == 5) return tc::launch<5, 32, 1, 0>(p, st);
+    if (c.ks == 7 && c.nph == 2) return tc::launch<7, 16, 1, 0, 2>(p, st);
     if (c.ks == 7 && c.ck == 32) return tc::launch<7, 32, 1, 0>(p, st);
     if (c.ks == 7 && c.ck == 16) return tc::launch<7, 16, 1, 0>(p, st);
   }
@@ -896,9 +928,9 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
 using namespace tdvc;
 
 static size_t f16_elems(const TdvcConvParams* p, const tc::Choice& c) {
-  const int ntt = c.split ? 128 : tc::NT;
+  const int ntt = c.split ? 128 : tc::NT / c.nph;
   const int n_jt = cdiv(p->cout, ntt), n_units = cdiv(p->cin, c.ck);
-  return (size_t)n_jt * n_units * c.ks * c.ks * (c.split ? 2 : 1) * 128 * c.ck;
+  return (size_t)n_jt * n_units * (c.ks + c.nph - 1) * c.ks * (c.split ? 2 : 1) * 128 * c.ck;
 }
 
 extern "C" size_t tdvc_conv2d_f16_bytes(const TdvcConvParams* p) {
@@ -918,14 +950,15 @@ extern "C" int tdvc_conv2d_pack_f16(const TdvcConvParams* p, void* out, void* st
   TDVC_REQUIRE(p && out && p->weight, "conv2d_pack_f16: null pointer");
   TDVC_REQUIRE(tc::choose(*p, &c), "conv2d_pack_f16: shape has no tcgen05 path");
   TDVC_REQUIRE(!c.split || (p->w_shift >= -100 && p->w_shift <= 100), "conv2d_pack_f16: w_shift %d out of range", p->w_shift);
-  const int ntt = c.split ? 128 : tc::NT;
+  const int ntt = c.split ? 128 : tc::NT / c.nph;
   const int n_jt = cdiv(p->cout, ntt), n_units = cdiv(p->cin, c.ck);
   const int64_t total = (int64_t)f16_elems(p, c);
   int grid = cdiv(total, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   const float scale = c.split ? ldexpf(1.f, p->w_shift) : 1.f;
-  tc::pack_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->weight, static_cast<__half*>(out), c.ks * c.ks, p->cin,
-                                                             p->cin_pad, p->cout, p->cout_pad, c.ck, n_units, n_jt, c.split, scale);
+  tc::pack_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->weight, static_cast<__half*>(out), (c.ks + c.nph - 1) * c.ks, p->cin,
+                                                             p->cin_pad, p->cout, p->cout_pad, c.ck, n_units, n_jt, c.split, scale,
+                                                             c.ks, c.nph);
   TDVC_CHECK_LAUNCH("conv2d_pack_f16");
   return TDVC_OK;
 }

@@ -97,6 +97,9 @@ TC_CASES = [
     ([8], 32, 7, 1, 16, 24, dict(act=1)),                              # SPyNet 7x7
     ([16], 2, 7, 1, 16, 16, dict(res=True)),
     ([32], 64, 7, 1, 32, 16, dict(act=1)),
+    ([64], 32, 7, 1, 70, 20, dict(act=1)),                             # <= 32 output channels: two row phases per item
+    ([32], 16, 7, 1, 33, 9, dict(act=1, N=2)),                         # odd height: the last row has phase 0 only
+    ([8], 32, 7, 1, 129, 17, dict(act=2, slope=0.1, res=True)),        # three 64-row items, ragged
     ([64], 128, 3, 2, 32, 48, dict(act=2, slope=0.01)),               # stride 2
     ([128], 128, 3, 2, 18, 30, dict(N=2)),
     ([64], 128, 1, 2, 32, 32, dict(pad=0)),                            # 1x1 stride-2 skip
