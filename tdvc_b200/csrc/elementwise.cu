@@ -191,8 +191,19 @@ __global__ void se_scale_kernel(float* __restrict__ partial, int nblk, const flo
   const int nsl = blockDim.x / C;               // slices of the partial-sum rows summed in parallel (blockDim.x % C == 0)
   const int c = threadIdx.x % C, sl = threadIdx.x / C;
   float s = 0.f;
-  if (sl < nsl)
-    for (int b = sl; b < nblk; b += nsl) s += partial[((int64_t)b * N + n) * C + c];
+  if (sl < nsl) {   // 8 independent loads in flight per thread: the reduction is latency-bound, not bandwidth-bound
+    const float* pp = partial + (int64_t)n * C + c;
+    const int64_t rs = (int64_t)N * C;
+    int b = sl;
+    for (; b + 7 * nsl < nblk; b += 8 * nsl) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = pp[(int64_t)(b + k * nsl) * rs];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[k];
+    }
+    for (; b < nblk; b += nsl) s += pp[(int64_t)b * rs];
+  }
   red[threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.x < C) {
@@ -357,7 +368,7 @@ extern "C" int tdvc_se_apply(const float* x, int ld, float* partial, int nblk, c
   int gx = ew_grid(HW * (C / 4));
   if (gx > kNumSMs * 8) gx = kNumSMs * 8;
   dim3 grid(gx, N);
-  const int sthreads = C <= 256 ? (256 / C) * C : C;   // a multiple of C
+  const int sthreads = (1024 / C) * C;   // a multiple of C
   TDVC_REQUIRE(C <= 1024, "se_apply: C %d > 1024", C);
   se_scale_kernel<<<N, sthreads, (C + Cr + sthreads) * sizeof(float), (cudaStream_t)stream>>>(
       partial, nblk, w1, b1, w2, b2, N, HW, C, Cr);
