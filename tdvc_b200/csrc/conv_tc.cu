@@ -96,10 +96,18 @@ struct Cfg {
   static constexpr int KSTEPS = CK / 16;
   static constexpr int TAPS = KY * KS;               // weight blocks per unit
   static constexpr int NW = (CK == 32) ? 4 : (SPLIT ? 4 : 6);
+  // 1x1 stride-1 layers are bound by the depth of the producers' load pipeline (a few float4 per thread in registers), not by
+  // the tensor pipe: their producers stage the fp32 unit in shared memory with cp.async, NSTG units ahead (each thread reads
+  // back only the 16-byte slots it copied itself, so no barrier is involved), and convert from there.
+  static constexpr bool STAGED = (KS == 1 && S == 1);
+  static constexpr int NSTG = 2;
+  static constexpr int LOADS_PER_THREAD = (NHALO * (CK / 4) / 32 + kProdWarps - 1) / kProdWarps;   // = ProdCfg::PER_WARP
+  static constexpr int STG_UNIT = LOADS_PER_THREAD * kProdThreads * 16;
+  static constexpr int STG_BYTES = STAGED ? NSTG * STG_UNIT : 0;
   static constexpr int kNxMax = TDVC_CONV_TC_NX_MAX;
-  static constexpr bool fits(int nx) { return nx * X_STAGE + NW * W_BLOCK + 256 <= 227 * 1024; }
+  static constexpr bool fits(int nx) { return nx * X_STAGE + NW * W_BLOCK + STG_BYTES + 256 <= 227 * 1024; }
   static constexpr int NX = (kNxMax >= 4 && fits(4)) ? 4 : (fits(3) ? 3 : 2);
-  static constexpr int SMEM = NX * X_STAGE + NW * W_BLOCK + 256;
+  static constexpr int SMEM = NX * X_STAGE + NW * W_BLOCK + STG_BYTES + 256;
   static_assert(NPIXP >= NPIX, "pitch");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   // smem pixel slot of halo pixel (hy, hx)
@@ -241,7 +249,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* x_buf = smem;                                  // NX stages of [hi plane | lo plane]
   uint8_t* w_buf = smem + C::NX * C::X_STAGE;             // NW weight blocks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_buf + C::NW * C::W_BLOCK);
+  uint8_t* stg_buf = w_buf + C::NW * C::W_BLOCK;           // cp.async staging of the 1x1 producers (STG_BYTES, may be 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_buf + C::STG_BYTES);
   // barrier indices
   constexpr int X_FULL = 0, X_EMPTY = X_FULL + C::NX, W_FULL = X_EMPTY + C::NX, W_EMPTY = W_FULL + C::NW,
                 ACC_FULL = W_EMPTY + C::NW, ACC_EMPTY = ACC_FULL + 2, NBARS = ACC_EMPTY + 2;
@@ -292,6 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     const bool planar_vec = planar && (Wo & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0;
     const float a_neg = act == TDVC_ACT_NONE ? 1.f : (act == TDVC_ACT_LRELU ? p.slope : 0.f);
     const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
+    const bool has_act = act != TDVC_ACT_NONE;
     const float unscale = __int_as_float((127 - p.w_shift) << 23);   // 2^-w_shift, exact
     const int o_rs = sh * oW * p.out_ld, m_rs = sh * oW * p.mul_ld, r1_rs = sh * oW * p.res1_ld, r2_rs = sh * oW * p.res2_ld;
     const int o_xs = sh * p.out_ld, m_xs = sh * p.mul_ld, r1_xs = sh * p.res1_ld, r2_xs = sh * p.res2_ld;
@@ -370,8 +380,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             if (ty0 + h2 >= ny) continue;
+            if (has_act)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[h2 * 8 + k] = fminf(fmaxf(o[h2 * 8 + k], a_neg * o[h2 * 8 + k]), a_hi);
+              for (int k = 0; k < 8; ++k) o[h2 * 8 + k] = fminf(fmaxf(o[h2 * 8 + k], a_neg * o[h2 * 8 + k]), a_hi);
             float* op = o0 + (int64_t)(ty0 + h2) * Wo;
             if (planar_vec && nx >= 8) {
               stg256(op, o + h2 * 8);   // one full 32-byte sector
@@ -393,8 +404,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
               for (int j = 0; j < 16; ++j) o[j] = ra[j] * rsqrtf(o[j]);
             }
           }
+          if (has_act)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = fminf(fmaxf(o[j], a_neg * o[j]), a_hi);
+            for (int j = 0; j < 16; ++j) o[j] = fminf(fmaxf(o[j], a_neg * o[j]), a_hi);
           if (r10) {
             if (m0) {   // multiplier and residual together: the residual is loaded in place
 #pragma unroll
@@ -471,6 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     // branch-free activation: a(v) = min(max(v, a_neg * v), a_hi)   (0 <= a_neg <= 1)
     const float a_neg = act == TDVC_ACT_NONE ? 1.f : (act == TDVC_ACT_LRELU ? p.slope : 0.f);
     const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
+    const bool has_act = act != TDVC_ACT_NONE;
     const float rscale = part ? kLoUnscale : 1.f;   // lo rows carry w_lo * 2^12
     // element strides of one tile row / one tile column in out / mul / res1 / res2 (all address the same logical pixel)
     // (a tile row is NPHS image rows apart; the phase offset is folded into the base pointers)
@@ -559,8 +572,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         if (side && c < 6) l2_prefetch_row(ty + 4);
         if (planar) {  // NCHW planes: the 8 x-adjacent pixels of the tile row are contiguous in this channel's plane
           if (co < cout) {
+            if (has_act)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = fminf(fmaxf(o[k], a_neg * o[k]), a_hi);
+              for (int k = 0; k < 8; ++k) o[k] = fminf(fmaxf(o[k], a_neg * o[k]), a_hi);
             float* op = o0 + (int64_t)ty * NPHS * Wo;
             if (planar_vec && nx >= 8) {
               stg256(op, o);   // one full 32-byte sector
@@ -584,8 +598,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
                 for (int k = 0; k < 8; ++k) o[k] = mv[k] * rsqrtf(o[k]);
               }
             }
+            if (has_act)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = fminf(fmaxf(o[k], a_neg * o[k]), a_hi);
+              for (int k = 0; k < 8; ++k) o[k] = fminf(fmaxf(o[k], a_neg * o[k]), a_hi);
             if (r10) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) o[k] += ra[k];
@@ -602,8 +617,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             }
           } else {
             // activation a(v) = min(max(v, a_neg * v), a_hi): identity (a_neg 1), ReLU (0), LeakyReLU (slope), clamp01
+            if (has_act)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = fminf(fmaxf(o[k], a_neg * o[k]), a_hi);
+              for (int k = 0; k < 8; ++k) o[k] = fminf(fmaxf(o[k], a_neg * o[k]), a_hi);
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k, op += o_xs) *op = o[k];
@@ -682,6 +698,70 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       return item < n_items;
     };
 
+    if constexpr (C::STAGED) {
+      // ---- 1x1: global -> (cp.async) -> private staging slots -> fp16 hi/lo operand planes, NSTG units ahead
+      static_assert(P::PER_WARP == C::LOADS_PER_THREAD, "staging size");
+      const int ptid = threadIdx.x - kEpiWarps * 32;
+      uint8_t* const my_stg = stg_buf + ptid * 16;   // slot (d, k) at + (d * PER_WARP + k) * kProdThreads * 16
+      int is_item = blockIdx.x, is_u = 0;            // next unit to issue
+      auto issue = [&](int slot) {
+        if (is_item < n_items) {
+          const Item it = decode_item(is_item, n_jt, tiles_x, tiles_y, flip, C::THO);
+          const float* sp = nullptr;
+          int sld = 0;
+          int cc = is_u * CK + fi * 4;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q < p.n_src && sp == nullptr) {
+              if (cc < p.src_c[q]) { sp = p.src[q] + cc; sld = p.src_ld[q]; }
+              else cc -= p.src_c[q];
+            }
+          }
+          const float* org = sp ? sp + (((int64_t)it.n * p.H + it.y0) * p.W + it.x0) * sld : p.src[0];
+          const int ny = p.H - it.y0, nx = p.W - it.x0;
+#pragma unroll
+          for (int k = 0; k < P::PER_WARP; ++k) {
+            const int sidx = (k * kProdWarps + pw) * P::PPI + psub;   // tile pixel: row sidx / 8, column sidx % 8
+            if (sidx < C::NHALO) {
+              const int hy = sidx >> 3, hx = sidx & 7;
+              const bool ok = sp != nullptr && hy < ny && hx < nx;
+              const float* g = ok ? org + ((int64_t)hy * p.W + hx) * sld : p.src[0];
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(my_stg + (slot * P::PER_WARP + k) * (kProdThreads * 16))),
+                           "l"(g), "r"(ok ? 16 : 0)
+                           : "memory");
+            }
+          }
+          if (++is_u == n_units) { is_u = 0; is_item += gridDim.x; }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // (possibly empty: keeps the group count uniform)
+      };
+#pragma unroll
+      for (int d = 0; d < C::NSTG; ++d) issue(d);
+      int cv_item = blockIdx.x, cv_u = 0, slot = 0;
+      while (cv_item < n_items) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(C::NSTG - 1) : "memory");
+        mbar_wait(bar(X_EMPTY + sX), phX);
+        uint8_t* const hi = x_buf + sX * C::X_STAGE + th.lane_smem;
+#pragma unroll
+        for (int k = 0; k < P::PER_WARP; ++k) {
+          if ((th.vmask >> k) & 1) {
+            float4 v = *reinterpret_cast<const float4*>(my_stg + (slot * P::PER_WARP + k) * (kProdThreads * 16));
+            if (p.in_square) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
+            uint2 hv, lv;
+            split4(v, hv, lv);
+            uint8_t* dst = hi + k * (kProdWarps * P::PPI * 16);
+            *reinterpret_cast<uint2*>(dst) = hv;
+            *reinterpret_cast<uint2*>(dst + C::X_HALF) = lv;
+          }
+        }
+        fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(bar(X_FULL + sX));
+        if (++sX == C::NX) { sX = 0; phX ^= 1; }
+        issue(slot);         // refill the slot just consumed with the unit NSTG ahead
+        if (++slot == C::NSTG) slot = 0;
+        if (++cv_u == n_units) { cv_u = 0; cv_item += gridDim.x; }
+      }
+    } else {
     float4 va[P::BATCH], vb[P::BATCH];
     ProdUnit cur, nxt;
     bool have = item < n_items;
@@ -710,6 +790,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       mbar_arrive(bar(X_FULL + cur.stage));
       cur = nxt;
       have = have_next;
+    }
     }
   } else if (warp == kMmaWarp) {
     // ===================================================================== MMA issuer (one elected thread)
