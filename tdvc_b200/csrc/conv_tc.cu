@@ -398,10 +398,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           if (m0) {   // GDN / IGDN: v = mul * rsqrt(v) | mul * sqrt(v)   (rows past ny are never stored)
             if (post == TDVC_POST_IGDN) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = ra[j] * sqrtf(o[j]);
+              for (int j = 0; j < 16; ++j) o[j] = ra[j] * sqrt_fast(o[j]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = ra[j] * rsqrtf(o[j]);
+              for (int j = 0; j < 16; ++j) o[j] = ra[j] * rsqrt_fast(o[j]);
             }
           }
           if (has_act)
@@ -592,10 +592,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             if (m0) {  // GDN / IGDN: v = mul * rsqrt(v) | mul * sqrt(v)
               if (post == TDVC_POST_IGDN) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) o[k] = mv[k] * sqrtf(o[k]);
+                for (int k = 0; k < 8; ++k) o[k] = mv[k] * sqrt_fast(o[k]);
               } else {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) o[k] = mv[k] * rsqrtf(o[k]);
+                for (int k = 0; k < 8; ++k) o[k] = mv[k] * rsqrt_fast(o[k]);
               }
             }
             if (has_act)

@@ -113,6 +113,19 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hv, uint2& lv) {
 }
 
 
+// single-instruction MUFU forms for the GDN epilogue (rsqrtf / sqrtf carry a denormal-input wrapper with branches, ~15
+// instructions each; the GDN norm is >= beta > 0, a normal number).  Relative error <= 2 ulp, far below the split-MMA's 2^-22.
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // 256-bit global accesses (sm_100+): one request for the 8 channels of a deformable group / half a pixel row
