@@ -47,6 +47,24 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: `done` (one static array per launch site)
+// remembers the largest size already set on each device, so that a process driving several GPUs (nn.DataParallel
+// replicas) sets it on every one of them.  A racing second call sets the same value again, which is harmless.
+constexpr int kMaxDevices = 64;
+template <class K>
+static inline int ensure_dynamic_smem(K kernel, size_t bytes, int (&done)[kMaxDevices], const char* name) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = kMaxDevices - 1;
+  if ((size_t)done[dev] >= bytes) return TDVC_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%d bytes) failed: %s", name, (int)bytes, cudaGetErrorString(e));
+    return TDVC_ECUDA;
+  }
+  done[dev] = (int)bytes;
+  return TDVC_OK;
+}
+
 // 148 SMs on B200; persistent / grid-stride launches size their grids from this.
 constexpr int kNumSMs = 148;
 

@@ -155,15 +155,8 @@ static int launch(const TdvcConvParams& p, cudaStream_t st) {
   using C = Cfg<K, CO>;
   const size_t smem = C::smem(p.cin);
   TDVC_REQUIRE(smem <= 200 * 1024, "conv_small: cin %d needs %zu bytes of shared memory", p.cin, smem);
-  static size_t attr_bytes = 0;   // grows monotonically; a benign race sets it twice
-  if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_small_kernel<K, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("conv_small: cudaFuncSetAttribute(%d bytes) failed: %s", (int)smem, cudaGetErrorString(e));
-      return TDVC_ECUDA;
-    }
-    attr_bytes = smem;
-  }
+  static int smem_done[kMaxDevices] = {0};
+  if (int rc = ensure_dynamic_smem(conv_small_kernel<K, CO>, smem, smem_done, "conv_small")) return rc;
   const int tiles_x = cdiv(p.Wo, TS), tiles_y = cdiv(p.Ho, TS);
   const int64_t blocks = (int64_t)tiles_x * tiles_y * p.N;
   TDVC_REQUIRE(blocks < (1ll << 31), "conv_small: too many tiles");

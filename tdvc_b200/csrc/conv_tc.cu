@@ -945,15 +945,8 @@ static bool choose(const TdvcConvParams& p, Choice* c) {
 template <int KS, int CK, int S, int SPLIT, int NPH = 1>
 static int launch(const TdvcConvParams& p, cudaStream_t st) {
   using C = Cfg<KS, CK, S, SPLIT, NPH>;
-  static bool attr_set = false;  // idempotent; a benign race sets it twice
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KS, CK, S, SPLIT, NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-    if (e != cudaSuccess) {
-      set_error("conv_tc: cudaFuncSetAttribute(%d bytes) failed: %s", C::SMEM, cudaGetErrorString(e));
-      return TDVC_ECUDA;
-    }
-    attr_set = true;
-  }
+  static int smem_done[kMaxDevices] = {0};
+  if (int rc = ensure_dynamic_smem(conv_tc_kernel<KS, CK, S, SPLIT, NPH>, C::SMEM, smem_done, "conv_tc")) return rc;
   if (SPLIT) TDVC_REQUIRE(p.w_shift >= -100 && p.w_shift <= 100, "conv_tc: w_shift %d out of range", p.w_shift);
   const int tiles_x = cdiv(p.Wo, TW), tiles_y = cdiv(p.Ho, C::THO);
   const int n_jt = cdiv(p.cout, C::NTT), n_units = cdiv(p.cin, CK);

@@ -341,17 +341,13 @@ int dcn_tc_supported(const TdvcDcnParams& p) {
 }
 
 int dcn_tc(const TdvcDcnParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dcn::dcn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dcn::SMEM);
-    if (e != cudaSuccess) {
-      set_error("dcn_tc: cudaFuncSetAttribute(%d bytes) failed: %s", dcn::SMEM, cudaGetErrorString(e));
-      return TDVC_ECUDA;
-    }
-    // ask for the smallest shared-memory carve-out that holds the CTA: the rest of the 228 KB stays L1 for the gather
-    cudaFuncSetAttribute(dcn::dcn_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (dcn::SMEM + 1024) * 100 / (228 * 1024) + 1);
-    attr_set = true;
-  }
+  static int smem_done[kMaxDevices] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool first = dev >= 0 && dev < kMaxDevices && smem_done[dev] == 0;
+  if (int rc = ensure_dynamic_smem(dcn::dcn_tc_kernel, dcn::SMEM, smem_done, "dcn_tc")) return rc;
+  // ask for the smallest shared-memory carve-out that holds the CTA: the rest of the 228 KB stays L1 for the gather
+  if (first) cudaFuncSetAttribute(dcn::dcn_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (dcn::SMEM + 1024) * 100 / (228 * 1024) + 1);
   const int tiles_x = cdiv(p.W, dcn::kTile), tiles_y = cdiv(p.H, dcn::kTileH);
   const int64_t items = (int64_t)p.N * tiles_x * tiles_y;
   TDVC_REQUIRE(items < (1ll << 31), "dcn_tc: too many work items");
