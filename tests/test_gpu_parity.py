@@ -72,6 +72,12 @@ def test_pframe_forward_vs_oracle(net, oracle_model, dev, case, impl):
     _check_frame(net, oracle_model, dev, *case, impl)
 
 
+def test_pframe_forward_vs_oracle_multi_tile(net, oracle_model, dev):
+    """256x320: several 32- and 64-row items per column of tiles on every pyramid level (the row-phase 7x7 SPyNet layers
+    walk four 64-row items), 128-channel split tiles at 1/2 scale, FeatureFix with more than one candidate block."""
+    _check_frame(net, oracle_model, dev, 256, 320, 3, 0)
+
+
 @pytest.mark.parametrize("impl", [1, 0])
 @pytest.mark.parametrize("name", ["p64x64_s1", "p128x192_s2"])
 def test_pframe_forward_vs_reference_golden(net, dev, name, impl):
