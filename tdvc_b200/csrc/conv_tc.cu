@@ -281,11 +281,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 
   if (warp < kEpiWarps) {
     // ===================================================================== epilogue (8 warps: lane quadrant x pixel half)
-    // The 4 warps of a pixel half (128 threads, named barrier 1 + half) move 16 pixels (two tile rows) at a time:
-    //   write: warp = TMEM lane quadrant, lane = weight row -> slab[px][row] (conflict-free 128 B per pixel and warp);
-    //          the lo rows are rescaled and carry the bias;
-    //   read : thread = (tile column tx, 4 consecutive output channels) -> hi + lo as two float4, GDN / activation /
-    //          residuals, one 16-byte store per tile row: 16 lanes cover the 256 contiguous bytes of an NHWC pixel.
+    // Warp = (TMEM lane quadrant, pixel half): it reads its 32 accumulator rows 16 pixels (two tile rows) at a time with
+    // tcgen05.ld (the next chunk's load in flight while the current one is processed) and stores them itself.
     if constexpr (SPLIT == 1) {
     // ---- 128 output channels per item, one accumulator row per channel (TMEM lane = channel): every lane stores its own
     //      channel straight from the registers tcgen05.ld filled - per pixel the 32 lanes of a warp write 128 contiguous
