@@ -36,6 +36,7 @@
 //              an NHWC pixel.  128-channel items (split scheme): lane = channel, 32 lanes = 128 contiguous bytes.
 //              Bias / GDN / activation / residuals are applied in registers; GDN multipliers and the first residual
 //              are loaded one chunk ahead.  Overlaps the next item's MMAs (two accumulator stages = all 512 TMEM columns).
+#include <cuda.h>
 #include "tc_common.cuh"
 
 #ifndef TDVC_CONV_TC_NX_MAX
@@ -63,7 +64,7 @@ constexpr int NT = 64;                         // output channels per item (M = 
 //            kernel shifted down by f rows (tap (ky', kx) -> W[ky' - f][kx], zero outside), so one pass over KS + NPH - 1
 //            kernel rows produces NPH output rows per N column.  A 32-channel 7x7 layer then needs 8 x 7 MMA taps per
 //            512 pixels instead of 7 x 7 per 256 with half of the M rows idle.
-template <int KS, int CK, int S, int SPLIT = 0, int NPH = 1>
+template <int KS, int CK, int S, int SPLIT = 0, int NPH = 1, int PLN = 0>
 struct Cfg {
   static_assert(S == 1 || (S == 2 && (KS == 1 || KS == 3)), "stride");
   static_assert(NPH == 1 || (KS == 7 && S == 1 && SPLIT == 0 && (NPH == 2 || NPH == 4)), "row phases");
@@ -104,10 +105,13 @@ struct Cfg {
   static constexpr int LOADS_PER_THREAD = (NHALO * (CK / 4) / 32 + kProdWarps - 1) / kProdWarps;   // = ProdCfg::PER_WARP
   static constexpr int STG_UNIT = LOADS_PER_THREAD * kProdThreads * 16;
   static constexpr int STG_BYTES = STAGED ? NSTG * STG_UNIT : 0;
+  // PLN: planar (NCHW) output through tensor-map TMA stores: per epilogue warp two staging boxes of [32 channels][2 rows][8 px]
+  static_assert(PLN == 0 || SPLIT == 1, "TMA planar stores: split-scheme items only");
+  static constexpr int PLN_BYTES = PLN ? kEpiWarps * 2 * 2048 : 0;
   static constexpr int kNxMax = TDVC_CONV_TC_NX_MAX;
-  static constexpr bool fits(int nx) { return nx * X_STAGE + NW * W_BLOCK + STG_BYTES + 256 <= 227 * 1024; }
+  static constexpr bool fits(int nx) { return nx * X_STAGE + NW * W_BLOCK + STG_BYTES + PLN_BYTES + 256 <= 227 * 1024; }
   static constexpr int NX = (kNxMax >= 4 && fits(4)) ? 4 : (fits(3) ? 3 : 2);
-  static constexpr int SMEM = NX * X_STAGE + NW * W_BLOCK + STG_BYTES + 256;
+  static constexpr int SMEM = NX * X_STAGE + NW * W_BLOCK + STG_BYTES + PLN_BYTES + 256;
   static_assert(NPIXP >= NPIX, "pitch");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   // smem pixel slot of halo pixel (hy, hx)
@@ -242,15 +246,19 @@ __device__ __forceinline__ void prod_convert_rt(const TdvcConvParams& p, const P
   else prod_convert<C, P, 5>(p, th, tab, c, v);
 }
 
-template <int KS, int CK, int S, int SPLIT, int NPH>
+// PlanarMap: the 4-D tensor map (x, y, channel, image) of a planar output for the PLN variant, an empty tag otherwise
+struct NoMap {};
+template <int KS, int CK, int S, int SPLIT, int NPH, int PLN>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvParams p, int tiles_x, int tiles_y, int n_jt,
-                                                              int n_units, int n_items) {
-  using C = Cfg<KS, CK, S, SPLIT, NPH>;
+                                                              int n_units, int n_items,
+                                                              const __grid_constant__ std::conditional_t<PLN != 0, CUtensorMap, NoMap> omap) {
+  using C = Cfg<KS, CK, S, SPLIT, NPH, PLN>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* x_buf = smem;                                  // NX stages of [hi plane | lo plane]
   uint8_t* w_buf = smem + C::NX * C::X_STAGE;             // NW weight blocks
   uint8_t* stg_buf = w_buf + C::NW * C::W_BLOCK;           // cp.async staging of the 1x1 producers (STG_BYTES, may be 0)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_buf + C::STG_BYTES);
+  uint8_t* pln_buf = stg_buf + C::STG_BYTES;              // TMA planar-store staging of the epilogue warps (PLN_BYTES, may be 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pln_buf + C::PLN_BYTES);
   // barrier indices
   constexpr int X_FULL = 0, X_EMPTY = X_FULL + C::NX, W_FULL = X_EMPTY + C::NX, W_EMPTY = W_FULL + C::NW,
                 ACC_FULL = W_EMPTY + C::NW, ACC_EMPTY = ACC_FULL + 2, NBARS = ACC_EMPTY + 2;
@@ -371,6 +379,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 #pragma unroll
         for (int j = 0; j < 16; ++j) o[j] = fmaf(__uint_as_float(r[j]), unscale, wbias);
         if (c < 7) tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128 + (c + 1) * 16), r);
+        if constexpr (PLN != 0) {
+          // Planar (NCHW) output.  A lane's tile row is one 32-byte sector of its own plane, so a warp-wide st.global.v8
+          // scatters over 32 lines - four times the LSU wavefronts of an NHWC store, and the producers' operand stores
+          // queue behind them (64->216 3x3 @1024x1920: 1.71 ms planar vs 1.13 ms NHWC).  Instead the warp stages its
+          // [32 channels][2 rows][8 px] box in shared memory and one lane hands it to the TMA engine (4-D tensor map over
+          // (x, y, channel, image)), which also clips the box at the image and channel-count edges.
+          if (planar && ty0 < ny) {
+            if (has_act)
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = fminf(fmaxf(o[j], a_neg * o[j]), a_hi);
+            uint8_t* box = pln_buf + (warp * 2 + (c & 1)) * 2048;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store issued two chunks ago has read this box
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<float4*>(box + lane * 64)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(
+                               reinterpret_cast<uint64_t>(&omap)),
+                           "r"(it.x0), "r"(it.y0 + ty0), "r"(it.jt * C::NTT + quad * 32), "r"(it.n), "r"(smem_u32(box))
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            continue;
+          }
+        }
         if (!(ch_ok && ty0 < ny)) continue;
         if (side && c < 6) l2_prefetch_rows(ty0 + 4);
         if (planar) {  // NCHW planes: the 8 x-adjacent pixels of a tile row are contiguous in this channel's plane
@@ -456,6 +492,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           }
         }
       }
+    }
+    if constexpr (PLN != 0) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every staged box has been written out
     }
     } else {
     // ---- 64 output channels per item, rows [hi | lo * 2^12].  Row order (pack_f16_kernel): TMEM lane quadrant q holds channels
@@ -939,18 +978,34 @@ static bool choose(const TdvcConvParams& p, Choice* c) {
   return false;
 }
 
-template <int KS, int CK, int S, int SPLIT, int NPH = 1>
+template <int KS, int CK, int S, int SPLIT, int NPH = 1, int PLN = 0>
 static int launch(const TdvcConvParams& p, cudaStream_t st) {
-  using C = Cfg<KS, CK, S, SPLIT, NPH>;
+  using C = Cfg<KS, CK, S, SPLIT, NPH, PLN>;
   static int smem_done[kMaxDevices] = {0};
-  if (int rc = ensure_dynamic_smem(conv_tc_kernel<KS, CK, S, SPLIT, NPH>, C::SMEM, smem_done, "conv_tc")) return rc;
+  if (int rc = ensure_dynamic_smem(conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN>, C::SMEM, smem_done, "conv_tc")) return rc;
   if (SPLIT) TDVC_REQUIRE(p.w_shift >= -100 && p.w_shift <= 100, "conv_tc: w_shift %d out of range", p.w_shift);
   const int tiles_x = cdiv(p.Wo, TW), tiles_y = cdiv(p.Ho, C::THO);
   const int n_jt = cdiv(p.cout, C::NTT), n_units = cdiv(p.cin, CK);
   const int64_t items = (int64_t)p.N * tiles_x * tiles_y * n_jt;
   TDVC_REQUIRE(items < (1ll << 31), "conv_tc: too many work items");
   const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  conv_tc_kernel<KS, CK, S, SPLIT, NPH><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items);
+  if constexpr (PLN != 0) {
+    // tensor map of the planar output (N, cout, Ho, Wo) fp32: box = 8 px x 2 rows x 32 channels x 1 image
+    CUtensorMap tm;
+    const cuuint64_t dims[4] = {(cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.cout, (cuuint64_t)p.N};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.Wo * 4, (cuuint64_t)p.Ho * p.Wo * 4, (cuuint64_t)p.cout * p.Ho * p.Wo * 4};
+    const cuuint32_t box[4] = {8, 2, 32, 1}, estr[4] = {1, 1, 1, 1};
+    const CUresult r = cuTensorMapEncodeTiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out, dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+      return TDVC_ECUDA;
+    }
+    conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items, tm);
+  } else {
+    conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items, NoMap{});
+  }
   TDVC_CHECK_LAUNCH("conv_tc");
   return TDVC_OK;
 }
@@ -976,6 +1031,9 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
   if (c.split) {
     if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2, 1>(p, st);
     if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2, 1>(p, st);
+    // DCN offset / mask head: planar output through TMA tensor stores (needs 16-byte aligned planes and row pitch)
+    if (c.ks == 3 && p.out_planar && (p.Wo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
+      return tc::launch<3, 32, 1, 1, 1, 1>(p, st);
     if (c.ks == 3) return tc::launch<3, 32, 1, 1>(p, st);
     if (c.ks == 1) return tc::launch<1, 32, 1, 1>(p, st);
     if (c.ks == 5) return tc::launch<5, 32, 1, 1>(p, st);

@@ -134,6 +134,28 @@ def test_conv2d_small_cout_vs_torch(plan, dev, idx):
     assert (got - want).abs().max() <= 2e-5 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("shape", [(2, 37, 44), (1, 64, 96), (1, 19, 42)])
+def test_conv2d_planar_output_vs_torch(plan, dev, shape):
+    """out_planar = 1 (the DCN offset / mask head, 64 -> 216): NCHW planes written by the tensor-core kernel.  W % 4 == 0 takes
+    the tensor-map TMA store (box clipped at the right / bottom edge and at the channel count), W % 4 != 0 the st.global path."""
+    from tdvc_b200.model import Act, pack_conv
+    from tdvc_b200 import tc
+    N, H, W = shape
+    torch.manual_seed(300 + H)
+    conv = torch.nn.Conv2d(64, 216, 3, 1, 1)
+    x = torch.randn(N, 64, H, W)
+    want = conv(x).detach()
+    cw = pack_conv(conv.weight.to(dev), conv.bias.to(dev), src_layout=[(64, 64)])
+    tc.attach_f16({"w": cw})
+    guard = 64
+    flat = torch.full((N * 216 * H * W + 2 * guard,), 7.0, device=dev)
+    out = flat[guard:guard + N * 216 * H * W].view(N, 216, H, W)
+    plan.conv([Act.from_nchw(x.to(dev))], cw, out, planar=True, impl=2)
+    torch.cuda.synchronize()
+    assert (out.cpu() - want).abs().max() <= 2e-4 * max(1.0, want.abs().max().item())
+    assert bool((flat[:guard] == 7.0).all()) and bool((flat[-guard:] == 7.0).all())   # nothing written outside the tensor
+
+
 def test_conv2d_rejects_bad_arguments(plan, dev):
     from tdvc_b200 import lib as L
     p = L.ConvParams()
