@@ -27,18 +27,15 @@ __global__ void avgpool2x2_kernel(const float* __restrict__ src, float* __restri
 // One SPyNet level's input assembly.  flow_prev: (N, h/2, w/2, 2) or NULL (level 0 => zero flow).
 __global__ void spynet_prep_kernel(const float* __restrict__ ref4, const float* __restrict__ supp4,
                                    const float* __restrict__ flow_prev, float* __restrict__ out8, int N, int h, int w) {
-  const int64_t total = (int64_t)N * h * w;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int hp = h >> 1, wp = w >> 1;
   // align_corners=True source scale, as ATen computes it: (in-1)/(out-1) in fp32
   const float rh = h > 1 ? (float)(hp - 1) / (float)(h - 1) : 0.f;
   const float rw = w > 1 ? (float)(wp - 1) / (float)(w - 1) : 0.f;
   const float wm1 = (float)(w - 1 > 1 ? w - 1 : 1), hm1 = (float)(h - 1 > 1 ? h - 1 : 1);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int x = (int)(i % w);
-    const int64_t r = i / w;
-    const int y = (int)(r % h);
-    const int n = (int)(r / h);
+  // one block row per image row (blockIdx.y = n*h + y): no per-pixel index divisions, consecutive threads = consecutive pixels
+  const int y = blockIdx.y % h, n = blockIdx.y / h;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
+    const int64_t i = ((int64_t)n * h + y) * w + x;
     float fx = 0.f, fy = 0.f;
     if (flow_prev != nullptr) {
       const float h1r = rh * (float)y, w1r = rw * (float)x;
@@ -155,7 +152,10 @@ extern "C" int tdvc_spynet_prep(const float* ref4, const float* supp4, const flo
                                 int N, int h, int w, void* stream) {
   TDVC_REQUIRE(ref4 && supp4 && out8 && N > 0 && h >= 2 && w >= 2, "spynet_prep: bad args");
   TDVC_REQUIRE(flow_prev == nullptr || (h % 2 == 0 && w % 2 == 0), "spynet_prep: odd level size");
-  spynet_prep_kernel<<<grid_for((int64_t)N * h * w), 256, 0, (cudaStream_t)stream>>>(ref4, supp4, flow_prev, out8, N, h, w);
+  TDVC_REQUIRE((int64_t)N * h <= 65535, "spynet_prep: N*h %lld > 65535", (long long)N * h);
+  const int tpb = w >= 256 ? 256 : (w >= 128 ? 128 : 64);
+  dim3 grid((w + tpb - 1) / tpb, N * h);
+  spynet_prep_kernel<<<grid, tpb, 0, (cudaStream_t)stream>>>(ref4, supp4, flow_prev, out8, N, h, w);
   TDVC_CHECK_LAUNCH("spynet_prep");
   return TDVC_OK;
 }
