@@ -69,6 +69,14 @@ struct Cfg {
   static_assert(S == 1 || (S == 2 && (KS == 1 || KS == 3)), "stride");
   static_assert(NPH == 1 || (KS == 7 && S == 1 && SPLIT == 0 && (NPH == 2 || NPH == 4)), "row phases");
   static constexpr int THO = TH * NPH;                       // output rows of an item
+  // warp roles: 8 epilogue + 10 producer warps; the 1x1 stride-1 split-scheme layers (GDN / IGDN, 1x1 with >= 96 output
+  // channels) are bound by the epilogue's instruction stream while their cp.async-staged producers have little to do, so
+  // there the same 640 threads are 12 epilogue + 6 producer warps (3 epilogue warps per TMEM lane quadrant: 5, 5 and 6 of the
+  // sixteen 16-column chunks; 16 + 2 made the two producer warps the bottleneck: GDN 0.147 -> 0.194 ms)
+  static constexpr bool WIDE_EPI = (KS == 1 && S == 1 && SPLIT == 1);
+  static constexpr int EPIW = WIDE_EPI ? 12 : kEpiWarps, PRODW = WIDE_EPI ? 6 : kProdWarps;
+  static_assert(EPIW + PRODW + 2 == kThreads / 32 && EPIW % 4 == 0, "warp roles");
+  static constexpr int NGRP = EPIW / 4;                      // epilogue warps per TMEM lane quadrant: they share the 16 chunks
   static constexpr int KY = KS + NPH - 1;                    // kernel rows walked by the MMA loop
   static_assert(CK == 16 || CK == 32, "cin chunk");
   static constexpr int PAD = KS / 2;
@@ -102,12 +110,12 @@ struct Cfg {
   // back only the 16-byte slots it copied itself, so no barrier is involved), and convert from there.
   static constexpr bool STAGED = (KS == 1 && S == 1);
   static constexpr int NSTG = 2;
-  static constexpr int LOADS_PER_THREAD = (NHALO * (CK / 4) / 32 + kProdWarps - 1) / kProdWarps;   // = ProdCfg::PER_WARP
-  static constexpr int STG_UNIT = LOADS_PER_THREAD * kProdThreads * 16;
+  static constexpr int LOADS_PER_THREAD = (NHALO * (CK / 4) / 32 + PRODW - 1) / PRODW;   // = ProdCfg::PER_WARP
+  static constexpr int STG_UNIT = LOADS_PER_THREAD * PRODW * 32 * 16;
   static constexpr int STG_BYTES = STAGED ? NSTG * STG_UNIT : 0;
   // PLN: planar (NCHW) output through tensor-map TMA stores: per epilogue warp two staging boxes of [32 channels][2 rows][8 px]
   static_assert(PLN == 0 || SPLIT == 1, "TMA planar stores: split-scheme items only");
-  static constexpr int PLN_BYTES = PLN ? kEpiWarps * 2 * 2048 : 0;
+  static constexpr int PLN_BYTES = PLN ? EPIW * 2 * 2048 : 0;
   static constexpr int kNxMax = TDVC_CONV_TC_NX_MAX;
   static constexpr bool fits(int nx) { return nx * X_STAGE + NW * W_BLOCK + STG_BYTES + PLN_BYTES + 256 <= 227 * 1024; }
   static constexpr int NX = (kNxMax >= 4 && fits(4)) ? 4 : (fits(3) ? 3 : 2);
@@ -149,7 +157,7 @@ struct ProdCfg {
   static constexpr int LPP = CK / 4;                       // lanes (float4) per pixel
   static constexpr int PPI = 32 / LPP;                     // pixels per warp-wide load
   static constexpr int NLD = (C::NHALO + PPI - 1) / PPI;   // warp-wide loads per unit
-  static constexpr int PER_WARP = (NLD + kProdWarps - 1) / kProdWarps;
+  static constexpr int PER_WARP = (NLD + C::PRODW - 1) / C::PRODW;
   static constexpr int NBATCH = PER_WARP <= 12 ? 2 : 4;    // even: the two register buffers alternate
   static constexpr int BATCH = (PER_WARP + NBATCH - 1) / NBATCH;
 };
@@ -185,7 +193,7 @@ __device__ __forceinline__ void prod_issue(const TdvcConvParams& p, const ProdTh
 #pragma unroll
     for (int k = 0; k < P::BATCH; ++k) {
       const int kk = B * P::BATCH + k;
-      const int sidx = (kk * kProdWarps + th.pw) * P::PPI + th.psub;
+      const int sidx = (kk * C::PRODW + th.pw) * P::PPI + th.psub;
       const int hy = sidx / C::IW, hx = sidx - hy * C::IW;
       const int iy = c.iy0 + hy * C::STEP, ix = c.ix0 + hx * C::STEP;
       v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -215,7 +223,7 @@ __device__ __forceinline__ void prod_convert(const TdvcConvParams& p, const Prod
           const int po = tab[kk < P::PER_WARP ? kk : 0];
           dst = c.hi - (th.pw * P::PPI + th.psub) * 16 + C::slot(po >> 8, po & 255) * 16;
         } else {
-          dst = c.hi + kk * (kProdWarps * P::PPI * 16);   // flat slot = pixel index
+          dst = c.hi + kk * (C::PRODW * P::PPI * 16);   // flat slot = pixel index
         }
         *reinterpret_cast<uint2*>(dst) = hv;
         *reinterpret_cast<uint2*>(dst + C::X_HALF) = lv;
@@ -271,12 +279,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   const int flip = p.order ? n_items - 1 : -1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::NX; ++i) { mbar_init(bar(X_FULL + i), kProdThreads); mbar_init(bar(X_EMPTY + i), 1); }
+    for (int i = 0; i < C::NX; ++i) { mbar_init(bar(X_FULL + i), C::PRODW * 32); mbar_init(bar(X_EMPTY + i), 1); }
     for (int i = 0; i < C::NW; ++i) { mbar_init(bar(W_FULL + i), 1); mbar_init(bar(W_EMPTY + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(ACC_FULL + i), 1); mbar_init(bar(ACC_EMPTY + i), kEpiWarps * 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(ACC_FULL + i), 1); mbar_init(bar(ACC_EMPTY + i), C::EPIW * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kMmaWarp) {
+  if (warp == C::EPIW + C::PRODW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)TMEM_COLS)
                  : "memory");
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  if (warp < kEpiWarps) {
+  if (warp < C::EPIW) {
     // ===================================================================== epilogue (8 warps: lane quadrant x pixel half)
     // Warp = (TMEM lane quadrant, pixel half): it reads its 32 accumulator rows 16 pixels (two tile rows) at a time with
     // tcgen05.ld (the next chunk's load in flight while the current one is processed) and stores them itself.
@@ -295,7 +303,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     // ---- 128 output channels per item, one accumulator row per channel (TMEM lane = channel): every lane stores its own
     //      channel straight from the registers tcgen05.ld filled - per pixel the 32 lanes of a warp write 128 contiguous
     //      bytes of the NHWC pixel and the 4 quadrant warps cover its 512 bytes.  No shared-memory transposition.
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, grp = warp >> 2;   // TMEM lane quadrant, column group
+    // this warp's share of the sixteen 16-pixel chunks of an item: chunks chunk0 .. chunk0 + nchunk - 1
+    const int chunk0 = C::NGRP == 2 ? 8 * grp : (16 * grp) / C::NGRP;
+    const int nchunk = C::NGRP == 2 ? 8 : (16 * (grp + 1)) / C::NGRP - chunk0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int t = quad * 32 + lane;
     const int Ho = p.Ho, Wo = p.Wo, cout = p.cout, act = p.act, post = p.post;
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       const float* const r20 = p.res2 ? p.res2 + pix0 * p.res2_ld + oc : nullptr;
       const bool side = m0 || r10 || r20;
       uint32_t r[16];
-      tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128), r);
+      tmem_ld16(lane_addr + (uint32_t)(sa * NPX + chunk0 * 16), r);
       // residual / GDN-multiplier rows are pulled into L2 two chunks (4 tile rows) ahead: lane l < 16 covers pixel (row l / 8,
       // column l % 8) of the chunk - the 128 bytes of this quadrant's 32 channels are one line
       auto l2_prefetch_rows = [&](int tyb) {
@@ -363,22 +374,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         }
       };
       if (side) {
-        l2_prefetch_rows(half * 16);
-        l2_prefetch_rows(half * 16 + 2);
-        res_load(half * 16);
+        l2_prefetch_rows(2 * chunk0);
+        l2_prefetch_rows(2 * chunk0 + 2);
+        res_load(2 * chunk0);
       }
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        const int ty0 = half * 16 + c * 2;
+      for (int c = 0; c < nchunk; ++c) {
+        const int ty0 = 2 * chunk0 + c * 2;
         tmem_ld_wait();
-        if (c == 7) {
+        if (c == nchunk - 1) {
           tc_fence_before();
           mbar_arrive(bar(ACC_EMPTY + sa));
         }
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) o[j] = fmaf(__uint_as_float(r[j]), unscale, wbias);
-        if (c < 7) tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128 + (c + 1) * 16), r);
+        if (c < nchunk - 1) tmem_ld16(lane_addr + (uint32_t)(sa * NPX + chunk0 * 16 + (c + 1) * 16), r);
         if constexpr (PLN != 0) {
           // Planar (NCHW) output.  A lane's tile row is one 32-byte sector of its own plane, so a warp-wide st.global.v8
           // scatters over 32 lines - four times the LSU wavefronts of an NHWC store, and the producers' operand stores
@@ -408,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           }
         }
         if (!(ch_ok && ty0 < ny)) continue;
-        if (side && c < 6) l2_prefetch_rows(ty0 + 4);
+        if (side && c < nchunk - 2) l2_prefetch_rows(ty0 + 4);
         if (planar) {  // NCHW planes: the 8 x-adjacent pixels of a tile row are contiguous in this channel's plane
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
@@ -457,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
               for (int j = 0; j < 16; ++j) o[j] += ra[j];
             }
           }
-          if (pf0 && c < 7) res_load(ty0 + 2);
+          if (pf0 && c < nchunk - 1) res_load(ty0 + 2);
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             if (ty0 + h2 >= ny) continue;
@@ -502,7 +513,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     //      ONE warp and are merged with a lane-xor-16 shuffle - no shared-memory transposition, no barrier.  After the merge
     //      lanes 0-15 own the chunk's first tile row (8 pixels) and lanes 16-31 the second: per pixel the 16 lanes write 64
     //      contiguous bytes (two full sectors) of the NHWC pixel, and the 4 quadrant warps cover its 256 bytes.
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, grp = warp >> 2;   // TMEM lane quadrant, column group
+    // this warp's share of the sixteen 16-pixel chunks of an item: chunks chunk0 .. chunk0 + nchunk - 1
+    const int chunk0 = C::NGRP == 2 ? 8 * grp : (16 * grp) / C::NGRP;
+    const int nchunk = C::NGRP == 2 ? 8 : (16 * (grp + 1)) / C::NGRP - chunk0;
     const int part = lane >> 4, cl = lane & 15;
     // row phases (Cfg::NPH): this lane's (hi, lo) row pair belongs to phase phi and channel cch of the item
     constexpr int NPHS = NPH;
@@ -553,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       const float* const r20 = p.res2 ? p.res2 + pix0 * p.res2_ld + oc : nullptr;
       const bool side = m0 || r10 || r20;
       uint32_t r[16];
-      tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128), r);
+      tmem_ld16(lane_addr + (uint32_t)(sa * NPX + chunk0 * 16), r);
       // residual and GDN-multiplier rows: their DRAM latency (~1.5 us under load) is longer than a chunk, so they are pulled
       // into L2 two chunks (4 tile rows) ahead with prefetch.global.L2 - no registers held.  Lane cl < 8 covers tile column
       // cl of its part's row: the 64 bytes of this quadrant's 16 channels lie in one 128-byte line.
@@ -581,15 +595,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         }
       };
       if (side) {
-        l2_prefetch_row(half * 16 + part);
-        l2_prefetch_row(half * 16 + 2 + part);
-        side_load(half * 16 + part);
+        l2_prefetch_row(2 * chunk0 + part);
+        l2_prefetch_row(2 * chunk0 + 2 + part);
+        side_load(2 * chunk0 + part);
       }
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        const int ty = half * 16 + c * 2 + part;
+      for (int c = 0; c < nchunk; ++c) {
+        const int ty = 2 * chunk0 + c * 2 + part;
         tmem_ld_wait();
-        if (c == 7) {  // all TMEM reads of this warp are done: the accumulator stage may be overwritten
+        if (c == nchunk - 1) {  // all TMEM reads of this warp are done: the accumulator stage may be overwritten
           tc_fence_before();
           mbar_arrive(bar(ACC_EMPTY + sa));
         }
@@ -603,9 +617,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           o[k] = (part ? vb : va) + got;
         }
         // next chunk's accumulator columns: the TMEM read overlaps the loads / stores below
-        if (c < 7) tmem_ld16(lane_addr + (uint32_t)(sa * NPX + half * 128 + (c + 1) * 16), r);
+        if (c < nchunk - 1) tmem_ld16(lane_addr + (uint32_t)(sa * NPX + chunk0 * 16 + (c + 1) * 16), r);
         if (!(ch_ok && ty < ny)) continue;
-        if (side && c < 6) l2_prefetch_row(ty + 4);
+        if (side && c < nchunk - 2) l2_prefetch_row(ty + 4);
         if (planar) {  // NCHW planes: the 8 x-adjacent pixels of the tile row are contiguous in this channel's plane
           if (co < cout) {
             if (has_act)
@@ -641,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 #pragma unroll
               for (int k = 0; k < 8; ++k) o[k] += ra[k];
             }
-            if (c < 7) side_load(ty + 2);   // next chunk's multiplier / residual values: in flight across the stores,
+            if (c < nchunk - 1) side_load(ty + 2);   // next chunk's multiplier / residual values: in flight across the stores,
                                             // the TMEM wait and the merge of the next iteration
             if (r20) {
               const float* rp = r20 + ty * r2_rs;
@@ -678,7 +692,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       }
     }
     }
-  } else if (warp < kEpiWarps + kProdWarps) {
+  } else if (warp < C::EPIW + C::PRODW) {
     // ===================================================================== producers: fp32 halo -> fp16 hi/lo planes
     // LPP lanes cover the CK channels of a pixel (one float4 each), 32/LPP pixels per warp-wide load; the halo is
     // walked as a flat pixel list s = (k*8 + warp)*PPI + lane/LPP.  Each thread keeps, for its PER_WARP loads, the
@@ -687,7 +701,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     // batches AND units: the loads of batch b+1 (or of the next unit's batch 0) are issued before batch b is converted,
     // so the memory latency is covered by the fp32 -> fp16 hi/lo conversion of the previous batch.
     using P = ProdCfg<C, CK>;
-    const int pw = warp - kEpiWarps;
+    const int pw = warp - C::EPIW;
     const int fi = lane % P::LPP, psub = lane / P::LPP;
     ProdThread th;
     th.pw = pw;
@@ -696,7 +710,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     int tab[P::PER_WARP];   // non-PLANES: source pixel offset hy*STEP*W + hx*STEP;  PLANES: hy << 8 | hx
 #pragma unroll
     for (int k = 0; k < P::PER_WARP; ++k) {
-      const int sidx = (k * kProdWarps + pw) * P::PPI + psub;
+      const int sidx = (k * C::PRODW + pw) * P::PPI + psub;
       const int hy = sidx / C::IW, hx = sidx - hy * C::IW;
       tab[k] = C::PLANES ? ((hy << 8) | hx) : (hy * C::STEP * p.W + hx * C::STEP);
       if (sidx < C::NHALO) th.vmask |= 1u << k;
@@ -737,7 +751,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     if constexpr (C::STAGED) {
       // ---- 1x1: global -> (cp.async) -> private staging slots -> fp16 hi/lo operand planes, NSTG units ahead
       static_assert(P::PER_WARP == C::LOADS_PER_THREAD, "staging size");
-      const int ptid = threadIdx.x - kEpiWarps * 32;
+      const int ptid = threadIdx.x - C::EPIW * 32;
       uint8_t* const my_stg = stg_buf + ptid * 16;   // slot (d, k) at + (d * PER_WARP + k) * kProdThreads * 16
       int is_item = blockIdx.x, is_u = 0;            // next unit to issue
       auto issue = [&](int slot) {
@@ -757,12 +771,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           const int ny = p.H - it.y0, nx = p.W - it.x0;
 #pragma unroll
           for (int k = 0; k < P::PER_WARP; ++k) {
-            const int sidx = (k * kProdWarps + pw) * P::PPI + psub;   // tile pixel: row sidx / 8, column sidx % 8
+            const int sidx = (k * C::PRODW + pw) * P::PPI + psub;   // tile pixel: row sidx / 8, column sidx % 8
             if (sidx < C::NHALO) {
               const int hy = sidx >> 3, hx = sidx & 7;
               const bool ok = sp != nullptr && hy < ny && hx < nx;
               const float* g = ok ? org + ((int64_t)hy * p.W + hx) * sld : p.src[0];
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(my_stg + (slot * P::PER_WARP + k) * (kProdThreads * 16))),
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(my_stg + (slot * P::PER_WARP + k) * (C::PRODW * 32 * 16))),
                            "l"(g), "r"(ok ? 16 : 0)
                            : "memory");
             }
@@ -781,11 +795,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 #pragma unroll
         for (int k = 0; k < P::PER_WARP; ++k) {
           if ((th.vmask >> k) & 1) {
-            float4 v = *reinterpret_cast<const float4*>(my_stg + (slot * P::PER_WARP + k) * (kProdThreads * 16));
+            float4 v = *reinterpret_cast<const float4*>(my_stg + (slot * P::PER_WARP + k) * (C::PRODW * 32 * 16));
             if (p.in_square) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
             uint2 hv, lv;
             split4(v, hv, lv);
-            uint8_t* dst = hi + k * (kProdWarps * P::PPI * 16);
+            uint8_t* dst = hi + k * (C::PRODW * P::PPI * 16);
             *reinterpret_cast<uint2*>(dst) = hv;
             *reinterpret_cast<uint2*>(dst + C::X_HALF) = lv;
           }
@@ -828,7 +842,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       have = have_next;
     }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == C::EPIW + C::PRODW) {
     // ===================================================================== MMA issuer (one elected thread)
     // Descriptors are built once; every MMA only adds a compile-time offset (16-byte units) to their low word.
     if (elect_one()) {
@@ -898,7 +912,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == C::EPIW + C::PRODW) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
