@@ -16,14 +16,14 @@
 //   offsets / mask planar: plane (g*18 + 2*tap [+1]) resp. (g*9 + tap) of H*W floats - exactly the reference's NCHW
 //           offset / mask tensors (dcn_v2.h:9-46), and what the offset/mask convolution writes with out_planar = 1.
 //
-// Work decomposition (persistent, one CTA per SM, 576 threads):
+// Work decomposition (persistent, one CTA per SM, 768 threads):
 //   item = 16x8 output pixels = one MMA tile (M = 128: 8 rows x 16 px, row m = (y%8)*16 + x); kTiles tiles per item;
 //   K is ordered k' = (g*9 + tap)*8 + c (one 16-byte core-matrix row per (pixel, g, tap)), padded per group from 72
 //   to 80 (5 MMA k-steps); one pipeline stage = one deformable group.
-//   warps 4-15  producers: lane = pixel, task = (32 pixels, tap): 3 coalesced parameter loads, 4 x 256-bit corner
+//   warps 4-21  producers (18 warps, 80 registers: the gather is latency-bound, 12 warps at 94 registers were 8 % slower): lane = pixel, task = (32 pixels, tap): 3 coalesced parameter loads, 4 x 256-bit corner
 //               loads, bilinear blend * mask for the group's 8 channels, fp16 hi/lo split, two 16-byte smem stores.
-//   warp 17     streams the group's weight block [128 rows = w_hi | w_lo*2^12][80] (20 KB) by 1-D bulk TMA, 3-deep ring.
-//   warp 16     one elected thread issues per (stage, tile, k-step): D[:,0:128] += A_hi*[W_hi|W_lo]^T, D[:,0:64] += A_lo*W_hi^T.
+//   warp 23     streams the group's weight block [128 rows = w_hi | w_lo*2^12][80] (20 KB) by 1-D bulk TMA, 3-deep ring.
+//   warp 22     one elected thread issues per (stage, tile, k-step): D[:,0:128] += A_hi*[W_hi|W_lo]^T, D[:,0:64] += A_lo*W_hi^T.
 //   warps 0-3   epilogue: tcgen05.ld, hi+lo columns, bias, optional fp16 rounding + LeakyReLU as torch does on a
 //               Half tensor, 256-bit stores (NHWC fp32); overlaps the next item (2 accumulator stages in TMEM).
 #include "tc_common.cuh"
@@ -33,9 +33,9 @@ namespace dcn {
 
 using namespace tc;
 
-constexpr int kEpiWarps = 4, kProdWarps = 12;
+constexpr int kEpiWarps = 4, kProdWarps = 18;
 constexpr int kMmaWarp = kEpiWarps + kProdWarps, kLoadWarp = kMmaWarp + 1;
-constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 576
+constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;  // 768
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kTile = 16;                     // item width (pixels)
 constexpr int kTiles = 1;                    // MMA tiles (8 rows x 16 px, M = 128) per item.  One tile keeps the CTA at 140 KB
