@@ -1009,9 +1009,25 @@ static int launch(const TdvcConvParams& p, cudaStream_t st) {
     const cuuint64_t dims[4] = {(cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.cout, (cuuint64_t)p.N};
     const cuuint64_t strides[3] = {(cuuint64_t)p.Wo * 4, (cuuint64_t)p.Ho * p.Wo * 4, (cuuint64_t)p.cout * p.Ho * p.Wo * 4};
     const cuuint32_t box[4] = {8, 2, 32, 1}, estr[4] = {1, 1, 1, 1};
-    const CUresult r = cuTensorMapEncodeTiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out, dims, strides, box, estr,
-                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // cuTensorMapEncodeTiled is looked up through the runtime at first use: linking libcuda.so directly would make the
+    // library unloadable on a host without a driver (the CPU-only build / symbol checks load it there)
+    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;   // idempotent; a benign race resolves it twice
+    if (encode == nullptr) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+          qres != cudaDriverEntryPointSuccess) {
+        set_error("conv_tc: cuTensorMapEncodeTiled is not available from this driver");
+        return TDVC_ECUDA;
+      }
+      encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
       return TDVC_ECUDA;
