@@ -12,8 +12,10 @@ ranks of CUDA-event time around the K steps, bracketed by barrier + synchronize.
 
 JSON keys beyond the base contract: `e2e` (same metric through VideoCompressor.forward with pinned HOST frames:
 H2D of the frame and D2H of the reconstruction + bpp inside the timed region), `roofline` (dominant kernel,
-live per-launch CUDA-event timing of an instrumented eager pass), `cpu_baseline` (oracle on the host cores, bounded
-sample), `gpu_launches`, `clocks`, `stats` (bpp / PSNR of the coded frames).
+live per-launch CUDA-event timing of an instrumented eager pass of a steady-state chain frame), `cpu_baseline` (oracle on
+the host cores: ONE true 1920x1024 P-frame plus the 384x640 sample of round 1), `gpu_eager_baseline` (the same PyTorch
+restatement run eagerly on this B200: fp32, TF32 convolutions, autocast fp16), `config5` (multi-frame fusion + in-loop
+filter alone), `products_per_mac`, `gpu_launches`, `clocks`, `stats` (bpp / PSNR of the coded frames).
 """
 import argparse
 import json
@@ -31,7 +33,8 @@ sys.path.insert(0, ROOT)
 
 H, W, GOP = 1024, 1920, 12
 MACS_PER_PX = 3832051  # MAC per full-resolution pixel of one P-frame
-CPU_SAMPLE = (384, 640)  # 1/8 of the 1920x1024 pixels
+DEFAULT_PRECISION = "exact"
+CPU_SAMPLE = (384, 640)  # 1/8 of the 1920x1024 pixels (secondary CPU sample; the primary one is a full frame)
 
 
 def _peaks():
@@ -81,9 +84,12 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_oracle_rate(steps, warmup):
-    """Reference CPU path (oracle = restatement pinned bit-exact to the reference code) on a bounded sample:
-    P-frames at 384x640 (1/8 of the pixels of 1920x1024), all host threads; scaled by pixel count."""
+def cpu_oracle_rate(steps, warmup, full=True):
+    """Reference CPU path (oracle = restatement pinned bit-exact to the reference code), all host threads.
+    Primary sample: `steps` TRUE 1920x1024 P-frames (the workload's own first GOP, frame pair 1) after `warmup` warm-up
+    frames at 384x640 (a full-size warm-up would double the minutes for nothing: the first call costs < 1 % of a 35-90 s
+    frame).  Secondary: one 384x640 frame (1/8 of the pixels, the round-1 extrapolation base) and BASELINE config 1
+    (256x256).  Returns a dict."""
     import torch
     from oracle.stats import build_oracle
     from tdvc_b200 import synth
@@ -91,43 +97,105 @@ def cpu_oracle_rate(steps, warmup):
     torch.set_num_threads(cores)
     orc = build_oracle()
     h, w = CPU_SAMPLE
-    x, refs = synth.make_frame_pair(h, w, seed=3)
-    ts = []
+    xs, rs = synth.make_frame_pair(h, w, seed=3)
+    out = {"cores": torch.get_num_threads()}
     with torch.no_grad():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            orc(x, refs, False)
-            if i >= warmup:
-                ts.append(time.perf_counter() - t0)
-    t = sum(ts) / len(ts)
-    scale = (H * W) / (h * w)
-    # BASELINE config 1 (the reference's own CPU-runnable case): one 256x256 frame pair, batch 1
-    x1, r1 = synth.make_frame_pair(256, 256, seed=4)
-    with torch.no_grad():
+        for _ in range(max(warmup, 1)):
+            orc(xs, rs, False)
+        t0 = time.perf_counter()
+        orc(xs, rs, False)
+        out["sample_384x640_s"] = time.perf_counter() - t0
+        x1, r1 = synth.make_frame_pair(256, 256, seed=4)
         orc(x1, r1, False)
         t0 = time.perf_counter()
         orc(x1, r1, False)
-        cpu_oracle_rate.config1_s = time.perf_counter() - t0
-    return 1.0 / (t * scale), t, cores, torch.get_num_threads()
+        out["config1_256x256_s"] = time.perf_counter() - t0
+        if full:
+            g = synth.make_gop(H, W, gop=2, seed=100)
+            x, refs = g[1:2], g[0:1].unsqueeze(1).expand(-1, 4, -1, -1, -1).contiguous()
+            ts = []
+            for _ in range(steps):
+                t0 = time.perf_counter()
+                orc(x, refs, False)
+                ts.append(time.perf_counter() - t0)
+            out["full_s"] = sum(ts) / len(ts)
+            out["full_steps"] = steps
+    return out
+
+
+def _cpu_record(r):
+    if "full_s" in r:
+        fps = 1.0 / r["full_s"]
+        sample = (f"{r['full_steps']} true 1920x1024 P-frame(s) (frame 1 of the bench's first GOP), {r['full_s']:.1f} s each, after a "
+                  f"384x640 warm-up; oracle/model.py, torch fp32, {r['cores']} threads")
+    else:
+        fps = 1.0 / (r["sample_384x640_s"] * (H * W) / (CPU_SAMPLE[0] * CPU_SAMPLE[1]))
+        sample = (f"1 P-frame at 384x640 (1/8 of the pixels), {r['sample_384x640_s']:.2f} s, rate scaled by pixel count (extrapolated); "
+                  f"oracle/model.py, torch fp32, {r['cores']} threads")
+    return {"value": fps, "unit": "P-frames/s", "cores": r["cores"], "kind": "port", "sample": sample,
+            "extrapolated": "full_s" not in r, "sample_hw": [H, W] if "full_s" in r else list(CPU_SAMPLE),
+            "sample_384x640_s_per_frame": r["sample_384x640_s"],
+            "extrapolated_from_384x640_fps": 1.0 / (r["sample_384x640_s"] * (H * W) / (CPU_SAMPLE[0] * CPU_SAMPLE[1])),
+            "config1_256x256_s_per_frame": r["config1_256x256_s"]}
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (the oracle port) on the host cores, TRUE 1920x1024
+    frames: min(K, 2) timed steps so that the run ends within a few minutes (35-90 s per frame)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    fps, t, cores, threads = cpu_oracle_rate(steps, warmup)
-    sample = (f"{steps} P-frame(s) at {CPU_SAMPLE[0]}x{CPU_SAMPLE[1]} (1/8 of 1920x1024 pixels) after {warmup} warm-up, "
-              f"{t:.2f} s each, rate scaled by pixel count; oracle/model.py (torch fp32, {threads} threads)")
-    line = {"impl": "reference", "metric": "1920x1024 P-frames/sec", "value": fps, "unit": "P-frames/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak",
+    steps = max(1, min(args.steps, 2))
+    r = cpu_oracle_rate(steps, 1, full=True)
+    rec = _cpu_record(r)
+    line = {"impl": "reference", "metric": "1920x1024 P-frames/sec", "value": rec["value"], "unit": "P-frames/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": 1000.0 / rec["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "UVG-shaped synthetic 1920x1024 sequence, GOP 12, P-frame forward (bounded CPU sample)"},
-            "cpu_baseline": {"value": fps, "unit": "P-frames/s", "cores": threads, "kind": "port", "sample": sample,
-                             "config1_256x256_s_per_frame": cpu_oracle_rate.config1_s},
-            "e2e": {"value": fps, "unit": "P-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": {"workload": "UVG-shaped synthetic 1920x1024 sequence, GOP 12, P-frame forward, batch 1 "
+                                   f"({steps} true-size frame(s) on the host cores)"},
+            "cpu_baseline": rec,
+            "e2e": {"value": rec["value"], "unit": "P-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_baseline(dev, hh, ww, iters=3):
+    """The PyTorch restatement of the reference forward (oracle/model.py: cuDNN convolutions, torchvision deformable conv)
+    run EAGERLY on this GPU - what the reference's own code path costs on a B200 - in exact fp32, with TF32 convolutions,
+    and under autocast fp16 (the reference's shipped `enable_amp: True`).  A reported baseline."""
+    import torch
+    from oracle.stats import build_oracle
+    from tdvc_b200 import synth
+    out = {}
+    try:
+        orc = build_oracle().to(dev).eval()
+        g = synth.make_gop(hh, ww, gop=2, seed=100).to(dev)
+        x, refs = g[1:2], g[0:1].unsqueeze(1).expand(-1, 4, -1, -1, -1).contiguous()
+        tf0, tf1 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        for name, tf32, amp in (("fp32", False, False), ("tf32", True, False), ("autocast_fp16", True, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.no_grad():
+                for _ in range(2):
+                    with torch.autocast("cuda", enabled=amp):
+                        orc(x, refs, amp)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(iters):
+                    with torch.autocast("cuda", enabled=amp):
+                        orc(x, refs, amp)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            out[name] = {"ms_per_frame": ms, "fps": 1000.0 / ms}
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf0, tf1
+        out["what"] = "oracle/model.py in PyTorch eager mode on this GPU (cuDNN + torchvision deform_conv2d), batch 1, CUDA events"
+        del orc
+        torch.cuda.empty_cache()
+    except Exception as e:  # a baseline leg must never take the bench line down
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    return out
 
 
 def main():
@@ -137,8 +205,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="tdvc_b200")
     ap.add_argument("--conv-impl", type=int, default=0, help="0 auto (tcgen05 where supported), 1 SIMT fp32, 2 force tcgen05")
+    ap.add_argument("--precision", default=DEFAULT_PRECISION, choices=["exact", "mixed"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cache", action="store_true", help="recompute the per-GOP features every frame (as the reference does)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", default="full", choices=["full", "small"])
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
     args = ap.parse_args()
@@ -148,6 +220,7 @@ def main():
     import torch
     import torch.distributed as dist
     from tdvc_b200 import gop as G
+    from tdvc_b200 import lib as L
     from tdvc_b200 import synth
     from tdvc_b200.model import VideoCompressor
 
@@ -163,6 +236,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     hh, ww = args.height, args.width
     K, Wm = args.steps, max(args.warmup, 3)
+    # one untimed GOP in front of the W warm-up steps: every launch variant of a GOP (which features are cached) is run and
+    # captured into its CUDA graph there, so warm-up and timed steps replay graphs only
+    Wm_total = Wm + (GOP - 1)
 
     # ---- model: module default init under the reference seed + deterministic conditioning (synth.py)
     torch.manual_seed(synth.SEED)
@@ -172,19 +248,20 @@ def main():
     net.load_state_dict(sd)
     net = net.to(dev)
     net.conv_impl = args.conv_impl
+    net.precision = args.precision
     net.use_cuda_graph = not args.no_graph
+    net.cache_features = not args.no_cache
 
     # ---- synthetic sequence: this rank's GOPs (round-robin shard of a global GOP list), pinned on the host
-    n_gops_rank = math.ceil((K + Wm) / (GOP - 1)) + 1
-    my_gops = [g * world + rank for g in range(n_gops_rank)]
+    my_gops = [g * world + rank for g in range(2)]
     host_gops = []
-    for g in my_gops[:2]:  # two distinct GOPs are generated, then cycled (generation is slow on the host)
+    for g in my_gops:  # two distinct GOPs are generated, then cycled (generation is slow on the host)
         host_gops.append(synth.make_gop(hh, ww, gop=GOP, seed=100 + g).pin_memory())
     dev_gops = [g.to(dev, non_blocking=True) for g in host_gops]
     torch.cuda.synchronize()
 
     def frame_stream(src):
-        """yields (gop_index, frame_index, I-frame or P-frame) endlessly, GOP after GOP."""
+        """yields (gop, frame index) endlessly, GOP after GOP."""
         gi = 0
         while True:
             g = src[gi % len(src)]
@@ -197,7 +274,7 @@ def main():
         stats = torch.zeros(7, device=dev, dtype=torch.float64)
         sse = torch.zeros(1, device=dev, dtype=torch.float64)
         it = frame_stream(src)
-        refs, cur = None, None
+        refs = None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pin_out = torch.empty((1, 3, hh, ww), dtype=torch.float32).pin_memory() if host_io else None
         pin_bpp = torch.empty(2, dtype=torch.float32).pin_memory() if host_io else None
@@ -210,8 +287,7 @@ def main():
                 sampler.start()
                 ev0.record()
             g, t = next(it)
-            if t == 1 or g is not cur:
-                cur = g
+            if t == 1:
                 refs = [g[0:1].to(dev, non_blocking=True) if host_io else g[0:1]]
             x = g[t:t + 1].to(dev, non_blocking=True) if host_io else g[t:t + 1]
             recon, bpp_res, bpp_mv = net(x, G.reference_window(refs), False)
@@ -240,11 +316,11 @@ def main():
         return ms, stats, launches
 
     sampler = ClockSampler(local)
-    ms, stats, launches = run_chain(dev_gops, Wm, K, host_io=False)
+    ms, stats, launches = run_chain(dev_gops, Wm_total, K, host_io=False)
     clocks = sampler.stop()
     sampler = ClockSampler(local)
     sampler.start = lambda: None  # clocks are sampled on the device-resident leg only
-    ms_e2e, _, _ = run_chain(host_gops, Wm, K, host_io=True)
+    ms_e2e, _, _ = run_chain(host_gops, Wm_total, K, host_io=True)
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -257,33 +333,41 @@ def main():
     line = None
     if rank == 0:
         peaks, which = _peaks()
-        # ---- roofline of the dominant kernel: instrumented eager pass, per-launch CUDA events
+        # ---- roofline of the dominant kernel: instrumented eager pass over a steady-state chain frame (frame 7 of a GOP: the
+        #      I-frame features and two of the three fusion fronts come from the caches, as in 6 of every 11 frames),
+        #      per-launch CUDA events; the hyperprior side stream is serialised so that every launch is timed alone
         net.use_cuda_graph = False
         plan = net._plan(1, hh, ww, dev)
         g = dev_gops[0]
-        refs = G.reference_window([g[0:1], g[1:2], g[2:3], g[3:4]][:1])
-        for _ in range(2):
-            net(g[1:2], refs, False)
-        plan.prof = []
-        net(g[1:2], refs, False)
+        refs = [g[0:1]]
+        prof = None
+        for tt in range(1, 8):
+            if tt == 7:
+                plan.prof = []
+            recon, _, _ = net(g[tt:tt + 1], G.reference_window(refs), False)
+            refs.append(recon)
+            if len(refs) > 4:
+                refs = [refs[0]] + refs[-3:]
         torch.cuda.synchronize()
         prof, plan.prof = plan.prof, None
         agg = {}
-        for label, macs, nbytes, e0, e1 in prof:
-            a = agg.setdefault(label, [0, 0.0, 0, 0])
+        for label, macs, nbytes, e0, e1, prod in prof:
+            a = agg.setdefault(label, [0, 0.0, 0, 0, prod])
             a[0] += 1
             a[1] += e0.elapsed_time(e1)
             a[2] += macs
             a[3] += nbytes
         total_ms = sum(a[1] for a in agg.values())
+        mma_macs = sum(a[2] for a in agg.values() if a[4])
+        products_per_mac = sum(a[2] * a[4] for a in agg.values() if a[4]) / max(mma_macs, 1)
         top = sorted(agg.items(), key=lambda kv: -kv[1][1])
-        dom_label, (cnt, dms, dmacs, dbytes) = top[0]
+        dom_label, (cnt, dms, dmacs, dbytes, dprod) = top[0]
         if dmacs > 0 and not dom_label.startswith("dcn"):
             achieved = 2.0 * dmacs / (dms / 1e3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
             traffic = None
             try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/)
-                dj = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant.json")))
+                dj = json.load(open(os.path.join(ROOT, "profiles", "r02_dominant.json")))
                 if dj["label"] == dom_label:
                     images = dmacs / cnt / (hh * ww * 64 * 64 * 9)
                     traffic = dj["dram_bytes_per_image"] * images
@@ -292,10 +376,11 @@ def main():
             roof = {"kernel": dom_label, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic, "launches": cnt, "avg_launch_ms": dms / cnt,
                     "share_of_frame": dms / total_ms, "peak_source": which + " (sustained bf16)",
-                    "mma_equivalent_tflops": 4.0 * achieved, "mma_equivalent_frac": 4.0 * achieved / peak,
-                    "note": "achieved = algorithmic FLOPs (2*MACs of the convolution); the fp32-class FP16-split scheme "
-                            "issues 4 MMA products per algorithmic MAC, so tensor-pipe work is 4x (mma_equivalent_*); "
-                            "traffic = ncu dram bytes per launch (profiles/r01_dominant.json), averaged over the batch sizes launched"}
+                    "products_per_mac": dprod,
+                    "mma_equivalent_tflops": dprod * achieved, "mma_equivalent_frac": dprod * achieved / peak,
+                    "note": "achieved = algorithmic FLOPs (2*MACs of the convolution); this kernel issues `products_per_mac` fp16 MMA "
+                            "products per algorithmic MAC (fp32-class hi/lo split), so tensor-pipe work is that multiple "
+                            "(mma_equivalent_*); traffic = ncu dram bytes per launch (profiles/r02_dominant.json)"}
         else:
             achieved = dbytes / (dms / 1e3) / 1e9
             peak = peaks["hbm_gbs"]
@@ -304,7 +389,8 @@ def main():
                     "share_of_frame": dms / total_ms, "peak_source": which}
         kernels = {k: {"launches": v[0], "ms": round(v[1], 4),
                        "tflops": round(2.0 * v[2] / (v[1] / 1e3) / 1e12, 2) if v[2] and v[1] > 0 else None,
-                       "gbs": round(v[3] / (v[1] / 1e3) / 1e9, 1) if v[3] and v[1] > 0 else None} for k, v in top}
+                       "gbs": round(v[3] / (v[1] / 1e3) / 1e9, 1) if v[3] and v[1] > 0 else None,
+                       "products_per_mac": v[4] or None} for k, v in top}
         # memory-bound kernels of the frame against the measured HBM peak (warp, DCN gather, GDN, bits)
         mem_rows = {}
         for k, v in agg.items():
@@ -312,28 +398,53 @@ def main():
                 gbs = v[3] / (v[1] / 1e3) / 1e9
                 mem_rows[k] = {"ms": round(v[1], 4), "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 3)}
         frame_tflops = 2.0 * MACS_PER_PX * hh * ww / (ms / K / 1e3) / 1e12
+        # ---- BASELINE config 5 on its own: multi-frame fusion + in-loop filter with 4 reference frames (nothing cached)
+        cfg5 = None
+        try:
+            p1 = torch.randn(1, 64, hh, ww, device=dev) * 0.5
+            rf = torch.randn(1, 64, hh, ww, device=dev) * 0.5
+            r4 = G.reference_window([g[0:1], g[1:2], g[2:3], g[3:4]])
+            for _ in range(2):
+                net.fusion_and_filter(p1, r4, rf)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                net.fusion_and_filter(p1, r4, rf)
+            e1.record()
+            torch.cuda.synchronize()
+            c5ms = e0.elapsed_time(e1) / 5
+            cfg5 = {"ms_per_call": c5ms, "tflops": 2.0 * 1438138 * hh * ww / (c5ms / 1e3) / 1e12, "launches": net.last_launches,
+                    "what": "VideoCompressor.fusion_and_filter: mcfilter + loopfilter at full size, 4 reference frames, no cache, "
+                            "eager launches, includes the NCHW<->NHWC conversions of the 64-channel inputs / output"}
+            del p1, rf
+        except Exception as e:
+            cfg5 = {"error": f"{type(e).__name__}: {e}"[:300]}
+        eager = None
+        if not args.no_eager_baseline and world == 1:
+            eager = gpu_eager_baseline(dev, hh, ww)
         cpu = None
-        if not args.no_cpu_baseline:
-            fps_cpu, tcpu, cores, threads = cpu_oracle_rate(1, 1)
-            cpu = {"value": fps_cpu, "unit": "P-frames/s", "cores": threads, "kind": "port",
-                   "sample": f"1 P-frame at {CPU_SAMPLE[0]}x{CPU_SAMPLE[1]} (1/8 of the 1920x1024 pixels) after 1 warm-up, "
-                             f"{tcpu:.2f} s, rate scaled by pixel count; oracle/model.py, torch fp32, {threads} threads",
-                   "config1_256x256_s_per_frame": cpu_oracle_rate.config1_s}
+        if not args.no_cpu_baseline and world == 1:
+            cpu = _cpu_record(cpu_oracle_rate(1, 1, full=args.cpu_sample == "full"))
         frame_bytes = 3 * hh * ww * 4
+        dtype = ("f32 (convolutions: fp32 operands split into fp16 hi+lo, tcgen05 MMA, fp32 accumulation in TMEM"
+                 + ("; one fp16 product - the reference's autocast arithmetic - behind the last quantiser of the frame)"
+                    if args.precision == "mixed" else ")"))
         line = {"metric": "1920x1024 P-frames/sec", "value": value, "unit": "P-frames/s", "n_gpus": world, "steps": K,
-                "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (convolutions: fp32 operands split into fp16 hi+lo, tcgen05 MMA, fp32 accumulation in TMEM)",
-                "data": "synthetic",
+                "warmup": Wm_total, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": dtype, "data": "synthetic",
                 "config": {"workload": f"UVG-shaped synthetic {ww}x{hh} sequence, GOP 12 (I-frame raw + 11 chained P-frames), "
                                        "inference, batch 1 per GPU, GOP-sharded over ranks",
                            "l2": "per-frame working set >> 126 MB L2 (each full-resolution 64-channel tensor is 503 MB)",
-                           "cuda_graph": not args.no_graph, "conv_impl": args.conv_impl},
+                           "cuda_graph": not args.no_graph, "conv_impl": args.conv_impl, "precision": args.precision,
+                           "feature_cache": not args.no_cache},
                 "e2e": {"value": e2e, "unit": "P-frames/s", "h2d_bytes_per_step": frame_bytes,
                         "d2h_bytes_per_step": frame_bytes + 8},
                 "gpu_launches": launches, "clocks": clocks,
                 "roofline": roof, "frame_tensor_tflops": frame_tflops,
                 "frame_tensor_frac_of_sustained_bf16": frame_tflops / peaks["bf16_tflops_sustained"],
-                "memory_bound_kernels": mem_rows, "kernels": kernels, "cpu_baseline": cpu, "stats": G.summarise(stats)}
+                "products_per_mac": products_per_mac, "instrumented_frame_ms": total_ms,
+                "memory_bound_kernels": mem_rows, "kernels": kernels, "config5": cfg5, "gpu_eager_baseline": eager,
+                "cpu_baseline": cpu, "stats": G.summarise(stats)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

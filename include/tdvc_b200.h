@@ -78,6 +78,14 @@ typedef struct {
                                consecutive layers lets a layer start on the tiles its producer wrote last (still in the 126 MB L2) */
   int32_t out_planar;       /* 1: store NCHW planes, out[((n*cout + c)*Ho + y)*Wo + x] (no shuffle / residual / post);
                                the DCN offset/mask head writes the reference's planar offset & mask tensors this way */
+  float* out_absmax;        /* optional device scalar: *out_absmax = max(*out_absmax, max |v| over every value stored) (atomic
+                               max on the float bits; the caller zeroes it).  Feeds `in_absmax` of the GDN that squares this output */
+  const float* in_absmax;   /* tcgen05 path with in_square: device scalar >= max |x| of the input.  x*x is pre-scaled by the exact
+                               power of two that keeps max x*x below 2^15 (fp16 operands saturate at 65504) and the scale is undone
+                               in the epilogue; NULL or a value <= 181 leaves the arithmetic unchanged.  The SIMT path ignores it */
+  int32_t products;         /* tcgen05 path: 0 = fp32-class scheme (fp16 hi+lo split of both operands, 4 or 3 MMA products per
+                               MAC); 1 = one product, fp16(w) * fp16(x) with fp32 accumulation - the arithmetic of the reference
+                               under autocast (`enabled_amp`); weight_f16 must have been packed with the same value */
 } TdvcConvParams;
 int tdvc_conv2d(const TdvcConvParams* p, void* stream);
 /* tcgen05 path: size of / builder for the fp16 (hi, lo) weight blocks of a convolution, from its fp32 packed
@@ -85,15 +93,21 @@ int tdvc_conv2d(const TdvcConvParams* p, void* stream);
  * post, in_square) and `weight` are read.  bytes == 0: the shape has no tensor-core path (SIMT kernel is used). */
 size_t tdvc_conv2d_f16_bytes(const TdvcConvParams* p);
 int tdvc_conv2d_pack_f16(const TdvcConvParams* p, void* out, void* stream);
-/* 1 when the shape uses the 3-product split scheme (128-channel tiles; needs p->w_shift), else 0 */
+/* 1 when the fp16 weight blocks of the shape are pre-scaled by 2^w_shift (3-product split scheme with 128-channel tiles, and
+ * every one-product layer; the caller must then set p->w_shift as described above), else 0 */
 int tdvc_conv2d_f16_is_split(const TdvcConvParams* p);
+/* which kernel tdvc_conv2d runs for *p, as fp16 MMA products issued per algorithmic MAC: 0 = an exact fp32 SIMT kernel,
+ * 4 = hi/lo rows, 3 = split scheme, 1 = one product; -1 = invalid parameters (bench.py's `products_per_mac`) */
+int tdvc_conv2d_products(const TdvcConvParams* p);
 
 /* ---- DCNv2 forward, the reference's `_ext.dcn_v2_forward` (dcn_v2.h:9-46): contiguous NCHW fp32,
  * offset (N, 2*dg*kh*kw, H, W) ordered [g][tap][dy,dx], mask (N, dg*kh*kw, H, W), weight (O, C, kh, kw),
- * bias (O).  Only the configuration TDVC uses is implemented: 3x3, stride 1, pad 1, dilation 1; anything
- * else returns TDVC_EINVAL (the reference raises through AT_ASSERTM, dcn_v2_cuda.cu:38-62).
- * workspace: at least tdvc_dcn_v2_workspace_bytes(N,C,O,H,W,dg) bytes.  No im2col `columns` tensor is
- * materialised (reference dcn_v2_cuda.cu:68, 4.5 GB at 1920x1024).                                     */
+ * bias (O; NULL is accepted and means no bias - the reference's op always passes one, dcn_v2.h:12).  The configuration TDVC uses (3x3, stride 1,
+ * pad 1, dilation 1, 8 channels per deformable group) runs on the fused channels-last kernel through `workspace`; every
+ * other geometry (any kernel size / stride / padding / dilation / group width) is answered by a generic NCHW kernel that
+ * needs no workspace.  Inconsistent shapes return TDVC_EINVAL (the reference raises through AT_ASSERTM,
+ * dcn_v2_cuda.cu:38-62).  workspace: at least tdvc_dcn_v2_workspace_bytes(N,C,O,H,W,dg) bytes.  No im2col `columns`
+ * tensor is materialised (reference dcn_v2_cuda.cu:68, 4.5 GB at 1920x1024).                            */
 size_t tdvc_dcn_v2_workspace_bytes(int N, int C, int O, int H, int W, int dg);
 int tdvc_dcn_v2_forward(const float* input, const float* weight, const float* bias, const float* offset,
                         const float* mask, float* output, int N, int C, int O, int H, int W,
@@ -129,6 +143,17 @@ size_t tdvc_dcn_f16_bytes(int dg);
 int tdvc_dcn_pack_f16(const float* weight_packed, int O, int O_pad, int dg, void* out, void* stream);
 /* NHWC (src_ld floats per pixel, C % 8 == 0) -> [(n*C/8 + g)][H][W][8]: one 32-byte sector per (pixel, group) */
 int tdvc_nhwc_to_group_planar(const float* src, int src_ld, float* dst, int N, int H, int W, int C, void* stream);
+
+/* ---- frame plumbing ----
+ * zero_bytes: cudaMemsetAsync(p, 0, n) on the stream (per-frame accumulators).
+ * slices_hash: 128-bit content hash of n_slices slabs of slice_words 32-bit words each (slab i starts at base + i*stride_words):
+ *   out[2*i], out[2*i+1] = two independent order-free sums of mixed (word, position) pairs.  VideoCompressor.forward keys its
+ *   per-GOP caches on it (features of the I-frame, reference pnet.py:213-217, and of the previous reconstructions, :277-283,
+ *   are recomputed by the reference for every P-frame although their inputs repeat).
+ * bpp_finish: bpp[c] = (acc[2c] + acc[2c+1]) * scale for the two coders (reference pnet.py:38-43, 62-67).                    */
+int tdvc_zero_bytes(void* p, size_t n, void* stream);
+int tdvc_slices_hash(const void* base, int64_t slice_words, int64_t stride_words, int n_slices, uint64_t* out, void* stream);
+int tdvc_bpp_finish(const double* acc4, float* bpp2, double scale, void* stream);
 
 /* ---- layout ---- */
 int tdvc_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int dst_ld, void* stream); /* pads c>=C with 0 */

@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
                 raise RuntimeError(f"nvcc failed on {src}")
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in srcs]
     if force or jobs or _stale(LIB, objs):
-        r = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"], capture_output=True, text=True)
+        r = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"], capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")

@@ -18,6 +18,7 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st);
 int conv2d_small_supported(const TdvcConvParams& p);
 int conv2d_small(const TdvcConvParams& p, cudaStream_t st);
 }  // namespace tdvc
+extern "C" int tdvc_conv2d_f16_is_split(const TdvcConvParams* p);
 
 extern "C" int tdvc_version(void) { return 100; }
 extern "C" const char* tdvc_last_error(void) { return tdvc::g_err; }
@@ -33,8 +34,23 @@ extern "C" int tdvc_conv2d(const TdvcConvParams* p, void* stream) {
     }
     return tdvc::conv2d_tc(*p, st);
   }
+  if (p->out_absmax != nullptr && (p->impl == 3 || (p->impl == 0 && tdvc::conv2d_small_supported(*p)))) {
+    tdvc::set_error("conv2d: out_absmax is not available on the <= 4-channel kernel");
+    return TDVC_EINVAL;
+  }
   if (p->impl == 3) return tdvc::conv2d_small(*p, st);
   if (p->impl == 0 && tdvc::conv2d_small_supported(*p)) return tdvc::conv2d_small(*p, st);
   if (p->impl == 0 && tdvc::conv2d_tc_supported(*p)) return tdvc::conv2d_tc(*p, st);
   return tdvc::conv2d_simt(*p, st);
+}
+
+// which kernel tdvc_conv2d would run for *p and what it costs the tensor pipe: 0 = an exact fp32 SIMT kernel (no MMA),
+// otherwise the fp16 MMA products issued per algorithmic MAC (4 = hi/lo rows, 3 = split scheme, 1 = one product)
+extern "C" int tdvc_conv2d_products(const TdvcConvParams* p) {
+  if (p == nullptr || tdvc::conv2d_validate(p) != TDVC_OK) return -1;
+  if (p->impl == 1 || p->impl == 3) return 0;
+  if (p->impl == 0 && tdvc::conv2d_small_supported(*p)) return 0;
+  if (!tdvc::conv2d_tc_supported(*p)) return p->impl == 2 ? -1 : 0;
+  if (p->products == 1) return 1;
+  return tdvc_conv2d_f16_is_split(p) ? 3 : 4;
 }

@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_simt_kernel(const TdvcConvP
   const int oy = oy0 + py;
   if (oy >= p.Ho) return;
   const int cobase = ct * TN + cg * CPT;
+  float amax = 0.f;   // TdvcConvParams::out_absmax: max |v| over the values this thread stored
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int ox = ox0 + px0 + i;
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_simt_kernel(const TdvcConvP
             v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
           }
           *reinterpret_cast<float4*>(p.out + l.pix * p.out_ld + l.c) = v;
+          amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
         }
         continue;
       }
@@ -203,10 +205,17 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_simt_kernel(const TdvcConvP
       if (co >= p.cout) continue;
       const OutLoc l = out_loc(p, n, oy, ox, co);
       float v = acc[i][j] + (p.bias ? __ldg(p.bias + co) : 0.f);
-      if (p.out_planar) p.out[(((int64_t)n * p.cout + co) * p.Ho + oy) * p.Wo + ox] = apply_act(v, p.act, p.slope);
-      else p.out[l.pix * p.out_ld + l.c] = epilogue1(p, v, l);
+      if (p.out_planar) {
+        v = apply_act(v, p.act, p.slope);
+        p.out[(((int64_t)n * p.cout + co) * p.Ho + oy) * p.Wo + ox] = v;
+      } else {
+        v = epilogue1(p, v, l);
+        p.out[l.pix * p.out_ld + l.c] = v;
+      }
+      amax = fmaxf(amax, fabsf(v));
     }
   }
+  if (p.out_absmax != nullptr && amax > 0.f) atomicMax(reinterpret_cast<int*>(p.out_absmax), __float_as_int(amax));
 }
 
 template <int TN, int K, int S>
@@ -262,6 +271,9 @@ int conv2d_validate(const TdvcConvParams* p) {
   TDVC_REQUIRE(p->out_planar == 0 || (p->shuffle == 0 && p->post == TDVC_POST_NONE && !p->res1 && !p->res2),
                "conv2d: out_planar excludes shuffle / post / residual");
   TDVC_REQUIRE(p->N <= 65535 && p->cout_pad / 16 <= 65535, "conv2d: grid too large");
+  TDVC_REQUIRE(p->products == 0 || p->products == 1, "conv2d: products %d (0 = fp32-class split scheme, 1 = one fp16 product)", p->products);
+  TDVC_REQUIRE((reinterpret_cast<uintptr_t>(p->out_absmax) & 3) == 0 && (reinterpret_cast<uintptr_t>(p->in_absmax) & 3) == 0,
+               "conv2d: out_absmax / in_absmax not 4-byte aligned");
   return TDVC_OK;
 }
 

@@ -64,16 +64,26 @@ constexpr int NT = 64;                         // output channels per item (M = 
 //            kernel shifted down by f rows (tap (ky', kx) -> W[ky' - f][kx], zero outside), so one pass over KS + NPH - 1
 //            kernel rows produces NPH output rows per N column.  A 32-channel 7x7 layer then needs 8 x 7 MMA taps per
 //            512 pixels instead of 7 x 7 per 256 with half of the M rows idle.
-template <int KS, int CK, int S, int SPLIT = 0, int NPH = 1, int PLN = 0>
+// PR = 1 ("one product", TdvcConvParams::products): operands are plain fp16(w) and fp16(x), ONE MMA per k-step, no lo planes
+//            and no lo rows: the 128 M rows are 128 output channels (weights pre-scaled by 2^w_shift like the split scheme) or,
+//            for 3x3 layers with <= 64 output channels, 64 channels x 2 row phases.  This is the arithmetic of the reference
+//            under autocast; it is used for the stages behind the last quantiser only (precision budget).
+template <int KS, int CK, int S, int SPLIT = 0, int NPH = 1, int PLN = 0, int PR = 0>
 struct Cfg {
   static_assert(S == 1 || (S == 2 && (KS == 1 || KS == 3)), "stride");
-  static_assert(NPH == 1 || (KS == 7 && S == 1 && SPLIT == 0 && (NPH == 2 || NPH == 4)), "row phases");
+  static_assert(PR == 0 || (PR == 1 && SPLIT == 0), "one product: SPLIT is meaningless, pass 0");
+  static_assert(NPH == 1 || (S == 1 && SPLIT == 0 && ((KS == 7 && PR == 0 && (NPH == 2 || NPH == 4)) || (KS == 3 && PR == 1 && NPH == 2))),
+                "row phases");
+  // DIRECT: one accumulator row per (channel, phase) - the epilogue stores TMEM lanes as they are; otherwise the item's rows are
+  // (hi, lo) pairs that the epilogue merges
+  static constexpr bool DIRECT = (SPLIT == 1 || PR == 1);
+  static constexpr bool ONE = (PR == 1);
   static constexpr int THO = TH * NPH;                       // output rows of an item
   // warp roles: 8 epilogue + 10 producer warps; the 1x1 stride-1 split-scheme layers (GDN / IGDN, 1x1 with >= 96 output
   // channels) are bound by the epilogue's instruction stream while their cp.async-staged producers have little to do, so
   // there the same 640 threads are 12 epilogue + 6 producer warps (3 epilogue warps per TMEM lane quadrant: 5, 5 and 6 of the
   // sixteen 16-column chunks; 16 + 2 made the two producer warps the bottleneck: GDN 0.147 -> 0.194 ms)
-  static constexpr bool WIDE_EPI = (KS == 1 && S == 1 && SPLIT == 1);
+  static constexpr bool WIDE_EPI = (KS == 1 && S == 1 && DIRECT);
   static constexpr int EPIW = WIDE_EPI ? 12 : kEpiWarps, PRODW = WIDE_EPI ? 6 : kProdWarps;
   static_assert(EPIW + PRODW + 2 == kThreads / 32 && EPIW % 4 == 0, "warp roles");
   static constexpr int NGRP = EPIW / 4;                      // epilogue warps per TMEM lane quadrant: they share the 16 chunks
@@ -96,15 +106,16 @@ struct Cfg {
   static constexpr int NPIXP = (CK == 32) ? ((NPIX + 3) / 8 * 8 + 4) : (NPIX | 1);
   static constexpr int NCH8 = CK / 8;
   static constexpr int X_HALF = NCH8 * NPIXP * 16;   // bytes of the hi (or lo) plane of one unit
-  static constexpr int X_STAGE = 2 * X_HALF;
+  static constexpr int X_STAGE = (PR == 1 ? 1 : 2) * X_HALF;
   static constexpr int LBO_X = NPIXP * 16, SBO_X = NPH * PW * 16;
-  static constexpr int NTT = SPLIT ? 128 : 64 / NPH;  // output channels per item
+  static constexpr int NTT = (DIRECT ? 128 : 64) / NPH;  // output channels per item
   static constexpr int W_HALF = 128 * CK * 2;        // one [128 rows][CK] fp16 block
   static constexpr int W_BLOCK = SPLIT ? 2 * W_HALF : W_HALF;   // SPLIT: [W_hi block | W_lo block]
   static constexpr int LBO_W = 128, SBO_W = NCH8 * 128;
   static constexpr int KSTEPS = CK / 16;
   static constexpr int TAPS = KY * KS;               // weight blocks per unit
-  static constexpr int NW = (CK == 32) ? 4 : (SPLIT ? 4 : 6);
+  // weight ring depth: a one-product block is consumed in KSTEPS * 128 cycles, well below the latency of its bulk copy
+  static constexpr int NW = PR == 1 ? 8 : ((CK == 32) ? 4 : (SPLIT ? 4 : 6));
   // 1x1 stride-1 layers are bound by the depth of the producers' load pipeline (a few float4 per thread in registers), not by
   // the tensor pipe: their producers stage the fp32 unit in shared memory with cp.async, NSTG units ahead (each thread reads
   // back only the 16-byte slots it copied itself, so no barrier is involved), and convert from there.
@@ -114,7 +125,7 @@ struct Cfg {
   static constexpr int STG_UNIT = LOADS_PER_THREAD * PRODW * 32 * 16;
   static constexpr int STG_BYTES = STAGED ? NSTG * STG_UNIT : 0;
   // PLN: planar (NCHW) output through tensor-map TMA stores: per epilogue warp two staging boxes of [32 channels][2 rows][8 px]
-  static_assert(PLN == 0 || SPLIT == 1, "TMA planar stores: split-scheme items only");
+  static_assert(PLN == 0 || (SPLIT == 1 && NPH == 1), "TMA planar stores: split-scheme items only");
   static constexpr int PLN_BYTES = PLN ? EPIW * 2 * 2048 : 0;
   static constexpr int kNxMax = TDVC_CONV_TC_NX_MAX;
   static constexpr bool fits(int nx) { return nx * X_STAGE + NW * W_BLOCK + STG_BYTES + PLN_BYTES + 256 <= 227 * 1024; }
@@ -151,6 +162,25 @@ __device__ __forceinline__ Item decode_item(int item, int n_jt, int tiles_x, int
   return it;
 }
 
+// GDN / IGDN (in_square): x*x is pre-scaled by 2^-s so that max x*x < 2^15 stays inside the fp16 operand range (fp16 saturates
+// at 65504, i.e. |x| > 255 would clamp silently); s comes from the device scalar the producing layer's epilogue maintains
+// (TdvcConvParams::out_absmax -> in_absmax) and is undone exactly in the epilogue.  |x| <= 181: s = 0, nothing changes.
+__device__ __forceinline__ int square_shift(const TdvcConvParams& p) {
+  if (!p.in_square || p.in_absmax == nullptr) return 0;
+  const float m = __ldg(p.in_absmax);
+  if (!(m * m > 32768.f)) return 0;
+  const int e = ((__float_as_int(m) >> 23) & 0xff) - 127;   // m = f * 2^e, 1 <= f < 2  =>  m*m < 2^(2e+2)
+  const int s = 2 * e + 2 - 15;
+  return s < 0 ? 0 : (s > 100 ? 100 : s);
+}
+__device__ __forceinline__ float pow2f(int e) { return __int_as_float((127 + e) << 23); }   // -126 <= e <= 127
+// per-warp running max of |v| over the values an epilogue warp stored -> one atomic per warp (non-negative floats order like ints)
+__device__ __forceinline__ void absmax_commit(float* dst, float amax) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0 && dst != nullptr) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(amax));
+}
+
 // ---- producer helpers -------------------------------------------------------------------------------------------
 template <class C, int CK>
 struct ProdCfg {
@@ -164,6 +194,7 @@ struct ProdCfg {
 struct ProdThread {
   int pw, psub;
   uint32_t vmask, lane_smem;
+  float sq;   // in_square: exact power-of-two scale of x*x (square_shift), else unused
 };
 struct ProdUnit {
   const float* org;
@@ -209,7 +240,10 @@ __device__ __forceinline__ void prod_convert(const TdvcConvParams& p, const Prod
                                              const ProdUnit& c, float4 (&v)[P::BATCH]) {
   if (p.in_square) {
 #pragma unroll
-    for (int k = 0; k < P::BATCH; ++k) { v[k].x *= v[k].x; v[k].y *= v[k].y; v[k].z *= v[k].z; v[k].w *= v[k].w; }
+    for (int k = 0; k < P::BATCH; ++k) {
+      v[k].x = v[k].x * v[k].x * th.sq; v[k].y = v[k].y * v[k].y * th.sq;
+      v[k].z = v[k].z * v[k].z * th.sq; v[k].w = v[k].w * v[k].w * th.sq;
+    }
   }
 #pragma unroll
   for (int k = 0; k < P::BATCH; ++k) {
@@ -217,7 +251,12 @@ __device__ __forceinline__ void prod_convert(const TdvcConvParams& p, const Prod
     if (kk < P::PER_WARP) {
       if ((th.vmask >> kk) & 1) {
         uint2 hv, lv;
-        split4(v[k], hv, lv);
+        if constexpr (C::ONE) {
+          hv.x = pack_h2_sat(v[k].x, v[k].y);
+          hv.y = pack_h2_sat(v[k].z, v[k].w);
+        } else {
+          split4(v[k], hv, lv);
+        }
         uint8_t* dst;
         if (C::PLANES) {
           const int po = tab[kk < P::PER_WARP ? kk : 0];
@@ -226,7 +265,7 @@ __device__ __forceinline__ void prod_convert(const TdvcConvParams& p, const Prod
           dst = c.hi + kk * (C::PRODW * P::PPI * 16);   // flat slot = pixel index
         }
         *reinterpret_cast<uint2*>(dst) = hv;
-        *reinterpret_cast<uint2*>(dst + C::X_HALF) = lv;
+        if constexpr (!C::ONE) *reinterpret_cast<uint2*>(dst + C::X_HALF) = lv;
       }
     }
   }
@@ -256,11 +295,11 @@ __device__ __forceinline__ void prod_convert_rt(const TdvcConvParams& p, const P
 
 // PlanarMap: the 4-D tensor map (x, y, channel, image) of a planar output for the PLN variant, an empty tag otherwise
 struct NoMap {};
-template <int KS, int CK, int S, int SPLIT, int NPH, int PLN>
+template <int KS, int CK, int S, int SPLIT, int NPH, int PLN, int PR>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvParams p, int tiles_x, int tiles_y, int n_jt,
                                                               int n_units, int n_items,
                                                               const __grid_constant__ std::conditional_t<PLN != 0, CUtensorMap, NoMap> omap) {
-  using C = Cfg<KS, CK, S, SPLIT, NPH, PLN>;
+  using C = Cfg<KS, CK, S, SPLIT, NPH, PLN, PR>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* x_buf = smem;                                  // NX stages of [hi plane | lo plane]
   uint8_t* w_buf = smem + C::NX * C::X_STAGE;             // NW weight blocks
@@ -299,7 +338,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     // ===================================================================== epilogue (8 warps: lane quadrant x pixel half)
     // Warp = (TMEM lane quadrant, pixel half): it reads its 32 accumulator rows 16 pixels (two tile rows) at a time with
     // tcgen05.ld (the next chunk's load in flight while the current one is processed) and stores them itself.
-    if constexpr (SPLIT == 1) {
+    const int sq_shift = square_shift(p);   // GDN / IGDN: the accumulator holds the norm * 2^-sq_shift
+    float amax = 0.f;                       // max |v| over the values this lane stored (TdvcConvParams::out_absmax)
+    const bool track = p.out_absmax != nullptr;
+    if constexpr (C::DIRECT) {
     // ---- 128 output channels per item, one accumulator row per channel (TMEM lane = channel): every lane stores its own
     //      channel straight from the registers tcgen05.ld filled - per pixel the 32 lanes of a warp write 128 contiguous
     //      bytes of the NHWC pixel and the 4 quadrant warps cover its 512 bytes.  No shared-memory transposition.
@@ -309,6 +351,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     const int nchunk = C::NGRP == 2 ? 8 : (16 * (grp + 1)) / C::NGRP - chunk0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int t = quad * 32 + lane;
+    // row phases (one-product 3x3 layers with <= 64 channels): row t = phase phi, channel cch of the item
+    constexpr int NPHS = NPH;
+    const int phi = t / C::NTT, cch = t - phi * C::NTT;
     const int Ho = p.Ho, Wo = p.Wo, cout = p.cout, act = p.act, post = p.post;
     const int sh = p.shuffle == 2 ? 2 : 1;
     const int cr = cout >> 2;
@@ -318,8 +363,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     const float a_neg = act == TDVC_ACT_NONE ? 1.f : (act == TDVC_ACT_LRELU ? p.slope : 0.f);
     const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
     const bool has_act = act != TDVC_ACT_NONE;
-    const float unscale = __int_as_float((127 - p.w_shift) << 23);   // 2^-w_shift, exact
-    const int o_rs = sh * oW * p.out_ld, m_rs = sh * oW * p.mul_ld, r1_rs = sh * oW * p.res1_ld, r2_rs = sh * oW * p.res2_ld;
+    const float unscale = pow2f(-p.w_shift) * pow2f(sq_shift);   // 2^(sq_shift - w_shift), exact
+    const int o_rs = NPHS * sh * oW * p.out_ld, m_rs = NPHS * sh * oW * p.mul_ld, r1_rs = NPHS * sh * oW * p.res1_ld,
+              r2_rs = NPHS * sh * oW * p.res2_ld;
     const int o_xs = sh * p.out_ld, m_xs = sh * p.mul_ld, r1_xs = sh * p.res1_ld, r2_xs = sh * p.res2_ld;
     int acc_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++acc_it) {
@@ -327,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       const int sa = acc_it & 1;
       mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
       tc_fence_after();
-      const int co = it.jt * C::NTT + t;
+      const int co = it.jt * C::NTT + cch;
       const bool ch_ok = co < cout;
       const float wbias = (p.bias && ch_ok) ? __ldg(p.bias + co) : 0.f;
       int oc = co, qy = 0, qx = 0;
@@ -337,9 +383,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         qy = q >> 1;
         qx = q & 1;
       }
-      const int ny = Ho - it.y0, nx = Wo - it.x0;   // valid tile rows / columns
-      const int64_t pix0 = ((int64_t)it.n * oH + (it.y0 * sh + qy)) * oW + (it.x0 * sh + qx);
-      float* const o0 = planar ? p.out + (((int64_t)it.n * cout + co) * Ho + it.y0) * Wo + it.x0 : p.out + pix0 * p.out_ld + oc;
+      const int yb = it.y0 + phi;                   // first output row of this lane's phase
+      const int ny = Ho > yb ? (Ho - yb + NPHS - 1) / NPHS : 0, nx = Wo - it.x0;   // valid tile rows / columns
+      const int64_t pix0 = ((int64_t)it.n * oH + (yb * sh + qy)) * oW + (it.x0 * sh + qx);
+      float* const o0 = planar ? p.out + (((int64_t)it.n * cout + co) * Ho + yb) * Wo + it.x0 : p.out + pix0 * p.out_ld + oc;
       const float* const m0 = post != TDVC_POST_NONE ? p.mul + pix0 * p.mul_ld + oc : nullptr;
       const float* const r10 = p.res1 ? p.res1 + pix0 * p.res1_ld + oc : nullptr;
       const float* const r20 = p.res2 ? p.res2 + pix0 * p.res2_ld + oc : nullptr;
@@ -427,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             if (has_act)
 #pragma unroll
               for (int k = 0; k < 8; ++k) o[h2 * 8 + k] = fminf(fmaxf(o[h2 * 8 + k], a_neg * o[h2 * 8 + k]), a_hi);
-            float* op = o0 + (int64_t)(ty0 + h2) * Wo;
+            float* op = o0 + (int64_t)(ty0 + h2) * NPHS * Wo;
             if (planar_vec && nx >= 8) {
               stg256(op, o + h2 * 8);   // one full 32-byte sector
             } else {
@@ -483,6 +530,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             float* op = o0 + (ty0 + h2) * o_rs;
 #pragma unroll
             for (int k = 0; k < 8; ++k, op += o_xs) *op = o[h2 * 8 + k];
+            if (track)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(o[h2 * 8 + k]));
           }
         } else {         // ragged right edge (Wo % 8 != 0): one pixel at a time
 #pragma unroll 1
@@ -500,6 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             if (r10) v += __ldg(r10 + ty * r1_rs + k * r1_xs);
             if (r20) v += __ldg(r20 + ty * r2_rs + k * r2_xs);
             o0[ty * o_rs + k * o_xs] = v;
+            amax = fmaxf(amax, fabsf(v));
           }
         }
       }
@@ -534,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     const float a_neg = act == TDVC_ACT_NONE ? 1.f : (act == TDVC_ACT_LRELU ? p.slope : 0.f);
     const float a_hi = act == TDVC_ACT_CLAMP01 ? 1.f : __int_as_float(0x7f800000);
     const bool has_act = act != TDVC_ACT_NONE;
-    const float rscale = part ? kLoUnscale : 1.f;   // lo rows carry w_lo * 2^12
+    const float rscale = (part ? kLoUnscale : 1.f) * pow2f(sq_shift);   // lo rows carry w_lo * 2^12
     // element strides of one tile row / one tile column in out / mul / res1 / res2 (all address the same logical pixel)
     // (a tile row is NPHS image rows apart; the phase offset is folded into the base pointers)
     const int o_rs = NPHS * sh * oW * p.out_ld, m_rs = NPHS * sh * oW * p.mul_ld, r1_rs = NPHS * sh * oW * p.res1_ld,
@@ -673,6 +724,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k, op += o_xs) *op = o[k];
+          if (track && co < cout)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(o[k]));
         } else {         // ragged right edge (Wo % 8 != 0): one pixel at a time
 #pragma unroll 1
           for (int k = 0; k < nx; ++k) {
@@ -687,11 +741,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             if (r10) v += __ldg(r10 + ty * r1_rs + k * r1_xs);
             if (r20) v += __ldg(r20 + ty * r2_rs + k * r2_xs);
             op[k * o_xs] = v;
+            if (co < cout) amax = fmaxf(amax, fabsf(v));
           }
         }
       }
     }
     }
+    if (track) absmax_commit(p.out_absmax, amax);
   } else if (warp < C::EPIW + C::PRODW) {
     // ===================================================================== producers: fp32 halo -> fp16 hi/lo planes
     // LPP lanes cover the CK channels of a pixel (one float4 each), 32/LPP pixels per warp-wide load; the halo is
@@ -716,6 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       if (sidx < C::NHALO) th.vmask |= 1u << k;
     }
     th.lane_smem = (uint32_t)(((fi >> 1) * C::NPIXP) * 16 + (fi & 1) * 8 + (pw * P::PPI + psub) * 16);
+    th.sq = pow2f(-square_shift(p));
 
     // unit context: where the lane's 4 channels of unit (item, u) come from and which stage they go to
     int item = blockIdx.x, u = 0, sX = 0, phX = 1;
@@ -796,12 +853,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
         for (int k = 0; k < P::PER_WARP; ++k) {
           if ((th.vmask >> k) & 1) {
             float4 v = *reinterpret_cast<const float4*>(my_stg + (slot * P::PER_WARP + k) * (C::PRODW * 32 * 16));
-            if (p.in_square) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
+            if (p.in_square) { v.x = v.x * v.x * th.sq; v.y = v.y * v.y * th.sq; v.z = v.z * v.z * th.sq; v.w = v.w * v.w * th.sq; }
             uint2 hv, lv;
-            split4(v, hv, lv);
             uint8_t* dst = hi + k * (C::PRODW * P::PPI * 16);
-            *reinterpret_cast<uint2*>(dst) = hv;
-            *reinterpret_cast<uint2*>(dst + C::X_HALF) = lv;
+            if constexpr (C::ONE) {
+              hv.x = pack_h2_sat(v.x, v.y);
+              hv.y = pack_h2_sat(v.z, v.w);
+              *reinterpret_cast<uint2*>(dst) = hv;
+            } else {
+              split4(v, hv, lv);
+              *reinterpret_cast<uint2*>(dst) = hv;
+              *reinterpret_cast<uint2*>(dst + C::X_HALF) = lv;
+            }
           }
         }
         fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -878,7 +941,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
                 const uint64_t xl = desc_add(x_row, xo + s * KX + C::X_HALF / 16);
                 if (kx == 0 && s == 0) tc_mma(d, wk, xh, IDESC, (uint32_t)((u | ky) != 0));
                 else tc_mma(d, wk, xh, IDESC, 1u);
-                tc_mma(d, wk, xl, IDESC, 1u);
+                if constexpr (PR == 0) tc_mma(d, wk, xl, IDESC, 1u);
                 if constexpr (SPLIT == 1) tc_mma(d, desc_add(wk, C::W_HALF / 16), xh, IDESC, 1u);   // W_lo * x_hi
               }
               tc_commit(bar(W_EMPTY + sW));
@@ -925,8 +988,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
 // split = 1: per (cout tile of 128, unit, tap) two such blocks, W_hi then W_lo, row = channel, both scaled by 2^w_shift.
 // nph > 1 (row phases, see Cfg): T = (ks + nph - 1) * ks packed taps; the item's 64 row pairs are 64 / nph channels x nph phases
 // and the rows of phase f take tap (ky' - f, kx) of the ks x ks kernel (zero where that leaves the kernel).
+// pr = 1 (one product): per (cout tile, unit, tap) ONE block fp16(w * 2^w_shift); row = phase * (128 / nph) + channel.
 __global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict__ out, int T, int cin, int cin_pad,
-                                 int cout, int cout_pad, int CK, int n_units, int n_jt, int split, float scale, int ks, int nph) {
+                                 int cout, int cout_pad, int CK, int n_units, int n_jt, int split, float scale, int ks, int nph,
+                                 int pr) {
   const int64_t per_block = (int64_t)(split ? 2 : 1) * 128 * CK;
   const int64_t total = (int64_t)n_jt * n_units * T * per_block;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -943,11 +1008,12 @@ __global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict_
     const int row = ng * 8 + n8, k = kc * 8 + k8;
     const int quad = row >> 5;
     const int ci = u * CK + k;
-    const int ntt = NT / nph;                       // channels per item (64-channel scheme)
-    const int vc = quad * 16 + (row & 15);          // (phase, channel) pair of this row
-    const int phase = split ? 0 : vc / ntt;
-    const int co = split ? jt * 128 + row : jt * ntt + (vc - phase * ntt);
-    const bool lo = split ? which == 1 : (row & 16) != 0;
+    const bool direct = split || pr;
+    const int ntt = (direct ? 128 : NT) / nph;      // channels per item
+    const int vc = direct ? row : quad * 16 + (row & 15);          // (phase, channel) pair of this row
+    const int phase = vc / ntt;
+    const int co = jt * ntt + (vc - phase * ntt);
+    const bool lo = direct ? which == 1 : (row & 16) != 0;
     int src_tap = tap;
     if (nph > 1) {
       const int ky = tap / ks - phase, kx = tap % ks;
@@ -958,12 +1024,12 @@ __global__ void pack_f16_kernel(const float* __restrict__ w, __half* __restrict_
       v = w[((int64_t)src_tap * cin_pad + ci) * cout_pad + co] * scale;
     v = fminf(fmaxf(v, -65504.f), 65504.f);
     const __half hi = __float2half_rn(v);
-    out[i] = lo ? __float2half_rn((v - __half2float(hi)) * (split ? 1.f : kLoScale)) : hi;
+    out[i] = lo ? __float2half_rn((v - __half2float(hi)) * (direct ? 1.f : kLoScale)) : hi;
   }
 }
 
 struct Choice {
-  int ks, ck, s, split, nph;
+  int ks, ck, s, split, nph, pr;
 };
 
 // Every KxK (K in 1,3,5,7; pad K/2) stride-1 convolution and the stride-2 3x3 / 1x1 ones have a tensor-core path;
@@ -971,33 +1037,42 @@ struct Choice {
 // with >= 96 output channels (a multiple of 4), in tiles of 128 with the 3-product split scheme.
 static bool choose(const TdvcConvParams& p, Choice* c) {
   if (p.kh != p.kw || p.pad != p.kh / 2 || p.cin < 4 || p.cout < 1) return false;
+  if (p.products == 1) {
+    // one product: stride-1 3x3 (<= 64 output channels: 64 channels x 2 row phases per item) and 1x1 layers with >= 32 inputs
+    if (p.stride != 1 || p.cin < 32) return false;
+    if (p.kh == 3) { *c = {3, 32, 1, 0, p.cout <= 64 ? 2 : 1, 1}; return true; }
+    if (p.kh == 1) { *c = {1, 32, 1, 0, 1, 1}; return true; }
+    return false;
+  }
+  if (p.products != 0) return false;
   // (1x1 layers included: with the slab epilogue they were faster on 64-channel tiles, with the direct epilogue the
   // 128-channel tiles win - GDN 128->128 @512x960 0.230 -> 0.179 ms, 1x1 + residual 0.219 -> 0.135 ms)
   const int split = (p.cout >= 96 && (p.cout & 3) == 0 && p.kh != 7) ? 1 : 0;
   if (p.stride == 2) {
-    if (p.kh == 3) { *c = {3, 16, 2, split, 1}; return true; }
-    if (p.kh == 1) { *c = {1, 32, 2, split, 1}; return p.cin >= 32; }
+    if (p.kh == 3) { *c = {3, 16, 2, split, 1, 0}; return true; }
+    if (p.kh == 1) { *c = {1, 32, 2, split, 1, 0}; return p.cin >= 32; }
     return false;
   }
   if (p.stride != 1) return false;
   const int ck = p.cin > 16 ? 32 : 16;
-  if (p.kh == 3) { *c = {3, ck, 1, ck == 32 ? split : 0, 1}; return true; }
+  if (p.kh == 3) { *c = {3, ck, 1, ck == 32 ? split : 0, 1, 0}; return true; }
   if (p.kh == 7) {
     // <= 32 output channels (SPyNet 8->32, 64->32, 32->16): two row phases fill the 64 row pairs of the M side
-    if (p.cout <= 32) { *c = {7, 16, 1, 0, 2}; return true; }
-    *c = {7, ck, 1, 0, 1};
+    if (p.cout <= 32) { *c = {7, 16, 1, 0, 2, 0}; return true; }
+    *c = {7, ck, 1, 0, 1, 0};
     return true;
   }
-  if (p.kh == 1 || p.kh == 5) { *c = {p.kh, 32, 1, split, 1}; return p.cin >= 32; }
+  if (p.kh == 1 || p.kh == 5) { *c = {p.kh, 32, 1, split, 1, 0}; return p.cin >= 32; }
   return false;
 }
 
-template <int KS, int CK, int S, int SPLIT, int NPH = 1, int PLN = 0>
+template <int KS, int CK, int S, int SPLIT, int NPH = 1, int PLN = 0, int PR = 0>
 static int launch(const TdvcConvParams& p, cudaStream_t st) {
-  using C = Cfg<KS, CK, S, SPLIT, NPH, PLN>;
+  using C = Cfg<KS, CK, S, SPLIT, NPH, PLN, PR>;
   static int smem_done[kMaxDevices] = {0};
-  if (int rc = ensure_dynamic_smem(conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN>, C::SMEM, smem_done, "conv_tc")) return rc;
-  if (SPLIT) TDVC_REQUIRE(p.w_shift >= -100 && p.w_shift <= 100, "conv_tc: w_shift %d out of range", p.w_shift);
+  if (int rc = ensure_dynamic_smem(conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN, PR>, C::SMEM, smem_done, "conv_tc")) return rc;
+  if (C::DIRECT) TDVC_REQUIRE(p.w_shift >= -100 && p.w_shift <= 100, "conv_tc: w_shift %d out of range", p.w_shift);
+  TDVC_REQUIRE(NPH == 1 || !p.out_planar, "conv_tc: planar output is not available for row-phase items");
   const int tiles_x = cdiv(p.Wo, TW), tiles_y = cdiv(p.Ho, C::THO);
   const int n_jt = cdiv(p.cout, C::NTT), n_units = cdiv(p.cin, CK);
   const int64_t items = (int64_t)p.N * tiles_x * tiles_y * n_jt;
@@ -1032,9 +1107,9 @@ static int launch(const TdvcConvParams& p, cudaStream_t st) {
       set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
       return TDVC_ECUDA;
     }
-    conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items, tm);
+    conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN, PR><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items, tm);
   } else {
-    conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items, NoMap{});
+    conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN, PR><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items, NoMap{});
   }
   TDVC_CHECK_LAUNCH("conv_tc");
   return TDVC_OK;
@@ -1058,7 +1133,11 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
     set_error("conv_tc: unsupported shape");
     return TDVC_EINVAL;
   }
-  if (c.split) {
+  if (c.pr == 1) {
+    if (c.ks == 3 && c.nph == 2) return tc::launch<3, 32, 1, 0, 2, 0, 1>(p, st);
+    if (c.ks == 3) return tc::launch<3, 32, 1, 0, 1, 0, 1>(p, st);
+    if (c.ks == 1) return tc::launch<1, 32, 1, 0, 1, 0, 1>(p, st);
+  } else if (c.split) {
     if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2, 1>(p, st);
     if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2, 1>(p, st);
     // DCN offset / mask head: planar output through TMA tensor stores (needs 16-byte aligned planes and row pitch)
@@ -1087,7 +1166,7 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
 using namespace tdvc;
 
 static size_t f16_elems(const TdvcConvParams* p, const tc::Choice& c) {
-  const int ntt = c.split ? 128 : tc::NT / c.nph;
+  const int ntt = ((c.split || c.pr) ? 128 : tc::NT) / c.nph;
   const int n_jt = cdiv(p->cout, ntt), n_units = cdiv(p->cin, c.ck);
   return (size_t)n_jt * n_units * (c.ks + c.nph - 1) * c.ks * (c.split ? 2 : 1) * 128 * c.ck;
 }
@@ -1101,23 +1180,24 @@ extern "C" size_t tdvc_conv2d_f16_bytes(const TdvcConvParams* p) {
 extern "C" int tdvc_conv2d_f16_is_split(const TdvcConvParams* p) {
   tc::Choice c;
   if (p == nullptr || !tc::choose(*p, &c)) return 0;
-  return c.split;
+  return c.split || c.pr;
 }
 
 extern "C" int tdvc_conv2d_pack_f16(const TdvcConvParams* p, void* out, void* stream) {
   tc::Choice c;
   TDVC_REQUIRE(p && out && p->weight, "conv2d_pack_f16: null pointer");
   TDVC_REQUIRE(tc::choose(*p, &c), "conv2d_pack_f16: shape has no tcgen05 path");
-  TDVC_REQUIRE(!c.split || (p->w_shift >= -100 && p->w_shift <= 100), "conv2d_pack_f16: w_shift %d out of range", p->w_shift);
-  const int ntt = c.split ? 128 : tc::NT / c.nph;
+  const bool direct = c.split || c.pr;
+  TDVC_REQUIRE(!direct || (p->w_shift >= -100 && p->w_shift <= 100), "conv2d_pack_f16: w_shift %d out of range", p->w_shift);
+  const int ntt = (direct ? 128 : tc::NT) / c.nph;
   const int n_jt = cdiv(p->cout, ntt), n_units = cdiv(p->cin, c.ck);
   const int64_t total = (int64_t)f16_elems(p, c);
   int grid = cdiv(total, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  const float scale = c.split ? ldexpf(1.f, p->w_shift) : 1.f;
+  const float scale = direct ? ldexpf(1.f, p->w_shift) : 1.f;
   tc::pack_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->weight, static_cast<__half*>(out), (c.ks + c.nph - 1) * c.ks, p->cin,
                                                              p->cin_pad, p->cout, p->cout_pad, c.ck, n_units, n_jt, c.split, scale,
-                                                             c.ks, c.nph);
+                                                             c.ks, c.nph, c.pr);
   TDVC_CHECK_LAUNCH("conv2d_pack_f16");
   return TDVC_OK;
 }

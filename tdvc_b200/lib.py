@@ -27,7 +27,8 @@ class ConvParams(C.Structure):
                 ("mul", c_fp), ("mul_ld", C.c_int32), ("res1", c_fp), ("res1_ld", C.c_int32),
                 ("res2", c_fp), ("res2_ld", C.c_int32), ("out", c_fp), ("out_ld", C.c_int32),
                 ("shuffle", C.c_int32), ("impl", C.c_int32), ("weight_f16", c_fp), ("chan_sum", c_fp),
-                ("w_shift", C.c_int32), ("order", C.c_int32), ("out_planar", C.c_int32)]
+                ("w_shift", C.c_int32), ("order", C.c_int32), ("out_planar", C.c_int32),
+                ("out_absmax", c_fp), ("in_absmax", c_fp), ("products", C.c_int32)]
 
 
 class DcnParams(C.Structure):
@@ -49,6 +50,7 @@ SIGNATURES = {
     "tdvc_conv2d": [C.POINTER(ConvParams), vp],
     "tdvc_conv2d_f16_bytes": [C.POINTER(ConvParams)],
     "tdvc_conv2d_f16_is_split": [C.POINTER(ConvParams)],
+    "tdvc_conv2d_products": [C.POINTER(ConvParams)],
     "tdvc_conv2d_pack_f16": [C.POINTER(ConvParams), vp, vp],
     "tdvc_dcn_v2_workspace_bytes": [i32] * 6,
     "tdvc_dcn_v2_forward": [vp] * 6 + [i32] * 14 + [vp, sz, vp],
@@ -56,6 +58,9 @@ SIGNATURES = {
     "tdvc_dcn_f16_bytes": [i32],
     "tdvc_dcn_pack_f16": [vp, i32, i32, i32, vp, vp],
     "tdvc_nhwc_to_group_planar": [vp, i32, vp, i32, i32, i32, i32, vp],
+    "tdvc_zero_bytes": [vp, sz, vp],
+    "tdvc_slices_hash": [vp, i64, i64, i32, vp, vp],
+    "tdvc_bpp_finish": [vp, vp, C.c_double, vp],
     "tdvc_nchw_to_nhwc": [vp, vp, i32, i32, i32, i32, i32, vp],
     "tdvc_nhwc_to_nchw": [vp, i32, vp, i32, i32, i32, i32, vp],
     "tdvc_avgpool2x2": [vp, vp, i32, i32, i32, i32, vp],

@@ -11,9 +11,16 @@ Structure of this file
 
 Scope: inference (`eval()`), `is_compress=False`.  Training-mode quantisation noise / backward and the
 rANS bitstream are "next" rows and raise NotImplementedError.
+
+Per-GOP feature caches (`_Plan`): the features the reference recomputes for every P-frame from inputs that repeat
+inside a GOP are keyed on a content hash of the reference slice and reused; `forward` stays stateless in its results.
 """
+import ctypes as C
+import itertools
 import math
 import os
+import threading
+import weakref
 
 import torch
 import torch.nn as nn
@@ -324,7 +331,8 @@ def _r(x, m):
 
 # =============================================================================== packed weights
 class ConvW:
-    __slots__ = ("w", "b", "cin", "cin_real", "cin_pad", "cout", "cout_pad", "k", "pad", "shuffle", "w_f16", "stride", "w_shift")
+    __slots__ = ("w", "b", "cin", "cin_real", "cin_pad", "cout", "cout_pad", "k", "pad", "shuffle", "w_f16", "stride", "w_shift",
+                 "w_f16_p1", "w_shift_p1", "p1_ok", "wmax")
 
 
 def pack_conv(weight, bias, src_layout=None, shuffle=0, pad=None, stride=1):
@@ -364,27 +372,45 @@ def pack_conv(weight, bias, src_layout=None, shuffle=0, pad=None, stride=1):
     cw.stride = stride   # the tcgen05 weight blocking depends on it (csrc/conv_tc.cu `choose`)
     cw.w_f16 = None
     cw.w_shift = 0
+    cw.w_f16_p1 = None       # one-product fp16 blocks (tc.attach_f16), for the stages `precision = "mixed"` relaxes
+    cw.w_shift_p1 = 0
+    cw.p1_ok = False
+    cw.wmax = None
     return cw
 
 
 def _reparam(p, mod):
     """compressai NonNegativeParametrizer.forward: max(p, bound)^2 - pedestal."""
-    return torch.max(p.detach(), mod.lower_bound.bound) ** 2 - mod.pedestal
+    p = p.detach()
+    return torch.max(p, mod.lower_bound.bound.to(p.device)) ** 2 - mod.pedestal.to(p.device)
+
+
+# stages that may run with ONE fp16 MMA product (`VideoCompressor.precision = "mixed"`): everything behind the last quantiser
+# of the frame - the residual coder's synthesis transform and the in-loop filter on the reconstruction.  Measured budget:
+# profiles/r02_precision_budget.txt (DESIGN.md, precision).  FeatureExtract_ref stays exact: it is cached per GOP.
+_ONE_PRODUCT_PREFIXES = ("rs.gs", "lf.fe_in", "lf.featfusion", "lf.res")
 
 
 class _Packed:
-    """All device-side packed weights of one VideoCompressor, rebuilt when any parameter changes."""
+    """All packed weights of one VideoCompressor on one device.  Packing runs on the HOST from one copy of the parameters and
+    goes to the device as a single flat fp32 buffer (one H2D copy; the fp16 blocks of the tensor-core kernels are then built
+    from it by `pack_f16_kernel`), so loading a model issues no torch kernels."""
 
-    def __init__(self, m):
-        self.key = _param_key(m)
+    def __init__(self, m, dev):
         c = {}
+        cpu = {k: v.detach().to("cpu", torch.float32) for k, v in list(m.named_parameters()) + list(m.named_buffers())}
+
+        def P(mod, name):   # host copy of a parameter / buffer of `mod`
+            return cpu[self._names[id(getattr(mod, name))]]
+
+        self._names = {id(v): k for k, v in list(m.named_parameters()) + list(m.named_buffers())}
 
         def cv(name, mod, **kw):
-            c[name] = pack_conv(mod.weight, mod.bias, **kw)
+            c[name] = pack_conv(P(mod, "weight"), P(mod, "bias") if mod.bias is not None else None, **kw)
 
         def cv3d(name, mod):
-            w = mod.weight
-            c[name] = pack_conv(w.reshape(w.shape[0], w.shape[1], w.shape[3], w.shape[4]), mod.bias)
+            w = P(mod, "weight")
+            c[name] = pack_conv(w.reshape(w.shape[0], w.shape[1], w.shape[3], w.shape[4]), P(mod, "bias"))
 
         def res(name, stack):
             for i, rb in enumerate(stack):
@@ -392,10 +418,9 @@ class _Packed:
                 cv(f"{name}.{i}.conv2", rb.conv2)
 
         def se(name, mod):
-            c[name] = (mod.conv1.conv.weight.detach().float().reshape(mod.conv1.conv.weight.shape[0], -1).contiguous(),
-                       mod.conv1.conv.bias.detach().float().contiguous(),
-                       mod.conv2.conv.weight.detach().float().reshape(mod.conv2.conv.weight.shape[0], -1).contiguous(),
-                       mod.conv2.conv.bias.detach().float().contiguous())
+            w1, w2 = P(mod.conv1.conv, "weight"), P(mod.conv2.conv, "weight")
+            c[name] = (w1.reshape(w1.shape[0], -1).contiguous(), P(mod.conv1.conv, "bias").contiguous(),
+                       w2.reshape(w2.shape[0], -1).contiguous(), P(mod.conv2.conv, "bias").contiguous())
 
         img = [(3, 4)]
         cv("extra_fea.conv_first", m.extra_fea.conv_first, src_layout=img)
@@ -416,13 +441,13 @@ class _Packed:
                 cv(f"spy.{lvl}.{i}", me.spynet.basic_module[lvl].basic_module[i].conv)
         mc = m.mcnet
         cv("mc.offmask", mc.dconv.conv_offset_mask)
-        wd = mc.dconv.weight.detach().float()  # (O, C, 3, 3) -> [C*9][O_pad], row = c*9 + tap
+        wd = P(mc.dconv, "weight")  # (O, C, 3, 3) -> [C*9][O_pad], row = c*9 + tap
         O, Cc = wd.shape[0], wd.shape[1]
         opad = _r(O, 64)
-        pk = torch.zeros(Cc * 9, opad, device=wd.device, dtype=torch.float32)
+        pk = torch.zeros(Cc * 9, opad, dtype=torch.float32)
         pk[:, :O] = wd.reshape(O, Cc * 9).t()
         c["mc.dcn.w"] = pk.contiguous()
-        c["mc.dcn.b"] = mc.dconv.bias.detach().float().contiguous()
+        c["mc.dcn.b"] = P(mc.dconv, "bias").contiguous()
         cv("mc.conv", mc.conv, src_layout=[(64, 64), (64, 64)])
         res("mc.res", mc.recon_layer)
         mf = m.mcfilter
@@ -432,7 +457,7 @@ class _Packed:
         cv3d("mf.l1.conv1", mf.layer1.conv1)
         cv3d("mf.l1.spatial", mf.layer1.spatial_conv3d)
         cv3d("mf.l1.conv3", mf.layer1.conv3)
-        wt = mf.layer1.temporal_conv3d.weight.detach().float()  # (64, 64, 3, 1, 1): [o][c][t] -> 1x1 over (t, c)
+        wt = P(mf.layer1.temporal_conv3d, "weight")  # (64, 64, 3, 1, 1): [o][c][t] -> 1x1 over (t, c)
         c["mf.l1.temporal"] = pack_conv(wt[:, :, :, 0, 0].permute(0, 2, 1).reshape(64, 192, 1, 1), None,
                                         src_layout=[(64, 64)] * 3)
         cv("mf.fusion", mf.feat_fusion, src_layout=[(64, 64)] * 4)
@@ -448,15 +473,19 @@ class _Packed:
         cv("lf.featdown", lf.featdown)
         se("lf.attn", lf.attn)
         for cn, cd in (("mv", m.mvCoder), ("rs", m.resCoder)):
-            self._pack_coder(c, cn, cd, cv, se)
-        self.c = c
+            self._pack_coder(c, cn, cd, cv, se, P)
+        for name, v in c.items():
+            if isinstance(v, ConvW):
+                v.p1_ok = name.startswith(_ONE_PRODUCT_PREFIXES)
+        self.c = _upload(c, dev)
+        del self._names
 
     @staticmethod
-    def _pack_coder(c, cn, cd, cv, se):
+    def _pack_coder(c, cn, cd, cv, se, P):
         def gdn(name, g):
             C = g.beta.numel()
-            gamma = _reparam(g.gamma, g.gamma_reparam)  # (C_out, C_in)
-            beta = _reparam(g.beta, g.beta_reparam)
+            gamma = _reparam(P(g, "gamma"), g.gamma_reparam)  # (C_out, C_in)
+            beta = _reparam(P(g, "beta"), g.beta_reparam)
             c[name] = pack_conv(gamma.reshape(C, C, 1, 1), beta)
 
         ga, gs = cd.g_a, cd.g_s
@@ -490,19 +519,54 @@ class _Packed:
             gdn(f"{cn}.gs{i}.igdn", gs[i].igdn)
         cv(f"{cn}.gs9", gs[9][0], shuffle=2)
         ctx = cd.context_prediction
-        c[f"{cn}.ctx"] = pack_conv(ctx.weight.detach() * ctx.mask, ctx.bias)  # MaskedConv2d 'A' (12 live taps)
+        c[f"{cn}.ctx"] = pack_conv(P(ctx, "weight") * P(ctx, "mask"), P(ctx, "bias"))  # MaskedConv2d 'A' (12 live taps)
         ep = cd.entropy_parameters
         cv(f"{cn}.ep0", ep[0], src_layout=[(256, 256), (256, 256)])
         cv(f"{cn}.ep2", ep[2], src_layout=[(ep[2].in_channels, _r(ep[2].in_channels, 4))])
         cv(f"{cn}.ep4", ep[4], src_layout=[(ep[4].in_channels, _r(ep[4].in_channels, 4))])
         eb = cd.entropy_bottleneck
         Cc = eb.quantiles.shape[0]
-        mats = torch.cat([F.softplus(getattr(eb, f"_matrix{i}").detach().float()).reshape(Cc, -1) for i in range(5)], 1)
-        biases = torch.cat([getattr(eb, f"_bias{i}").detach().float().reshape(Cc, -1) for i in range(5)], 1)
-        factors = torch.cat([torch.tanh(getattr(eb, f"_factor{i}").detach().float()).reshape(Cc, -1) for i in range(4)], 1)
-        assert mats.shape[1] == 33 and biases.shape[1] == 13 and factors.shape[1] == 12
+        mats = torch.cat([F.softplus(P(eb, f"_matrix{i}")).reshape(Cc, -1) for i in range(5)], 1)
+        biases = torch.cat([P(eb, f"_bias{i}").reshape(Cc, -1) for i in range(5)], 1)
+        factors = torch.cat([torch.tanh(P(eb, f"_factor{i}")).reshape(Cc, -1) for i in range(4)], 1)
+        if mats.shape[1] != 33 or biases.shape[1] != 13 or factors.shape[1] != 12:
+            raise RuntimeError("EntropyBottleneck: expected filters (3, 3, 3, 3)")
         c[f"{cn}.eb"] = (mats.contiguous(), biases.contiguous(), factors.contiguous(),
-                         eb.quantiles.detach().float()[:, 0, 1].contiguous())
+                         P(eb, "quantiles")[:, 0, 1].contiguous())
+
+
+_PACK_GEN = itertools.count(1)
+
+
+def _upload(c, dev):
+    """Host-packed weights -> one flat device buffer (a single H2D copy); every tensor of `c` becomes a view into it."""
+    slots = []   # (setter, host tensor)
+    for name, v in c.items():
+        if isinstance(v, ConvW):
+            v.wmax = float(v.w.abs().max())   # the split / one-product schemes scale their fp16 blocks by it (tc.attach_f16)
+            slots.append((lambda t, v=v: setattr(v, "w", t), v.w))
+            if v.b is not None:
+                slots.append((lambda t, v=v: setattr(v, "b", t), v.b))
+        elif isinstance(v, tuple):
+            lst = [None] * len(v)
+            c[name] = lst
+            for i, t in enumerate(v):
+                slots.append((lambda t2, lst=lst, i=i: lst.__setitem__(i, t2), t))
+        else:
+            slots.append((lambda t, name=name: c.__setitem__(name, t), v))
+    offs, total = [], 0
+    for _, t in slots:
+        offs.append(total)
+        total += _r(t.numel(), 64)   # 256-byte aligned pieces
+    flat = torch.zeros(total, dtype=torch.float32)
+    for (_, t), o in zip(slots, offs):
+        flat[o:o + t.numel()] = t.reshape(-1)
+    flat = flat.to(dev)
+    for (setter, t), o in zip(slots, offs):
+        setter(flat[o:o + t.numel()].view(t.shape))
+    c["_flat"] = flat
+    c["_gen"] = next(_PACK_GEN)   # plans compare it to know that their cached features / graphs belong to these weights
+    return c
 
 
 def _param_key(m):
@@ -511,20 +575,54 @@ def _param_key(m):
 
 # =============================================================================== the plan
 class _Plan:
-    """Static buffer plan + launch sequence of one P-frame for a fixed (N, H, W) on one device."""
+    """Static buffer plan + launch sequence of one P-frame for a fixed (N, H, W) on one device, and the per-GOP feature
+    caches: everything the reference recomputes for every P-frame from inputs that repeat inside a GOP -
+    FeatureExtract_ref(I-frame) with its pooled descriptors (reference pnet.py:213-217, 225-233) and, per previous
+    reconstruction, the frame-wise front of the multi-frame fusion (conv01, conv02, conv1, layer1.conv1, layer1.spatial_conv3d
+    act on each frame separately: pnet.py:277-290, 309-312) - is keyed on a 128-bit content hash of the reference slice it was
+    computed from and reused while that hash matches.  Results are bit-identical to recomputing (same kernels, same inputs)."""
+
+    GDN_SLOTS = {f"{cn}.{l}": i for i, (cn, l) in enumerate((cn, l) for cn in ("mv", "rs")
+                                                            for l in ("ga0", "ga2", "ga5", "gs2", "gs4", "gs7"))}
 
     def __init__(self, N, H, W, device):
         self.N, self.H, self.W, self.dev = N, H, W, device
         self.lib = L.load()
         self.bufs = {}
-        self.acc = torch.zeros(4, device=device, dtype=torch.float64)  # [mv_y, mv_z, res_y, res_z] sum ln p
+        # per-frame device state, zeroed by one memset: [mv_y, mv_z, res_y, res_z] sum ln p (fp64) | abs-max of every GDN input (fp32)
+        self.fstate = torch.zeros(4 + 8, device=device, dtype=torch.float64)
+        self.acc = self.fstate[:4]
+        self.bpp = torch.zeros(2, device=device, dtype=torch.float32)   # [bpp_mv, bpp_res]
         self.impl = L.IMPL_AUTO
+        self.precision = "exact"
         self.launches = 0
         self.prof = None  # list of (label, macs, bytes, start_event, end_event) when instrumented (bench.py)
         self._order = 0
         self.alternate_order = os.environ.get("TDVC_B200_NO_ALTERNATE") is None   # developer A/B switch
         self.overlap_hyper = os.environ.get("TDVC_B200_NO_OVERLAP") is None       # developer A/B switch
         self._side = None
+        # caches
+        self.if_key = None                       # hash of the I-frame slice whose FeatureExtract_ref output is resident
+        self.ring = [None, None, None]           # hash of the reference slice whose fusion front sits in ring entry e
+        self.ring_used = [0, 0, 0]
+        self.frame_no = 0
+        self.hdev = torch.zeros(8 * N, device=device, dtype=torch.int64)
+        self.hpin = torch.zeros(8 * N, dtype=torch.int64).pin_memory()
+        self.graphs = {}
+        self.cache_hits = 0
+        self.weights_gen = None
+
+    def bind(self, W):
+        """Cached features and captured graphs belong to one set of packed weights."""
+        if self.weights_gen != W["_gen"]:
+            self.invalidate()
+            self.weights_gen = W["_gen"]
+
+    def invalidate(self):
+        """Forget every cached feature (weights changed / buffers were used by another entry point)."""
+        self.if_key = None
+        self.ring = [None, None, None]
+        self.graphs = {}
 
     def _prof_begin(self):
         if self.prof is None:
@@ -533,12 +631,12 @@ class _Plan:
         e.record(torch.cuda.current_stream(self.dev))
         return e
 
-    def _prof_end(self, e0, label, macs=0, nbytes=0):
+    def _prof_end(self, e0, label, macs=0, nbytes=0, products=0):
         if e0 is None:
             return
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record(torch.cuda.current_stream(self.dev))
-        self.prof.append((label, macs, nbytes, e0, e1))
+        self.prof.append((label, macs, nbytes, e0, e1, products))   # products: fp16 MMA products per MAC (0: no MMA)
 
     # ---------------------------------------------------------------- buffers
     def buf(self, name, N, H, W, C, ld=None, zero=False):
@@ -557,35 +655,40 @@ class _Plan:
             self.bufs[key] = t
         return t
 
+    def absmax_ptr(self, layer):
+        return self.fstate.data_ptr() + 32 + 4 * self.GDN_SLOTS[layer]
+
     # ---------------------------------------------------------------- kernel wrappers
     def _st(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def conv(self, srcs, cw, out, stride=1, act=L.ACT_NONE, slope=0.0, res1=None, res2=None, post=L.POST_NONE,
-             mul=None, in_square=False, impl=None, planar=False):
-        """planar=True: `out` is a plain (N, cout, Ho, Wo) tensor written as NCHW planes (no shuffle / residual)."""
+             mul=None, in_square=False, impl=None, planar=False, absmax_out=None, absmax_in=None, products=None):
+        """planar=True: `out` is a plain (N, cout, Ho, Wo) tensor written as NCHW planes (no shuffle / residual).
+        products: None = by `self.precision` and the layer's stage (ConvW.p1_ok); 0 / 1 force the scheme."""
         p = L.ConvParams()
         s0 = srcs[0]
         cin = 0
         for i, s in enumerate(srcs):
-            assert (s.N, s.H, s.W) == (s0.N, s0.H, s0.W)
+            if (s.N, s.H, s.W) != (s0.N, s0.H, s0.W):
+                raise RuntimeError("conv: sources differ in shape")
             p.src[i] = s.ptr
             sc = _r(s.C, 4)
             p.src_c[i] = sc
             p.src_ld[i] = s.ld
             cin += sc
-        assert cin == cw.cin, (cin, cw.cin)
-        assert stride == cw.stride, (stride, cw.stride)
+        if cin != cw.cin or stride != cw.stride:
+            raise RuntimeError(f"conv: input channels / stride {cin}, {stride} do not match the packed weight ({cw.cin}, {cw.stride})")
         p.n_src = len(srcs)
         p.N, p.H, p.W = s0.N, s0.H, s0.W
         p.Ho = (s0.H + 2 * cw.pad - cw.k) // stride + 1
         p.Wo = (s0.W + 2 * cw.pad - cw.k) // stride + 1
         sh = 2 if cw.shuffle == 2 else 1
         if planar:
-            assert tuple(out.shape) == (s0.N, cw.cout, p.Ho, p.Wo) and out.is_contiguous() and sh == 1
-        else:
-            assert (out.N, out.H, out.W) == (s0.N, p.Ho * sh, p.Wo * sh), ((out.N, out.H, out.W), (p.Ho, p.Wo, sh))
-            assert out.C == (cw.cout // 4 if cw.shuffle == 2 else cw.cout)
+            if tuple(out.shape) != (s0.N, cw.cout, p.Ho, p.Wo) or not out.is_contiguous() or sh != 1:
+                raise RuntimeError("conv: planar output tensor has the wrong shape")
+        elif (out.N, out.H, out.W) != (s0.N, p.Ho * sh, p.Wo * sh) or out.C != (cw.cout // 4 if cw.shuffle == 2 else cw.cout):
+            raise RuntimeError(f"conv: output {(out.N, out.H, out.W, out.C)} does not match {(s0.N, p.Ho * sh, p.Wo * sh, cw.cout)}")
         p.weight = cw.w.data_ptr()
         p.bias = cw.b.data_ptr() if cw.b is not None else None
         p.cin, p.cin_pad, p.cout, p.cout_pad = cw.cin, cw.cin_pad, cw.cout, cw.cout_pad
@@ -605,8 +708,16 @@ class _Plan:
             p.out, p.out_ld = out.ptr, out.ld
         p.shuffle = cw.shuffle
         p.impl = self.impl if impl is None else impl
-        p.weight_f16 = cw.w_f16.data_ptr() if cw.w_f16 is not None else None
-        p.w_shift = cw.w_shift
+        if products is None:
+            products = 1 if (self.precision == "mixed" and cw.p1_ok and cw.w_f16_p1 is not None and p.impl != L.IMPL_SIMT) else 0
+        if products == 1:
+            if cw.w_f16_p1 is None:
+                raise RuntimeError("conv: this layer has no one-product weight blocks")
+            p.products, p.weight_f16, p.w_shift = 1, cw.w_f16_p1.data_ptr(), cw.w_shift_p1
+        else:
+            p.weight_f16 = cw.w_f16.data_ptr() if cw.w_f16 is not None else None
+            p.w_shift = cw.w_shift
+        p.out_absmax, p.in_absmax = absmax_out, absmax_in
         self._order ^= 1          # alternate the tile walk direction between consecutive layers (L2 reuse)
         p.order = self._order if self.alternate_order else 0
         e0 = self._prof_begin()
@@ -615,11 +726,15 @@ class _Plan:
             npx = s0.N * p.Ho * p.Wo
             gdn = post != L.POST_NONE and mul is not None and mul.ptr == s0.ptr   # x is both the conv input and the multiplier
             name = ("gdn" if post == L.POST_GDN else "igdn") if gdn else f"conv{cw.k}x{cw.k}s{stride}"
+            prod = max(self.lib.tdvc_conv2d_products(p), 0)
+            if prod == 1:
+                name += "_p1"
             # algorithmic bytes: inputs + output (+ multiplier / residual rows); a GDN reads x once (1,024 B/px)
             self._prof_end(e0, f"{name}_{cw.cin}to{cw.cout}@{p.Ho}x{p.Wo}",
                            macs=npx * cw.cout * cw.cin_real * cw.k * cw.k,
                            nbytes=4 * (s0.N * s0.H * s0.W * cw.cin_real +
-                                       npx * cw.cout * (1 + (mul is not None and not gdn) + (res1 is not None) + (res2 is not None))))
+                                       npx * cw.cout * (1 + (mul is not None and not gdn) + (res1 is not None) + (res2 is not None))),
+                           products=prod)
         self.launches += 1
         return out
 
@@ -661,12 +776,15 @@ class _Plan:
         lr = dict(act=L.ACT_LRELU, slope=0.01)
         b = lambda nme, h, w, c=128, **kw: self.buf(f"{cn}.{nme}", N, h, w, c, **kw)
 
+        # GDN / IGDN: the layer that produces the GDN input also maintains max |t2| (one atomic per epilogue warp); the GDN
+        # kernel pre-scales x*x by a power of two from it so that the fp16 operands cannot saturate (csrc/conv_tc.cu)
         def rb_stride(i, x, h, w):
+            am = self.absmax_ptr(f"{cn}.ga{i}")
             idt = self.conv([x], W[f"{cn}.ga{i}.skip"], b(f"ga{i}.id", h, w), stride=2)
             t = self.conv([x], W[f"{cn}.ga{i}.conv1"], b(f"ga{i}.t", h, w), stride=2, **lr)
-            t2 = self.conv([t], W[f"{cn}.ga{i}.conv2"], b(f"ga{i}.t2", h, w))
+            t2 = self.conv([t], W[f"{cn}.ga{i}.conv2"], b(f"ga{i}.t2", h, w), absmax_out=am)
             return self.conv([t2], W[f"{cn}.ga{i}.gdn"], b(f"ga{i}.o", h, w), in_square=True, post=L.POST_GDN,
-                             mul=t2, res1=idt)
+                             mul=t2, res1=idt, absmax_in=am)
 
         def rb(pfx, i, x):
             t = self.conv([x], W[f"{cn}.{pfx}{i}.conv1"], b(f"{pfx}{i}.t", x.H, x.W), **lr)
@@ -674,11 +792,12 @@ class _Plan:
 
         def rb_up(i, x):
             h, w = 2 * x.H, 2 * x.W
+            am = self.absmax_ptr(f"{cn}.gs{i}")
             t = self.conv([x], W[f"{cn}.gs{i}.subpel"], b(f"gs{i}.t", h, w), **lr)
-            t2 = self.conv([t], W[f"{cn}.gs{i}.conv"], b(f"gs{i}.t2", h, w))
+            t2 = self.conv([t], W[f"{cn}.gs{i}.conv"], b(f"gs{i}.t2", h, w), absmax_out=am)
             idt = self.conv([x], W[f"{cn}.gs{i}.upsample"], b(f"gs{i}.id", h, w))
             return self.conv([t2], W[f"{cn}.gs{i}.igdn"], b(f"gs{i}.o", h, w), in_square=True, post=L.POST_IGDN,
-                             mul=t2, res1=idt)
+                             mul=t2, res1=idt, absmax_in=am)
 
         # ---- g_a
         a = rb_stride(0, x, H // 2, Wd // 2)
@@ -695,9 +814,10 @@ class _Plan:
         self.call("tdvc_round_half_even", y.ptr, yh.ptr, y.N * y.H * y.W * 128, nbytes=8 * y.N * y.H * y.W * 128)
         # The hyperprior / context / entropy-parameter chain only feeds the bit count (x_hat depends on round(y) alone,
         # SURVEY.md App. A): ~17 small, latency-bound launches at H/16..H/64.  They run on a side stream, concurrently
-        # with the (equally small) first layers of g_s, and are joined before this coder returns.
+        # with the (equally small) first layers of g_s, and are joined before this coder returns.  (Serialised when the
+        # launches are being timed one by one: an event pair on the side stream would time the wait behind a main-stream kernel.)
         main = torch.cuda.current_stream(self.dev)
-        side = self._side_stream() if self.overlap_hyper else None
+        side = self._side_stream() if (self.overlap_hyper and self.prof is None) else None
         if side is not None:
             side.wait_stream(main)
         with torch.cuda.stream(side if side is not None else main):
@@ -755,25 +875,113 @@ class _Plan:
                   nbytes=12 * y.N * y.H * y.W * 128)
         return gp, z, zh
 
+    # ---------------------------------------------------------------- cache keys and the variant of a frame
+    def _variant(self, refs, cache):
+        """Decide, from the content hashes of the four reference slices, what this frame has to compute.
+        Returns (if_miss, assign, misses, keys): assign[j] = ring entry holding the fusion front of refer_frames[:, j + 1];
+        misses = ((entry, j), ...) entries to compute from refer_frames[:, j + 1]."""
+        N, H, Wd = self.N, self.H, self.W
+        if not cache:
+            return True, (0, 1, 2), ((0, 0), (1, 1), (2, 2)), [None] * 4
+        fr = 3 * H * Wd
+        L.check(self.lib.tdvc_slices_hash(refs.data_ptr(), fr, fr, 4 * N, self.hdev.data_ptr(), self._st()), "slices_hash")
+        self.launches += 1
+        self.hpin.copy_(self.hdev, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        hv = self.hpin.view(N, 4, 2).tolist()
+        keys = [tuple((hv[n][j][0], hv[n][j][1]) for n in range(N)) for j in range(4)]
+        if_miss = keys[0] != self.if_key
+        assign, misses, taken = [None] * 3, [], set()
+        for j in range(3):
+            for e in range(3):
+                if self.ring[e] is not None and self.ring[e] == keys[j + 1]:
+                    assign[j] = e
+                    taken.add(e)
+                    break
+        for j in (2, 1, 0):   # newest first: refer_frames[:, 3] is converted to NHWC for the feature extractor anyway
+            if assign[j] is not None:
+                continue
+            same = [e for (e, jj) in misses if keys[jj + 1] == keys[j + 1]]
+            if same:
+                assign[j] = same[0]
+                continue
+            free = [e for e in range(3) if e not in taken]
+            e = min(free, key=lambda q: self.ring_used[q])
+            taken.add(e)
+            assign[j] = e
+            misses.append((e, j))
+        self.cache_hits += (0 if if_miss else 1) + (3 - len(misses))
+        return if_miss, tuple(assign), tuple(misses), keys
+
     # ---------------------------------------------------------------- one P-frame
-    def forward(self, W, x_nchw, refs_nchw, taps=None):
-        """reference pnet.py:26-83 (eval branch).  x (N,3,H,W), refs (N,4,3,H,W) contiguous fp32 CUDA."""
+    def run(self, W, x_nchw, refs_nchw, taps=None, graph=False, cache=True):
+        """reference pnet.py:26-83 (eval branch).  x (N,3,H,W), refs (N,4,3,H,W) contiguous fp32 CUDA.
+        Returns the plan's static (recon (N,3,H,W), bpp [mv, res]) buffers."""
+        N, H, Wd = self.N, self.H, self.W
+        self.launches = 0
+        if_miss, assign, misses, keys = self._variant(refs_nchw, cache)
+        # ---- prologue (eager: reads the caller's tensors): NCHW -> NHWC (ld 4) of what this frame needs
+        imgs = self.buf("imgs", 2 * N, H, Wd, 3, ld=4)        # [0:N] = input, [N:2N] = x^(t-1)
+        ifr = self.buf("iframe", N, H, Wd, 3, ld=4)
+        fr = 3 * H * Wd * 4
+        self.call("tdvc_nchw_to_nhwc", x_nchw.data_ptr(), imgs.ptr, N, 3, H, Wd, 4, nbytes=28 * N * H * Wd)
+        miss_imgs = {}
+        for n in range(N):
+            base = refs_nchw.data_ptr() + n * 4 * fr
+            if if_miss:
+                self.call("tdvc_nchw_to_nhwc", base, ifr.batch(n).ptr, 1, 3, H, Wd, 4, nbytes=28 * H * Wd)
+            self.call("tdvc_nchw_to_nhwc", base + 3 * fr, imgs.batch(N + n).ptr, 1, 3, H, Wd, 4, nbytes=28 * H * Wd)
+            for e, j in misses:
+                if j == 2:
+                    miss_imgs[e] = imgs.batch(N, N)
+                else:
+                    mi = miss_imgs.setdefault(e, self.buf(f"mf.img{j}", N, H, Wd, 3, ld=4))
+                    self.call("tdvc_nchw_to_nhwc", base + (j + 1) * fr, mi.batch(n).ptr, 1, 3, H, Wd, 4, nbytes=28 * H * Wd)
+        variant = (if_miss, assign, tuple((e, j) for e, j in misses), self.impl, self.precision)
+        pre = self.launches
+        if graph and taps is None and self.prof is None:
+            g = self.graphs.get(variant)
+            if g is None:
+                # first frame of this variant: run it eagerly (allocates its buffers), then record it for the next time
+                self.body(W, if_miss, assign, misses, miss_imgs, None)
+                n_body = self.launches - pre
+                graph_obj = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_obj):
+                    self.body(W, if_miss, assign, misses, miss_imgs, None)
+                self.graphs[variant] = (graph_obj, n_body)
+                self.launches = pre + n_body
+            else:
+                g[0].replay()
+                self.launches = pre + g[1]
+        else:
+            self.body(W, if_miss, assign, misses, miss_imgs, taps)
+        # ---- the caches now hold what this frame computed
+        self.frame_no += 1
+        if cache:
+            self.if_key = keys[0]
+            for e, j in misses:
+                self.ring[e] = keys[j + 1]
+            for e in set(assign):
+                self.ring_used[e] = self.frame_no
+        else:
+            self.if_key, self.ring = None, [None, None, None]
+        return self.raw("recon", (N, 3, H, Wd)), self.bpp
+
+    def body(self, W, if_miss, assign, misses, miss_imgs, taps):
+        """Everything of the frame that only touches plan buffers (graph-capturable)."""
         N, H, Wd = self.N, self.H, self.W
         lib = self.lib
         lr1 = dict(act=L.ACT_LRELU, slope=0.1)
-        self.acc.zero_()
         self._order = 0
-        # ---- NCHW -> NHWC (ld 4).  imgs: [x, ref(t-1)] per n, refs4: all four references
-        imgs = self.buf("imgs", 2 * N, H, Wd, 3, ld=4)        # [0:N] = input, [N:2N] = x^(t-1)
-        r123 = self.buf("r123", 3 * N, H, Wd, 3, ld=4)        # per n: x^(t-3), x^(t-2), x^(t-1)
+        self.call("tdvc_zero_bytes", self.fstate.data_ptr(), self.fstate.numel() * 8)
+        self.launches -= 1   # a memset node, not a kernel
+        imgs = self.buf("imgs", 2 * N, H, Wd, 3, ld=4)
         ifr = self.buf("iframe", N, H, Wd, 3, ld=4)
-        self.call("tdvc_nchw_to_nhwc", x_nchw.data_ptr(), imgs.ptr, N, 3, H, Wd, 4, nbytes=28 * N * H * Wd)
-        fr = 3 * H * Wd * 4
-        for n in range(N):
-            base = refs_nchw.data_ptr() + n * 4 * fr
-            self.call("tdvc_nchw_to_nhwc", base, ifr.batch(n).ptr, 1, 3, H, Wd, 4, nbytes=28 * H * Wd)
-            self.call("tdvc_nchw_to_nhwc", base + fr, r123.batch(3 * n).ptr, 3, 3, H, Wd, 4, nbytes=84 * H * Wd)
-            self.call("tdvc_nchw_to_nhwc", base + 3 * fr, imgs.batch(N + n).ptr, 1, 3, H, Wd, 4, nbytes=28 * H * Wd)
+        # ---- per-GOP / per-reference features that missed their cache
+        if if_miss:
+            self.loopfilter_ref(W, ifr)
+        for e, j in misses:
+            self.mcfilter_front(W, miss_imgs[e], e)
         # ---- feature extraction on both images (pnet.py:29-30, 86-96)
         f0 = self.conv([imgs], W["extra_fea.conv_first"], self.buf("fe.0", 2 * N, H, Wd, 64), **lr1)
         feats = self.res_stack(W, "extra_fea.res", 2, f0, "fe", out_last=self.buf("feats", 2 * N, H, Wd, 64))
@@ -814,50 +1022,53 @@ class _Plan:
         e0 = self._prof_begin()
         L.check(lib.tdvc_dcn_nhwc(dp, self._st()), "dcn_nhwc")
         # algorithmic bytes: ref 256 + offsets 576 + masks 288 + out 256 B/px
-        self._prof_end(e0, "dcn_tc" if tc_dcn else "dcn_nhwc", macs=N * H * Wd * 576 * 64, nbytes=N * H * Wd * 1376)
+        self._prof_end(e0, "dcn_tc" if tc_dcn else "dcn_nhwc", macs=N * H * Wd * 576 * 64, nbytes=N * H * Wd * 1376,
+                       products=4 if tc_dcn else 0)
         self.launches += 1
         o2 = self.conv([dcn_out, ref_f], W["mc.conv"], self.buf("mc.o2", N, H, Wd, 64), **lr1)
-        t4 = self.buf("mf.t4", 4 * N, H, Wd, 64)  # per n: [x^(t-3), x^(t-2), x^(t-1) features, prediction1]
-        pred1 = self.buf("pred1", N, H, Wd, 64) if N > 1 else t4.batch(3)
-        self.res_stack(W, "mc.res", 3, o2, "mc", last_res2=dcn_out, out_last=pred1)
+        pred1 = self.res_stack(W, "mc.res", 3, o2, "mc", last_res2=dcn_out, out_last=self.buf("pred1", N, H, Wd, 64))
         # ---- multi-frame fusion (pnet.py:277-293, 309-317)
-        pred = self.mcfilter(W, pred1, r123, t4)
+        pred = self.mcfilter(W, pred1, assign)
         # ---- residual coder (pnet.py:55-67, 76)
         resid = self.buf("resid", N, H, Wd, 64)
         self.call("tdvc_axpby", in_f.ptr, pred.ptr, resid.ptr, N * H * Wd * 64, 1.0, -1.0, nbytes=768 * N * H * Wd)
         rec_f = self.coder(W, "rs", resid, 2, taps, final_res=pred, out=self.buf("rec_f", N, H, Wd, 64))
         # ---- reference-based in-loop filter (pnet.py:213-263) + clamp (:78)
-        recon4 = self.loopfilter(W, rec_f, ifr, taps)
+        recon4 = self.loopfilter(W, rec_f, taps)
         recon = self.raw("recon", (N, 3, H, Wd))
         self.call("tdvc_nhwc_to_nchw", recon4.ptr, recon4.ld, recon.data_ptr(), N, 3, H, Wd, nbytes=28 * N * H * Wd)
         # ---- bpp (pnet.py:38-43, 62-67): sum ln p / (-ln2 * N*H*W), per coder
-        bpp = self.acc.view(2, 2).sum(1) / (-_LN2 * N * H * Wd)
+        self.call("tdvc_bpp_finish", self.acc.data_ptr(), self.bpp.data_ptr(), C.c_double(-1.0 / (_LN2 * N * H * Wd)))
         if taps is not None:
             taps.update({"input_feat": in_f.nchw(), "ref_feat": ref_f.nchw(), "estmv": estmv.nchw(),
                          "mv.x_hat": mv_xhat.nchw(), "mcnet.om": om_nchw.clone() if om_nchw is not None else om.nchw(), "mcnet.dcn_act": dcn_out.nchw(),
                          "prediction1": pred1.nchw(), "prediction": pred.nchw(), "input_residual": resid.nchw(),
                          "recon_feat": rec_f.nchw()})
-        return recon, bpp
 
     def fusion_and_filter(self, W, pred1_nchw, refs_nchw, recf_nchw):
         """BASELINE config 5: the multi-frame feature fusion (reference pnet.py:266-293, 296-317) and the reference-based
         in-loop filter (:187-263) on their own.  pred1 / recf (N,64,H,W), refs (N,4,3,H,W) contiguous fp32 CUDA."""
         N, H, Wd = self.N, self.H, self.W
         self._order = 0
-        r123 = self.buf("r123", 3 * N, H, Wd, 3, ld=4)
+        self.launches = 0
+        self.if_key, self.ring = None, [None, None, None]   # the cache entries are overwritten below
         ifr = self.buf("iframe", N, H, Wd, 3, ld=4)
         fr = 3 * H * Wd * 4
+        imgs = [self.buf(f"mf.img{j}", N, H, Wd, 3, ld=4) for j in range(3)]
         for n in range(N):
             base = refs_nchw.data_ptr() + n * 4 * fr
             self.call("tdvc_nchw_to_nhwc", base, ifr.batch(n).ptr, 1, 3, H, Wd, 4)
-            self.call("tdvc_nchw_to_nhwc", base + fr, r123.batch(3 * n).ptr, 3, 3, H, Wd, 4)
-        t4 = self.buf("mf.t4", 4 * N, H, Wd, 64)
-        pred1 = self.buf("pred1", N, H, Wd, 64) if N > 1 else t4.batch(3)
+            for j in range(3):
+                self.call("tdvc_nchw_to_nhwc", base + (j + 1) * fr, imgs[j].batch(n).ptr, 1, 3, H, Wd, 4)
+        pred1 = self.buf("pred1", N, H, Wd, 64)
         self.call("tdvc_nchw_to_nhwc", pred1_nchw.data_ptr(), pred1.ptr, N, 64, H, Wd, 64)
         rec_f = self.buf("rec_f", N, H, Wd, 64)
         self.call("tdvc_nchw_to_nhwc", recf_nchw.data_ptr(), rec_f.ptr, N, 64, H, Wd, 64)
-        pred = self.mcfilter(W, pred1, r123, t4)
-        recon4 = self.loopfilter(W, rec_f, ifr, None)
+        for j in range(3):
+            self.mcfilter_front(W, imgs[j], j)
+        pred = self.mcfilter(W, pred1, (0, 1, 2))
+        self.loopfilter_ref(W, ifr)
+        recon4 = self.loopfilter(W, rec_f, None)
         pred_out = self.raw("c5.pred", (N, 64, H, Wd))
         recon = self.raw("recon", (N, 3, H, Wd))
         self.call("tdvc_nhwc_to_nchw", pred.ptr, pred.ld, pred_out.data_ptr(), N, 64, H, Wd)
@@ -900,7 +1111,6 @@ class _Plan:
     def spynet(self, W, imgs, taps):
         """reference flownet.py:82-140 with ref = input image, supp = x^(t-1) (pnet.py:162)."""
         N, H, Wd = self.N, self.H, self.W
-        assert H % 32 == 0 and Wd % 32 == 0
         pyr = [imgs]
         for l in range(5):
             s = pyr[-1]
@@ -924,58 +1134,82 @@ class _Plan:
                 taps[f"spynet.flow{lvl}"] = flow.nchw()
         return flow
 
-    def mcfilter(self, W, pred1, r123, t4):
+    # ---- multi-frame fusion (reference LoopFilter, pnet.py:266-293 + Bottleneck3D :296-317).  Every layer in front of the
+    # temporal convolution acts on one frame at a time (Conv3d kernels (1,3,3)), so the front of a reference frame -
+    # a = lrelu(conv1(conv02(lrelu(conv01 x)))) and s = spatial(lrelu(layer1.conv1 a)) - is computed once per reconstruction and
+    # kept in a 3-entry ring for the three P-frames that reference it.
+    def mcfilter_front(self, W, img, e):
         N, H, Wd = self.N, self.H, self.W
         lr1 = dict(act=L.ACT_LRELU, slope=0.1)
-        b = lambda nme, n, c=64: self.buf("mf." + nme, n, H, Wd, c)
-        r = self.conv([r123], W["mf.conv01"], b("r01", 3 * N), **lr1)
-        if N == 1:
-            self.conv([r], W["mf.conv02"], t4.batch(0, 3))
-        else:
-            for n in range(N):
-                self.conv([r.batch(3 * n, 3)], W["mf.conv02"], t4.batch(4 * n, 3))
-                self.call("tdvc_axpby", pred1.batch(n).ptr, pred1.batch(n).ptr, t4.batch(4 * n + 3).ptr, H * Wd * 64, 1.0, 0.0)
-        a = self.conv([t4], W["mf.conv1"], b("a", 4 * N), **lr1)
-        c1 = self.conv([a], W["mf.l1.conv1"], b("c1", 4 * N), **lr1)
-        s = self.conv([c1], W["mf.l1.spatial"], b("s", 4 * N))
-        tmp = b("tmp", N)
-        o = b("c1", 4 * N)  # reuse
-        for n in range(N):
-            self.conv([s.batch(4 * n), s.batch(4 * n + 1), s.batch(4 * n + 2)], W["mf.l1.temporal"], tmp.batch(n))
-            self.call("tdvc_bcast_add_lrelu", s.batch(4 * n).ptr, tmp.batch(n).ptr, o.batch(4 * n).ptr, 4, H * Wd * 64, 0.1,
-                      nbytes=9 * 256 * H * Wd)  # read 4 frames + the temporal term, write 4 frames
-        bo = self.conv([o], W["mf.l1.conv3"], b("s", 4 * N), res1=a)  # reuse `s`
-        fu = b("fu", N)
-        for n in range(N):
-            self.conv([bo.batch(4 * n + t) for t in range(4)], W["mf.fusion"], fu.batch(n), **lr1)
+        b = lambda nme, c=64: self.buf("mf." + nme, N, H, Wd, c)
+        r = self.conv([img], W["mf.conv01"], b("r01"), **lr1)
+        f = self.conv([r], W["mf.conv02"], b("f02"))
+        a = self.conv([f], W["mf.conv1"], b(f"a.{e}"), **lr1)
+        c1 = self.conv([a], W["mf.l1.conv1"], b("c1"), **lr1)
+        return self.conv([c1], W["mf.l1.spatial"], b(f"s.{e}"))
+
+    def mcfilter(self, W, pred1, assign):
+        N, H, Wd = self.N, self.H, self.W
+        lr1 = dict(act=L.ACT_LRELU, slope=0.1)
+        b = lambda nme, c=64: self.buf("mf." + nme, N, H, Wd, c)
+        # the prediction is the 4th "frame" of the stack (pnet.py:286-288)
+        a_p = self.conv([pred1], W["mf.conv1"], b("a.p"), **lr1)
+        c1 = self.conv([a_p], W["mf.l1.conv1"], b("c1"), **lr1)
+        s_p = self.conv([c1], W["mf.l1.spatial"], b("s.p"))
+        A = [b(f"a.{e}") for e in assign] + [a_p]
+        S = [b(f"s.{e}") for e in assign] + [s_p]
+        # temporal (3,1,1) stride 3: one output step from frames 0..2, broadcast-added to all four (pnet.py:313-314)
+        tmp = self.conv(S[:3], W["mf.l1.temporal"], b("tmp"))
+        bo, done = [], {}
+        for t in range(4):
+            k = assign[t] if t < 3 else "p"
+            if k not in done:   # duplicated references (GOP warm-up, predict.py:55-60) share their entry
+                o = b(f"o.{k}")
+                self.call("tdvc_bcast_add_lrelu", S[t].ptr, tmp.ptr, o.ptr, 1, N * H * Wd * 64, 0.1, nbytes=3 * 256 * N * H * Wd)
+                done[k] = self.conv([o], W["mf.l1.conv3"], b(f"bo.{k}"), res1=A[t])
+            bo.append(done[k])
+        fu = self.conv(bo, W["mf.fusion"], b("fu"), **lr1)
         return self.se(fu, W["mf.attn"], self.buf("pred", N, H, Wd, 64), res=pred1)
 
-    def loopfilter(self, W, rec_f, ifr, taps):
+    # ---- reference-based in-loop filter (reference FeatureFix, pnet.py:187-263)
+    def _ff_geometry(self):
+        H, Wd = self.H, self.W
+        scale = int(H / 8)  # eval branch of pnet.py:220-223
+        ph, pw = H // scale, Wd // scale
+        PH, PW = (ph + 3) // 3 + 1, (pw + 3) // 3 + 1
+        bs = 3 * scale
+        if (H + bs) // bs + 1 != PH or (Wd + bs) // bs + 1 != PW:
+            raise RuntimeError(f"FeatureFix: patch grid {PH}x{PW} does not match the block grid of a {H}x{Wd} frame")
+        return scale, ph, pw, PH * PW
+
+    def _fe(self, W, pfx, x, tag):
+        b = lambda nme, c=64: self.buf("lf." + nme, self.N, self.H, self.W, c)
+        x1 = self.conv([x], W[pfx + ".first"], b(tag + ".x1"), act=L.ACT_LRELU, slope=0.01)
+        y = self.res_stack(W, pfx + ".body", 2, x1, "lf." + tag)
+        return self.conv([y], W[pfx + ".last"], b(tag + ".f"), res1=x1)
+
+    def loopfilter_ref(self, W, ifr):
+        """FeatureExtract_ref(I-frame), its pooled map and patch descriptors: once per GOP."""
+        N, H, Wd = self.N, self.H, self.W
+        scale, ph, pw, P = self._ff_geometry()
+        f_ref = self._fe(W, "lf.fe_ref", ifr, "ref")
+        p_ref = self.raw("lf.p_ref", (N, ph, pw, 64))
+        self.call("tdvc_avgpool_scale", f_ref.ptr, f_ref.ld, p_ref.data_ptr(), N, H, Wd, 64, scale, nbytes=256 * N * H * Wd)
+        self.call("tdvc_ff_descriptors", p_ref.data_ptr(), self.raw("lf.d_ref", (N, P, 576)).data_ptr(), N, ph, pw, 64)
+
+    def loopfilter(self, W, rec_f, taps):
         N, H, Wd = self.N, self.H, self.W
         lr1 = dict(act=L.ACT_LRELU, slope=0.1)
         b = lambda nme, c=64: self.buf("lf." + nme, N, H, Wd, c)
-
-        def fe(pfx, x, tag):
-            x1 = self.conv([x], W[pfx + ".first"], b(tag + ".x1"), act=L.ACT_LRELU, slope=0.01)
-            y = self.res_stack(W, pfx + ".body", 2, x1, "lf." + tag)
-            return self.conv([y], W[pfx + ".last"], b(tag + ".f"), res1=x1)
-
-        f_in = fe("lf.fe_in", rec_f, "in")
-        f_ref = fe("lf.fe_ref", ifr, "ref")
-        scale = int(H / 8)  # eval branch of pnet.py:220-223
-        ph, pw = H // scale, Wd // scale
+        scale, ph, pw, P = self._ff_geometry()
+        f_in = self._fe(W, "lf.fe_in", rec_f, "in")
+        f_ref = b("ref.f")
         p_in = self.raw("lf.p_in", (N, ph, pw, 64))
         p_ref = self.raw("lf.p_ref", (N, ph, pw, 64))
         self.call("tdvc_avgpool_scale", f_in.ptr, f_in.ld, p_in.data_ptr(), N, H, Wd, 64, scale, nbytes=256 * N * H * Wd)
-        self.call("tdvc_avgpool_scale", f_ref.ptr, f_ref.ld, p_ref.data_ptr(), N, H, Wd, 64, scale, nbytes=256 * N * H * Wd)
-        PH, PW = (ph + 3) // 3 + 1, (pw + 3) // 3 + 1
-        P = PH * PW
-        bs = 3 * scale
-        assert (H + bs) // bs + 1 == PH and (Wd + bs) // bs + 1 == PW
         d_in = self.raw("lf.d_in", (N, P, 576))
         d_ref = self.raw("lf.d_ref", (N, P, 576))
         self.call("tdvc_ff_descriptors", p_in.data_ptr(), d_in.data_ptr(), N, ph, pw, 64)
-        self.call("tdvc_ff_descriptors", p_ref.data_ptr(), d_ref.data_ptr(), N, ph, pw, 64)
         ind = self.raw("lf.ind", (N, P), torch.int32)
         sim = self.raw("lf.sim", (N, P, P)) if taps is not None else None
         self.call("tdvc_ff_match", d_in.data_ptr(), d_ref.data_ptr(), ind.data_ptr(),
@@ -1002,6 +1236,15 @@ class _Plan:
 
 
 # =============================================================================== the module
+class _Origin:
+    """Shared by a module and its nn.DataParallel replicas (replicate() copies __dict__ shallowly): lets a replica find the
+    module that owns the master parameters, whose versions key the packed-weight cache."""
+
+    def __init__(self, module):
+        self.ref = weakref.ref(module)
+        self.lock = threading.Lock()
+
+
 class VideoCompressor(nn.Module):
     """Drop-in for reference main/model/pnet.py::VideoCompressor (constructor `:16-24`, forward `:26-83`)."""
 
@@ -1014,33 +1257,76 @@ class VideoCompressor(nn.Module):
         self.mcnet = _MCNet(3)
         self.loopfilter = _FeatureFix()
         self.mcfilter = _LoopFilter()
-        self._packed = {}
-        self._plans = {}
-        self._graphs = {}
+        self._packed = {}              # device -> (key, packed weights)
+        self._plans = {}               # (device, N, H, W) -> _Plan
+        self._origin = _Origin(self)
         self.conv_impl = L.IMPL_AUTO   # 0 auto (tcgen05 where supported), 1 exact fp32 SIMT, 2 force tcgen05
+        self.precision = "exact"       # "exact": fp32-class split MMA everywhere; "mixed": one fp16 product behind the last quantiser
         self.use_cuda_graph = False
+        self.cache_features = True     # per-GOP feature caches (results are bit-identical either way)
         self.last_launches = 0
 
-    # -- packing / planning caches are per device (nn.DataParallel replicas each get their own)
+    # the packed weights, plans and the replica link are runtime state: copies and pickles start without them
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_packed"], d["_plans"], d["_origin"] = {}, {}, None
+        return d
+
+    def __setstate__(self, d):
+        super().__setstate__(d)
+        self._packed, self._plans, self._origin = {}, {}, _Origin(self)
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__setstate__(copy.deepcopy(self.__getstate__(), memo))
+        return new
+
+    # -- nn.DataParallel: replicas are shallow copies made for every forward; their parameters are fresh broadcast copies.  The
+    #    packed weights are therefore keyed on the ORIGINAL module's parameter versions and built from its parameters
+    def _source(self):
+        if getattr(self, "_is_replica", False):
+            src = self._origin.ref()
+            if src is not None:
+                return src
+        return self
+
     def _weights(self, dev):
-        key = _param_key(self)
-        pk = self._packed.get(dev)
-        if pk is None or pk.key != key:
-            with torch.no_grad():
-                pk = _Packed(self)
-                from tdvc_b200 import tc
-                tc.attach_f16(pk.c)
-                tc.attach_dcn_f16(pk.c, "mc.dcn.w", 64, 8)
-            self._packed[dev] = pk
-            self._graphs = {k: v for k, v in self._graphs.items() if k[0] != dev}
+        src = self._source()
+        key = _param_key(src)
+        with self._origin.lock:
+            ent = self._packed.get(dev)
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        with torch.no_grad(), torch.cuda.device(dev):
+            pk = _Packed(src, dev)
+            from tdvc_b200 import tc
+            tc.attach_f16(pk.c)
+            tc.attach_dcn_f16(pk.c, "mc.dcn.w", 64, 8)
+        with self._origin.lock:
+            self._packed[dev] = (key, pk.c)
         return pk.c
 
     def _plan(self, N, H, W, dev):
         k = (dev, N, H, W)
-        p = self._plans.get(k)
-        if p is None:
-            p = self._plans[k] = _Plan(N, H, W, dev)
+        with self._origin.lock:
+            p = self._plans.get(k)
+            if p is None:
+                p = self._plans[k] = _Plan(N, H, W, dev)
         return p
+
+    def _check(self, a, b, c_a):
+        if not a.is_cuda:
+            raise RuntimeError("tdvc_b200.VideoCompressor runs on CUDA (sm_100a) only; there is no CPU fallback")
+        N, C_, H, W = a.shape
+        if C_ != c_a or b.shape != (N, 4, 3, H, W):
+            raise RuntimeError(f"expected input (N,{c_a},H,W) and refer_frames (N,4,3,H,W), got {tuple(a.shape)} and {tuple(b.shape)}")
+        if H % 64 or W % 64:
+            raise RuntimeError("H and W must be multiples of 64 (pad as reference main/utils/utils.py:59-87 does)")
+        if self.precision not in ("exact", "mixed"):
+            raise RuntimeError(f"precision must be 'exact' or 'mixed', not {self.precision!r}")
+        return N, H, W
 
     def forward(self, input_image, refer_frames, enabled_amp=False, is_compress=False, taps=None):
         """Same contract as reference pnet.py:26-83.  `enabled_amp` is accepted and ignored: the kernels
@@ -1049,74 +1335,35 @@ class VideoCompressor(nn.Module):
             raise NotImplementedError("entropy coding (is_compress=True) is a 'next' row (SURVEY.md 8f.3)")
         if self.training:
             raise NotImplementedError("training mode (noise quantisation / backward) is a 'next' row (SURVEY.md 8f.1)")
-        if not input_image.is_cuda:
-            raise RuntimeError("tdvc_b200.VideoCompressor runs on CUDA (sm_100a) only; there is no CPU fallback")
-        N, C, H, W = input_image.shape
-        if C != 3 or refer_frames.shape != (N, 4, 3, H, W):
-            raise RuntimeError(f"expected input (N,3,H,W) and refer_frames (N,4,3,H,W), got {tuple(input_image.shape)} "
-                               f"and {tuple(refer_frames.shape)}")
-        if H % 64 or W % 64:
-            raise RuntimeError("H and W must be multiples of 64 (pad as reference main/utils/utils.py:59-87 does)")
+        N, H, W = self._check(input_image, refer_frames, 3)
         dev = input_image.device
         with torch.cuda.device(dev), torch.no_grad():
             x = input_image.detach().float().contiguous()
             refs = refer_frames.detach().float().contiguous()
             Wt = self._weights(dev)
             plan = self._plan(N, H, W, dev)
-            plan.impl = self.conv_impl
-            if self.use_cuda_graph and taps is None:
-                recon, bpp = self._graph_forward(plan, Wt, x, refs)
-            else:
-                plan.launches = 0
-                recon, bpp = plan.forward(Wt, x, refs, taps)
-                self.last_launches = plan.launches
-            recon = recon.clone()
-            bpp = bpp.float()
+            plan.bind(Wt)
+            plan.impl, plan.precision = self.conv_impl, self.precision
+            recon, bpp = plan.run(Wt, x, refs, taps, graph=self.use_cuda_graph, cache=self.cache_features)
+            self.last_launches = plan.launches
+            recon, bpp = recon.clone(), bpp.clone()   # the plan's buffers are overwritten by the next frame
         # reference returns (recon, bpp_res.view(-1), bpp_mv.view(-1))  (pnet.py:82-83)
-        return recon, bpp[1].view(-1), bpp[0].view(-1)
+        return recon, bpp[1:2], bpp[0:1]
 
     def fusion_and_filter(self, prediction1, refer_frames, recon_feat):
         """BASELINE config 5 entry: `mcfilter` (reference pnet.py:53) on `prediction1` and `loopfilter` + clamp (:77-78) on
         `recon_feat`, with the 4 reference frames.  Returns (prediction (N,64,H,W), recon (N,3,H,W))."""
-        if not prediction1.is_cuda:
-            raise RuntimeError("tdvc_b200.VideoCompressor runs on CUDA (sm_100a) only; there is no CPU fallback")
-        N, C, H, W = prediction1.shape
-        if C != 64 or recon_feat.shape != prediction1.shape or refer_frames.shape != (N, 4, 3, H, W):
+        N, H, W = self._check(prediction1, refer_frames, 64)
+        if recon_feat.shape != prediction1.shape:
             raise RuntimeError("expected prediction1 / recon_feat (N,64,H,W) and refer_frames (N,4,3,H,W)")
-        if H % 64 or W % 64:
-            raise RuntimeError("H and W must be multiples of 64")
         dev = prediction1.device
         with torch.cuda.device(dev), torch.no_grad():
             Wt = self._weights(dev)
             plan = self._plan(N, H, W, dev)
-            plan.impl = self.conv_impl
-            plan.launches = 0
+            plan.bind(Wt)
+            plan.impl, plan.precision = self.conv_impl, self.precision
             pred, recon = plan.fusion_and_filter(Wt, prediction1.detach().float().contiguous(),
                                                  refer_frames.detach().float().contiguous(),
                                                  recon_feat.detach().float().contiguous())
             self.last_launches = plan.launches
             return pred.clone(), recon.clone()
-
-    def _graph_forward(self, plan, Wt, x, refs):
-        k = (x.device, plan.N, plan.H, plan.W, self.conv_impl)
-        g = self._graphs.get(k)
-        if g is None:
-            sx, sr = torch.empty_like(x), torch.empty_like(refs)
-            sx.copy_(x)
-            sr.copy_(refs)
-            s = torch.cuda.Stream(device=x.device)
-            s.wait_stream(torch.cuda.current_stream(x.device))
-            with torch.cuda.stream(s):  # warm-up run allocates every buffer outside capture
-                plan.forward(Wt, sx, sr, None)
-            torch.cuda.current_stream(x.device).wait_stream(s)
-            graph = torch.cuda.CUDAGraph()
-            plan.launches = 0
-            with torch.cuda.graph(graph):
-                out = plan.forward(Wt, sx, sr, None)
-            g = self._graphs[k] = (graph, sx, sr, out, plan.launches)
-        graph, sx, sr, out, nl = g
-        sx.copy_(x)
-        sr.copy_(refs)
-        graph.replay()
-        self.last_launches = nl
-        return out

@@ -24,13 +24,16 @@ def plan(dev):
 
 
 def _conv_case(plan, dev, cin_list, cout, k, stride, H, W, N=1, act=0, slope=0.0, shuffle=0, res=False, impl=1, seed=0,
-               pad=None):
+               pad=None, products=0):
     from tdvc_b200.model import Act, pack_conv
     torch.manual_seed(seed)
     cin = sum(cin_list)
     conv = torch.nn.Conv2d(cin, cout, k, stride, k // 2 if pad is None else pad)
     xs = [torch.randn(N, c, H, W) for c in cin_list]
-    want = conv(torch.cat(xs, 1))
+    if products == 1:   # the one-product scheme multiplies fp16(w) by fp16(x) exactly and accumulates in fp32
+        want = F.conv2d(torch.cat(xs, 1).half().float(), conv.weight.half().float(), conv.bias, stride, k // 2 if pad is None else pad)
+    else:
+        want = conv(torch.cat(xs, 1))
     if act == 1:
         want = F.relu(want)
     elif act == 2:
@@ -43,11 +46,11 @@ def _conv_case(plan, dev, cin_list, cout, k, stride, H, W, N=1, act=0, slope=0.0
     layout = [(c, (c + 3) // 4 * 4) for c in cin_list]
     cw = pack_conv(conv.weight.to(dev), conv.bias.to(dev), src_layout=layout, shuffle=shuffle, pad=pad, stride=stride)
     from tdvc_b200 import tc
-    tc.attach_f16({"w": cw})
+    tc.attach_f16({"w": cw}, one_product=products == 1)
     srcs = [Act.from_nchw(x.to(dev), ld=(x.shape[1] + 3) // 4 * 4) for x in xs]
     out = Act.alloc(N, want.shape[2], want.shape[3], want.shape[1], dev, ld=(want.shape[1] + 3) // 4 * 4 if want.shape[1] % 4 else None)
     r1 = Act.from_nchw(r.to(dev)) if res else None
-    plan.conv(srcs, cw, out, stride=stride, act=act, slope=slope, res1=r1, impl=impl)
+    plan.conv(srcs, cw, out, stride=stride, act=act, slope=slope, res1=r1, impl=impl, products=products)
     torch.cuda.synchronize()
     return out.nchw().cpu(), want.detach()
 
@@ -113,6 +116,74 @@ def test_conv2d_tcgen05_vs_torch(plan, dev, idx):
     got, want = _conv_case(plan, dev, cin_list, cout, k, stride, H, W, impl=2, seed=100 + idx, **kw)
     assert got.shape == want.shape
     assert (got - want).abs().max() <= 2e-4 * max(1.0, want.abs().max().item())
+
+
+P1_CASES = [
+    # one fp16 MMA product (TdvcConvParams::products = 1): cin_list, cout, k, stride, H, W, kwargs
+    ([64], 64, 3, 1, 40, 56, dict(act=1)),                              # 64 channels x 2 row phases per item
+    ([64], 64, 3, 1, 17, 23, dict(act=2, slope=0.1, res=True)),        # ragged edges, odd height: last row has phase 0 only
+    ([64], 64, 3, 1, 129, 9, dict(res=True, N=2)),                      # three 64-row items
+    ([64, 64], 64, 3, 1, 33, 16, dict(act=2, slope=0.1)),              # featfusion: four K units from two sources
+    ([64], 48, 3, 1, 20, 20, dict()),                                   # fewer channels than a phase holds
+    ([128], 128, 3, 1, 24, 24, dict(act=2, slope=0.01, res=True)),     # 128 channels per item, one phase
+    ([128], 512, 3, 1, 8, 12, dict(shuffle=2, act=2, slope=0.01)),     # subpel conv
+    ([128], 256, 3, 1, 16, 16, dict(shuffle=2)),                        # g_s[9]
+    ([128], 128, 1, 1, 19, 21, dict(pad=0)),                            # 1x1
+]
+
+
+@pytest.mark.parametrize("idx", range(len(P1_CASES)))
+def test_conv2d_one_product_vs_torch(plan, dev, idx):
+    """products = 1: against the fp32 convolution of the fp16-rounded operands (what one fp16 MMA with fp32 accumulation
+    computes): only the summation order differs."""
+    cin_list, cout, k, stride, H, W, kw = P1_CASES[idx]
+    got, want = _conv_case(plan, dev, cin_list, cout, k, stride, H, W, impl=2, seed=400 + idx, products=1, **kw)
+    assert got.shape == want.shape
+    assert (got - want).abs().max() <= 3e-5 * max(1.0, want.abs().max().item())
+
+
+def test_conv2d_out_absmax(plan, dev):
+    """TdvcConvParams::out_absmax: max |v| over everything the layer stored, on the tensor-core and the SIMT kernel."""
+    from tdvc_b200.model import Act, pack_conv
+    from tdvc_b200 import tc
+    torch.manual_seed(5)
+    for cout, H, W in ((128, 21, 19), (64, 33, 10)):
+        conv = torch.nn.Conv2d(64, cout, 3, 1, 1)
+        x = torch.randn(2, 64, H, W)
+        cw = pack_conv(conv.weight.to(dev), conv.bias.to(dev), src_layout=[(64, 64)])
+        tc.attach_f16({"w": cw})
+        out = Act.alloc(2, H, W, cout, dev)
+        for impl in (1, 2):
+            am = torch.zeros(1, device=dev)
+            plan.conv([Act.from_nchw(x.to(dev))], cw, out, impl=impl, absmax_out=am.data_ptr())
+            assert am.item() == out.nchw().abs().max().item()
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("amp", [300.0, 3000.0])
+def test_gdn_large_activations(plan, dev, inverse, amp):
+    """|x| > 255 made x*x saturate the fp16 operands of the tensor-core GDN.  With `in_absmax` (maintained by the
+    producing layer's epilogue) x*x is pre-scaled by an exact power of two: the result follows the fp32 reference."""
+    from oracle.compressai_port import GDN
+    from tdvc_b200 import lib as L
+    from tdvc_b200 import tc
+    from tdvc_b200.model import Act, _reparam, pack_conv
+    torch.manual_seed(9)
+    g = GDN(128, inverse=inverse)
+    g.beta.data.add_(torch.rand(128) * 0.5)
+    g.gamma.data.add_(torch.rand(128, 128) * 0.02)
+    x = torch.randn(1, 128, 19, 21) * amp
+    want = g(x)
+    cw = pack_conv(_reparam(g.gamma, g.gamma_reparam).reshape(128, 128, 1, 1), _reparam(g.beta, g.beta_reparam))
+    cw.w, cw.b = cw.w.to(dev), cw.b.to(dev)
+    tc.attach_f16({"w": cw})
+    xa = Act.from_nchw(x.to(dev))
+    am = x.abs().max().reshape(1).to(dev)
+    out = Act.alloc(1, 19, 21, 128, dev)
+    for impl, tol in ((1, 2e-5), (2, 1e-4)):
+        plan.conv([xa], cw, out, in_square=True, post=L.POST_IGDN if inverse else L.POST_GDN, mul=xa, impl=impl,
+                  absmax_in=am.data_ptr())
+        assert (out.nchw().cpu() - want).abs().max() < tol * want.abs().max(), impl
 
 
 SMALL_CASES = [
