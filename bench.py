@@ -274,7 +274,7 @@ def main():
         stats = torch.zeros(7, device=dev, dtype=torch.float64)
         sse = torch.zeros(1, device=dev, dtype=torch.float64)
         it = frame_stream(src)
-        refs = None
+        refs = None   # tdvc_b200.gop.RefBuffer of the running GOP
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pin_out = torch.empty((1, 3, hh, ww), dtype=torch.float32).pin_memory() if host_io else None
         pin_bpp = torch.empty(2, dtype=torch.float32).pin_memory() if host_io else None
@@ -288,14 +288,19 @@ def main():
                 ev0.record()
             g, t = next(it)
             if t == 1:
-                refs = [g[0:1].to(dev, non_blocking=True) if host_io else g[0:1]]
+                refs = G.RefBuffer(g[0:1].to(dev, non_blocking=True) if host_io else g[0:1])
             x = g[t:t + 1].to(dev, non_blocking=True) if host_io else g[t:t + 1]
-            recon, bpp_res, bpp_mv = net(x, G.reference_window(refs), False)
+            window, keys = refs.window()
+            if host_io:
+                # end to end: the reference-facing call exactly as tools/predict.py:64-65 makes it (the feature caches are keyed
+                # on the device-side content hash of the reference slices: one host synchronisation per frame)
+                recon, bpp_res, bpp_mv = net(x, window, False)
+            else:
+                # resident leg: through the GOP driver's call (tdvc_b200/gop.py), which passes the frame identities it knows
+                recon, bpp_res, bpp_mv = net(x, window, False, ref_keys=keys)
             if i >= n_warm:
                 launches += net.last_launches
-            refs.append(recon)
-            if len(refs) > 4:
-                refs = [refs[0]] + refs[-3:]
+            refs.push(recon)
             if host_io:
                 pin_out.copy_(recon, non_blocking=True)
                 pin_bpp.copy_(torch.cat([bpp_res, bpp_mv]), non_blocking=True)

@@ -197,6 +197,18 @@ int tdvc_se_apply(const float* x, int ld, float* partial, int nblk, const float*
 int tdvc_eb_bits(const float* z, float* z_hat, const float* mats, const float* biases, const float* factors,
                  const float* medians, int64_t npix, int C, double* acc, void* stream);
 int tdvc_gc_bits(const float* y, const float* params, int params_ld, int64_t npix, int C, double* acc, void* stream);
+/* Training-mode forms (`self.training`, reference pnet.py:26-83 with compressai's quantize(.., "noise")): the quantisers add
+ * uniform noise instead of rounding.  eb_bits_noise: z_tilde = z + noise, likelihood at z_tilde.  gc_bits_noise: likelihood of
+ * y + noise under (scales, means).  `noise` has the layout of the latent it is added to.
+ * eb_aux_loss: EntropyBottleneck.loss() = sum |logits_cumulative(quantiles) - target| (quantiles [C][3], target3 [3]) -> *out.
+ * uniform_noise: out[i] ~ U[-0.5, 0.5) from Philox4x32-10 keyed by `seed`, sub-stream `stream_id`, counter i / 4.          */
+int tdvc_eb_bits_noise(const float* z, const float* noise, float* z_tilde, const float* mats, const float* biases,
+                       const float* factors, int64_t npix, int C, double* acc, void* stream);
+int tdvc_gc_bits_noise(const float* y, const float* noise, const float* params, int params_ld, int64_t npix, int C,
+                       double* acc, void* stream);
+int tdvc_eb_aux_loss(const float* mats, const float* biases, const float* factors, const float* quantiles,
+                     const float* target3, int C, float* out, void* stream);
+int tdvc_uniform_noise(float* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream);
 
 /* ---- reference-based in-loop filter pieces (reference pnet.py:213-257) ----
  * avgpool_scale: nn.AvgPool2d(scale) -> (N, H/scale, W/scale, C)                         (:219-226)

@@ -51,8 +51,9 @@ __device__ __forceinline__ float eb_logits(const EbSmem& s, int c, float v) {
   return mr[0] * h[0] + mr[C] * h[1] + mr[2 * C] * h[2] + s.b[12 * C + c];
 }
 
-__global__ void eb_bits_kernel(const float* __restrict__ z, float* __restrict__ z_hat, const float* __restrict__ mats,
-                               const float* __restrict__ biases, const float* __restrict__ factors,
+// noise != nullptr: training-mode quantisation, z_hat = z + noise (compressai quantize(.., "noise"): the medians are not used)
+__global__ void eb_bits_kernel(const float* __restrict__ z, const float* __restrict__ noise, float* __restrict__ z_hat,
+                               const float* __restrict__ mats, const float* __restrict__ biases, const float* __restrict__ factors,
                                const float* __restrict__ medians, int64_t total, int C, double* acc) {
   extern __shared__ float sh[];
   float* sm = sh;                // [33][C]
@@ -70,7 +71,7 @@ __global__ void eb_bits_kernel(const float* __restrict__ z, float* __restrict__ 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int c = (int)(i % C);
     const float med = smed[c];
-    const float q = __fadd_rn(rintf(__fsub_rn(z[i], med)), med);
+    const float q = noise != nullptr ? __fadd_rn(z[i], noise[i]) : __fadd_rn(rintf(__fsub_rn(z[i], med)), med);
     z_hat[i] = q;
     const float lower = eb_logits(s, c, q - 0.5f);
     const float upper = eb_logits(s, c, q + 0.5f);
@@ -83,8 +84,9 @@ __global__ void eb_bits_kernel(const float* __restrict__ z, float* __restrict__ 
   block_accumulate(sum, acc);
 }
 
-__global__ void gc_bits_kernel(const float* __restrict__ y, const float* __restrict__ params, int params_ld,
-                               int64_t total, int C, double* acc) {
+// noise != nullptr: training mode, the likelihood is evaluated at y + noise instead of the dequantised value
+__global__ void gc_bits_kernel(const float* __restrict__ y, const float* __restrict__ noise, const float* __restrict__ params,
+                               int params_ld, int64_t total, int C, double* acc) {
   double sum = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const float kc = -0.70710678118654752440f;  // -(2 ** -0.5)
@@ -94,7 +96,8 @@ __global__ void gc_bits_kernel(const float* __restrict__ y, const float* __restr
     const float yv = __ldg(y + i);
     const float scale = __ldg(params + p * params_ld + c);
     const float mean = __ldg(params + p * params_ld + C + c);
-    const float out = __fadd_rn(rintf(__fsub_rn(yv, mean)), mean);  // dequantised value
+    const float out = noise != nullptr ? __fadd_rn(yv, __ldg(noise + i))
+                                       : __fadd_rn(rintf(__fsub_rn(yv, mean)), mean);  // dequantised value
     const float v = fabsf(__fsub_rn(out, mean));
     const float sc = fmaxf(scale, 0.11f);
     const float upper = 0.5f * erfcf(kc * __fdiv_rn(__fsub_rn(0.5f, v), sc));
@@ -103,6 +106,60 @@ __global__ void gc_bits_kernel(const float* __restrict__ y, const float* __restr
     sum += (double)logf(lik);
   }
   block_accumulate(sum, acc);
+}
+
+// EntropyBottleneck.loss(): sum_c sum_k |logits_cumulative(quantiles[c][k]) - target[k]|  (compressai entropy_models.py;
+// reference pnet.py:35,59 `aux_loss()`).  One block; fixed-order tree: deterministic.
+__global__ void eb_aux_loss_kernel(const float* __restrict__ mats, const float* __restrict__ biases,
+                                   const float* __restrict__ factors, const float* __restrict__ quantiles,
+                                   const float* __restrict__ target, int C, float* __restrict__ out) {
+  extern __shared__ float sh[];
+  float* sm = sh;
+  float* sb = sh + 33 * C;
+  float* sf = sb + 13 * C;
+  float* red = sf + 12 * C;   // [blockDim.x]
+  for (int i = threadIdx.x; i < 33 * C; i += blockDim.x) sm[(i % 33) * C + i / 33] = mats[i];
+  for (int i = threadIdx.x; i < 13 * C; i += blockDim.x) sb[(i % 13) * C + i / 13] = biases[i];
+  for (int i = threadIdx.x; i < 12 * C; i += blockDim.x) sf[(i % 12) * C + i / 12] = factors[i];
+  __syncthreads();
+  EbSmem s{sm, sb, sf, C};
+  float t = 0.f;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+    const int c = i / 3, k = i - 3 * c;
+    t += fabsf(eb_logits(s, c, quantiles[i]) - target[k]);
+  }
+  red[threadIdx.x] = t;
+  __syncthreads();
+  for (int st = blockDim.x >> 1; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0];
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter = element index / 4, key = seed: uniform noise in [-0.5, 0.5) for the
+// training-mode quantisers (compressai quantize(.., "noise") draws torch.empty_like(x).uniform_(-0.5, 0.5)).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__global__ void uniform_noise_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t stream_id) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += stride) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q * 4 + j < n) out[q * 4 + j] = (float)(v[j] >> 8) * (1.0f / 16777216.0f) - 0.5f;   // 24 random bits: exact in fp32
+  }
 }
 
 }  // namespace tdvc
@@ -117,8 +174,41 @@ extern "C" int tdvc_eb_bits(const float* z, float* z_hat, const float* mats, con
   const int64_t total = npix * C;
   int grid = cdiv(total, 256);
   if (grid > kNumSMs * 4) grid = kNumSMs * 4;
-  eb_bits_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(z, z_hat, mats, biases, factors, medians, total, C, acc);
+  eb_bits_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(z, nullptr, z_hat, mats, biases, factors, medians, total, C, acc);
   TDVC_CHECK_LAUNCH("eb_bits");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_eb_bits_noise(const float* z, const float* noise, float* z_tilde, const float* mats, const float* biases,
+                                  const float* factors, int64_t npix, int C, double* acc, void* stream) {
+  TDVC_REQUIRE(z && noise && z_tilde && mats && biases && factors && acc && npix > 0 && C > 0, "eb_bits_noise: bad args");
+  const size_t smem = (size_t)(33 + 13 + 12 + 1) * C * sizeof(float);
+  TDVC_REQUIRE(smem <= 48 * 1024, "eb_bits_noise: C=%d too large", C);
+  const int64_t total = npix * C;
+  int grid = cdiv(total, 256);
+  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+  eb_bits_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(z, noise, z_tilde, mats, biases, factors, biases /* unused */, total, C, acc);
+  TDVC_CHECK_LAUNCH("eb_bits_noise");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_eb_aux_loss(const float* mats, const float* biases, const float* factors, const float* quantiles,
+                                const float* target3, int C, float* out, void* stream) {
+  TDVC_REQUIRE(mats && biases && factors && quantiles && target3 && out && C > 0, "eb_aux_loss: bad args");
+  const size_t smem = (size_t)((33 + 13 + 12) * C + 256) * sizeof(float);
+  TDVC_REQUIRE(smem <= 48 * 1024, "eb_aux_loss: C=%d too large", C);
+  eb_aux_loss_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(mats, biases, factors, quantiles, target3, C, out);
+  TDVC_CHECK_LAUNCH("eb_aux_loss");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_uniform_noise(float* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream) {
+  TDVC_REQUIRE(out && n >= 0, "uniform_noise: bad args");
+  if (n == 0) return TDVC_OK;
+  int grid = cdiv(n / 4 + 1, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  uniform_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n, seed, stream_id);
+  TDVC_CHECK_LAUNCH("uniform_noise");
   return TDVC_OK;
 }
 
@@ -127,7 +217,18 @@ extern "C" int tdvc_gc_bits(const float* y, const float* params, int params_ld, 
   const int64_t total = npix * C;
   int grid = cdiv(total, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  gc_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, params, params_ld, total, C, acc);
+  gc_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, nullptr, params, params_ld, total, C, acc);
   TDVC_CHECK_LAUNCH("gc_bits");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_gc_bits_noise(const float* y, const float* noise, const float* params, int params_ld, int64_t npix, int C,
+                                  double* acc, void* stream) {
+  TDVC_REQUIRE(y && noise && params && acc && npix > 0 && C > 0 && params_ld >= 2 * C, "gc_bits_noise: bad args");
+  const int64_t total = npix * C;
+  int grid = cdiv(total, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  gc_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, noise, params, params_ld, total, C, acc);
+  TDVC_CHECK_LAUNCH("gc_bits_noise");
   return TDVC_OK;
 }

@@ -47,6 +47,33 @@ def reference_window(ref_list):
     return torch.stack(sel, dim=1)
 
 
+class RefBuffer:
+    """The reference-frame list of one GOP (reference tools/predict.py:51-68: `ref_image` grows by one reconstruction per
+    P-frame) together with a host-side identity per frame.  `window()` returns the (N,4,3,H,W) tensor the codec takes and the four
+    identities of its slices; passing those to `VideoCompressor.forward(ref_keys=...)` lets the per-GOP feature caches be keyed
+    without hashing the frames on the device (one host synchronisation per frame less)."""
+    _serial = 0
+
+    def __init__(self, i_frame):
+        self.frames, self.ids = [i_frame], [self._new_id()]
+
+    @classmethod
+    def _new_id(cls):
+        cls._serial += 1
+        return cls._serial
+
+    def push(self, recon):
+        self.frames.append(recon)
+        self.ids.append(self._new_id())
+        if len(self.frames) > 4:   # only the I-frame and the last three reconstructions are ever referenced again
+            self.frames, self.ids = [self.frames[0]] + self.frames[-3:], [self.ids[0]] + self.ids[-3:]
+
+    def window(self):
+        n = len(self.frames)
+        sel = (0, n - 1, n - 1, n - 1) if n == 1 else ((0, n - 2, n - 1, n - 1) if n == 2 else (0, n - 3, n - 2, n - 1))
+        return torch.stack([self.frames[i] for i in sel], dim=1), tuple(self.ids[i] for i in sel)
+
+
 def sq_err_sum(a, b, acc, slot):
     """acc[slot] += sum (a-b)^2 on the device (CUDA kernel; fp64 accumulator)."""
     a, b = a.contiguous(), b.contiguous()
@@ -61,15 +88,18 @@ def code_gop(net, i_frame, p_frames, enable_amp=False, keep_recon=False, with_ms
     cropped frame) and `numel`; plus `recon` (list of cropped reconstructions) when keep_recon."""
     dev = p_frames.device
     T, _, h, w = p_frames.shape
-    refs = [pad(i_frame, 64)]
+    refs = RefBuffer(pad(i_frame, 64))
+    keyed = "ref_keys" in getattr(getattr(net, "forward", None), "__code__", type("c", (), {"co_varnames": ()})).co_varnames
     sse = torch.zeros(T, device=dev, dtype=torch.float64)
     bmv, bres, recons, mss = [], [], [], []
     for i in range(T):
         x = pad(p_frames[i:i + 1], 64)
-        recon, bpp_res, bpp_mv = net(x, reference_window(refs), enable_amp)
-        refs.append(recon)           # padded, clamped reconstruction feeds the next frame (predict.py:68)
-        if len(refs) > 4:
-            refs = [refs[0]] + refs[-3:]
+        window, keys = refs.window()
+        if keyed:   # tdvc_b200.VideoCompressor: the identities of the reference slices key its per-GOP feature caches
+            recon, bpp_res, bpp_mv = net(x, window, enable_amp, ref_keys=keys)
+        else:       # any module with the reference's signature (pnet.py:26)
+            recon, bpp_res, bpp_mv = net(x, window, enable_amp)
+        refs.push(recon)             # padded, clamped reconstruction feeds the next frame (predict.py:68)
         rc = crop(recon, (h, w))
         sq_err_sum(rc, p_frames[i:i + 1], sse, i)
         if with_msssim:              # tools/predict.py:93-94 (the enable_amp branch of the shipped cfg/predict.yaml)

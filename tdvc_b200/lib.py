@@ -74,6 +74,10 @@ SIGNATURES = {
     "tdvc_se_apply": [vp, i32, vp, i32, vp, vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, i32, vp, i32, vp],
     "tdvc_eb_bits": [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp],
     "tdvc_gc_bits": [vp, vp, i32, i64, i32, vp, vp],
+    "tdvc_eb_bits_noise": [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp],
+    "tdvc_gc_bits_noise": [vp, vp, vp, i32, i64, i32, vp, vp],
+    "tdvc_eb_aux_loss": [vp, vp, vp, vp, vp, i32, vp, vp],
+    "tdvc_uniform_noise": [vp, i64, C.c_uint64, C.c_uint64, vp],
     "tdvc_avgpool_scale": [vp, i32, vp, i32, i32, i32, i32, i32, vp],
     "tdvc_ff_descriptors": [vp, vp, i32, i32, i32, i32, vp],
     "tdvc_ff_match": [vp, vp, vp, vp, i32, i32, i32, vp],

@@ -876,21 +876,29 @@ class _Plan:
         return gp, z, zh
 
     # ---------------------------------------------------------------- cache keys and the variant of a frame
-    def _variant(self, refs, cache):
-        """Decide, from the content hashes of the four reference slices, what this frame has to compute.
+    def _variant(self, refs, cache, ref_keys=None):
+        """Decide, from the content hashes of the four reference slices (or from the caller's own identities of them,
+        `ref_keys`), what this frame has to compute.
         Returns (if_miss, assign, misses, keys): assign[j] = ring entry holding the fusion front of refer_frames[:, j + 1];
         misses = ((entry, j), ...) entries to compute from refer_frames[:, j + 1]."""
         N, H, Wd = self.N, self.H, self.W
         if not cache:
             return True, (0, 1, 2), ((0, 0), (1, 1), (2, 2)), [None] * 4
-        fr = 3 * H * Wd
-        L.check(self.lib.tdvc_slices_hash(refs.data_ptr(), fr, fr, 4 * N, self.hdev.data_ptr(), self._st()), "slices_hash")
-        self.launches += 1
-        self.hpin.copy_(self.hdev, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
-        hv = self.hpin.view(N, 4, 2).tolist()
-        keys = [tuple((hv[n][j][0], hv[n][j][1]) for n in range(N)) for j in range(4)]
+        if ref_keys is not None:
+            keys = [("id", k) for k in ref_keys]
+        else:
+            fr = 3 * H * Wd
+            L.check(self.lib.tdvc_slices_hash(refs.data_ptr(), fr, fr, 4 * N, self.hdev.data_ptr(), self._st()), "slices_hash")
+            self.launches += 1
+            self.hpin.copy_(self.hdev, non_blocking=True)
+            torch.cuda.current_stream(self.dev).synchronize()
+            hv = self.hpin.view(N, 4, 2).tolist()
+            keys = [tuple((hv[n][j][0], hv[n][j][1]) for n in range(N)) for j in range(4)]
         if_miss = keys[0] != self.if_key
+        if not any(k is not None and k in keys[1:] for k in self.ring):
+            # nothing of the ring is referenced any more (a new GOP): start from the canonical empty state, so that every GOP
+            # walks through the same sequence of launch variants (and replays the graphs captured for the first one)
+            self.ring, self.ring_used = [None, None, None], [0, 0, 0]
         assign, misses, taken = [None] * 3, [], set()
         for j in range(3):
             for e in range(3):
@@ -914,12 +922,12 @@ class _Plan:
         return if_miss, tuple(assign), tuple(misses), keys
 
     # ---------------------------------------------------------------- one P-frame
-    def run(self, W, x_nchw, refs_nchw, taps=None, graph=False, cache=True):
+    def run(self, W, x_nchw, refs_nchw, taps=None, graph=False, cache=True, ref_keys=None):
         """reference pnet.py:26-83 (eval branch).  x (N,3,H,W), refs (N,4,3,H,W) contiguous fp32 CUDA.
         Returns the plan's static (recon (N,3,H,W), bpp [mv, res]) buffers."""
         N, H, Wd = self.N, self.H, self.W
         self.launches = 0
-        if_miss, assign, misses, keys = self._variant(refs_nchw, cache)
+        if_miss, assign, misses, keys = self._variant(refs_nchw, cache, ref_keys)
         # ---- prologue (eager: reads the caller's tensors): NCHW -> NHWC (ld 4) of what this frame needs
         imgs = self.buf("imgs", 2 * N, H, Wd, 3, ld=4)        # [0:N] = input, [N:2N] = x^(t-1)
         ifr = self.buf("iframe", N, H, Wd, 3, ld=4)
@@ -1328,9 +1336,12 @@ class VideoCompressor(nn.Module):
             raise RuntimeError(f"precision must be 'exact' or 'mixed', not {self.precision!r}")
         return N, H, W
 
-    def forward(self, input_image, refer_frames, enabled_amp=False, is_compress=False, taps=None):
+    def forward(self, input_image, refer_frames, enabled_amp=False, is_compress=False, taps=None, ref_keys=None):
         """Same contract as reference pnet.py:26-83.  `enabled_amp` is accepted and ignored: the kernels
-        always compute at >= the reference's fp32 path accuracy class (precision)."""
+        always compute at >= the reference's fp32 path accuracy class (precision).
+        ref_keys (extension, optional): four hashable identities of refer_frames[:, 0..3] from a caller that knows them (a GOP
+        driver: `tdvc_b200.gop.code_gop`); the per-GOP feature caches are then keyed on them instead of on a device-side
+        content hash, which saves the one host synchronisation per frame the hash costs.  Equal keys MUST mean equal content."""
         if is_compress:
             raise NotImplementedError("entropy coding (is_compress=True) is a 'next' row (SURVEY.md 8f.3)")
         if self.training:
@@ -1344,7 +1355,9 @@ class VideoCompressor(nn.Module):
             plan = self._plan(N, H, W, dev)
             plan.bind(Wt)
             plan.impl, plan.precision = self.conv_impl, self.precision
-            recon, bpp = plan.run(Wt, x, refs, taps, graph=self.use_cuda_graph, cache=self.cache_features)
+            if ref_keys is not None and len(ref_keys) != 4:
+                raise RuntimeError("ref_keys: expected four identities, one per reference slice")
+            recon, bpp = plan.run(Wt, x, refs, taps, graph=self.use_cuda_graph, cache=self.cache_features, ref_keys=ref_keys)
             self.last_launches = plan.launches
             recon, bpp = recon.clone(), bpp.clone()   # the plan's buffers are overwritten by the next frame
         # reference returns (recon, bpp_res.view(-1), bpp_mv.view(-1))  (pnet.py:82-83)

@@ -256,16 +256,24 @@ def _dilate_latent(bad, r):
 
 
 def _symbols_vs_golden(g, taps, net, prefix=""):
-    """Fraction of identical symbols per latent + mask (1/16 scale) of the flipped y positions; flips must sit at rounding ties."""
-    same, bad_any = {}, None
+    """Fraction of identical symbols per latent + mask (1/16 scale) of the flipped y positions.  Mismatches are allowed only at
+    rounding ties: a flipped motion symbol must have its pre-quantiser value next to a half-integer; a flipped residual symbol
+    either sits at a tie itself or lies in the footprint (12 latent cells) of a flipped motion symbol - there the motion
+    compensation, hence the residual it codes, legitimately differs."""
+    same, bad_any, near_mv = {}, None, None
     for c, cn in (("mv", "mvCoder"), ("res", "resCoder")):
         yh = taps[f"{c}.y_hat"].cpu()
         bad = yh.numpy().astype(np.int16) != g[prefix + f"{c}_y_hat"].astype(np.int16)
         same[c + ".y"] = 1.0 - bad.mean()
         bad = torch.from_numpy(bad)
-        if bad.any():   # mismatches only at rounding ties: the pre-quantiser value sits next to a half-integer
-            y = taps[f"{c}.y"].cpu()[bad]
-            assert ((y - torch.floor(y)) - 0.5).abs().max() < 5e-3, f"{c}: symbol mismatch away from a rounding tie"
+        if bad.any():
+            y = taps[f"{c}.y"].cpu()
+            tie = ((y - torch.floor(y)) - 0.5).abs()
+            check = bad if near_mv is None else (bad & ~near_mv)
+            if check.any():
+                assert tie[check].max() < 5e-3, f"{c}: symbol mismatch away from a rounding tie ({tie[check].max().item()})"
+        if c == "mv":
+            near_mv = torch.nn.functional.max_pool2d(bad.any(1, keepdim=True).float(), 25, 1, 12) > 0
         bad_any = bad if bad_any is None else (bad_any | bad)
         med = getattr(net, cn).entropy_bottleneck.quantiles[:, 0, 1].detach().view(1, -1, 1, 1).cpu()
         zq = torch.round(taps[f"{c}.z_hat"].cpu() - med).numpy().astype(np.int16)
@@ -298,11 +306,16 @@ def test_fullres_pframe_vs_reference_golden(net, dev, precision):
     assert (taps["loopfilter.ind"].cpu().numpy().astype(np.int32) == g["ind"]).all()
     assert abs(bres.item() - float(g["bpp_res"][0])) <= 1e-3 * float(g["bpp_res"][0])
     assert abs(bmv.item() - float(g["bpp_mv"][0])) <= 1e-3 * float(g["bpp_mv"][0])
+    # reconstruction <= 1e-3; where a symbol flipped at a tie (a few hundred of the 2 million: any two fp32 implementations
+    # differ there) the decoder legitimately differs inside that symbol's footprint: every pixel above the bar must lie within 4
+    # latent cells of a flipped symbol, and they must be rare
     want = torch.from_numpy(g["recon_q16"].astype(np.float32) / 65535.0)
     err = (recon.cpu() - want).abs()[0].max(0).values
-    clean = ~_dilate_latent(bad, 12) if bad.any() else torch.ones_like(err, dtype=torch.bool)
-    assert clean.float().mean() > 0.9
-    assert err[clean].max().item() <= 1e-3 + 1.0 / 65535, err[clean].max().item()
+    over = err > 1e-3 + 1.0 / 65535
+    print("recon max err", err.max().item(), "pixels over 1e-3:", int(over.sum()))
+    assert over.float().mean().item() < 1e-3 and err.max().item() < 5e-3
+    if over.any():
+        assert bad.any() and not (over & ~_dilate_latent(bad, 4)).any(), "reconstruction error above 1e-3 away from any flipped symbol"
     mse = ((recon.cpu().double() - x.double()) ** 2).mean().item()
     assert abs(10 * math.log10(1 / mse) - 10 * math.log10(1 / float(g["mse"]))) <= 0.01
     # ---- BASELINE config 5 at full size: multi-frame fusion + in-loop filter with 4 reference frames.  Stage tensors of the
@@ -312,10 +325,10 @@ def test_fullres_pframe_vs_reference_golden(net, dev, precision):
         v = taps[k].cpu()
         scale = float(g["stat_" + k][2])
         d = (v[:, :, ::32, ::32] - torch.from_numpy(g["s32_" + k])).abs()
-        frac_off = (d > 1e-4 * scale).float().mean().item()
-        assert frac_off < (5e-3 if bad.any() else 1e-6), (k, frac_off, d.max().item())
+        frac_off = (d > 1e-3 * scale).float().mean().item()
+        assert frac_off < (1e-3 if bad.any() else 1e-6) and d.max().item() < 1e-2 * scale, (k, frac_off, d.max().item())
         tm = torch.nn.functional.avg_pool2d(v.double(), 64).float()
-        assert (tm - torch.from_numpy(g["tile_" + k])).abs().max().item() <= 1e-3 * scale
+        assert (tm - torch.from_numpy(g["tile_" + k])).abs().max().item() <= 1e-4 * scale
     net.precision = precision
     try:
         pred, rec5 = net.fusion_and_filter(taps["prediction1"], refs.to(dev), taps["recon_feat"])
@@ -327,8 +340,9 @@ def test_fullres_pframe_vs_reference_golden(net, dev, precision):
 def test_fullres_gop_chain_vs_reference_golden(net, dev):
     """Six chained 1920x1024 P-frames of the GOP bench.py codes first, free running (every frame references OUR previous
     reconstructions, reference tools/predict.py:51-68), against the reference's chain: per frame bpp within 0.1 %, PSNR within
-    0.01 dB, FeatureFix indices identical, >= 99.9 % of the symbols identical on the first frame and - since two fp32
-    implementations of a closed-loop codec drift apart wherever a rounding tie flipped - >= 99 % on the following ones."""
+    0.01 dB, FeatureFix indices identical and >= 99.9 % of the symbols of both coders identical on EVERY frame (measured: 0.01 %
+    of the motion and 0.04 % of the residual symbols differ per frame, without growth along the chain), reconstruction within
+    1e-3 on >= 99.9 % of the sampled pixels."""
     from tdvc_b200 import gop as G
     from tdvc_b200 import synth
     g = load_golden("chain1024x1920_s100")
@@ -347,16 +361,18 @@ def test_fullres_gop_chain_vs_reference_golden(net, dev):
         if len(refs) > 4:
             refs = [refs[0]] + refs[-3:]
         p = f"f{t}_"
+        # frame 1 sees exactly the reference's inputs: its flips must sit at rounding ties; later frames reference our own
+        # reconstructions, which already differ inside the footprints of earlier flips
         same, bad = _symbols_vs_golden(g, taps, net, p) if t == 1 else _symbols_vs_golden_loose(g, taps, net, p)
         mse = ((recon.double() - x.double()) ** 2).mean().item()
         d = (recon[:, :, ::4, ::4].cpu() - torch.from_numpy(g[p + "recon_s4_q16"].astype(np.float32) / 65535.0)).abs()
         print(f"frame {t}: identical {same}, recon sample max err {d.max().item():.2e}, frac > 1e-3 {(d > 1e-3).float().mean().item():.2e}")
-        assert min(same.values()) >= (0.999 if t == 1 else 0.99), (t, same)
+        assert min(same.values()) >= 0.999, (t, same)
         assert (taps["loopfilter.ind"].cpu().numpy().astype(np.int32) == g[p + "ind"]).all(), t
         assert abs(bres.item() - float(g[p + "bpp_res"][0])) <= 1e-3 * float(g[p + "bpp_res"][0]), t
         assert abs(bmv.item() - float(g[p + "bpp_mv"][0])) <= 1e-3 * float(g[p + "bpp_mv"][0]), t
         assert abs(10 * math.log10(1 / mse) - 10 * math.log10(1 / float(g[p + "mse"]))) <= 0.01, t
-        assert (d > 1e-3).float().mean().item() < 0.02, t
+        assert (d > 1e-3).float().mean().item() < 1e-3 and d.max().item() < 5e-3, t
         tm = torch.nn.functional.avg_pool2d(recon.double(), 64).float().cpu()
         assert (tm - torch.from_numpy(g[p + "recon_tile"])).abs().max().item() <= 1e-3, t
 
