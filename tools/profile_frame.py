@@ -14,7 +14,7 @@ warnings.filterwarnings("ignore")
 sys.path.insert(0, ".")
 
 
-def main(h=1024, w=1920, impl=0):
+def main(h=1024, w=1920, impl=0, amp=1):
     from tdvc_b200 import gop as G
     from tdvc_b200 import synth
     from tdvc_b200.model import VideoCompressor
@@ -26,15 +26,18 @@ def main(h=1024, w=1920, impl=0):
     net.load_state_dict(sd)
     net = net.to(dev)
     net.conv_impl = impl
-    g = synth.make_gop(h, w, gop=4, seed=100).to(dev)
-    refs = [g[0:1]]
+    # frame 7 of a GOP is the steady state: I-frame features and two of the three fusion fronts come from the per-GOP caches
+    g = synth.make_gop(h, w, gop=8, seed=100).to(dev)
+    refs = G.RefBuffer(g[0:1])
     with torch.no_grad():
-        for t in (1, 2):
-            recon, _, _ = net(g[t:t + 1], G.reference_window(refs), False)
-            refs.append(recon)
+        for t in range(1, 7):
+            win, keys = refs.window()
+            recon, _, _ = net(g[t:t + 1], win, bool(amp), ref_keys=keys)
+            refs.push(recon)
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        recon, bres, bmv = net(g[3:4], G.reference_window(refs), False)
+        win, keys = refs.window()
+        recon, bres, bmv = net(g[7:8], win, bool(amp), ref_keys=keys)
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
     print(f"profiled 1 P-frame {h}x{w}: launches {net.last_launches}, bpp_res {bres.item():.4f} bpp_mv {bmv.item():.4f}")
