@@ -208,6 +208,10 @@ int tdvc_gc_bits_noise(const float* y, const float* noise, const float* params, 
                        double* acc, void* stream);
 int tdvc_eb_aux_loss(const float* mats, const float* biases, const float* factors, const float* quantiles,
                      const float* target3, int C, float* out, void* stream);
+/* d eb_aux_loss / d quantiles ([C][3]) times *grad_out (device scalar): the gradient `aux_loss.backward()` needs to step the
+ * aux optimiser on `.quantiles` (reference tools/train.py:101-113,147-159; matrices / biases / factors are detached there). */
+int tdvc_eb_aux_loss_grad(const float* mats, const float* biases, const float* factors, const float* quantiles,
+                          const float* target3, const float* grad_out, int C, float* grad_quantiles, void* stream);
 int tdvc_uniform_noise(float* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream);
 
 /* ---- reference-based in-loop filter pieces (reference pnet.py:213-257) ----

@@ -137,6 +137,52 @@ __global__ void eb_aux_loss_kernel(const float* __restrict__ mats, const float* 
   if (threadIdx.x == 0) *out = red[0];
 }
 
+// d loss / d quantiles of eb_aux_loss (the only gradient the reference takes of it: `aux_loss.backward()` steps the aux
+// optimiser on `.quantiles`, reference tools/train.py:101-113,147-159; compressai evaluates the logits with the matrices,
+// biases and factors detached).  grad_q[c][k] = grad_out * sign(logits - target) * d logits / d q, one thread per (c, k).
+__global__ void eb_aux_loss_grad_kernel(const float* __restrict__ mats, const float* __restrict__ biases,
+                                        const float* __restrict__ factors, const float* __restrict__ quantiles,
+                                        const float* __restrict__ target, const float* __restrict__ grad_out, int C,
+                                        float* __restrict__ grad_q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * C) return;
+  const int c = i / 3, k = i - 3 * c;
+  const float* m = mats + c * 33;
+  const float* b = biases + c * 13;
+  const float* f = factors + c * 12;
+  // forward value h and derivative d of every layer, widths 1,3,3,3,3,1
+  float h[3], d[3], g[3], e[3];
+  const float v = quantiles[i];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float t = m[j] * v + b[j];
+    const float th = tanhf(t);
+    h[j] = t + f[j] * th;
+    d[j] = m[j] * (1.f + f[j] * (1.f - th * th));
+  }
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float* mr = m + 3 + l * 9 + r * 3;
+      const float t = mr[0] * h[0] + mr[1] * h[1] + mr[2] * h[2] + b[3 + l * 3 + r];
+      const float dt = mr[0] * d[0] + mr[1] * d[1] + mr[2] * d[2];
+      const float th = tanhf(t);
+      const float fr = f[3 + l * 3 + r];
+      g[r] = t + fr * th;
+      e[r] = dt * (1.f + fr * (1.f - th * th));
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { h[r] = g[r]; d[r] = e[r]; }
+  }
+  const float* mr = m + 30;
+  const float logit = mr[0] * h[0] + mr[1] * h[1] + mr[2] * h[2] + b[12];
+  const float dlogit = mr[0] * d[0] + mr[1] * d[1] + mr[2] * d[2];
+  const float diff = logit - target[k];
+  const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+  grad_q[i] = grad_out[0] * sgn * dlogit;
+}
+
 // Philox4x32-10 (Salmon et al. 2011), counter = element index / 4, key = seed: uniform noise in [-0.5, 0.5) for the
 // training-mode quantisers (compressai quantize(.., "noise") draws torch.empty_like(x).uniform_(-0.5, 0.5)).
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
@@ -199,6 +245,15 @@ extern "C" int tdvc_eb_aux_loss(const float* mats, const float* biases, const fl
   TDVC_REQUIRE(smem <= 48 * 1024, "eb_aux_loss: C=%d too large", C);
   eb_aux_loss_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(mats, biases, factors, quantiles, target3, C, out);
   TDVC_CHECK_LAUNCH("eb_aux_loss");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_eb_aux_loss_grad(const float* mats, const float* biases, const float* factors, const float* quantiles,
+                                     const float* target3, const float* grad_out, int C, float* grad_quantiles, void* stream) {
+  TDVC_REQUIRE(mats && biases && factors && quantiles && target3 && grad_out && grad_quantiles && C > 0, "eb_aux_loss_grad: bad args");
+  eb_aux_loss_grad_kernel<<<cdiv(3 * C, 128), 128, 0, (cudaStream_t)stream>>>(mats, biases, factors, quantiles, target3, grad_out, C,
+                                                                              grad_quantiles);
+  TDVC_CHECK_LAUNCH("eb_aux_loss_grad");
   return TDVC_OK;
 }
 

@@ -77,6 +77,7 @@ SIGNATURES = {
     "tdvc_eb_bits_noise": [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp],
     "tdvc_gc_bits_noise": [vp, vp, vp, i32, i64, i32, vp, vp],
     "tdvc_eb_aux_loss": [vp, vp, vp, vp, vp, i32, vp, vp],
+    "tdvc_eb_aux_loss_grad": [vp, vp, vp, vp, vp, vp, i32, vp, vp],
     "tdvc_uniform_noise": [vp, i64, C.c_uint64, C.c_uint64, vp],
     "tdvc_avgpool_scale": [vp, i32, vp, i32, i32, i32, i32, i32, vp],
     "tdvc_ff_descriptors": [vp, vp, i32, i32, i32, i32, vp],

@@ -532,7 +532,8 @@ class _Packed:
         if mats.shape[1] != 33 or biases.shape[1] != 13 or factors.shape[1] != 12:
             raise RuntimeError("EntropyBottleneck: expected filters (3, 3, 3, 3)")
         c[f"{cn}.eb"] = (mats.contiguous(), biases.contiguous(), factors.contiguous(),
-                         P(eb, "quantiles")[:, 0, 1].contiguous())
+                         P(eb, "quantiles")[:, 0, 1].contiguous(), P(eb, "quantiles").reshape(Cc, 3).contiguous(),
+                         P(eb, "target").reshape(3).contiguous())
 
 
 _PACK_GEN = itertools.count(1)
@@ -611,6 +612,10 @@ class _Plan:
         self.graphs = {}
         self.cache_hits = 0
         self.weights_gen = None
+        # training-mode forward (`VideoCompressor.train()`): noise quantisation, FeatureFix at scale 8, aux losses
+        self.training = False
+        self.noise = None                        # {"mv.z" | "mv.y" | "mv.y_lik" | "rs.z" | ...: NHWC Act of U(-0.5, 0.5) noise}
+        self.aux = torch.zeros(2, device=device, dtype=torch.float32)   # [mv_aux_loss, res_aux_loss]
 
     def bind(self, W):
         """Cached features and captured graphs belong to one set of packed weights."""
@@ -811,7 +816,10 @@ class _Plan:
         y = self.se(a, W[f"{cn}.ga8"], b("y", a.H, a.W))
         # ---- y_hat first: both the synthesis transform and the entropy model start from it
         yh = b("y_hat", y.H, y.W)
-        self.call("tdvc_round_half_even", y.ptr, yh.ptr, y.N * y.H * y.W * 128, nbytes=8 * y.N * y.H * y.W * 128)
+        if self.training:   # compressai quantize(y, "noise"): y + U(-0.5, 0.5)   (JointAutoregressiveHierarchicalPriors.forward)
+            self.call("tdvc_axpby", y.ptr, self.noise[f"{cn}.y"].ptr, yh.ptr, y.N * y.H * y.W * 128, 1.0, 1.0)
+        else:
+            self.call("tdvc_round_half_even", y.ptr, yh.ptr, y.N * y.H * y.W * 128, nbytes=8 * y.N * y.H * y.W * 128)
         # The hyperprior / context / entropy-parameter chain only feeds the bit count (x_hat depends on round(y) alone,
         # SURVEY.md App. A): ~17 small, latency-bound launches at H/16..H/64.  They run on a side stream, concurrently
         # with the (equally small) first layers of g_s, and are joined before this coder returns.  (Serialised when the
@@ -856,9 +864,16 @@ class _Plan:
         z = self.conv([h], W[f"{cn}.ha8"], b("z", h.H // 2, h.W // 2), stride=2)
         # ---- factorised prior on z: quantise + likelihood + sum ln p in one pass
         zh = b("z_hat", z.H, z.W)
-        mats, biases, factors, med = W[f"{cn}.eb"]
-        self.call("tdvc_eb_bits", z.ptr, zh.ptr, mats.data_ptr(), biases.data_ptr(), factors.data_ptr(), med.data_ptr(),
-                  z.N * z.H * z.W, 128, self.acc.data_ptr() + 8 * (acc_off + 1))
+        mats, biases, factors, med, quantiles, target = W[f"{cn}.eb"]
+        if self.training:
+            self.call("tdvc_eb_bits_noise", z.ptr, self.noise[f"{cn}.z"].ptr, zh.ptr, mats.data_ptr(), biases.data_ptr(),
+                      factors.data_ptr(), z.N * z.H * z.W, 128, self.acc.data_ptr() + 8 * (acc_off + 1))
+            # EntropyBottleneck.loss() of this coder (reference pnet.py:35,59: `aux_loss()`)
+            self.call("tdvc_eb_aux_loss", mats.data_ptr(), biases.data_ptr(), factors.data_ptr(), quantiles.data_ptr(),
+                      target.data_ptr(), 128, self.aux.data_ptr() + 4 * (acc_off // 2))
+        else:
+            self.call("tdvc_eb_bits", z.ptr, zh.ptr, mats.data_ptr(), biases.data_ptr(), factors.data_ptr(), med.data_ptr(),
+                      z.N * z.H * z.W, 128, self.acc.data_ptr() + 8 * (acc_off + 1))
         # ---- h_s
         s = self.conv([zh], W[f"{cn}.hs0"], b("hs0", z.H, z.W), **lr)
         s = self.conv([s], W[f"{cn}.hs2"], b("hs2", 2 * z.H, 2 * z.W), **lr)
@@ -871,8 +886,12 @@ class _Plan:
         e = self.conv([params, ctx], W[f"{cn}.ep0"], b("ep0", y.H, y.W, c0, ld=_r(c0, 8), zero=True), **lr)
         e = self.conv([e], W[f"{cn}.ep2"], b("ep2", y.H, y.W, c2, ld=_r(c2, 8), zero=True), **lr)
         gp = self.conv([e], W[f"{cn}.ep4"], b("gp", y.H, y.W, 256))
-        self.call("tdvc_gc_bits", y.ptr, gp.ptr, gp.ld, y.N * y.H * y.W, 128, self.acc.data_ptr() + 8 * acc_off,
-                  nbytes=12 * y.N * y.H * y.W * 128)
+        if self.training:   # GaussianConditional.forward draws its own noise for the likelihood
+            self.call("tdvc_gc_bits_noise", y.ptr, self.noise[f"{cn}.y_lik"].ptr, gp.ptr, gp.ld, y.N * y.H * y.W, 128,
+                      self.acc.data_ptr() + 8 * acc_off)
+        else:
+            self.call("tdvc_gc_bits", y.ptr, gp.ptr, gp.ld, y.N * y.H * y.W, 128, self.acc.data_ptr() + 8 * acc_off,
+                      nbytes=12 * y.N * y.H * y.W * 128)
         return gp, z, zh
 
     # ---------------------------------------------------------------- cache keys and the variant of a frame
@@ -1182,7 +1201,7 @@ class _Plan:
     # ---- reference-based in-loop filter (reference FeatureFix, pnet.py:187-263)
     def _ff_geometry(self):
         H, Wd = self.H, self.W
-        scale = int(H / 8)  # eval branch of pnet.py:220-223
+        scale = 8 if self.training else int(H / 8)  # pnet.py:220-223
         ph, pw = H // scale, Wd // scale
         PH, PW = (ph + 3) // 3 + 1, (pw + 3) // 3 + 1
         bs = 3 * scale
@@ -1244,6 +1263,29 @@ class _Plan:
 
 
 # =============================================================================== the module
+class _AuxLoss(torch.autograd.Function):
+    """EntropyBottleneck.loss() of one coder with its gradient with respect to `.quantiles` - the one backward the reference
+    takes of it (`aux_loss.backward(); aux_optimizer.step()`, reference tools/train.py:147-159).  Forward value: the plan's
+    `tdvc_eb_aux_loss` launch; backward: `tdvc_eb_aux_loss_grad`."""
+
+    @staticmethod
+    def forward(ctx, quantiles, value, eb_packed):
+        ctx.eb = eb_packed
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        mats, biases, factors, _, q, target = ctx.eb
+        g = torch.empty_like(q)
+        go = grad_out.detach().float().reshape(1).contiguous()
+        lib = L.load()
+        with torch.cuda.device(q.device):
+            L.check(lib.tdvc_eb_aux_loss_grad(mats.data_ptr(), biases.data_ptr(), factors.data_ptr(), q.data_ptr(),
+                                              target.data_ptr(), go.data_ptr(), q.shape[0], g.data_ptr(),
+                                              torch.cuda.current_stream(q.device).cuda_stream), "eb_aux_loss_grad")
+        return g.view(q.shape[0], 1, 3), None, None
+
+
 class _Origin:
     """Shared by a module and its nn.DataParallel replicas (replicate() copies __dict__ shallowly): lets a replica find the
     module that owns the master parameters, whose versions key the packed-weight cache."""
@@ -1354,7 +1396,7 @@ class VideoCompressor(nn.Module):
         if is_compress:
             raise NotImplementedError("entropy coding (is_compress=True) is a 'next' row (SURVEY.md 8f.3)")
         if self.training:
-            raise NotImplementedError("training mode (noise quantisation / backward) is a 'next' row (SURVEY.md 8f.1)")
+            return self._forward_training(input_image, refer_frames, taps, noise=None)
         N, H, W = self._check(input_image, refer_frames, 3)
         dev = input_image.device
         with torch.cuda.device(dev), torch.no_grad():
@@ -1371,6 +1413,57 @@ class VideoCompressor(nn.Module):
             recon, bpp = recon.clone(), bpp.clone()   # the plan's buffers are overwritten by the next frame
         # reference returns (recon, bpp_res.view(-1), bpp_mv.view(-1))  (pnet.py:82-83)
         return recon, bpp[1:2], bpp[0:1]
+
+    def _forward_training(self, input_image, refer_frames, taps=None, noise=None):
+        """`self.training` branch of reference pnet.py:26-83: uniform-noise quantisation in both coders (compressai
+        quantize(.., "noise"): z + u, y + u for the synthesis / context path and a second draw for the likelihood of y),
+        FeatureFix patch matching at scale 8 (pnet.py:220-221), and the 5-tuple return with the two aux losses (:80-81).
+        noise: None = drawn on the device (Philox4x32-10 seeded from torch's CPU generator, so torch.manual_seed governs it), or
+        {"mv.z", "mv.y", "mv.y_lik", "res.z", "res.y", "res.y_lik": (N,128,h,w) CUDA tensors} to inject given draws (tests).
+        FORWARD ONLY: reconstruction and bpp carry no autograd graph (backward kernels of the convolutions are SURVEY.md 8f row
+        1, not built), so `rd_loss.backward()` raises; the aux losses DO back-propagate to `.quantiles`."""
+        N, H, W = self._check(input_image, refer_frames, 3)
+        dev = input_image.device
+        with torch.cuda.device(dev):
+            with torch.no_grad():
+                x = input_image.detach().float().contiguous()
+                refs = refer_frames.detach().float().contiguous()
+                Wt = self._weights(dev)
+                plan = self._plan(N, H, W, dev)
+                plan.bind(Wt)
+                plan.impl, plan.precision = self.conv_impl, "exact"
+                plan.training = True
+                try:
+                    plan.noise = self._noise(plan, noise, N, H, W)
+                    recon, bpp = plan.run(Wt, x, refs, taps, graph=False, cache=False)
+                finally:
+                    plan.training, plan.noise = False, None
+                self.last_launches = plan.launches
+                recon, bpp, aux = recon.clone(), bpp.clone(), plan.aux.clone()
+            mv_aux = _AuxLoss.apply(self.mvCoder.entropy_bottleneck.quantiles, aux[0], Wt["mv.eb"])
+            res_aux = _AuxLoss.apply(self.resCoder.entropy_bottleneck.quantiles, aux[1], Wt["rs.eb"])
+        return recon, bpp[1:2], bpp[0:1], mv_aux, res_aux
+
+    def _noise(self, plan, given, N, H, W):
+        lib = L.load()
+        st = torch.cuda.current_stream(plan.dev).cuda_stream
+        seed = None
+        out = {}
+        for ci, (cn, nm) in enumerate((("mv", "mv"), ("rs", "res"))):
+            for ki, (kind, sc) in enumerate((("z", 64), ("y", 16), ("y_lik", 16))):
+                a = plan.buf(f"noise.{cn}.{kind}", N, H // sc, W // sc, 128)
+                if given is not None:
+                    t = given[f"{nm}.{kind}"]
+                    if tuple(t.shape) != (N, 128, H // sc, W // sc) or not t.is_cuda:
+                        raise RuntimeError(f"noise[{nm}.{kind}]: expected a CUDA tensor of shape {(N, 128, H // sc, W // sc)}")
+                    t = t.detach().float().contiguous()
+                    L.check(lib.tdvc_nchw_to_nhwc(t.data_ptr(), a.ptr, N, 128, H // sc, W // sc, 128, st), "nchw_to_nhwc")
+                else:
+                    if seed is None:
+                        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+                    L.check(lib.tdvc_uniform_noise(a.ptr, N * (H // sc) * (W // sc) * 128, seed, ci * 3 + ki, st), "uniform_noise")
+                out[f"{cn}.{kind}"] = a
+        return out
 
     def fusion_and_filter(self, prediction1, refer_frames, recon_feat, enabled_amp=False):
         """BASELINE config 5 entry: `mcfilter` (reference pnet.py:53) on `prediction1` and `loopfilter` + clamp (:77-78) on

@@ -511,3 +511,98 @@ def test_data_parallel_replicas(oracle_model, dev):
         outs = parallel_apply(reps, [(xa.to(dev), ra.to(dev), False), (xb.to(dev), rb.to(dev), False)], devices=[devices[0]] * 2)
     assert all(torch.equal(p, q) for p, q in zip(outs[0], wa)) and all(torch.equal(p, q) for p, q in zip(outs[1], wb))
     assert all(m._packed[k][1] is packs[k][1] for k in packs), "a replica re-packed the weights"
+
+
+# ------------------------------------------------------------------------------------------------ training-mode forward (slice a)
+def _train_noise(N, H, W):
+    """The six uniform draws of one training forward in the order the oracle makes them (mv: z, y, y for the likelihood; then
+    the residual coder), with the layouts compressai uses: EntropyBottleneck draws on the (C, 1, N*h*w) view."""
+    out = {}
+    for c in ("mv", "res"):
+        hz, wz, hy, wy = H // 64, W // 64, H // 16, W // 16
+        nz = torch.empty(128, 1, N * hz * wz).uniform_(-0.5, 0.5)
+        out[f"{c}.z"] = nz.view(128, N, hz, wz).permute(1, 0, 2, 3).contiguous()
+        out[f"{c}.y"] = torch.empty(N, 128, hy, wy).uniform_(-0.5, 0.5)
+        out[f"{c}.y_lik"] = torch.empty(N, 128, hy, wy).uniform_(-0.5, 0.5)
+    return out
+
+
+@pytest.mark.parametrize("case", [(1, 64, 128, 71), (2, 128, 128, 72)])
+def test_training_mode_forward_vs_oracle(net, oracle_model, dev, case):
+    """`net.train()`: noise quantisation with injected draws, FeatureFix at scale 8 (reference pnet.py:220-221), aux losses and
+    the 5-tuple return (:80-81) against the oracle in train() mode under the same torch seed (the oracle draws its noise from
+    torch's generator in a fixed order; the same draws are reproduced here and handed to the CUDA path)."""
+    from tdvc_b200 import synth
+    N, H, W, seed = case
+    xs, rs = zip(*[synth.make_frame_pair(H, W, seed=seed + i) for i in range(N)])
+    x, refs = torch.cat(xs, 0), torch.cat(rs, 0)
+    oracle_model.train()
+    net.train()
+    try:
+        torch.manual_seed(1234)
+        ot = {}
+        with torch.no_grad():
+            want = oracle_model(x, refs, False, taps=ot)
+        torch.manual_seed(1234)
+        noise = {k: v.to(dev) for k, v in _train_noise(N, H, W).items()}
+        gt = {}
+        got = net._forward_training(x.to(dev), refs.to(dev), taps=gt, noise=noise)
+    finally:
+        oracle_model.eval()
+        net.eval()
+    assert len(got) == 5 and got[1].shape == (1,) and got[2].shape == (1,) and got[3].dim() == 0 and got[4].dim() == 0
+    for c in ("mv", "res"):
+        assert (ot[f"{c}.y_hat"] - gt[f"{c}.y_hat"].cpu()).abs().max().item() < 2e-3    # y + noise: continuous, no rounding
+        assert (ot[f"{c}.z_hat"] - gt[f"{c}.z_hat"].cpu()).abs().max().item() < 2e-3
+    assert torch.equal(ot["loopfilter.ind"], gt["loopfilter.ind"].cpu())
+    assert ot["loopfilter.ind"].shape[1] == ((H // 8 + 3) // 3 + 1) * ((W // 8 + 3) // 3 + 1)      # scale 8 patch grid
+    assert (want[0] - got[0].cpu()).abs().max().item() <= 1e-3
+    for i in (1, 2):
+        assert abs(want[i].item() - got[i].item()) <= 1e-3 * want[i].item()
+    for i in (3, 4):
+        assert abs(want[i].item() - got[i].item()) <= 1e-5 * max(1.0, abs(want[i].item()))
+
+
+def test_training_mode_aux_loss_backward_and_own_noise(net, oracle_model, dev):
+    """The aux losses back-propagate to `.quantiles` like the reference's (`aux_loss.backward()`, tools/train.py:147-159); the
+    device-side Philox noise is uniform in [-0.5, 0.5), reproducible under torch.manual_seed, and the rate-distortion outputs
+    carry no graph (their backward kernels are not built: calling backward on them fails loudly)."""
+    from tdvc_b200 import lib as L
+    from tdvc_b200 import synth
+    x, refs = synth.make_frame_pair(64, 64, seed=81)
+    net.train()
+    oracle_model.train()
+    try:
+        for m in (net, oracle_model):
+            for cd in (m.mvCoder, m.resCoder):
+                cd.entropy_bottleneck.quantiles.grad = None
+        torch.manual_seed(5)
+        a = net(x.to(dev), refs.to(dev), False)
+        torch.manual_seed(5)
+        b = net(x.to(dev), refs.to(dev), False)
+        assert all(torch.equal(p.detach(), q.detach()) for p, q in zip(a, b))
+        torch.manual_seed(6)
+        c = net(x.to(dev), refs.to(dev), False)
+        assert not torch.equal(a[0], c[0])
+        (a[3] + a[4]).backward()
+        want = oracle_model.mvCoder.aux_loss() + oracle_model.resCoder.aux_loss()
+        want.backward()
+        for cn in ("mvCoder", "resCoder"):
+            g = getattr(net, cn).entropy_bottleneck.quantiles.grad.cpu()
+            w = getattr(oracle_model, cn).entropy_bottleneck.quantiles.grad
+            assert (g - w).abs().max().item() <= 1e-5 * max(1.0, w.abs().max().item())
+        assert not a[0].requires_grad and not a[1].requires_grad
+        with pytest.raises(RuntimeError):
+            (a[0].mean() + a[1].sum()).backward()
+    finally:
+        net.eval()
+        oracle_model.eval()
+        for m in (net, oracle_model):
+            for cd in (m.mvCoder, m.resCoder):
+                cd.entropy_bottleneck.quantiles.grad = None
+    n = 1 << 20
+    buf = torch.empty(n, device=dev)
+    L.check(L.load().tdvc_uniform_noise(buf.data_ptr(), n, 12345, 7, torch.cuda.current_stream(dev).cuda_stream), "noise")
+    assert buf.min().item() >= -0.5 and buf.max().item() < 0.5
+    assert abs(buf.mean().item()) < 2e-3 and abs(buf.var().item() - 1.0 / 12) < 1e-3
+    assert abs(torch.corrcoef(torch.stack([buf[:-1], buf[1:]]))[0, 1].item()) < 5e-3

@@ -56,7 +56,7 @@ def test_state_dict_matches_reference_key_set(oracle_model):
         assert v.shape == osd[k].shape and torch.equal(v, osd[k]), k
 
 
-def test_forward_refuses_cpu_and_training():
+def test_forward_refuses_cpu_and_entropy_coding():
     from tdvc_b200.model import VideoCompressor
     net = VideoCompressor().eval()
     x, r = torch.zeros(1, 3, 64, 64), torch.zeros(1, 4, 3, 64, 64)
@@ -65,8 +65,8 @@ def test_forward_refuses_cpu_and_training():
     with pytest.raises(NotImplementedError):
         net(x, r, False, True)
     net.train()
-    with pytest.raises(NotImplementedError):
-        net(x, r, False)
+    with pytest.raises(RuntimeError):
+        net(x, r, False)  # the training-mode forward is CUDA-only as well
 
 
 def _emulate_packed_conv(xs, cw, stride=1):

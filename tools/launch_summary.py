@@ -13,8 +13,8 @@ for r in rows:
     a[0] += 1
     a[1] += v
 tot = sum(a[1] for a in agg.values())
-print("# ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 400 : python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline")
-print("# 400 consecutive launches (a little more than one 1920x1024 P-frame); per-launch times are cold-cache and serialised: compare SHARES")
+print("# ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none : python tools/profile_frame.py")
+print("# the launches of ONE steady-state 1920x1024 P-frame (frame 7 of a GOP, enabled_amp=True); per-launch times are cold-cache and serialised: compare SHARES")
 print(f"# total {tot / 1000.0:.2f} ms over {len(rows)} launches")
 for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{k[:88]:88s} {n:4d} launches {us:10.1f} us {100.0 * us / tot:5.1f}%")
