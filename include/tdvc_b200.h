@@ -114,6 +114,19 @@ int tdvc_dcn_v2_forward(const float* input, const float* weight, const float* bi
                         int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- DCNv2 backward, the reference's `_ext.dcn_v2_backward` (dcn_v2.h:48-92, dcn_v2_cuda.cu:97-216,
+ * dcn_v2_im2col_cuda.cu:197-327): same tensor conventions as the forward, any geometry; grad_output (N, O, Ho, Wo).
+ * Writes grad_input (N,C,H,W), grad_offset / grad_mask (shapes of offset / mask), grad_weight (O,C,kh,kw), grad_bias (O).
+ * Deterministic (the reference's col2im uses float atomicAdd): grad_input is accumulated as 64-bit fixed point in `workspace`
+ * (>= tdvc_dcn_v2_backward_workspace_bytes(N,C,H,W) bytes, 8-byte aligned), everything else has one owner per element.
+ * `bias` is not needed (its gradient is the plain sum of grad_output).                                                      */
+size_t tdvc_dcn_v2_backward_workspace_bytes(int N, int C, int H, int W);
+int tdvc_dcn_v2_backward(const float* input, const float* weight, const float* offset, const float* mask,
+                         const float* grad_output, float* grad_input, float* grad_offset, float* grad_mask,
+                         float* grad_weight, float* grad_bias, int N, int C, int O, int H, int W, int kh, int kw,
+                         int sh, int sw, int ph, int pw, int dh, int dw, int dg, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* Fused channels-last form used inside the P-frame graph (reference dcn_v2_amp.py:219-234 + :67-69 +
  * pnet.py:180): offsets / mask read straight from the 27*dg-channel conv_offset_mask output, sigmoid,
  * bilinear gather, 9*C -> O contraction, bias, optional fp16 rounding (`round_fp16`, the reference's

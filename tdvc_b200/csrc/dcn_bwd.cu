@@ -1,0 +1,240 @@
+// DCNv2 backward - the reference's `_ext.dcn_v2_backward` (reference main/utils/dcnv2/src/dcn_v2.h:48-92,
+// src/cuda/dcn_v2_cuda.cu:97-216, src/cuda/dcn_v2_im2col_cuda.cu:55-123 (gradient / coordinate weights), :197-327 (col2im,
+// col2im_coord)) for any kernel size / stride / padding / dilation / deformable-group width, contiguous NCHW fp32.
+//
+// The reference materialises grad_col = W^T * grad_output per image (`columns`, C*K x Ho*Wo), scatters it into grad_input with
+// float atomicAdd (col2im: run-to-run different low bits), and re-reads it for grad_offset / grad_mask and, through a second
+// im2col, for grad_weight.  Here nothing of size C*K*Ho*Wo is stored and every result is DETERMINISTIC:
+//   dcn_bwd_sample_kernel  one thread per (n, group, tap, ho, wo): for each channel of the group it forms grad_col on the fly
+//                          (a dot product over the output channels), accumulates grad_mask and both grad_offset components in
+//                          registers (plain stores: each element has one owner) and adds the four bilinear corner terms of
+//                          grad_input as 64-bit FIXED-POINT integers (atomicAdd on integers is associative, so the sum does not
+//                          depend on the order in which threads arrive);
+//   dcn_bwd_finish_kernel  fixed point -> fp32 grad_input;
+//   dcn_bwd_weight_kernel  one CTA per (c, tap): recomputes the modulated sample of every output position, accumulates its
+//                          product with grad_output for all output channels in registers, fixed-order tree over the CTA;
+//   dcn_bwd_bias_kernel    grad_bias[o] = sum grad_output, same tree.
+// The fixed-point scale is a power of two derived on the device from max|grad_output| and max|weight| (dcn_bwd_scale_kernel).
+#include "common.cuh"
+
+namespace tdvc {
+namespace dcnb {
+
+struct Geo {
+  int N, C, O, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, dg;
+};
+
+// max |x| over a tensor -> *out (bits of a non-negative float order like ints)
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+// scale[0] = 2^e with  O * max|w| * max|go| * 2^20 * 2^e <= 2^62 : a single grad_col term is at most O*max|w|*max|go|, and up to
+// 2^20 terms of that size may meet in one input pixel before the 64-bit accumulator could overflow.  scale[1] = 1 / scale[0].
+__global__ void scale_kernel(const float* __restrict__ maxes, int O, double* __restrict__ scale) {
+  const double bound = fmax((double)O * (double)maxes[0] * (double)maxes[1], 1e-30);
+  int e = 0;
+  frexp(bound, &e);               // bound < 2^e
+  const int k = 62 - 20 - e;
+  scale[0] = ldexp(1.0, k);
+  scale[1] = ldexp(1.0, -k);
+}
+
+__device__ __forceinline__ void fx_add(long long* acc, double v, double scale) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)__double2ll_rn(v * scale));
+}
+
+__global__ void __launch_bounds__(128) dcn_bwd_sample_kernel(const float* __restrict__ input, const float* __restrict__ weight,
+                                                             const float* __restrict__ offset, const float* __restrict__ mask,
+                                                             const float* __restrict__ go, long long* __restrict__ gi_fx,
+                                                             float* __restrict__ g_off, float* __restrict__ g_msk,
+                                                             const double* __restrict__ scale_p, Geo q) {
+  const int K = q.kh * q.kw, cpg = q.C / q.dg;
+  const int64_t hw = (int64_t)q.Ho * q.Wo, HW = (int64_t)q.H * q.W;
+  const int64_t total = (int64_t)q.N * q.dg * K * hw;
+  const double scale = scale_p[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % q.Wo);
+    int64_t r = i / q.Wo;
+    const int ho = (int)(r % q.Ho); r /= q.Ho;
+    const int k = (int)(r % K); r /= K;
+    const int g = (int)(r % q.dg);
+    const int n = (int)(r / q.dg);
+    const int ki = k / q.kw, kj = k - ki * q.kw;
+    const int64_t pix = (int64_t)ho * q.Wo + wo;
+    const int64_t off_c = ((int64_t)n * q.dg * K + g * K + k) * 2;
+    const float dy = offset[off_c * hw + pix], dx = offset[(off_c + 1) * hw + pix];
+    const float m = mask[((int64_t)n * q.dg * K + g * K + k) * hw + pix];
+    const float h_im = (float)(ho * q.sh - q.ph + ki * q.dh) + dy;
+    const float w_im = (float)(wo * q.sw - q.pw + kj * q.dw) + dx;
+    float gm = 0.f, gh = 0.f, gw = 0.f;
+    const bool inside = h_im > -1.f && w_im > -1.f && h_im < (float)q.H && w_im < (float)q.W;
+    if (inside) {
+      const float hf = floorf(h_im), wf = floorf(w_im);
+      const int h_low = (int)hf, w_low = (int)wf, h_high = h_low + 1, w_high = w_low + 1;
+      const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw_ = 1.f - lw;
+      const bool t_ok = h_low >= 0, b_ok = h_high <= q.H - 1, l_ok = w_low >= 0, r_ok = w_high <= q.W - 1;
+      const float* go_n = go + (int64_t)n * q.O * hw + pix;
+      for (int cc = 0; cc < cpg; ++cc) {
+        const int c = g * cpg + cc;
+        // grad_col(c, k, ho, wo) = sum_o weight[o][c][k] * grad_output[n][o][ho][wo]   (dcn_v2_cuda.cu:147-153)
+        float gc = 0.f;
+        const float* wp = weight + (int64_t)c * K + k;
+        for (int o = 0; o < q.O; ++o) gc = fmaf(__ldg(wp + (int64_t)o * q.C * K), __ldg(go_n + (int64_t)o * hw), gc);
+        const float* im = input + ((int64_t)n * q.C + c) * HW;
+        const float v1 = (t_ok && l_ok) ? im[(int64_t)h_low * q.W + w_low] : 0.f;
+        const float v2 = (t_ok && r_ok) ? im[(int64_t)h_low * q.W + w_high] : 0.f;
+        const float v3 = (b_ok && l_ok) ? im[(int64_t)h_high * q.W + w_low] : 0.f;
+        const float v4 = (b_ok && r_ok) ? im[(int64_t)h_high * q.W + w_high] : 0.f;
+        // grad_mask: grad_col * bilinear(im)   (dcn_v2_im2col_cuda.cu:307-310)
+        gm = fmaf(gc, hh * hw_ * v1 + hh * lw * v2 + lh * hw_ * v3 + lh * lw * v4, gm);
+        // grad_offset: grad_col * mask * d bilinear / d (h, w)   (dmcn_get_coordinate_weight_cuda, :82-123)
+        gh = fmaf(gc * m, -hw_ * v1 - lw * v2 + hw_ * v3 + lw * v4, gh);
+        gw = fmaf(gc * m, -hh * v1 + hh * v2 - lh * v3 + lh * v4, gw);
+        // grad_input: the four corners get their bilinear weight of grad_col * mask   (col2im, :197-252)
+        const double top = (double)gc * (double)m;
+        long long* gp = gi_fx + ((int64_t)n * q.C + c) * HW;
+        if (t_ok && l_ok) fx_add(gp + (int64_t)h_low * q.W + w_low, top * (double)(hh * hw_), scale);
+        if (t_ok && r_ok) fx_add(gp + (int64_t)h_low * q.W + w_high, top * (double)(hh * lw), scale);
+        if (b_ok && l_ok) fx_add(gp + (int64_t)h_high * q.W + w_low, top * (double)(lh * hw_), scale);
+        if (b_ok && r_ok) fx_add(gp + (int64_t)h_high * q.W + w_high, top * (double)(lh * lw), scale);
+      }
+    }
+    g_off[off_c * hw + pix] = gh;
+    g_off[(off_c + 1) * hw + pix] = gw;
+    g_msk[((int64_t)n * q.dg * K + g * K + k) * hw + pix] = gm;
+  }
+}
+
+__global__ void dcn_bwd_finish_kernel(const long long* __restrict__ fx, float* __restrict__ out, int64_t n,
+                                      const double* __restrict__ scale_p) {
+  const double inv = scale_p[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (float)((double)fx[i] * inv);
+}
+
+// grad_weight[o][c][k] = sum_{n, ho, wo} grad_output[n][o][ho][wo] * mask * bilinear(input[n][c], sample(n, g, k, ho, wo))
+// One CTA per (c, k); OT output channels per pass; thread t walks the positions t, t + 256, ... in a fixed order and the CTA
+// combines its 256 partial sums with a fixed tree: deterministic.
+constexpr int OT = 16;
+__global__ void __launch_bounds__(256) dcn_bwd_weight_kernel(const float* __restrict__ input, const float* __restrict__ offset,
+                                                             const float* __restrict__ mask, const float* __restrict__ go,
+                                                             float* __restrict__ g_w, Geo q) {
+  __shared__ float red[256];
+  const int K = q.kh * q.kw, cpg = q.C / q.dg;
+  const int c = blockIdx.x / K, k = blockIdx.x - c * K;
+  const int g = c / cpg;
+  const int ki = k / q.kw, kj = k - ki * q.kw;
+  const int64_t hw = (int64_t)q.Ho * q.Wo, HW = (int64_t)q.H * q.W;
+  const int64_t npos = (int64_t)q.N * hw;
+  for (int o0 = 0; o0 < q.O; o0 += OT) {
+    float acc[OT];
+#pragma unroll
+    for (int j = 0; j < OT; ++j) acc[j] = 0.f;
+    for (int64_t p = threadIdx.x; p < npos; p += blockDim.x) {
+      const int n = (int)(p / hw);
+      const int64_t pix = p - (int64_t)n * hw;
+      const int ho = (int)(pix / q.Wo), wo = (int)(pix - (int64_t)ho * q.Wo);
+      const int64_t off_c = ((int64_t)n * q.dg * K + g * K + k) * 2;
+      const float h_im = (float)(ho * q.sh - q.ph + ki * q.dh) + offset[off_c * hw + pix];
+      const float w_im = (float)(wo * q.sw - q.pw + kj * q.dw) + offset[(off_c + 1) * hw + pix];
+      if (!(h_im > -1.f && w_im > -1.f && h_im < (float)q.H && w_im < (float)q.W)) continue;
+      const float hf = floorf(h_im), wf = floorf(w_im);
+      const int h_low = (int)hf, w_low = (int)wf, h_high = h_low + 1, w_high = w_low + 1;
+      const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw_ = 1.f - lw;
+      const float* im = input + ((int64_t)n * q.C + c) * HW;
+      const float v1 = (h_low >= 0 && w_low >= 0) ? im[(int64_t)h_low * q.W + w_low] : 0.f;
+      const float v2 = (h_low >= 0 && w_high <= q.W - 1) ? im[(int64_t)h_low * q.W + w_high] : 0.f;
+      const float v3 = (h_high <= q.H - 1 && w_low >= 0) ? im[(int64_t)h_high * q.W + w_low] : 0.f;
+      const float v4 = (h_high <= q.H - 1 && w_high <= q.W - 1) ? im[(int64_t)h_high * q.W + w_high] : 0.f;
+      const float col = (hh * hw_ * v1 + hh * lw * v2 + lh * hw_ * v3 + lh * lw * v4) * mask[((int64_t)n * q.dg * K + g * K + k) * hw + pix];
+      const float* gp = go + ((int64_t)n * q.O + o0) * hw + pix;
+#pragma unroll
+      for (int j = 0; j < OT; ++j)
+        if (o0 + j < q.O) acc[j] = fmaf(__ldg(gp + (int64_t)j * hw), col, acc[j]);
+    }
+    for (int j = 0; j < OT; ++j) {
+      if (o0 + j >= q.O) break;
+      red[threadIdx.x] = acc[j];
+      __syncthreads();
+      for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) g_w[((int64_t)(o0 + j) * q.C + c) * K + k] = red[0];
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dcn_bwd_bias_kernel(const float* __restrict__ go, float* __restrict__ g_b, int N, int O, int64_t hw) {
+  __shared__ float red[256];
+  const int o = blockIdx.x;
+  float s = 0.f;
+  for (int64_t p = threadIdx.x; p < (int64_t)N * hw; p += blockDim.x) {
+    const int64_t n = p / hw;
+    s += go[(n * O + o) * hw + (p - n * hw)];
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) g_b[o] = red[0];
+}
+
+}  // namespace dcnb
+}  // namespace tdvc
+
+using namespace tdvc;
+
+extern "C" size_t tdvc_dcn_v2_backward_workspace_bytes(int N, int C, int H, int W) {
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)N * C * H * W * sizeof(long long) + 256;   // fixed-point grad_input + {max|go|, max|w|, scale, 1/scale}
+}
+
+extern "C" int tdvc_dcn_v2_backward(const float* input, const float* weight, const float* offset, const float* mask,
+                                    const float* grad_output, float* grad_input, float* grad_offset, float* grad_mask,
+                                    float* grad_weight, float* grad_bias, int N, int C, int O, int H, int W, int kh, int kw,
+                                    int sh, int sw, int ph, int pw, int dh, int dw, int dg, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  TDVC_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_offset && grad_mask && grad_weight && grad_bias,
+               "dcn_v2_backward: null pointer");
+  TDVC_REQUIRE(N > 0 && C > 0 && O > 0 && H > 0 && W > 0 && dg > 0 && C % dg == 0, "dcn_v2_backward: bad shape");
+  TDVC_REQUIRE(kh > 0 && kw > 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && ph >= 0 && pw >= 0, "dcn_v2_backward: bad conv geometry");
+  const int Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1, Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
+  TDVC_REQUIRE(Ho > 0 && Wo > 0, "dcn_v2_backward: empty output");
+  TDVC_REQUIRE(workspace != nullptr && workspace_bytes >= tdvc_dcn_v2_backward_workspace_bytes(N, C, H, W) &&
+                   (reinterpret_cast<uintptr_t>(workspace) & 7) == 0,
+               "dcn_v2_backward: workspace too small or misaligned (%zu < %zu)", workspace_bytes,
+               tdvc_dcn_v2_backward_workspace_bytes(N, C, H, W));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t n_in = (int64_t)N * C * H * W;
+  long long* fx = static_cast<long long*>(workspace);
+  float* maxes = reinterpret_cast<float*>(fx + n_in);
+  double* scale = reinterpret_cast<double*>(fx + n_in + 2);
+  if (cudaMemsetAsync(workspace, 0, (size_t)n_in * sizeof(long long) + 64, st) != cudaSuccess) {
+    set_error("dcn_v2_backward: cudaMemsetAsync failed");
+    return TDVC_ECUDA;
+  }
+  const dcnb::Geo q{N, C, O, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, dg};
+  const int64_t n_go = (int64_t)N * O * Ho * Wo, n_w = (int64_t)O * C * kh * kw;
+  auto grid_for = [](int64_t n, int t) { int64_t b = (n + t - 1) / t; return (int)(b < 1 ? 1 : (b > kNumSMs * 16 ? kNumSMs * 16 : b)); };
+  dcnb::absmax_kernel<<<grid_for(n_go, 256), 256, 0, st>>>(grad_output, n_go, maxes);
+  dcnb::absmax_kernel<<<grid_for(n_w, 256), 256, 0, st>>>(weight, n_w, maxes + 1);
+  dcnb::scale_kernel<<<1, 1, 0, st>>>(maxes, O, scale);
+  const int64_t n_s = (int64_t)N * dg * kh * kw * Ho * Wo;
+  dcnb::dcn_bwd_sample_kernel<<<grid_for(n_s, 128), 128, 0, st>>>(input, weight, offset, mask, grad_output, fx, grad_offset, grad_mask,
+                                                                 scale, q);
+  TDVC_CHECK_LAUNCH("dcn_bwd_sample");
+  dcnb::dcn_bwd_finish_kernel<<<grid_for(n_in, 256), 256, 0, st>>>(fx, grad_input, n_in, scale);
+  dcnb::dcn_bwd_weight_kernel<<<C * kh * kw, 256, 0, st>>>(input, offset, mask, grad_output, grad_weight, q);
+  dcnb::dcn_bwd_bias_kernel<<<O, 256, 0, st>>>(grad_output, grad_bias, N, O, (int64_t)Ho * Wo);
+  TDVC_CHECK_LAUNCH("dcn_bwd");
+  return TDVC_OK;
+}

@@ -54,6 +54,8 @@ SIGNATURES = {
     "tdvc_conv2d_pack_f16": [C.POINTER(ConvParams), vp, vp],
     "tdvc_dcn_v2_workspace_bytes": [i32] * 6,
     "tdvc_dcn_v2_forward": [vp] * 6 + [i32] * 14 + [vp, sz, vp],
+    "tdvc_dcn_v2_backward_workspace_bytes": [i32] * 4,
+    "tdvc_dcn_v2_backward": [vp] * 10 + [i32] * 14 + [vp, sz, vp],
     "tdvc_dcn_nhwc": [C.POINTER(DcnParams), vp],
     "tdvc_dcn_f16_bytes": [i32],
     "tdvc_dcn_pack_f16": [vp, i32, i32, i32, vp, vp],
@@ -106,6 +108,7 @@ def load():
         fn.restype = C.c_int
     lib.tdvc_last_error.restype = C.c_char_p
     lib.tdvc_dcn_v2_workspace_bytes.restype = C.c_size_t
+    lib.tdvc_dcn_v2_backward_workspace_bytes.restype = C.c_size_t
     lib.tdvc_conv2d_f16_bytes.restype = C.c_size_t
     lib.tdvc_dcn_f16_bytes.restype = C.c_size_t
     _lib = lib

@@ -389,6 +389,50 @@ def test_dcn_generic_geometry_vs_torchvision(dev):
     assert (got - want).abs().max() < 2e-5 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64, 13, 17, 8, 3, 3, 1, 1, 1, 1, 1, 1), (1, 16, 24, 9, 7, 2, 3, 3, 1, 1, 1, 1, 1, 1),
+                                   (2, 4, 6, 11, 12, 2, 5, 3, 2, 1, 2, 1, 1, 2)])
+def test_dcn_backward_vs_torchvision_autograd(dev, shape):
+    """`dcn_v2_backward` (reference dcn_v2.h:48-92) against autograd through torchvision.ops.deform_conv2d on the CPU (the same
+    MXNet-lineage arithmetic): all five gradients, offsets with many samples outside the image, TDVC's geometry
+    and a generic one; and it is deterministic (the reference's col2im is not: float atomicAdd)."""
+    import torchvision.ops
+    from tdvc_b200.ops import dcn_v2_backward
+    N, C, O, H, W, dg, kh, kw, sh, sw, ph, pw, dh, dw = shape
+    torch.manual_seed(13)
+    Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    x = torch.randn(N, C, H, W, requires_grad=True)
+    wgt = (torch.randn(O, C, kh, kw) * 0.1).requires_grad_()
+    b = torch.randn(O, requires_grad=True)
+    off = (torch.randn(N, dg * 2 * kh * kw, Ho, Wo) * 3.0).requires_grad_()
+    msk = torch.rand(N, dg * kh * kw, Ho, Wo, requires_grad=True)
+    go = torch.randn(N, O, Ho, Wo)
+    out = torchvision.ops.deform_conv2d(x, off, wgt, b, stride=(sh, sw), padding=(ph, pw), dilation=(dh, dw), mask=msk)
+    out.backward(go)
+    args = [t.detach().to(dev) for t in (x, wgt, b, off, msk, go)] + [kh, kw, sh, sw, ph, pw, dh, dw, dg]
+    got = dcn_v2_backward(*args)
+    again = dcn_v2_backward(*args)
+    for name, g, w, g2 in zip(("input", "offset", "mask", "weight", "bias"), got, (x.grad, off.grad, msk.grad, wgt.grad, b.grad), again):
+        assert g.shape == w.shape, name
+        assert (g.cpu() - w).abs().max().item() <= 2e-4 * max(1.0, w.abs().max().item()), name
+        assert torch.equal(g, g2), f"grad_{name} is not deterministic"
+
+
+def test_dcn_gradcheck_like_reference(dev):
+    """reference main/utils/dcnv2/testcuda.py:73-101 (check_gradient_dconv): torch.autograd.gradcheck of the autograd function
+    built on the two native ops, same sizes and tolerances."""
+    from torch.autograd import gradcheck
+    from tdvc_b200.ops import dcn_v2_conv
+    torch.manual_seed(2)
+    N, inC, inH, inW, outC, kH, kW, dg = 2, 2, 4, 4, 2, 3, 3, 1
+    x = (torch.rand(N, inC, inH, inW, device=dev) * 0.01).requires_grad_()
+    off = (torch.randn(N, dg * 2 * kW * kH, inH, inW, device=dev) * 2).requires_grad_()
+    msk = torch.sigmoid(torch.rand(N, dg * kW * kH, inH, inW, device=dev)).requires_grad_()
+    wgt = torch.randn(outC, inC, kH, kW, device=dev).requires_grad_()
+    b = torch.rand(outC, device=dev).requires_grad_()
+    assert gradcheck(dcn_v2_conv, (x, off, msk, wgt, b, 1, 1, 1, dg), eps=1e-3, atol=1e-4, rtol=1e-2, nondet_tol=0.0)
+
+
 def test_dcn_errors_like_reference(dev):
     from tdvc_b200.ops import dcn_v2_forward
     x = torch.randn(1, 8, 4, 4, device=dev)
