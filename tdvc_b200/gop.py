@@ -117,6 +117,37 @@ def code_gop(net, i_frame, p_frames, enable_amp=False, keep_recon=False, with_ms
     return out
 
 
+def validate(dataset, net, enable_amp=True, device=None, with_msssim=True, gops=None):
+    """The reference's `validation` (reference tools/predict.py:35-110) over a `tdvc_b200.data.GopDataset`: every GOP is coded
+    by `code_gop`; bpp / PSNR / MS-SSIM are averaged over ALL frames, the BPG-coded I-frame of each GOP included with the bpp /
+    PSNR / MS-SSIM its loader reports (:47-50), while bpp_mv / bpp_res / mse average over the P-frames only (:95-97).
+    Returns (bpp, bpp_mv, bpp_res, psnr, msssim, mse) like the reference (:110).  `gops`: indices to code (a rank's shard)."""
+    device = device or next(net.parameters()).device
+    tot = torch.zeros(7, device=device, dtype=torch.float64)
+    n_i, i_bpp, i_psnr, i_ms = 0, 0.0, 0.0, 0.0
+    for g in (range(len(dataset)) if gops is None else gops):
+        p_frames, i_frame, bpp_i, psnr_i, _, raw = dataset[g]
+        p_frames, i_frame = p_frames.to(device), i_frame.to(device).unsqueeze(0)
+        res = code_gop(net, i_frame, p_frames, enable_amp=enable_amp, with_msssim=with_msssim)
+        tot += gop_stats(res)
+        n_i += 1
+        i_bpp += float(bpp_i)
+        i_psnr += float(psnr_i)
+        if with_msssim:
+            from tdvc_b200.metrics import ms_ssim
+            i_ms += float(ms_ssim(raw[0:1].to(device), i_frame, data_range=1.0))
+    return combine_with_iframes(summarise(tot), n_i, i_bpp, i_psnr, i_ms)
+
+
+def combine_with_iframes(p_summary, n_i, sum_i_bpp, sum_i_psnr, sum_i_msssim):
+    """Averages as the reference forms them (tools/predict.py:47-50, 86-110): the lists `bpps`, `psnrs`, `ssims` hold one entry per
+    I-frame and per P-frame; `mvs`, `ress`, `mses` hold the P-frames only."""
+    n_p = p_summary["frames"]
+    n = max(n_p + n_i, 1)
+    return ((p_summary["bpp"] * n_p + sum_i_bpp) / n, p_summary["bpp_mv"], p_summary["bpp_res"],
+            (p_summary["psnr"] * n_p + sum_i_psnr) / n, (p_summary["msssim"] * n_p + sum_i_msssim) / n, p_summary["mse"])
+
+
 def gop_stats(res):
     """Per-GOP sums in the reference's reporting units -> fp64 tensor
     [sum bpp, sum bpp_mv, sum bpp_res, sum psnr, sum msssim (0 unless code_gop(with_msssim=True)), sum mse, n_frames]."""

@@ -606,3 +606,38 @@ def test_training_mode_aux_loss_backward_and_own_noise(net, oracle_model, dev):
     assert buf.min().item() >= -0.5 and buf.max().item() < 0.5
     assert abs(buf.mean().item()) < 2e-3 and abs(buf.var().item() - 1.0 / 12) < 1e-3
     assert abs(torch.corrcoef(torch.stack([buf[:-1], buf[1:]]))[0, 1].item()) < 5e-3
+
+
+def test_validate_over_a_gop_dataset(net, dev, tmp_path):
+    """tdvc_b200.gop.validate = the reference's `validation` (tools/predict.py:35-110) over frames on disk laid out as the
+    reference's datasets are (tdvc_b200/data.py): I+P averages, the P-frame part equal to coding the GOPs by hand."""
+    import os
+    from torchvision.io import write_png
+    from tdvc_b200 import data as D
+    from tdvc_b200 import gop as G
+    from tdvc_b200 import synth
+    net.conv_impl, net.precision = 0, "auto"
+    gop, qp = 4, 27
+    seqs = {"a_416x240_50": synth.make_gop(56, 120, gop=8, seed=91), "b_416x240_50": synth.make_gop(56, 120, gop=4, seed=92)}
+    for seq, fr in seqs.items():
+        os.makedirs(tmp_path / "ori_img" / seq)
+        os.makedirs(tmp_path / "compress_img_bpg" / seq / str(qp))
+        for i in range(fr.shape[0]):
+            write_png((fr[i] * 255).round().to(torch.uint8), str(tmp_path / "ori_img" / seq / f"im{i + 1:03d}.png"))
+        for g in range(fr.shape[0] // gop):
+            ref = ((fr[g * gop] * 255).round() + 2).clamp(0, 255).to(torch.uint8)
+            write_png(ref, str(tmp_path / "compress_img_bpg" / seq / str(qp) / f"im{g * gop + 1:03d}_{qp}.png"))
+            open(tmp_path / "compress_img_bpg" / seq / str(qp) / f"im{g * gop + 1:03d}_{qp}.txt", "w").write("0.75\n")
+    ds = D.GopDataset(str(tmp_path), 2048, gop, testfull=True)
+    assert len(ds) == 3
+    bpp, mv, rs, psnr, ms, mse = G.validate(ds, net, enable_amp=False)
+    tot = torch.zeros(7, device=dev, dtype=torch.float64)
+    i_psnr = 0.0
+    for g in range(3):
+        p_frames, i_frame, _, ps, _, _ = ds[g]
+        tot += G.gop_stats(G.code_gop(net, i_frame.unsqueeze(0).to(dev), p_frames.to(dev), with_msssim=True))
+        i_psnr += ps
+    summ = G.summarise(tot)
+    assert summ["frames"] == 9 and abs(mv - summ["bpp_mv"]) < 1e-9 and abs(rs - summ["bpp_res"]) < 1e-9 and abs(mse - summ["mse"]) < 1e-12
+    assert abs(bpp - (summ["bpp"] * 9 + 3 * 0.75) / 12) < 1e-9 and abs(psnr - (summ["psnr"] * 9 + i_psnr) / 12) < 1e-9
+    assert 0.0 < ms <= 1.0 and math.isfinite(psnr)

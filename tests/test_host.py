@@ -204,3 +204,51 @@ def test_stats_allreduce_world2_gloo():
     from tdvc_b200 import gop as G
     summ = G.summarise(torch.tensor(res[0][1], dtype=torch.float64))
     assert summ["frames"] == 66 and abs(summ["psnr"] - 30.0) < 1e-9 and abs(summ["bpp"] - 2.5) < 1e-9
+
+
+def test_gop_dataset_and_iframe_averaging(tmp_path):
+    """tdvc_b200.data.GopDataset lists and loads GOPs like the reference's UVGDataSet / HEVCDataSet (reference
+    main/dataloader/dataset.py:16-193) and `combine_with_iframes` averages like tools/predict.py:47-50,86-110."""
+    from torchvision.io import write_png
+    from tdvc_b200 import data as D
+    from tdvc_b200 import gop as G
+    assert [D.qp_for_lambda(l) for l in (512, 1024, 2048, 4096, 64)] == [37, 32, 27, 22, 27]
+    assert sorted(["im10.png", "im2.png", "im1.png"], key=D.natural_key) == ["im1.png", "im2.png", "im10.png"]
+    torch.manual_seed(0)
+    gop, qp = 3, 27
+    frames = {}
+    for seq, nfr in (("Seq10_416x240_50", 7), ("Seq2_416x240_30", 6), ("BQSquare_416x240_60", 6)):
+        os.makedirs(tmp_path / "ori_img" / seq)
+        os.makedirs(tmp_path / "compress_img_bpg" / seq / str(qp))
+        for i in range(nfr):
+            img = (torch.rand(3, 12, 20) * 255).to(torch.uint8)
+            frames[(seq, i + 1)] = img
+            write_png(img, str(tmp_path / "ori_img" / seq / f"im{i + 1:03d}.png"))
+        for g in range(nfr // gop):
+            ref = (frames[(seq, g * gop + 1)].int() + 3).clamp(0, 255).to(torch.uint8)
+            write_png(ref, str(tmp_path / "compress_img_bpg" / seq / str(qp) / f"im{g * gop + 1:03d}_{qp}.png"))
+            open(tmp_path / "compress_img_bpg" / seq / str(qp) / f"im{g * gop + 1:03d}_{qp}.txt", "w").write(f"{0.5 + g}\n")
+    ds = D.GopDataset(str(tmp_path), 2048, gop, testfull=True)
+    assert len(ds) == 2 + 2 + 2
+    order = [os.path.basename(os.path.dirname(p[0])) for p in ds.input]
+    assert order == ["BQSquare_416x240_60"] * 2 + ["Seq2_416x240_30"] * 2 + ["Seq10_416x240_50"] * 2   # natural order
+    p_frames, i_frame, bpp_i, psnr_i, names, raw = ds[5]
+    assert p_frames.shape == (2, 3, 12, 20) and raw.shape == (3, 3, 12, 20) and bpp_i == 1.5 and names[0].endswith("im004.png")
+    assert torch.equal(raw[1], frames[("Seq10_416x240_50", 5)].float() / 255.0)
+    want_mse = ((frames[("Seq10_416x240_50", 4)].float() / 255 - i_frame) ** 2).mean().item()
+    assert abs(psnr_i - 10 * torch.log10(torch.tensor(1.0 / want_mse)).item()) < 1e-4
+    hevc = D.GopDataset(str(tmp_path), 2048, gop, testfull=True, hevc_class="D")
+    assert len(hevc) == 2 and all("BQSquare" in p for p in hevc.ref)
+    # averaging: 2 I-frames (bpp 0.5, 1.5; psnr 30, 32) + 4 P-frames (bpp 0.1, psnr 35)
+    summ = {"bpp": 0.1, "bpp_mv": 0.04, "bpp_res": 0.06, "psnr": 35.0, "msssim": 0.9, "mse": 1e-3, "frames": 4}
+    bpp, mv, rs, psnr, ms, mse = G.combine_with_iframes(summ, 2, 2.0, 62.0, 1.9)
+    assert abs(bpp - (0.4 + 2.0) / 6) < 1e-12 and abs(psnr - (140 + 62) / 6) < 1e-12 and abs(ms - (3.6 + 1.9) / 6) < 1e-12
+    assert (mv, rs, mse) == (0.04, 0.06, 1e-3)
+
+
+def test_shared_library_has_no_libcuda_dependency():
+    """The library must load on a host without a driver: the driver entry point it needs is resolved at run time."""
+    import subprocess
+    from tdvc_b200 import lib as L
+    out = subprocess.run(["readelf", "-d", L.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcudart" in out and "libcuda.so" not in out
