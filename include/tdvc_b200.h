@@ -71,7 +71,10 @@ typedef struct {
   int32_t shuffle;          /* 0 or 2 */
   int32_t impl;
   const void* weight_f16;  /* tcgen05 path: fp16 (hi | lo*2^12) weight blocks built by tdvc_conv2d_pack_f16, or NULL */
-  float* chan_sum;          /* optional [N][gridDim-dependent] — reserved for fused SE partial sums */
+  float* chan_sum;          /* optional, tcgen05 path: partial channel sums of the stored output, [rows][N][cout] floats with
+                               rows = tdvc_conv2d_chan_sum_rows(p) (the caller zeroes the buffer): the squeeze-excitation mean of
+                               reference inflate.py:189-207 comes out of the producing layer's epilogue, tdvc_se_apply(nblk = rows)
+                               finishes it.  Deterministic (one owner per cell, fixed walk order).  NULL: not computed */
   int32_t w_shift;          /* tcgen05 split scheme (tdvc_conv2d_f16_is_split): the fp16 weight blocks hold w * 2^w_shift, chosen by
                                the caller so that max|w| * 2^w_shift lies in [2^13, 2^14]; same value at pack time and at launch */
   int32_t order;            /* tcgen05 path: 1 = walk the output tiles in descending order.  Alternating the direction between
@@ -99,6 +102,8 @@ int tdvc_conv2d_f16_is_split(const TdvcConvParams* p);
 /* which kernel tdvc_conv2d runs for *p, as fp16 MMA products issued per algorithmic MAC: 0 = an exact fp32 SIMT kernel,
  * 4 = hi/lo rows, 3 = split scheme, 1 = one product; -1 = invalid parameters (bench.py's `products_per_mac`) */
 int tdvc_conv2d_products(const TdvcConvParams* p);
+/* rows of the `chan_sum` buffer tdvc_conv2d would fill for *p; 0 = this launch cannot produce channel sums */
+int tdvc_conv2d_chan_sum_rows(const TdvcConvParams* p);
 
 /* ---- DCNv2 forward, the reference's `_ext.dcn_v2_forward` (dcn_v2.h:9-46): contiguous NCHW fp32,
  * offset (N, 2*dg*kh*kw, H, W) ordered [g][tap][dy,dx], mask (N, dg*kh*kw, H, W), weight (O, C, kh, kw),
@@ -195,11 +200,14 @@ int tdvc_round_half_even(const float* x, float* out, int64_t n, void* stream);
  * se_partial_sums: partial[b][n][c] = sum over a slab of pixels (deterministic two-stage mean).
  * se_apply: s = sigmoid(W2 relu(W1 mean + b1) + b2) computed once per image (a one-block kernel that overwrites
  * partial[n*C + c] with the gate), then out = act(x*s) (+ res) streamed by a second kernel.
- * w1: [Cr][C], w2: [C][Cr] (the 1x1 conv weights as stored). nblk <= 1024.                          */
+ * w1: [Cr][C], w2: [C][Cr] (the 1x1 conv weights as stored). nblk <= 1024.
+ * Optional second output in the same pass: out2 = sub_from - out (the residual `input_feat - prediction` of reference
+ * pnet.py:55 when `out` is the prediction); both NULL otherwise.                                      */
 int tdvc_se_partial_sums(const float* x, int ld, int N, int64_t HW, int C, float* partial, int nblk, void* stream);
 int tdvc_se_apply(const float* x, int ld, float* partial, int nblk, const float* w1, const float* b1,
                   const float* w2, const float* b2, int N, int64_t HW, int C, int Cr, int act, float slope,
-                  const float* res, int res_ld, float* out, int out_ld, void* stream);
+                  const float* res, int res_ld, float* out, int out_ld, const float* sub_from, int sub_ld,
+                  float* out2, int out2_ld, void* stream);
 
 /* ---- entropy models -> bits (compressai EntropyBottleneck / GaussianConditional forward in eval mode,
  * SURVEY App. A; reductions of reference pnet.py:38-43,62-67).  `acc` is a device double: += sum ln(p).

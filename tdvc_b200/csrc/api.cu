@@ -14,7 +14,7 @@ void set_error(const char* fmt, ...) {
 int conv2d_validate(const TdvcConvParams* p);
 int conv2d_simt(const TdvcConvParams& p, cudaStream_t st);
 int conv2d_tc_supported(const TdvcConvParams& p);
-int conv2d_tc(const TdvcConvParams& p, cudaStream_t st);
+int conv2d_tc(const TdvcConvParams& p, cudaStream_t st, int* rows_only = nullptr);
 int conv2d_small_supported(const TdvcConvParams& p);
 int conv2d_small(const TdvcConvParams& p, cudaStream_t st);
 }  // namespace tdvc
@@ -34,13 +34,17 @@ extern "C" int tdvc_conv2d(const TdvcConvParams* p, void* stream) {
     }
     return tdvc::conv2d_tc(*p, st);
   }
-  if (p->out_absmax != nullptr && (p->impl == 3 || (p->impl == 0 && tdvc::conv2d_small_supported(*p)))) {
-    tdvc::set_error("conv2d: out_absmax is not available on the <= 4-channel kernel");
+  if ((p->out_absmax != nullptr || p->chan_sum != nullptr) && (p->impl == 3 || (p->impl == 0 && tdvc::conv2d_small_supported(*p)))) {
+    tdvc::set_error("conv2d: out_absmax / chan_sum are not available on the <= 4-channel kernel");
     return TDVC_EINVAL;
   }
   if (p->impl == 3) return tdvc::conv2d_small(*p, st);
   if (p->impl == 0 && tdvc::conv2d_small_supported(*p)) return tdvc::conv2d_small(*p, st);
   if (p->impl == 0 && tdvc::conv2d_tc_supported(*p)) return tdvc::conv2d_tc(*p, st);
+  if (p->chan_sum != nullptr) {
+    tdvc::set_error("conv2d: chan_sum is produced by the tcgen05 kernel only (ask tdvc_conv2d_chan_sum_rows first)");
+    return TDVC_EINVAL;
+  }
   return tdvc::conv2d_simt(*p, st);
 }
 
@@ -53,4 +57,13 @@ extern "C" int tdvc_conv2d_products(const TdvcConvParams* p) {
   if (!tdvc::conv2d_tc_supported(*p)) return p->impl == 2 ? -1 : 0;
   if (p->products == 1) return 1;
   return tdvc_conv2d_f16_is_split(p) ? 3 : 4;
+}
+
+// rows of the `chan_sum` buffer ([rows][N][cout] floats) tdvc_conv2d would fill for *p; 0 = this launch cannot produce channel
+// sums (an exact fp32 SIMT kernel would run, several output-channel tiles, planar or pixel-shuffled output)
+extern "C" int tdvc_conv2d_chan_sum_rows(const TdvcConvParams* p) {
+  if (tdvc_conv2d_products(p) <= 0) return 0;
+  int rows = 0;
+  if (tdvc::conv2d_tc(*p, nullptr, &rows) != TDVC_OK) return 0;
+  return rows;
 }

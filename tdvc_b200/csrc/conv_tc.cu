@@ -83,7 +83,10 @@ struct Cfg {
   // channels) are bound by the epilogue's instruction stream while their cp.async-staged producers have little to do, so
   // there the same 640 threads are 12 epilogue + 6 producer warps (3 epilogue warps per TMEM lane quadrant: 5, 5 and 6 of the
   // sixteen 16-column chunks; 16 + 2 made the two producer warps the bottleneck: GDN 0.147 -> 0.194 ms)
-  static constexpr bool WIDE_EPI = (KS == 1 && S == 1 && DIRECT);
+#ifndef TDVC_CONV_TC_WIDE16
+#define TDVC_CONV_TC_WIDE16 0   // A/B switch: 12 + 6 warp roles for the image-input 3x3 layers as well (see below)
+#endif
+  static constexpr bool WIDE_EPI = (KS == 1 && S == 1 && DIRECT) || (TDVC_CONV_TC_WIDE16 && KS == 3 && S == 1 && CK == 16 && NPH == 1 && !DIRECT);
   static constexpr int EPIW = WIDE_EPI ? 12 : kEpiWarps, PRODW = WIDE_EPI ? 6 : kProdWarps;
   static_assert(EPIW + PRODW + 2 == kThreads / 32 && EPIW % 4 == 0, "warp roles");
   static constexpr int NGRP = EPIW / 4;                      // epilogue warps per TMEM lane quadrant: they share the 16 chunks
@@ -341,6 +344,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     const int sq_shift = square_shift(p);   // GDN / IGDN: the accumulator holds the norm * 2^-sq_shift
     float amax = 0.f;                       // max |v| over the values this lane stored (TdvcConvParams::out_absmax)
     const bool track = p.out_absmax != nullptr;
+    // TdvcConvParams::chan_sum (squeeze-excitation means fused into the producing layer): running sum of the values this lane
+    // stored for its channel in image csum_n; flushed to row (CTA, epilogue column group, row phase) when the image changes.
+    // Every (row, image, channel) cell has one owner and the items of a CTA are walked in a fixed order: deterministic.
+    const bool csum_on = p.chan_sum != nullptr;
+    float csum = 0.f;
+    int csum_n = -1;
     if constexpr (C::DIRECT) {
     // ---- 128 output channels per item, one accumulator row per channel (TMEM lane = channel): every lane stores its own
     //      channel straight from the registers tcgen05.ld filled - per pixel the 32 lanes of a warp write 128 contiguous
@@ -376,6 +385,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       const int co = it.jt * C::NTT + cch;
       const bool ch_ok = co < cout;
       const float wbias = (p.bias && ch_ok) ? __ldg(p.bias + co) : 0.f;
+      if (csum_on && it.n != csum_n) {
+        if (csum_n >= 0 && ch_ok)
+          p.chan_sum[((int64_t)((blockIdx.x * C::NGRP + grp) * NPHS + phi) * p.N + csum_n) * cout + co] = csum;
+        csum_n = it.n;
+        csum = 0.f;
+      }
       int oc = co, qy = 0, qx = 0;
       if (sh == 2) {
         const int q = ch_ok ? co / cr : 0;
@@ -533,6 +548,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             if (track)
 #pragma unroll
               for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(o[h2 * 8 + k]));
+            if (csum_on)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) csum += o[h2 * 8 + k];
           }
         } else {         // ragged right edge (Wo % 8 != 0): one pixel at a time
 #pragma unroll 1
@@ -551,9 +569,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             if (r20) v += __ldg(r20 + ty * r2_rs + k * r2_xs);
             o0[ty * o_rs + k * o_xs] = v;
             amax = fmaxf(amax, fabsf(v));
+            csum += v;
           }
         }
       }
+    }
+    if (csum_on && csum_n >= 0) {
+      const int co = cch;   // chan_sum needs a single output-channel tile (launch() checks it)
+      if (co < cout) p.chan_sum[((int64_t)((blockIdx.x * C::NGRP + grp) * NPHS + phi) * p.N + csum_n) * cout + co] = csum;
     }
     if constexpr (PLN != 0) {
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every staged box has been written out
@@ -598,6 +621,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       mbar_wait(bar(ACC_FULL + sa), (acc_it >> 1) & 1);
       tc_fence_after();
       const int co = it.jt * C::NTT + cch;   // this lane's output channel (same for its hi and lo lane)
+      if (csum_on && it.n != csum_n) {   // (uniform over the warp: all lanes see the same item)
+        const float both = csum + __shfl_xor_sync(0xffffffffu, csum, 16);   // the two tile rows of a chunk sit in lanes l, l ^ 16
+        if (csum_n >= 0 && part == 0 && co < cout)
+          p.chan_sum[((int64_t)((blockIdx.x * C::NGRP + grp) * NPHS + phi) * p.N + csum_n) * cout + co] = both;
+        csum_n = it.n;
+        csum = 0.f;
+      }
       float wbias = 0.f;                           // added once, on the lo row
       if (part && p.bias && co < cout) wbias = __ldg(p.bias + co);
       // where the channel lands (PixelShuffle(2) folded into the store: co' = q*(cout/4) + c)
@@ -727,6 +757,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
           if (track && co < cout)
 #pragma unroll
             for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(o[k]));
+          if (csum_on)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) csum += o[k];
         } else {         // ragged right edge (Wo % 8 != 0): one pixel at a time
 #pragma unroll 1
           for (int k = 0; k < nx; ++k) {
@@ -742,9 +775,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
             if (r20) v += __ldg(r20 + ty * r2_rs + k * r2_xs);
             op[k * o_xs] = v;
             if (co < cout) amax = fmaxf(amax, fabsf(v));
+            csum += v;
           }
         }
       }
+    }
+    if (csum_on) {
+      const float both = csum + __shfl_xor_sync(0xffffffffu, csum, 16);
+      if (csum_n >= 0 && part == 0 && cch < cout)
+        p.chan_sum[((int64_t)((blockIdx.x * C::NGRP + grp) * NPHS + phi) * p.N + csum_n) * cout + cch] = both;
     }
     }
     if (track) absmax_commit(p.out_absmax, amax);
@@ -1067,12 +1106,19 @@ static bool choose(const TdvcConvParams& p, Choice* c) {
 }
 
 template <int KS, int CK, int S, int SPLIT, int NPH = 1, int PLN = 0, int PR = 0>
-static int launch(const TdvcConvParams& p, cudaStream_t st) {
+static int launch(const TdvcConvParams& p, cudaStream_t st, int* rows_only) {
   using C = Cfg<KS, CK, S, SPLIT, NPH, PLN, PR>;
+  if (rows_only != nullptr) {   // query: rows of the chan_sum buffer this launch would write (CTAs x epilogue column groups x phases)
+    const int64_t it = (int64_t)p.N * cdiv(p.Wo, TW) * cdiv(p.Ho, C::THO) * cdiv(p.cout, C::NTT);
+    *rows_only = (p.cout <= C::NTT && !p.out_planar && p.shuffle == 0) ? (int)(it < kNumSMs ? it : kNumSMs) * C::NGRP * NPH : 0;
+    return TDVC_OK;
+  }
   static int smem_done[kMaxDevices] = {0};
   if (int rc = ensure_dynamic_smem(conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN, PR>, C::SMEM, smem_done, "conv_tc")) return rc;
   if (C::DIRECT) TDVC_REQUIRE(p.w_shift >= -100 && p.w_shift <= 100, "conv_tc: w_shift %d out of range", p.w_shift);
   TDVC_REQUIRE(NPH == 1 || !p.out_planar, "conv_tc: planar output is not available for row-phase items");
+  TDVC_REQUIRE(p.chan_sum == nullptr || (p.cout <= C::NTT && !p.out_planar && p.shuffle == 0),
+               "conv_tc: chan_sum needs a single output-channel tile (cout %d <= %d), NHWC output, no pixel shuffle", p.cout, C::NTT);
   const int tiles_x = cdiv(p.Wo, TW), tiles_y = cdiv(p.Ho, C::THO);
   const int n_jt = cdiv(p.cout, C::NTT), n_units = cdiv(p.cin, CK);
   const int64_t items = (int64_t)p.N * tiles_x * tiles_y * n_jt;
@@ -1127,35 +1173,35 @@ int conv2d_tc_supported(const TdvcConvParams& p) {
   return 1;
 }
 
-int conv2d_tc(const TdvcConvParams& p, cudaStream_t st) {
+int conv2d_tc(const TdvcConvParams& p, cudaStream_t st, int* rows_only) {
   tc::Choice c;
   if (!tc::choose(p, &c)) {
     set_error("conv_tc: unsupported shape");
     return TDVC_EINVAL;
   }
   if (c.pr == 1) {
-    if (c.ks == 3 && c.nph == 2) return tc::launch<3, 32, 1, 0, 2, 0, 1>(p, st);
-    if (c.ks == 3) return tc::launch<3, 32, 1, 0, 1, 0, 1>(p, st);
-    if (c.ks == 1) return tc::launch<1, 32, 1, 0, 1, 0, 1>(p, st);
+    if (c.ks == 3 && c.nph == 2) return tc::launch<3, 32, 1, 0, 2, 0, 1>(p, st, rows_only);
+    if (c.ks == 3) return tc::launch<3, 32, 1, 0, 1, 0, 1>(p, st, rows_only);
+    if (c.ks == 1) return tc::launch<1, 32, 1, 0, 1, 0, 1>(p, st, rows_only);
   } else if (c.split) {
-    if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2, 1>(p, st);
-    if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2, 1>(p, st);
+    if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2, 1>(p, st, rows_only);
+    if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2, 1>(p, st, rows_only);
     // DCN offset / mask head: planar output through TMA tensor stores (needs 16-byte aligned planes and row pitch)
     if (c.ks == 3 && p.out_planar && (p.Wo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
-      return tc::launch<3, 32, 1, 1, 1, 1>(p, st);
-    if (c.ks == 3) return tc::launch<3, 32, 1, 1>(p, st);
-    if (c.ks == 1) return tc::launch<1, 32, 1, 1>(p, st);
-    if (c.ks == 5) return tc::launch<5, 32, 1, 1>(p, st);
+      return tc::launch<3, 32, 1, 1, 1, 1>(p, st, rows_only);
+    if (c.ks == 3) return tc::launch<3, 32, 1, 1>(p, st, rows_only);
+    if (c.ks == 1) return tc::launch<1, 32, 1, 1>(p, st, rows_only);
+    if (c.ks == 5) return tc::launch<5, 32, 1, 1>(p, st, rows_only);
   } else {
-    if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2, 0>(p, st);
-    if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2, 0>(p, st);
-    if (c.ks == 3 && c.ck == 32) return tc::launch<3, 32, 1, 0>(p, st);
-    if (c.ks == 3 && c.ck == 16) return tc::launch<3, 16, 1, 0>(p, st);
-    if (c.ks == 1) return tc::launch<1, 32, 1, 0>(p, st);
-    if (c.ks == 5) return tc::launch<5, 32, 1, 0>(p, st);
-    if (c.ks == 7 && c.nph == 2) return tc::launch<7, 16, 1, 0, 2>(p, st);
-    if (c.ks == 7 && c.ck == 32) return tc::launch<7, 32, 1, 0>(p, st);
-    if (c.ks == 7 && c.ck == 16) return tc::launch<7, 16, 1, 0>(p, st);
+    if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2, 0>(p, st, rows_only);
+    if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2, 0>(p, st, rows_only);
+    if (c.ks == 3 && c.ck == 32) return tc::launch<3, 32, 1, 0>(p, st, rows_only);
+    if (c.ks == 3 && c.ck == 16) return tc::launch<3, 16, 1, 0>(p, st, rows_only);
+    if (c.ks == 1) return tc::launch<1, 32, 1, 0>(p, st, rows_only);
+    if (c.ks == 5) return tc::launch<5, 32, 1, 0>(p, st, rows_only);
+    if (c.ks == 7 && c.nph == 2) return tc::launch<7, 16, 1, 0, 2>(p, st, rows_only);
+    if (c.ks == 7 && c.ck == 32) return tc::launch<7, 32, 1, 0>(p, st, rows_only);
+    if (c.ks == 7 && c.ck == 16) return tc::launch<7, 16, 1, 0>(p, st, rows_only);
   }
   set_error("conv_tc: no instantiation for ks=%d ck=%d stride=%d split=%d", c.ks, c.ck, c.s, c.split);
   return TDVC_EINVAL;

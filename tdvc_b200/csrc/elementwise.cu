@@ -227,7 +227,8 @@ __global__ void se_scale_kernel(float* __restrict__ partial, int nblk, const flo
 
 __global__ void se_apply_kernel(const float* __restrict__ x, int ld, const float* __restrict__ gate,
                                 int N, int64_t HW, int C, int act, float slope,
-                                const float* __restrict__ res, int res_ld, float* __restrict__ out, int out_ld) {
+                                const float* __restrict__ res, int res_ld, float* __restrict__ out, int out_ld,
+                                const float* __restrict__ sub_from, int sub_ld, float* __restrict__ out2, int out2_ld) {
   extern __shared__ float sh[];
   float* sc = sh;              // [C]
   const int n = blockIdx.y;
@@ -239,11 +240,13 @@ __global__ void se_apply_kernel(const float* __restrict__ x, int ld, const float
   const float* xb = x + (int64_t)n * HW * ld;
   float* ob = out + (int64_t)n * HW * out_ld;
   const float* rb = res ? res + (int64_t)n * HW * res_ld : nullptr;
+  const float* sb2 = sub_from ? sub_from + (int64_t)n * HW * sub_ld : nullptr;   // second output: out2 = sub_from - out
+  float* ob2 = out2 ? out2 + (int64_t)n * HW * out2_ld : nullptr;
   // four float4 per thread and iteration, all loads issued before the first use (memory-level parallelism)
   const bool pow2 = (lanes_c & (lanes_c - 1)) == 0;
   const int lshift = __ffs(lanes_c) - 1;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
-    float4 v[4], r[4];
+    float4 v[4], r[4], sf[4];
     int64_t pp[4];
     int cc[4];
 #pragma unroll
@@ -256,6 +259,7 @@ __global__ void se_apply_kernel(const float* __restrict__ x, int ld, const float
       if (i < total) {
         v[j] = __ldg(reinterpret_cast<const float4*>(xb + pp[j] * ld + cc[j]));
         if (rb) r[j] = __ldg(reinterpret_cast<const float4*>(rb + pp[j] * res_ld + cc[j]));
+        if (sb2) sf[j] = __ldg(reinterpret_cast<const float4*>(sb2 + pp[j] * sub_ld + cc[j]));
       }
     }
 #pragma unroll
@@ -268,6 +272,7 @@ __global__ void se_apply_kernel(const float* __restrict__ x, int ld, const float
       o.z = apply_act(v[j].z * sc[c + 2], act, slope) + r[j].z;
       o.w = apply_act(v[j].w * sc[c + 3], act, slope) + r[j].w;
       *reinterpret_cast<float4*>(ob + pp[j] * out_ld + c) = o;
+      if (sb2) *reinterpret_cast<float4*>(ob2 + pp[j] * out2_ld + c) = make_float4(sf[j].x - o.x, sf[j].y - o.y, sf[j].z - o.z, sf[j].w - o.w);
     }
   }
 }
@@ -361,8 +366,12 @@ extern "C" int tdvc_se_partial_sums(const float* x, int ld, int N, int64_t HW, i
 
 extern "C" int tdvc_se_apply(const float* x, int ld, float* partial, int nblk, const float* w1, const float* b1,
                              const float* w2, const float* b2, int N, int64_t HW, int C, int Cr, int act, float slope,
-                             const float* res, int res_ld, float* out, int out_ld, void* stream) {
+                             const float* res, int res_ld, float* out, int out_ld, const float* sub_from, int sub_ld,
+                             float* out2, int out2_ld, void* stream) {
   TDVC_REQUIRE(x && partial && w1 && b1 && w2 && b2 && out && N > 0 && HW > 0 && Cr > 0, "se_apply: bad args");
+  TDVC_REQUIRE((sub_from == nullptr) == (out2 == nullptr), "se_apply: sub_from and out2 go together");
+  TDVC_REQUIRE(sub_from == nullptr || (sub_ld % 4 == 0 && out2_ld % 4 == 0 && aligned16(sub_from) && aligned16(out2)),
+               "se_apply: sub_from / out2 alignment");
   TDVC_REQUIRE(C % 4 == 0 && ld % 4 == 0 && out_ld % 4 == 0 && aligned16(x) && aligned16(out), "se_apply: C/ld/alignment");
   TDVC_REQUIRE(res == nullptr || (res_ld % 4 == 0 && aligned16(res)), "se_apply: res alignment");
   int gx = ew_grid(HW * (C / 4));
@@ -374,7 +383,7 @@ extern "C" int tdvc_se_apply(const float* x, int ld, float* partial, int nblk, c
       partial, nblk, w1, b1, w2, b2, N, HW, C, Cr);
   TDVC_CHECK_LAUNCH("se_scale");
   se_apply_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>(
-      x, ld, partial, N, HW, C, act, slope, res, res_ld, out, out_ld);
+      x, ld, partial, N, HW, C, act, slope, res, res_ld, out, out_ld, sub_from, sub_ld, out2, out2_ld);
   TDVC_CHECK_LAUNCH("se_apply");
   return TDVC_OK;
 }

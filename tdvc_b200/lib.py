@@ -51,6 +51,7 @@ SIGNATURES = {
     "tdvc_conv2d_f16_bytes": [C.POINTER(ConvParams)],
     "tdvc_conv2d_f16_is_split": [C.POINTER(ConvParams)],
     "tdvc_conv2d_products": [C.POINTER(ConvParams)],
+    "tdvc_conv2d_chan_sum_rows": [C.POINTER(ConvParams)],
     "tdvc_conv2d_pack_f16": [C.POINTER(ConvParams), vp, vp],
     "tdvc_dcn_v2_workspace_bytes": [i32] * 6,
     "tdvc_dcn_v2_forward": [vp] * 6 + [i32] * 14 + [vp, sz, vp],
@@ -73,7 +74,7 @@ SIGNATURES = {
     "tdvc_bcast_add_lrelu": [vp, vp, vp, i32, i64, f32, vp],
     "tdvc_round_half_even": [vp, vp, i64, vp],
     "tdvc_se_partial_sums": [vp, i32, i32, i64, i32, vp, i32, vp],
-    "tdvc_se_apply": [vp, i32, vp, i32, vp, vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, i32, vp, i32, vp],
+    "tdvc_se_apply": [vp, i32, vp, i32, vp, vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, i32, vp, i32, vp, i32, vp, i32, vp],
     "tdvc_eb_bits": [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp],
     "tdvc_gc_bits": [vp, vp, i32, i64, i32, vp, vp],
     "tdvc_eb_bits_noise": [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp],

@@ -597,6 +597,7 @@ class _Plan:
         self.impl = L.IMPL_AUTO
         self.precision = "exact"
         self.launches = 0
+        self.last_csum = None
         self.prof = None  # list of (label, macs, bytes, start_event, end_event) when instrumented (bench.py)
         self._order = 0
         self.alternate_order = os.environ.get("TDVC_B200_NO_ALTERNATE") is None   # developer A/B switch
@@ -668,9 +669,11 @@ class _Plan:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def conv(self, srcs, cw, out, stride=1, act=L.ACT_NONE, slope=0.0, res1=None, res2=None, post=L.POST_NONE,
-             mul=None, in_square=False, impl=None, planar=False, absmax_out=None, absmax_in=None, products=None):
+             mul=None, in_square=False, impl=None, planar=False, absmax_out=None, absmax_in=None, products=None, csum=False):
         """planar=True: `out` is a plain (N, cout, Ho, Wo) tensor written as NCHW planes (no shuffle / residual).
-        products: None = by `self.precision` and the layer's stage (ConvW.p1_ok); 0 / 1 force the scheme."""
+        products: None = by `self.precision` and the layer's stage (ConvW.p1_ok); 0 / 1 force the scheme.
+        csum=True: also produce the per-channel partial sums of the output for a following squeeze-excitation (`self.se(...,
+        csum=self.last_csum)`); `self.last_csum` stays None when the launch cannot (exact fp32 SIMT kernel)."""
         p = L.ConvParams()
         s0 = srcs[0]
         cin = 0
@@ -723,8 +726,18 @@ class _Plan:
             p.weight_f16 = cw.w_f16.data_ptr() if cw.w_f16 is not None else None
             p.w_shift = cw.w_shift
         p.out_absmax, p.in_absmax = absmax_out, absmax_in
+        self.last_csum = None
+        if csum and not planar:
+            rows = self.lib.tdvc_conv2d_chan_sum_rows(p)
+            if rows > 0:
+                part = self.raw(("se_csum", cw.cout, rows), (rows * s0.N * cw.cout,))
+                L.check(self.lib.tdvc_zero_bytes(part.data_ptr(), part.numel() * 4, self._st()), "zero_bytes")
+                p.chan_sum = part.data_ptr()
+                self.last_csum = (part, rows)
         self._order ^= 1          # alternate the tile walk direction between consecutive layers (L2 reuse)
         p.order = self._order if self.alternate_order else 0
+        if p.chan_sum:            # the partial channel sums are per CTA: their summation order must not depend on how many
+            p.order = 0           # layers ran before this one (cache hits skip layers), so these launches always walk forwards
         e0 = self._prof_begin()
         L.check(self.lib.tdvc_conv2d(p, self._st()), "conv2d")
         if e0 is not None:
@@ -743,21 +756,30 @@ class _Plan:
         self.launches += 1
         return out
 
-    def se(self, x, w, out, act=L.ACT_NONE, slope=0.0, res=None):
+    def se(self, x, w, out, act=L.ACT_NONE, slope=0.0, res=None, csum=None, sub_from=None, out2=None):
+        """Squeeze-excitation (reference inflate.py:159-208).  csum = `self.last_csum` of the convolution that produced x: the
+        channel sums were accumulated in its epilogue, the pass over x for the mean is skipped."""
         w1, b1, w2, b2 = w
         HW = x.H * x.W
-        nblk = max(1, min(592, HW // 64))
-        part = self.raw(("se_part", x.C), (nblk * x.N * x.C,))
-        e0 = self._prof_begin()
-        L.check(self.lib.tdvc_se_partial_sums(x.ptr, x.ld, x.N, HW, x.C, part.data_ptr(), nblk, self._st()), "se_partial_sums")
-        self._prof_end(e0, f"se_partial_sums_{x.C}ch@{x.H}x{x.W}", 0, 4 * x.N * HW * x.C)
+        if csum is not None:
+            part, nblk = csum
+        else:
+            nblk = max(1, min(592, HW // 64))
+            part = self.raw(("se_part", x.C), (nblk * x.N * x.C,))
+            e0 = self._prof_begin()
+            L.check(self.lib.tdvc_se_partial_sums(x.ptr, x.ld, x.N, HW, x.C, part.data_ptr(), nblk, self._st()), "se_partial_sums")
+            self._prof_end(e0, f"se_partial_sums_{x.C}ch@{x.H}x{x.W}", 0, 4 * x.N * HW * x.C)
+            self.launches += 1
         e0 = self._prof_begin()
         L.check(self.lib.tdvc_se_apply(x.ptr, x.ld, part.data_ptr(), nblk, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
                                        b2.data_ptr(), x.N, HW, x.C, w1.shape[0], act, slope,
                                        res.ptr if res is not None else None, res.ld if res is not None else 0,
-                                       out.ptr, out.ld, self._st()), "se_apply")
-        self._prof_end(e0, f"se_apply_{x.C}ch@{x.H}x{x.W}", 0, 4 * x.N * HW * x.C * (3 if res is not None else 2))
-        self.launches += 3   # partial sums, gate (one block per image), apply
+                                       out.ptr, out.ld, sub_from.ptr if sub_from is not None else None,
+                                       sub_from.ld if sub_from is not None else 0, out2.ptr if out2 is not None else None,
+                                       out2.ld if out2 is not None else 0, self._st()), "se_apply")
+        self._prof_end(e0, f"se_apply_{x.C}ch@{x.H}x{x.W}", 0,
+                       4 * x.N * HW * x.C * (2 + (res is not None) + 2 * (sub_from is not None)))
+        self.launches += 2   # gate (one block per image), apply
         return out
 
     def call(self, fn, *a, nbytes=0, tag=""):
@@ -789,7 +811,7 @@ class _Plan:
             t = self.conv([x], W[f"{cn}.ga{i}.conv1"], b(f"ga{i}.t", h, w), stride=2, **lr)
             t2 = self.conv([t], W[f"{cn}.ga{i}.conv2"], b(f"ga{i}.t2", h, w), absmax_out=am)
             return self.conv([t2], W[f"{cn}.ga{i}.gdn"], b(f"ga{i}.o", h, w), in_square=True, post=L.POST_GDN,
-                             mul=t2, res1=idt, absmax_in=am)
+                             mul=t2, res1=idt, absmax_in=am, csum=(i == 2))
 
         def rb(pfx, i, x):
             t = self.conv([x], W[f"{cn}.{pfx}{i}.conv1"], b(f"{pfx}{i}.t", x.H, x.W), **lr)
@@ -802,18 +824,18 @@ class _Plan:
             t2 = self.conv([t], W[f"{cn}.gs{i}.conv"], b(f"gs{i}.t2", h, w), absmax_out=am)
             idt = self.conv([x], W[f"{cn}.gs{i}.upsample"], b(f"gs{i}.id", h, w))
             return self.conv([t2], W[f"{cn}.gs{i}.igdn"], b(f"gs{i}.o", h, w), in_square=True, post=L.POST_IGDN,
-                             mul=t2, res1=idt, absmax_in=am)
+                             mul=t2, res1=idt, absmax_in=am, csum=(i == 4))
 
         # ---- g_a
         a = rb_stride(0, x, H // 2, Wd // 2)
         a = rb("ga", 1, a)
         a = rb_stride(2, a, H // 4, Wd // 4)
-        a = self.se(a, W[f"{cn}.ga3"], b("ga3.o", a.H, a.W))
+        a = self.se(a, W[f"{cn}.ga3"], b("ga3.o", a.H, a.W), csum=self.last_csum)
         a = rb("ga", 4, a)
         a = rb_stride(5, a, H // 8, Wd // 8)
         a = rb("ga", 6, a)
-        a = self.conv([a], W[f"{cn}.ga7"], b("ga7.o", H // 16, Wd // 16), stride=2)
-        y = self.se(a, W[f"{cn}.ga8"], b("y", a.H, a.W))
+        a = self.conv([a], W[f"{cn}.ga7"], b("ga7.o", H // 16, Wd // 16), stride=2, csum=True)
+        y = self.se(a, W[f"{cn}.ga8"], b("y", a.H, a.W), csum=self.last_csum)
         # ---- y_hat first: both the synthesis transform and the entropy model start from it
         yh = b("y_hat", y.H, y.W)
         if self.training:   # compressai quantize(y, "noise"): y + U(-0.5, 0.5)   (JointAutoregressiveHierarchicalPriors.forward)
@@ -836,7 +858,7 @@ class _Plan:
         g = rb_up(2, g)
         g = rb("gs", 3, g)
         g = rb_up(4, g)
-        g = self.se(g, W[f"{cn}.gs5"], b("gs5.o", g.H, g.W))
+        g = self.se(g, W[f"{cn}.gs5"], b("gs5.o", g.H, g.W), csum=self.last_csum)
         g = rb("gs", 6, g)
         g = rb_up(7, g)
         g = rb("gs", 8, g)
@@ -1055,10 +1077,10 @@ class _Plan:
         o2 = self.conv([dcn_out, ref_f], W["mc.conv"], self.buf("mc.o2", N, H, Wd, 64), **lr1)
         pred1 = self.res_stack(W, "mc.res", 3, o2, "mc", last_res2=dcn_out, out_last=self.buf("pred1", N, H, Wd, 64))
         # ---- multi-frame fusion (pnet.py:277-293, 309-317)
-        pred = self.mcfilter(W, pred1, assign)
-        # ---- residual coder (pnet.py:55-67, 76)
+        # (the residual input_feat - prediction of pnet.py:55 is written by the same pass that finishes the prediction)
         resid = self.buf("resid", N, H, Wd, 64)
-        self.call("tdvc_axpby", in_f.ptr, pred.ptr, resid.ptr, N * H * Wd * 64, 1.0, -1.0, nbytes=768 * N * H * Wd)
+        pred = self.mcfilter(W, pred1, assign, in_f, resid)
+        # ---- residual coder (pnet.py:55-67, 76)
         rec_f = self.coder(W, "rs", resid, 2, taps, final_res=pred, out=self.buf("rec_f", N, H, Wd, 64))
         # ---- reference-based in-loop filter (pnet.py:213-263) + clamp (:78)
         recon4 = self.loopfilter(W, rec_f, taps)
@@ -1132,8 +1154,8 @@ class _Plan:
         flow = self.spynet(W, imgs, taps)
         offf = b("off_flow", N, H, Wd)
         self.call("tdvc_add_flow_tiled", off.ptr, flow.ptr, offf.ptr, N, H, Wd, 64, nbytes=520 * N * H * Wd)
-        ff = self.conv([offf], W["me.feat_fusion_"], b("ff", N, H, Wd))
-        return self.se(ff, W["me.attn"], b("estmv", N, H, Wd))
+        ff = self.conv([offf], W["me.feat_fusion_"], b("ff", N, H, Wd), csum=True)
+        return self.se(ff, W["me.attn"], b("estmv", N, H, Wd), csum=self.last_csum)
 
     def spynet(self, W, imgs, taps):
         """reference flownet.py:82-140 with ref = input image, supp = x^(t-1) (pnet.py:162)."""
@@ -1175,7 +1197,7 @@ class _Plan:
         c1 = self.conv([a], W["mf.l1.conv1"], b("c1"), **lr1)
         return self.conv([c1], W["mf.l1.spatial"], b(f"s.{e}"))
 
-    def mcfilter(self, W, pred1, assign):
+    def mcfilter(self, W, pred1, assign, sub_from=None, out2=None):
         N, H, Wd = self.N, self.H, self.W
         lr1 = dict(act=L.ACT_LRELU, slope=0.1)
         b = lambda nme, c=64: self.buf("mf." + nme, N, H, Wd, c)
@@ -1195,8 +1217,8 @@ class _Plan:
                 self.call("tdvc_bcast_add_lrelu", S[t].ptr, tmp.ptr, o.ptr, 1, N * H * Wd * 64, 0.1, nbytes=3 * 256 * N * H * Wd)
                 done[k] = self.conv([o], W["mf.l1.conv3"], b(f"bo.{k}"), res1=A[t])
             bo.append(done[k])
-        fu = self.conv(bo, W["mf.fusion"], b("fu"), **lr1)
-        return self.se(fu, W["mf.attn"], self.buf("pred", N, H, Wd, 64), res=pred1)
+        fu = self.conv(bo, W["mf.fusion"], b("fu"), csum=True, **lr1)
+        return self.se(fu, W["mf.attn"], self.buf("pred", N, H, Wd, 64), res=pred1, csum=self.last_csum, sub_from=sub_from, out2=out2)
 
     # ---- reference-based in-loop filter (reference FeatureFix, pnet.py:187-263)
     def _ff_geometry(self):
@@ -1248,8 +1270,8 @@ class _Plan:
                   gth.ptr if gth is not None else None, cor.data_ptr() if cor is not None else None, N, H, Wd, 64, scale,
                   nbytes=N * H * Wd * 1024)  # read f_in + gathered f_ref, write both gated halves
         o = self.conv([ga, gb], W["lf.featfusion"], b("o"), **lr1)
-        o = self.conv([o, f_ref], W["lf.featfusion2"], b("o2"))
-        o = self.se(o, W["lf.attn"], b("o3"), act=L.ACT_LRELU, slope=0.1)
+        o = self.conv([o, f_ref], W["lf.featfusion2"], b("o2"), csum=True)
+        o = self.se(o, W["lf.attn"], b("o3"), act=L.ACT_LRELU, slope=0.1, csum=self.last_csum)
         o = self.res_stack(W, "lf.res", 2, o, "lf.rs", last_res2=rec_f)  # ... + feat (pnet.py:262-263)
         out = self.buf("lf.recon4", N, H, Wd, 3, ld=4)
         self.conv([o], W["lf.featdown"], out, act=L.ACT_CLAMP01)

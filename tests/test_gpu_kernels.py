@@ -142,6 +142,41 @@ def test_conv2d_one_product_vs_torch(plan, dev, idx):
     assert (got - want).abs().max() <= 3e-5 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("case", [(64, 64, 3, 2, 45, 70, 0, False), (128, 128, 3, 1, 21, 19, 0, True), (64, 64, 3, 1, 33, 40, 1, False),
+                                  (128, 64, 1, 3, 16, 24, 0, False), (128, 128, 3, 1, 20, 12, 1, True)])
+def test_conv2d_chan_sum_feeds_squeeze_excitation(plan, dev, case):
+    """TdvcConvParams::chan_sum: the channel sums of a convolution's output, accumulated in its epilogue (every tile scheme:
+    hi/lo rows, split, one product with and without row phases; batches), equal the sums over the stored tensor, and the
+    squeeze-excitation built on them equals the one built on a separate pass over the tensor."""
+    from oracle.model import SELayer
+    from tdvc_b200.model import Act, pack_conv
+    from tdvc_b200 import tc
+    cin, cout, k, N, H, W, products, res = case
+    torch.manual_seed(31)
+    conv = torch.nn.Conv2d(cin, cout, k, 1, k // 2)
+    x = torch.randn(N, cin, H, W)
+    r = torch.randn(N, cout, H, W) if res else None
+    cw = pack_conv(conv.weight.to(dev), conv.bias.to(dev), src_layout=[(cin, cin)])
+    tc.attach_f16({"w": cw}, one_product=products == 1)
+    out = Act.alloc(N, H, W, cout, dev)
+    plan.conv([Act.from_nchw(x.to(dev))], cw, out, act=2, slope=0.1, res1=Act.from_nchw(r.to(dev)) if res else None, impl=2,
+              products=products, csum=True)
+    assert plan.last_csum is not None
+    part, rows = plan.last_csum
+    sums = part.view(rows, N, cout).double().sum(0).cpu()
+    want = out.nchw().double().sum((2, 3)).cpu()
+    assert (sums - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item()) * (H * W) ** 0.5
+    se = SELayer(cout)
+    w = [se.conv1.conv.weight.reshape(cout // 16, cout).contiguous().to(dev), se.conv1.conv.bias.to(dev),
+         se.conv2.conv.weight.reshape(cout, cout // 16).contiguous().to(dev), se.conv2.conv.bias.to(dev)]
+    o1, o2 = Act.alloc(N, H, W, cout, dev), Act.alloc(N, H, W, cout, dev)
+    plan.se(out, w, o1, csum=plan.last_csum)
+    plan.se(out, w, o2)
+    ref = se(out.nchw().cpu())
+    assert (o1.nchw().cpu() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert (o1.nchw() - o2.nchw()).abs().max().item() < 2e-6 * max(1.0, ref.abs().max().item())
+
+
 def test_conv2d_out_absmax(plan, dev):
     """TdvcConvParams::out_absmax: max |v| over everything the layer stored, on the tensor-core and the SIMT kernel."""
     from tdvc_b200.model import Act, pack_conv

@@ -618,7 +618,7 @@ def test_validate_over_a_gop_dataset(net, dev, tmp_path):
     from tdvc_b200 import synth
     net.conv_impl, net.precision = 0, "auto"
     gop, qp = 4, 27
-    seqs = {"a_416x240_50": synth.make_gop(56, 120, gop=8, seed=91), "b_416x240_50": synth.make_gop(56, 120, gop=4, seed=92)}
+    seqs = {"a_416x240_50": synth.make_gop(176, 208, gop=8, seed=91), "b_416x240_50": synth.make_gop(176, 208, gop=4, seed=92)}
     for seq, fr in seqs.items():
         os.makedirs(tmp_path / "ori_img" / seq)
         os.makedirs(tmp_path / "compress_img_bpg" / seq / str(qp))
