@@ -237,7 +237,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))   # a hang must fail fast
     hh, ww = args.height, args.width
     K, Wm = args.steps, max(args.warmup, 3)
     # one untimed GOP in front of the W warm-up steps: every launch variant of a GOP (which features are cached) is run and
@@ -332,7 +333,7 @@ def main():
     ms_e2e, _, _ = run_chain(host_gops, Wm_total, K, host_io=True)
     # secondary: the same resident chain with every convolution at fp32-class accuracy (enabled_amp=False semantics)
     ms_exact = None
-    if net._precision(ENABLE_AMP) != "exact" and rank == 0:
+    if net._precision(ENABLE_AMP) != "exact" and world == 1:   # (run_chain holds collectives: a leg is run by all ranks or none)
         net.precision = "exact"
         ms_exact, _, _ = run_chain(dev_gops, GOP - 1, GOP - 1, host_io=False)
         ms_exact /= GOP - 1
