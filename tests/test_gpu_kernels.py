@@ -487,9 +487,11 @@ def test_spynet_prep_vs_oracle(plan, dev):
     from oracle.model import flow_warp_border
     from tdvc_b200.model import Act
     torch.manual_seed(2)
-    for (h, w) in ((8, 10), (32, 60), (64, 64)):
+    # several 64x8 tiles per image, ragged tile edges, batch; flows of sigma 6 (2 x 3) put most samples inside the staged
+    # shared-memory tile (margin 8) and a good fraction outside it (the global-memory path), sigma 30 nearly all outside
+    for (h, w, sig) in ((8, 10, 3.0), (32, 60, 3.0), (64, 64, 3.0), (70, 200, 3.0), (34, 150, 15.0)):
         ref, supp = torch.rand(1, 3, h, w), torch.rand(1, 3, h, w)
-        flow = torch.randn(1, 2, h // 2, w // 2) * 3
+        flow = torch.randn(1, 2, h // 2, w // 2) * sig
         up = F.interpolate(flow, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
         warped = flow_warp_border(supp, up.permute(0, 2, 3, 1))
         want = torch.cat([ref, warped, up], 1)
