@@ -295,8 +295,9 @@ def test_gdn_as_fused_conv(plan, dev):
             assert (out.nchw().cpu() - want).abs().max() < tol * want.abs().max(), impl
 
 
-@pytest.mark.parametrize("cout,H,W", [(64, 17, 23), (216, 33, 9), (128, 40, 31), (32, 35, 12)])
-def test_conv_tc_writes_only_its_view(plan, dev, cout, H, W):
+@pytest.mark.parametrize("cout,H,W,products", [(64, 17, 23, 0), (216, 33, 9, 0), (128, 40, 31, 0), (32, 35, 12, 0),
+                                               (64, 33, 23, 1), (48, 65, 9, 1), (128, 40, 31, 1), (216, 19, 12, 1)])
+def test_conv_tc_writes_only_its_view(plan, dev, cout, H, W, products):
     """Guard bands: the tensor-core kernel stores through a channel view (ld > C, offset 4 floats... here 8 to keep the
     16-byte alignment) of a larger tensor with guard rows before and after; everything outside the view keeps its
     sentinel (ragged tiles in x, y and in the channel dimension)."""
@@ -307,13 +308,38 @@ def test_conv_tc_writes_only_its_view(plan, dev, cout, H, W):
     x = torch.randn(1, 64, H, W)
     want = conv(x)
     cw = pack_conv(conv.weight.to(dev), conv.bias.to(dev), src_layout=[(64, 64)])
-    tc.attach_f16({"w": cw})
+    tc.attach_f16({"w": cw}, one_product=products == 1)
     ld = cout + 16
     big = torch.full((H + 4, W, ld), 12345.0, device=dev)          # 2 guard rows above and below
     view = Act(big, big.data_ptr() + 4 * (2 * W * ld + 8), 1, H, W, cout, ld)
-    plan.conv([Act.from_nchw(x.to(dev))], cw, view, impl=2)
+    # the channel-sum rows of the launch live in a guarded buffer too (TdvcConvParams::chan_sum)
+    real_raw, guarded = plan.raw, {}
+
+    def raw(name, shape, dtype=torch.float32):
+        if isinstance(name, tuple) and name[0] == "se_csum":
+            g = torch.full((shape[0] + 512,), 777.0, device=dev)
+            guarded["buf"] = g
+            return g[256:256 + shape[0]]
+        return real_raw(name, shape, dtype)
+
+    plan.raw = raw
+    try:
+        plan.conv([Act.from_nchw(x.to(dev))], cw, view, impl=2, products=products, csum=cout <= 128)
+    finally:
+        plan.raw = real_raw
     torch.cuda.synchronize()
+    if cout <= 128 and (cout <= 64 or products == 1 or cout >= 96):
+        assert plan.last_csum is not None
+    if plan.last_csum is not None:
+        g = guarded["buf"]
+        assert (g[:256] == 777.0).all() and (g[-256:] == 777.0).all()
+        part, rows = plan.last_csum
+        sums = part.view(rows, 1, cout).double().sum(0).cpu()[0]
+        got_sum = big[2:H + 2, :, 8:8 + cout].double().sum((0, 1)).cpu()
+        assert (sums - got_sum).abs().max().item() <= 1e-4 * max(1.0, got_sum.abs().max().item())
     got = big[2:H + 2, :, 8:8 + cout].permute(2, 0, 1).unsqueeze(0).cpu()
+    if products == 1:
+        want = F.conv2d(x.half().float(), conv.weight.half().float(), conv.bias, 1, 1)
     assert (got - want).abs().max() < 1e-4 * want.abs().max()
     assert (big[:2] == 12345.0).all() and (big[H + 2:] == 12345.0).all()
     assert (big[2:H + 2, :, :8] == 12345.0).all() and (big[2:H + 2, :, 8 + cout:] == 12345.0).all()
