@@ -194,6 +194,10 @@ int tdvc_add_flow_tiled(const float* offset, const float* flow2, float* out, int
 int tdvc_axpby(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, void* stream);
 /* out[t] = lrelu(x[t] + tmp) for t < T (Bottleneck3D temporal broadcast add, reference pnet.py:313-314) */
 int tdvc_bcast_add_lrelu(const float* x, const float* tmp, float* out, int T, int64_t n_per_t, float slope, void* stream);
+/* the same for T <= 4 frames that do not lie next to each other: out[t] = lrelu(x[t] + tmp), `x` / `out` are HOST arrays of T
+ * device pointers (n floats each); tmp is read once for all of them */
+int tdvc_bcast_add_lrelu_multi(const float* const* x, const float* tmp, float* const* out, int T, int64_t n, float slope,
+                               void* stream);
 int tdvc_round_half_even(const float* x, float* out, int64_t n, void* stream);
 
 /* ---- squeeze-excitation (reference inflate.py:159-208): two launches.

@@ -34,12 +34,14 @@ extern "C" int tdvc_conv2d(const TdvcConvParams* p, void* stream) {
     }
     return tdvc::conv2d_tc(*p, st);
   }
-  if ((p->out_absmax != nullptr || p->chan_sum != nullptr) && (p->impl == 3 || (p->impl == 0 && tdvc::conv2d_small_supported(*p)))) {
+  if ((p->out_absmax != nullptr || p->chan_sum != nullptr) &&
+      (p->impl == 3 || (p->impl == 0 && p->products == 0 && tdvc::conv2d_small_supported(*p)))) {
     tdvc::set_error("conv2d: out_absmax / chan_sum are not available on the <= 4-channel kernel");
     return TDVC_EINVAL;
   }
   if (p->impl == 3) return tdvc::conv2d_small(*p, st);
-  if (p->impl == 0 && tdvc::conv2d_small_supported(*p)) return tdvc::conv2d_small(*p, st);
+  // (a one-product layer stays on the tensor cores even with <= 4 output channels: the exact fp32 SIMT kernel is slower there)
+  if (p->impl == 0 && p->products == 0 && tdvc::conv2d_small_supported(*p)) return tdvc::conv2d_small(*p, st);
   if (p->impl == 0 && tdvc::conv2d_tc_supported(*p)) return tdvc::conv2d_tc(*p, st);
   if (p->chan_sum != nullptr) {
     tdvc::set_error("conv2d: chan_sum is produced by the tcgen05 kernel only (ask tdvc_conv2d_chan_sum_rows first)");
@@ -53,7 +55,7 @@ extern "C" int tdvc_conv2d(const TdvcConvParams* p, void* stream) {
 extern "C" int tdvc_conv2d_products(const TdvcConvParams* p) {
   if (p == nullptr || tdvc::conv2d_validate(p) != TDVC_OK) return -1;
   if (p->impl == 1 || p->impl == 3) return 0;
-  if (p->impl == 0 && tdvc::conv2d_small_supported(*p)) return 0;
+  if (p->impl == 0 && p->products == 0 && tdvc::conv2d_small_supported(*p)) return 0;
   if (!tdvc::conv2d_tc_supported(*p)) return p->impl == 2 ? -1 : 0;
   if (p->products == 1) return 1;
   return tdvc_conv2d_f16_is_split(p) ? 3 : 4;

@@ -109,6 +109,32 @@ __global__ void bcast_add_lrelu_kernel(const float* __restrict__ x, const float*
   }
 }
 
+// out[j] = lrelu(x[j] + tmp) for up to four independent (x, out) pairs: tmp is read once for all of them
+struct Ptr4 {
+  const float* x[4];
+  float* out[4];
+};
+__global__ void bcast_add_lrelu_multi_kernel(Ptr4 q, const float* __restrict__ tmp, int T, int64_t n4, float slope) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(tmp) + i);
+    float4 v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (t < T) v[t] = __ldg(reinterpret_cast<const float4*>(q.x[t]) + i);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (t < T) {
+        float4 o = v[t];
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+        o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+        reinterpret_cast<float4*>(q.out[t])[i] = o;
+      }
+    }
+  }
+}
+
 __global__ void round_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = rintf(x[i]);
@@ -337,6 +363,20 @@ extern "C" int tdvc_bcast_add_lrelu(const float* x, const float* tmp, float* out
   TDVC_REQUIRE(aligned16(x) && aligned16(tmp) && aligned16(out), "bcast_add_lrelu: alignment");
   bcast_add_lrelu_kernel<<<ew_grid(n_per_t / 4), 256, 0, (cudaStream_t)stream>>>(x, tmp, out, T, n_per_t / 4, slope);
   TDVC_CHECK_LAUNCH("bcast_add_lrelu");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_bcast_add_lrelu_multi(const float* const* x, const float* tmp, float* const* out, int T, int64_t n,
+                                          float slope, void* stream) {
+  TDVC_REQUIRE(x && tmp && out && T > 0 && T <= 4 && n > 0 && n % 4 == 0 && aligned16(tmp), "bcast_add_lrelu_multi: bad args");
+  Ptr4 q;
+  for (int t = 0; t < 4; ++t) {
+    q.x[t] = t < T ? x[t] : nullptr;
+    q.out[t] = t < T ? out[t] : nullptr;
+    TDVC_REQUIRE(t >= T || (q.x[t] && q.out[t] && aligned16(q.x[t]) && aligned16(q.out[t])), "bcast_add_lrelu_multi: pointer %d", t);
+  }
+  bcast_add_lrelu_multi_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(q, tmp, T, n / 4, slope);
+  TDVC_CHECK_LAUNCH("bcast_add_lrelu_multi");
   return TDVC_OK;
 }
 

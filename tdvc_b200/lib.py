@@ -72,6 +72,7 @@ SIGNATURES = {
     "tdvc_add_flow_tiled": [vp, vp, vp, i32, i32, i32, i32, vp],
     "tdvc_axpby": [vp, vp, vp, i64, f32, f32, vp],
     "tdvc_bcast_add_lrelu": [vp, vp, vp, i32, i64, f32, vp],
+    "tdvc_bcast_add_lrelu_multi": [C.POINTER(vp), vp, C.POINTER(vp), i32, i64, f32, vp],
     "tdvc_round_half_even": [vp, vp, i64, vp],
     "tdvc_se_partial_sums": [vp, i32, i32, i64, i32, vp, i32, vp],
     "tdvc_se_apply": [vp, i32, vp, i32, vp, vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, i32, vp, i32, vp, i32, vp, i32, vp],

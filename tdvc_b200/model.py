@@ -388,7 +388,7 @@ def _reparam(p, mod):
 # stages that may run with ONE fp16 MMA product (`VideoCompressor.precision = "mixed"`): everything behind the last quantiser
 # of the frame - the residual coder's synthesis transform and the in-loop filter on the reconstruction.  Measured budget:
 # profiles/r02_precision_budget.txt (precision).  FeatureExtract_ref stays exact: it is cached per GOP.
-_ONE_PRODUCT_PREFIXES = ("rs.gs", "lf.fe_in", "lf.featfusion", "lf.res")
+_ONE_PRODUCT_PREFIXES = ("rs.gs", "lf.fe_in", "lf.featfusion", "lf.res", "lf.featdown")
 
 
 class _Packed:
@@ -1209,14 +1209,20 @@ class _Plan:
         S = [b(f"s.{e}") for e in assign] + [s_p]
         # temporal (3,1,1) stride 3: one output step from frames 0..2, broadcast-added to all four (pnet.py:313-314)
         tmp = self.conv(S[:3], W["mf.l1.temporal"], b("tmp"))
-        bo, done = [], {}
+        # o_t = lrelu(s_t + tmp) for the distinct frames of the stack in ONE pass (tmp is read once); duplicated references (GOP
+        # warm-up, predict.py:55-60) share their entry
+        keys, first = [], {}
         for t in range(4):
             k = assign[t] if t < 3 else "p"
-            if k not in done:   # duplicated references (GOP warm-up, predict.py:55-60) share their entry
-                o = b(f"o.{k}")
-                self.call("tdvc_bcast_add_lrelu", S[t].ptr, tmp.ptr, o.ptr, 1, N * H * Wd * 64, 0.1, nbytes=3 * 256 * N * H * Wd)
-                done[k] = self.conv([o], W["mf.l1.conv3"], b(f"bo.{k}"), res1=A[t])
-            bo.append(done[k])
+            keys.append(k)
+            first.setdefault(k, t)
+        uniq = list(first.items())
+        xs = (C.c_void_p * 4)(*[S[t].ptr for _, t in uniq])
+        os_ = (C.c_void_p * 4)(*[b(f"o.{k}").ptr for k, _ in uniq])
+        self.call("tdvc_bcast_add_lrelu_multi", xs, tmp.ptr, os_, len(uniq), N * H * Wd * 64, 0.1,
+                  nbytes=(2 * len(uniq) + 1) * 256 * N * H * Wd)
+        done = {k: self.conv([b(f"o.{k}")], W["mf.l1.conv3"], b(f"bo.{k}"), res1=A[t]) for k, t in uniq}
+        bo = [done[k] for k in keys]
         fu = self.conv(bo, W["mf.fusion"], b("fu"), csum=True, **lr1)
         return self.se(fu, W["mf.attn"], self.buf("pred", N, H, Wd, 64), res=pred1, csum=self.last_csum, sub_from=sub_from, out2=out2)
 

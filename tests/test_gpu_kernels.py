@@ -38,6 +38,8 @@ def _conv_case(plan, dev, cin_list, cout, k, stride, H, W, N=1, act=0, slope=0.0
         want = F.relu(want)
     elif act == 2:
         want = F.leaky_relu(want, slope)
+    elif act == 3:
+        want = want.clamp(0.0, 1.0)
     if shuffle == 2:
         want = F.pixel_shuffle(want, 2)
     r = torch.randn_like(want) if res else None
@@ -129,6 +131,7 @@ P1_CASES = [
     ([128], 512, 3, 1, 8, 12, dict(shuffle=2, act=2, slope=0.01)),     # subpel conv
     ([128], 256, 3, 1, 16, 16, dict(shuffle=2)),                        # g_s[9]
     ([128], 128, 1, 1, 19, 21, dict(pad=0)),                            # 1x1
+    ([64], 3, 3, 1, 37, 33, dict(act=3)),                               # featdown + clamp: 3 of the 128 rows carry data
 ]
 
 

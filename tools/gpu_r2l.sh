@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "spynet or pool" --maxfail=8 2>&1 | tail -40 > gpurun_out/r2l_tests.log
+timeout 1500 python -m pytest tests -q -m gpu --maxfail=8 2>&1 | tail -40 > gpurun_out/r2l_tests.log
 grep -E "passed|failed|Error|assert " gpurun_out/r2l_tests.log | tail -20
 timeout 900 python bench.py --steps 22 --warmup 3 --no-cpu-baseline --no-eager-baseline > gpurun_out/r2l_bench.json 2> gpurun_out/r2l_bench.err
 python -c "
