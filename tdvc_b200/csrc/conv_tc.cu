@@ -37,6 +37,8 @@
 //              Bias / GDN / activation / residuals are applied in registers; GDN multipliers and the first residual
 //              are loaded one chunk ahead.  Overlaps the next item's MMAs (two accumulator stages = all 512 TMEM columns).
 #include <cuda.h>
+#include <stdlib.h>
+#include <type_traits>
 #include "tc_common.cuh"
 
 #ifndef TDVC_CONV_TC_NX_MAX
@@ -68,9 +70,17 @@ constexpr int NT = 64;                         // output channels per item (M = 
 //            and no lo rows: the 128 M rows are 128 output channels (weights pre-scaled by 2^w_shift like the split scheme) or,
 //            for 3x3 layers with <= 64 output channels, 64 channels x 2 row phases.  This is the arithmetic of the reference
 //            under autocast; it is used for the stages behind the last quantiser only (precision budget).
-template <int KS, int CK, int S, int SPLIT = 0, int NPH = 1, int PLN = 0, int PR = 0>
+// TMA = 1 ("TMA-fed activations", stride-1 KxK layers): the fp32 halo of a unit is not loaded by the producer warps' LDGs but by
+//            tensor-map bulk copies (cp.async.bulk.tensor.4d over (channel, x, y, image) of every source; the hardware clips the
+//            box at the image border and zero-fills, so the border / channel-tail predicates of the LDG path disappear).  One
+//            elected lane issues a box of [IH][IW][SUB channels] fp32 per sub-unit into a small staging ring; the converter
+//            warps read the staged box linearly (conflict-free 16-byte reads), split it to fp16 hi / lo and write the operand
+//            planes.  Loads in flight no longer cost registers, and their depth is the staging ring, not a register batch.
+template <int KS, int CK, int S, int SPLIT = 0, int NPH = 1, int PLN = 0, int PR = 0, int TMA = 0>
 struct Cfg {
   static_assert(S == 1 || (S == 2 && (KS == 1 || KS == 3)), "stride");
+  static_assert(TMA == 0 || (S == 1 && KS != 1), "TMA-fed activations: stride-1 KxK layers (1x1 layers stage with cp.async)");
+  static constexpr bool TMAIN = (TMA != 0);
   static_assert(PR == 0 || (PR == 1 && SPLIT == 0), "one product: SPLIT is meaningless, pass 0");
   static_assert(NPH == 1 || (S == 1 && SPLIT == 0 && ((KS == 7 && PR == 0 && (NPH == 2 || NPH == 4)) || (KS == 3 && PR == 1 && NPH == 2))),
                 "row phases");
@@ -88,6 +98,7 @@ struct Cfg {
 #endif
   static constexpr bool WIDE_EPI = (KS == 1 && S == 1 && DIRECT) || (TDVC_CONV_TC_WIDE16 && KS == 3 && S == 1 && CK == 16 && NPH == 1 && !DIRECT);
   static constexpr int EPIW = WIDE_EPI ? 12 : kEpiWarps, PRODW = WIDE_EPI ? 6 : kProdWarps;
+  static constexpr int CONVW = TMAIN ? PRODW - 1 : PRODW;   // warps that write operand planes (TMA: one producer warp issues the copies)
   static_assert(EPIW + PRODW + 2 == kThreads / 32 && EPIW % 4 == 0, "warp roles");
   static constexpr int NGRP = EPIW / 4;                      // epilogue warps per TMEM lane quadrant: they share the 16 chunks
   static constexpr int KY = KS + NPH - 1;                    // kernel rows walked by the MMA loop
@@ -131,9 +142,24 @@ struct Cfg {
   static_assert(PLN == 0 || (SPLIT == 1 && NPH == 1), "TMA planar stores: split-scheme items only");
   static constexpr int PLN_BYTES = PLN ? EPIW * 2 * 2048 : 0;
   static constexpr int kNxMax = TDVC_CONV_TC_NX_MAX;
-  static constexpr bool fits(int nx) { return nx * X_STAGE + NW * W_BLOCK + STG_BYTES + PLN_BYTES + 256 <= 227 * 1024; }
-  static constexpr int NX = (kNxMax >= 4 && fits(4)) ? 4 : (fits(3) ? 3 : 2);
-  static constexpr int SMEM = NX * X_STAGE + NW * W_BLOCK + STG_BYTES + PLN_BYTES + 256;
+  static constexpr int kBarBytes = 384;
+  // TMA staging ring: sub-units of SUB channels ([IH][IW][SUB] fp32 = NHALO * SUB * 4 bytes, a multiple of 128), NTS stages.
+  // Preference: three operand stages with >= 2 staging stages of 16 channels, else 8-channel sub-units, else two operand stages
+  static constexpr int fixed_bytes = NW * W_BLOCK + STG_BYTES + PLN_BYTES + kBarBytes;
+  static constexpr bool tfits(int nx, int sub, int nts) { return nx * X_STAGE + fixed_bytes + nts * NHALO * sub * 4 <= 227 * 1024; }
+  static constexpr int pick(int what) {   // what: 0 = NX, 1 = SUB, 2 = NTS
+    if (!TMAIN) return what == 0 ? ((kNxMax >= 4 && tfits(4, 0, 0)) ? 4 : (tfits(3, 0, 0) ? 3 : 2)) : (what == 1 ? 16 : 0);
+    const int cand[8][3] = {{3, 16, 3}, {3, 16, 2}, {3, 8, 3}, {2, 16, 3}, {2, 16, 2}, {2, 8, 3}, {2, 8, 2}, {2, 8, 1}};
+    for (int i = 0; i < 8; ++i)
+      if (tfits(cand[i][0], cand[i][1], cand[i][2])) return cand[i][what];
+    return what == 0 ? 2 : (what == 1 ? 8 : 1);
+  }
+  static constexpr int NX = pick(0);
+  static constexpr int SUB = pick(1), NSUB = CK / SUB, NTS = pick(2);
+  static constexpr int TSTG = NHALO * SUB * 4;        // bytes of one staged sub-unit
+  static constexpr int TS_BYTES = NTS * TSTG;
+  static constexpr int SMEM = NX * X_STAGE + fixed_bytes + TS_BYTES;
+  static_assert(!TMAIN || (TSTG % 128 == 0 && IW <= 256 && IH <= 256), "TMA box");
   static_assert(NPIXP >= NPIX, "pitch");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   // smem pixel slot of halo pixel (hy, hx)
@@ -298,21 +324,28 @@ __device__ __forceinline__ void prod_convert_rt(const TdvcConvParams& p, const P
 
 // PlanarMap: the 4-D tensor map (x, y, channel, image) of a planar output for the PLN variant, an empty tag otherwise
 struct NoMap {};
-template <int KS, int CK, int S, int SPLIT, int NPH, int PLN, int PR>
+// InMaps: one 4-D tensor map (channel, x, y, image) per concatenated source for the TMA variant, an empty tag otherwise
+struct InMaps {
+  CUtensorMap m[4];
+};
+template <int KS, int CK, int S, int SPLIT, int NPH, int PLN, int PR, int TMA>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvParams p, int tiles_x, int tiles_y, int n_jt,
                                                               int n_units, int n_items,
-                                                              const __grid_constant__ std::conditional_t<PLN != 0, CUtensorMap, NoMap> omap) {
-  using C = Cfg<KS, CK, S, SPLIT, NPH, PLN, PR>;
+                                                              const __grid_constant__ std::conditional_t<PLN != 0, CUtensorMap, NoMap> omap,
+                                                              const __grid_constant__ std::conditional_t<TMA != 0, InMaps, NoMap> imaps) {
+  using C = Cfg<KS, CK, S, SPLIT, NPH, PLN, PR, TMA>;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* x_buf = smem;                                  // NX stages of [hi plane | lo plane]
-  uint8_t* w_buf = smem + C::NX * C::X_STAGE;             // NW weight blocks
+  uint8_t* ts_buf = smem;                                 // TMA staging ring of the fp32 sub-units (TS_BYTES, may be 0; 128-byte aligned)
+  uint8_t* x_buf = smem + C::TS_BYTES;                    // NX stages of [hi plane | lo plane]
+  uint8_t* w_buf = x_buf + C::NX * C::X_STAGE;            // NW weight blocks
   uint8_t* stg_buf = w_buf + C::NW * C::W_BLOCK;           // cp.async staging of the 1x1 producers (STG_BYTES, may be 0)
   uint8_t* pln_buf = stg_buf + C::STG_BYTES;              // TMA planar-store staging of the epilogue warps (PLN_BYTES, may be 0)
   uint64_t* bars = reinterpret_cast<uint64_t*>(pln_buf + C::PLN_BYTES);
   // barrier indices
   constexpr int X_FULL = 0, X_EMPTY = X_FULL + C::NX, W_FULL = X_EMPTY + C::NX, W_EMPTY = W_FULL + C::NW,
-                ACC_FULL = W_EMPTY + C::NW, ACC_EMPTY = ACC_FULL + 2, NBARS = ACC_EMPTY + 2;
-  static_assert(NBARS * 8 + 8 <= 256, "barrier area");
+                ACC_FULL = W_EMPTY + C::NW, ACC_EMPTY = ACC_FULL + 2, TS_FULL = ACC_EMPTY + 2, TS_EMPTY = TS_FULL + C::NTS,
+                NBARS = TS_EMPTY + C::NTS;
+  static_assert(NBARS * 8 + 8 <= C::kBarBytes, "barrier area");
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
   const uint32_t bar0 = smem_u32(bars);
   auto bar = [&](int i) { return bar0 + 8u * i; };
@@ -321,7 +354,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
   const int flip = p.order ? n_items - 1 : -1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::NX; ++i) { mbar_init(bar(X_FULL + i), C::PRODW * 32); mbar_init(bar(X_EMPTY + i), 1); }
+    for (int i = 0; i < C::NX; ++i) { mbar_init(bar(X_FULL + i), C::CONVW * 32); mbar_init(bar(X_EMPTY + i), 1); }
+    for (int i = 0; i < C::NTS; ++i) { mbar_init(bar(TS_FULL + i), 1); mbar_init(bar(TS_EMPTY + i), C::CONVW * 32); }
     for (int i = 0; i < C::NW; ++i) { mbar_init(bar(W_FULL + i), 1); mbar_init(bar(W_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(ACC_FULL + i), 1); mbar_init(bar(ACC_EMPTY + i), C::EPIW * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -795,6 +829,92 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
     // address instruction per load.  The loads of a unit are split into NBATCH batches and software-pipelined across
     // batches AND units: the loads of batch b+1 (or of the next unit's batch 0) are issued before batch b is converted,
     // so the memory latency is covered by the fp32 -> fp16 hi/lo conversion of the previous batch.
+    if constexpr (C::TMAIN) {
+    const int pw = warp - C::EPIW;
+    if (pw == C::PRODW - 1) {
+      // ------------------------------------------------------------- activation loader: tensor-map bulk copies of the halo
+      if (elect_one()) {
+        int sT = 0, phT = 1;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+          const Item it = decode_item(item, n_jt, tiles_x, tiles_y, flip, C::THO);
+          const int iy0 = it.y0 - C::PAD, ix0 = it.x0 - C::PAD;
+          for (int u = 0; u < n_units; ++u) {
+#pragma unroll 1
+            for (int sub = 0; sub < C::NSUB; ++sub) {
+              int cc = u * CK + sub * C::SUB, q = 0;   // first channel of the sub-unit in the concatenated input -> source q
+#pragma unroll
+              for (int k = 0; k < 3; ++k)
+                if (q == k && k + 1 < p.n_src && cc >= p.src_c[k]) { cc -= p.src_c[k]; q = k + 1; }
+              mbar_wait(bar(TS_EMPTY + sT), phT);
+              mbar_expect_tx(bar(TS_FULL + sT), C::TSTG);
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                  ::"r"(smem_u32(ts_buf + sT * C::TSTG)), "l"(reinterpret_cast<uint64_t>(&imaps.m[q])), "r"(cc), "r"(ix0), "r"(iy0),
+                  "r"(it.n), "r"(bar(TS_FULL + sT))
+                  : "memory");
+              if (++sT == C::NTS) { sT = 0; phT ^= 1; }
+            }
+          }
+        }
+      }
+    } else {
+      // ------------------------------------------------------------- converters: staged fp32 box -> fp16 hi / lo operand planes
+      constexpr int F4PP = C::SUB / 4;                         // float4 per pixel of a sub-unit
+      constexpr int NF4 = C::NHALO * F4PP;                     // float4 per sub-unit
+      constexpr int CT = C::CONVW * 32;
+      constexpr int PER = (NF4 + CT - 1) / CT;
+      const int ctid = threadIdx.x - C::EPIW * 32;
+      const float sq = pow2f(-square_shift(p));
+      int sX = 0, phX = 1, sT = 0, phT = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int u = 0; u < n_units; ++u) {
+          mbar_wait(bar(X_EMPTY + sX), phX);
+          uint8_t* const hi = x_buf + sX * C::X_STAGE;
+#pragma unroll 1
+          for (int sub = 0; sub < C::NSUB; ++sub) {
+            mbar_wait(bar(TS_FULL + sT), phT);
+            const uint8_t* const stg = ts_buf + sT * C::TSTG;
+            float4 v[PER];
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+              const int idx = k * CT + ctid;
+              v[k] = idx < NF4 ? *reinterpret_cast<const float4*>(stg + idx * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // the box is in registers: the loader may refill the stage.  The refill is an async-proxy write of memory this
+            // thread read through the generic proxy: the proxy fence orders the two (without it the first pixels of a box
+            // were occasionally overwritten before the reads had been performed)
+            fence_async_smem();
+            mbar_arrive(bar(TS_EMPTY + sT));
+            if (++sT == C::NTS) { sT = 0; phT ^= 1; }
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+              const int idx = k * CT + ctid;
+              if (idx < NF4) {
+                const int px = idx / F4PP, f = idx - px * F4PP;
+                const int g = sub * (C::SUB / 8) + (f >> 1);
+                float4 w = v[k];
+                if (p.in_square) { w.x = w.x * w.x * sq; w.y = w.y * w.y * sq; w.z = w.z * w.z * sq; w.w = w.w * w.w * sq; }
+                uint8_t* dst = hi + (g * C::NPIXP + px) * 16 + (f & 1) * 8;
+                uint2 hv, lv;
+                if constexpr (C::ONE) {
+                  hv.x = pack_h2_sat(w.x, w.y);
+                  hv.y = pack_h2_sat(w.z, w.w);
+                  *reinterpret_cast<uint2*>(dst) = hv;
+                } else {
+                  split4(w, hv, lv);
+                  *reinterpret_cast<uint2*>(dst) = hv;
+                  *reinterpret_cast<uint2*>(dst + C::X_HALF) = lv;
+                }
+              }
+            }
+          }
+          fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+          mbar_arrive(bar(X_FULL + sX));
+          if (++sX == C::NX) { sX = 0; phX ^= 1; }
+        }
+      }
+    }
+    } else {
     using P = ProdCfg<C, CK>;
     const int pw = warp - C::EPIW;
     const int fi = lane % P::LPP, psub = lane / P::LPP;
@@ -942,6 +1062,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TdvcConvPara
       mbar_arrive(bar(X_FULL + cur.stage));
       cur = nxt;
       have = have_next;
+    }
     }
     }
   } else if (warp == C::EPIW + C::PRODW) {
@@ -1105,16 +1226,45 @@ static bool choose(const TdvcConvParams& p, Choice* c) {
   return false;
 }
 
-template <int KS, int CK, int S, int SPLIT, int NPH = 1, int PLN = 0, int PR = 0>
+// cuTensorMapEncodeTiled is looked up through the runtime at first use: linking libcuda.so directly would make the library
+// unloadable on a host without a driver (the CPU-only build / symbol checks load it there)
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn tensor_map_encoder() {
+  static EncodeFn encode = nullptr;   // idempotent; a benign race resolves it twice
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  return encode;
+}
+
+// can the sources of *p be walked by tensor maps in sub-units of `sub` channels?  (every source but the last must end on a
+// sub-unit boundary; TMA needs 16-byte aligned bases and strides)
+static bool tma_sources_ok(const TdvcConvParams& p, int ck) {
+  if (getenv("TDVC_B200_CONV_LDG") != nullptr) return false;   // developer A/B switch: producers load with LDG
+  for (int q = 0; q < p.n_src; ++q) {
+    if ((reinterpret_cast<uintptr_t>(p.src[q]) & 15) != 0 || (p.src_ld[q] & 3) != 0) return false;
+    if (q + 1 < p.n_src && p.src_c[q] % ck != 0) return false;
+  }
+  return true;
+}
+
+template <int KS, int CK, int S, int SPLIT, int NPH = 1, int PLN = 0, int PR = 0, int TMA = 0>
 static int launch(const TdvcConvParams& p, cudaStream_t st, int* rows_only) {
-  using C = Cfg<KS, CK, S, SPLIT, NPH, PLN, PR>;
+  using C = Cfg<KS, CK, S, SPLIT, NPH, PLN, PR, TMA>;
   if (rows_only != nullptr) {   // query: rows of the chan_sum buffer this launch would write (CTAs x epilogue column groups x phases)
     const int64_t it = (int64_t)p.N * cdiv(p.Wo, TW) * cdiv(p.Ho, C::THO) * cdiv(p.cout, C::NTT);
     *rows_only = (p.cout <= C::NTT && !p.out_planar && p.shuffle == 0) ? (int)(it < kNumSMs ? it : kNumSMs) * C::NGRP * NPH : 0;
     return TDVC_OK;
   }
   static int smem_done[kMaxDevices] = {0};
-  if (int rc = ensure_dynamic_smem(conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN, PR>, C::SMEM, smem_done, "conv_tc")) return rc;
+  if (int rc = ensure_dynamic_smem(conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN, PR, TMA>, C::SMEM, smem_done, "conv_tc")) return rc;
   if (C::DIRECT) TDVC_REQUIRE(p.w_shift >= -100 && p.w_shift <= 100, "conv_tc: w_shift %d out of range", p.w_shift);
   TDVC_REQUIRE(NPH == 1 || !p.out_planar, "conv_tc: planar output is not available for row-phase items");
   TDVC_REQUIRE(p.chan_sum == nullptr || (p.cout <= C::NTT && !p.out_planar && p.shuffle == 0),
@@ -1124,27 +1274,40 @@ static int launch(const TdvcConvParams& p, cudaStream_t st, int* rows_only) {
   const int64_t items = (int64_t)p.N * tiles_x * tiles_y * n_jt;
   TDVC_REQUIRE(items < (1ll << 31), "conv_tc: too many work items");
   const int grid = (int)(items < kNumSMs ? items : kNumSMs);
+  std::conditional_t<TMA != 0, InMaps, NoMap> imaps;
+  if constexpr (TMA != 0) {
+    // one tensor map per source over (channel, x, y, image) fp32; box = SUB channels x IW x IH x 1 image.  Coordinates outside
+    // the tensor (image border, channels past the source) are zero-filled by the hardware
+    EncodeFn encode = tensor_map_encoder();
+    if (encode == nullptr) {
+      set_error("conv_tc: cuTensorMapEncodeTiled is not available from this driver");
+      return TDVC_ECUDA;
+    }
+    for (int q = 0; q < p.n_src; ++q) {
+      const cuuint64_t ld = (cuuint64_t)p.src_ld[q];
+      const cuuint64_t dims[4] = {(cuuint64_t)p.src_c[q], (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+      const cuuint64_t strides[3] = {ld * 4, (cuuint64_t)p.W * ld * 4, (cuuint64_t)p.H * p.W * ld * 4};
+      const cuuint32_t box[4] = {(cuuint32_t)C::SUB, (cuuint32_t)C::IW, (cuuint32_t)C::IH, 1}, estr[4] = {1, 1, 1, 1};
+      const CUresult r = encode(&imaps.m[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.src[q]), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("conv_tc: cuTensorMapEncodeTiled failed for source %d (%d)", q, (int)r);
+        return TDVC_ECUDA;
+      }
+    }
+    for (int q = p.n_src; q < 4; ++q) imaps.m[q] = imaps.m[0];
+  }
   if constexpr (PLN != 0) {
     // tensor map of the planar output (N, cout, Ho, Wo) fp32: box = 8 px x 2 rows x 32 channels x 1 image
     CUtensorMap tm;
     const cuuint64_t dims[4] = {(cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.cout, (cuuint64_t)p.N};
     const cuuint64_t strides[3] = {(cuuint64_t)p.Wo * 4, (cuuint64_t)p.Ho * p.Wo * 4, (cuuint64_t)p.cout * p.Ho * p.Wo * 4};
     const cuuint32_t box[4] = {8, 2, 32, 1}, estr[4] = {1, 1, 1, 1};
-    // cuTensorMapEncodeTiled is looked up through the runtime at first use: linking libcuda.so directly would make the
-    // library unloadable on a host without a driver (the CPU-only build / symbol checks load it there)
-    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;   // idempotent; a benign race resolves it twice
+    EncodeFn encode = tensor_map_encoder();
     if (encode == nullptr) {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult qres;
-      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
-          qres != cudaDriverEntryPointSuccess) {
-        set_error("conv_tc: cuTensorMapEncodeTiled is not available from this driver");
-        return TDVC_ECUDA;
-      }
-      encode = reinterpret_cast<EncodeFn>(fn);
+      set_error("conv_tc: cuTensorMapEncodeTiled is not available from this driver");
+      return TDVC_ECUDA;
     }
     const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out, dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -1153,9 +1316,9 @@ static int launch(const TdvcConvParams& p, cudaStream_t st, int* rows_only) {
       set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
       return TDVC_ECUDA;
     }
-    conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN, PR><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items, tm);
+    conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN, PR, TMA><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items, tm, imaps);
   } else {
-    conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN, PR><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items, NoMap{});
+    conv_tc_kernel<KS, CK, S, SPLIT, NPH, PLN, PR, TMA><<<grid, kThreads, C::SMEM, st>>>(p, tiles_x, tiles_y, n_jt, n_units, (int)items, NoMap{}, imaps);
   }
   TDVC_CHECK_LAUNCH("conv_tc");
   return TDVC_OK;
@@ -1179,29 +1342,35 @@ int conv2d_tc(const TdvcConvParams& p, cudaStream_t st, int* rows_only) {
     set_error("conv_tc: unsupported shape");
     return TDVC_EINVAL;
   }
+  // TMA-fed activations (stride-1 KxK layers).  Measured per shape (tools/conv_bench.py, tools/ab_frame.py): the
+  // tensor-map path wins where the producers were the limit - the one-product layers and the 4-channel image layers - and costs
+  // 1-2 % on the MMA-bound fp32-class layers (the staged box crosses shared memory twice), so it is the default for the former
+  // only.  TDVC_B200_CONV_TMA=1 / TDVC_B200_CONV_LDG=1 force it on / off for every eligible layer (developer A/B).
+  const bool tma_ok = c.s == 1 && c.ks != 1 && tc::tma_sources_ok(p, c.ck);
+  const bool tma = tma_ok && (getenv("TDVC_B200_CONV_TMA") != nullptr || c.pr == 1 || (c.ks == 3 && c.ck == 16));
   if (c.pr == 1) {
-    if (c.ks == 3 && c.nph == 2) return tc::launch<3, 32, 1, 0, 2, 0, 1>(p, st, rows_only);
-    if (c.ks == 3) return tc::launch<3, 32, 1, 0, 1, 0, 1>(p, st, rows_only);
+    if (c.ks == 3 && c.nph == 2) return tma ? tc::launch<3, 32, 1, 0, 2, 0, 1, 1>(p, st, rows_only) : tc::launch<3, 32, 1, 0, 2, 0, 1>(p, st, rows_only);
+    if (c.ks == 3) return tma ? tc::launch<3, 32, 1, 0, 1, 0, 1, 1>(p, st, rows_only) : tc::launch<3, 32, 1, 0, 1, 0, 1>(p, st, rows_only);
     if (c.ks == 1) return tc::launch<1, 32, 1, 0, 1, 0, 1>(p, st, rows_only);
   } else if (c.split) {
     if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2, 1>(p, st, rows_only);
     if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2, 1>(p, st, rows_only);
     // DCN offset / mask head: planar output through TMA tensor stores (needs 16-byte aligned planes and row pitch)
     if (c.ks == 3 && p.out_planar && (p.Wo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
-      return tc::launch<3, 32, 1, 1, 1, 1>(p, st, rows_only);
-    if (c.ks == 3) return tc::launch<3, 32, 1, 1>(p, st, rows_only);
+      return tma ? tc::launch<3, 32, 1, 1, 1, 1, 0, 1>(p, st, rows_only) : tc::launch<3, 32, 1, 1, 1, 1>(p, st, rows_only);
+    if (c.ks == 3) return tma ? tc::launch<3, 32, 1, 1, 1, 0, 0, 1>(p, st, rows_only) : tc::launch<3, 32, 1, 1>(p, st, rows_only);
     if (c.ks == 1) return tc::launch<1, 32, 1, 1>(p, st, rows_only);
-    if (c.ks == 5) return tc::launch<5, 32, 1, 1>(p, st, rows_only);
+    if (c.ks == 5) return tma ? tc::launch<5, 32, 1, 1, 1, 0, 0, 1>(p, st, rows_only) : tc::launch<5, 32, 1, 1>(p, st, rows_only);
   } else {
     if (c.s == 2 && c.ks == 3) return tc::launch<3, 16, 2, 0>(p, st, rows_only);
     if (c.s == 2 && c.ks == 1) return tc::launch<1, 32, 2, 0>(p, st, rows_only);
-    if (c.ks == 3 && c.ck == 32) return tc::launch<3, 32, 1, 0>(p, st, rows_only);
-    if (c.ks == 3 && c.ck == 16) return tc::launch<3, 16, 1, 0>(p, st, rows_only);
+    if (c.ks == 3 && c.ck == 32) return tma ? tc::launch<3, 32, 1, 0, 1, 0, 0, 1>(p, st, rows_only) : tc::launch<3, 32, 1, 0>(p, st, rows_only);
+    if (c.ks == 3 && c.ck == 16) return tma ? tc::launch<3, 16, 1, 0, 1, 0, 0, 1>(p, st, rows_only) : tc::launch<3, 16, 1, 0>(p, st, rows_only);
     if (c.ks == 1) return tc::launch<1, 32, 1, 0>(p, st, rows_only);
-    if (c.ks == 5) return tc::launch<5, 32, 1, 0>(p, st, rows_only);
-    if (c.ks == 7 && c.nph == 2) return tc::launch<7, 16, 1, 0, 2>(p, st, rows_only);
-    if (c.ks == 7 && c.ck == 32) return tc::launch<7, 32, 1, 0>(p, st, rows_only);
-    if (c.ks == 7 && c.ck == 16) return tc::launch<7, 16, 1, 0>(p, st, rows_only);
+    if (c.ks == 5) return tma ? tc::launch<5, 32, 1, 0, 1, 0, 0, 1>(p, st, rows_only) : tc::launch<5, 32, 1, 0>(p, st, rows_only);
+    if (c.ks == 7 && c.nph == 2) return tma ? tc::launch<7, 16, 1, 0, 2, 0, 0, 1>(p, st, rows_only) : tc::launch<7, 16, 1, 0, 2>(p, st, rows_only);
+    if (c.ks == 7 && c.ck == 32) return tma ? tc::launch<7, 32, 1, 0, 1, 0, 0, 1>(p, st, rows_only) : tc::launch<7, 32, 1, 0>(p, st, rows_only);
+    if (c.ks == 7 && c.ck == 16) return tma ? tc::launch<7, 16, 1, 0, 1, 0, 0, 1>(p, st, rows_only) : tc::launch<7, 16, 1, 0>(p, st, rows_only);
   }
   set_error("conv_tc: no instantiation for ks=%d ck=%d stride=%d split=%d", c.ks, c.ck, c.s, c.split);
   return TDVC_EINVAL;

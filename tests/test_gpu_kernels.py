@@ -180,6 +180,39 @@ def test_conv2d_chan_sum_feeds_squeeze_excitation(plan, dev, case):
     assert (o1.nchw() - o2.nchw()).abs().max().item() < 2e-6 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("case", [(64, 64, 3, 1024, 1920, 1, 0), (64, 64, 3, 1024, 1920, 1, 1), (128, 128, 3, 512, 960, 1, 1),
+                                  (4, 64, 3, 512, 960, 2, 0), (64, 32, 7, 512, 960, 1, 0), (128, 256, 5, 64, 120, 1, 0)])
+def test_conv_tma_fed_equals_ldg_fed(plan, dev, case):
+    """The two activation paths of conv_tc - tensor-map bulk copies into a staging ring (UTMALDG) and per-lane LDG - feed the same
+    operand planes: identical bits, repeatedly, at sizes where every CTA walks dozens of items (a missing proxy fence between the
+    converters' reads of a staged box and the next bulk copy into it once showed up only there)."""
+    import os
+    from tdvc_b200.model import Act, pack_conv
+    from tdvc_b200 import tc
+    cin, cout, k, H, W, N, products = case
+    torch.manual_seed(17)
+    conv = torch.nn.Conv2d(cin, cout, k, 1, k // 2).to(dev)
+    cw = pack_conv(conv.weight, conv.bias, src_layout=[(cin, (cin + 3) // 4 * 4)])
+    tc.attach_f16({"w": cw}, one_product=products == 1)
+    x = Act.alloc(N, H, W, cin, dev, ld=(cin + 3) // 4 * 4, zero=True)
+    x.t[..., :cin].normal_()
+    saved = {k_: os.environ.pop(k_, None) for k_ in ("TDVC_B200_CONV_LDG", "TDVC_B200_CONV_TMA")}
+    try:
+        outs = []
+        for var in ("TDVC_B200_CONV_LDG", "TDVC_B200_CONV_TMA", "TDVC_B200_CONV_TMA", "TDVC_B200_CONV_TMA"):
+            os.environ[var] = "1"
+            out = Act.alloc(N, H, W, cout, dev, ld=(cout + 3) // 4 * 4, zero=True)
+            plan.conv([x], cw, out, impl=2, products=products, act=2, slope=0.1)
+            torch.cuda.synchronize()
+            outs.append(out.t)
+            del os.environ[var]
+    finally:
+        for k_, v in saved.items():
+            if v is not None:
+                os.environ[k_] = v
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+
 def test_conv2d_out_absmax(plan, dev):
     """TdvcConvParams::out_absmax: max |v| over everything the layer stored, on the tensor-core and the SIMT kernel."""
     from tdvc_b200.model import Act, pack_conv

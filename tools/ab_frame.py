@@ -40,7 +40,14 @@ def main(attr="overlap_cache", blocks=4, frames=44, amp=1):
     res = {True: [], False: []}
     for b in range(2 * blocks):
         val = b % 2 == 0
-        setattr(plan, attr, val)
+        if attr.startswith("env:"):      # an environment switch read by the library at launch time: True = variable unset
+            import os
+            if val:
+                os.environ.pop(attr[4:], None)
+            else:
+                os.environ[attr[4:]] = "1"
+        else:
+            setattr(plan, attr, val)
         plan.graphs = {}          # the switch changes the captured launch structure
         chain(22)
         torch.cuda.synchronize()
