@@ -134,7 +134,10 @@ struct Cfg {
   // the tensor pipe: their producers stage the fp32 unit in shared memory with cp.async, NSTG units ahead (each thread reads
   // back only the 16-byte slots it copied itself, so no barrier is involved), and convert from there.
   static constexpr bool STAGED = (KS == 1 && S == 1);
-  static constexpr int NSTG = 2;
+#ifndef TDVC_CONV_TC_NSTG
+#define TDVC_CONV_TC_NSTG 2
+#endif
+  static constexpr int NSTG = TDVC_CONV_TC_NSTG;
   static constexpr int LOADS_PER_THREAD = (NHALO * (CK / 4) / 32 + PRODW - 1) / PRODW;   // = ProdCfg::PER_WARP
   static constexpr int STG_UNIT = LOADS_PER_THREAD * PRODW * 32 * 16;
   static constexpr int STG_BYTES = STAGED ? NSTG * STG_UNIT : 0;
