@@ -641,3 +641,36 @@ def test_validate_over_a_gop_dataset(net, dev, tmp_path):
     assert summ["frames"] == 9 and abs(mv - summ["bpp_mv"]) < 1e-9 and abs(rs - summ["bpp_res"]) < 1e-9 and abs(mse - summ["mse"]) < 1e-12
     assert abs(bpp - (summ["bpp"] * 9 + 3 * 0.75) / 12) < 1e-9 and abs(psnr - (summ["psnr"] * 9 + i_psnr) / 12) < 1e-9
     assert 0.0 < ms <= 1.0 and math.isfinite(psnr)
+
+
+def test_batch_of_two_graphs_and_caches(net, dev):
+    """N = 2 through the per-variant CUDA graphs and the per-GOP caches (keys are per batch element): a 4-frame chain of a
+    2-sequence batch equals the eager, cache-free chain bit for bit, and each sequence equals its own single-sequence chain in
+    the symbols-free outputs to fp32 rounding (batched SE / bpp reductions sum in a different order)."""
+    from tdvc_b200 import gop as G
+    from tdvc_b200 import synth
+    net.conv_impl, net.precision = 0, "auto"
+    fa, fb = synth.make_gop(64, 128, gop=5, seed=71).to(dev), synth.make_gop(64, 128, gop=5, seed=72).to(dev)
+    both = torch.stack([fa, fb], 1)    # (T, 2, 3, H, W)
+
+    def chain(frames, cache, graph, amp=False):
+        net.cache_features, net.use_cuda_graph = cache, graph
+        refs, out = [frames[0]], []
+        for t in range(1, frames.shape[0]):
+            with torch.no_grad():
+                r = net(frames[t], G.reference_window(refs), amp)
+            refs.append(r[0])
+            out.append(r)
+        return out
+
+    try:
+        base = chain(both, False, False)
+        fast = chain(both, True, True)
+        fast2 = chain(both, True, True)     # second pass: graph replays
+        single = chain(fa.unsqueeze(1), True, False)
+    finally:
+        net.cache_features, net.use_cuda_graph = True, False
+    for a, b, c in zip(base, fast, fast2):
+        assert all(torch.equal(u, v) and torch.equal(u, w) for u, v, w in zip(a, b, c))
+    for a, s in zip(base, single):
+        assert (a[0][0:1] - s[0]).abs().max().item() <= 1e-4
