@@ -239,6 +239,47 @@ int tdvc_eb_aux_loss_grad(const float* mats, const float* biases, const float* f
                           const float* target3, const float* grad_out, int C, float* grad_quantiles, void* stream);
 int tdvc_uniform_noise(float* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream);
 
+/* ---- real entropy coding (`is_compress=True`: reference pnet.py:45-49,69-73 -> compressai `update(force=True)` and
+ * `compress()`; compressai is not in the reference tree, SURVEY App. A / DESIGN.md section 7) ----
+ * Tables (`update`): pmf_to_quantized_cdf (HOST pointers, host code as in compressai): n probabilities (the last one the
+ *   tail mass) -> n + 1 cumulative 16-bit counts; empty bins steal from the smallest bin above 1.
+ * Symbols (`compress`):
+ *   eb_symbols: z NHWC -> symbols round(z - median) and table indexes (= channel) in NCHW order.
+ *   ar_code: the autoregressive pass over y of compressai `_compress_ar` as wavefronts inside one launch, one thread-block
+ *     cluster per image: symbols round(y - mean), table indexes of max(scale, 0.11) and y_hat = symbol + mean, all NHWC
+ *     ((h, w, c): the order compressai codes them in).  Weights in the fp32 layout of tdvc_conv2d ([tap][cin_pad][cout_pad]):
+ *     w_ctx the masked 5x5 context model (C -> 2C), w1 / w2 / w3 the entropy-parameter 1x1 layers (4C -> c1 -> c2 -> 2C,
+ *     LeakyReLU 0.01 between; w1 rows: hyper-decoder output first, context second).  `cluster` = CTAs per image (8; 16 =
+ *     non-portable size).  `workspace`: tdvc_ar_code_workspace_bytes(N, c1_pad, c2_pad) bytes.
+ * Coder (HOST pointers, host code: compressai's `ans` extension runs on the CPU too): 64-bit rANS, 16-bit precision, one CDF
+ *   row per table index, out-of-range symbols escape through the last bin + a 4-bit bypass code.  encode returns the stream
+ *   length in bytes (< 0: error code); decode is its inverse given the same indexes.                                        */
+typedef struct TdvcArParams {
+  const float* y;        int32_t y_ld;
+  const float* params;   int32_t params_ld;
+  const float* w_ctx;    const float* b_ctx;
+  const float* w1;       const float* b1;   int32_t c1, c1_pad;
+  const float* w2;       const float* b2;   int32_t c2, c2_pad;
+  const float* w3;       const float* b3;
+  const float* scale_table;  int32_t n_scales;
+  float* y_hat;          /* [N][H][W][C] */
+  int32_t* symbols;      /* [N][H][W][C] */
+  int32_t* indexes;      /* [N][H][W][C] */
+  int32_t N, H, W, C;
+  int32_t cluster;
+} TdvcArParams;
+int tdvc_pmf_to_quantized_cdf(const float* pmf, int n, int precision, int32_t* cdf);
+int tdvc_eb_symbols(const float* z, int ld, const float* medians, int N, int HW, int C, int32_t* symbols, int32_t* indexes,
+                    void* stream);
+size_t tdvc_ar_code_workspace_bytes(int N, int c1_pad, int c2_pad);
+int tdvc_ar_code(const TdvcArParams* p, void* workspace, size_t workspace_bytes, void* stream);
+int64_t tdvc_rans_encode_with_indexes(const int32_t* symbols, const int32_t* indexes, int64_t n, const int32_t* cdfs,
+                                      int cdf_stride, const int32_t* cdf_lengths, const int32_t* offsets, int n_tables,
+                                      uint8_t* out, int64_t capacity);
+int tdvc_rans_decode_with_indexes(const uint8_t* data, int64_t nbytes, const int32_t* indexes, int64_t n, const int32_t* cdfs,
+                                  int cdf_stride, const int32_t* cdf_lengths, const int32_t* offsets, int n_tables,
+                                  int32_t* symbols);
+
 /* ---- reference-based in-loop filter pieces (reference pnet.py:213-257) ----
  * avgpool_scale: nn.AvgPool2d(scale) -> (N, H/scale, W/scale, C)                         (:219-226)
  * ff_descriptors: unfold(3, pad 3, stride 3) + F.normalize -> desc (N, P, C*9), feature c*9 + ky*3 + kx;

@@ -389,7 +389,7 @@ class VideoCompressor(nn.Module):
         self.mcfilter = LoopFilter()
 
     def forward(self, input_image, refer_frames, enabled_amp=False, is_compress=False, taps=None):
-        assert not is_compress, "entropy coding is a 'next' row (SURVEY 8f.3)"
+        self.last_coded = {}
         ref = refer_frames[:, -1]
         in_f = self.extra_fea(input_image)  # pnet.py:29-30
         ref_f = self.extra_fea(ref)
@@ -399,12 +399,16 @@ class VideoCompressor(nn.Module):
         n, _, h, w = input_image.shape
         npx = n * h * w
         bpp_mv = _bpp(mv["likelihoods"], npx)  # :38-43
+        if is_compress:  # :45-49 (the reference computes ac_bpp_mv and drops it; kept here for the tests)
+            self._code("mv", self.mvCoder, estmv.float(), npx, taps)
         pred1 = self.mcnet(mv["x_hat"], ref_f, taps)  # :52
         pred = self.mcfilter(pred1, refer_frames)  # :53
         resid = in_f - pred  # :55
         rs = self.resCoder.forward(resid.float())  # :58
         rs_aux = self.resCoder.aux_loss()
         bpp_res = _bpp(rs["likelihoods"], npx)  # :62-67
+        if is_compress:  # :69-73
+            self._code("res", self.resCoder, resid.float(), npx, taps)
         rec_f = pred + rs["x_hat"]  # :76
         recon = self.loopfilter(rec_f, refer_frames, taps).clamp(0.0, 1.0)  # :77-78
         if taps is not None:
@@ -419,3 +423,15 @@ class VideoCompressor(nn.Module):
         if self.training:
             return recon, bpp_res.view(-1), bpp_mv.view(-1), mv_aux, rs_aux
         return recon, bpp_res.view(-1), bpp_mv.view(-1)
+
+    def _code(self, name, coder, x, npx, taps):
+        """reference pnet.py:45-49 / 69-73: eval(), update(force=True), compress(); coded bits of the FIRST batch item
+        of each string list over N*H*W pixels, exactly as the reference writes it (`len(s[0])`)."""
+        coder.eval()
+        coder.update(force=True)
+        t = {} if taps is not None else None
+        out_enc = coder.compress(x, taps=t)
+        ac_bpp = sum(len(s[0]) for s in out_enc["strings"]) * 8.0 / npx
+        self.last_coded[name] = {"strings": out_enc["strings"], "shape": tuple(out_enc["shape"]), "ac_bpp": ac_bpp}
+        if taps is not None:
+            taps.update({f"{name}.ac.{k}": v for k, v in t.items()})

@@ -208,6 +208,24 @@ __global__ void uniform_noise_kernel(float* __restrict__ out, int64_t n, uint64_
   }
 }
 
+// ---- real entropy coding: the "symbols" quantiser of z (compressai EntropyBottleneck.compress; reached from reference
+// pnet.py:45-49,69-73 `compress()`).
+// eb_symbols: z NHWC -> int32 symbols round(z - median) in NCHW order (the order compressai's EntropyBottleneck.compress
+// flattens them in), indexes[i] = channel.
+__global__ void eb_symbols_kernel(const float* __restrict__ z, int ld, const float* __restrict__ medians, int N, int HW, int C,
+                                  int32_t* __restrict__ symbols, int32_t* __restrict__ indexes) {
+  const int64_t total = (int64_t)N * C * HW;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int p = (int)(i % HW);
+    const int c = (int)((i / HW) % C);
+    const int n = (int)(i / ((int64_t)HW * C));
+    const float v = __ldg(z + ((int64_t)n * HW + p) * ld + c);
+    symbols[i] = __float2int_rn(__fsub_rn(v, medians[c]));
+    indexes[i] = c;
+  }
+}
+
 }  // namespace tdvc
 
 using namespace tdvc;
@@ -285,5 +303,15 @@ extern "C" int tdvc_gc_bits_noise(const float* y, const float* noise, const floa
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   gc_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, noise, params, params_ld, total, C, acc);
   TDVC_CHECK_LAUNCH("gc_bits_noise");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_eb_symbols(const float* z, int ld, const float* medians, int N, int HW, int C, int32_t* symbols,
+                               int32_t* indexes, void* stream) {
+  TDVC_REQUIRE(z && medians && symbols && indexes && N > 0 && HW > 0 && C > 0 && ld >= C, "eb_symbols: bad args");
+  int grid = cdiv((int64_t)N * HW * C, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  eb_symbols_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, ld, medians, N, HW, C, symbols, indexes);
+  TDVC_CHECK_LAUNCH("eb_symbols");
   return TDVC_OK;
 }

@@ -41,6 +41,14 @@ class DcnParams(C.Structure):
                 ("params_planar", C.c_int32)]
 
 
+class ArParams(C.Structure):
+    _fields_ = [("y", c_fp), ("y_ld", C.c_int32), ("params", c_fp), ("params_ld", C.c_int32),
+                ("w_ctx", c_fp), ("b_ctx", c_fp), ("w1", c_fp), ("b1", c_fp), ("c1", C.c_int32), ("c1_pad", C.c_int32),
+                ("w2", c_fp), ("b2", c_fp), ("c2", C.c_int32), ("c2_pad", C.c_int32), ("w3", c_fp), ("b3", c_fp),
+                ("scale_table", c_fp), ("n_scales", C.c_int32), ("y_hat", c_fp), ("symbols", c_fp), ("indexes", c_fp),
+                ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("cluster", C.c_int32)]
+
+
 i32, i64, f32, vp, sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 
 # name -> argtypes, in header order (tests check that every symbol declared in include/tdvc_b200.h is here)
@@ -83,6 +91,12 @@ SIGNATURES = {
     "tdvc_eb_aux_loss": [vp, vp, vp, vp, vp, i32, vp, vp],
     "tdvc_eb_aux_loss_grad": [vp, vp, vp, vp, vp, vp, i32, vp, vp],
     "tdvc_uniform_noise": [vp, i64, C.c_uint64, C.c_uint64, vp],
+    "tdvc_pmf_to_quantized_cdf": [vp, i32, i32, vp],
+    "tdvc_eb_symbols": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
+    "tdvc_ar_code_workspace_bytes": [i32, i32, i32],
+    "tdvc_ar_code": [C.POINTER(ArParams), vp, sz, vp],
+    "tdvc_rans_encode_with_indexes": [vp, vp, i64, vp, i32, vp, vp, i32, vp, i64],
+    "tdvc_rans_decode_with_indexes": [vp, i64, vp, i64, vp, i32, vp, vp, i32, vp],
     "tdvc_avgpool_scale": [vp, i32, vp, i32, i32, i32, i32, i32, vp],
     "tdvc_ff_descriptors": [vp, vp, i32, i32, i32, i32, vp],
     "tdvc_ff_match": [vp, vp, vp, vp, i32, i32, i32, vp],
@@ -113,6 +127,8 @@ def load():
     lib.tdvc_dcn_v2_backward_workspace_bytes.restype = C.c_size_t
     lib.tdvc_conv2d_f16_bytes.restype = C.c_size_t
     lib.tdvc_dcn_f16_bytes.restype = C.c_size_t
+    lib.tdvc_ar_code_workspace_bytes.restype = C.c_size_t
+    lib.tdvc_rans_encode_with_indexes.restype = C.c_int64
     _lib = lib
     return lib
 

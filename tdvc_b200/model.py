@@ -32,6 +32,9 @@ _LN2 = math.log(2.0)
 
 
 # =============================================================================== parameter containers
+_CDF_BUFFERS = ("_offset", "_quantized_cdf", "_cdf_length", "scale_table")   # written by update(); no packed weight reads them
+
+
 class _ConvModule(nn.Module):  # mmcv ConvModule naming: `<name>.conv.weight`
     def __init__(self, i, o, k):
         super().__init__()
@@ -223,7 +226,20 @@ class _RBUpsample(nn.Module):
         self.upsample = _subpel(i, o, r)
 
 
-class _EntropyBottleneck(nn.Module):
+class _CdfBuffers(nn.Module):
+    """compressai's entropy models carry their coding tables as buffers that `update()` resizes; a checkpoint saved after
+    `update()` holds them filled.  Loading resizes ours to whatever arrives (compressai: `update_registered_buffers`)."""
+
+    def _load_from_state_dict(self, state_dict, prefix, *args):
+        for name in _CDF_BUFFERS:
+            t = state_dict.get(prefix + name)
+            buf = getattr(self, name, None)
+            if t is not None and buf is not None and buf.shape != t.shape:
+                setattr(self, name, torch.empty(t.shape, dtype=buf.dtype, device=buf.device))
+        super()._load_from_state_dict(state_dict, prefix, *args)
+
+
+class _EntropyBottleneck(_CdfBuffers):
     def __init__(self, channels, tail_mass=1e-9, init_scale=10, filters=(3, 3, 3, 3)):
         super().__init__()
         f = (1,) + tuple(filters) + (1,)
@@ -243,7 +259,7 @@ class _EntropyBottleneck(nn.Module):
         self.likelihood_lower_bound = _Bound(1e-9)
 
 
-class _GaussianConditional(nn.Module):
+class _GaussianConditional(_CdfBuffers):
     def __init__(self):
         super().__init__()
         self.register_buffer("_offset", torch.IntTensor())
@@ -524,16 +540,23 @@ class _Packed:
         cv(f"{cn}.ep0", ep[0], src_layout=[(256, 256), (256, 256)])
         cv(f"{cn}.ep2", ep[2], src_layout=[(ep[2].in_channels, _r(ep[2].in_channels, 4))])
         cv(f"{cn}.ep4", ep[4], src_layout=[(ep[4].in_channels, _r(ep[4].in_channels, 4))])
-        eb = cd.entropy_bottleneck
-        Cc = eb.quantiles.shape[0]
-        mats = torch.cat([F.softplus(P(eb, f"_matrix{i}")).reshape(Cc, -1) for i in range(5)], 1)
-        biases = torch.cat([P(eb, f"_bias{i}").reshape(Cc, -1) for i in range(5)], 1)
-        factors = torch.cat([torch.tanh(P(eb, f"_factor{i}")).reshape(Cc, -1) for i in range(4)], 1)
-        if mats.shape[1] != 33 or biases.shape[1] != 13 or factors.shape[1] != 12:
-            raise RuntimeError("EntropyBottleneck: expected filters (3, 3, 3, 3)")
-        c[f"{cn}.eb"] = (mats.contiguous(), biases.contiguous(), factors.contiguous(),
-                         P(eb, "quantiles")[:, 0, 1].contiguous(), P(eb, "quantiles").reshape(Cc, 3).contiguous(),
-                         P(eb, "target").reshape(3).contiguous())
+        c[f"{cn}.eb"] = pack_entropy_bottleneck(cd.entropy_bottleneck, P)
+
+
+def pack_entropy_bottleneck(eb, P=None):
+    """Host tensors of one EntropyBottleneck as the kernels (and coding.eb_tables) read them: (softplus(matrices) [C][33],
+    biases [C][13], tanh(factors) [C][12], medians [C], quantiles [C][3], target [3])."""
+    if P is None:
+        P = lambda mod, name: getattr(mod, name).detach().float().cpu()
+    Cc = eb.quantiles.shape[0]
+    mats = torch.cat([F.softplus(P(eb, f"_matrix{i}")).reshape(Cc, -1) for i in range(5)], 1)
+    biases = torch.cat([P(eb, f"_bias{i}").reshape(Cc, -1) for i in range(5)], 1)
+    factors = torch.cat([torch.tanh(P(eb, f"_factor{i}")).reshape(Cc, -1) for i in range(4)], 1)
+    if mats.shape[1] != 33 or biases.shape[1] != 13 or factors.shape[1] != 12:
+        raise RuntimeError("EntropyBottleneck: expected filters (3, 3, 3, 3)")
+    return (mats.contiguous(), biases.contiguous(), factors.contiguous(),
+            P(eb, "quantiles")[:, 0, 1].contiguous(), P(eb, "quantiles").reshape(Cc, 3).contiguous(),
+            P(eb, "target").reshape(3).contiguous())
 
 
 _PACK_GEN = itertools.count(1)
@@ -571,7 +594,8 @@ def _upload(c, dev):
 
 
 def _param_key(m):
-    return tuple((p.data_ptr(), p._version) for p in list(m.parameters()) + list(m.buffers()))
+    bufs = [b for n, b in m.named_buffers() if n.rsplit(".", 1)[-1] not in _CDF_BUFFERS]
+    return tuple((p.data_ptr(), p._version) for p in list(m.parameters()) + bufs)
 
 
 # =============================================================================== the plan
@@ -1421,9 +1445,10 @@ class VideoCompressor(nn.Module):
         ref_keys (extension, optional): four hashable identities of refer_frames[:, 0..3] from a caller that knows them (a GOP
         driver: `tdvc_b200.gop.code_gop`); the per-GOP feature caches are then keyed on them instead of on a device-side
         content hash, which saves the one host synchronisation per frame the hash costs.  Equal keys MUST mean equal content."""
-        if is_compress:
-            raise NotImplementedError("entropy coding (is_compress=True) is a 'next' row (SURVEY.md 8f.3)")
         if self.training:
+            if is_compress:
+                raise RuntimeError("is_compress=True is served in eval() mode (the reference switches both coders to eval() "
+                                   "before it codes, pnet.py:46,70)")
             return self._forward_training(input_image, refer_frames, taps, noise=None)
         N, H, W = self._check(input_image, refer_frames, 3)
         dev = input_image.device
@@ -1437,10 +1462,45 @@ class VideoCompressor(nn.Module):
             if ref_keys is not None and len(ref_keys) != 4:
                 raise RuntimeError("ref_keys: expected four identities, one per reference slice")
             recon, bpp = plan.run(Wt, x, refs, taps, graph=self.use_cuda_graph, cache=self.cache_features, ref_keys=ref_keys)
-            self.last_launches = plan.launches
             recon, bpp = recon.clone(), bpp.clone()   # the plan's buffers are overwritten by the next frame
+            if is_compress:
+                self.last_coded = self._code(plan, Wt, N * H * W, taps)
+            self.last_launches = plan.launches
         # reference returns (recon, bpp_res.view(-1), bpp_mv.view(-1))  (pnet.py:82-83)
         return recon, bpp[1:2], bpp[0:1]
+
+    def _code(self, plan, Wt, num_pixels, taps=None):
+        """reference pnet.py:45-49,69-73: `update(force=True)` + `compress()` of both coders on this frame's latents and the
+        coded size `ac_bpp = sum(len(s[0]) for s in strings) * 8 / num_pixels`.  The reference computes ac_bpp_mv / ac_bpp_res
+        and drops them (the return tuple is unchanged); here they stay readable in `self.last_coded`:
+        {"mv" | "res": {"strings": [y_strings, z_strings], "shape": (h, w), "ac_bpp": float}}."""
+        from tdvc_b200 import coding
+        out, pending = {}, []
+        main = torch.cuda.current_stream(plan.dev)
+        side = plan._side_stream()
+        tabs = Wt.setdefault("_tables", {})
+        for cn, nm, stream in (("mv", "mv", main), ("rs", "res", side)):
+            if cn not in tabs:   # update(force=True) recomputes the same tables from the same parameters: once per pack
+                tabs[cn] = coding.CoderTables(Wt, cn, plan.dev)
+                src = self._source()
+                smod = src.mvCoder if cn == "mv" else src.resCoder
+                for m, t in ((smod.entropy_bottleneck, tabs[cn].eb), (smod.gaussian_conditional, tabs[cn].gc)):
+                    m._quantized_cdf, m._cdf_length, m._offset = t.tensors(plan.dev)   # compressai's buffers, as update() leaves them
+                smod.gaussian_conditional.scale_table = tabs[cn].scale_table.clone()
+            # the two coders' autoregressive passes (one 8-16 SM cluster per image each) run side by side on two streams;
+            # the host codes the motion strings while the residual pass is still running
+            if stream is not main:
+                stream.wait_stream(main)
+            pending.append((nm, coding.launch_coding(plan, Wt, cn, tabs[cn], stream=stream)))
+        for nm, h in pending:
+            enc = coding.finish_coding(h, keep=taps is not None)
+            enc["ac_bpp"] = sum(len(s[0]) for s in enc["strings"]) * 8.0 / num_pixels
+            if taps is not None:
+                for k in ("y_symbols", "y_indexes", "y_hat", "z_symbols"):
+                    taps[f"{nm}.ac.{k}"] = enc.pop(k)
+            out[nm] = enc
+        main.wait_stream(side)
+        return out
 
     def _forward_training(self, input_image, refer_frames, taps=None, noise=None):
         """`self.training` branch of reference pnet.py:26-83: uniform-noise quantisation in both coders (compressai

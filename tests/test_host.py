@@ -32,17 +32,17 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    """ctypes mirrors of the two parameter structs must have the C sizes (checked against a tiny C program)."""
+    """ctypes mirrors of the parameter structs must have the C sizes (checked against a tiny C program)."""
     import ctypes
     import subprocess
     import tempfile
     from tdvc_b200 import lib as L
-    src = '#include <stdio.h>\n#include "tdvc_b200.h"\nint main(){printf("%zu %zu\\n", sizeof(TdvcConvParams), sizeof(TdvcDcnParams));return 0;}\n'
+    src = '#include <stdio.h>\n#include "tdvc_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(TdvcConvParams), sizeof(TdvcDcnParams), sizeof(TdvcArParams));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
-        a, b = subprocess.check_output([os.path.join(d, "s")]).split()
-    assert int(a) == ctypes.sizeof(L.ConvParams) and int(b) == ctypes.sizeof(L.DcnParams)
+        a, b, c = subprocess.check_output([os.path.join(d, "s")]).split()
+    assert int(a) == ctypes.sizeof(L.ConvParams) and int(b) == ctypes.sizeof(L.DcnParams) and int(c) == ctypes.sizeof(L.ArParams)
 
 
 def test_state_dict_matches_reference_key_set(oracle_model):
@@ -56,17 +56,19 @@ def test_state_dict_matches_reference_key_set(oracle_model):
         assert v.shape == osd[k].shape and torch.equal(v, osd[k]), k
 
 
-def test_forward_refuses_cpu_and_entropy_coding():
+def test_forward_refuses_cpu():
     from tdvc_b200.model import VideoCompressor
     net = VideoCompressor().eval()
     x, r = torch.zeros(1, 3, 64, 64), torch.zeros(1, 4, 3, 64, 64)
     with pytest.raises(RuntimeError):
         net(x, r, False)  # no CPU fallback
-    with pytest.raises(NotImplementedError):
-        net(x, r, False, True)
+    with pytest.raises(RuntimeError):
+        net(x, r, False, True)  # entropy coding is CUDA-only as well
     net.train()
     with pytest.raises(RuntimeError):
         net(x, r, False)  # the training-mode forward is CUDA-only as well
+    with pytest.raises(RuntimeError):
+        net(x, r, False, True)  # coding is served in eval() mode
 
 
 def _emulate_packed_conv(xs, cw, stride=1):
