@@ -239,6 +239,22 @@ int tdvc_eb_aux_loss_grad(const float* mats, const float* biases, const float* f
                           const float* target3, const float* grad_out, int C, float* grad_quantiles, void* stream);
 int tdvc_uniform_noise(float* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream);
 
+/* ---- backward pieces of the convolutions (the reference's training step takes them from cuDNN through
+ * autograd, tools/train.py:125-159).  dgrad is tdvc_conv2d itself on the transposed, flipped weight (pad' = k - 1 - pad),
+ * after zero_insert for a strided layer; see tdvc_b200/ops.py `conv2d`.
+ * act_backward: grad_pre = grad_y * f'(y) from the layer's OUTPUT y (TDVC_ACT_*; NONE copies).
+ * zero_insert: out (N,H,W,C) <- g (N,Ho,Wo,C): out[n][oy*stride][ox*stride] = g[n][oy][ox], zero elsewhere (C % 4 == 0).
+ * conv2d_wgrad: grad_w[cout][cin][k][k] (nn.Conv2d.weight layout) = sum_p x[p*stride + tap - pad][ci] * grad_y[p][co] and
+ *   grad_b[co] = sum_p grad_y[p][co] (NULL: skipped); x (N,H,W,cin) / grad_y (N,Ho,Wo,cout) NHWC with leading dimensions;
+ *   exact fp32, deterministic (fixed-order two-stage sum).  workspace: tdvc_conv2d_wgrad_workspace_bytes(N,Ho,Wo,cin,cout,k). */
+int tdvc_act_backward(const float* y, const float* grad_y, float* grad_pre, int64_t n, int act, float slope, void* stream);
+int tdvc_zero_insert(const float* g, int g_ld, float* out, int out_ld, int N, int H, int W, int Ho, int Wo, int C, int stride,
+                     void* stream);
+size_t tdvc_conv2d_wgrad_workspace_bytes(int N, int Ho, int Wo, int cin, int cout, int k);
+int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, int N, int H, int W, int cin, int cout, int k,
+                      int stride, int pad, float* grad_w, float* grad_b_or_null, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* ---- real entropy coding (`is_compress=True`: reference pnet.py:45-49,69-73 -> compressai `update(force=True)` and
  * `compress()`; compressai is not in the reference tree, SURVEY App. A / DESIGN.md section 7) ----
  * Tables (`update`): pmf_to_quantized_cdf (HOST pointers, host code as in compressai): n probabilities (the last one the

@@ -1,0 +1,238 @@
+// Backward pieces of the convolutions (the training step's dgrad / wgrad; reference tools/train.py:125-159
+// takes them from cuDNN through autograd).
+//
+// * dgrad needs no kernel of its own: d x = conv(d y, W^T flipped) is a stride-1 convolution of the output gradient with
+//   the transposed, spatially flipped weight (pad' = k - 1 - pad), so it runs on the forward kernels (tcgen05 hi/lo split
+//   included) from a re-packed weight.  A stride-s layer first spreads its output gradient over the input grid
+//   (`zero_insert`: g_up[oy * s][ox * s] = g[oy][ox], zeros elsewhere).
+// * `act_backward`: g * f'(y) from the layer's OUTPUT (ReLU / LeakyReLU / clamp keep the sign information there).
+// * `wgrad`: d W[co][ci][ky][kx] = sum over pixels of x[p + tap][ci] * g[p][co], exact fp32 FFMA, deterministic: the pixel
+//   range is cut into S slabs, a CTA owns (slab, tap, 64 ci, 64 co) with a 4x4 register tile per thread, partial sums go to
+//   a workspace and a second kernel adds the S partials in a fixed order (the bias gradient rides along).
+#include "common.cuh"
+
+namespace tdvc {
+
+__global__ void act_backward_kernel(const float* __restrict__ y, const float* __restrict__ g, float* __restrict__ out, int64_t n,
+                                    int act, float slope) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = y[i], gv = g[i];
+    float d = 1.f;
+    if (act == TDVC_ACT_RELU) d = v > 0.f ? 1.f : 0.f;
+    else if (act == TDVC_ACT_LRELU) d = v > 0.f ? 1.f : slope;
+    else if (act == TDVC_ACT_CLAMP01) d = (v > 0.f && v < 1.f) ? 1.f : 0.f;
+    out[i] = gv * d;
+  }
+}
+
+// out (N, H, W, C) <- g (N, Ho, Wo, C): out[n][oy*s][ox*s] = g[n][oy][ox], zero elsewhere.  One float4 per thread.
+__global__ void zero_insert_kernel(const float* __restrict__ g, int g_ld, float* __restrict__ out, int out_ld, int N, int H, int W,
+                                   int Ho, int Wo, int C4, int s) {
+  const int64_t total = (int64_t)N * H * W * C4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c4 = (int)(i % C4);
+    int64_t p = i / C4;
+    const int x = (int)(p % W);
+    p /= W;
+    const int y = (int)(p % H);
+    const int n = (int)(p / H);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y % s == 0 && x % s == 0 && y / s < Ho && x / s < Wo)
+      v = *reinterpret_cast<const float4*>(g + (((int64_t)n * Ho + y / s) * Wo + x / s) * g_ld + 4 * c4);
+    *reinterpret_cast<float4*>(out + (((int64_t)n * H + y) * W + x) * out_ld + 4 * c4) = v;
+  }
+}
+
+constexpr int WG_T = 64;      // ci x co tile of a CTA
+constexpr int WG_P = 32;      // output pixels per staged chunk
+constexpr int WG_LD = WG_T + 4;
+
+struct WgradArgs {
+  const float* x; int x_ld;
+  const float* g; int g_ld;
+  int N, H, W, Ho, Wo, cin, cout, k, stride, pad;
+  int S, ci_tiles, co_tiles;
+  float* part;        // [S][k*k][cin][cout]
+  float* part_bias;   // [S][cout] or nullptr
+};
+
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
+  __shared__ __align__(16) float xs[WG_P][WG_LD];
+  __shared__ __align__(16) float gs[WG_P][WG_LD];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  int r = blockIdx.y;
+  const int co_t = r % a.co_tiles; r /= a.co_tiles;
+  const int ci_t = r % a.ci_tiles; r /= a.ci_tiles;
+  const int tap = r;
+  const int ky = tap / a.k, kx = tap - ky * a.k;
+  const int s = blockIdx.x;
+  const int64_t npix = (int64_t)a.N * a.Ho * a.Wo;
+  const int64_t p_begin = npix * s / a.S, p_end = npix * (s + 1) / a.S;
+  const int ci0 = ci_t * WG_T, co0 = co_t * WG_T;
+  const bool do_bias = a.part_bias != nullptr && tap == 0 && ci_t == 0 && ty == 0;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t pc = p_begin; pc < p_end; pc += WG_P) {
+    // stage WG_P pixels x 64 channels of x (shifted by the tap, zero outside the image) and of g
+    for (int i = tid; i < WG_P * (WG_T / 4); i += 256) {
+      const int pl = i >> 4, c4 = (i & 15) * 4;
+      const int64_t p = pc + pl;
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+      if (p < p_end) {
+        const int ox = (int)(p % a.Wo);
+        const int64_t q = p / a.Wo;
+        const int oy = (int)(q % a.Ho), n = (int)(q / a.Ho);
+        const int iy = oy * a.stride + ky - a.pad, ix = ox * a.stride + kx - a.pad;
+        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+          const float* src = a.x + (((int64_t)n * a.H + iy) * a.W + ix) * a.x_ld;
+          const int c = ci0 + c4;
+          if (c + 3 < a.cin) xv = *reinterpret_cast<const float4*>(src + c);
+          else {
+            if (c < a.cin) xv.x = src[c];
+            if (c + 1 < a.cin) xv.y = src[c + 1];
+            if (c + 2 < a.cin) xv.z = src[c + 2];
+          }
+        }
+        const float* gsrc = a.g + p * a.g_ld;
+        const int c = co0 + c4;
+        if (c + 3 < a.cout) gv = *reinterpret_cast<const float4*>(gsrc + c);
+        else {
+          if (c < a.cout) gv.x = gsrc[c];
+          if (c + 1 < a.cout) gv.y = gsrc[c + 1];
+          if (c + 2 < a.cout) gv.z = gsrc[c + 2];
+        }
+      }
+      *reinterpret_cast<float4*>(&xs[pl][c4]) = xv;
+      *reinterpret_cast<float4*>(&gs[pl][c4]) = gv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int pl = 0; pl < WG_P; ++pl) {
+      const float4 xa = *reinterpret_cast<const float4*>(&xs[pl][ty * 4]);
+      const float4 gb = *reinterpret_cast<const float4*>(&gs[pl][tx * 4]);
+      const float xv[4] = {xa.x, xa.y, xa.z, xa.w}, gv[4] = {gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], gv[j], acc[i][j]);
+      if (do_bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bsum[j] += gv[j];
+      }
+    }
+    __syncthreads();
+  }
+  float* dst = a.part + ((int64_t)s * a.k * a.k + tap) * a.cin * a.cout;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci0 + ty * 4 + i;
+    if (ci >= a.cin) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co < a.cout) dst[(int64_t)ci * a.cout + co] = acc[i][j];
+    }
+  }
+  if (do_bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co < a.cout) a.part_bias[(int64_t)s * a.cout + co] = bsum[j];
+    }
+  }
+}
+
+// grad_w[co][ci][ky][kx] (the layout of nn.Conv2d.weight) = sum_s part[s][tap][ci][co], s ascending; grad_b likewise
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ part_bias, int S, int kk, int cin,
+                                    int cout, float* __restrict__ grad_w, float* __restrict__ grad_b) {
+  const int64_t nw = (int64_t)kk * cin * cout;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nw) {
+    const int co = (int)(i % cout);
+    const int64_t r = i / cout;
+    const int ci = (int)(r % cin), tap = (int)(r / cin);
+    float v = 0.f;
+    for (int s = 0; s < S; ++s) v += part[(int64_t)s * nw + i];
+    grad_w[((int64_t)co * cin + ci) * kk + tap] = v;
+  } else if (grad_b != nullptr && i < nw + cout) {
+    const int co = (int)(i - nw);
+    float v = 0.f;
+    for (int s = 0; s < S; ++s) v += part_bias[(int64_t)s * cout + co];
+    grad_b[co] = v;
+  }
+}
+
+static int wgrad_slabs(int64_t npix, int tiles) {
+  int S = (4 * kNumSMs + tiles - 1) / tiles;           // ~4 CTAs per SM in total
+  const int64_t max_s = (npix + 4 * WG_P - 1) / (4 * WG_P);   // at least 4 chunks per slab
+  if (S > max_s) S = (int)max_s;
+  return S < 1 ? 1 : S;
+}
+
+}  // namespace tdvc
+
+using namespace tdvc;
+
+extern "C" int tdvc_act_backward(const float* y, const float* grad_y, float* grad_pre, int64_t n, int act, float slope, void* stream) {
+  TDVC_REQUIRE(y && grad_y && grad_pre && n >= 0, "act_backward: bad args");
+  TDVC_REQUIRE(act >= TDVC_ACT_NONE && act <= TDVC_ACT_CLAMP01, "act_backward: activation %d", act);
+  if (n == 0) return TDVC_OK;
+  int grid = cdiv(n, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  act_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, grad_y, grad_pre, n, act, slope);
+  TDVC_CHECK_LAUNCH("act_backward");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_zero_insert(const float* g, int g_ld, float* out, int out_ld, int N, int H, int W, int Ho, int Wo, int C,
+                                int stride, void* stream) {
+  TDVC_REQUIRE(g && out && N > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && C > 0 && stride >= 1, "zero_insert: bad args");
+  TDVC_REQUIRE(C % 4 == 0 && g_ld % 4 == 0 && out_ld % 4 == 0 && g_ld >= C && out_ld >= C, "zero_insert: channels / ld must be multiples of 4");
+  TDVC_REQUIRE((Ho - 1) * stride < H && (Wo - 1) * stride < W, "zero_insert: the gradient does not fit the input grid");
+  int grid = cdiv((int64_t)N * H * W * (C / 4), 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  zero_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, g_ld, out, out_ld, N, H, W, Ho, Wo, C / 4, stride);
+  TDVC_CHECK_LAUNCH("zero_insert");
+  return TDVC_OK;
+}
+
+extern "C" size_t tdvc_conv2d_wgrad_workspace_bytes(int N, int Ho, int Wo, int cin, int cout, int k) {
+  if (N <= 0 || Ho <= 0 || Wo <= 0 || cin <= 0 || cout <= 0 || k <= 0) return 0;
+  const int tiles = k * k * cdiv(cin, WG_T) * cdiv(cout, WG_T);
+  const int S = wgrad_slabs((int64_t)N * Ho * Wo, tiles);
+  return (size_t)S * ((size_t)k * k * cin * cout + cout) * sizeof(float);
+}
+
+extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, int N, int H, int W, int cin, int cout,
+                                 int k, int stride, int pad, float* grad_w, float* grad_b_or_null, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  TDVC_REQUIRE(x && grad_y && grad_w && N > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "conv2d_wgrad: bad args");
+  TDVC_REQUIRE(k >= 1 && k <= 7 && stride >= 1 && pad >= 0, "conv2d_wgrad: k=%d stride=%d pad=%d", k, stride, pad);
+  TDVC_REQUIRE(x_ld >= cin && g_ld >= cout && x_ld % 4 == 0 && g_ld % 4 == 0, "conv2d_wgrad: leading dimensions");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  TDVC_REQUIRE(Ho > 0 && Wo > 0, "conv2d_wgrad: empty output");
+  const size_t need = tdvc_conv2d_wgrad_workspace_bytes(N, Ho, Wo, cin, cout, k);
+  TDVC_REQUIRE(workspace != nullptr && workspace_bytes >= need, "conv2d_wgrad: workspace of %zu bytes, %zu needed", workspace_bytes, need);
+  WgradArgs a;
+  a.x = x; a.x_ld = x_ld; a.g = grad_y; a.g_ld = g_ld;
+  a.N = N; a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo; a.cin = cin; a.cout = cout; a.k = k; a.stride = stride; a.pad = pad;
+  a.ci_tiles = cdiv(cin, WG_T);
+  a.co_tiles = cdiv(cout, WG_T);
+  const int tiles = k * k * a.ci_tiles * a.co_tiles;
+  a.S = wgrad_slabs((int64_t)N * Ho * Wo, tiles);
+  a.part = (float*)workspace;
+  a.part_bias = a.part + (size_t)a.S * k * k * cin * cout;
+  cudaStream_t st = (cudaStream_t)stream;
+  wgrad_kernel<<<dim3(a.S, tiles), 256, 0, st>>>(a);
+  TDVC_CHECK_LAUNCH("conv2d_wgrad");
+  const int64_t n_out = (int64_t)k * k * cin * cout + cout;
+  wgrad_reduce_kernel<<<cdiv(n_out, 256), 256, 0, st>>>(a.part, a.part_bias, a.S, k * k, cin, cout, grad_w, grad_b_or_null);
+  TDVC_CHECK_LAUNCH("conv2d_wgrad_reduce");
+  return TDVC_OK;
+}

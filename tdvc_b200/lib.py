@@ -91,6 +91,10 @@ SIGNATURES = {
     "tdvc_eb_aux_loss": [vp, vp, vp, vp, vp, i32, vp, vp],
     "tdvc_eb_aux_loss_grad": [vp, vp, vp, vp, vp, vp, i32, vp, vp],
     "tdvc_uniform_noise": [vp, i64, C.c_uint64, C.c_uint64, vp],
+    "tdvc_act_backward": [vp, vp, vp, i64, i32, f32, vp],
+    "tdvc_zero_insert": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "tdvc_conv2d_wgrad_workspace_bytes": [i32] * 6,
+    "tdvc_conv2d_wgrad": [vp, i32, vp, i32] + [i32] * 8 + [vp, vp, vp, sz, vp],
     "tdvc_pmf_to_quantized_cdf": [vp, i32, i32, vp],
     "tdvc_eb_symbols": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
     "tdvc_ar_code_workspace_bytes": [i32, i32, i32],
@@ -128,6 +132,7 @@ def load():
     lib.tdvc_conv2d_f16_bytes.restype = C.c_size_t
     lib.tdvc_dcn_f16_bytes.restype = C.c_size_t
     lib.tdvc_ar_code_workspace_bytes.restype = C.c_size_t
+    lib.tdvc_conv2d_wgrad_workspace_bytes.restype = C.c_size_t
     lib.tdvc_rans_encode_with_indexes.restype = C.c_int64
     _lib = lib
     return lib

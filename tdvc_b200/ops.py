@@ -3,7 +3,11 @@ main/utils/dcnv2/src/vision.cpp:4-9).  `dcn_v2_forward` / `dcn_v2_backward` take
 (src/dcn_v2.h:9-46, :48-92) and tensor conventions (contiguous NCHW fp32 CUDA; offset (N, 2*dg*kh*kw, H, W) ordered
 [g][tap][dy,dx]; mask (N, dg*kh*kw, H, W)), return freshly allocated tensors, raise RuntimeError on invalid input (the
 reference raises through AT_ASSERTM, src/cuda/dcn_v2_cuda.cu:38-62) and launch on the current stream.  `dcn_v2_conv` is the
-autograd function built on them (reference dcn_v2_amp.py:24-122, `_DCNv2.apply`).  No CPU path."""
+autograd function built on them (reference dcn_v2_amp.py:24-122, `_DCNv2.apply`).  `conv2d` is `F.conv2d` (+ an optional
+fused activation) with autograd through our own kernels: the convolution forward / dgrad on the tcgen05 kernels, wgrad and the
+bias gradient on `tdvc_conv2d_wgrad` - the first convolution slice of the training step.  No CPU path."""
+import weakref
+
 import torch
 
 from tdvc_b200 import lib as L
@@ -114,3 +118,138 @@ class _DCNv2(torch.autograd.Function):
 
 
 dcn_v2_conv = _DCNv2.apply
+
+
+# ----------------------------------------------------------------------------------------------- conv2d with autograd
+_ACTS = {None: L.ACT_NONE, "none": L.ACT_NONE, "relu": L.ACT_RELU, "leaky_relu": L.ACT_LRELU, "clamp01": L.ACT_CLAMP01}
+_PACKS = {}
+
+
+def _packed(weight, bias, stride, pad, transposed):
+    """ConvW (fp32 implicit-GEMM layout + tcgen05 fp16 blocks) of `weight`, or of its transposed, spatially flipped form
+    (the dgrad operator), cached on the parameter's identity and version."""
+    from tdvc_b200 import model as M, tc
+    key = (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version), stride, pad,
+           transposed)
+    ent = _PACKS.get(key)
+    # an address can be handed to another tensor once its owner is freed: the entry also remembers WHICH tensors it packed
+    cw = ent[0] if ent is not None and ent[1]() is weight and (bias is None or ent[2]() is bias) else None
+    if cw is None:
+        if len(_PACKS) >= 256:
+            _PACKS.clear()
+        w = weight.detach().float()
+        if transposed:
+            w = w.flip(2, 3).transpose(0, 1).contiguous()
+        cw = M.pack_conv(w, None if (bias is None or transposed) else bias.detach().float(), pad=pad, stride=stride)
+        tc.attach_f16({"w": cw})
+        _PACKS[key] = (cw, weakref.ref(weight), weakref.ref(bias) if bias is not None else None)
+    return cw
+
+
+def _launch_conv(x, cw, out, stride, act, slope, impl):
+    lib = L.load()
+    p = L.ConvParams()
+    p.src[0], p.src_c[0], p.src_ld[0], p.n_src = x.ptr, x.ld, x.ld, 1
+    p.N, p.H, p.W = x.N, x.H, x.W
+    p.Ho, p.Wo = out.H, out.W
+    p.weight = cw.w.data_ptr()
+    p.bias = cw.b.data_ptr() if cw.b is not None else None
+    p.cin, p.cin_pad, p.cout, p.cout_pad = cw.cin, cw.cin_pad, cw.cout, cw.cout_pad
+    p.kh = p.kw = cw.k
+    p.stride, p.pad = stride, cw.pad
+    p.act, p.slope = act, slope
+    p.out, p.out_ld = out.ptr, out.ld
+    p.impl = impl
+    p.weight_f16 = cw.w_f16.data_ptr() if cw.w_f16 is not None else None
+    p.w_shift = cw.w_shift
+    L.check(lib.tdvc_conv2d(p, torch.cuda.current_stream(out.t.device).cuda_stream), "conv2d")
+
+
+def _nhwc(t):
+    """NCHW tensor -> channels-last Act with the channel count padded to a multiple of 4 (zeros)."""
+    from tdvc_b200.model import Act
+    N, C, H, W = t.shape
+    a = Act.alloc(N, H, W, C, t.device, ld=(C + 3) // 4 * 4, zero=(C % 4 != 0))
+    L.check(L.load().tdvc_nchw_to_nhwc(t.data_ptr(), a.ptr, N, C, H, W, a.ld, torch.cuda.current_stream(t.device).cuda_stream),
+            "nchw_to_nhwc")
+    return a
+
+
+def _nchw(a):
+    out = torch.empty((a.N, a.C, a.H, a.W), device=a.t.device, dtype=torch.float32)
+    L.check(L.load().tdvc_nhwc_to_nchw(a.ptr, a.ld, out.data_ptr(), a.N, a.C, a.H, a.W,
+                                      torch.cuda.current_stream(a.t.device).cuda_stream), "nhwc_to_nchw")
+    return out
+
+
+class _Conv2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, act, slope, impl):
+        from tdvc_b200.model import Act
+        for name, t in (("input", x), ("weight", weight)) + ((("bias", bias),) if bias is not None else ()):
+            if not t.is_cuda or t.dtype != torch.float32:
+                raise RuntimeError(f"conv2d: {name} must be a float32 CUDA tensor (tdvc_b200 has no CPU path)")
+        if x.dim() != 4 or weight.dim() != 4 or weight.shape[1] != x.shape[1] or weight.shape[2] != weight.shape[3]:
+            raise RuntimeError(f"conv2d: input {tuple(x.shape)} / weight {tuple(weight.shape)} mismatch (square kernels, groups = 1)")
+        if act not in _ACTS:
+            raise RuntimeError(f"conv2d: unknown activation {act!r}")
+        N, C, H, W = x.shape
+        O, _, k, _ = weight.shape
+        if 2 * padding != k - 1 and not (k == 1 and padding == 0):
+            raise RuntimeError("conv2d: padding must be (k - 1) / 2 (every convolution of the reference is)")
+        Ho, Wo = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
+        with torch.cuda.device(x.device):
+            xa = _nhwc(x.detach().contiguous())
+            cw = _packed(weight, bias, stride, padding, False)
+            ya = Act.alloc(N, Ho, Wo, O, x.device, ld=(O + 3) // 4 * 4, zero=(O % 4 != 0))
+            _launch_conv(xa, cw, ya, stride, _ACTS[act], slope, impl)
+            y = _nchw(ya)
+        ctx.geom = (stride, padding, _ACTS[act], slope, impl, bias is not None)
+        ctx.xa, ctx.ya = xa, (ya if _ACTS[act] != L.ACT_NONE else None)
+        ctx.save_for_backward(weight)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        from tdvc_b200.model import Act
+        (weight,) = ctx.saved_tensors
+        stride, padding, act, slope, impl, has_bias = ctx.geom
+        xa = ctx.xa
+        lib = L.load()
+        O, C, k, _ = weight.shape
+        dev = gy.device
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            ga = _nhwc(gy.float().contiguous())
+            if act != L.ACT_NONE:   # g * f'(y), from the stored output
+                L.check(lib.tdvc_act_backward(ctx.ya.ptr, ga.ptr, ga.ptr, ga.N * ga.H * ga.W * ga.ld, act, slope, st), "act_backward")
+            gx = gw = gb = None
+            if ctx.needs_input_grad[0]:
+                cwt = _packed(weight, None, 1, k - 1 - padding, True)
+                if stride > 1:
+                    up = Act.alloc(xa.N, xa.H, xa.W, O, dev, ld=ga.ld)
+                    L.check(lib.tdvc_zero_insert(ga.ptr, ga.ld, up.ptr, up.ld, xa.N, xa.H, xa.W, ga.H, ga.W, ga.ld, stride, st),
+                            "zero_insert")
+                else:
+                    up = ga
+                gxa = Act.alloc(xa.N, xa.H, xa.W, C, dev, ld=(C + 3) // 4 * 4, zero=(C % 4 != 0))
+                _launch_conv(up, cwt, gxa, 1, L.ACT_NONE, 0.0, impl)
+                gx = _nchw(gxa)
+            if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+                gw = torch.empty_like(weight)
+                gb = torch.empty(O, device=dev, dtype=torch.float32) if has_bias else None
+                nb = lib.tdvc_conv2d_wgrad_workspace_bytes(xa.N, ga.H, ga.W, C, O, k)
+                ws = torch.empty((nb + 3) // 4, device=dev, dtype=torch.float32)
+                L.check(lib.tdvc_conv2d_wgrad(xa.ptr, xa.ld, ga.ptr, ga.ld, xa.N, xa.H, xa.W, C, O, k, stride, padding,
+                                              gw.data_ptr(), gb.data_ptr() if gb is not None else None, ws.data_ptr(), nb, st),
+                        "conv2d_wgrad")
+        return gx, gw, gb, None, None, None, None, None
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0, act=None, slope=0.01, impl=L.IMPL_AUTO):
+    """F.conv2d(input, weight, bias, stride, padding) followed by `act` (None | "relu" | "leaky_relu" | "clamp01"), NCHW float32
+    CUDA tensors, with autograd: grad_input by the forward kernels on the transposed, flipped weight (fp32-class tcgen05 path
+    included), grad_weight / grad_bias by the deterministic fp32 wgrad kernel.  impl: lib.IMPL_* (1 = exact fp32 SIMT forward
+    and dgrad)."""
+    return _Conv2d.apply(input, weight, bias, int(stride), int(padding), act, float(slope), int(impl))

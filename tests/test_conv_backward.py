@@ -1,0 +1,104 @@
+"""Convolution backward slice of the training step (the reference takes these gradients from cuDNN through
+autograd, tools/train.py:125-159): `tdvc_b200.ops.conv2d` against torch's own float64 convolution and its autograd on the same
+GPU.  grad_input runs on the forward kernels (tcgen05 hi/lo split) from the transposed, flipped weight; grad_weight / grad_bias
+on the deterministic fp32 `tdvc_conv2d_wgrad`."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # N, cin, cout, k, stride, H, W, act
+    (2, 64, 64, 3, 1, 40, 56, "relu"),          # Res_Block convolution (reference utils.py:43-56)
+    (1, 64, 128, 3, 2, 64, 96, "leaky_relu"),   # ResidualBlockWithStride.conv1
+    (1, 64, 128, 1, 2, 64, 96, None),           # ... .skip
+    (2, 3, 64, 3, 1, 48, 40, "leaky_relu"),     # image-input layer (3 channels, stored as 4)
+    (1, 8, 32, 7, 1, 32, 64, "relu"),           # SPyNet basic module
+    (1, 128, 256, 5, 1, 24, 40, None),          # context model size
+    (1, 426, 341, 1, 1, 16, 24, "leaky_relu"),  # entropy_parameters[2]: channel counts that are no multiple of 4
+    (1, 64, 3, 3, 1, 32, 32, "clamp01"),        # image head
+]
+
+
+def _ref(x, w, b, stride, pad, act, slope):
+    y = F.conv2d(x, w, b, stride, pad)
+    if act == "relu":
+        y = F.relu(y)
+    elif act == "leaky_relu":
+        y = F.leaky_relu(y, slope)
+    elif act == "clamp01":
+        y = y.clamp(0.0, 1.0)
+    return y
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[1]}to{c[2]}k{c[3]}s{c[4]}" for c in CASES])
+def test_conv2d_forward_backward_vs_torch_fp64(case):
+    from tdvc_b200 import ops
+    N, ci, co, k, s, H, W, act = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(k * 1000 + ci)
+    x = torch.randn(N, ci, H, W, generator=g).to(dev)
+    w = (torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5).to(dev)
+    b = (torch.randn(co, generator=g) * 0.1 + (0.5 if act == "clamp01" else 0.0)).to(dev)
+    gy = torch.randn(N, co, (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1, generator=g).to(dev)
+    slope = 0.1
+    xs, ws, bs = (t.clone().requires_grad_(True) for t in (x, w, b))
+    y = ops.conv2d(xs, ws, bs, s, k // 2, act, slope)
+    y.backward(gy)
+    xd, wd, bd = (t.double().clone().requires_grad_(True) for t in (x, w, b))
+    yd = _ref(xd, wd, bd, s, k // 2, act, slope)
+    # the activation mask of the reference must be the one our forward saw (outputs within rounding of a kink flip it)
+    yd.backward(gy.double())
+    assert y.shape == yd.shape
+    assert (y.double() - yd).abs().max().item() <= 2e-5 * max(1.0, yd.abs().max().item())
+    pre = F.conv2d(xd.detach(), wd.detach(), bd.detach(), s, k // 2)
+    kink = (pre.abs() < 1e-4) if act in ("relu", "leaky_relu") else torch.zeros_like(pre, dtype=torch.bool)
+    if act == "clamp01":
+        kink = (pre.abs() < 1e-4) | ((pre - 1).abs() < 1e-4)
+    assert kink.float().mean().item() < 0.01
+    tol = 1.0 if not kink.any() else 50.0   # a flipped mask element moves a few gradient entries by one term of the sum
+    for name, a, r, rel in (("grad_input", xs.grad, xd.grad, 3e-5), ("grad_weight", ws.grad, wd.grad, 1e-4),
+                            ("grad_bias", bs.grad, bd.grad, 1e-4)):
+        assert a is not None and a.shape == r.shape, name
+        err = (a.double() - r).abs().max().item()
+        assert err <= tol * rel * max(1.0, r.abs().max().item()), (name, err, r.abs().max().item())
+
+
+def test_conv2d_backward_is_deterministic_and_composes():
+    """Two backward passes give identical bits; a Res_Block (reference utils.py:43-56) built from ops.conv2d has the gradients of
+    the same block in torch."""
+    from tdvc_b200 import ops
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    x = torch.randn(2, 64, 48, 64, device=dev)
+    w1, w2 = (torch.randn(64, 64, 3, 3, device=dev) / 24.0 for _ in range(2))
+    b1, b2 = (torch.randn(64, device=dev) * 0.1 for _ in range(2))
+
+    def run(double):
+        ps = [t.double() if double else t.clone() for t in (x, w1, b1, w2, b2)]
+        ps = [t.requires_grad_(True) for t in ps]
+        xx, a1, c1, a2, c2 = ps
+        if double:
+            out = xx + F.conv2d(F.relu(F.conv2d(xx, a1, c1, 1, 1)), a2, c2, 1, 1)
+        else:
+            out = xx + ops.conv2d(ops.conv2d(xx, a1, c1, 1, 1, "relu"), a2, c2, 1, 1)
+        (out * out).sum().backward()
+        return [p.grad for p in ps]
+
+    ga, gb, gd = run(False), run(False), run(True)
+    for a, b_, d in zip(ga, gb, gd):
+        assert torch.equal(a, b_)
+        assert (a.double() - d).abs().max().item() <= 2e-4 * d.abs().max().item()
+
+
+def test_conv2d_rejects_bad_input():
+    from tdvc_b200 import ops
+    dev = torch.device("cuda:0")
+    x, w = torch.zeros(1, 8, 16, 16, device=dev), torch.zeros(8, 8, 3, 3, device=dev)
+    with pytest.raises(RuntimeError):
+        ops.conv2d(x.cpu(), w.cpu())
+    with pytest.raises(RuntimeError):
+        ops.conv2d(x, w, None, 1, 0)          # padding != (k - 1) / 2
+    with pytest.raises(RuntimeError):
+        ops.conv2d(x, torch.zeros(8, 4, 3, 3, device=dev), None, 1, 1)
