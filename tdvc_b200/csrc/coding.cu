@@ -13,6 +13,7 @@
 // Host side (as in compressai, whose entropy coder runs on the CPU): pmf -> 16-bit quantised CDF, and the 64-bit rANS
 // coder (ryg_rans rans64 + compressai's bypass escape) over the symbols / table indexes the device produced.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -25,19 +26,35 @@ constexpr int AR_THREADS = 512;
 constexpr int AR_WARPS = AR_THREADS / 32;
 constexpr int AR_PT = 8;        // positions per warp task (register tile)
 constexpr int AR_PCH = 40;      // positions per chunk of a wavefront (1920x1024: 64x120 latent, <= 40 per wavefront)
-constexpr int AR_KS_MAX = 4;    // K splits per (channel group, position group)
+constexpr int AR_KS_MAX = 16;   // K splits per (channel group, position group): a short wavefront still keeps every warp busy
 constexpr int AR_NS_MAX = 64;   // output channels of one CTA per stage
 constexpr int AR_C = 128;       // latent channels (Cheng2020Anchor N = M = 128 in both coders)
 constexpr int AR_KC = 128;      // K chunk staged in shared memory (one tap of the context model)
 constexpr int AR_NBUF = 3;      // staging depth
-constexpr size_t AR_SMEM = (size_t)(AR_NBUF * (AR_PCH * AR_KC + AR_KC * AR_NS_MAX) + AR_KS_MAX * AR_PCH * AR_NS_MAX) * sizeof(float);
+constexpr int AR_RED = AR_WARPS * AR_PT * 32;   // one (AR_PT positions x 32 channels) tile of partial sums per warp task
+constexpr size_t AR_SMEM = (size_t)(AR_NBUF * (AR_PCH * AR_KC + AR_KC * AR_NS_MAX) + AR_RED) * sizeof(float);
 
 struct ArDev {
   TdvcArParams a;
   float* ctx_s;   // [N][AR_PCH][2C]
   float* h1_s;    // [N][AR_PCH][c1_pad]
   float* h2_s;    // [N][AR_PCH][c2_pad]
+  unsigned long long* dbg;   // developer timing (TDVC_B200_AR_DEBUG): ns per phase, summed over the wavefronts by CTA 0
 };
+
+__device__ __forceinline__ unsigned long long ar_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define AR_MARK(i)                                                  \
+  do {                                                              \
+    if (d.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {  \
+      const unsigned long long now_ = ar_now();                     \
+      d.dbg[i] += now_ - t_last;                                    \
+      t_last = now_;                                                \
+    }                                                               \
+  } while (0)
 
 __device__ __forceinline__ void ar_slice(int total, int align, int rank, int R, int& n0, int& n1) {
   const int q = (total + align - 1) / align;
@@ -99,7 +116,8 @@ __device__ __forceinline__ void ar_issue_a(const ArW& w, int c, int P, float* sA
   }
 }
 
-// partial sums of out[p][n] = sum_k A(p, k) * Wt[k][col(n)], n in [n0, n0 + ns), p < P, left in red[ks][p][n - n0].
+// partial sums of out[p][n] = sum_k A(p, k) * Wt[k][col(n)], n in [n0, n0 + ns), p < P, left in red[task][p % AR_PT][n % 32]
+// with task = ((n / 32) * PG + p / AR_PT) * KS + ks (ar_sum adds the KS splits in order).
 // K is walked in chunks of AR_KC staged in shared memory through a 3-deep cp.async ring.  The weight parts of chunks 0 and 1
 // are already in flight when the stage starts (two committed groups, issued by the caller before the cluster barrier: they
 // do not depend on the previous stage).  A warp owns one (position group, channel group, K split): lanes = output channels,
@@ -173,18 +191,20 @@ __device__ __forceinline__ int ar_stage(const ArW& w, int P, float* sA, float* s
     }
   }
   cp_async_wait<0>();
-  if (busy && nl < ns) {
+  if (busy) {
 #pragma unroll
-    for (int j = 0; j < AR_PT; ++j)
-      if (p0 + j < P) red[(ks * AR_PCH + p0 + j) * AR_NS_MAX + nl] = acc[j];
+    for (int j = 0; j < AR_PT; ++j) red[(warp * AR_PT + j) * 32 + lane] = acc[j];
   }
   __syncthreads();        // every warp is done with the ring: the next layer's first weight chunks may be issued
   return KS;
 }
 
-__device__ __forceinline__ float ar_sum(const float* red, int KS, int p, int nl) {
-  float v = red[p * AR_NS_MAX + nl];
-  for (int ks = 1; ks < KS; ++ks) v += red[(ks * AR_PCH + p) * AR_NS_MAX + nl];
+// sum over the K splits of output (position p, local channel nl) of a stage that ran with P positions and KS splits
+__device__ __forceinline__ float ar_sum(const float* red, int KS, int P, int p, int nl) {
+  const int PG = (P + AR_PT - 1) / AR_PT;
+  const float* r = red + ((((nl >> 5) * PG + p / AR_PT) * KS) * AR_PT + (p % AR_PT)) * 32 + (nl & 31);
+  float v = r[0];
+  for (int ks = 1; ks < KS; ++ks) v += r[ks * AR_PT * 32];
   return v;
 }
 
@@ -208,7 +228,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_code_kernel(const ArDev d) {
   extern __shared__ __align__(16) float ar_smem[];
   float* sA = ar_smem;                                   // [AR_NBUF][AR_PCH][AR_KC]
   float* sW = sA + AR_NBUF * AR_PCH * AR_KC;             // [AR_NBUF][AR_KC][AR_NS_MAX]
-  float* red = sW + AR_NBUF * AR_KC * AR_NS_MAX;         // [AR_KS_MAX][AR_PCH][AR_NS_MAX]
+  float* red = sW + AR_NBUF * AR_KC * AR_NS_MAX;         // [AR_WARPS][AR_PT][32]
   __shared__ float s_table[64];
   for (int i = threadIdx.x; i < a.n_scales - 1; i += AR_THREADS) s_table[i] = a.scale_table[i];
   __syncthreads();
@@ -235,6 +255,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_code_kernel(const ArDev d) {
   const ArW wD{a.w3, C2, (a.c2 + 3) & ~3, n0, 2 * (n1 - n0), n1 - n0};  // c2 -> (scales | means)
 
   ar_prefetch_w(wA, sW);
+  unsigned long long t_last = d.dbg != nullptr ? ar_now() : 0ull;
   const int waves = W + 3 * (H - 1);
   for (int t = 0; t < waves; ++t) {
     int h_lo = t - (W - 1);
@@ -254,14 +275,17 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_code_kernel(const ArDev d) {
           return yhat + ((int64_t)hh * W + ww) * C + c;
         };
         const int KS = ar_stage(wA, P, sA, sW, red, asrc);
+        AR_MARK(0);
         ar_prefetch_w(wB, sW);
         for (int i = threadIdx.x; i < P * wA.ns; i += AR_THREADS) {
           const int p = i / wA.ns, nl = i - p * wA.ns;
-          ctx_s[p * C2 + wA.n0 + nl] = ar_sum(red, KS, p, nl) + __ldg(a.b_ctx + wA.n0 + nl);
+          ctx_s[p * C2 + wA.n0 + nl] = ar_sum(red, KS, P, p, nl) + __ldg(a.b_ctx + wA.n0 + nl);
         }
       }
+      AR_MARK(1);
       __threadfence();
       cluster.sync();
+      AR_MARK(2);
       // ---- entropy_parameters[0]: (params | ctx) -> c1, LeakyReLU(0.01)
       {
         auto asrc = [&](int p, int k) -> const float* {
@@ -272,39 +296,46 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_code_kernel(const ArDev d) {
           return ctx_s + p * C2 + (k - C2);
         };
         const int KS = ar_stage(wB, P, sA, sW, red, asrc);
+        AR_MARK(3);
         ar_prefetch_w(wC, sW);
         for (int i = threadIdx.x; i < P * wB.ns; i += AR_THREADS) {
           const int p = i / wB.ns, nl = i - p * wB.ns;
-          const float v = ar_sum(red, KS, p, nl) + __ldg(a.b1 + wB.n0 + nl);
+          const float v = ar_sum(red, KS, P, p, nl) + __ldg(a.b1 + wB.n0 + nl);
           h1_s[p * a.c1_pad + wB.n0 + nl] = v > 0.f ? v : v * 0.01f;
         }
       }
+      AR_MARK(4);
       __threadfence();
       cluster.sync();
+      AR_MARK(5);
       // ---- entropy_parameters[2]: c1 -> c2, LeakyReLU(0.01)
       {
         auto asrc = [&](int p, int k) -> const float* { return h1_s + p * a.c1_pad + k; };
         const int KS = ar_stage(wC, P, sA, sW, red, asrc);
+        AR_MARK(6);
         ar_prefetch_w(wD, sW);
         for (int i = threadIdx.x; i < P * wC.ns; i += AR_THREADS) {
           const int p = i / wC.ns, nl = i - p * wC.ns;
-          const float v = ar_sum(red, KS, p, nl) + __ldg(a.b2 + wC.n0 + nl);
+          const float v = ar_sum(red, KS, P, p, nl) + __ldg(a.b2 + wC.n0 + nl);
           h2_s[p * a.c2_pad + wC.n0 + nl] = v > 0.f ? v : v * 0.01f;
         }
       }
+      AR_MARK(7);
       __threadfence();
       cluster.sync();
+      AR_MARK(8);
       // ---- entropy_parameters[4]: c2 -> (scales | means); quantise relative to the mean, table index of the scale
       {
         auto asrc = [&](int p, int k) -> const float* { return h2_s + p * a.c2_pad + k; };
         const int KS = ar_stage(wD, P, sA, sW, red, asrc);
+        AR_MARK(9);
         ar_prefetch_w(wA, sW);
         const int nch = wD.split, ch0 = wD.n0;
         for (int i = threadIdx.x; i < P * nch; i += AR_THREADS) {
           const int p = i / nch, j = i - p * nch;
           const int ch = ch0 + j;
-          float scale = ar_sum(red, KS, p, j) + __ldg(a.b3 + ch);
-          const float mean = ar_sum(red, KS, p, nch + j) + __ldg(a.b3 + C + ch);
+          float scale = ar_sum(red, KS, P, p, j) + __ldg(a.b3 + ch);
+          const float mean = ar_sum(red, KS, P, p, nch + j) + __ldg(a.b3 + C + ch);
           const int hh = hc + p, ww = t - 3 * hh;
           const int64_t pix = (int64_t)hh * W + ww;
           const float q = rintf(__fsub_rn(__ldg(y + pix * a.y_ld + ch), mean));
@@ -316,8 +347,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_code_kernel(const ArDev d) {
           idx[pix * C + ch] = ix;
         }
       }
+      AR_MARK(10);
       __threadfence();
       cluster.sync();
+      AR_MARK(11);
     }
   }
   cp_async_wait<0>();
@@ -370,6 +403,14 @@ extern "C" int tdvc_ar_code(const TdvcArParams* p, void* workspace, size_t works
   d.ctx_s = (float*)workspace;
   d.h1_s = d.ctx_s + (size_t)p->N * AR_PCH * 2 * AR_C;
   d.h2_s = d.h1_s + (size_t)p->N * AR_PCH * p->c1_pad;
+  d.dbg = nullptr;
+  static unsigned long long* dbg_buf = nullptr;
+  const bool debug = getenv("TDVC_B200_AR_DEBUG") != nullptr;
+  if (debug) {
+    if (dbg_buf == nullptr) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), st);
+    d.dbg = dbg_buf;
+  }
   static int smem_done[kMaxDevices] = {};
   {
     const int rc = ensure_dynamic_smem(ar_code_kernel, AR_SMEM, smem_done, "ar_code");
@@ -393,7 +434,17 @@ extern "C" int tdvc_ar_code(const TdvcArParams* p, void* workspace, size_t works
       cfg.numAttrs = 1;
       e = cudaLaunchKernelEx(&cfg, ar_code_kernel, d);
     }
-    if (e == cudaSuccess) return TDVC_OK;
+    if (e == cudaSuccess) {
+      if (debug) {
+        unsigned long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        static const char* nm[12] = {"A chunks", "A sums", "A fence+barrier", "B chunks", "B sums", "B fence+barrier",
+                                     "C chunks", "C sums", "C fence+barrier", "D chunks", "D sums", "D fence+barrier"};
+        for (int i = 0; i < 12; ++i) fprintf(stderr, "ar_code[R=%d] %-16s %8.3f ms\n", R, nm[i], h[i] * 1e-6);
+      }
+      return TDVC_OK;
+    }
     (void)cudaGetLastError();
     if (auto_r && R == 16) { R = 8; continue; }
     set_error("ar_code: launch with clusters of %d CTAs failed: %s", R, cudaGetErrorString(e));
