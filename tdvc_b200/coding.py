@@ -241,3 +241,57 @@ def finish_coding(h, keep=False):
 
 def code_latents(plan, W, cn, tables, cluster=0, keep=False):
     return finish_coding(launch_coding(plan, W, cn, tables, cluster=cluster), keep=keep)
+
+
+# ----------------------------------------------------------------------------------------------- bitstream container
+_MAGIC = b"TDVC"
+
+
+def pack_frame(coded):
+    """`net.last_coded` of one P-frame -> bytes.  The reference only sketches a container (dead code, reference
+    tools/utils/encoder.py:61-68: per string a big-endian shape header, a length and the payload); this one follows the
+    sketch with 32-bit lengths (a 1920x1024 motion string is ~1 MB, beyond the sketch's uint16):
+    magic "TDVC" | >B n_coders | per coder: >4s name | >2I hyper-latent shape (h, w) | >B n_lists | per list: >I n_strings |
+    per string: >I length | payload."""
+    import struct
+    out = [_MAGIC, struct.pack(">B", len(coded))]
+    for name, enc in coded.items():
+        out.append(struct.pack(">4s2IB", name.encode()[:4].ljust(4), int(enc["shape"][0]), int(enc["shape"][1]),
+                               len(enc["strings"])))
+        for lst in enc["strings"]:
+            out.append(struct.pack(">I", len(lst)))
+            for s_ in lst:
+                out.append(struct.pack(">I", len(s_)))
+                out.append(bytes(s_))
+    return b"".join(out)
+
+
+def unpack_frame(data):
+    """Inverse of pack_frame -> {name: {"strings": [[bytes, ...], ...], "shape": (h, w)}}."""
+    import struct
+    if data[:4] != _MAGIC:
+        raise RuntimeError("unpack_frame: not a tdvc_b200 frame container")
+    pos = 4
+    (n,) = struct.unpack_from(">B", data, pos)
+    pos += 1
+    out = {}
+    for _ in range(n):
+        name, h, w, nl = struct.unpack_from(">4s2IB", data, pos)
+        pos += struct.calcsize(">4s2IB")
+        lists = []
+        for _ in range(nl):
+            (ns,) = struct.unpack_from(">I", data, pos)
+            pos += 4
+            strs = []
+            for _ in range(ns):
+                (ln,) = struct.unpack_from(">I", data, pos)
+                pos += 4
+                if pos + ln > len(data):
+                    raise RuntimeError("unpack_frame: truncated container")
+                strs.append(bytes(data[pos:pos + ln]))
+                pos += ln
+            lists.append(strs)
+        out[name.decode().strip()] = {"strings": lists, "shape": (h, w)}
+    if pos != len(data):
+        raise RuntimeError("unpack_frame: trailing bytes")
+    return out

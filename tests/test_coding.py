@@ -135,6 +135,29 @@ def test_tables_are_bit_identical_to_oracle(oracle_model):
         assert ours.cdf.shape == (64, 3133)
 
 
+def test_frame_container_round_trip(oracle_model):
+    """pack_frame / unpack_frame on the oracle's own strings, and the oracle decodes what comes back out."""
+    from tdvc_b200 import coding, synth
+    x, refs = synth.make_frame_pair(64, 64, seed=6)
+    with torch.no_grad():
+        oracle_model(x, refs, False, is_compress=True)
+    coded = oracle_model.last_coded
+    blob = coding.pack_frame(coded)
+    back = coding.unpack_frame(blob)
+    assert set(back) == {"mv", "res"}
+    for k in coded:
+        assert back[k]["strings"] == coded[k]["strings"] and back[k]["shape"] == coded[k]["shape"]
+    payload = sum(len(s) for v in coded.values() for lst in v["strings"] for s in lst)
+    assert len(blob) == payload + 5 + 2 * (13 + 2 * 4 + 2 * 4)
+    with torch.no_grad():
+        dec = oracle_model.mvCoder.decompress(back["mv"]["strings"], back["mv"]["shape"])
+    assert dec["x_hat"].shape == (1, 64, 64, 64)
+    with pytest.raises(RuntimeError):
+        coding.unpack_frame(blob[:-3])
+    with pytest.raises(RuntimeError):
+        coding.unpack_frame(b"XXXX" + blob[4:])
+
+
 # ------------------------------------------------------------------------------------------------------ GPU
 def _build(oracle_model, dev):
     from tdvc_b200.model import VideoCompressor
