@@ -252,8 +252,15 @@ int tdvc_zero_insert(const float* g, int g_ld, float* out, int out_ld, int N, in
                      void* stream);
 size_t tdvc_conv2d_wgrad_workspace_bytes(int N, int Ho, int Wo, int cin, int cout, int k);
 int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, int N, int H, int W, int cin, int cout, int k,
-                      int stride, int pad, float* grad_w, float* grad_b_or_null, void* workspace, size_t workspace_bytes,
-                      void* stream);
+                      int stride, int pad, int in_square, float* grad_w, float* grad_b_or_null, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* GDN / IGDN backward (compressai GDN: out = x * norm^(-1/2), inverse: x * norm^(1/2), norm = beta + gamma . x^2), element-wise
+ * parts on flat fp32 arrays (n % 4 == 0): pre -> dx_direct = g * norm^(-+1/2), dnorm = d loss / d norm; the 1x1 convolution's
+ * dgrad (tdvc_conv2d on gamma^T) turns dnorm into d(x^2) and tdvc_conv2d_wgrad(in_square = 1) into d gamma / d beta;
+ * post -> dx = dx_direct + 2 x d(x^2).  (`in_square` of conv2d_wgrad: x is squared on load.)                             */
+int tdvc_gdn_backward_pre(const float* x, const float* norm, const float* grad_out, float* dx_direct, float* dnorm, int64_t n,
+                          int inverse, void* stream);
+int tdvc_gdn_backward_post(const float* dx_direct, const float* x, const float* dxsq, float* dx, int64_t n, void* stream);
 
 /* ---- real entropy coding (`is_compress=True`: reference pnet.py:45-49,69-73 -> compressai `update(force=True)` and
  * `compress()`; compressai is not in the reference tree, SURVEY App. A / DESIGN.md section 7) ----

@@ -45,6 +45,43 @@ __global__ void zero_insert_kernel(const float* __restrict__ g, int g_ld, float*
   }
 }
 
+// GDN / IGDN backward, element-wise parts (compressai GDN: out = x * norm^(-1/2), inverse: x * norm^(+1/2), norm = beta +
+// gamma . x^2).  pre: the direct term d_x = g * norm^(-+1/2) and d_norm = -+1/2 * g * x * norm^(-3/2 | -1/2); the caller then
+// sends d_norm through the 1x1 convolution's dgrad (-> d(x^2)) and wgrad (in_square -> d gamma, d beta); post: d_x += 2 x d(x^2).
+__global__ void gdn_bwd_pre_kernel(const float* __restrict__ x, const float* __restrict__ norm, const float* __restrict__ g,
+                                   float* __restrict__ dx_direct, float* __restrict__ dnorm, int64_t n4, int inverse) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i), nv = __ldg(reinterpret_cast<const float4*>(norm) + i),
+                 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ns[4] = {nv.x, nv.y, nv.z, nv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+    float a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float r = rsqrtf(ns[j]);                      // norm^(-1/2)
+      if (inverse) {
+        a[j] = gs[j] * (ns[j] * r);                       // g * sqrt(norm)
+        b[j] = 0.5f * gs[j] * xs[j] * r;                  // +1/2 g x norm^(-1/2)
+      } else {
+        a[j] = gs[j] * r;
+        b[j] = -0.5f * gs[j] * xs[j] * (r * r * r);       // -1/2 g x norm^(-3/2)
+      }
+    }
+    reinterpret_cast<float4*>(dx_direct)[i] = make_float4(a[0], a[1], a[2], a[3]);
+    reinterpret_cast<float4*>(dnorm)[i] = make_float4(b[0], b[1], b[2], b[3]);
+  }
+}
+__global__ void gdn_bwd_post_kernel(const float* __restrict__ dx_direct, const float* __restrict__ x, const float* __restrict__ dxsq,
+                                    float* __restrict__ dx, int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(dx_direct) + i), xv = __ldg(reinterpret_cast<const float4*>(x) + i),
+                 q = __ldg(reinterpret_cast<const float4*>(dxsq) + i);
+    reinterpret_cast<float4*>(dx)[i] = make_float4(fmaf(2.f * xv.x, q.x, a.x), fmaf(2.f * xv.y, q.y, a.y),
+                                                   fmaf(2.f * xv.z, q.z, a.z), fmaf(2.f * xv.w, q.w, a.w));
+  }
+}
+
 constexpr int WG_T = 64;      // ci x co tile of a CTA
 constexpr int WG_P = 32;      // output pixels per staged chunk
 constexpr int WG_LD = WG_T + 4;
@@ -54,6 +91,7 @@ struct WgradArgs {
   const float* g; int g_ld;
   int N, H, W, Ho, Wo, cin, cout, k, stride, pad;
   int S, ci_tiles, co_tiles;
+  int in_square;      // x is squared on load: the weight gradient of a GDN's 1x1 convolution of x^2
   float* part;        // [S][k*k][cin][cout]
   float* part_bias;   // [S][cout] or nullptr
 };
@@ -108,6 +146,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
           if (c + 2 < a.cout) gv.z = gsrc[c + 2];
         }
       }
+      if (a.in_square) { xv.x *= xv.x; xv.y *= xv.y; xv.z *= xv.z; xv.w *= xv.w; }
       *reinterpret_cast<float4*>(&xs[pl][c4]) = xv;
       *reinterpret_cast<float4*>(&gs[pl][c4]) = gv;
     }
@@ -210,7 +249,7 @@ extern "C" size_t tdvc_conv2d_wgrad_workspace_bytes(int N, int Ho, int Wo, int c
 }
 
 extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, int N, int H, int W, int cin, int cout,
-                                 int k, int stride, int pad, float* grad_w, float* grad_b_or_null, void* workspace,
+                                 int k, int stride, int pad, int in_square, float* grad_w, float* grad_b_or_null, void* workspace,
                                  size_t workspace_bytes, void* stream) {
   TDVC_REQUIRE(x && grad_y && grad_w && N > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "conv2d_wgrad: bad args");
   TDVC_REQUIRE(k >= 1 && k <= 7 && stride >= 1 && pad >= 0, "conv2d_wgrad: k=%d stride=%d pad=%d", k, stride, pad);
@@ -222,6 +261,7 @@ extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, 
   WgradArgs a;
   a.x = x; a.x_ld = x_ld; a.g = grad_y; a.g_ld = g_ld;
   a.N = N; a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo; a.cin = cin; a.cout = cout; a.k = k; a.stride = stride; a.pad = pad;
+  a.in_square = in_square ? 1 : 0;
   a.ci_tiles = cdiv(cin, WG_T);
   a.co_tiles = cdiv(cout, WG_T);
   const int tiles = k * k * a.ci_tiles * a.co_tiles;
@@ -234,5 +274,24 @@ extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, 
   const int64_t n_out = (int64_t)k * k * cin * cout + cout;
   wgrad_reduce_kernel<<<cdiv(n_out, 256), 256, 0, st>>>(a.part, a.part_bias, a.S, k * k, cin, cout, grad_w, grad_b_or_null);
   TDVC_CHECK_LAUNCH("conv2d_wgrad_reduce");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_gdn_backward_pre(const float* x, const float* norm, const float* grad_out, float* dx_direct, float* dnorm,
+                                     int64_t n, int inverse, void* stream) {
+  TDVC_REQUIRE(x && norm && grad_out && dx_direct && dnorm && n > 0 && n % 4 == 0, "gdn_backward_pre: bad args");
+  int grid = cdiv(n / 4, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  gdn_bwd_pre_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, norm, grad_out, dx_direct, dnorm, n / 4, inverse);
+  TDVC_CHECK_LAUNCH("gdn_backward_pre");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_gdn_backward_post(const float* dx_direct, const float* x, const float* dxsq, float* dx, int64_t n, void* stream) {
+  TDVC_REQUIRE(dx_direct && x && dxsq && dx && n > 0 && n % 4 == 0, "gdn_backward_post: bad args");
+  int grid = cdiv(n / 4, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  gdn_bwd_post_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dx_direct, x, dxsq, dx, n / 4);
+  TDVC_CHECK_LAUNCH("gdn_backward_post");
   return TDVC_OK;
 }

@@ -241,7 +241,7 @@ class _Conv2d(torch.autograd.Function):
                 gb = torch.empty(O, device=dev, dtype=torch.float32) if has_bias else None
                 nb = lib.tdvc_conv2d_wgrad_workspace_bytes(xa.N, ga.H, ga.W, C, O, k)
                 ws = torch.empty((nb + 3) // 4, device=dev, dtype=torch.float32)
-                L.check(lib.tdvc_conv2d_wgrad(xa.ptr, xa.ld, ga.ptr, ga.ld, xa.N, xa.H, xa.W, C, O, k, stride, padding,
+                L.check(lib.tdvc_conv2d_wgrad(xa.ptr, xa.ld, ga.ptr, ga.ld, xa.N, xa.H, xa.W, C, O, k, stride, padding, 0,
                                               gw.data_ptr(), gb.data_ptr() if gb is not None else None, ws.data_ptr(), nb, st),
                         "conv2d_wgrad")
         return gx, gw, gb, None, None, None, None, None
@@ -253,3 +253,87 @@ def conv2d(input, weight, bias=None, stride=1, padding=0, act=None, slope=0.01, 
     included), grad_weight / grad_bias by the deterministic fp32 wgrad kernel.  impl: lib.IMPL_* (1 = exact fp32 SIMT forward
     and dgrad)."""
     return _Conv2d.apply(input, weight, bias, int(stride), int(padding), act, float(slope), int(impl))
+
+
+# ----------------------------------------------------------------------------------------------- GDN / IGDN with autograd
+def _launch_gdn(x, cw, out, inverse, norm_only, impl, absmax):
+    """out = x * (beta + gamma . x^2)^(-+1/2) on the fused tensor-core kernel (1x1 convolution of x^2 with the GDN epilogue),
+    or just the norm (norm_only: the backward pass recomputes it instead of keeping a second activation)."""
+    lib = L.load()
+    p = L.ConvParams()
+    p.src[0], p.src_c[0], p.src_ld[0], p.n_src = x.ptr, x.ld, x.ld, 1
+    p.N, p.H, p.W, p.Ho, p.Wo = x.N, x.H, x.W, x.H, x.W
+    p.weight, p.bias = cw.w.data_ptr(), cw.b.data_ptr()
+    p.cin, p.cin_pad, p.cout, p.cout_pad = cw.cin, cw.cin_pad, cw.cout, cw.cout_pad
+    p.kh = p.kw = 1
+    p.stride, p.pad = 1, 0
+    p.in_square = 1
+    if not norm_only:
+        p.post = L.POST_IGDN if inverse else L.POST_GDN
+        p.mul, p.mul_ld = x.ptr, x.ld
+    p.out, p.out_ld = out.ptr, out.ld
+    p.impl = impl
+    p.weight_f16 = cw.w_f16.data_ptr() if cw.w_f16 is not None else None
+    p.w_shift = cw.w_shift
+    p.in_absmax = absmax.data_ptr()   # max |x|: x * x is pre-scaled by a power of two so that the fp16 operands cannot saturate
+    L.check(lib.tdvc_conv2d(p, torch.cuda.current_stream(out.t.device).cuda_stream), "conv2d (gdn)")
+
+
+class _GDN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, beta, gamma, inverse, impl):
+        from tdvc_b200.model import Act
+        for name, t in (("input", x), ("beta", beta), ("gamma", gamma)):
+            if not t.is_cuda or t.dtype != torch.float32:
+                raise RuntimeError(f"gdn: {name} must be a float32 CUDA tensor (tdvc_b200 has no CPU path)")
+        N, C, H, W = x.shape
+        if tuple(gamma.shape) != (C, C) or tuple(beta.shape) != (C,) or C % 4:
+            raise RuntimeError(f"gdn: expected beta ({C},) and gamma ({C},{C}), channels a multiple of 4")
+        with torch.cuda.device(x.device):
+            xa = _nhwc(x.detach().contiguous())
+            w4 = gamma.detach().reshape(C, C, 1, 1)
+            cw = _packed(w4, beta.detach(), 1, 0, False)
+            ya = Act.alloc(N, H, W, C, x.device)
+            am = x.detach().abs().amax().reshape(1).float()   # (the inference path gets it from the producing layer's epilogue)
+            _launch_gdn(xa, cw, ya, inverse, False, impl, am)
+            y = _nchw(ya)
+        ctx.xa, ctx.cw, ctx.w4, ctx.inverse, ctx.impl, ctx.am = xa, cw, w4, inverse, impl, am
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        from tdvc_b200.model import Act
+        xa, cw, inverse, impl = ctx.xa, ctx.cw, ctx.inverse, ctx.impl
+        lib = L.load()
+        N, H, W, C = xa.N, xa.H, xa.W, xa.C
+        dev = gy.device
+        n = N * H * W * C
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            ga = _nhwc(gy.float().contiguous())
+            norm = Act.alloc(N, H, W, C, dev)
+            _launch_gdn(xa, cw, norm, inverse, True, impl, ctx.am)
+            dxd, dn = Act.alloc(N, H, W, C, dev), Act.alloc(N, H, W, C, dev)
+            L.check(lib.tdvc_gdn_backward_pre(xa.ptr, norm.ptr, ga.ptr, dxd.ptr, dn.ptr, n, 1 if inverse else 0, st), "gdn_backward_pre")
+            cwt = _packed(ctx.w4, None, 1, 0, True)          # gamma^T: d(x^2) = dgrad of the 1x1 convolution
+            dxsq = Act.alloc(N, H, W, C, dev)
+            _launch_conv(dn, cwt, dxsq, 1, L.ACT_NONE, 0.0, impl)
+            L.check(lib.tdvc_gdn_backward_post(dxd.ptr, xa.ptr, dxsq.ptr, dxd.ptr, n, st), "gdn_backward_post")
+            gx = _nchw(dxd)
+            gw = torch.empty((C, C, 1, 1), device=dev, dtype=torch.float32)
+            gb = torch.empty(C, device=dev, dtype=torch.float32)
+            nb = lib.tdvc_conv2d_wgrad_workspace_bytes(N, H, W, C, C, 1)
+            ws = torch.empty((nb + 3) // 4, device=dev, dtype=torch.float32)
+            L.check(lib.tdvc_conv2d_wgrad(xa.ptr, xa.ld, dn.ptr, dn.ld, N, H, W, C, C, 1, 1, 0, 1, gw.data_ptr(), gb.data_ptr(),
+                                          ws.data_ptr(), nb, st), "conv2d_wgrad (gdn)")
+        return gx, gb, gw.view(C, C), None, None
+
+
+def gdn(input, beta, gamma, inverse=False, impl=L.IMPL_AUTO):
+    """compressai GDN / IGDN on NCHW float32 CUDA tensors: input * (beta + gamma . input^2)^(-1/2) (inverse: ^(+1/2)), with
+    autograd.  beta (C,) and gamma (C, C) are the EFFECTIVE (reparametrised, non-negative) values - compressai's
+    `beta_reparam(self.beta)`, `gamma_reparam(self.gamma)`, which stay ordinary torch parameter arithmetic on the caller's side.
+    Forward: the fused tcgen05 kernel of the inference path; backward: two element-wise kernels around the 1x1 convolution's
+    dgrad / wgrad."""
+    return _GDN.apply(input, beta, gamma, bool(inverse), int(impl))

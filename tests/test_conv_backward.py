@@ -102,3 +102,36 @@ def test_conv2d_rejects_bad_input():
         ops.conv2d(x, w, None, 1, 0)          # padding != (k - 1) / 2
     with pytest.raises(RuntimeError):
         ops.conv2d(x, torch.zeros(8, 4, 3, 3, device=dev), None, 1, 1)
+
+
+@pytest.mark.parametrize("inverse", [False, True], ids=["gdn", "igdn"])
+def test_gdn_forward_backward_vs_torch_fp64(inverse):
+    """compressai GDN / IGDN: out = x * (beta + gamma . x^2)^(-+1/2); forward on the fused tcgen05 kernel,
+    backward through the two element-wise kernels + the 1x1 convolution's dgrad / wgrad, against float64 autograd."""
+    from tdvc_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11 + inverse)
+    C = 128
+    x = (torch.randn(2, C, 24, 40, generator=g) * 3.0).to(dev)
+    gamma = (0.1 * torch.eye(C) + 0.01 * torch.rand(C, C, generator=g)).to(dev)
+    beta = (1.0 + 0.2 * torch.rand(C, generator=g)).to(dev)
+    gy = torch.randn(2, C, 24, 40, generator=g).to(dev)
+    xs, bs, gs = (t.clone().requires_grad_(True) for t in (x, beta, gamma))
+    y = ops.gdn(xs, bs, gs, inverse)
+    y.backward(gy)
+    xd, bd, gd = (t.double().clone().requires_grad_(True) for t in (x, beta, gamma))
+    norm = F.conv2d(xd * xd, gd.reshape(C, C, 1, 1), bd)
+    yd = xd * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))
+    yd.backward(gy.double())
+    assert (y.double() - yd).abs().max().item() <= 2e-5 * yd.abs().max().item()
+    for name, a, r, rel in (("grad_input", xs.grad, xd.grad, 5e-5), ("grad_beta", bs.grad, bd.grad, 2e-4),
+                            ("grad_gamma", gs.grad, gd.grad, 2e-4)):
+        assert a is not None and a.shape == r.shape, name
+        err = (a.double() - r).abs().max().item()
+        assert err <= rel * r.abs().max().item(), (name, err, r.abs().max().item())
+    # large activations: the squared operand is range-scaled instead of saturating fp16 (|x| > 255)
+    xb = (x * 200.0).requires_grad_(True)
+    yb = ops.gdn(xb, beta, gamma, inverse)
+    nb = F.conv2d((x * 200.0).double() ** 2, gamma.double().reshape(C, C, 1, 1), beta.double())
+    rb = (x * 200.0).double() * (torch.sqrt(nb) if inverse else torch.rsqrt(nb))
+    assert (yb.double() - rb).abs().max().item() <= 5e-5 * rb.abs().max().item()
