@@ -238,6 +238,17 @@ int tdvc_eb_aux_loss(const float* mats, const float* biases, const float* factor
 int tdvc_eb_aux_loss_grad(const float* mats, const float* biases, const float* factors, const float* quantiles,
                           const float* target3, const float* grad_out, int C, float* grad_quantiles, void* stream);
 int tdvc_uniform_noise(float* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream);
+/* Backward of the two noise-mode reductions (the reference takes them from autograd through compressai, tools/train.py:132-145).
+ * S = sum ln max(p, 1e-9); grad_sum = d loss / d S (device scalar); compressai's LowerBound gradient rule (pass where the input
+ * is above the bound or the gradient is negative) for the likelihood bound and the 0.11 scale bound.
+ * gc_bits_backward: grad_y (ld = C), grad_params (ld = params_ld: d / d scale at channel c, d / d mean at C + c).
+ * eb_bits_backward: grad_z (ld = C) and the gradients with respect to the TRANSFORMED parameters the kernels read (mats =
+ *   softplus(matrix) [C][33], biases [C][13], factors = tanh(factor) [C][12]); deterministic (one CTA per channel).          */
+int tdvc_gc_bits_backward(const float* y, const float* noise, const float* params, int params_ld, const float* grad_sum,
+                          float* grad_y, float* grad_params, int64_t npix, int C, void* stream);
+int tdvc_eb_bits_backward(const float* z_tilde, const float* mats, const float* biases, const float* factors, const float* grad_sum,
+                          float* grad_z, float* grad_mats, float* grad_biases, float* grad_factors, int64_t npix, int C,
+                          void* stream);
 
 /* ---- backward pieces of the convolutions (the reference's training step takes them from cuDNN through
  * autograd, tools/train.py:125-159).  dgrad is tdvc_conv2d itself on the transposed, flipped weight (pad' = k - 1 - pad),

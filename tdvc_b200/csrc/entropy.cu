@@ -226,6 +226,161 @@ __global__ void eb_symbols_kernel(const float* __restrict__ z, int ld, const flo
   }
 }
 
+// ---- backward of the two likelihood-to-bits reductions in training (noise) mode (the reference takes these
+// gradients from autograd through compressai's entropy models, tools/train.py:132-145).  S = sum ln max(p, 1e-9); `gS` is
+// d loss / d S (device scalar).  compressai's LowerBound passes a gradient where the input is above the bound OR the gradient
+// is negative (both the 1e-9 likelihood bound and the 0.11 scale bound).
+//
+// gc_bits_backward: p = Phi((0.5 - v) / s) - Phi((-0.5 - v) / s), v = |y + noise - mean|, s = max(scale, 0.11):
+//   g_y (ld = C), g_params (ld = params_ld: d/d scale at channel c, d/d mean at C + c).  Element-wise.
+__global__ void gc_bits_backward_kernel(const float* __restrict__ y, const float* __restrict__ noise, const float* __restrict__ params,
+                                        int params_ld, const float* __restrict__ gS, float* __restrict__ g_y,
+                                        float* __restrict__ g_params, int64_t total, int C) {
+  const float g = __ldg(gS);
+  const float kc = -0.70710678118654752440f, inv_sqrt_2pi = 0.39894228040143267794f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t px = i / C;
+    const int c = (int)(i - px * C);
+    const float scale = __ldg(params + px * params_ld + c), mean = __ldg(params + px * params_ld + C + c);
+    const float d = __fsub_rn(__fadd_rn(__ldg(y + i), __ldg(noise + i)), mean);
+    const float v = fabsf(d), sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    const float sc = fmaxf(scale, 0.11f);
+    const float u = (0.5f - v) / sc, l = (-0.5f - v) / sc;
+    const float p_raw = 0.5f * erfcf(kc * u) - 0.5f * erfcf(kc * l);
+    float g_p = g / fmaxf(p_raw, 1e-9f);
+    if (!(p_raw >= 1e-9f || g_p < 0.f)) g_p = 0.f;
+    const float g_u = g_p * inv_sqrt_2pi * expf(-0.5f * u * u), g_l = -g_p * inv_sqrt_2pi * expf(-0.5f * l * l);
+    const float g_v = -(g_u + g_l) / sc;
+    float g_s = -(g_u * u + g_l * l) / sc;
+    if (!(scale >= 0.11f || g_s < 0.f)) g_s = 0.f;
+    const float g_d = g_v * sgn;
+    g_y[i] = g_d;
+    g_params[px * params_ld + c] = g_s;
+    g_params[px * params_ld + C + c] = -g_d;
+  }
+}
+
+// eb_bits_backward: p = |sigmoid(s U) - sigmoid(s L)|, L / U = cumulative logits at z~ -+ 1/2, s = -sign(L + U) (a constant of
+// the graph).  One CTA per channel: its threads walk the channel's elements, back-propagate both logits through the 5-layer
+// MLP (widths 1,3,3,3,3,1) and keep the 58 parameter gradients of the channel in registers; a fixed-order block reduction
+// makes them deterministic.  Gradients are with respect to the TRANSFORMED parameters the kernels read (softplus(matrix),
+// bias, tanh(factor)); the caller chains through softplus / tanh.
+struct EbTape {
+  float v;          // input
+  float h[4][3];    // layer outputs h_0..h_3
+  float th[4][3];   // tanh(t_i)
+};
+__device__ __forceinline__ float eb_forward_tape(const float* m, const float* b, const float* f, float v, EbTape& tp) {
+  tp.v = v;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float t = m[r] * v + b[r];
+    tp.th[0][r] = tanhf(t);
+    tp.h[0][r] = t + f[r] * tp.th[0][r];
+  }
+#pragma unroll
+  for (int l = 1; l < 4; ++l) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float* mr = m + 3 + (l - 1) * 9 + r * 3;
+      const float t = mr[0] * tp.h[l - 1][0] + mr[1] * tp.h[l - 1][1] + mr[2] * tp.h[l - 1][2] + b[3 * l + r];
+      tp.th[l][r] = tanhf(t);
+      tp.h[l][r] = t + f[3 * l + r] * tp.th[l][r];
+    }
+  }
+  return m[30] * tp.h[3][0] + m[31] * tp.h[3][1] + m[32] * tp.h[3][2] + b[12];
+}
+// accumulates into gm[33], gb[13], gf[12]; returns d logit / d v times g
+__device__ __forceinline__ float eb_backward_tape(const float* m, const float* f, const EbTape& tp, float g, float* gm, float* gb,
+                                                  float* gf) {
+  float gh[3];
+  gb[12] += g;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    gm[30 + j] += g * tp.h[3][j];
+    gh[j] = g * m[30 + j];
+  }
+#pragma unroll
+  for (int l = 3; l >= 1; --l) {
+    float gt[3], gprev[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      gf[3 * l + r] += gh[r] * tp.th[l][r];
+      gt[r] = gh[r] * (1.f + f[3 * l + r] * (1.f - tp.th[l][r] * tp.th[l][r]));
+      gb[3 * l + r] += gt[r];
+      const float* mr = m + 3 + (l - 1) * 9 + r * 3;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        gm[3 + (l - 1) * 9 + r * 3 + j] += gt[r] * tp.h[l - 1][j];
+        gprev[j] += gt[r] * mr[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) gh[j] = gprev[j];
+  }
+  float gv = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    gf[r] += gh[r] * tp.th[0][r];
+    const float gt = gh[r] * (1.f + f[r] * (1.f - tp.th[0][r] * tp.th[0][r]));
+    gb[r] += gt;
+    gm[r] += gt * tp.v;
+    gv += gt * m[r];
+  }
+  return gv;
+}
+
+__global__ void __launch_bounds__(256) eb_bits_backward_kernel(const float* __restrict__ z_tilde, const float* __restrict__ mats,
+                                                               const float* __restrict__ biases, const float* __restrict__ factors,
+                                                               const float* __restrict__ gS, float* __restrict__ g_z,
+                                                               float* __restrict__ g_mats, float* __restrict__ g_biases,
+                                                               float* __restrict__ g_factors, int64_t npix, int C) {
+  const int c = blockIdx.x;
+  float m[33], b[13], f[12];
+#pragma unroll
+  for (int i = 0; i < 33; ++i) m[i] = mats[c * 33 + i];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) b[i] = biases[c * 13 + i];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) f[i] = factors[c * 12 + i];
+  float acc[58];
+#pragma unroll
+  for (int i = 0; i < 58; ++i) acc[i] = 0.f;
+  const float g = __ldg(gS);
+  for (int64_t px = threadIdx.x; px < npix; px += blockDim.x) {
+    const float q = z_tilde[px * C + c];
+    EbTape tl, tu;
+    const float lo = eb_forward_tape(m, b, f, q - 0.5f, tl), up = eb_forward_tape(m, b, f, q + 0.5f, tu);
+    const float t = lo + up;
+    const float s = t > 0.f ? -1.f : (t < 0.f ? 1.f : 0.f);
+    const float a = sigmoidf_(s * up), bb = sigmoidf_(s * lo);
+    const float diff = a - bb, p_raw = fabsf(diff);
+    float g_p = g / fmaxf(p_raw, 1e-9f);
+    if (!(p_raw >= 1e-9f || g_p < 0.f)) g_p = 0.f;
+    const float g_diff = g_p * (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
+    const float g_up = g_diff * a * (1.f - a) * s, g_lo = -g_diff * bb * (1.f - bb) * s;
+    float gz = eb_backward_tape(m, f, tu, g_up, acc, acc + 33, acc + 46);
+    gz += eb_backward_tape(m, f, tl, g_lo, acc, acc + 33, acc + 46);
+    g_z[px * C + c] = gz;
+  }
+  __shared__ float sh[8];
+#pragma unroll 1
+  for (int i = 0; i < 58; ++i) {
+    float v = warp_sum(acc[i]);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tsum = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tsum += sh[w];
+      if (i < 33) g_mats[c * 33 + i] = tsum;
+      else if (i < 46) g_biases[c * 13 + (i - 33)] = tsum;
+      else g_factors[c * 12 + (i - 46)] = tsum;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace tdvc
 
 using namespace tdvc;
@@ -313,5 +468,28 @@ extern "C" int tdvc_eb_symbols(const float* z, int ld, const float* medians, int
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   eb_symbols_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, ld, medians, N, HW, C, symbols, indexes);
   TDVC_CHECK_LAUNCH("eb_symbols");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_gc_bits_backward(const float* y, const float* noise, const float* params, int params_ld, const float* grad_sum,
+                                     float* grad_y, float* grad_params, int64_t npix, int C, void* stream) {
+  TDVC_REQUIRE(y && noise && params && grad_sum && grad_y && grad_params && npix > 0 && C > 0 && params_ld >= 2 * C,
+               "gc_bits_backward: bad args");
+  const int64_t total = npix * C;
+  int grid = cdiv(total, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  gc_bits_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, noise, params, params_ld, grad_sum, grad_y, grad_params, total, C);
+  TDVC_CHECK_LAUNCH("gc_bits_backward");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_eb_bits_backward(const float* z_tilde, const float* mats, const float* biases, const float* factors,
+                                     const float* grad_sum, float* grad_z, float* grad_mats, float* grad_biases,
+                                     float* grad_factors, int64_t npix, int C, void* stream) {
+  TDVC_REQUIRE(z_tilde && mats && biases && factors && grad_sum && grad_z && grad_mats && grad_biases && grad_factors &&
+                   npix > 0 && C > 0, "eb_bits_backward: bad args");
+  eb_bits_backward_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(z_tilde, mats, biases, factors, grad_sum, grad_z, grad_mats,
+                                                               grad_biases, grad_factors, npix, C);
+  TDVC_CHECK_LAUNCH("eb_bits_backward");
   return TDVC_OK;
 }

@@ -103,6 +103,8 @@ SIGNATURES = {
     "tdvc_ar_code": [C.POINTER(ArParams), vp, sz, vp],
     "tdvc_rans_encode_with_indexes": [vp, vp, i64, vp, i32, vp, vp, i32, vp, i64],
     "tdvc_rans_decode_with_indexes": [vp, i64, vp, i64, vp, i32, vp, vp, i32, vp],
+    "tdvc_gc_bits_backward": [vp, vp, vp, i32, vp, vp, vp, i64, i32, vp],
+    "tdvc_eb_bits_backward": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     "tdvc_avgpool_scale": [vp, i32, vp, i32, i32, i32, i32, i32, vp],
     "tdvc_ff_descriptors": [vp, vp, i32, i32, i32, i32, vp],
     "tdvc_ff_match": [vp, vp, vp, vp, i32, i32, i32, vp],

@@ -337,3 +337,103 @@ def gdn(input, beta, gamma, inverse=False, impl=L.IMPL_AUTO):
     Forward: the fused tcgen05 kernel of the inference path; backward: two element-wise kernels around the 1x1 convolution's
     dgrad / wgrad."""
     return _GDN.apply(input, beta, gamma, bool(inverse), int(impl))
+
+
+# ----------------------------------------------------------------------------------------------- likelihood -> bits with autograd
+def _scalar_from_acc(acc):
+    return acc.float().reshape(())
+
+
+class _GcBits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, scales, means, noise):
+        from tdvc_b200.model import Act
+        for name, t in (("y", y), ("scales", scales), ("means", means), ("noise", noise)):
+            if not t.is_cuda or t.dtype != torch.float32 or t.shape != y.shape:
+                raise RuntimeError(f"gaussian_conditional_bits: {name} must be a float32 CUDA tensor of y's shape")
+        N, C, H, W = y.shape
+        lib = L.load()
+        with torch.cuda.device(y.device):
+            st = torch.cuda.current_stream(y.device).cuda_stream
+            ya, na = _nhwc(y.detach().contiguous()), _nhwc(noise.detach().contiguous())
+            pa = _nhwc(torch.cat((scales.detach(), means.detach()), 1))   # (scales | means), the layout of the entropy-parameter output
+            acc = torch.zeros(1, device=y.device, dtype=torch.float64)
+            L.check(lib.tdvc_gc_bits_noise(ya.ptr, na.ptr, pa.ptr, pa.ld, N * H * W, C, acc.data_ptr(), st), "gc_bits_noise")
+        ctx.t = (ya, na, pa)
+        return _scalar_from_acc(acc)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gS):
+        from tdvc_b200.model import Act
+        ya, na, pa = ctx.t
+        N, H, W, C = ya.N, ya.H, ya.W, ya.C
+        lib = L.load()
+        dev = gS.device
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            g = gS.detach().float().reshape(1).contiguous()
+            gy, gp = Act.alloc(N, H, W, C, dev), Act.alloc(N, H, W, 2 * C, dev)
+            L.check(lib.tdvc_gc_bits_backward(ya.ptr, na.ptr, pa.ptr, pa.ld, g.data_ptr(), gy.ptr, gp.ptr, N * H * W, C, st),
+                    "gc_bits_backward")
+            return _nchw(gy), _nchw(gp.chan(0, C)), _nchw(gp.chan(C, C)), None
+
+
+def gaussian_conditional_bits(y, scales, means, noise):
+    """sum ln max(p, 1e-9) of compressai's GaussianConditional in training mode - the likelihood of y + noise under N(means,
+    max(scales, 0.11)) integrated over the quantisation bin - as a 0-d tensor with autograd to y, scales and means (NCHW float32
+    CUDA tensors of one shape; reference pnet.py:38-43 divides the sum by -ln 2 * num_pixels)."""
+    return _GcBits.apply(y, scales, means, noise)
+
+
+class _EbBits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, noise, mats, biases, factors):
+        from tdvc_b200.model import Act
+        N, C, H, W = z.shape
+        if tuple(mats.shape) != (C, 33) or tuple(biases.shape) != (C, 13) or tuple(factors.shape) != (C, 12):
+            raise RuntimeError("entropy_bottleneck_bits: expected filters (3, 3, 3, 3)")
+        lib = L.load()
+        with torch.cuda.device(z.device):
+            st = torch.cuda.current_stream(z.device).cuda_stream
+            za, na = _nhwc(z.detach().contiguous()), _nhwc(noise.detach().contiguous())
+            zt = Act.alloc(N, H, W, C, z.device)
+            m, b, f = (t.detach().float().contiguous() for t in (mats, biases, factors))
+            acc = torch.zeros(1, device=z.device, dtype=torch.float64)
+            L.check(lib.tdvc_eb_bits_noise(za.ptr, na.ptr, zt.ptr, m.data_ptr(), b.data_ptr(), f.data_ptr(), N * H * W, C,
+                                           acc.data_ptr(), st), "eb_bits_noise")
+            z_tilde = _nchw(zt)
+        ctx.t = (zt, m, b, f)
+        return z_tilde, _scalar_from_acc(acc)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_zt, gS):
+        from tdvc_b200.model import Act
+        zt, m, b, f = ctx.t
+        N, H, W, C = zt.N, zt.H, zt.W, zt.C
+        lib = L.load()
+        dev = m.device
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            g = gS.detach().float().reshape(1).contiguous()
+            gz = Act.alloc(N, H, W, C, dev)
+            gm, gb, gf = torch.empty_like(m), torch.empty_like(b), torch.empty_like(f)
+            L.check(lib.tdvc_eb_bits_backward(zt.ptr, m.data_ptr(), b.data_ptr(), f.data_ptr(), g.data_ptr(), gz.ptr,
+                                              gm.data_ptr(), gb.data_ptr(), gf.data_ptr(), N * H * W, C, st), "eb_bits_backward")
+            if g_zt is not None:   # z~ = z + noise: what flows into z~ from its consumers flows into z unchanged
+                ga = _nhwc(g_zt.float().contiguous())
+                L.check(lib.tdvc_axpby(gz.ptr, ga.ptr, gz.ptr, N * H * W * C, 1.0, 1.0, st), "axpby")
+            return _nchw(gz), None, gm, gb, gf
+
+
+def entropy_bottleneck_bits(z, noise, matrices, biases, factors):
+    """compressai EntropyBottleneck in training mode: z~ = z + noise and sum ln max(p(z~), 1e-9) of the factorised prior
+    (per-channel cumulative MLP, widths 1,3,3,3,3,1) -> (z~, 0-d sum), with autograd to z and to the RAW parameters
+    (`_matrix0..4`, `_bias0..4`, `_factor0..3` as compressai stores them: the softplus / tanh reparametrisation is ordinary
+    torch arithmetic on these small tensors, the element-wise work and its backward are kernels)."""
+    C = z.shape[1]
+    m = torch.cat([torch.nn.functional.softplus(t).reshape(C, -1) for t in matrices], 1)
+    b = torch.cat([t.reshape(C, -1) for t in biases], 1)
+    f = torch.cat([torch.tanh(t).reshape(C, -1) for t in factors], 1)
+    return _EbBits.apply(z, noise, m, b, f)

@@ -135,3 +135,78 @@ def test_gdn_forward_backward_vs_torch_fp64(inverse):
     nb = F.conv2d((x * 200.0).double() ** 2, gamma.double().reshape(C, C, 1, 1), beta.double())
     rb = (x * 200.0).double() * (torch.sqrt(nb) if inverse else torch.rsqrt(nb))
     assert (yb.double() - rb).abs().max().item() <= 5e-5 * rb.abs().max().item()
+
+
+def test_gaussian_conditional_bits_backward_vs_oracle_fp64():
+    """sum ln p of the conditional Gaussian in noise mode and its gradients against the oracle's GaussianConditional in float64
+    (compressai's LowerBound gradient rule included: scales below 0.11, likelihoods below 1e-9, both signs of the upstream
+    gradient)."""
+    from oracle.compressai_port import GaussianConditional
+    from tdvc_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(21)
+    shape = (2, 128, 8, 12)
+    y = torch.randn(shape, generator=g) * 4
+    means = torch.randn(shape, generator=g) * 2
+    scales = torch.exp(torch.randn(shape, generator=g) * 1.5 - 0.5)       # spans both sides of the 0.11 bound
+    y[0, :4] += 40.0                                                     # far tails: likelihood below the 1e-9 bound
+    noise = torch.rand(shape, generator=g) - 0.5
+    gc = GaussianConditional(None).double()
+    for gs in (-0.37, 0.8):
+        ys, ss, ms = (t.to(dev).requires_grad_(True) for t in (y, scales, means))
+        S = ops.gaussian_conditional_bits(ys, ss, ms, noise.to(dev))
+        (S * gs).backward()
+        yd, sd, md = (t.double().requires_grad_(True) for t in (y, scales, means))
+        lik = gc.likelihood_lower_bound(gc._likelihood(yd + noise.double(), sd, md))
+        Sd = torch.log(lik).sum()
+        (Sd * gs).backward()
+        assert abs(S.item() - Sd.item()) <= 2e-5 * abs(Sd.item())
+        for name, a, r in (("y", ys.grad, yd.grad), ("scales", ss.grad, sd.grad), ("means", ms.grad, md.grad)):
+            a = a.cpu().double()
+            # fp32 erfc differences are amplified where p is tiny (g / p): compare relative to the local gradient scale
+            err = ((a - r).abs() / (r.abs() + 1e-3 * r.abs().max())).max().item()
+            assert err <= 2e-3, (name, gs, err)
+            # the bound rule zeroes the same entries (fp32 additionally underflows gradients below ~1e-38 in the far tails)
+            assert (a[r == 0] == 0).all() and (a[r.abs() > 1e-12 * r.abs().max()] != 0).all(), name
+
+
+def test_entropy_bottleneck_bits_backward_vs_oracle_fp64():
+    from oracle.compressai_port import EntropyBottleneck
+    from tdvc_b200 import ops
+    dev = torch.device("cuda:0")
+    torch.manual_seed(31)
+    C = 128
+    eb = EntropyBottleneck(C)
+    with torch.no_grad():
+        for n, p in eb.named_parameters():
+            if n.startswith("_factor"):
+                p.copy_(torch.randn_like(p) * 0.3)
+            elif n.startswith("_matrix"):
+                p.add_(torch.randn_like(p) * 0.2)
+    ebd = EntropyBottleneck(C).double()
+    ebd.load_state_dict(eb.state_dict())
+    z = torch.randn(2, C, 4, 6) * 3
+    z[0, :3] += 60.0                                  # likelihood below the bound
+    noise = torch.rand(z.shape) - 0.5
+    gzt = torch.randn(z.shape) * 0.01                 # gradient arriving at z~ from its consumers (h_s)
+    for gs in (-0.37, 0.8):
+        zs = z.to(dev).requires_grad_(True)
+        params = {n: p.detach().to(dev).requires_grad_(True) for n, p in eb.named_parameters() if n != "quantiles"}
+        zt, S = ops.entropy_bottleneck_bits(zs, noise.to(dev), [params[f"_matrix{i}"] for i in range(5)],
+                                            [params[f"_bias{i}"] for i in range(5)], [params[f"_factor{i}"] for i in range(4)])
+        (S * gs + (zt * gzt.to(dev)).sum()).backward()
+        zd = z.double().requires_grad_(True)
+        for p in ebd.parameters():
+            p.grad = None
+        v = (zd + noise.double()).permute(1, 0, 2, 3).reshape(C, 1, -1)
+        lik = ebd.likelihood_lower_bound(ebd._likelihood(v))
+        Sd = torch.log(lik).sum()
+        (Sd * gs + ((zd + noise.double()) * gzt.double()).sum()).backward()
+        assert (zt.cpu() - (z + noise)).abs().max().item() < 1e-6
+        assert abs(S.item() - Sd.item()) <= 2e-5 * abs(Sd.item())
+        pairs = [("z", zs.grad, zd.grad)] + [(n, params[n].grad, dict(ebd.named_parameters())[n].grad) for n in params]
+        for name, a, r in pairs:
+            assert a is not None, name
+            a = a.cpu().double()
+            err = (a - r).abs().max().item()
+            assert err <= 1e-3 * max(r.abs().max().item(), 1e-6), (name, gs, err, r.abs().max().item())
