@@ -1449,6 +1449,8 @@ class VideoCompressor(nn.Module):
             if is_compress:
                 raise RuntimeError("is_compress=True is served in eval() mode (the reference switches both coders to eval() "
                                    "before it codes, pnet.py:46,70)")
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                return self._forward_training_autograd(input_image, refer_frames)
             return self._forward_training(input_image, refer_frames, taps, noise=None)
         N, H, W = self._check(input_image, refer_frames, 3)
         dev = input_image.device
@@ -1508,8 +1510,9 @@ class VideoCompressor(nn.Module):
         FeatureFix patch matching at scale 8 (pnet.py:220-221), and the 5-tuple return with the two aux losses (:80-81).
         noise: None = drawn on the device (Philox4x32-10 seeded from torch's CPU generator, so torch.manual_seed governs it), or
         {"mv.z", "mv.y", "mv.y_lik", "res.z", "res.y", "res.y_lik": (N,128,h,w) CUDA tensors} to inject given draws (tests).
-        FORWARD ONLY: reconstruction and bpp carry no autograd graph (backward kernels of the convolutions are SURVEY.md 8f row
-        1, not built), so `rd_loss.backward()` raises; the aux losses DO back-propagate to `.quantiles`."""
+        FORWARD ONLY, on the fused inference kernels (used under torch.no_grad() / for frozen models): reconstruction and bpp
+        carry no autograd graph; with gradients enabled `forward` takes `_forward_training_autograd` instead.  The aux losses
+        back-propagate to `.quantiles` on both paths."""
         N, H, W = self._check(input_image, refer_frames, 3)
         dev = input_image.device
         with torch.cuda.device(dev):
@@ -1531,6 +1534,30 @@ class VideoCompressor(nn.Module):
             mv_aux = _AuxLoss.apply(self.mvCoder.entropy_bottleneck.quantiles, aux[0], Wt["mv.eb"])
             res_aux = _AuxLoss.apply(self.resCoder.entropy_bottleneck.quantiles, aux[1], Wt["rs.eb"])
         return recon, bpp[1:2], bpp[0:1], mv_aux, res_aux
+
+    def _forward_training_autograd(self, input_image, refer_frames, noise=None):
+        """`self.training` with gradients enabled: the same forward built from the autograd functions of `tdvc_b200.ops`
+        (tdvc_b200/train_graph.py), so that the reference's training step - `rd_loss.backward()`, gradient clipping, the two
+        Adam steps, `aux_loss.backward()` (tools/train.py:125-159) - runs on this module.  Returns the 5-tuple of pnet.py:80-81;
+        every output carries its graph.  noise: as `_forward_training` (None: drawn on the device)."""
+        self._check(input_image, refer_frames, 3)
+        from tdvc_b200 import train_graph
+        dev = input_image.device
+        with torch.cuda.device(dev):
+            x = input_image.float().contiguous()
+            refs = refer_frames.float().contiguous()
+            recon, bpp_res, bpp_mv, ind = train_graph.forward(self, x, refs, noise)
+            self.last_ind = ind
+            aux = []
+            lib = L.load()
+            st = torch.cuda.current_stream(dev).cuda_stream
+            for cd in (self.mvCoder, self.resCoder):   # EntropyBottleneck.loss() (pnet.py:35,59) and its gradient to .quantiles
+                eb = pack_entropy_bottleneck(cd.entropy_bottleneck, P=lambda mod, name: getattr(mod, name).detach().float())
+                val = torch.empty(1, device=dev, dtype=torch.float32)
+                L.check(lib.tdvc_eb_aux_loss(eb[0].data_ptr(), eb[1].data_ptr(), eb[2].data_ptr(), eb[4].data_ptr(), eb[5].data_ptr(),
+                                             eb[0].shape[0], val.data_ptr(), st), "eb_aux_loss")
+                aux.append(_AuxLoss.apply(cd.entropy_bottleneck.quantiles, val[0], eb))
+        return recon, bpp_res, bpp_mv, aux[0], aux[1]
 
     def _noise(self, plan, given, N, H, W):
         lib = L.load()
