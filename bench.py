@@ -200,6 +200,73 @@ def gpu_eager_baseline(dev, hh, ww, iters=3):
     return out
 
 
+def training_leg(dev, world, steps, warmup, batch=8, size=256):
+    """BASELINE config 4: one training step of reference tools/train.py:125-159 (enable_amp False branch) - forward, rd_loss
+    (2048 * MSE + bpp_res + bpp_mv), backward, clip_grad_norm_(2), Adam step, aux_loss backward, aux Adam step - on a
+    Vimeo-shaped synthetic batch: `batch` samples of 256x256 with 4 references each PER GPU (the reference splits a global
+    batch over DataParallel replicas; one process per GPU with DistributedDataParallel here, NCCL gradient all-reduce).
+    CUDA-event timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from tdvc_b200 import synth
+    from tdvc_b200.model import VideoCompressor
+    torch.manual_seed(synth.SEED)
+    net = VideoCompressor()
+    sd = net.state_dict()
+    synth.condition_state_dict(sd)
+    net.load_state_dict(sd)
+    net = net.to(dev).train()
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], find_unused_parameters=True)
+    params = [p for n, p in net.named_parameters() if not n.endswith(".quantiles")]
+    aux_params = [p for n, p in net.named_parameters() if n.endswith(".quantiles")]
+    opt = torch.optim.Adam(params, lr=1e-4)            # reference main/utils/utils.py:90-113 (cfg/train.yaml lr)
+    aux_opt = torch.optim.Adam(aux_params, lr=1e-3)
+    rank = dist.get_rank() if world > 1 else 0
+    pairs = [synth.make_frame_pair(size, size, seed=500 + rank * batch + i) for i in range(batch)]
+    x = torch.cat([p[0] for p in pairs]).to(dev)
+    refs = torch.cat([p[1] for p in pairs]).to(dev)
+    losses = []
+
+    def step():
+        out = model(x, refs, False)
+        mse = torch.nn.MSELoss()(out[0], x)
+        loss = 2048 * mse + out[1].mean() + out[2].mean()
+        aux = out[3] + out[4]
+        opt.zero_grad()
+        aux_opt.zero_grad()
+        # one backward pass for both losses: rd_loss does not depend on `.quantiles` and aux_loss depends on nothing else, so
+        # the gradients are those of the reference's two passes (DistributedDataParallel ties a forward's outputs to ONE pass)
+        (loss + aux).backward()
+        torch.nn.utils.clip_grad_norm_(params, 2)
+        opt.step()
+        aux_opt.step()
+        losses.append(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    return {"ms_per_step": ms, "samples_per_s": batch * world / (ms / 1e3), "batch_per_gpu": batch, "size": size, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+            "what": "forward + rd_loss backward + clip + Adam + aux step (reference tools/train.py:125-159); convolutions, GDN, DCN "
+                    "and entropy models on tdvc_b200 kernels, torch autograd as the tape with torch glue operators between "
+                    "them (DESIGN.md section 7)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -215,6 +282,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--cpu-sample", default="full", choices=["full", "small"])
+    ap.add_argument("--workload", default="predict", choices=["predict", "train"],
+                    help="predict: the headline P-frame coding benchmark; train: BASELINE config 4 (training step) on its own")
+    ap.add_argument("--no-train-leg", action="store_true")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
     args = ap.parse_args()
@@ -239,6 +309,18 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))   # a hang must fail fast
+    if args.workload == "train":
+        rec = training_leg(dev, world, max(1, min(args.steps, 8)), max(args.warmup, 3))
+        if rank == 0:
+            print(json.dumps({"metric": "training samples/sec (256x256 Vimeo-shaped, batch 8 per GPU)", "value": rec["samples_per_s"],
+                              "unit": "samples/s", "n_gpus": world, "steps": rec["steps"], "warmup": rec["warmup"],
+                              "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "f32", "data": "synthetic", "config": {"workload": "BASELINE config 4: " + rec["what"]},
+                              "training_step": rec}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     hh, ww = args.height, args.width
     K, Wm = args.steps, max(args.warmup, 3)
     # one untimed GOP in front of the W warm-up steps: every launch variant of a GOP (which features are cached) is run and
@@ -462,6 +544,14 @@ def main():
                                   "kernel per coder (two streams) + host rANS (compressai's coder runs on the host too)"}
             except Exception as e:
                 coding = {"error": f"{type(e).__name__}: {e}"[:300]}
+        train = None
+        if world == 1 and not args.no_train_leg:
+            try:
+                torch.cuda.empty_cache()
+                train = training_leg(dev, 1, 3, 1)
+            except Exception as e:
+                train = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
         eager = None
         if not args.no_eager_baseline and world == 1:
             eager = gpu_eager_baseline(dev, hh, ww)
@@ -487,7 +577,7 @@ def main():
                 "roofline": roof, "frame_tensor_tflops": frame_tflops,
                 "frame_tensor_frac_of_sustained_bf16": frame_tflops / peaks["bf16_tflops_sustained"],
                 "products_per_mac": products_per_mac, "instrumented_frame_ms": total_ms,
-                "memory_bound_kernels": mem_rows, "kernels": kernels, "config5": cfg5, "entropy_coding": coding,
+                "memory_bound_kernels": mem_rows, "kernels": kernels, "config5": cfg5, "entropy_coding": coding, "training_step": train,
                 "gpu_eager_baseline": eager, "exact_precision_ms_per_step": ms_exact,
                 "cpu_baseline": cpu, "stats": G.summarise(stats)}
         print(json.dumps(line), flush=True)

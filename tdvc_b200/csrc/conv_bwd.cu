@@ -6,9 +6,11 @@
 //   included) from a re-packed weight.  A stride-s layer first spreads its output gradient over the input grid
 //   (`zero_insert`: g_up[oy * s][ox * s] = g[oy][ox], zeros elsewhere).
 // * `act_backward`: g * f'(y) from the layer's OUTPUT (ReLU / LeakyReLU / clamp keep the sign information there).
-// * `wgrad`: d W[co][ci][ky][kx] = sum over pixels of x[p + tap][ci] * g[p][co], exact fp32 FFMA, deterministic: the pixel
-//   range is cut into S slabs, a CTA owns (slab, tap, 64 ci, 64 co) with a 4x4 register tile per thread, partial sums go to
-//   a workspace and a second kernel adds the S partials in a fixed order (the bias gradient rides along).
+// * `wgrad`: d W[co][ci][ky][kx] = sum over pixels of x[p + tap][ci] * g[p][co]: a GEMM whose reduction runs over the pixels.
+//   The pixel range is cut into S slabs, a CTA owns (slab, tap, 64 ci, 64 co) and contracts staged 32-pixel chunks with
+//   warp-level TF32 MMAs on (hi, lo) operand pairs (three products: fp32-class); partial sums go to a workspace and a second
+//   kernel adds the S partials in a fixed order (deterministic; the bias gradient rides along).  (A first exact-FFMA version
+//   with a 4x4 register tile per thread spent 250 of the 436 ms of a training step here.)
 #include "common.cuh"
 
 namespace tdvc {
@@ -84,7 +86,7 @@ __global__ void gdn_bwd_post_kernel(const float* __restrict__ dx_direct, const f
 
 constexpr int WG_T = 64;      // ci x co tile of a CTA
 constexpr int WG_P = 32;      // output pixels per staged chunk
-constexpr int WG_LD = WG_T + 4;
+constexpr int WG_LD = WG_T + 8;   // row pitch = 8 banks: the (k = lane & 3, m = lane >> 2) fragment reads are conflict-free
 
 struct WgradArgs {
   const float* x; int x_ld;
@@ -96,41 +98,71 @@ struct WgradArgs {
   float* part_bias;   // [S][cout] or nullptr
 };
 
+// fp32 -> (hi, lo) TF32 pair: hi = rna(v), lo = rna(v - hi); hi*hi' + lo*hi' + hi*lo' carries ~21 significand bits
+__device__ __forceinline__ void tf32_split(float v, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(v - __uint_as_float(hi)));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// One CTA = (tap, 64 ci, 64 co, pixel slab).  The reduction dimension of this GEMM is the PIXEL index, so both operands are
+// read "transposed" from their channels-last rows: chunks of 32 pixels x 64 channels of x (shifted by the tap) and of grad_y
+// are staged in shared memory and contracted with warp-level m16n8k8 TF32 MMAs, each fp32 operand split into a TF32 (hi, lo)
+// pair and three products issued (fp32-class accuracy: the weight gradient sums ~10^5..10^6 terms).  8 warps: warp w owns ci
+// rows 16 (w & 3) .. +16 and co columns 32 (w >> 2) .. +32 (four n-tiles).
 __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
   __shared__ __align__(16) float xs[WG_P][WG_LD];
   __shared__ __align__(16) float gs[WG_P][WG_LD];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  int r = blockIdx.y;
-  const int co_t = r % a.co_tiles; r /= a.co_tiles;
-  const int ci_t = r % a.ci_tiles; r /= a.ci_tiles;
-  const int tap = r;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int kk = a.k * a.k;
+  int r = blockIdx.x;            // the taps of one tile are neighbours in launch order: they read the same slab through L2
+  const int tap = r % kk; r /= kk;
+  const int co_t = r % a.co_tiles;
+  const int ci_t = r / a.co_tiles;
   const int ky = tap / a.k, kx = tap - ky * a.k;
-  const int s = blockIdx.x;
+  const int s = blockIdx.y;
   const int64_t npix = (int64_t)a.N * a.Ho * a.Wo;
   const int64_t p_begin = npix * s / a.S, p_end = npix * (s + 1) / a.S;
   const int ci0 = ci_t * WG_T, co0 = co_t * WG_T;
-  const bool do_bias = a.part_bias != nullptr && tap == 0 && ci_t == 0 && ty == 0;
+  const bool do_bias = a.part_bias != nullptr && tap == 0 && ci_t == 0 && warp == 0;
+  const int m0 = 16 * (warp & 3), n0 = 32 * (warp >> 2);
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t pc = p_begin; pc < p_end; pc += WG_P) {
-    // stage WG_P pixels x 64 channels of x (shifted by the tap, zero outside the image) and of g
-    for (int i = tid; i < WG_P * (WG_T / 4); i += 256) {
+  float bsum0 = 0.f, bsum1 = 0.f;
+  // global -> registers for one chunk (two float4 of x and of g per thread); the loads of chunk i + 1 are in flight while the
+  // MMAs of chunk i run
+  // (the pixel coordinates of a thread's two staging slots advance by WG_P per chunk: tracked incrementally, no divisions)
+  int sn[2], sy[2], sx[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t p = p_begin + ((tid + 256 * h) >> 4);
+    sx[h] = (int)(p % a.Wo);
+    const int64_t q = p / a.Wo;
+    sy[h] = (int)(q % a.Ho);
+    sn[h] = (int)(q / a.Ho);
+  }
+  auto fetch = [&](int64_t pc, float4 (&xr)[2], float4 (&gr)[2]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = tid + 256 * h;
       const int pl = i >> 4, c4 = (i & 15) * 4;
       const int64_t p = pc + pl;
       float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
       if (p < p_end) {
-        const int ox = (int)(p % a.Wo);
-        const int64_t q = p / a.Wo;
-        const int oy = (int)(q % a.Ho), n = (int)(q / a.Ho);
+        const int ox = sx[h], oy = sy[h], n = sn[h];
         const int iy = oy * a.stride + ky - a.pad, ix = ox * a.stride + kx - a.pad;
         if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
           const float* src = a.x + (((int64_t)n * a.H + iy) * a.W + ix) * a.x_ld;
           const int c = ci0 + c4;
-          if (c + 3 < a.cin) xv = *reinterpret_cast<const float4*>(src + c);
+          if (c + 3 < a.cin) xv = __ldg(reinterpret_cast<const float4*>(src + c));
           else {
             if (c < a.cin) xv.x = src[c];
             if (c + 1 < a.cin) xv.y = src[c + 1];
@@ -139,51 +171,80 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
         }
         const float* gsrc = a.g + p * a.g_ld;
         const int c = co0 + c4;
-        if (c + 3 < a.cout) gv = *reinterpret_cast<const float4*>(gsrc + c);
+        if (c + 3 < a.cout) gv = __ldg(reinterpret_cast<const float4*>(gsrc + c));
         else {
           if (c < a.cout) gv.x = gsrc[c];
           if (c + 1 < a.cout) gv.y = gsrc[c + 1];
           if (c + 2 < a.cout) gv.z = gsrc[c + 2];
         }
       }
+      xr[h] = xv;
+      gr[h] = gv;
+      sx[h] += WG_P;
+      while (sx[h] >= a.Wo) {
+        sx[h] -= a.Wo;
+        if (++sy[h] == a.Ho) { sy[h] = 0; ++sn[h]; }
+      }
+    }
+  };
+  float4 xr[2], gr[2];
+  fetch(p_begin, xr, gr);
+  for (int64_t pc = p_begin; pc < p_end; pc += WG_P) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = tid + 256 * h;
+      float4 xv = xr[h];   // (squared here, not at the load: the prefetched registers must not be touched before they are needed)
       if (a.in_square) { xv.x *= xv.x; xv.y *= xv.y; xv.z *= xv.z; xv.w *= xv.w; }
-      *reinterpret_cast<float4*>(&xs[pl][c4]) = xv;
-      *reinterpret_cast<float4*>(&gs[pl][c4]) = gv;
+      *reinterpret_cast<float4*>(&xs[i >> 4][(i & 15) * 4]) = xv;
+      *reinterpret_cast<float4*>(&gs[i >> 4][(i & 15) * 4]) = gr[h];
     }
     __syncthreads();
+    if (pc + WG_P < p_end) fetch(pc + WG_P, xr, gr);
+#pragma unroll
+    for (int k0 = 0; k0 < WG_P; k0 += 8) {
+      // A fragment (16 ci x 8 pixels): element (row m, col k) = xs[k][m]
+      uint32_t ah[4], al[4];
+      tf32_split(xs[k0 + tq][m0 + gq], ah[0], al[0]);
+      tf32_split(xs[k0 + tq][m0 + gq + 8], ah[1], al[1]);
+      tf32_split(xs[k0 + tq + 4][m0 + gq], ah[2], al[2]);
+      tf32_split(xs[k0 + tq + 4][m0 + gq + 8], ah[3], al[3]);
+      // B fragments (8 pixels x 8 co each): element (row k, col n) = gs[k][n]
+      uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        tf32_split(gs[k0 + tq][n0 + 8 * nt + gq], bh0[nt], bl0[nt]);
+        tf32_split(gs[k0 + tq + 4][n0 + 8 * nt + gq], bh1[nt], bl1[nt]);
+      }
+      // consecutive MMAs go to different accumulators (an accumulator's three products are 4 issues apart)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], al, bh0[nt], bh1[nt]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], ah, bl0[nt], bl1[nt]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], ah, bh0[nt], bh1[nt]);
+    }
+    if (do_bias) {
 #pragma unroll 8
-    for (int pl = 0; pl < WG_P; ++pl) {
-      const float4 xa = *reinterpret_cast<const float4*>(&xs[pl][ty * 4]);
-      const float4 gb = *reinterpret_cast<const float4*>(&gs[pl][tx * 4]);
-      const float xv[4] = {xa.x, xa.y, xa.z, xa.w}, gv[4] = {gb.x, gb.y, gb.z, gb.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], gv[j], acc[i][j]);
-      if (do_bias) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bsum[j] += gv[j];
+      for (int pl = 0; pl < WG_P; ++pl) {
+        bsum0 += gs[pl][lane];
+        bsum1 += gs[pl][lane + 32];
       }
     }
     __syncthreads();
   }
-  float* dst = a.part + ((int64_t)s * a.k * a.k + tap) * a.cin * a.cout;
+  float* dst = a.part + ((int64_t)s * kk + tap) * a.cin * a.cout;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ci = ci0 + ty * 4 + i;
-    if (ci >= a.cin) continue;
+  for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = co0 + tx * 4 + j;
-      if (co < a.cout) dst[(int64_t)ci * a.cout + co] = acc[i][j];
+    for (int e = 0; e < 4; ++e) {
+      const int ci = ci0 + m0 + gq + ((e & 2) ? 8 : 0);
+      const int co = co0 + n0 + 8 * nt + 2 * tq + (e & 1);
+      if (ci < a.cin && co < a.cout) dst[(int64_t)ci * a.cout + co] = acc[nt][e];
     }
   }
   if (do_bias) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = co0 + tx * 4 + j;
-      if (co < a.cout) a.part_bias[(int64_t)s * a.cout + co] = bsum[j];
-    }
+    if (co0 + lane < a.cout) a.part_bias[(int64_t)s * a.cout + co0 + lane] = bsum0;
+    if (co0 + lane + 32 < a.cout) a.part_bias[(int64_t)s * a.cout + co0 + lane + 32] = bsum1;
   }
 }
 
@@ -269,7 +330,7 @@ extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, 
   a.part = (float*)workspace;
   a.part_bias = a.part + (size_t)a.S * k * k * cin * cout;
   cudaStream_t st = (cudaStream_t)stream;
-  wgrad_kernel<<<dim3(a.S, tiles), 256, 0, st>>>(a);
+  wgrad_kernel<<<dim3(tiles, a.S), 256, 0, st>>>(a);
   TDVC_CHECK_LAUNCH("conv2d_wgrad");
   const int64_t n_out = (int64_t)k * k * cin * cout + cout;
   wgrad_reduce_kernel<<<cdiv(n_out, 256), 256, 0, st>>>(a.part, a.part_bias, a.S, k * k, cin, cout, grad_w, grad_b_or_null);
