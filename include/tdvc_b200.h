@@ -123,9 +123,9 @@ int tdvc_dcn_v2_forward(const float* input, const float* weight, const float* bi
  * dcn_v2_im2col_cuda.cu:197-327): same tensor conventions as the forward, any geometry; grad_output (N, O, Ho, Wo).
  * Writes grad_input (N,C,H,W), grad_offset / grad_mask (shapes of offset / mask), grad_weight (O,C,kh,kw), grad_bias (O).
  * Deterministic (the reference's col2im uses float atomicAdd): grad_input is accumulated as 64-bit fixed point in `workspace`
- * (>= tdvc_dcn_v2_backward_workspace_bytes(N,C,H,W) bytes, 8-byte aligned), everything else has one owner per element.
+ * (>= tdvc_dcn_v2_backward_workspace_bytes(N,C,O,H,W,Ho,Wo,kh*kw) bytes, 16-byte aligned: fixed-point grad_input, the im2col rows and the partial sums of the weight gradient), everything else has one owner per element.
  * `bias` is not needed (its gradient is the plain sum of grad_output).                                                      */
-size_t tdvc_dcn_v2_backward_workspace_bytes(int N, int C, int H, int W);
+size_t tdvc_dcn_v2_backward_workspace_bytes(int N, int C, int O, int H, int W, int Ho, int Wo, int K);
 int tdvc_dcn_v2_backward(const float* input, const float* weight, const float* offset, const float* mask,
                          const float* grad_output, float* grad_input, float* grad_offset, float* grad_mask,
                          float* grad_weight, float* grad_bias, int N, int C, int O, int H, int W, int kh, int kw,

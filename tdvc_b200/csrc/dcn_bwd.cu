@@ -11,8 +11,8 @@
 //                          grad_input as 64-bit FIXED-POINT integers (atomicAdd on integers is associative, so the sum does not
 //                          depend on the order in which threads arrive);
 //   dcn_bwd_finish_kernel  fixed point -> fp32 grad_input;
-//   dcn_bwd_weight_kernel  one CTA per (c, tap): recomputes the modulated sample of every output position, accumulates its
-//                          product with grad_output for all output channels in registers, fixed-order tree over the CTA;
+//   dcn_im2col_kernel      the modulated samples as rows [position][c * K + k]; grad_weight is then the weight gradient of a
+//                          1x1 convolution of those rows (tdvc_conv2d_wgrad: MMA contraction, fixed-order two-stage sum);
 //   dcn_bwd_bias_kernel    grad_bias[o] = sum grad_output, same tree.
 // The fixed-point scale is a power of two derived on the device from max|grad_output| and max|weight| (dcn_bwd_scale_kernel).
 #include "common.cuh"
@@ -117,56 +117,48 @@ __global__ void dcn_bwd_finish_kernel(const long long* __restrict__ fx, float* _
     out[i] = (float)((double)fx[i] * inv);
 }
 
-// grad_weight[o][c][k] = sum_{n, ho, wo} grad_output[n][o][ho][wo] * mask * bilinear(input[n][c], sample(n, g, k, ho, wo))
-// One CTA per (c, k); OT output channels per pass; thread t walks the positions t, t + 256, ... in a fixed order and the CTA
-// combines its 256 partial sums with a fixed tree: deterministic.
-constexpr int OT = 16;
-__global__ void __launch_bounds__(256) dcn_bwd_weight_kernel(const float* __restrict__ input, const float* __restrict__ offset,
-                                                             const float* __restrict__ mask, const float* __restrict__ go,
-                                                             float* __restrict__ g_w, Geo q) {
-  __shared__ float red[256];
+// grad_weight[o][c][k] = sum_{n, ho, wo} grad_output[n][o][ho][wo] * col[n, ho, wo][c][k], col = mask * bilinear(input[n][c],
+// sample(n, g, k, ho, wo)): a GEMM over the output positions.  dcn_im2col_kernel writes col as rows [position][c * K + k] (one
+// thread per (position, group, tap): the bilinear weights are formed once and applied to the channels of the group) and
+// tdvc_conv2d_wgrad contracts it with the channels-last grad_output as a 1x1 "convolution" (csrc/conv_bwd.cu; deterministic
+// two-stage sum).  (A first version - one CTA per (c, k) walking every position and re-reading grad_output - took 70 ms of a
+// 440 ms training step: 576 CTAs each streamed the whole 134 MB gradient.)
+__global__ void __launch_bounds__(256) dcn_im2col_kernel(const float* __restrict__ input, const float* __restrict__ offset,
+                                                         const float* __restrict__ mask, float* __restrict__ col, int col_ld, Geo q) {
   const int K = q.kh * q.kw, cpg = q.C / q.dg;
-  const int c = blockIdx.x / K, k = blockIdx.x - c * K;
-  const int g = c / cpg;
-  const int ki = k / q.kw, kj = k - ki * q.kw;
   const int64_t hw = (int64_t)q.Ho * q.Wo, HW = (int64_t)q.H * q.W;
-  const int64_t npos = (int64_t)q.N * hw;
-  for (int o0 = 0; o0 < q.O; o0 += OT) {
-    float acc[OT];
-#pragma unroll
-    for (int j = 0; j < OT; ++j) acc[j] = 0.f;
-    for (int64_t p = threadIdx.x; p < npos; p += blockDim.x) {
-      const int n = (int)(p / hw);
-      const int64_t pix = p - (int64_t)n * hw;
-      const int ho = (int)(pix / q.Wo), wo = (int)(pix - (int64_t)ho * q.Wo);
-      const int64_t off_c = ((int64_t)n * q.dg * K + g * K + k) * 2;
-      const float h_im = (float)(ho * q.sh - q.ph + ki * q.dh) + offset[off_c * hw + pix];
-      const float w_im = (float)(wo * q.sw - q.pw + kj * q.dw) + offset[(off_c + 1) * hw + pix];
-      if (!(h_im > -1.f && w_im > -1.f && h_im < (float)q.H && w_im < (float)q.W)) continue;
-      const float hf = floorf(h_im), wf = floorf(w_im);
-      const int h_low = (int)hf, w_low = (int)wf, h_high = h_low + 1, w_high = w_low + 1;
-      const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw_ = 1.f - lw;
-      const float* im = input + ((int64_t)n * q.C + c) * HW;
-      const float v1 = (h_low >= 0 && w_low >= 0) ? im[(int64_t)h_low * q.W + w_low] : 0.f;
-      const float v2 = (h_low >= 0 && w_high <= q.W - 1) ? im[(int64_t)h_low * q.W + w_high] : 0.f;
-      const float v3 = (h_high <= q.H - 1 && w_low >= 0) ? im[(int64_t)h_high * q.W + w_low] : 0.f;
-      const float v4 = (h_high <= q.H - 1 && w_high <= q.W - 1) ? im[(int64_t)h_high * q.W + w_high] : 0.f;
-      const float col = (hh * hw_ * v1 + hh * lw * v2 + lh * hw_ * v3 + lh * lw * v4) * mask[((int64_t)n * q.dg * K + g * K + k) * hw + pix];
-      const float* gp = go + ((int64_t)n * q.O + o0) * hw + pix;
-#pragma unroll
-      for (int j = 0; j < OT; ++j)
-        if (o0 + j < q.O) acc[j] = fmaf(__ldg(gp + (int64_t)j * hw), col, acc[j]);
+  const int64_t total = (int64_t)q.N * hw * q.dg * K;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int k = (int)(i % K);
+    int64_t r = i / K;
+    const int g = (int)(r % q.dg);
+    const int64_t p = r / q.dg;                      // n * hw + pix
+    const int n = (int)(p / hw);
+    const int64_t pix = p - (int64_t)n * hw;
+    const int ho = (int)(pix / q.Wo), wo = (int)(pix - (int64_t)ho * q.Wo);
+    const int ki = k / q.kw, kj = k - ki * q.kw;
+    const int64_t off_c = ((int64_t)n * q.dg * K + g * K + k) * 2;
+    const float h_im = (float)(ho * q.sh - q.ph + ki * q.dh) + offset[off_c * hw + pix];
+    const float w_im = (float)(wo * q.sw - q.pw + kj * q.dw) + offset[(off_c + 1) * hw + pix];
+    float* dst = col + p * (int64_t)col_ld + (int64_t)g * cpg * K + k;
+    if (!(h_im > -1.f && w_im > -1.f && h_im < (float)q.H && w_im < (float)q.W)) {
+      for (int cc = 0; cc < cpg; ++cc) dst[cc * K] = 0.f;
+      continue;
     }
-    for (int j = 0; j < OT; ++j) {
-      if (o0 + j >= q.O) break;
-      red[threadIdx.x] = acc[j];
-      __syncthreads();
-      for (int st = 128; st > 0; st >>= 1) {
-        if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) g_w[((int64_t)(o0 + j) * q.C + c) * K + k] = red[0];
-      __syncthreads();
+    const float hf = floorf(h_im), wf = floorf(w_im);
+    const int h_low = (int)hf, w_low = (int)wf, h_high = h_low + 1, w_high = w_low + 1;
+    const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw_ = 1.f - lw;
+    const float m = mask[((int64_t)n * q.dg * K + g * K + k) * hw + pix];
+    const bool b1 = h_low >= 0 && w_low >= 0, b2 = h_low >= 0 && w_high <= q.W - 1, b3 = h_high <= q.H - 1 && w_low >= 0,
+               b4 = h_high <= q.H - 1 && w_high <= q.W - 1;
+    const float* im = input + ((int64_t)n * q.C + (int64_t)g * cpg) * HW;
+    for (int cc = 0; cc < cpg; ++cc, im += HW) {
+      const float v1 = b1 ? im[(int64_t)h_low * q.W + w_low] : 0.f;
+      const float v2 = b2 ? im[(int64_t)h_low * q.W + w_high] : 0.f;
+      const float v3 = b3 ? im[(int64_t)h_high * q.W + w_low] : 0.f;
+      const float v4 = b4 ? im[(int64_t)h_high * q.W + w_high] : 0.f;
+      dst[cc * K] = (hh * hw_ * v1 + hh * lw * v2 + lh * hw_ * v3 + lh * lw * v4) * m;
     }
   }
 }
@@ -193,9 +185,23 @@ __global__ void __launch_bounds__(256) dcn_bwd_bias_kernel(const float* __restri
 
 using namespace tdvc;
 
-extern "C" size_t tdvc_dcn_v2_backward_workspace_bytes(int N, int C, int H, int W) {
-  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
-  return (size_t)N * C * H * W * sizeof(long long) + 256;   // fixed-point grad_input + {max|go|, max|w|, scale, 1/scale}
+extern "C" size_t tdvc_conv2d_wgrad_workspace_bytes(int N, int Ho, int Wo, int cin, int cout, int k);
+extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, int N, int H, int W, int cin, int cout,
+                                 int k, int stride, int pad, int in_square, float* grad_w, float* grad_b_or_null, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+extern "C" int tdvc_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int dst_ld, void* stream);
+
+static size_t dcn_bwd_fixed_bytes(int N, int C, int H, int W) {
+  return ((size_t)N * C * H * W * sizeof(long long) + 256 + 255) / 256 * 256;   // fixed-point grad_input + {max|go|, max|w|, scale, 1/scale}
+}
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+
+// fixed-point grad_input | col rows [N*Ho*Wo][C*K] | channels-last grad_output | wgrad partial sums
+extern "C" size_t tdvc_dcn_v2_backward_workspace_bytes(int N, int C, int O, int H, int W, int Ho, int Wo, int K) {
+  if (N <= 0 || C <= 0 || O <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || K <= 0) return 0;
+  const size_t npos = (size_t)N * Ho * Wo;
+  return dcn_bwd_fixed_bytes(N, C, H, W) + align256(npos * ((C * K + 3) / 4 * 4) * sizeof(float)) + align256(npos * ((O + 3) / 4 * 4) * sizeof(float)) +
+         tdvc_conv2d_wgrad_workspace_bytes(N, Ho, Wo, C * K, O, 1);
 }
 
 extern "C" int tdvc_dcn_v2_backward(const float* input, const float* weight, const float* offset, const float* mask,
@@ -209,10 +215,10 @@ extern "C" int tdvc_dcn_v2_backward(const float* input, const float* weight, con
   TDVC_REQUIRE(kh > 0 && kw > 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && ph >= 0 && pw >= 0, "dcn_v2_backward: bad conv geometry");
   const int Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1, Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
   TDVC_REQUIRE(Ho > 0 && Wo > 0, "dcn_v2_backward: empty output");
-  TDVC_REQUIRE(workspace != nullptr && workspace_bytes >= tdvc_dcn_v2_backward_workspace_bytes(N, C, H, W) &&
-                   (reinterpret_cast<uintptr_t>(workspace) & 7) == 0,
-               "dcn_v2_backward: workspace too small or misaligned (%zu < %zu)", workspace_bytes,
-               tdvc_dcn_v2_backward_workspace_bytes(N, C, H, W));
+  const size_t need = tdvc_dcn_v2_backward_workspace_bytes(N, C, O, H, W, Ho, Wo, kh * kw);
+  TDVC_REQUIRE(workspace != nullptr && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+               "dcn_v2_backward: workspace too small or misaligned (%zu < %zu)", workspace_bytes, need);
+
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t n_in = (int64_t)N * C * H * W;
   long long* fx = static_cast<long long*>(workspace);
@@ -233,7 +239,21 @@ extern "C" int tdvc_dcn_v2_backward(const float* input, const float* weight, con
                                                                  scale, q);
   TDVC_CHECK_LAUNCH("dcn_bwd_sample");
   dcnb::dcn_bwd_finish_kernel<<<grid_for(n_in, 256), 256, 0, st>>>(fx, grad_input, n_in, scale);
-  dcnb::dcn_bwd_weight_kernel<<<C * kh * kw, 256, 0, st>>>(input, offset, mask, grad_output, grad_weight, q);
+  {
+    const size_t npos = (size_t)N * Ho * Wo;
+    const int K = kh * kw, Op = (O + 3) / 4 * 4, col_ld = (C * K + 3) / 4 * 4;   // (the row tails beyond C * K are never read)
+    char* base = static_cast<char*>(workspace) + dcn_bwd_fixed_bytes(N, C, H, W);
+    float* col = reinterpret_cast<float*>(base);
+    float* go_nhwc = reinterpret_cast<float*>(base + align256(npos * col_ld * sizeof(float)));
+    char* wws = reinterpret_cast<char*>(go_nhwc) + align256(npos * Op * sizeof(float));
+    dcnb::dcn_im2col_kernel<<<grid_for((int64_t)npos * dg * K, 256), 256, 0, st>>>(input, offset, mask, col, col_ld, q);
+    TDVC_CHECK_LAUNCH("dcn_im2col");
+    int rc = tdvc_nchw_to_nhwc(grad_output, go_nhwc, N, O, Ho, Wo, Op, st);
+    if (rc != TDVC_OK) return rc;
+    rc = tdvc_conv2d_wgrad(col, col_ld, go_nhwc, Op, N, Ho, Wo, C * K, O, 1, 1, 0, 0, grad_weight, nullptr, wws,
+                           tdvc_conv2d_wgrad_workspace_bytes(N, Ho, Wo, C * K, O, 1), st);
+    if (rc != TDVC_OK) return rc;
+  }
   dcnb::dcn_bwd_bias_kernel<<<O, 256, 0, st>>>(grad_output, grad_bias, N, O, (int64_t)Ho * Wo);
   TDVC_CHECK_LAUNCH("dcn_bwd");
   return TDVC_OK;

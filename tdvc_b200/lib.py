@@ -63,7 +63,7 @@ SIGNATURES = {
     "tdvc_conv2d_pack_f16": [C.POINTER(ConvParams), vp, vp],
     "tdvc_dcn_v2_workspace_bytes": [i32] * 6,
     "tdvc_dcn_v2_forward": [vp] * 6 + [i32] * 14 + [vp, sz, vp],
-    "tdvc_dcn_v2_backward_workspace_bytes": [i32] * 4,
+    "tdvc_dcn_v2_backward_workspace_bytes": [i32] * 8,
     "tdvc_dcn_v2_backward": [vp] * 10 + [i32] * 14 + [vp, sz, vp],
     "tdvc_dcn_nhwc": [C.POINTER(DcnParams), vp],
     "tdvc_dcn_f16_bytes": [i32],

@@ -78,7 +78,7 @@ def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, ke
     g_in, g_off, g_msk = torch.empty_like(input), torch.empty_like(offset), torch.empty_like(mask)
     g_w, g_b = torch.empty_like(weight), torch.empty(O, device=input.device, dtype=torch.float32)
     with torch.cuda.device(input.device):
-        nb = lib.tdvc_dcn_v2_backward_workspace_bytes(N, C, H, W)
+        nb = lib.tdvc_dcn_v2_backward_workspace_bytes(N, C, O, H, W, Ho, Wo, K)
         ws = torch.empty(nb // 8 + 1, device=input.device, dtype=torch.int64)
         st = torch.cuda.current_stream(input.device)
         rc = lib.tdvc_dcn_v2_backward(input.data_ptr(), weight.data_ptr(), offset.data_ptr(), mask.data_ptr(),
