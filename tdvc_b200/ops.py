@@ -166,9 +166,15 @@ def _launch_conv(x, cw, out, stride, act, slope, impl):
 
 
 def _nhwc(t):
-    """NCHW tensor -> channels-last Act with the channel count padded to a multiple of 4 (zeros)."""
+    """NCHW-shaped tensor -> channels-last Act.  A tensor that already lives in torch's channels_last memory format (what our
+    own functions return) with a channel count that is a multiple of 4 is wrapped WITHOUT a copy - the Act then aliases it and
+    must be treated as read-only; anything else goes through the layout kernel (channels padded to a multiple of 4 with zeros)."""
     from tdvc_b200.model import Act
     N, C, H, W = t.shape
+    if C % 4 == 0 and t.dtype == torch.float32 and t.is_contiguous(memory_format=torch.channels_last) and t.data_ptr() % 16 == 0:
+        v = t.permute(0, 2, 3, 1)
+        return Act(v, v.data_ptr(), N, H, W, C, C)
+    t = t.float().contiguous()
     a = Act.alloc(N, H, W, C, t.device, ld=(C + 3) // 4 * 4, zero=(C % 4 != 0))
     L.check(L.load().tdvc_nchw_to_nhwc(t.data_ptr(), a.ptr, N, C, H, W, a.ld, torch.cuda.current_stream(t.device).cuda_stream),
             "nchw_to_nhwc")
@@ -176,6 +182,9 @@ def _nhwc(t):
 
 
 def _nchw(a):
+    """Act -> NCHW-shaped tensor: a channels_last VIEW of the Act's buffer when it is dense (ld == C), a copy otherwise."""
+    if a.ld == a.C and a.t.dim() == 4 and a.t.data_ptr() == a.ptr and tuple(a.t.shape) == (a.N, a.H, a.W, a.C):
+        return a.t.permute(0, 3, 1, 2)
     out = torch.empty((a.N, a.C, a.H, a.W), device=a.t.device, dtype=torch.float32)
     L.check(L.load().tdvc_nhwc_to_nchw(a.ptr, a.ld, out.data_ptr(), a.N, a.C, a.H, a.W,
                                       torch.cuda.current_stream(a.t.device).cuda_stream), "nhwc_to_nchw")
@@ -199,7 +208,7 @@ class _Conv2d(torch.autograd.Function):
             raise RuntimeError("conv2d: padding must be (k - 1) / 2 (every convolution of the reference is)")
         Ho, Wo = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
         with torch.cuda.device(x.device):
-            xa = _nhwc(x.detach().contiguous())
+            xa = _nhwc(x.detach())
             cw = _packed(weight, bias, stride, padding, False)
             ya = Act.alloc(N, Ho, Wo, O, x.device, ld=(O + 3) // 4 * 4, zero=(O % 4 != 0))
             _launch_conv(xa, cw, ya, stride, _ACTS[act], slope, impl)
@@ -221,9 +230,11 @@ class _Conv2d(torch.autograd.Function):
         dev = gy.device
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
-            ga = _nhwc(gy.float().contiguous())
-            if act != L.ACT_NONE:   # g * f'(y), from the stored output
-                L.check(lib.tdvc_act_backward(ctx.ya.ptr, ga.ptr, ga.ptr, ga.N * ga.H * ga.W * ga.ld, act, slope, st), "act_backward")
+            ga = _nhwc(gy)
+            if act != L.ACT_NONE:   # g * f'(y), from the stored output (into a buffer of our own: `ga` may alias autograd's tensor)
+                gp = Act.alloc(ga.N, ga.H, ga.W, ga.C, dev, ld=ga.ld)
+                L.check(lib.tdvc_act_backward(ctx.ya.ptr, ga.ptr, gp.ptr, ga.N * ga.H * ga.W * ga.ld, act, slope, st), "act_backward")
+                ga = gp
             gx = gw = gb = None
             if ctx.needs_input_grad[0]:
                 cwt = _packed(weight, None, 1, k - 1 - padding, True)
@@ -290,7 +301,7 @@ class _GDN(torch.autograd.Function):
         if tuple(gamma.shape) != (C, C) or tuple(beta.shape) != (C,) or C % 4:
             raise RuntimeError(f"gdn: expected beta ({C},) and gamma ({C},{C}), channels a multiple of 4")
         with torch.cuda.device(x.device):
-            xa = _nhwc(x.detach().contiguous())
+            xa = _nhwc(x.detach())
             w4 = gamma.detach().reshape(C, C, 1, 1)
             cw = _packed(w4, beta.detach(), 1, 0, False)
             ya = Act.alloc(N, H, W, C, x.device)
@@ -311,7 +322,7 @@ class _GDN(torch.autograd.Function):
         n = N * H * W * C
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
-            ga = _nhwc(gy.float().contiguous())
+            ga = _nhwc(gy)
             norm = Act.alloc(N, H, W, C, dev)
             _launch_gdn(xa, cw, norm, inverse, True, impl, ctx.am)
             dxd, dn = Act.alloc(N, H, W, C, dev), Act.alloc(N, H, W, C, dev)
@@ -355,7 +366,7 @@ class _GcBits(torch.autograd.Function):
         lib = L.load()
         with torch.cuda.device(y.device):
             st = torch.cuda.current_stream(y.device).cuda_stream
-            ya, na = _nhwc(y.detach().contiguous()), _nhwc(noise.detach().contiguous())
+            ya, na = _nhwc(y.detach()), _nhwc(noise.detach())
             pa = _nhwc(torch.cat((scales.detach(), means.detach()), 1))   # (scales | means), the layout of the entropy-parameter output
             acc = torch.zeros(1, device=y.device, dtype=torch.float64)
             L.check(lib.tdvc_gc_bits_noise(ya.ptr, na.ptr, pa.ptr, pa.ld, N * H * W, C, acc.data_ptr(), st), "gc_bits_noise")
@@ -396,7 +407,7 @@ class _EbBits(torch.autograd.Function):
         lib = L.load()
         with torch.cuda.device(z.device):
             st = torch.cuda.current_stream(z.device).cuda_stream
-            za, na = _nhwc(z.detach().contiguous()), _nhwc(noise.detach().contiguous())
+            za, na = _nhwc(z.detach()), _nhwc(noise.detach())
             zt = Act.alloc(N, H, W, C, z.device)
             m, b, f = (t.detach().float().contiguous() for t in (mats, biases, factors))
             acc = torch.zeros(1, device=z.device, dtype=torch.float64)
@@ -422,7 +433,7 @@ class _EbBits(torch.autograd.Function):
             L.check(lib.tdvc_eb_bits_backward(zt.ptr, m.data_ptr(), b.data_ptr(), f.data_ptr(), g.data_ptr(), gz.ptr,
                                               gm.data_ptr(), gb.data_ptr(), gf.data_ptr(), N * H * W, C, st), "eb_bits_backward")
             if g_zt is not None:   # z~ = z + noise: what flows into z~ from its consumers flows into z unchanged
-                ga = _nhwc(g_zt.float().contiguous())
+                ga = _nhwc(g_zt)
                 L.check(lib.tdvc_axpby(gz.ptr, ga.ptr, gz.ptr, N * H * W * C, 1.0, 1.0, st), "axpby")
             return _nchw(gz), None, gm, gb, gf
 

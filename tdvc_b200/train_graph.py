@@ -201,17 +201,17 @@ def mcfilter(mf, pred, refer_frames):
     """reference LoopFilter (pnet.py:277-293) + Bottleneck3D (:309-317); frames are batched as (N * T, 64, H, W)."""
     r = refer_frames[:, 1:]
     n, m, _, h, w = r.shape
-    r = _cv(mf.conv02, _cv(mf.conv01, r.reshape(n * m, 3, h, w), "leaky_relu", 0.1)).view(n, m, 64, h, w)
+    r = _cv(mf.conv02, _cv(mf.conv01, r.reshape(n * m, 3, h, w), "leaky_relu", 0.1)).reshape(n, m, 64, h, w)
     T = m + 1
     x = torch.cat((r, pred.unsqueeze(1)), 1).reshape(n * T, 64, h, w)
     x = _cv3d(mf.conv1, x, "leaky_relu", 0.1)
     b3 = mf.layer1
-    out = _cv3d(b3.spatial_conv3d, _cv3d(b3.conv1, x, "leaky_relu", 0.1)).view(n, T, 64, h, w)
+    out = _cv3d(b3.spatial_conv3d, _cv3d(b3.conv1, x, "leaky_relu", 0.1)).reshape(n, T, 64, h, w)
     # temporal (3, 1, 1) kernel, stride 3, no bias: one output step from frames 0..2 = a 1x1 convolution of their channels
     wt = b3.temporal_conv3d.weight.squeeze(-1).squeeze(-1).permute(0, 2, 1).reshape(64, 192, 1, 1)
     tmp = ops.conv2d(out[:, :3].reshape(n, 192, h, w), wt, None, 1, 0)
     out = F.leaky_relu(out + tmp.unsqueeze(1), 0.1).reshape(n * T, 64, h, w)
-    x = (_cv3d(b3.conv3, out) + x).view(n, T * 64, h, w)
+    x = (_cv3d(b3.conv3, out) + x).reshape(n, T, 64, h, w).reshape(n, T * 64, h, w)
     x = _se(mf.attn, _cv(mf.feat_fusion, x, "leaky_relu", 0.1))
     return pred + x
 
