@@ -230,7 +230,7 @@ def training_leg(dev, world, steps, warmup, batch=8, size=256):
     losses = []
 
     def step():
-        out = model(x, refs, False)
+        out = model(x, refs, ENABLE_AMP)   # cfg/train.yaml `amp: True`
         mse = torch.nn.MSELoss()(out[0], x)
         loss = 2048 * mse + out[1].mean() + out[2].mean()
         aux = out[3] + out[4]

@@ -257,13 +257,16 @@ int tdvc_eb_bits_backward(const float* z_tilde, const float* mats, const float* 
  * zero_insert: out (N,H,W,C) <- g (N,Ho,Wo,C): out[n][oy*stride][ox*stride] = g[n][oy][ox], zero elsewhere (C % 4 == 0).
  * conv2d_wgrad: grad_w[cout][cin][k][k] (nn.Conv2d.weight layout) = sum_p x[p*stride + tap - pad][ci] * grad_y[p][co] and
  *   grad_b[co] = sum_p grad_y[p][co] (NULL: skipped); x (N,H,W,cin) / grad_y (N,Ho,Wo,cout) NHWC with leading dimensions;
- *   exact fp32, deterministic (fixed-order two-stage sum).  workspace: tdvc_conv2d_wgrad_workspace_bytes(N,Ho,Wo,cin,cout,k). */
+ *   warp-level TF32 MMAs over staged 32-pixel chunks, `products` = 3: fp32-class ((hi, lo) operand pairs, three products),
+ *   1: one TF32 product (what cuDNN runs by default for fp32 training convolutions; the reference's shipped cfg/train.yaml
+ *   trains under AMP, i.e. with fp16 products); deterministic (fixed-order two-stage sum).
+ *   workspace: tdvc_conv2d_wgrad_workspace_bytes(N,Ho,Wo,cin,cout,k). */
 int tdvc_act_backward(const float* y, const float* grad_y, float* grad_pre, int64_t n, int act, float slope, void* stream);
 int tdvc_zero_insert(const float* g, int g_ld, float* out, int out_ld, int N, int H, int W, int Ho, int Wo, int C, int stride,
                      void* stream);
 size_t tdvc_conv2d_wgrad_workspace_bytes(int N, int Ho, int Wo, int cin, int cout, int k);
 int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, int N, int H, int W, int cin, int cout, int k,
-                      int stride, int pad, int in_square, float* grad_w, float* grad_b_or_null, void* workspace,
+                      int stride, int pad, int in_square, int products, float* grad_w, float* grad_b_or_null, void* workspace,
                       size_t workspace_bytes, void* stream);
 /* GDN / IGDN backward (compressai GDN: out = x * norm^(-1/2), inverse: x * norm^(1/2), norm = beta + gamma . x^2), element-wise
  * parts on flat fp32 arrays (n % 4 == 0): pre -> dx_direct = g * norm^(-+1/2), dnorm = d loss / d norm; the 1x1 convolution's

@@ -114,6 +114,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 // are staged in shared memory and contracted with warp-level m16n8k8 TF32 MMAs, each fp32 operand split into a TF32 (hi, lo)
 // pair and three products issued (fp32-class accuracy: the weight gradient sums ~10^5..10^6 terms).  8 warps: warp w owns ci
 // rows 16 (w & 3) .. +16 and co columns 32 (w >> 2) .. +32 (four n-tiles).
+template <int PRODUCTS>
 __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
   __shared__ __align__(16) float xs[WG_P][WG_LD];
   __shared__ __align__(16) float gs[WG_P][WG_LD];
@@ -202,26 +203,40 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
     if (pc + WG_P < p_end) fetch(pc + WG_P, xr, gr);
 #pragma unroll
     for (int k0 = 0; k0 < WG_P; k0 += 8) {
-      // A fragment (16 ci x 8 pixels): element (row m, col k) = xs[k][m]
-      uint32_t ah[4], al[4];
-      tf32_split(xs[k0 + tq][m0 + gq], ah[0], al[0]);
-      tf32_split(xs[k0 + tq][m0 + gq + 8], ah[1], al[1]);
-      tf32_split(xs[k0 + tq + 4][m0 + gq], ah[2], al[2]);
-      tf32_split(xs[k0 + tq + 4][m0 + gq + 8], ah[3], al[3]);
-      // B fragments (8 pixels x 8 co each): element (row k, col n) = gs[k][n]
-      uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
+      // A fragment (16 ci x 8 pixels): element (row m, col k) = xs[k][m]; B fragments (8 pixels x 8 co): (row k, col n) = gs[k][n]
+      if (PRODUCTS == 1) {   // one TF32 product (what cuDNN runs by default for fp32 training convolutions)
+        uint32_t af[4], lo_;
+        tf32_split(xs[k0 + tq][m0 + gq], af[0], lo_);
+        tf32_split(xs[k0 + tq][m0 + gq + 8], af[1], lo_);
+        tf32_split(xs[k0 + tq + 4][m0 + gq], af[2], lo_);
+        tf32_split(xs[k0 + tq + 4][m0 + gq + 8], af[3], lo_);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        tf32_split(gs[k0 + tq][n0 + 8 * nt + gq], bh0[nt], bl0[nt]);
-        tf32_split(gs[k0 + tq + 4][n0 + 8 * nt + gq], bh1[nt], bl1[nt]);
+        for (int nt = 0; nt < 4; ++nt) {
+          uint32_t b0, b1;
+          tf32_split(gs[k0 + tq][n0 + 8 * nt + gq], b0, lo_);
+          tf32_split(gs[k0 + tq + 4][n0 + 8 * nt + gq], b1, lo_);
+          mma_tf32(acc[nt], af, b0, b1);
+        }
+      } else {
+        uint32_t ah[4], al[4];
+        tf32_split(xs[k0 + tq][m0 + gq], ah[0], al[0]);
+        tf32_split(xs[k0 + tq][m0 + gq + 8], ah[1], al[1]);
+        tf32_split(xs[k0 + tq + 4][m0 + gq], ah[2], al[2]);
+        tf32_split(xs[k0 + tq + 4][m0 + gq + 8], ah[3], al[3]);
+        uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          tf32_split(gs[k0 + tq][n0 + 8 * nt + gq], bh0[nt], bl0[nt]);
+          tf32_split(gs[k0 + tq + 4][n0 + 8 * nt + gq], bh1[nt], bl1[nt]);
+        }
+        // consecutive MMAs go to different accumulators (an accumulator's three products are 4 issues apart)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], al, bh0[nt], bh1[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], ah, bl0[nt], bl1[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], ah, bh0[nt], bh1[nt]);
       }
-      // consecutive MMAs go to different accumulators (an accumulator's three products are 4 issues apart)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], al, bh0[nt], bh1[nt]);
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], ah, bl0[nt], bl1[nt]);
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], ah, bh0[nt], bh1[nt]);
     }
     if (do_bias) {
 #pragma unroll 8
@@ -310,8 +325,9 @@ extern "C" size_t tdvc_conv2d_wgrad_workspace_bytes(int N, int Ho, int Wo, int c
 }
 
 extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, int N, int H, int W, int cin, int cout,
-                                 int k, int stride, int pad, int in_square, float* grad_w, float* grad_b_or_null, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
+                                 int k, int stride, int pad, int in_square, int products, float* grad_w, float* grad_b_or_null,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  TDVC_REQUIRE(products == 1 || products == 3, "conv2d_wgrad: products must be 1 (TF32) or 3 (fp32-class TF32 split)");
   TDVC_REQUIRE(x && grad_y && grad_w && N > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "conv2d_wgrad: bad args");
   TDVC_REQUIRE(k >= 1 && k <= 7 && stride >= 1 && pad >= 0, "conv2d_wgrad: k=%d stride=%d pad=%d", k, stride, pad);
   TDVC_REQUIRE(x_ld >= cin && g_ld >= cout && x_ld % 4 == 0 && g_ld % 4 == 0, "conv2d_wgrad: leading dimensions");
@@ -330,7 +346,8 @@ extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, 
   a.part = (float*)workspace;
   a.part_bias = a.part + (size_t)a.S * k * k * cin * cout;
   cudaStream_t st = (cudaStream_t)stream;
-  wgrad_kernel<<<dim3(tiles, a.S), 256, 0, st>>>(a);
+  if (products == 1) wgrad_kernel<1><<<dim3(tiles, a.S), 256, 0, st>>>(a);
+  else wgrad_kernel<3><<<dim3(tiles, a.S), 256, 0, st>>>(a);
   TDVC_CHECK_LAUNCH("conv2d_wgrad");
   const int64_t n_out = (int64_t)k * k * cin * cout + cout;
   wgrad_reduce_kernel<<<cdiv(n_out, 256), 256, 0, st>>>(a.part, a.part_bias, a.S, k * k, cin, cout, grad_w, grad_b_or_null);

@@ -187,8 +187,8 @@ using namespace tdvc;
 
 extern "C" size_t tdvc_conv2d_wgrad_workspace_bytes(int N, int Ho, int Wo, int cin, int cout, int k);
 extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, int N, int H, int W, int cin, int cout,
-                                 int k, int stride, int pad, int in_square, float* grad_w, float* grad_b_or_null, void* workspace,
-                                 size_t workspace_bytes, void* stream);
+                                 int k, int stride, int pad, int in_square, int products, float* grad_w, float* grad_b_or_null,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 extern "C" int tdvc_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int dst_ld, void* stream);
 
 static size_t dcn_bwd_fixed_bytes(int N, int C, int H, int W) {
@@ -250,7 +250,7 @@ extern "C" int tdvc_dcn_v2_backward(const float* input, const float* weight, con
     TDVC_CHECK_LAUNCH("dcn_im2col");
     int rc = tdvc_nchw_to_nhwc(grad_output, go_nhwc, N, O, Ho, Wo, Op, st);
     if (rc != TDVC_OK) return rc;
-    rc = tdvc_conv2d_wgrad(col, col_ld, go_nhwc, Op, N, Ho, Wo, C * K, O, 1, 1, 0, 0, grad_weight, nullptr, wws,
+    rc = tdvc_conv2d_wgrad(col, col_ld, go_nhwc, Op, N, Ho, Wo, C * K, O, 1, 1, 0, 0, 3, grad_weight, nullptr, wws,
                            tdvc_conv2d_wgrad_workspace_bytes(N, Ho, Wo, C * K, O, 1), st);
     if (rc != TDVC_OK) return rc;
   }

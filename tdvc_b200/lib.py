@@ -94,7 +94,7 @@ SIGNATURES = {
     "tdvc_act_backward": [vp, vp, vp, i64, i32, f32, vp],
     "tdvc_zero_insert": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "tdvc_conv2d_wgrad_workspace_bytes": [i32] * 6,
-    "tdvc_conv2d_wgrad": [vp, i32, vp, i32] + [i32] * 9 + [vp, vp, vp, sz, vp],
+    "tdvc_conv2d_wgrad": [vp, i32, vp, i32] + [i32] * 10 + [vp, vp, vp, sz, vp],
     "tdvc_gdn_backward_pre": [vp, vp, vp, vp, vp, i64, i32, vp],
     "tdvc_gdn_backward_post": [vp, vp, vp, vp, i64, vp],
     "tdvc_pmf_to_quantized_cdf": [vp, i32, i32, vp],

@@ -1450,7 +1450,7 @@ class VideoCompressor(nn.Module):
                 raise RuntimeError("is_compress=True is served in eval() mode (the reference switches both coders to eval() "
                                    "before it codes, pnet.py:46,70)")
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-                return self._forward_training_autograd(input_image, refer_frames)
+                return self._forward_training_autograd(input_image, refer_frames, enabled_amp=enabled_amp)
             return self._forward_training(input_image, refer_frames, taps, noise=None)
         N, H, W = self._check(input_image, refer_frames, 3)
         dev = input_image.device
@@ -1535,18 +1535,25 @@ class VideoCompressor(nn.Module):
             res_aux = _AuxLoss.apply(self.resCoder.entropy_bottleneck.quantiles, aux[1], Wt["rs.eb"])
         return recon, bpp[1:2], bpp[0:1], mv_aux, res_aux
 
-    def _forward_training_autograd(self, input_image, refer_frames, noise=None):
+    def _forward_training_autograd(self, input_image, refer_frames, noise=None, enabled_amp=False):
         """`self.training` with gradients enabled: the same forward built from the autograd functions of `tdvc_b200.ops`
         (tdvc_b200/train_graph.py), so that the reference's training step - `rd_loss.backward()`, gradient clipping, the two
         Adam steps, `aux_loss.backward()` (tools/train.py:125-159) - runs on this module.  Returns the 5-tuple of pnet.py:80-81;
-        every output carries its graph.  noise: as `_forward_training` (None: drawn on the device)."""
+        every output carries its graph.  noise: as `_forward_training` (None: drawn on the device).  enabled_amp (the reference
+        then trains with fp16 autocast products outside the coders, cfg/train.yaml `amp: True`): the weight-gradient MMAs use one
+        TF32 product instead of the fp32-class three; forward and grad_input keep fp32-class accuracy either way."""
         self._check(input_image, refer_frames, 3)
         from tdvc_b200 import train_graph
         dev = input_image.device
         with torch.cuda.device(dev):
             x = input_image.float().contiguous()
             refs = refer_frames.float().contiguous()
-            recon, bpp_res, bpp_mv, ind = train_graph.forward(self, x, refs, noise)
+            from tdvc_b200 import ops
+            saved, ops.WGRAD_PRODUCTS = ops.WGRAD_PRODUCTS, (1 if enabled_amp else 3)
+            try:
+                recon, bpp_res, bpp_mv, ind = train_graph.forward(self, x, refs, noise)
+            finally:
+                ops.WGRAD_PRODUCTS = saved
             self.last_ind = ind
             aux = []
             lib = L.load()

@@ -121,6 +121,11 @@ dcn_v2_conv = _DCNv2.apply
 
 
 # ----------------------------------------------------------------------------------------------- conv2d with autograd
+# fp16 / TF32 products of the weight-gradient MMAs: 3 = fp32-class (default), 1 = one TF32 product.  `VideoCompressor` sets it
+# from the reference's own switch for the duration of a training forward (`enabled_amp=True`, the shipped cfg/train.yaml: the
+# reference then trains with fp16 autocast products); every function captures the value at forward time.
+WGRAD_PRODUCTS = 3
+
 _ACTS = {None: L.ACT_NONE, "none": L.ACT_NONE, "relu": L.ACT_RELU, "leaky_relu": L.ACT_LRELU, "clamp01": L.ACT_CLAMP01}
 _PACKS = {}
 
@@ -214,6 +219,7 @@ class _Conv2d(torch.autograd.Function):
             _launch_conv(xa, cw, ya, stride, _ACTS[act], slope, impl)
             y = _nchw(ya)
         ctx.geom = (stride, padding, _ACTS[act], slope, impl, bias is not None)
+        ctx.wg_products = WGRAD_PRODUCTS
         ctx.xa, ctx.ya = xa, (ya if _ACTS[act] != L.ACT_NONE else None)
         ctx.save_for_backward(weight)
         return y
@@ -253,7 +259,7 @@ class _Conv2d(torch.autograd.Function):
                 nb = lib.tdvc_conv2d_wgrad_workspace_bytes(xa.N, ga.H, ga.W, C, O, k)
                 ws = torch.empty((nb + 3) // 4, device=dev, dtype=torch.float32)
                 L.check(lib.tdvc_conv2d_wgrad(xa.ptr, xa.ld, ga.ptr, ga.ld, xa.N, xa.H, xa.W, C, O, k, stride, padding, 0,
-                                              gw.data_ptr(), gb.data_ptr() if gb is not None else None, ws.data_ptr(), nb, st),
+                                              ctx.wg_products, gw.data_ptr(), gb.data_ptr() if gb is not None else None, ws.data_ptr(), nb, st),
                         "conv2d_wgrad")
         return gx, gw, gb, None, None, None, None, None
 
@@ -309,6 +315,7 @@ class _GDN(torch.autograd.Function):
             _launch_gdn(xa, cw, ya, inverse, False, impl, am)
             y = _nchw(ya)
         ctx.xa, ctx.cw, ctx.w4, ctx.inverse, ctx.impl, ctx.am = xa, cw, w4, inverse, impl, am
+        ctx.wg_products = WGRAD_PRODUCTS
         return y
 
     @staticmethod
@@ -336,7 +343,7 @@ class _GDN(torch.autograd.Function):
             gb = torch.empty(C, device=dev, dtype=torch.float32)
             nb = lib.tdvc_conv2d_wgrad_workspace_bytes(N, H, W, C, C, 1)
             ws = torch.empty((nb + 3) // 4, device=dev, dtype=torch.float32)
-            L.check(lib.tdvc_conv2d_wgrad(xa.ptr, xa.ld, dn.ptr, dn.ld, N, H, W, C, C, 1, 1, 0, 1, gw.data_ptr(), gb.data_ptr(),
+            L.check(lib.tdvc_conv2d_wgrad(xa.ptr, xa.ld, dn.ptr, dn.ld, N, H, W, C, C, 1, 1, 0, 1, ctx.wg_products, gw.data_ptr(), gb.data_ptr(),
                                           ws.data_ptr(), nb, st), "conv2d_wgrad (gdn)")
         return gx, gb, gw.view(C, C), None, None
 

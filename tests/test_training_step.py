@@ -33,10 +33,13 @@ def _rd_loss(out, x):
     return 2048 * mse + out[1].mean() + out[2].mean(), mse     # tools/train.py:132-140, train_lambda 2048
 
 
-@pytest.mark.parametrize("case", [(2, 64, 64, 91), (1, 128, 192, 92)])
+@pytest.mark.parametrize("case", [(2, 64, 64, 91, False), (1, 128, 192, 92, False), (2, 64, 64, 91, True)],
+                         ids=["2x64x64", "1x128x192", "2x64x64-amp"])
 def test_rd_loss_backward_vs_oracle(oracle_model, case):
+    """amp: `enabled_amp=True` (the reference's shipped cfg/train.yaml) - one TF32 product in the weight-gradient MMAs - is held
+    to the same bars against the oracle's fp32 gradients."""
     from tdvc_b200 import synth
-    N, H, W, seed = case
+    N, H, W, seed, amp = case
     dev = torch.device("cuda:0")
     orc, net = _build(oracle_model, dev)
     xs, rs = zip(*[synth.make_frame_pair(H, W, seed=seed + i) for i in range(N)])
@@ -47,7 +50,7 @@ def test_rd_loss_backward_vs_oracle(oracle_model, case):
     lw.backward()
     torch.manual_seed(77)
     noise = {k: v.to(dev) for k, v in _noise(N, H, W).items()}
-    got = net._forward_training_autograd(x.to(dev), refs.to(dev), noise=noise)
+    got = net._forward_training_autograd(x.to(dev), refs.to(dev), noise=noise, enabled_amp=amp)
     lg, _ = _rd_loss(got, x.to(dev))
     lg.backward()
     assert (want[0] - got[0].detach().cpu()).abs().max().item() <= 1e-3

@@ -7,6 +7,7 @@ sys.path.insert(0, ".")
 from tdvc_b200 import lib as L
 
 N, C, O, k, H, W = (int(a) for a in sys.argv[1:7]) if len(sys.argv) > 6 else (8, 64, 64, 3, 256, 256)
+PR = int(sys.argv[7]) if len(sys.argv) > 7 else 3
 dev = torch.device("cuda:0")
 lib = L.load()
 x = torch.randn(N, H, W, C, device=dev)
@@ -19,7 +20,7 @@ st = torch.cuda.current_stream(dev).cuda_stream
 for rep in range(4):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    L.check(lib.tdvc_conv2d_wgrad(x.data_ptr(), C, g.data_ptr(), O, N, H, W, C, O, k, 1, k // 2, 0, gw.data_ptr(), gb.data_ptr(),
+    L.check(lib.tdvc_conv2d_wgrad(x.data_ptr(), C, g.data_ptr(), O, N, H, W, C, O, k, 1, k // 2, 0, PR, gw.data_ptr(), gb.data_ptr(),
                                   ws.data_ptr(), nb, st), "wgrad")
     b.record()
     torch.cuda.synchronize()
