@@ -200,6 +200,62 @@ def gpu_eager_baseline(dev, hh, ww, iters=3):
     return out
 
 
+def gpu_eager_training_baseline(dev, batch=8, size=256, iters=3):
+    """The same training step on the PyTorch restatement of the reference (oracle/model.py, cuDNN + torchvision deformable
+    convolution, torch autograd) run EAGERLY on this GPU: exact fp32, TF32 convolutions (PyTorch's default), autocast fp16 (the
+    reference's shipped cfg/train.yaml).  A reported baseline."""
+    import torch
+    from oracle.stats import build_oracle
+    from tdvc_b200 import synth
+    out = {}
+    try:
+        pairs = [synth.make_frame_pair(size, size, seed=500 + i) for i in range(batch)]
+        x = torch.cat([p[0] for p in pairs]).to(dev)
+        refs = torch.cat([p[1] for p in pairs]).to(dev)
+        tf0, tf1 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        for name, tf32, amp in (("fp32", False, False), ("tf32", True, False), ("autocast_fp16", True, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            orc = build_oracle().to(dev).train()
+            params = [p for n, p in orc.named_parameters() if not n.endswith(".quantiles")]
+            aux_params = [p for n, p in orc.named_parameters() if n.endswith(".quantiles")]
+            opt, aux_opt = torch.optim.Adam(params, lr=1e-4), torch.optim.Adam(aux_params, lr=1e-3)
+            scaler = torch.amp.GradScaler("cuda", enabled=amp)
+
+            def step():
+                with torch.autocast("cuda", enabled=amp):
+                    o = orc(x, refs, amp)
+                    mse = torch.nn.MSELoss()(o[0], x)
+                loss = 2048 * mse + o[1].mean() + o[2].mean()
+                opt.zero_grad()
+                aux_opt.zero_grad()
+                scaler.scale(loss).backward()
+                scaler.unscale_(opt)
+                torch.nn.utils.clip_grad_norm_(params, 2)
+                scaler.step(opt)
+                scaler.update()
+                (o[3] + o[4]).backward()
+                aux_opt.step()
+
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            out[name] = {"ms_per_step": ms, "samples_per_s": batch * 1000.0 / ms}
+            del orc, opt, aux_opt
+            torch.cuda.empty_cache()
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf0, tf1
+        out["what"] = "oracle/model.py training step in PyTorch eager mode on this GPU (cuDNN, torchvision deform_conv2d autograd)"
+    except Exception as e:
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    return out
+
+
 def training_leg(dev, world, steps, warmup, batch=8, size=256):
     """BASELINE config 4: one training step of reference tools/train.py:125-159 (enable_amp False branch) - forward, rd_loss
     (2048 * MSE + bpp_res + bpp_mv), backward, clip_grad_norm_(2), Adam step, aux_loss backward, aux Adam step - on a
@@ -311,6 +367,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))   # a hang must fail fast
     if args.workload == "train":
         rec = training_leg(dev, world, max(1, min(args.steps, 8)), max(args.warmup, 3))
+        if rank == 0 and world == 1 and not args.no_eager_baseline:
+            torch.cuda.empty_cache()
+            rec["gpu_eager_baseline"] = gpu_eager_training_baseline(dev)
         if rank == 0:
             print(json.dumps({"metric": "training samples/sec (256x256 Vimeo-shaped, batch 8 per GPU)", "value": rec["samples_per_s"],
                               "unit": "samples/s", "n_gpus": world, "steps": rec["steps"], "warmup": rec["warmup"],
@@ -552,6 +611,8 @@ def main():
             except Exception as e:
                 train = {"error": f"{type(e).__name__}: {e}"[:300]}
             torch.cuda.empty_cache()
+            if not args.no_eager_baseline and "error" not in train:
+                train["gpu_eager_baseline"] = gpu_eager_training_baseline(dev)
         eager = None
         if not args.no_eager_baseline and world == 1:
             eager = gpu_eager_baseline(dev, hh, ww)
