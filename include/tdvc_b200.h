@@ -275,6 +275,15 @@ int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, i
 int tdvc_gdn_backward_pre(const float* x, const float* norm, const float* grad_out, float* dx_direct, float* dnorm, int64_t n,
                           int inverse, void* stream);
 int tdvc_gdn_backward_post(const float* dx_direct, const float* x, const float* dxsq, float* dx, int64_t n, void* stream);
+/* Per-(image, channel) pieces of the squeeze-excitation layer in training (reference inflate.py:159-208), dense NHWC rows
+ * (C % 4 == 0): chan_affine: out[n][p][c] = a[n][p][c] * s[n][c] + t[n][c] (a NULL: out = s broadcast; t may be NULL) - the
+ * gated product, its grad_input, and the backward of the spatial mean; chan_dot: out[n][c] = scale * sum_p a * b (b NULL:
+ * plain sums) - the mean and the gate's gradient, two fixed-order stages (deterministic).                                   */
+int tdvc_chan_affine(const float* a_or_null, const float* s, const float* t_or_null, float* out, int N, int64_t HW, int C,
+                     void* stream);
+size_t tdvc_chan_dot_workspace_bytes(int N, int64_t HW, int C);
+int tdvc_chan_dot(const float* a, const float* b_or_null, float* out, int N, int64_t HW, int C, float scale, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* ---- real entropy coding (`is_compress=True`: reference pnet.py:45-49,69-73 -> compressai `update(force=True)` and
  * `compress()`; compressai is not in the reference tree, SURVEY App. A / DESIGN.md section 7) ----

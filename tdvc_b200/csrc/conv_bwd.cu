@@ -84,6 +84,73 @@ __global__ void gdn_bwd_post_kernel(const float* __restrict__ dx_direct, const f
   }
 }
 
+// ---- per-(image, channel) pieces of the squeeze-excitation layer in training (reference inflate.py:159-208):
+// chan_affine: out[n][p][c] = a[n][p][c] * s[n][c] + t[n][c]   (a == nullptr: out = s broadcast; t may be nullptr).
+//   forward of x * gate, its grad_input (g * gate), and the backward of the spatial mean (a broadcast).
+// chan_dot: out[n][c] = sum_p a[n][p][c] * b[n][p][c]  (b == nullptr: plain sums): the mean and the gate's gradient; two stages,
+//   fixed order: deterministic.  NHWC, dense rows of C channels (C % 4 == 0).
+__global__ void chan_affine_kernel(const float* __restrict__ a, const float* __restrict__ s, const float* __restrict__ t,
+                                   float* __restrict__ out, int64_t HW, int C4) {
+  const int n = blockIdx.y;
+  const int64_t total = HW * C4;
+  const float4* a4 = a != nullptr ? reinterpret_cast<const float4*>(a) + (int64_t)n * total : nullptr;
+  const float4* s4 = reinterpret_cast<const float4*>(s) + (int64_t)n * C4;
+  const float4* t4 = t != nullptr ? reinterpret_cast<const float4*>(t) + (int64_t)n * C4 : nullptr;
+  float4* o4 = reinterpret_cast<float4*>(out) + (int64_t)n * total;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    float4 v = __ldg(s4 + c);
+    if (a4 != nullptr) {
+      const float4 x = __ldg(a4 + i);
+      v = make_float4(x.x * v.x, x.y * v.y, x.z * v.z, x.w * v.w);
+    }
+    if (t4 != nullptr) {
+      const float4 y = __ldg(t4 + c);
+      v = make_float4(v.x + y.x, v.y + y.y, v.z + y.z, v.w + y.w);
+    }
+    o4[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) chan_dot_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t HW,
+                                                               int C4, float* __restrict__ partial) {
+  extern __shared__ float4 cd_sh[];
+  const int lanes_p = 256 / C4;
+  const int c = threadIdx.x % C4, pl = threadIdx.x / C4;
+  const int n = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int64_t chunk = (HW + nblk - 1) / nblk;
+  const int64_t p0 = (int64_t)blk * chunk, p1 = p0 + chunk < HW ? p0 + chunk : HW;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pl < lanes_p) {
+    const float4* a4 = reinterpret_cast<const float4*>(a) + (int64_t)n * HW * C4 + c;
+    const float4* b4 = b != nullptr ? reinterpret_cast<const float4*>(b) + (int64_t)n * HW * C4 + c : nullptr;
+    for (int64_t p = p0 + pl; p < p1; p += lanes_p) {
+      float4 x = __ldg(a4 + p * C4);
+      if (b4 != nullptr) {
+        const float4 y = __ldg(b4 + p * C4);
+        x = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
+      }
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+  }
+  cd_sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (pl == 0) {
+    for (int j = 1; j < lanes_p; ++j) {
+      const float4 v = cd_sh[j * C4 + c];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(partial)[((int64_t)blk * gridDim.y + n) * C4 + c] = acc;
+  }
+}
+__global__ void chan_dot_finish_kernel(const float* __restrict__ partial, int nblk, int NC, float scale, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  float v = 0.f;
+  for (int b = 0; b < nblk; ++b) v += partial[(int64_t)b * NC + i];
+  out[i] = v * scale;
+}
+
 constexpr int WG_T = 64;      // ci x co tile of a CTA
 constexpr int WG_P = 32;      // output pixels per staged chunk
 constexpr int WG_LD = WG_T + 8;   // row pitch = 8 banks: the (k = lane & 3, m = lane >> 2) fragment reads are conflict-free
@@ -371,5 +438,36 @@ extern "C" int tdvc_gdn_backward_post(const float* dx_direct, const float* x, co
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   gdn_bwd_post_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dx_direct, x, dxsq, dx, n / 4);
   TDVC_CHECK_LAUNCH("gdn_backward_post");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_chan_affine(const float* a_or_null, const float* s, const float* t_or_null, float* out, int N, int64_t HW, int C,
+                                void* stream) {
+  TDVC_REQUIRE(s && out && N > 0 && HW > 0 && C > 0 && C % 4 == 0, "chan_affine: bad args");
+  int gx = cdiv(HW * (C / 4), 256);
+  if (gx > kNumSMs * 8) gx = kNumSMs * 8;
+  chan_affine_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>(a_or_null, s, t_or_null, out, HW, C / 4);
+  TDVC_CHECK_LAUNCH("chan_affine");
+  return TDVC_OK;
+}
+
+extern "C" size_t tdvc_chan_dot_workspace_bytes(int N, int64_t HW, int C) {
+  if (N <= 0 || HW <= 0 || C <= 0) return 0;
+  int64_t nblk = HW / 64;
+  nblk = nblk < 1 ? 1 : (nblk > 296 ? 296 : nblk);
+  return (size_t)nblk * N * C * sizeof(float);
+}
+
+extern "C" int tdvc_chan_dot(const float* a, const float* b_or_null, float* out, int N, int64_t HW, int C, float scale,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  TDVC_REQUIRE(a && out && N > 0 && HW > 0 && C > 0 && C % 4 == 0 && C <= 1024, "chan_dot: bad args");
+  const size_t need = tdvc_chan_dot_workspace_bytes(N, HW, C);
+  TDVC_REQUIRE(workspace && workspace_bytes >= need, "chan_dot: workspace of %zu bytes, %zu needed", workspace_bytes, need);
+  const int nblk = (int)(need / ((size_t)N * C * sizeof(float)));
+  cudaStream_t st = (cudaStream_t)stream;
+  chan_dot_partial_kernel<<<dim3(nblk, N), 256, 256 * sizeof(float4), st>>>(a, b_or_null, HW, C / 4, (float*)workspace);
+  TDVC_CHECK_LAUNCH("chan_dot");
+  chan_dot_finish_kernel<<<cdiv((int64_t)N * C, 256), 256, 0, st>>>((const float*)workspace, nblk, N * C, scale, out);
+  TDVC_CHECK_LAUNCH("chan_dot_finish");
   return TDVC_OK;
 }

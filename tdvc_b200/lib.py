@@ -97,6 +97,9 @@ SIGNATURES = {
     "tdvc_conv2d_wgrad": [vp, i32, vp, i32] + [i32] * 10 + [vp, vp, vp, sz, vp],
     "tdvc_gdn_backward_pre": [vp, vp, vp, vp, vp, i64, i32, vp],
     "tdvc_gdn_backward_post": [vp, vp, vp, vp, i64, vp],
+    "tdvc_chan_affine": [vp, vp, vp, vp, i32, i64, i32, vp],
+    "tdvc_chan_dot_workspace_bytes": [i32, i64, i32],
+    "tdvc_chan_dot": [vp, vp, vp, i32, i64, i32, f32, vp, sz, vp],
     "tdvc_pmf_to_quantized_cdf": [vp, i32, i32, vp],
     "tdvc_eb_symbols": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
     "tdvc_ar_code_workspace_bytes": [i32, i32, i32],
@@ -137,6 +140,7 @@ def load():
     lib.tdvc_dcn_f16_bytes.restype = C.c_size_t
     lib.tdvc_ar_code_workspace_bytes.restype = C.c_size_t
     lib.tdvc_conv2d_wgrad_workspace_bytes.restype = C.c_size_t
+    lib.tdvc_chan_dot_workspace_bytes.restype = C.c_size_t
     lib.tdvc_rans_encode_with_indexes.restype = C.c_int64
     _lib = lib
     return lib

@@ -455,3 +455,79 @@ def entropy_bottleneck_bits(z, noise, matrices, biases, factors):
     b = torch.cat([t.reshape(C, -1) for t in biases], 1)
     f = torch.cat([torch.tanh(t).reshape(C, -1) for t in factors], 1)
     return _EbBits.apply(z, noise, m, b, f)
+
+
+# ----------------------------------------------------------------------------------------------- squeeze-excitation pieces
+def _chan_dot(a, b, scale):
+    """(N, C) = scale * sum over pixels of a * b (b None: of a); Acts with dense rows."""
+    lib = L.load()
+    dev = a.t.device
+    out = torch.empty((a.N, a.C), device=dev, dtype=torch.float32)
+    nb = lib.tdvc_chan_dot_workspace_bytes(a.N, a.H * a.W, a.C)
+    ws = torch.empty((nb + 3) // 4, device=dev, dtype=torch.float32)
+    L.check(lib.tdvc_chan_dot(a.ptr, b.ptr if b is not None else None, out.data_ptr(), a.N, a.H * a.W, a.C, scale, ws.data_ptr(), nb,
+                              torch.cuda.current_stream(dev).cuda_stream), "chan_dot")
+    return out
+
+
+def _chan_affine(a, s, t, like):
+    """Act out[n][p][c] = a * s[n][c] + t[n][c] (a / t may be None); `like` gives the shape."""
+    from tdvc_b200.model import Act
+    lib = L.load()
+    dev = like.t.device
+    out = Act.alloc(like.N, like.H, like.W, like.C, dev)
+    L.check(lib.tdvc_chan_affine(a.ptr if a is not None else None, s.data_ptr(), t.data_ptr() if t is not None else None, out.ptr,
+                                 like.N, like.H * like.W, like.C, torch.cuda.current_stream(dev).cuda_stream), "chan_affine")
+    return out
+
+
+def _dense(t):
+    a = _nhwc(t)
+    if a.ld != a.C:
+        raise RuntimeError("channel count must be a multiple of 4")
+    return a
+
+
+class _ChannelMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        with torch.cuda.device(x.device):
+            xa = _dense(x.detach())
+            ctx.like = xa
+            return _chan_dot(xa, None, 1.0 / (xa.H * xa.W))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        like = ctx.like
+        with torch.cuda.device(g.device):
+            s = (g.float() * (1.0 / (like.H * like.W))).contiguous()
+            return _nchw(_chan_affine(None, s, None, like))
+
+
+class _ChannelScale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s):
+        with torch.cuda.device(x.device):
+            xa = _dense(x.detach())
+            sc = s.detach().float().contiguous()
+            ctx.t = (xa, sc)
+            return _nchw(_chan_affine(xa, sc, None, xa))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        xa, sc = ctx.t
+        with torch.cuda.device(g.device):
+            ga = _dense(g)
+            return _nchw(_chan_affine(ga, sc, None, xa)), _chan_dot(ga, xa, 1.0)
+
+
+def channel_mean(x):
+    """(N, C, H, W) -> (N, C): the spatial mean (adaptive_avg_pool2d(x, 1)), with autograd; deterministic two-stage sum."""
+    return _ChannelMean.apply(x)
+
+
+def channel_scale(x, s):
+    """x * s[:, :, None, None] for s of shape (N, C), with autograd to both (the gated product of a squeeze-excitation layer)."""
+    return _ChannelScale.apply(x, s)

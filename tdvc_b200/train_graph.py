@@ -48,13 +48,14 @@ def _res_stack(stack, x):
 
 
 def _se(m, x):
-    """Squeeze-excitation (reference inflate.py:159-208): the gate MLP acts on N x C numbers."""
+    """Squeeze-excitation (reference inflate.py:159-208): spatial mean and gated product on our kernels; the gate MLP acts on
+    N x C numbers."""
     w1, w2 = m.conv1.conv.weight, m.conv2.conv.weight
-    s = x.mean((2, 3))                                                  # (N, C)
+    s = ops.channel_mean(x)                                             # (N, C)
     # (F.linear, not F.conv2d: cuDNN convolutions default to TF32, which would put 1e-3 into every gate)
     s = F.relu(F.linear(s, w1.view(w1.shape[0], -1), m.conv1.conv.bias))
     s = torch.sigmoid(F.linear(s, w2.view(w2.shape[0], -1), m.conv2.conv.bias))
-    return x * s[:, :, None, None]
+    return ops.channel_scale(x, s)
 
 
 class _LowerBound(torch.autograd.Function):

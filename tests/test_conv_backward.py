@@ -210,3 +210,24 @@ def test_entropy_bottleneck_bits_backward_vs_oracle_fp64():
             a = a.cpu().double()
             err = (a - r).abs().max().item()
             assert err <= 1e-3 * max(r.abs().max().item(), 1e-6), (name, gs, err, r.abs().max().item())
+
+
+def test_channel_mean_and_scale_vs_torch():
+    """The squeeze-excitation pieces (reference inflate.py:159-208): spatial mean and gated product, forward and backward."""
+    from tdvc_b200 import ops
+    dev = torch.device("cuda:0")
+    torch.manual_seed(41)
+    x = torch.randn(2, 128, 24, 40, device=dev)
+    s = torch.rand(2, 128, device=dev)
+    gm, gy = torch.randn(2, 128, device=dev), torch.randn(2, 128, 24, 40, device=dev)
+    xs, ss = x.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    m = ops.channel_mean(xs)
+    y = ops.channel_scale(xs, ss)
+    ((m * gm).sum() + (y * gy).sum()).backward()
+    xd, sd = x.double().requires_grad_(True), s.double().requires_grad_(True)
+    md = xd.mean((2, 3))
+    yd = xd * sd[:, :, None, None]
+    ((md * gm.double()).sum() + (yd * gy.double()).sum()).backward()
+    assert (m.double() - md).abs().max().item() < 1e-6 and (y.double() - yd).abs().max().item() < 1e-6
+    assert (xs.grad.double() - xd.grad).abs().max().item() < 1e-5
+    assert (ss.grad.double() - sd.grad).abs().max().item() <= 1e-5 * sd.grad.abs().max().item()
