@@ -10,7 +10,10 @@
 //   The pixel range is cut into S slabs, a CTA owns (slab, tap, 64 ci, 64 co) and contracts staged 32-pixel chunks with
 //   warp-level TF32 MMAs on (hi, lo) operand pairs (three products: fp32-class); partial sums go to a workspace and a second
 //   kernel adds the S partials in a fixed order (deterministic; the bias gradient rides along).  (A first exact-FFMA version
-//   with a 4x4 register tile per thread spent 250 of the 436 ms of a training step here.)
+//   with a 4x4 register tile per thread spent 250 of the 436 ms of a training step here.  A tcgen05 / TMEM version - kind::tf32,
+//   M = 128 rows of (tap, ci), D resident in TMEM over the slab, operands transposed into K-major rows by 4-byte cp.async -
+//   was written, gave the right numbers and was dropped: 1.16 ms against 0.85 ms for 64->64 3x3 at 8x256x256, the transposing
+//   producers issue one copy per element and the MMA pipe sat at 4 %)
 #include "common.cuh"
 
 namespace tdvc {
