@@ -185,6 +185,12 @@ int tdvc_nhwc_to_nchw(const float* src, int src_ld, float* dst, int N, int C, in
 int tdvc_avgpool2x2(const float* src, float* dst, int N, int H, int W, int C, void* stream);
 int tdvc_spynet_prep(const float* ref4, const float* supp4, const float* flow_prev, float* out8,
                      int N, int h, int w, void* stream);
+/* Backward of spynet_prep with respect to the coarse flow (the images are network inputs): grad_out8 (N,h,w,8) ->
+ * grad_flow_prev (N,h/2,w/2,2).  The warp's derivative follows grid_sample's border rule (a clamped coordinate has zero
+ * derivative, corners outside the image contribute zero); the x2 upsample's adjoint is a gather (deterministic).
+ * grad_fine_ws: N*h*w*2 floats of scratch (d loss / d upsampled flow).                                             */
+int tdvc_spynet_prep_backward(const float* supp4, const float* flow_prev, const float* grad_out8, float* grad_fine_ws,
+                              float* grad_flow_prev, int N, int h, int w, void* stream);
 /* nn.Upsample(x2, bilinear, align_corners=False) on NHWC (reference pnet.py:117,159) */
 int tdvc_upsample2x(const float* src, float* dst, int N, int H, int W, int C, void* stream);
 /* offset + flow.repeat(1, C/2, 1, 1)  (reference pnet.py:163) */

@@ -115,6 +115,110 @@ __global__ void __launch_bounds__(256) spynet_prep_kernel(const float* __restric
   }
 }
 
+// ---- backward of spynet_prep with respect to the coarse flow (the images are inputs of the network: no gradient).
+// out8 = [ref(3), warp(supp, f)(3), f(2)] with f = 2 * upsample_x2(flow_prev) (align_corners=True):
+// d loss / d f = grad8[6..7] + sum_c grad8[3 + c] * d warp_c / d f   (grid_sample backward: the bilinear weights' derivative,
+// corners outside the image contribute zero, a clamped coordinate has zero derivative - ATen's border-padding rule),
+// then the adjoint of the x2 upsample, as a GATHER over the fine pixels that read a coarse one (deterministic).
+__global__ void spynet_prep_bwd_fine_kernel(const float* __restrict__ supp4, const float* __restrict__ flow_prev,
+                                            const float* __restrict__ grad8, float* __restrict__ gf, int N, int h, int w) {
+  const int hp = h >> 1, wp = w >> 1;
+  const float rh = h > 1 ? (float)(hp - 1) / (float)(h - 1) : 0.f;
+  const float rw = w > 1 ? (float)(wp - 1) / (float)(w - 1) : 0.f;
+  const float wm1 = (float)(w - 1 > 1 ? w - 1 : 1), hm1 = (float)(h - 1 > 1 ? h - 1 : 1);
+  const int64_t total = (int64_t)N * h * w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int64_t q = i / w;
+    const int y = (int)(q % h), n = (int)(q / h);
+    float fx = 0.f, fy = 0.f;
+    {
+      const float h1r = rh * (float)y, w1r = rw * (float)x;
+      const int h1 = (int)h1r, w1 = (int)w1r;
+      const int h1p = h1 < hp - 1 ? 1 : 0, w1p = w1 < wp - 1 ? 1 : 0;
+      const float h1l = h1r - (float)h1, w1l = w1r - (float)w1;
+      const float h0l = 1.f - h1l, w0l = 1.f - w1l;
+      const float2* fp = reinterpret_cast<const float2*>(flow_prev) + ((int64_t)n * hp + h1) * wp + w1;
+      const float2 v00 = __ldg(fp), v01 = __ldg(fp + w1p), v10 = __ldg(fp + (int64_t)h1p * wp), v11 = __ldg(fp + (int64_t)h1p * wp + w1p);
+      fx = (h0l * (w0l * v00.x + w1l * v01.x) + h1l * (w0l * v10.x + w1l * v11.x)) * 2.0f;
+      fy = (h0l * (w0l * v00.y + w1l * v01.y) + h1l * (w0l * v10.y + w1l * v11.y)) * 2.0f;
+    }
+    const float gxn = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)x, fx)), wm1), 1.0f);
+    const float gyn = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)y, fy)), hm1), 1.0f);
+    float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gxn, 1.f), 2.f), (float)(w - 1));
+    float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gyn, 1.f), 2.f), (float)(h - 1));
+    // d ix / d fx = (w - 1) / wm1 inside the image, 0 where the coordinate is clamped (ATen clip_coordinates_set_grad)
+    const float mx = (ix <= 0.f || ix >= (float)(w - 1)) ? 0.f : (float)(w - 1) / wm1;
+    const float my = (iy <= 0.f || iy >= (float)(h - 1)) ? 0.f : (float)(h - 1) / hm1;
+    ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
+    iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
+    const float ixf = floorf(ix), iyf = floorf(iy);
+    const int x0 = (int)ixf, y0 = (int)iyf;
+    const float txw = ix - ixf, tyw = iy - iyf, ux = (ixf + 1.f) - ix, uy = (iyf + 1.f) - iy;
+    const float4* sp = reinterpret_cast<const float4*>(supp4) + (int64_t)n * h * w;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 nw = __ldg(sp + (int64_t)y0 * w + x0);
+    const float4 ne = x0 + 1 < w ? __ldg(sp + (int64_t)y0 * w + x0 + 1) : z;
+    const float4 sw = y0 + 1 < h ? __ldg(sp + (int64_t)(y0 + 1) * w + x0) : z;
+    const float4 se = (x0 + 1 < w && y0 + 1 < h) ? __ldg(sp + (int64_t)(y0 + 1) * w + x0 + 1) : z;
+    const float* g = grad8 + i * 8;
+    const float g0 = g[3], g1 = g[4], g2 = g[5];
+    // d warp_c / d ix = (ne - nw) * uy + (se - sw) * tyw ; d warp_c / d iy = (sw - nw) * ux + (se - ne) * txw
+    const float dix = g0 * ((ne.x - nw.x) * uy + (se.x - sw.x) * tyw) + g1 * ((ne.y - nw.y) * uy + (se.y - sw.y) * tyw) +
+                      g2 * ((ne.z - nw.z) * uy + (se.z - sw.z) * tyw);
+    const float diy = g0 * ((sw.x - nw.x) * ux + (se.x - ne.x) * txw) + g1 * ((sw.y - nw.y) * ux + (se.y - ne.y) * txw) +
+                      g2 * ((sw.z - nw.z) * ux + (se.z - ne.z) * txw);
+    gf[i * 2] = g[6] + dix * mx;
+    gf[i * 2 + 1] = g[7] + diy * my;
+  }
+}
+
+// adjoint of f = 2 * upsample_x2(flow_prev), align_corners=True: every coarse pixel gathers from the fine pixels whose
+// interpolation footprint contains it; the source index / weights are recomputed exactly as the forward computes them.
+__global__ void spynet_prep_bwd_coarse_kernel(const float* __restrict__ gf, float* __restrict__ gflow, int N, int h, int w) {
+  const int hp = h >> 1, wp = w >> 1;
+  const float rh = h > 1 ? (float)(hp - 1) / (float)(h - 1) : 0.f;
+  const float rw = w > 1 ? (float)(wp - 1) / (float)(w - 1) : 0.f;
+  const int64_t total = (int64_t)N * hp * wp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % wp);
+    const int64_t q = i / wp;
+    const int Y = (int)(q % hp), n = (int)(q / hp);
+    // fine rows whose h1 is Y - 1 or Y lie in [(Y - 1) / rh, (Y + 1) / rh); widened by 2 against rounding
+    int ylo = 0, yhi = h - 1, xlo = 0, xhi = w - 1;
+    if (rh > 0.f) { ylo = (int)floorf((float)(Y - 1) / rh) - 2; yhi = (int)ceilf((float)(Y + 1) / rh) + 2; }
+    if (rw > 0.f) { xlo = (int)floorf((float)(X - 1) / rw) - 2; xhi = (int)ceilf((float)(X + 1) / rw) + 2; }
+    ylo = ylo < 0 ? 0 : ylo; yhi = yhi > h - 1 ? h - 1 : yhi;
+    xlo = xlo < 0 ? 0 : xlo; xhi = xhi > w - 1 ? w - 1 : xhi;
+    float ax = 0.f, ay = 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+      const float h1r = rh * (float)y;
+      const int h1 = (int)h1r;
+      const int h1p = h1 < hp - 1 ? 1 : 0;
+      const float h1l = h1r - (float)h1;
+      float wy = 0.f;
+      if (h1 == Y) wy += 1.f - h1l;
+      if (h1 + h1p == Y) wy += h1l;
+      if (wy == 0.f) continue;
+      for (int x = xlo; x <= xhi; ++x) {
+        const float w1r = rw * (float)x;
+        const int w1 = (int)w1r;
+        const int w1p = w1 < wp - 1 ? 1 : 0;
+        const float w1l = w1r - (float)w1;
+        float wx = 0.f;
+        if (w1 == X) wx += 1.f - w1l;
+        if (w1 + w1p == X) wx += w1l;
+        if (wx == 0.f) continue;
+        const float2 gv = *reinterpret_cast<const float2*>(gf + (((int64_t)n * h + y) * w + x) * 2);
+        ax += wy * wx * gv.x;
+        ay += wy * wx * gv.y;
+      }
+    }
+    gflow[i * 2] = 2.f * ax;
+    gflow[i * 2 + 1] = 2.f * ay;
+  }
+}
+
 // nn.Upsample(scale_factor=2, bilinear, align_corners=False): src = 0.5*(dst+0.5)-0.5 clamped at 0.
 // One block row per output row (blockIdx.y = n*Ho + y): the row's source rows and vertical weights are block constants and
 // the index arithmetic is 32-bit; consecutive threads write consecutive float4 of the output row.
@@ -187,6 +291,22 @@ extern "C" int tdvc_spynet_prep(const float* ref4, const float* supp4, const flo
   TDVC_REQUIRE(blocks < (1ll << 31), "spynet_prep: too many tiles");
   spynet_prep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ref4, supp4, flow_prev, out8, N, h, w, tiles_x, tiles_y);
   TDVC_CHECK_LAUNCH("spynet_prep");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_spynet_prep_backward(const float* supp4, const float* flow_prev, const float* grad_out8, float* grad_fine_ws,
+                                         float* grad_flow_prev, int N, int h, int w, void* stream) {
+  TDVC_REQUIRE(supp4 && flow_prev && grad_out8 && grad_fine_ws && grad_flow_prev && N > 0 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0,
+               "spynet_prep_backward: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = cdiv((int64_t)N * h * w, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  spynet_prep_bwd_fine_kernel<<<grid, 256, 0, st>>>(supp4, flow_prev, grad_out8, grad_fine_ws, N, h, w);
+  TDVC_CHECK_LAUNCH("spynet_prep_backward (fine)");
+  int grid2 = cdiv((int64_t)N * (h / 2) * (w / 2), 128);
+  if (grid2 > kNumSMs * 16) grid2 = kNumSMs * 16;
+  spynet_prep_bwd_coarse_kernel<<<grid2, 128, 0, st>>>(grad_fine_ws, grad_flow_prev, N, h, w);
+  TDVC_CHECK_LAUNCH("spynet_prep_backward (coarse)");
   return TDVC_OK;
 }
 

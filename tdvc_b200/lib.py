@@ -76,6 +76,7 @@ SIGNATURES = {
     "tdvc_nhwc_to_nchw": [vp, i32, vp, i32, i32, i32, i32, vp],
     "tdvc_avgpool2x2": [vp, vp, i32, i32, i32, i32, vp],
     "tdvc_spynet_prep": [vp, vp, vp, vp, i32, i32, i32, vp],
+    "tdvc_spynet_prep_backward": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "tdvc_upsample2x": [vp, vp, i32, i32, i32, i32, vp],
     "tdvc_add_flow_tiled": [vp, vp, vp, i32, i32, i32, i32, vp],
     "tdvc_axpby": [vp, vp, vp, i64, f32, f32, vp],

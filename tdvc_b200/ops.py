@@ -531,3 +531,62 @@ def channel_mean(x):
 def channel_scale(x, s):
     """x * s[:, :, None, None] for s of shape (N, C), with autograd to both (the gated product of a squeeze-excitation layer)."""
     return _ChannelScale.apply(x, s)
+
+
+# ----------------------------------------------------------------------------------------------- SPyNet level input with autograd
+def _img4(t):
+    """(N, 3, h, w) image -> channels-last Act with 4 stored channels (the layout the SPyNet kernels read)."""
+    from tdvc_b200.model import Act
+    N, C, H, W = t.shape
+    a = Act.alloc(N, H, W, C, t.device, ld=4, zero=True)
+    tt = t.detach().float().contiguous()
+    L.check(L.load().tdvc_nchw_to_nhwc(tt.data_ptr(), a.ptr, N, C, H, W, 4, torch.cuda.current_stream(t.device).cuda_stream), "nchw_to_nhwc")
+    return a
+
+
+class _SpynetLevelInput(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ref, supp, flow_prev):
+        from tdvc_b200.model import Act
+        N, _, h, w = ref.shape
+        lib = L.load()
+        with torch.cuda.device(ref.device):
+            st = torch.cuda.current_stream(ref.device).cuda_stream
+            ra, sa = _img4(ref), _img4(supp)
+            fa = None
+            if flow_prev is not None:
+                if tuple(flow_prev.shape) != (N, 2, h // 2, w // 2):
+                    raise RuntimeError("spynet_level_input: flow_prev must be (N, 2, h/2, w/2)")
+                fa = Act.alloc(N, h // 2, w // 2, 2, ref.device, ld=2)
+                fp = flow_prev.detach().float().contiguous()
+                L.check(lib.tdvc_nchw_to_nhwc(fp.data_ptr(), fa.ptr, N, 2, h // 2, w // 2, 2, st), "nchw_to_nhwc")
+            out = Act.alloc(N, h, w, 8, ref.device)
+            L.check(lib.tdvc_spynet_prep(ra.ptr, sa.ptr, fa.ptr if fa is not None else None, out.ptr, N, h, w, st), "spynet_prep")
+        ctx.t = (sa, fa, N, h, w)
+        return _nchw(out)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        from tdvc_b200.model import Act
+        sa, fa, N, h, w = ctx.t
+        if fa is None:
+            return None, None, None
+        lib = L.load()
+        with torch.cuda.device(g.device):
+            st = torch.cuda.current_stream(g.device).cuda_stream
+            ga = _nhwc(g)
+            ws = torch.empty(N * h * w * 2, device=g.device, dtype=torch.float32)
+            gfl = Act.alloc(N, h // 2, w // 2, 2, g.device, ld=2)
+            L.check(lib.tdvc_spynet_prep_backward(sa.ptr, fa.ptr, ga.ptr, ws.data_ptr(), gfl.ptr, N, h, w, st), "spynet_prep_backward")
+            out = torch.empty((N, 2, h // 2, w // 2), device=g.device, dtype=torch.float32)
+            L.check(lib.tdvc_nhwc_to_nchw(gfl.ptr, 2, out.data_ptr(), N, 2, h // 2, w // 2, st), "nhwc_to_nchw")
+        return None, None, out
+
+
+def spynet_level_input(ref, supp, flow_prev=None):
+    """One SPyNet level's input (reference flownet.py:116-138): cat([ref, flow_warp(supp, up), up], 1) with up = 2 x the x2
+    bilinear upsample (align_corners=True) of the coarser level's flow (None at the coarsest level: zero flow) and flow_warp the
+    border-clamped bilinear backward warp of reference flownet.py:8-48, in ONE kernel; autograd to flow_prev (the images are
+    inputs of the network).  (N, 3, h, w) images, (N, 2, h/2, w/2) flow -> (N, 8, h, w)."""
+    return _SpynetLevelInput.apply(ref, supp, flow_prev)

@@ -131,17 +131,6 @@ def coder(cd, x, noise, num_pixels):
 
 
 # ----------------------------------------------------------------------------------------------- motion estimation
-def _flow_warp(x, flow):
-    """reference flownet.py:8-48: bilinear backward warp, border padding, align_corners=True, with the reference's own
-    normalise -> un-normalise coordinate round trip.  flow (N, 2, h, w)."""
-    _, _, h, w = x.shape
-    gy, gx = torch.meshgrid(torch.arange(0, h, device=x.device), torch.arange(0, w, device=x.device), indexing="ij")
-    gf = torch.stack((gx, gy), 2).type_as(x) + flow.permute(0, 2, 3, 1)
-    nx = 2.0 * gf[..., 0] / max(w - 1, 1) - 1.0
-    ny = 2.0 * gf[..., 1] / max(h - 1, 1) - 1.0
-    return F.grid_sample(x, torch.stack((nx, ny), dim=3), mode="bilinear", padding_mode="border", align_corners=True)
-
-
 def spynet(sp, ref, supp):
     """reference flownet.py:82-140 (6 levels, coarse to fine)."""
     n, _, h, w = ref.shape
@@ -152,14 +141,15 @@ def spynet(sp, ref, supp):
         refs.append(F.avg_pool2d(refs[-1], 2, 2, count_include_pad=False))
         supps.append(F.avg_pool2d(supps[-1], 2, 2, count_include_pad=False))
     refs, supps = refs[::-1], supps[::-1]
-    flow = ref.new_zeros(n, 2, h // 32, w // 32)
+    flow = None
     for lvl in range(6):
-        up = flow if lvl == 0 else F.interpolate(flow, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
-        t = torch.cat([refs[lvl], _flow_warp(supps[lvl], up), up], 1)
+        # [ref, warp(supp, up), up] with up = 2 * upsample_x2(flow): one kernel forward, two backward (ops.spynet_level_input)
+        x8 = ops.spynet_level_input(refs[lvl], supps[lvl], flow)
+        t = x8
         bm = sp.basic_module[lvl].basic_module
         for i in range(4):
             t = _cv(bm[i].conv, t, "relu")
-        flow = up + _cv(bm[4].conv, t)
+        flow = x8[:, 6:8] + _cv(bm[4].conv, t)
     return flow
 
 

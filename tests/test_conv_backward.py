@@ -231,3 +231,33 @@ def test_channel_mean_and_scale_vs_torch():
     assert (m.double() - md).abs().max().item() < 1e-6 and (y.double() - yd).abs().max().item() < 1e-6
     assert (xs.grad.double() - xd.grad).abs().max().item() < 1e-5
     assert (ss.grad.double() - sd.grad).abs().max().item() <= 1e-5 * sd.grad.abs().max().item()
+
+
+def test_spynet_level_input_vs_torch():
+    """One SPyNet level's input assembly (reference flownet.py:8-48, 116-138) and its gradient to the coarse flow against the
+    torch formulation (interpolate x2 align_corners=True, * 2, grid_sample border / align_corners=True, cat)."""
+    from oracle.model import flow_warp_border
+    from tdvc_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(51)
+    N, h, w = 2, 32, 48
+    ref, supp = torch.rand(N, 3, h, w, generator=g), torch.rand(N, 3, h, w, generator=g)
+    flow = torch.randn(N, 2, h // 2, w // 2, generator=g) * 3.0
+    flow[0, :, 0, :] = -40.0      # pushes samples beyond the border: clamped coordinates, zero derivative
+    gy = torch.randn(N, 8, h, w, generator=g)
+    fs = flow.to(dev).requires_grad_(True)
+    y = ops.spynet_level_input(ref.to(dev), supp.to(dev), fs)
+    (y * gy.to(dev)).sum().backward()
+    fd = flow.double().requires_grad_(True)
+    up = F.interpolate(fd, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
+    yd = torch.cat([ref.double(), flow_warp_border(supp.double(), up.permute(0, 2, 3, 1)), up], 1)
+    (yd * gy.double()).sum().backward()
+    # forward against the same fp32 arithmetic (white-noise images: a 1e-5 coordinate rounding moves a sample by 1e-5)
+    up32 = F.interpolate(flow, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
+    y32 = torch.cat([ref, flow_warp_border(supp, up32.permute(0, 2, 3, 1)), up32], 1)
+    assert (y.detach().cpu() - y32).abs().max().item() < 2e-5
+    assert (y.detach().cpu().double() - yd).abs().max().item() < 2e-4
+    err = (fs.grad.cpu().double() - fd.grad).abs().max().item()
+    assert err <= 1e-3 * fd.grad.abs().max().item(), (err, fd.grad.abs().max().item())
+    y0 = ops.spynet_level_input(ref.to(dev), supp.to(dev), None)      # coarsest level: zero flow
+    assert (y0[:, 3:6].cpu() - supp).abs().max().item() < 1e-5 and y0[:, 6:].abs().max().item() == 0.0
