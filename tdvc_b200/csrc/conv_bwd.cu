@@ -360,6 +360,13 @@ static int wgrad_slabs(int64_t npix, int tiles) {
   return S < 1 ? 1 : S;
 }
 
+// wgrad_tc.cu: the tcgen05 kernel for 3x3 stride-1 layers with 64-channel tiles (one TF32 product per MAC)
+bool wgrad_tc_eligible(const float* x, int x_ld, const float* g, int g_ld, int H, int W, int cin, int cout, int k, int stride, int pad,
+                       int in_square);
+size_t wgrad_tc_workspace_bytes(int N, int H, int W, int cin, int cout);
+int wgrad_tc_launch(const float* x, int x_ld, const float* g, int g_ld, int N, int H, int W, int cin, int cout, float* workspace,
+                    float** part_bias_out, int* S_out, cudaStream_t st);
+
 }  // namespace tdvc
 
 using namespace tdvc;
@@ -391,7 +398,12 @@ extern "C" size_t tdvc_conv2d_wgrad_workspace_bytes(int N, int Ho, int Wo, int c
   if (N <= 0 || Ho <= 0 || Wo <= 0 || cin <= 0 || cout <= 0 || k <= 0) return 0;
   const int tiles = k * k * cdiv(cin, WG_T) * cdiv(cout, WG_T);
   const int S = wgrad_slabs((int64_t)N * Ho * Wo, tiles);
-  return (size_t)S * ((size_t)k * k * cin * cout + cout) * sizeof(float);
+  size_t need = (size_t)S * ((size_t)k * k * cin * cout + cout) * sizeof(float);
+  if (k == 3 && cin % 64 == 0 && cout % 64 == 0) {   // the tensor-core kernel cuts its slabs differently; cover both
+    const size_t tc = wgrad_tc_workspace_bytes(N, Ho, Wo, cin, cout);
+    if (tc > need) need = tc;
+  }
+  return need;
 }
 
 extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, int N, int H, int W, int cin, int cout,
@@ -416,7 +428,9 @@ extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, 
   a.part = (float*)workspace;
   a.part_bias = a.part + (size_t)a.S * k * k * cin * cout;
   cudaStream_t st = (cudaStream_t)stream;
-  if (products == 1) wgrad_kernel<1><<<dim3(tiles, a.S), 256, 0, st>>>(a);
+  if (products == 1 && wgrad_tc_eligible(x, x_ld, grad_y, g_ld, H, W, cin, cout, k, stride, pad, in_square)) {
+    if (int rc = wgrad_tc_launch(x, x_ld, grad_y, g_ld, N, H, W, cin, cout, a.part, &a.part_bias, &a.S, st)) return rc;
+  } else if (products == 1) wgrad_kernel<1><<<dim3(tiles, a.S), 256, 0, st>>>(a);
   else wgrad_kernel<3><<<dim3(tiles, a.S), 256, 0, st>>>(a);
   TDVC_CHECK_LAUNCH("conv2d_wgrad");
   const int64_t n_out = (int64_t)k * k * cin * cout + cout;

@@ -248,6 +248,60 @@ def test_gop_dataset_and_iframe_averaging(tmp_path):
     assert (mv, rs, mse) == (0.04, 0.06, 1e-3)
 
 
+def test_vimeo_training_dataset(tmp_path):
+    """tdvc_b200.data.VimeoDataset lists samples like the reference's training `DataSet.get_vimeo` (reference
+    main/dataloader/dataset.py:210-247: references [im1, t-3, t-2, t-1] clipped at im1, short histories padded by repetition,
+    plus [im1, im1, im3, im5] -> im7) and applies ONE draw of the imgauglist2 augmentation (augmentation.py:29-85) to the five
+    frames of a sample."""
+    from torchvision.io import write_png
+    from tdvc_b200 import data as D
+    torch.manual_seed(3)
+    base = torch.rand(3, 40, 56)
+    for d, clip in (("00002", "0010"), ("00001", "0002"), ("00001", "0010")):
+        os.makedirs(tmp_path / d / clip)
+        for i in range(1, 8):
+            img = ((base * 0.8 + 0.02 * i) * 255).to(torch.uint8)     # frames of a clip differ by a constant
+            write_png(img, str(tmp_path / d / clip / f"im{i}.png"))
+    ds = D.VimeoDataset(str(tmp_path), 32, generator=torch.Generator().manual_seed(5))
+    assert len(ds) == 3 * 7
+    rel = lambda p: os.path.relpath(p, tmp_path)
+    assert [rel(p) for p in ds.image_input_list[:7]] == [f"00001/0002/im{t}.png" for t in (2, 3, 4, 5, 6, 7, 7)]
+    want = {0: (1, 1, 1, 1), 1: (1, 1, 2, 2), 2: (1, 1, 2, 3), 3: (1, 2, 3, 4), 4: (1, 3, 4, 5), 5: (1, 4, 5, 6), 6: (1, 1, 3, 5)}
+    for k, ids in want.items():
+        assert [rel(p) for p in ds.image_ref_list[k]] == [f"00001/0002/im{i}.png" for i in ids]
+    assert rel(ds.image_input_list[7]) == "00001/0010/im2.png" and rel(ds.image_input_list[14]) == "00002/0010/im2.png"
+    seen_crop = seen_resize = False
+    for k in range(21):
+        x, refs = ds[k]
+        assert x.shape == (3, 32, 32) and refs.shape == (4, 3, 32, 32) and x.dtype == torch.float32
+        assert 0.0 <= float(x.min()) and float(x.max()) <= 1.0
+        # one draw for all five frames: geometry and photometric change are shared, so slots holding the same source frame agree
+        ids = want[k % 7]
+        for a in range(4):
+            for b in range(a + 1, 4):
+                if ids[a] == ids[b]:
+                    assert torch.equal(refs[a], refs[b])
+    # the crop branch returns source pixels unchanged up to flips / photometric change; check it is reachable, and the resize too
+    g = torch.Generator().manual_seed(0)
+    ds2 = D.VimeoDataset(str(tmp_path), 32, generator=g)
+    fr = torch.rand(5, 3, 40, 56)
+    for _ in range(40):
+        out = ds2.augment(fr)
+        assert out.shape == (5, 3, 32, 32)
+        vals = set(torch.round(fr * 255).flatten().tolist())
+        if set(torch.round(out * 255).flatten().tolist()) <= vals and torch.isin(out, fr).all():
+            seen_crop = True
+        else:
+            seen_resize = True
+    assert seen_crop and seen_resize
+    with pytest.raises(RuntimeError):
+        for _ in range(40):
+            D.VimeoDataset(str(tmp_path), 64, generator=g).augment(fr)
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False, num_workers=0)
+    xb, rb = next(iter(loader))
+    assert xb.shape == (4, 3, 32, 32) and rb.shape == (4, 4, 3, 32, 32)     # forward(input_image, refer_frames) shapes (pnet.py:26)
+
+
 def test_shared_library_has_no_libcuda_dependency():
     """The library must load on a host without a driver: the driver entry point it needs is resolved at run time."""
     import subprocess

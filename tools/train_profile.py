@@ -8,6 +8,7 @@ from tdvc_b200 import synth
 from tdvc_b200.model import VideoCompressor
 
 dev = torch.device("cuda:0")
+AMP = "--amp" in sys.argv   # enabled_amp of the step (cfg/train.yaml ships amp: True)
 torch.manual_seed(synth.SEED)
 net = VideoCompressor()
 sd = net.state_dict()
@@ -22,7 +23,7 @@ refs = torch.cat([p[1] for p in pairs]).to(dev)
 
 
 def step():
-    out = net(x, refs, False)
+    out = net(x, refs, AMP)
     loss = 2048 * torch.nn.MSELoss()(out[0], x) + out[1].mean() + out[2].mean()
     opt.zero_grad()
     loss.backward()
