@@ -14,6 +14,7 @@
 //   M = 128 rows of (tap, ci), D resident in TMEM over the slab, operands transposed into K-major rows by 4-byte cp.async -
 //   was written, gave the right numbers and was dropped: 1.16 ms against 0.85 ms for 64->64 3x3 at 8x256x256, the transposing
 //   producers issue one copy per element and the MMA pipe sat at 4 %)
+#include <cstdlib>
 #include "common.cuh"
 
 namespace tdvc {
@@ -360,11 +361,11 @@ static int wgrad_slabs(int64_t npix, int tiles) {
   return S < 1 ? 1 : S;
 }
 
-// wgrad_tc.cu: the tcgen05 kernel for 3x3 stride-1 layers with 64-channel tiles (one TF32 product per MAC)
-bool wgrad_tc_eligible(const float* x, int x_ld, const float* g, int g_ld, int H, int W, int cin, int cout, int k, int stride, int pad,
-                       int in_square);
-size_t wgrad_tc_workspace_bytes(int N, int H, int W, int cin, int cout);
-int wgrad_tc_launch(const float* x, int x_ld, const float* g, int g_ld, int N, int H, int W, int cin, int cout, float* workspace,
+// wgrad_tc.cu: the tcgen05 kernels for stride-1 layers (one TF32 product per MAC)
+bool wgrad_tc_eligible(const float* x, int x_ld, const float* g, int g_ld, int N, int H, int W, int cin, int cout, int k, int stride,
+                       int pad, int in_square);
+size_t wgrad_tc_workspace_bytes(int N, int H, int W, int cin, int cout, int k);
+int wgrad_tc_launch(const float* x, int x_ld, const float* g, int g_ld, int N, int H, int W, int cin, int cout, int k, float* workspace,
                     float** part_bias_out, int* S_out, cudaStream_t st);
 
 }  // namespace tdvc
@@ -399,10 +400,8 @@ extern "C" size_t tdvc_conv2d_wgrad_workspace_bytes(int N, int Ho, int Wo, int c
   const int tiles = k * k * cdiv(cin, WG_T) * cdiv(cout, WG_T);
   const int S = wgrad_slabs((int64_t)N * Ho * Wo, tiles);
   size_t need = (size_t)S * ((size_t)k * k * cin * cout + cout) * sizeof(float);
-  if (k == 3 && cin % 64 == 0 && cout % 64 == 0) {   // the tensor-core kernel cuts its slabs differently; cover both
-    const size_t tc = wgrad_tc_workspace_bytes(N, Ho, Wo, cin, cout);
-    if (tc > need) need = tc;
-  }
+  const size_t tc = wgrad_tc_workspace_bytes(N, Ho, Wo, cin, cout, k);   // the tensor-core kernels cut their slabs differently; cover both
+  if (tc > need) need = tc;
   return need;
 }
 
@@ -428,14 +427,31 @@ extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, 
   a.part = (float*)workspace;
   a.part_bias = a.part + (size_t)a.S * k * k * cin * cout;
   cudaStream_t st = (cudaStream_t)stream;
-  if (products == 1 && wgrad_tc_eligible(x, x_ld, grad_y, g_ld, H, W, cin, cout, k, stride, pad, in_square)) {
-    if (int rc = wgrad_tc_launch(x, x_ld, grad_y, g_ld, N, H, W, cin, cout, a.part, &a.part_bias, &a.S, st)) return rc;
+  static const bool log_shapes = getenv("TDVC_B200_WGRAD_LOG") != nullptr;   // developer: one line per call (tools/train_profile.py)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (log_shapes) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+  }
+  if (products == 1 && wgrad_tc_eligible(x, x_ld, grad_y, g_ld, N, H, W, cin, cout, k, stride, pad, in_square)) {
+    if (int rc = wgrad_tc_launch(x, x_ld, grad_y, g_ld, N, H, W, cin, cout, k, a.part, &a.part_bias, &a.S, st)) return rc;
   } else if (products == 1) wgrad_kernel<1><<<dim3(tiles, a.S), 256, 0, st>>>(a);
   else wgrad_kernel<3><<<dim3(tiles, a.S), 256, 0, st>>>(a);
   TDVC_CHECK_LAUNCH("conv2d_wgrad");
   const int64_t n_out = (int64_t)k * k * cin * cout + cout;
   wgrad_reduce_kernel<<<cdiv(n_out, 256), 256, 0, st>>>(a.part, a.part_bias, a.S, k * k, cin, cout, grad_w, grad_b_or_null);
   TDVC_CHECK_LAUNCH("conv2d_wgrad_reduce");
+  if (log_shapes) {
+    float ms = 0.f;
+    cudaEventRecord(ev1, st);
+    cudaEventSynchronize(ev1);
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    fprintf(stderr, "wgrad N%d %dx%d cin%d cout%d k%d s%d p%d sq%d products%d ld%d/%d ms %.4f\n", N, H, W, cin, cout, k, stride, pad,
+            in_square, products, x_ld, g_ld, ms);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+  }
   return TDVC_OK;
 }
 

@@ -65,6 +65,53 @@ def test_conv2d_forward_backward_vs_torch_fp64(case):
         assert err <= tol * rel * max(1.0, r.abs().max().item()), (name, err, r.abs().max().item())
 
 
+AMP_CASES = [
+    # N, cin, cout, k, stride, H, W: the layer classes of the training step (weight gradient with one TF32 product, enabled_amp)
+    (2, 64, 64, 3, 1, 36, 64),      # Res_Block: tcgen05 kernel, 64-channel tiles (2 kernel rows per M = 128 operand)
+    (1, 128, 192, 3, 1, 12, 96),    # coder layers: several ci / co tiles
+    (2, 3, 64, 3, 1, 21, 50),       # image input: one 32-channel group zero-filled past channel 3, ragged tiles
+    (1, 64, 216, 3, 1, 16, 40),     # DCN offset / mask head: last co tile 24 channels wide
+    (1, 64, 3, 3, 1, 16, 40),       # image head
+    (1, 8, 32, 7, 1, 20, 40),       # SPyNet basic module, 4 kernel rows per operand
+    (1, 32, 64, 7, 1, 20, 40),      # ... kernel columns split over two CTAs
+    (1, 64, 32, 7, 1, 20, 40),      # ... two-row items
+    (1, 16, 2, 7, 1, 20, 40),       # ... flow head
+    (1, 192, 64, 1, 1, 20, 40),     # 1x1 fusion layer
+    (1, 64, 128, 3, 2, 32, 64),     # strided layer: warp-level kernel
+    (1, 128, 128, 3, 1, 8, 8),      # too small for the tensor-core items: warp-level kernel
+]
+
+
+@pytest.mark.parametrize("case", AMP_CASES, ids=[f"{c[1]}to{c[2]}k{c[3]}s{c[4]}@{c[5]}x{c[6]}" for c in AMP_CASES])
+def test_conv2d_weight_gradient_one_tf32_product(case):
+    """`enabled_amp=True` selects one TF32 product per MAC for the weight gradients (ops.WGRAD_PRODUCTS = 1: csrc/wgrad_tc.cu
+    on tcgen05 where the shape allows, else the warp-level kernel): against float64 within TF32 operand rounding (2^-11 per
+    operand; the tensor core truncates), bit-identical from run to run."""
+    from tdvc_b200 import ops
+    N, ci, co, k, s, H, W = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(7 * k + ci + co)
+    x = torch.randn(N, ci, H, W, generator=g).to(dev)
+    w = (torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5).to(dev)
+    b = (torch.randn(co, generator=g) * 0.1).to(dev)
+    Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    gy = torch.randn(N, co, Ho, Wo, generator=g).to(dev)
+    saved, ops.WGRAD_PRODUCTS = ops.WGRAD_PRODUCTS, 1
+    try:
+        grads = []
+        for _ in range(2):
+            ws, bs = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            ops.conv2d(x, ws, bs, s, k // 2).backward(gy)
+            grads.append((ws.grad, bs.grad))
+    finally:
+        ops.WGRAD_PRODUCTS = saved
+    wd, bd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    F.conv2d(x.double(), wd, bd, s, k // 2).backward(gy.double())
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
+    assert (grads[0][0].double() - wd.grad).abs().max().item() <= 2e-3 * wd.grad.abs().max().item()
+    assert (grads[0][1].double() - bd.grad).abs().max().item() <= 1e-5 * max(1.0, bd.grad.abs().max().item())
+
+
 def test_conv2d_backward_is_deterministic_and_composes():
     """Two backward passes give identical bits; a Res_Block (reference utils.py:43-56) built from ops.conv2d has the gradients of
     the same block in torch."""
