@@ -256,7 +256,7 @@ def gpu_eager_training_baseline(dev, batch=8, size=256, iters=3):
     return out
 
 
-def training_leg(dev, world, steps, warmup, batch=8, size=256):
+def training_leg(dev, world, steps, warmup, batch=8, size=256, graph=False):
     """BASELINE config 4: one training step of reference tools/train.py:125-159 (enable_amp False branch) - forward, rd_loss
     (2048 * MSE + bpp_res + bpp_mv), backward, clip_grad_norm_(2), Adam step, aux_loss backward, aux Adam step - on a
     Vimeo-shaped synthetic batch: `batch` samples of 256x256 with 4 references each PER GPU (the reference splits a global
@@ -277,8 +277,9 @@ def training_leg(dev, world, steps, warmup, batch=8, size=256):
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], find_unused_parameters=True)
     params = [p for n, p in net.named_parameters() if not n.endswith(".quantiles")]
     aux_params = [p for n, p in net.named_parameters() if n.endswith(".quantiles")]
-    opt = torch.optim.Adam(params, lr=1e-4)            # reference main/utils/utils.py:90-113 (cfg/train.yaml lr)
-    aux_opt = torch.optim.Adam(aux_params, lr=1e-3)
+    # reference main/utils/utils.py:90-113 (cfg/train.yaml lr); `capturable` keeps the step counters on the device (graph leg)
+    opt = torch.optim.Adam(params, lr=1e-4, capturable=graph)
+    aux_opt = torch.optim.Adam(aux_params, lr=1e-3, capturable=graph)
     rank = dist.get_rank() if world > 1 else 0
     pairs = [synth.make_frame_pair(size, size, seed=500 + rank * batch + i) for i in range(batch)]
     x = torch.cat([p[0] for p in pairs]).to(dev)
@@ -300,15 +301,33 @@ def training_leg(dev, world, steps, warmup, batch=8, size=256):
         aux_opt.step()
         losses.append(loss.detach())
 
+    torch.cuda.reset_peak_memory_stats(dev)
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
+    run = step
+    if graph:
+        # the whole step - forward, backward, clipping, both optimiser steps - captured once and replayed: the eager step is
+        # bound by the host (autograd + ~3,000 launches per step), not by the GPU
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            step()
+        run = cg.replay
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        step()
+        run()
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
@@ -316,7 +335,7 @@ def training_leg(dev, world, steps, warmup, batch=8, size=256):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     return {"ms_per_step": ms, "samples_per_s": batch * world / (ms / 1e3), "batch_per_gpu": batch, "size": size, "n_gpus": world,
-            "steps": steps, "warmup": warmup, "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
+            "steps": steps, "warmup": warmup, "cuda_graph": bool(graph), "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
             "what": "forward + rd_loss backward + clip + Adam + aux step (reference tools/train.py:125-159); convolutions, GDN, DCN "
                     "and entropy models on tdvc_b200 kernels, torch autograd as the tape with torch glue operators between "
@@ -341,6 +360,7 @@ def main():
     ap.add_argument("--workload", default="predict", choices=["predict", "train"],
                     help="predict: the headline P-frame coding benchmark; train: BASELINE config 4 (training step) on its own")
     ap.add_argument("--no-train-leg", action="store_true")
+    ap.add_argument("--train-graph", action="store_true", help="--workload train: capture the whole step in a CUDA graph and replay it (a measurement of the GPU-bound step: replays reuse the captured noise seed and weight scalings)")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
     args = ap.parse_args()
@@ -366,7 +386,7 @@ def main():
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))   # a hang must fail fast
     if args.workload == "train":
-        rec = training_leg(dev, world, max(1, min(args.steps, 8)), max(args.warmup, 3))
+        rec = training_leg(dev, world, max(1, min(args.steps, 8)), max(args.warmup, 3), graph=args.train_graph and world == 1)
         if rank == 0 and world == 1 and not args.no_eager_baseline:
             torch.cuda.empty_cache()
             rec["gpu_eager_baseline"] = gpu_eager_training_baseline(dev)
@@ -607,7 +627,7 @@ def main():
         if world == 1 and not args.no_train_leg:
             try:
                 torch.cuda.empty_cache()
-                train = training_leg(dev, 1, 3, 1)
+                train = training_leg(dev, 1, 4, 3)
             except Exception as e:
                 train = {"error": f"{type(e).__name__}: {e}"[:300]}
             torch.cuda.empty_cache()

@@ -274,6 +274,15 @@ size_t tdvc_conv2d_wgrad_workspace_bytes(int N, int Ho, int Wo, int cin, int cou
 int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, int N, int H, int W, int cin, int cout, int k,
                       int stride, int pad, int in_square, int products, float* grad_w, float* grad_b_or_null, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* conv2d_pack_weight: nn.Conv2d.weight (O, I, k, k) -> the implicit-GEMM layout tdvc_conv2d reads, out[k*k][cin_pad][cout_pad]
+ *   fp32, zero padded, in ONE launch (the training step re-packs every weight after every optimiser step).  transposed = 0:
+ *   out[tap][ci][co] = w[co][ci][tap] (cin_pad >= I, cout_pad >= O), bias (O) copied to bias_out[cout_pad] when given;
+ *   transposed = 1: the dgrad operator, w flipped spatially with input and output channels swapped:
+ *   out[tap][ci][co] = w[ci][co][k*k - 1 - tap] (cin_pad >= O, cout_pad >= I). */
+int tdvc_conv2d_pack_weight(const float* w, int O, int I, int k, int transposed, float* out, int cin_pad, int cout_pad,
+                            const float* bias_or_null, float* bias_out_or_null, void* stream);
+/* conv2d_wgrad with products = 1 runs stride-1 "same"-padded 1x1 / 3x3 / 7x7 layers on tcgen05 (csrc/wgrad_tc.cu: MN-major
+ * TF32 operands straight from the channels-last tensors by tensor-map bulk copies; operands truncated to TF32). */
 /* GDN / IGDN backward (compressai GDN: out = x * norm^(-1/2), inverse: x * norm^(1/2), norm = beta + gamma . x^2), element-wise
  * parts on flat fp32 arrays (n % 4 == 0): pre -> dx_direct = g * norm^(-+1/2), dnorm = d loss / d norm; the 1x1 convolution's
  * dgrad (tdvc_conv2d on gamma^T) turns dnorm into d(x^2) and tdvc_conv2d_wgrad(in_square = 1) into d gamma / d beta;

@@ -354,6 +354,28 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float*
   }
 }
 
+// nn.Conv2d.weight (O, I, k, k) -> [k*k][cin_pad][cout_pad], zero padded; transposed: the dgrad operator (flipped, channels swapped)
+__global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, int kk, int transposed, float* __restrict__ out,
+                                   int cin_pad, int cout_pad, const float* __restrict__ bias, float* __restrict__ bias_out) {
+  const int64_t nw = (int64_t)kk * cin_pad * cout_pad;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nw) {
+    const int co = (int)(i % cout_pad);
+    const int64_t r = i / cout_pad;
+    const int ci = (int)(r % cin_pad), tap = (int)(r / cin_pad);
+    float v = 0.f;
+    if (!transposed) {
+      if (co < O && ci < I) v = w[((int64_t)co * I + ci) * kk + tap];
+    } else {
+      if (ci < O && co < I) v = w[((int64_t)ci * I + co) * kk + (kk - 1 - tap)];
+    }
+    out[i] = v;
+  } else if (bias_out != nullptr && i < nw + cout_pad) {
+    const int co = (int)(i - nw);
+    bias_out[co] = (bias != nullptr && co < O) ? bias[co] : 0.f;
+  }
+}
+
 static int wgrad_slabs(int64_t npix, int tiles) {
   int S = (4 * kNumSMs + tiles - 1) / tiles;           // ~4 CTAs per SM in total
   const int64_t max_s = (npix + 4 * WG_P - 1) / (4 * WG_P);   // at least 4 chunks per slab
@@ -392,6 +414,18 @@ extern "C" int tdvc_zero_insert(const float* g, int g_ld, float* out, int out_ld
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   zero_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, g_ld, out, out_ld, N, H, W, Ho, Wo, C / 4, stride);
   TDVC_CHECK_LAUNCH("zero_insert");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_conv2d_pack_weight(const float* w, int O, int I, int k, int transposed, float* out, int cin_pad, int cout_pad,
+                                       const float* bias_or_null, float* bias_out_or_null, void* stream) {
+  TDVC_REQUIRE(w && out && O > 0 && I > 0 && k >= 1 && k <= 7, "conv2d_pack_weight: bad args");
+  TDVC_REQUIRE(transposed ? (cin_pad >= O && cout_pad >= I) : (cin_pad >= I && cout_pad >= O), "conv2d_pack_weight: padded sizes");
+  TDVC_REQUIRE(!(transposed && bias_out_or_null), "conv2d_pack_weight: the dgrad operator has no bias");
+  const int64_t n = (int64_t)k * k * cin_pad * cout_pad + (bias_out_or_null ? cout_pad : 0);
+  pack_weight_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, O, I, k * k, transposed ? 1 : 0, out, cin_pad, cout_pad,
+                                                                     bias_or_null, bias_out_or_null);
+  TDVC_CHECK_LAUNCH("conv2d_pack_weight");
   return TDVC_OK;
 }
 

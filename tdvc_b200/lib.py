@@ -96,6 +96,7 @@ SIGNATURES = {
     "tdvc_zero_insert": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "tdvc_conv2d_wgrad_workspace_bytes": [i32] * 6,
     "tdvc_conv2d_wgrad": [vp, i32, vp, i32] + [i32] * 10 + [vp, vp, vp, sz, vp],
+    "tdvc_conv2d_pack_weight": [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp],
     "tdvc_gdn_backward_pre": [vp, vp, vp, vp, vp, i64, i32, vp],
     "tdvc_gdn_backward_post": [vp, vp, vp, vp, i64, vp],
     "tdvc_chan_affine": [vp, vp, vp, vp, i32, i64, i32, vp],

@@ -130,9 +130,37 @@ _ACTS = {None: L.ACT_NONE, "none": L.ACT_NONE, "relu": L.ACT_RELU, "leaky_relu":
 _PACKS = {}
 
 
-def _packed(weight, bias, stride, pad, transposed):
+_WMAX = {}
+
+
+def _weight_max(weight, key):
+    """max |w| for the power-of-two weight scaling of the fp16 schemes (tc._pack), without stalling the host every step: the
+    value comes from the copy issued at the PREVIOUS pack of the same parameter (`key`: a stable object, the parameter itself
+    unless the caller names one) - one optimiser step old, and the scaling leaves a factor 4 of headroom; the first sight of
+    a parameter pays one synchronous read."""
+    ent = _WMAX.get(id(key))
+    if ent is None or ent[0]() is not key:
+        if len(_WMAX) >= 4096:
+            _WMAX.clear()
+        m = float(weight.detach().abs().max())
+        pinned = torch.empty(1, dtype=torch.float32, pin_memory=True)
+        pinned[0] = m
+        ent = (weakref.ref(key), pinned, torch.cuda.Event())
+        _WMAX[id(key)] = ent
+        return m
+    if torch.cuda.is_current_stream_capturing():
+        return float(ent[1][0])
+    ent[2].synchronize()
+    m = float(ent[1][0])
+    ent[1].copy_(weight.detach().abs().max().reshape(1), non_blocking=True)
+    ent[2].record(torch.cuda.current_stream(weight.device))
+    return m
+
+
+def _packed(weight, bias, stride, pad, transposed, max_key=None):
     """ConvW (fp32 implicit-GEMM layout + tcgen05 fp16 blocks) of `weight`, or of its transposed, spatially flipped form
-    (the dgrad operator), cached on the parameter's identity and version."""
+    (the dgrad operator), cached on the parameter's identity and version.  Packed by one kernel (tdvc_conv2d_pack_weight):
+    the training step re-packs every weight after every optimiser step."""
     from tdvc_b200 import model as M, tc
     key = (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version), stride, pad,
            transposed)
@@ -142,10 +170,27 @@ def _packed(weight, bias, stride, pad, transposed):
     if cw is None:
         if len(_PACKS) >= 256:
             _PACKS.clear()
-        w = weight.detach().float()
+        w = weight.detach().float().contiguous()
+        O, I, k, _ = w.shape
         if transposed:
-            w = w.flip(2, 3).transpose(0, 1).contiguous()
-        cw = M.pack_conv(w, None if (bias is None or transposed) else bias.detach().float(), pad=pad, stride=stride)
+            O, I = I, O
+        dev = w.device
+        cw = M.ConvW()
+        cw.cin = M._r(I, 4)
+        cw.cin_pad, cw.cout_pad = M._r(cw.cin, 8), M._r(O, 16)
+        cw.cout, cw.k, cw.cin_real = O, k, I
+        cw.w = torch.empty(k * k, cw.cin_pad, cw.cout_pad, device=dev, dtype=torch.float32)
+        has_b = bias is not None and not transposed
+        cw.b = torch.empty(cw.cout_pad, device=dev, dtype=torch.float32) if has_b else None
+        b = bias.detach().float().contiguous() if has_b else None
+        with torch.cuda.device(dev):
+            L.check(L.load().tdvc_conv2d_pack_weight(w.data_ptr(), w.shape[0], w.shape[1], k, 1 if transposed else 0, cw.w.data_ptr(),
+                                                     cw.cin_pad, cw.cout_pad, b.data_ptr() if has_b else None,
+                                                     cw.b.data_ptr() if has_b else None,
+                                                     torch.cuda.current_stream(dev).cuda_stream), "conv2d_pack_weight")
+        cw.pad, cw.shuffle, cw.stride = pad, 0, stride
+        cw.w_f16, cw.w_shift, cw.w_f16_p1, cw.w_shift_p1, cw.p1_ok = None, 0, None, 0, False
+        cw.wmax = _weight_max(weight, weight if max_key is None else max_key)
         tc.attach_f16({"w": cw})
         _PACKS[key] = (cw, weakref.ref(weight), weakref.ref(bias) if bias is not None else None)
     return cw
@@ -298,7 +343,7 @@ def _launch_gdn(x, cw, out, inverse, norm_only, impl, absmax):
 
 class _GDN(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, beta, gamma, inverse, impl):
+    def forward(ctx, x, beta, gamma, inverse, impl, max_key):
         from tdvc_b200.model import Act
         for name, t in (("input", x), ("beta", beta), ("gamma", gamma)):
             if not t.is_cuda or t.dtype != torch.float32:
@@ -309,12 +354,12 @@ class _GDN(torch.autograd.Function):
         with torch.cuda.device(x.device):
             xa = _nhwc(x.detach())
             w4 = gamma.detach().reshape(C, C, 1, 1)
-            cw = _packed(w4, beta.detach(), 1, 0, False)
+            cw = _packed(w4, beta.detach(), 1, 0, False, max_key)
             ya = Act.alloc(N, H, W, C, x.device)
             am = x.detach().abs().amax().reshape(1).float()   # (the inference path gets it from the producing layer's epilogue)
             _launch_gdn(xa, cw, ya, inverse, False, impl, am)
             y = _nchw(ya)
-        ctx.xa, ctx.cw, ctx.w4, ctx.inverse, ctx.impl, ctx.am = xa, cw, w4, inverse, impl, am
+        ctx.xa, ctx.cw, ctx.w4, ctx.inverse, ctx.impl, ctx.am, ctx.max_key = xa, cw, w4, inverse, impl, am, max_key
         ctx.wg_products = WGRAD_PRODUCTS
         return y
 
@@ -334,7 +379,7 @@ class _GDN(torch.autograd.Function):
             _launch_gdn(xa, cw, norm, inverse, True, impl, ctx.am)
             dxd, dn = Act.alloc(N, H, W, C, dev), Act.alloc(N, H, W, C, dev)
             L.check(lib.tdvc_gdn_backward_pre(xa.ptr, norm.ptr, ga.ptr, dxd.ptr, dn.ptr, n, 1 if inverse else 0, st), "gdn_backward_pre")
-            cwt = _packed(ctx.w4, None, 1, 0, True)          # gamma^T: d(x^2) = dgrad of the 1x1 convolution
+            cwt = _packed(ctx.w4, None, 1, 0, True, ctx.max_key)          # gamma^T: d(x^2) = dgrad of the 1x1 convolution
             dxsq = Act.alloc(N, H, W, C, dev)
             _launch_conv(dn, cwt, dxsq, 1, L.ACT_NONE, 0.0, impl)
             L.check(lib.tdvc_gdn_backward_post(dxd.ptr, xa.ptr, dxsq.ptr, dxd.ptr, n, st), "gdn_backward_post")
@@ -345,16 +390,16 @@ class _GDN(torch.autograd.Function):
             ws = torch.empty((nb + 3) // 4, device=dev, dtype=torch.float32)
             L.check(lib.tdvc_conv2d_wgrad(xa.ptr, xa.ld, dn.ptr, dn.ld, N, H, W, C, C, 1, 1, 0, 1, ctx.wg_products, gw.data_ptr(), gb.data_ptr(),
                                           ws.data_ptr(), nb, st), "conv2d_wgrad (gdn)")
-        return gx, gb, gw.view(C, C), None, None
+        return gx, gb, gw.view(C, C), None, None, None
 
 
-def gdn(input, beta, gamma, inverse=False, impl=L.IMPL_AUTO):
+def gdn(input, beta, gamma, inverse=False, impl=L.IMPL_AUTO, max_key=None):
     """compressai GDN / IGDN on NCHW float32 CUDA tensors: input * (beta + gamma . input^2)^(-1/2) (inverse: ^(+1/2)), with
     autograd.  beta (C,) and gamma (C, C) are the EFFECTIVE (reparametrised, non-negative) values - compressai's
     `beta_reparam(self.beta)`, `gamma_reparam(self.gamma)`, which stay ordinary torch parameter arithmetic on the caller's side.
     Forward: the fused tcgen05 kernel of the inference path; backward: two element-wise kernels around the 1x1 convolution's
     dgrad / wgrad."""
-    return _GDN.apply(input, beta, gamma, bool(inverse), int(impl))
+    return _GDN.apply(input, beta, gamma, bool(inverse), int(impl), max_key)
 
 
 # ----------------------------------------------------------------------------------------------- likelihood -> bits with autograd

@@ -79,7 +79,7 @@ def _reparam(p, mod):
 
 
 def _gdn(m, x):
-    return ops.gdn(x, _reparam(m.beta, m.beta_reparam), _reparam(m.gamma, m.gamma_reparam), m.inverse)
+    return ops.gdn(x, _reparam(m.beta, m.beta_reparam), _reparam(m.gamma, m.gamma_reparam), m.inverse, max_key=m.gamma)
 
 
 # ----------------------------------------------------------------------------------------------- coders
