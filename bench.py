@@ -631,6 +631,13 @@ def main():
             except Exception as e:
                 train = {"error": f"{type(e).__name__}: {e}"[:300]}
             torch.cuda.empty_cache()
+            if "error" not in train:
+                try:   # the same step captured in ONE CUDA graph and replayed (no host work per step)
+                    g = training_leg(dev, 1, 4, 3, graph=True)
+                    train["cuda_graph_replay"] = {k: g[k] for k in ("ms_per_step", "samples_per_s", "steps", "warmup", "peak_mem_gb")}
+                except Exception as e:
+                    train["cuda_graph_replay"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
             if not args.no_eager_baseline and "error" not in train:
                 train["gpu_eager_baseline"] = gpu_eager_training_baseline(dev)
         eager = None

@@ -244,6 +244,9 @@ int tdvc_eb_aux_loss(const float* mats, const float* biases, const float* factor
 int tdvc_eb_aux_loss_grad(const float* mats, const float* biases, const float* factors, const float* quantiles,
                           const float* target3, const float* grad_out, int C, float* grad_quantiles, void* stream);
 int tdvc_uniform_noise(float* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream);
+/* the same draws with the seed read from device memory at run time: inside a captured CUDA graph the caller advances *seed_dev
+ * with a captured operation, so that every replay of a training step quantises with fresh noise */
+int tdvc_uniform_noise_dev(float* out, int64_t n, const uint64_t* seed_dev, uint64_t stream_id, void* stream);
 /* Backward of the two noise-mode reductions (the reference takes them from autograd through compressai, tools/train.py:132-145).
  * S = sum ln max(p, 1e-9); grad_sum = d loss / d S (device scalar); compressai's LowerBound gradient rule (pass where the input
  * is above the bound or the gradient is negative) for the likelihood bound and the 0.11 scale bound.

@@ -196,7 +196,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
-__global__ void uniform_noise_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t stream_id) {
+// seed_dev != nullptr: the seed is read from device memory (a replayed CUDA graph draws fresh noise when a captured operation
+// advances that word between replays)
+__global__ void uniform_noise_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t stream_id,
+                                     const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev != nullptr) seed = *seed_dev;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += stride) {
     const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)),
@@ -435,8 +439,18 @@ extern "C" int tdvc_uniform_noise(float* out, int64_t n, uint64_t seed, uint64_t
   if (n == 0) return TDVC_OK;
   int grid = cdiv(n / 4 + 1, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  uniform_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n, seed, stream_id);
+  uniform_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n, seed, stream_id, nullptr);
   TDVC_CHECK_LAUNCH("uniform_noise");
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_uniform_noise_dev(float* out, int64_t n, const uint64_t* seed_dev, uint64_t stream_id, void* stream) {
+  TDVC_REQUIRE(out && seed_dev && n >= 0, "uniform_noise_dev: bad args");
+  if (n == 0) return TDVC_OK;
+  int grid = cdiv(n / 4 + 1, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  uniform_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n, 0, stream_id, seed_dev);
+  TDVC_CHECK_LAUNCH("uniform_noise_dev");
   return TDVC_OK;
 }
 

@@ -92,6 +92,7 @@ SIGNATURES = {
     "tdvc_eb_aux_loss": [vp, vp, vp, vp, vp, i32, vp, vp],
     "tdvc_eb_aux_loss_grad": [vp, vp, vp, vp, vp, vp, i32, vp, vp],
     "tdvc_uniform_noise": [vp, i64, C.c_uint64, C.c_uint64, vp],
+    "tdvc_uniform_noise_dev": [vp, i64, vp, C.c_uint64, vp],
     "tdvc_act_backward": [vp, vp, vp, i64, i32, f32, vp],
     "tdvc_zero_insert": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "tdvc_conv2d_wgrad_workspace_bytes": [i32] * 6,

@@ -190,7 +190,9 @@ def _packed(weight, bias, stride, pad, transposed, max_key=None):
                                                      torch.cuda.current_stream(dev).cuda_stream), "conv2d_pack_weight")
         cw.pad, cw.shuffle, cw.stride = pad, 0, stride
         cw.w_f16, cw.w_shift, cw.w_f16_p1, cw.w_shift_p1, cw.p1_ok = None, 0, None, 0, False
-        cw.wmax = _weight_max(weight, weight if max_key is None else max_key)
+        if max_key is None:   # a view of a parameter (a squeezed Conv3d weight) is a new object every step: key on its base
+            max_key = weight._base if weight._base is not None else weight
+        cw.wmax = _weight_max(weight, max_key)
         tc.attach_f16({"w": cw})
         _PACKS[key] = (cw, weakref.ref(weight), weakref.ref(bias) if bias is not None else None)
     return cw
@@ -243,7 +245,7 @@ def _nchw(a):
 
 class _Conv2d(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, act, slope, impl):
+    def forward(ctx, x, weight, bias, stride, padding, act, slope, impl, max_key=None):
         from tdvc_b200.model import Act
         for name, t in (("input", x), ("weight", weight)) + ((("bias", bias),) if bias is not None else ()):
             if not t.is_cuda or t.dtype != torch.float32:
@@ -259,11 +261,12 @@ class _Conv2d(torch.autograd.Function):
         Ho, Wo = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
         with torch.cuda.device(x.device):
             xa = _nhwc(x.detach())
-            cw = _packed(weight, bias, stride, padding, False)
+            cw = _packed(weight, bias, stride, padding, False, max_key)
             ya = Act.alloc(N, Ho, Wo, O, x.device, ld=(O + 3) // 4 * 4, zero=(O % 4 != 0))
             _launch_conv(xa, cw, ya, stride, _ACTS[act], slope, impl)
             y = _nchw(ya)
         ctx.geom = (stride, padding, _ACTS[act], slope, impl, bias is not None)
+        ctx.max_key = max_key
         ctx.wg_products = WGRAD_PRODUCTS
         ctx.xa, ctx.ya = xa, (ya if _ACTS[act] != L.ACT_NONE else None)
         ctx.save_for_backward(weight)
@@ -288,7 +291,7 @@ class _Conv2d(torch.autograd.Function):
                 ga = gp
             gx = gw = gb = None
             if ctx.needs_input_grad[0]:
-                cwt = _packed(weight, None, 1, k - 1 - padding, True)
+                cwt = _packed(weight, None, 1, k - 1 - padding, True, ctx.max_key)
                 if stride > 1:
                     up = Act.alloc(xa.N, xa.H, xa.W, O, dev, ld=ga.ld)
                     L.check(lib.tdvc_zero_insert(ga.ptr, ga.ld, up.ptr, up.ld, xa.N, xa.H, xa.W, ga.H, ga.W, ga.ld, stride, st),
@@ -306,15 +309,15 @@ class _Conv2d(torch.autograd.Function):
                 L.check(lib.tdvc_conv2d_wgrad(xa.ptr, xa.ld, ga.ptr, ga.ld, xa.N, xa.H, xa.W, C, O, k, stride, padding, 0,
                                               ctx.wg_products, gw.data_ptr(), gb.data_ptr() if gb is not None else None, ws.data_ptr(), nb, st),
                         "conv2d_wgrad")
-        return gx, gw, gb, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None
 
 
-def conv2d(input, weight, bias=None, stride=1, padding=0, act=None, slope=0.01, impl=L.IMPL_AUTO):
+def conv2d(input, weight, bias=None, stride=1, padding=0, act=None, slope=0.01, impl=L.IMPL_AUTO, max_key=None):
     """F.conv2d(input, weight, bias, stride, padding) followed by `act` (None | "relu" | "leaky_relu" | "clamp01"), NCHW float32
     CUDA tensors, with autograd: grad_input by the forward kernels on the transposed, flipped weight (fp32-class tcgen05 path
     included), grad_weight / grad_bias by the deterministic fp32 wgrad kernel.  impl: lib.IMPL_* (1 = exact fp32 SIMT forward
     and dgrad)."""
-    return _Conv2d.apply(input, weight, bias, int(stride), int(padding), act, float(slope), int(impl))
+    return _Conv2d.apply(input, weight, bias, int(stride), int(padding), act, float(slope), int(impl), max_key)
 
 
 # ----------------------------------------------------------------------------------------------- GDN / IGDN with autograd

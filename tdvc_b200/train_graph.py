@@ -200,7 +200,7 @@ def mcfilter(mf, pred, refer_frames):
     out = _cv3d(b3.spatial_conv3d, _cv3d(b3.conv1, x, "leaky_relu", 0.1)).reshape(n, T, 64, h, w)
     # temporal (3, 1, 1) kernel, stride 3, no bias: one output step from frames 0..2 = a 1x1 convolution of their channels
     wt = b3.temporal_conv3d.weight.squeeze(-1).squeeze(-1).permute(0, 2, 1).reshape(64, 192, 1, 1)
-    tmp = ops.conv2d(out[:, :3].reshape(n, 192, h, w), wt, None, 1, 0)
+    tmp = ops.conv2d(out[:, :3].reshape(n, 192, h, w), wt, None, 1, 0, max_key=b3.temporal_conv3d.weight)
     out = F.leaky_relu(out + tmp.unsqueeze(1), 0.1).reshape(n * T, 64, h, w)
     x = (_cv3d(b3.conv3, out) + x).reshape(n, T, 64, h, w).reshape(n, T * 64, h, w)
     x = _se(mf.attn, _cv(mf.feat_fusion, x, "leaky_relu", 0.1))
@@ -235,16 +235,33 @@ def loopfilter(lf, feat, refer_frames, training):
 
 
 # ----------------------------------------------------------------------------------------------- the frame
+_GRAPH_SEED = {}
+
+
 def draw_noise(shapes, device):
-    """Uniform(-0.5, 0.5) draws for the six noise quantisers from our Philox kernel, seeded from torch's CPU generator."""
+    """Uniform(-0.5, 0.5) draws for the six noise quantisers from our Philox kernel, seeded from torch's CPU generator.  While
+    a CUDA graph is being captured (a whole training step replayed as one graph) a host value would be frozen into the graph:
+    the seed then lives in a device word that a captured add advances, so every replay draws fresh noise."""
     lib = L.load()
-    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    capturing = torch.cuda.is_current_stream_capturing()
+    if capturing:
+        seed_dev = _GRAPH_SEED.get(device)
+        if seed_dev is None:
+            raise RuntimeError("run one eager training step on this device before capturing it in a CUDA graph")
+        seed_dev.add_(0x9E3779B97F4A7C15 - (1 << 64))    # a captured operation: advances the seed at every replay
+    else:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if device not in _GRAPH_SEED:
+            _GRAPH_SEED[device] = torch.tensor([seed ^ 0x5DEECE66D], dtype=torch.int64, device=device)
     out = {}
     with torch.cuda.device(device):
         st = torch.cuda.current_stream(device).cuda_stream
         for i, (k, shp) in enumerate(shapes.items()):
             t = torch.empty(shp, device=device, dtype=torch.float32)
-            L.check(lib.tdvc_uniform_noise(t.data_ptr(), t.numel(), seed, i, st), "uniform_noise")
+            if capturing:
+                L.check(lib.tdvc_uniform_noise_dev(t.data_ptr(), t.numel(), seed_dev.data_ptr(), i, st), "uniform_noise_dev")
+            else:
+                L.check(lib.tdvc_uniform_noise(t.data_ptr(), t.numel(), seed, i, st), "uniform_noise")
             out[k] = t
     return out
 

@@ -1,6 +1,8 @@
 """The training step of BASELINE config 4 (reference tools/train.py:125-159): `net.train()` with gradients enabled builds the
 forward from the autograd functions of tdvc_b200.ops (tdvc_b200/train_graph.py); `rd_loss.backward()` must give the
 gradients the oracle's autograd gives on the CPU for the same weights, frames and noise draws."""
+import math
+
 import pytest
 import torch
 
@@ -116,3 +118,57 @@ def test_training_steps_reduce_the_loss(oracle_model):
         auxes.append(aux.item())
     assert losses[-1] < losses[0], losses
     assert auxes[-1] < auxes[0], auxes
+
+
+def test_training_step_replayed_as_a_cuda_graph(oracle_model):
+    """The whole step - forward, rd_loss + aux_loss backward, clipping, both Adam steps (reference tools/train.py:125-159) -
+    captured once in a CUDA graph and replayed (`bench.py --workload train --train-graph`): no host synchronisation anywhere in
+    the training path (weight maxima come from the previous step's pinned copy), the quantisation noise is drawn from a device
+    seed a captured add advances (every replay sees new noise), and the replays keep training."""
+    from tdvc_b200 import synth
+    dev = torch.device("cuda:0")
+    _, net = _build(oracle_model, dev)
+    x, refs = synth.make_frame_pair(64, 64, seed=94)
+    x, refs = x.to(dev), refs.to(dev)
+    params = [p for n, p in net.named_parameters() if not n.endswith(".quantiles")]
+    aux_params = [p for n, p in net.named_parameters() if n.endswith(".quantiles")]
+    opt = torch.optim.Adam(params, lr=1e-4, capturable=True)
+    aux_opt = torch.optim.Adam(aux_params, lr=1e-3, capturable=True)
+    loss_out = torch.zeros(1, device=dev)
+
+    def step():
+        out = net(x, refs, True)
+        loss, _ = _rd_loss(out, x)
+        opt.zero_grad()
+        aux_opt.zero_grad()
+        (loss + out[3] + out[4]).backward()
+        torch.nn.utils.clip_grad_norm_(params, 2)
+        opt.step()
+        aux_opt.step()
+        loss_out.copy_(loss.detach().reshape(1))
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    eager_loss = loss_out.item()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    from tdvc_b200 import train_graph
+    seed_word = train_graph._GRAPH_SEED[dev]
+    w0, s0 = params[0].detach().clone(), int(seed_word.item())
+    losses = []
+    for _ in range(6):
+        graph.replay()
+        losses.append(loss_out.item())
+    assert all(math.isfinite(v) for v in losses), losses
+    assert max(losses) < 1.5 * eager_loss, (eager_loss, losses)        # the replays train on: no blow-up, same loss scale
+    assert len({round(v, 6) for v in losses}) == len(losses)           # weights and noise move from replay to replay
+    assert not torch.equal(params[0].detach(), w0)                     # the optimiser steps are part of the graph
+    s1 = int(seed_word.item())
+    graph.replay()
+    assert s1 != s0 and int(seed_word.item()) != s1                    # one new noise seed per replay
