@@ -487,7 +487,8 @@ def test_dcn_generic_geometry_vs_torchvision(dev):
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 64, 13, 17, 8, 3, 3, 1, 1, 1, 1, 1, 1), (1, 16, 24, 9, 7, 2, 3, 3, 1, 1, 1, 1, 1, 1),
-                                   (2, 4, 6, 11, 12, 2, 5, 3, 2, 1, 2, 1, 1, 2)])
+                                   (2, 4, 6, 11, 12, 2, 5, 3, 2, 1, 2, 1, 1, 2),
+                                   (1, 24, 70, 9, 7, 2, 3, 3, 1, 1, 1, 1, 1, 1)])   # 12 channels per group, > 64 outputs
 def test_dcn_backward_vs_torchvision_autograd(dev, shape):
     """`dcn_v2_backward` (reference dcn_v2.h:48-92) against autograd through torchvision.ops.deform_conv2d on the CPU (the same
     MXNet-lineage arithmetic): all five gradients, offsets with many samples outside the image, TDVC's geometry
