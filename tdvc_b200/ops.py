@@ -145,15 +145,17 @@ def _weight_max(weight, key):
         m = float(weight.detach().abs().max())
         pinned = torch.empty(1, dtype=torch.float32, pin_memory=True)
         pinned[0] = m
-        ent = (weakref.ref(key), pinned, torch.cuda.Event())
+        ent = (weakref.ref(key), pinned, torch.cuda.Event(), [weight._version])
         _WMAX[id(key)] = ent
         return m
     if torch.cuda.is_current_stream_capturing():
         return float(ent[1][0])
     ent[2].synchronize()
     m = float(ent[1][0])
-    ent[1].copy_(weight.detach().abs().max().reshape(1), non_blocking=True)
-    ent[2].record(torch.cuda.current_stream(weight.device))
+    if ent[3][0] != weight._version:      # one refresh per optimiser step (the forward and the dgrad pack both come here)
+        ent[3][0] = weight._version
+        ent[1].copy_(weight.detach().abs().max().reshape(1), non_blocking=True)
+        ent[2].record(torch.cuda.current_stream(weight.device))
     return m
 
 
@@ -192,8 +194,9 @@ def _packed(weight, bias, stride, pad, transposed, max_key=None):
         cw.w_f16, cw.w_shift, cw.w_f16_p1, cw.w_shift_p1, cw.p1_ok = None, 0, None, 0, False
         if max_key is None:   # a view of a parameter (a squeezed Conv3d weight) is a new object every step: key on its base
             max_key = weight._base if weight._base is not None else weight
-        cw.wmax = _weight_max(weight, max_key)
+        cw.wmax = lambda: _weight_max(weight, max_key)    # asked for by the split / one-product schemes only (tc._pack)
         tc.attach_f16({"w": cw})
+        cw.wmax = None     # (the closure would keep `weight` alive inside the cache)
         _PACKS[key] = (cw, weakref.ref(weight), weakref.ref(bias) if bias is not None else None)
     return cw
 

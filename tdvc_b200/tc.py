@@ -27,7 +27,8 @@ def _pack(lib, cw, products):
     if lib.tdvc_conv2d_f16_is_split(p):
         # weights are stored * 2^w_shift with max|w| * 2^w_shift in [2^13, 2^14): w_lo = w - fp16(w) (split scheme) and the small
         # weights of a one-product layer stay in the fp16 normal range for every weight above 2^-16 of the largest one
-        m = cw.wmax if getattr(cw, "wmax", None) is not None else float(cw.w.abs().max())
+        m = getattr(cw, "wmax", None)
+        m = m() if callable(m) else (m if m is not None else float(cw.w.abs().max()))
         shift = 13 - math.frexp(m)[1] + 1 if m > 0 else 0
     p.w_shift = shift
     with torch.cuda.device(cw.w.device):
