@@ -266,9 +266,11 @@ int tdvc_eb_bits_backward(const float* z_tilde, const float* mats, const float* 
  * zero_insert: out (N,H,W,C) <- g (N,Ho,Wo,C): out[n][oy*stride][ox*stride] = g[n][oy][ox], zero elsewhere (C % 4 == 0).
  * conv2d_wgrad: grad_w[cout][cin][k][k] (nn.Conv2d.weight layout) = sum_p x[p*stride + tap - pad][ci] * grad_y[p][co] and
  *   grad_b[co] = sum_p grad_y[p][co] (NULL: skipped); x (N,H,W,cin) / grad_y (N,Ho,Wo,cout) NHWC with leading dimensions;
- *   warp-level TF32 MMAs over staged 32-pixel chunks, `products` = 3: fp32-class ((hi, lo) operand pairs, three products),
+ *   `products` = 3: fp32-class (warp-level TF32 MMAs over staged 32-pixel chunks, (hi, lo) operand pairs, three products),
  *   1: one TF32 product (what cuDNN runs by default for fp32 training convolutions; the reference's shipped cfg/train.yaml
- *   trains under AMP, i.e. with fp16 products); deterministic (fixed-order two-stage sum).
+ *   trains under AMP, i.e. with fp16 products) - on tcgen05 for stride-1 "same"-padded 1x1 / 3x3 / 7x7 layers at least 16
+ *   pixels wide (csrc/wgrad_tc.cu; operands truncated to TF32 by the tensor core), on the warp-level kernel otherwise;
+ *   deterministic (fixed-order two-stage sum) in every case.
  *   workspace: tdvc_conv2d_wgrad_workspace_bytes(N,Ho,Wo,cin,cout,k). */
 int tdvc_act_backward(const float* y, const float* grad_y, float* grad_pre, int64_t n, int act, float slope, void* stream);
 int tdvc_zero_insert(const float* g, int g_ld, float* out, int out_ld, int N, int H, int W, int Ho, int Wo, int C, int stride,
@@ -284,8 +286,6 @@ int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, int g_ld, i
  *   out[tap][ci][co] = w[ci][co][k*k - 1 - tap] (cin_pad >= O, cout_pad >= I). */
 int tdvc_conv2d_pack_weight(const float* w, int O, int I, int k, int transposed, float* out, int cin_pad, int cout_pad,
                             const float* bias_or_null, float* bias_out_or_null, void* stream);
-/* conv2d_wgrad with products = 1 runs stride-1 "same"-padded 1x1 / 3x3 / 7x7 layers on tcgen05 (csrc/wgrad_tc.cu: MN-major
- * TF32 operands straight from the channels-last tensors by tensor-map bulk copies; operands truncated to TF32). */
 /* GDN / IGDN backward (compressai GDN: out = x * norm^(-1/2), inverse: x * norm^(1/2), norm = beta + gamma . x^2), element-wise
  * parts on flat fp32 arrays (n % 4 == 0): pre -> dx_direct = g * norm^(-+1/2), dnorm = d loss / d norm; the 1x1 convolution's
  * dgrad (tdvc_conv2d on gamma^T) turns dnorm into d(x^2) and tdvc_conv2d_wgrad(in_square = 1) into d gamma / d beta;

@@ -13,7 +13,9 @@
 //   with a 4x4 register tile per thread spent 250 of the 436 ms of a training step here.  A tcgen05 / TMEM version - kind::tf32,
 //   M = 128 rows of (tap, ci), D resident in TMEM over the slab, operands transposed into K-major rows by 4-byte cp.async -
 //   was written, gave the right numbers and was dropped: 1.16 ms against 0.85 ms for 64->64 3x3 at 8x256x256, the transposing
-//   producers issue one copy per element and the MMA pipe sat at 4 %)
+//   producers issue one copy per element and the MMA pipe sat at 4 %.  What works is feeding the channels-last rows to the MMA
+//   as MN-major operands, with no transposition at all: wgrad_tc.cu, which takes the one-product (enabled_amp) calls of every
+//   stride-1 1x1 / 3x3 / 7x7 layer; this file keeps the three-product mode and the remaining shapes.  DESIGN.md section 7.)
 #include <cstdlib>
 #include "common.cuh"
 
