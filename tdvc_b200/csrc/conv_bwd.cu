@@ -385,12 +385,12 @@ static int wgrad_slabs(int64_t npix, int tiles) {
   return S < 1 ? 1 : S;
 }
 
-// wgrad_tc.cu: the tcgen05 kernels for stride-1 layers (one TF32 product per MAC)
+// wgrad_tc.cu: the tcgen05 kernels for stride-1 layers (one TF32 product per MAC, or three: fp32-class)
 bool wgrad_tc_eligible(const float* x, int x_ld, const float* g, int g_ld, int N, int H, int W, int cin, int cout, int k, int stride,
-                       int pad, int in_square);
+                       int pad, int in_square, int products);
 size_t wgrad_tc_workspace_bytes(int N, int H, int W, int cin, int cout, int k);
-int wgrad_tc_launch(const float* x, int x_ld, const float* g, int g_ld, int N, int H, int W, int cin, int cout, int k, float* workspace,
-                    float** part_bias_out, int* S_out, cudaStream_t st);
+int wgrad_tc_launch(const float* x, int x_ld, const float* g, int g_ld, int N, int H, int W, int cin, int cout, int k, int products,
+                    float* workspace, float** part_bias_out, int* S_out, cudaStream_t st);
 
 }  // namespace tdvc
 
@@ -470,8 +470,9 @@ extern "C" int tdvc_conv2d_wgrad(const float* x, int x_ld, const float* grad_y, 
     cudaEventCreate(&ev1);
     cudaEventRecord(ev0, st);
   }
-  if (products == 1 && wgrad_tc_eligible(x, x_ld, grad_y, g_ld, N, H, W, cin, cout, k, stride, pad, in_square)) {
-    if (int rc = wgrad_tc_launch(x, x_ld, grad_y, g_ld, N, H, W, cin, cout, k, a.part, &a.part_bias, &a.S, st)) return rc;
+  static const bool tc3 = getenv("TDVC_B200_WGRAD_TC3_OFF") == nullptr;   // developer A/B switch for the three-product tcgen05 mode
+  if ((products == 1 || tc3) && wgrad_tc_eligible(x, x_ld, grad_y, g_ld, N, H, W, cin, cout, k, stride, pad, in_square, products)) {
+    if (int rc = wgrad_tc_launch(x, x_ld, grad_y, g_ld, N, H, W, cin, cout, k, products, a.part, &a.part_bias, &a.S, st)) return rc;
   } else if (products == 1) wgrad_kernel<1><<<dim3(tiles, a.S), 256, 0, st>>>(a);
   else wgrad_kernel<3><<<dim3(tiles, a.S), 256, 0, st>>>(a);
   TDVC_CHECK_LAUNCH("conv2d_wgrad");

@@ -1,6 +1,7 @@
 // Weight gradient of the stride-1 convolutions on the tensor cores (the training step; the reference
-// takes this gradient from cuDNN through autograd, tools/train.py:125-159).  One TF32 product per MAC: the arithmetic of
-// `enabled_amp=True` (the reference's shipped cfg/train.yaml; conv_bwd.cu keeps the fp32-class three-product kernel).
+// takes this gradient from cuDNN through autograd, tools/train.py:125-159).  One TF32 product per MAC - the arithmetic of
+// `enabled_amp=True` (the reference's shipped cfg/train.yaml) - or three (fp32-class: operands split into hi + lo, the lo parts
+// written next to the staged patches by the otherwise idle read-out warps; conv_bwd.cu keeps the shapes this file does not take).
 //
 //   d W[tap][ci][co] = sum over pixels p of x[p + tap][ci] * g[p][co]
 //
@@ -41,7 +42,7 @@ constexpr int NSTAGE = 2;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 512;
 
-template <int KS, int G, int NB, int R>
+template <int KS, int G, int NB, int R, int PR>
 struct Cfg {
   static constexpr int PAD = KS / 2;
   static constexpr int RPM = 4 / G;                                   // kernel rows one M = 128 operand spans
@@ -51,7 +52,8 @@ struct Cfg {
   static constexpr int NBG = NB / 32;
   static constexpr int BLK_X = XW * 128, BLK_G = BW * 128;
   static constexpr int X_BYTES = XROWS * G * BLK_X, G_BYTES = R * NBG * BLK_G;
-  static constexpr int STAGE = X_BYTES + G_BYTES;
+  static constexpr int TILE = X_BYTES + G_BYTES;                      // what the bulk copies bring
+  static constexpr int STAGE = (PR == 3 ? 2 : 1) * TILE;              // PR == 3: + the lo parts of both patches, same layout
   static constexpr int KXC = KS < TMEM_COLS / (NG * NB) ? KS : TMEM_COLS / (NG * NB);   // kernel columns per CTA
   static constexpr int NKX = (KS + KXC - 1) / KXC;
   static constexpr int SMEM = NSTAGE * STAGE + 1024 /* alignment slack */ + 128 /* barriers, TMEM slot */ + 512 /* bias exchange */;
@@ -102,18 +104,19 @@ __device__ __forceinline__ void tma4(uint32_t dst, const CUtensorMap* m, int c0,
       : "memory");
 }
 
-template <int KS, int G, int NB, int R>
+template <int KS, int G, int NB, int R, int PR>
 __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Args a, const __grid_constant__ Maps maps) {
-  using C = Cfg<KS, G, NB, R>;
+  using C = Cfg<KS, G, NB, R, PR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bars = base + NSTAGE * C::STAGE;            // full[2], empty[2], acc
+  const uint32_t bars = base + NSTAGE * C::STAGE;            // full[2], empty[2], acc, lo[2]
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(gen + NSTAGE * C::STAGE + 64);
   float* const bias_x = reinterpret_cast<float*>(gen + NSTAGE * C::STAGE + 128);   // [128]
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 16u + 8u * s; };
   const uint32_t acc_bar = bars + 32u;
+  auto lo_bar = [&](int s) { return bars + 40u + 8u * s; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.y;
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Args a, cons
   const int kx0 = kxs * C::KXC;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 5); }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 5); mbar_init(lo_bar(i), 4); }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Args a, cons
         const int ty = r % a.tiles_y;
         const int n = r / a.tiles_y;
         mbar_wait(empty(st), ph);
-        mbar_expect_tx(full(st), C::STAGE);
+        mbar_expect_tx(full(st), C::TILE);
         const uint32_t dst = base + st * C::STAGE;
 #pragma unroll 1
         for (int row = 0; row < C::XROWS; ++row)
@@ -171,22 +174,32 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Args a, cons
       tc_fence_after();
       if (elect_one()) {
         uint32_t acc = first ^ 1u;
-        const uint32_t xs = base + st * C::STAGE, gs = xs + C::X_BYTES;
+        // pass 0: x * g as staged (the tensor core reads the TF32 truncation of an fp32 word: the hi parts);
+        // PR == 3, passes 1, 2: x_lo * g and x * g_lo from the converted copies - hi hi + lo hi + hi lo carries ~21 bits
 #pragma unroll 1
-        for (int r = 0; r < R; ++r) {
+        for (int pass = 0; pass < PR; ++pass) {
+          if (pass == 1) {
+            mbar_wait(lo_bar(st), ph);
+            tc_fence_after();
+          }
+          const uint32_t xs = base + st * C::STAGE + (pass == 1 ? C::TILE : 0);
+          const uint32_t gs = base + st * C::STAGE + C::X_BYTES + (pass == 2 ? C::TILE : 0);
+#pragma unroll 1
+          for (int r = 0; r < R; ++r) {
 #pragma unroll
-          for (int c0 = 0; c0 < BW; c0 += 8) {
-            const uint64_t bdesc = mn_desc(gs + r * C::NBG * C::BLK_G + c0 * 128, C::BLK_G);
+            for (int c0 = 0; c0 < BW; c0 += 8) {
+              const uint64_t bdesc = mn_desc(gs + r * C::NBG * C::BLK_G + c0 * 128, C::BLK_G);
 #pragma unroll
-            for (int kxi = 0; kxi < C::KXC; ++kxi) {
-              if (C::NKX > 1 && kx0 + kxi >= KS) break;
+              for (int kxi = 0; kxi < C::KXC; ++kxi) {
+                if (C::NKX > 1 && kx0 + kxi >= KS) break;
 #pragma unroll
-              for (int gi = 0; gi < C::NG; ++gi) {
-                const uint64_t adesc = mn_desc(xs + (r + C::start(gi)) * G * C::BLK_X + (c0 + kx0 + kxi) * 128, C::BLK_X);
-                mma_tf32(tmem_base + (kxi * C::NG + gi) * NB, adesc, bdesc, idesc, acc);
+                for (int gi = 0; gi < C::NG; ++gi) {
+                  const uint64_t adesc = mn_desc(xs + (r + C::start(gi)) * G * C::BLK_X + (c0 + kx0 + kxi) * 128, C::BLK_X);
+                  mma_tf32(tmem_base + (kxi * C::NG + gi) * NB, adesc, bdesc, idesc, acc);
+                }
               }
+              acc = 1;
             }
-            acc = 1;
           }
         }
         tc_commit(empty(st));
@@ -207,6 +220,24 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Args a, cons
     int st = 0, ph = 0;
     for (int item = s; item < a.n_items; item += a.S) {
       mbar_wait(full(st), ph);
+      if (PR == 3) {
+        // lo = v - tf32_truncation(v), exact in fp32, for both patches; the generic-proxy stores are fenced for the tensor core
+        const float4* src = reinterpret_cast<const float4*>(gen + st * C::STAGE);
+        float4* dst = reinterpret_cast<float4*>(gen + st * C::STAGE + C::TILE);
+#pragma unroll 4
+        for (int i = et; i < C::TILE / 16; i += 128) {
+          const float4 v = src[i];
+          float4 l;
+          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          dst[i] = l;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(lo_bar(st));
+      }
       if (do_bias) {
         const uint8_t* gs = gen + st * C::STAGE + C::X_BYTES + (co >> 5) * C::BLK_G + (co & 7) * 4;
         const int ch = (co & 31) >> 3;
@@ -295,13 +326,14 @@ static EncodeFn encoder() {
 struct Plan {
   int id, G, NB, R, nkx, ci_tiles, co_tiles, tiles_x, tiles_y, n_items, S;
 };
-static Plan plan(int N, int H, int W, int cin, int cout, int k) {
+static Plan plan(int N, int H, int W, int cin, int cout, int k, int products) {
   Plan p = {};
   p.G = cin <= 32 ? 1 : 2;
   p.NB = cout <= 32 ? 32 : 64;
-  p.R = (k == 7 && p.G == 2) ? 2 : 4;
+  // rows per item: the three-product mode keeps a second copy of both patches (their lo parts) in shared memory
+  p.R = products == 3 ? 2 : ((k == 7 && p.G == 2) ? 2 : 4);
   if (k == 3) { p.id = 1; p.nkx = 1; }
-  else if (k == 7 && !(p.G == 2 && p.NB == 64)) { p.id = 2; p.nkx = (p.G == 1 && p.NB == 32) ? 1 : 2; }
+  else if (k == 7 && !(p.G == 2 && p.NB == 64) && !(products == 3 && p.G == 2)) { p.id = 2; p.nkx = (p.G == 1 && p.NB == 32) ? 1 : 2; }
   else if (k == 1 && p.G == 2 && p.NB == 64) { p.id = 3; p.nkx = 1; }
   else return p;
   p.ci_tiles = cdiv(cin, 32 * p.G);
@@ -316,13 +348,13 @@ static Plan plan(int N, int H, int W, int cin, int cout, int k) {
   return p;
 }
 
-template <int KS, int G, int NB, int R>
+template <int KS, int G, int NB, int R, int PR>
 static int launch(const Plan& p, const float* x, int x_ld, const float* g, int g_ld, int N, int H, int W, int cin, int cout,
                   float* workspace, float** part_bias_out, cudaStream_t st) {
-  using C = Cfg<KS, G, NB, R>;
+  using C = Cfg<KS, G, NB, R, PR>;
   TDVC_REQUIRE(p.nkx == C::NKX && p.R == R, "wgrad_tc: plan and kernel configuration disagree (k=%d G=%d NB=%d)", KS, G, NB);
   static int smem_done[kMaxDevices] = {0};
-  if (int rc = ensure_dynamic_smem(wgrad_tc_kernel<KS, G, NB, R>, C::SMEM, smem_done, "wgrad_tc")) return rc;
+  if (int rc = ensure_dynamic_smem(wgrad_tc_kernel<KS, G, NB, R, PR>, C::SMEM, smem_done, "wgrad_tc")) return rc;
   EncodeFn encode = encoder();
   if (encode == nullptr) {
     set_error("wgrad_tc: cuTensorMapEncodeTiled is not available from this driver");
@@ -353,46 +385,60 @@ static int launch(const Plan& p, const float* x, int x_ld, const float* g, int g
   a.part = workspace;
   a.part_bias = workspace + (size_t)a.S * KS * KS * cin * cout;
   *part_bias_out = a.part_bias;
-  wgrad_tc_kernel<KS, G, NB, R><<<dim3(p.ci_tiles * p.co_tiles * C::NKX, a.S), THREADS, C::SMEM, st>>>(a, maps);
+  wgrad_tc_kernel<KS, G, NB, R, PR><<<dim3(p.ci_tiles * p.co_tiles * C::NKX, a.S), THREADS, C::SMEM, st>>>(a, maps);
   TDVC_CHECK_LAUNCH("wgrad_tc");
   return TDVC_OK;
 }
 
 }  // namespace wgtc
 
-// shapes the tensor-core weight gradient takes: stride 1, "same" padding, 1x1 / 3x3 / 7x7 (see wgtc::plan)
+// shapes the tensor-core weight gradient takes: stride 1, "same" padding, 1x1 / 3x3 / 7x7 (see wgtc::plan); products 1 | 3
 bool wgrad_tc_eligible(const float* x, int x_ld, const float* g, int g_ld, int N, int H, int W, int cin, int cout, int k, int stride,
-                       int pad, int in_square) {
+                       int pad, int in_square, int products) {
   static const bool off = getenv("TDVC_B200_WGRAD_SIMT") != nullptr;   // developer A/B switch: warp-level MMA kernel everywhere
   if (off || stride != 1 || pad != k / 2 || in_square || W < 16 || H < 4) return false;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(g) & 15) != 0 || x_ld % 4 != 0 || g_ld % 4 != 0) return false;
-  return wgtc::plan(N, H, W, cin, cout, k).id != 0;
+  return wgtc::plan(N, H, W, cin, cout, k, products).id != 0;
 }
 
+// the larger of the two modes' needs (the query does not know the mode)
 size_t wgrad_tc_workspace_bytes(int N, int H, int W, int cin, int cout, int k) {
-  const wgtc::Plan p = wgtc::plan(N, H, W, cin, cout, k);
-  if (p.id == 0) return 0;
-  return (size_t)p.S * ((size_t)k * k * cin * cout + cout) * sizeof(float);
+  size_t need = 0;
+  for (int products = 1; products <= 3; products += 2) {
+    const wgtc::Plan p = wgtc::plan(N, H, W, cin, cout, k, products);
+    if (p.id == 0) continue;
+    const size_t b = (size_t)p.S * ((size_t)k * k * cin * cout + cout) * sizeof(float);
+    if (b > need) need = b;
+  }
+  return need;
 }
 
 // -> partial sums in the layout of conv_bwd.cu's reduction; *S_out slabs
-int wgrad_tc_launch(const float* x, int x_ld, const float* g, int g_ld, int N, int H, int W, int cin, int cout, int k, float* workspace,
-                    float** part_bias_out, int* S_out, cudaStream_t st) {
+int wgrad_tc_launch(const float* x, int x_ld, const float* g, int g_ld, int N, int H, int W, int cin, int cout, int k, int products,
+                    float* workspace, float** part_bias_out, int* S_out, cudaStream_t st) {
   using namespace wgtc;
-  const Plan p = plan(N, H, W, cin, cout, k);
+  const Plan p = plan(N, H, W, cin, cout, k, products);
   *S_out = p.S;
-#define TDVC_WG(KS, G_, NB_, R_) \
-  if (k == KS && p.G == G_ && p.NB == NB_) return launch<KS, G_, NB_, R_>(p, x, x_ld, g, g_ld, N, H, W, cin, cout, workspace, part_bias_out, st);
-  TDVC_WG(3, 2, 64, 4)
-  TDVC_WG(3, 1, 64, 4)
-  TDVC_WG(3, 2, 32, 4)
-  TDVC_WG(3, 1, 32, 4)
-  TDVC_WG(7, 1, 32, 4)
-  TDVC_WG(7, 1, 64, 4)
-  TDVC_WG(7, 2, 32, 2)
-  TDVC_WG(1, 2, 64, 4)
+#define TDVC_WG(KS, G_, NB_, R_, PR_)                                   \
+  if (k == KS && p.G == G_ && p.NB == NB_ && products == PR_)          \
+    return launch<KS, G_, NB_, R_, PR_>(p, x, x_ld, g, g_ld, N, H, W, cin, cout, workspace, part_bias_out, st);
+  TDVC_WG(3, 2, 64, 4, 1)
+  TDVC_WG(3, 1, 64, 4, 1)
+  TDVC_WG(3, 2, 32, 4, 1)
+  TDVC_WG(3, 1, 32, 4, 1)
+  TDVC_WG(7, 1, 32, 4, 1)
+  TDVC_WG(7, 1, 64, 4, 1)
+  TDVC_WG(7, 2, 32, 2, 1)
+  TDVC_WG(1, 2, 64, 4, 1)
+  TDVC_WG(3, 2, 64, 2, 3)
+  TDVC_WG(3, 1, 64, 2, 3)
+  TDVC_WG(3, 2, 32, 2, 3)
+  TDVC_WG(3, 1, 32, 2, 3)
+  TDVC_WG(7, 1, 32, 2, 3)
+  TDVC_WG(7, 1, 64, 2, 3)
+  TDVC_WG(1, 2, 64, 2, 3)
 #undef TDVC_WG
-  set_error("wgrad_tc: no kernel for k=%d cin=%d cout=%d", k, cin, cout);
+  set_error("wgrad_tc: no kernel for k=%d cin=%d cout=%d products=%d", k, cin, cout, products);
   return TDVC_EINVAL;
 }
 

@@ -34,12 +34,12 @@ def wgrad(x, g, k, products):
     return gw, gb, run
 
 
-def check(N, C, O, H, W, k=3, seed=0, timing=False):
+def check(N, C, O, H, W, k=3, seed=0, timing=False, products=1):
     g_ = torch.Generator().manual_seed(seed)
     x = torch.randn(N, C, H, W, generator=g_).to(dev)
     gy = torch.randn(N, O, H, W, generator=g_).to(dev)
     Cp, Op = (C + 3) // 4 * 4, (O + 3) // 4 * 4
-    gw, gb, run = wgrad(x, gy, k, 1)
+    gw, gb, run = wgrad(x, gy, k, products)
     xd = x.double()
     wd = torch.zeros(O, C, k, k, device=dev, dtype=torch.float64, requires_grad=True)
     F.conv2d(xd, wd, None, 1, k // 2).backward(gy.double())
@@ -48,7 +48,7 @@ def check(N, C, O, H, W, k=3, seed=0, timing=False):
     err = (gw.double() - ref).abs()
     bref = gy.double().sum((0, 2, 3))
     berr = (gb.double() - bref).abs().max().item() / bref.abs().max().item()
-    msg = f"N{N} {C}->{O} k{k} {H}x{W}: max rel err {err.max().item() / scale:.2e} bias {berr:.2e}"
+    msg = f"N{N} {C}->{O} k{k} {H}x{W} products {products}: max rel err {err.max().item() / scale:.2e} bias {berr:.2e}"
     if timing:
         for _ in range(3):
             run()
@@ -63,6 +63,13 @@ def check(N, C, O, H, W, k=3, seed=0, timing=False):
     print(msg, flush=True)
 
 
+if "exact" in sys.argv:   # the fp32-class three-product mode
+    for sh in ((2, 64, 64, 9, 50, 3), (2, 128, 192, 12, 96, 3), (2, 3, 64, 12, 40, 3), (2, 64, 216, 12, 40, 3), (1, 8, 32, 20, 40, 7),
+               (1, 32, 64, 20, 40, 7), (1, 192, 64, 20, 40, 1)):
+        check(*sh[:5], k=sh[5], seed=21, products=3)
+    for sh in ((8, 64, 64, 256, 256, 3), (8, 128, 128, 128, 128, 3), (8, 8, 32, 256, 256, 7), (8, 64, 32, 256, 256, 7)):
+        check(*sh[:5], k=sh[5], seed=22, timing=True, products=3)
+    sys.exit(0)
 if "big" in sys.argv:   # the profiled case (tools/gpu_prof_wgrad.sh): the dominant layer of the training step
     check(8, 64, 64, 256, 256, seed=4, timing=True)
     sys.exit(0)
