@@ -256,7 +256,7 @@ def gpu_eager_training_baseline(dev, batch=8, size=256, iters=3):
     return out
 
 
-def training_leg(dev, world, steps, warmup, batch=8, size=256, graph=False):
+def training_leg(dev, world, steps, warmup, batch=8, size=256, graph=False, amp=None):
     """BASELINE config 4: one training step of reference tools/train.py:125-159 (enable_amp False branch) - forward, rd_loss
     (2048 * MSE + bpp_res + bpp_mv), backward, clip_grad_norm_(2), Adam step, aux_loss backward, aux Adam step - on a
     Vimeo-shaped synthetic batch: `batch` samples of 256x256 with 4 references each PER GPU (the reference splits a global
@@ -287,7 +287,7 @@ def training_leg(dev, world, steps, warmup, batch=8, size=256, graph=False):
     losses = []
 
     def step():
-        out = model(x, refs, ENABLE_AMP)   # cfg/train.yaml `amp: True`
+        out = model(x, refs, ENABLE_AMP if amp is None else amp)   # cfg/train.yaml `amp: True`
         mse = torch.nn.MSELoss()(out[0], x)
         loss = 2048 * mse + out[1].mean() + out[2].mean()
         aux = out[3] + out[4]
@@ -360,6 +360,7 @@ def main():
     ap.add_argument("--workload", default="predict", choices=["predict", "train"],
                     help="predict: the headline P-frame coding benchmark; train: BASELINE config 4 (training step) on its own")
     ap.add_argument("--no-train-leg", action="store_true")
+    ap.add_argument("--train-exact", action="store_true", help="--workload train: enabled_amp=False (fp32-class weight gradients)")
     ap.add_argument("--train-graph", action="store_true", help="--workload train: capture the whole step in a CUDA graph and replay it (a measurement of the GPU-bound step: replays reuse the captured noise seed and weight scalings)")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
@@ -386,7 +387,7 @@ def main():
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))   # a hang must fail fast
     if args.workload == "train":
-        rec = training_leg(dev, world, max(1, min(args.steps, 8)), max(args.warmup, 3), graph=args.train_graph and world == 1)
+        rec = training_leg(dev, world, max(1, min(args.steps, 8)), max(args.warmup, 3), graph=args.train_graph and world == 1, amp=False if args.train_exact else None)
         if rank == 0 and world == 1 and not args.no_eager_baseline:
             torch.cuda.empty_cache()
             rec["gpu_eager_baseline"] = gpu_eager_training_baseline(dev)
@@ -637,6 +638,11 @@ def main():
                     train["cuda_graph_replay"] = {k: g[k] for k in ("ms_per_step", "samples_per_s", "steps", "warmup", "peak_mem_gb")}
                 except Exception as e:
                     train["cuda_graph_replay"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
+                try:   # enabled_amp=False: fp32-class arithmetic everywhere (three-product weight gradients)
+                    train["exact_precision_ms_per_step"] = training_leg(dev, 1, 4, 3, amp=False)["ms_per_step"]
+                except Exception as e:
+                    train["exact_precision_ms_per_step"] = f"{type(e).__name__}: {e}"[:300]
                 torch.cuda.empty_cache()
             if not args.no_eager_baseline and "error" not in train:
                 train["gpu_eager_baseline"] = gpu_eager_training_baseline(dev)

@@ -38,7 +38,6 @@ namespace wgtc {
 using namespace tc;
 
 constexpr int BW = 32;
-constexpr int NSTAGE = 2;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 512;
 
@@ -54,6 +53,7 @@ struct Cfg {
   static constexpr int X_BYTES = XROWS * G * BLK_X, G_BYTES = R * NBG * BLK_G;
   static constexpr int TILE = X_BYTES + G_BYTES;                      // what the bulk copies bring
   static constexpr int STAGE = (PR == 3 ? 2 : 1) * TILE;              // PR == 3: + the lo parts of both patches, same layout
+  static constexpr int NSTAGE = (PR == 3 && KS == 7 && G == 2) ? 1 : 2;   // (two such stages of the 64-channel 7x7 patch do not fit)
   static constexpr int KXC = KS < TMEM_COLS / (NG * NB) ? KS : TMEM_COLS / (NG * NB);   // kernel columns per CTA
   static constexpr int NKX = (KS + KXC - 1) / KXC;
   static constexpr int SMEM = NSTAGE * STAGE + 1024 /* alignment slack */ + 128 /* barriers, TMEM slot */ + 512 /* bias exchange */;
@@ -110,9 +110,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Args a, cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bars = base + NSTAGE * C::STAGE;            // full[2], empty[2], acc, lo[2]
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(gen + NSTAGE * C::STAGE + 64);
-  float* const bias_x = reinterpret_cast<float*>(gen + NSTAGE * C::STAGE + 128);   // [128]
+  const uint32_t bars = base + C::NSTAGE * C::STAGE;            // full[2], empty[2], acc, lo[2]
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(gen + C::NSTAGE * C::STAGE + 64);
+  float* const bias_x = reinterpret_cast<float*>(gen + C::NSTAGE * C::STAGE + 128);   // [128]
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 16u + 8u * s; };
   const uint32_t acc_bar = bars + 32u;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Args a, cons
   const int kx0 = kxs * C::KXC;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 5); mbar_init(lo_bar(i), 4); }
+    for (int i = 0; i < C::NSTAGE; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 5); mbar_init(lo_bar(i), 4); }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Args a, cons
 #pragma unroll
           for (int grp = 0; grp < C::NBG; ++grp)
             tma4(dst + C::X_BYTES + (row * C::NBG + grp) * C::BLK_G, &maps.g, co_t * NB + grp * 32, tx * BW, ty * R + row, n, full(st));
-        if (++st == NSTAGE) { st = 0; ph ^= 1; }
+        if (++st == C::NSTAGE) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Args a, cons
       }
       first = 0;
       __syncwarp();
-      if (++st == NSTAGE) { st = 0; ph ^= 1; }
+      if (++st == C::NSTAGE) { st = 0; ph ^= 1; }
     }
     if (elect_one()) tc_commit(acc_bar);
     __syncwarp();
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Args a, cons
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty(st));
-      if (++st == NSTAGE) { st = 0; ph ^= 1; }
+      if (++st == C::NSTAGE) { st = 0; ph ^= 1; }
     }
     if (do_bias) {
       bias_x[et] = bsum;
@@ -333,7 +333,7 @@ static Plan plan(int N, int H, int W, int cin, int cout, int k, int products) {
   // rows per item: the three-product mode keeps a second copy of both patches (their lo parts) in shared memory
   p.R = products == 3 ? 2 : ((k == 7 && p.G == 2) ? 2 : 4);
   if (k == 3) { p.id = 1; p.nkx = 1; }
-  else if (k == 7 && !(p.G == 2 && p.NB == 64) && !(products == 3 && p.G == 2)) { p.id = 2; p.nkx = (p.G == 1 && p.NB == 32) ? 1 : 2; }
+  else if (k == 7 && !(p.G == 2 && p.NB == 64)) { p.id = 2; p.nkx = (p.G == 1 && p.NB == 32) ? 1 : 2; }
   else if (k == 1 && p.G == 2 && p.NB == 64) { p.id = 3; p.nkx = 1; }
   else return p;
   p.ci_tiles = cdiv(cin, 32 * p.G);
@@ -436,6 +436,7 @@ int wgrad_tc_launch(const float* x, int x_ld, const float* g, int g_ld, int N, i
   TDVC_WG(3, 1, 32, 2, 3)
   TDVC_WG(7, 1, 32, 2, 3)
   TDVC_WG(7, 1, 64, 2, 3)
+  TDVC_WG(7, 2, 32, 2, 3)
   TDVC_WG(1, 2, 64, 2, 3)
 #undef TDVC_WG
   set_error("wgrad_tc: no kernel for k=%d cin=%d cout=%d products=%d", k, cin, cout, products);

@@ -1,7 +1,7 @@
 """Convolution backward slice of the training step (the reference takes these gradients from cuDNN through
 autograd, tools/train.py:125-159): `tdvc_b200.ops.conv2d` against torch's own float64 convolution and its autograd on the same
 GPU.  grad_input runs on the forward kernels (tcgen05 hi/lo split) from the transposed, flipped weight; grad_weight / grad_bias
-on the deterministic fp32 `tdvc_conv2d_wgrad`."""
+on the deterministic fp32-class `tdvc_conv2d_wgrad` (three TF32 products: tcgen05 for the stride-1 layers, warp-level MMAs else)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -15,6 +15,7 @@ CASES = [
     (1, 64, 128, 1, 2, 64, 96, None),           # ... .skip
     (2, 3, 64, 3, 1, 48, 40, "leaky_relu"),     # image-input layer (3 channels, stored as 4)
     (1, 8, 32, 7, 1, 32, 64, "relu"),           # SPyNet basic module
+    (1, 64, 32, 7, 1, 20, 40, "relu"),          # ... its 64-channel layer (single-stage three-product weight gradient)
     (1, 128, 256, 5, 1, 24, 40, None),          # context model size
     (1, 426, 341, 1, 1, 16, 24, "leaky_relu"),  # entropy_parameters[2]: channel counts that are no multiple of 4
     (1, 64, 3, 3, 1, 32, 32, "clamp01"),        # image head
