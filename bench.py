@@ -302,6 +302,7 @@ def training_leg(dev, world, steps, warmup, batch=8, size=256, graph=False, amp=
         losses.append(loss.detach())
 
     torch.cuda.reset_peak_memory_stats(dev)
+    mem0 = torch.cuda.memory_allocated(dev)     # what earlier legs of the same process still hold (graphs, caches) is not this leg's
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
@@ -336,7 +337,7 @@ def training_leg(dev, world, steps, warmup, batch=8, size=256, graph=False, amp=
     ms = float(ms)
     return {"ms_per_step": ms, "samples_per_s": batch * world / (ms / 1e3), "batch_per_gpu": batch, "size": size, "n_gpus": world,
             "steps": steps, "warmup": warmup, "cuda_graph": bool(graph), "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
-            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+            "peak_mem_gb": (torch.cuda.max_memory_allocated(dev) - mem0) / 2 ** 30,
             "what": "forward + rd_loss backward + clip + Adam + aux step (reference tools/train.py:125-159); convolutions, GDN, DCN "
                     "and entropy models on tdvc_b200 kernels, torch autograd as the tape with torch glue operators between "
                     "them (DESIGN.md section 7)"}
