@@ -63,6 +63,12 @@ def check(N, C, O, H, W, k=3, seed=0, timing=False, products=1):
     print(msg, flush=True)
 
 
+if "small" in sys.argv:   # every kernel instantiation once on a small shape (what a compute-sanitizer run walks)
+    for pr in (1, 3):
+        for sh in ((1, 64, 64, 6, 40, 3), (1, 3, 64, 5, 33, 3), (1, 64, 3, 5, 33, 3), (1, 24, 20, 5, 33, 3), (1, 8, 32, 9, 40, 7),
+                   (1, 32, 64, 9, 40, 7), (1, 64, 32, 9, 40, 7), (1, 192, 64, 6, 40, 1)):
+            check(*sh[:5], k=sh[5], seed=31, products=pr)
+    sys.exit(0)
 if "exact" in sys.argv:   # the fp32-class three-product mode
     for sh in ((2, 64, 64, 9, 50, 3), (2, 128, 192, 12, 96, 3), (2, 3, 64, 12, 40, 3), (2, 64, 216, 12, 40, 3), (1, 8, 32, 20, 40, 7),
                (1, 32, 64, 20, 40, 7), (1, 192, 64, 20, 40, 1)):
