@@ -274,7 +274,10 @@ def training_leg(dev, world, steps, warmup, batch=8, size=256, graph=False, amp=
     net = net.to(dev).train()
     model = net
     if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], find_unused_parameters=True)
+        # 76 of the 535 tensors get no gradient (layers the forward never runs): the set is the same every step, so DDP is told
+        # the graph is static instead of searching for it per step; gradients are views into the all-reduce buckets
+        ddp_kw = {"static_graph": True} if os.environ.get("TDVC_BENCH_DDP_DYNAMIC") is None else {"find_unused_parameters": True}
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], gradient_as_bucket_view=True, **ddp_kw)
     params = [p for n, p in net.named_parameters() if not n.endswith(".quantiles")]
     aux_params = [p for n, p in net.named_parameters() if n.endswith(".quantiles")]
     # reference main/utils/utils.py:90-113 (cfg/train.yaml lr); `capturable` keeps the step counters on the device (graph leg)
