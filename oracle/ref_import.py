@@ -45,3 +45,32 @@ def load_reference_pnet():
 
 def reference_video_compressor():
     return load_reference_pnet().VideoCompressor()
+
+
+def load_reference_dataset():
+    """Returns the reference module `main.dataloader.dataset` (reference main/dataloader/dataset.py), imported verbatim, to pin the
+    SAMPLE LISTS of tdvc_b200.data against the reference's own code.  Its imports that are absent here are stubbed: `cv2` and
+    `albumentations` (used only when an item is read), `natsort` (natsorted = sort by the digit runs as numbers) and
+    `main.model.basics` (drags in the unused TensorFlow-era helpers; only `CalcuPSNR` is referenced, at item-read time)."""
+    import re
+    import types
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    for p in (_REPO, _SHIMS, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+    def stub(name, **attrs):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+        return sys.modules[name]
+
+    key = lambda s: [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", str(s))]
+    stub("cv2")
+    stub("albumentations")
+    stub("natsort", natsorted=lambda seq: sorted(seq, key=key))
+    importlib.import_module("main.model")
+    stub("main.model.basics", CalcuPSNR=None)
+    return importlib.import_module("main.dataloader.dataset")

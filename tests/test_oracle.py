@@ -154,3 +154,38 @@ def test_msssim_oracle_vs_reference_function():
                               R.ms_ssim(x, y, data_range=1.0, size_average=False), atol=2e-5, rtol=0)
     x = torch.rand(1, 3, 176, 176)
     assert abs(float(R.ms_ssim(x, x, data_range=1.0)) - 1.0) < 1e-6 and abs(float(O.ms_ssim(x, x, data_range=1.0)) - 1.0) < 1e-6
+
+
+@needs_ref
+def test_dataset_sample_lists_match_reference_code(tmp_path):
+    """tdvc_b200.data lists the same samples as the reference's own loaders, run here from /root/reference (reference
+    main/dataloader/dataset.py: `DataSet.get_vimeo` :210-247, `UVGDataSet.__init__` :16-60, `HEVCDataSet.__init__` :100-166)."""
+    import os
+    from tdvc_b200 import data as D
+    ds_ref = ref_import.load_reference_dataset()
+    # --- vimeo_septuplet tree: <dir>/<clip>/im1..im7.png (directory names chosen so that natural and plain sorting differ)
+    vimeo = tmp_path / "vimeo"
+    for d, clip in (("00010", "0002"), ("00002", "0010"), ("00002", "0009")):
+        os.makedirs(vimeo / d / clip)
+        for i in range(1, 8):
+            open(vimeo / d / clip / f"im{i}.png", "wb").close()
+    want_in, want_ref = ds_ref.DataSet.get_vimeo(None, str(vimeo))
+    got_in, got_ref = D.VimeoDataset.get_vimeo(str(vimeo))
+    assert len(want_in) == 21 and got_in == want_in and got_ref == want_ref
+    # --- evaluation tree: ori_img/<seq>/imNNN.png + compress_img_bpg/<seq>/<qp>/imNNN_<qp>.{png,txt}
+    root, gop, qp = tmp_path / "eval", 3, 27
+    for seq, nfr in (("Seq10_416x240_50", 7), ("Seq2_416x240_30", 6), ("BQSquare_416x240_60", 9)):
+        os.makedirs(root / "ori_img" / seq)
+        os.makedirs(root / "compress_img_bpg" / seq / str(qp))
+        for i in range(nfr):
+            open(root / "ori_img" / seq / f"im{i + 1:03d}.png", "wb").close()
+        for g in range(nfr // gop):
+            stem = root / "compress_img_bpg" / seq / str(qp) / f"im{g * gop + 1:03d}_{qp}"
+            open(str(stem) + ".png", "wb").close()
+            open(str(stem) + ".txt", "w").write(f"{0.25 * (g + 1)}\n")
+    ref_uvg = ds_ref.UVGDataSet(str(root), 2048, gop, testfull=True, isTrain=False)
+    ours = D.GopDataset(str(root), 2048, gop, testfull=True)
+    assert (ours.ref, ours.refbpp, ours.input) == (ref_uvg.ref, ref_uvg.refbpp, ref_uvg.input) and len(ours) == 7
+    ref_hevc = ds_ref.HEVCDataSet(str(root), 64, gop, "D", testfull=True, isTrain=False)
+    ours = D.GopDataset(str(root), 64, gop, testfull=True, hevc_class="D")
+    assert (ours.ref, ours.refbpp, ours.input) == (ref_hevc.ref, ref_hevc.refbpp, ref_hevc.input) and len(ours) == 3
