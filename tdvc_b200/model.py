@@ -1372,6 +1372,12 @@ class VideoCompressor(nn.Module):
         self.cache_features = True     # per-GOP feature caches (results are bit-identical either way)
         self.last_launches = 0
 
+    def load_state_dict(self, *args, **kwargs):
+        # weights replaced wholesale: the training path must not scale their fp16 blocks by maxima remembered from the old ones
+        from tdvc_b200 import ops
+        ops.forget_weight_maxima()
+        return super().load_state_dict(*args, **kwargs)
+
     # the packed weights, plans and the replica link are runtime state: copies and pickles start without them
     def __getstate__(self):
         d = dict(self.__dict__)

@@ -159,6 +159,12 @@ def _weight_max(weight, key):
     return m
 
 
+def forget_weight_maxima():
+    """Drop the one-step-old maxima of `_weight_max`: call it after replacing weights wholesale (VideoCompressor.load_state_dict
+    does) - a maximum remembered from other weights would scale the fp16 blocks of the first step after the swap wrongly."""
+    _WMAX.clear()
+
+
 def _packed(weight, bias, stride, pad, transposed, max_key=None):
     """ConvW (fp32 implicit-GEMM layout + tcgen05 fp16 blocks) of `weight`, or of its transposed, spatially flipped form
     (the dgrad operator), cached on the parameter's identity and version.  Packed by one kernel (tdvc_conv2d_pack_weight):

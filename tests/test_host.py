@@ -302,6 +302,17 @@ def test_vimeo_training_dataset(tmp_path):
     assert xb.shape == (4, 3, 32, 32) and rb.shape == (4, 4, 3, 32, 32)     # forward(input_image, refer_frames) shapes (pnet.py:26)
 
 
+def test_load_state_dict_forgets_remembered_weight_maxima():
+    """The training path scales fp16 weight blocks by max |w| read one optimiser step late (ops._weight_max); swapping the weights
+    wholesale must drop what was remembered."""
+    from tdvc_b200 import ops
+    from tdvc_b200.model import VideoCompressor
+    net = VideoCompressor()
+    ops._WMAX[12345] = ("stale",)
+    net.load_state_dict(net.state_dict(), strict=True)
+    assert not ops._WMAX
+
+
 def test_shared_library_has_no_libcuda_dependency():
     """The library must load on a host without a driver: the driver entry point it needs is resolved at run time."""
     import subprocess
